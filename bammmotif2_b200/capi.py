@@ -1,0 +1,298 @@
+"""ctypes binding of the C ABI in include/bamm_b200.h (libbamm_b200.so, built in-tree by build.py).
+
+This is plumbing for the tests and bench.py; the drop-in host side of the product is the C++ mirror of the
+reference classes in bammmotif2_b200/host/. There is no fallback: if the library is missing the import fails,
+and every compute call fails without a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbamm_b200.so")
+
+_u8p, _u32p, _u64p, _f32p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_float))
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every entry point declared in include/bamm_b200.h
+SIGNATURES = {
+    "bamm_version": (C.c_int, []),
+    "bamm_last_error": (C.c_char_p, []),
+    "bamm_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "bamm_set_device": (C.c_int, [C.c_int]),
+    "bamm_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _u64p]),
+    "bamm_seqset_create": (C.c_int, [_u8p, _u64p, C.c_uint64, C.c_int, _u64p, _u64p, C.c_uint64, C.POINTER(_vp)]),
+    "bamm_seqset_index": (C.c_int, [_vp, C.c_int]),
+    "bamm_seqset_get_index": (C.c_int, [_vp, C.c_int, _u32p]),
+    "bamm_seqset_info": (C.c_int, [_vp, _u64p, _u64p, C.POINTER(C.c_int)]),
+    "bamm_seqset_count_kmers": (C.c_int, [_vp, C.c_int, _u64p]),
+    "bamm_seqset_destroy": (None, [_vp]),
+    "bamm_em_create": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "bamm_em_set_model": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_float]),
+    "bamm_em_estep": (C.c_int, [_vp, _f32p]),
+    "bamm_em_mstep": (C.c_int, [_vp]),
+    "bamm_em_optimize_q": (C.c_int, [_vp, _f32p]),
+    "bamm_em_optimize": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int), _f32p, _f32p, _f32p]),
+    "bamm_em_iterate": (C.c_int, [_vp, C.c_int, _f32p, _f32p]),
+    "bamm_em_get_model": (C.c_int, [_vp, _f32p]),
+    "bamm_em_get_counts": (C.c_int, [_vp, _f32p]),
+    "bamm_em_get_s": (C.c_int, [_vp, _f32p]),
+    "bamm_em_get_q": (C.c_int, [_vp, _f32p]),
+    "bamm_em_get_r": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _f32p]),
+    "bamm_em_r_size": (C.c_uint64, [_vp]),
+    "bamm_em_last_timing": (C.c_int, [_vp, _f32p, _f32p]),
+    "bamm_em_loop_timing": (C.c_int, [_vp, C.POINTER(C.c_int), _f32p, _f32p, _f32p, _f32p]),
+    "bamm_em_set_exchange_buffer": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "bamm_em_destroy": (None, [_vp]),
+    "bamm_em_exchange_buffer": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),
+    "bamm_em_set_global_nseq": (C.c_int, [_vp, C.c_uint64]),
+    "bamm_em_estep_local": (C.c_int, [_vp]),
+    "bamm_em_mstep_local": (C.c_int, [_vp]),
+    "bamm_em_finish_iteration": (C.c_int, [_vp, C.c_int, _f32p, _f32p]),
+    "bamm_em_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "bamm_score_logodds": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _u64p, _f32p]),
+}
+
+_lib = None
+
+
+class BammError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libbamm_b200.so and declares every prototype. Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BammError("libbamm_b200.so is missing: run `python -m bammmotif2_b200.build` (there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise BammError("bamm error %d: %s" % (rc, load().bamm_last_error().decode()))
+
+
+def _ptr(a, ptype):
+    return a.ctypes.data_as(ptype) if a is not None else None
+
+
+def model_size(A, K, W):
+    return sum(A ** (k + 1) * W for k in range(K + 1))
+
+
+def bg_size(A, K):
+    return sum(A ** (k + 1) for k in range(K + 1))
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = load().bamm_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def kmer_patches(codes, kmer):
+    """Positions whose hash depends on rand() draws for a code-0 base (Sequence.cpp:38): every position within
+    10 after a 0 code (k-mer hashes span 11 bases) — of the same sequence or not does not matter, a superset is
+    fine because the patch carries the reference's own hash. Returns (positions, kmer values)."""
+    zero = np.flatnonzero(codes == 0)
+    if len(zero) == 0:
+        return np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+    pos = (zero[:, None] + np.arange(11)[None, :]).ravel()
+    pos = np.unique(pos[pos < len(codes)]).astype(np.uint64)
+    return pos, np.ascontiguousarray(kmer[pos.astype(np.int64)], np.uint64)
+
+
+class SeqSet:
+    """Device-resident sequence set (bamm_seqset)."""
+
+    def __init__(self, codes, offsets, A, patch_pos=None, patch_kmer=None):
+        lib = load()
+        self.codes = np.ascontiguousarray(codes, np.uint8)
+        self.offsets = np.ascontiguousarray(offsets, np.uint64)
+        self.A = int(A)
+        pp = np.ascontiguousarray(patch_pos if patch_pos is not None else np.zeros(0), np.uint64)
+        pk = np.ascontiguousarray(patch_kmer if patch_kmer is not None else np.zeros(0), np.uint64)
+        h = _vp()
+        _check(lib.bamm_seqset_create(_ptr(self.codes, _u8p), _ptr(self.offsets, _u64p), len(self.offsets) - 1, self.A,
+                                      _ptr(pp, _u64p), _ptr(pk, _u64p), len(pp), C.byref(h)))
+        self.h = h
+        self.nseq = len(self.offsets) - 1
+        self.npos = int(self.offsets[-1])
+
+    def index(self, K):
+        _check(load().bamm_seqset_index(self.h, K))
+
+    def get_index(self, K):
+        out = np.zeros(self.npos, np.uint32)
+        _check(load().bamm_seqset_get_index(self.h, K, _ptr(out, _u32p)))
+        return out
+
+    def count_kmers(self, K):
+        out = np.zeros(bg_size(self.A, K), np.uint64)
+        _check(load().bamm_seqset_count_kmers(self.h, K, _ptr(out, _u64p)))
+        return out
+
+    def score(self, W, K, K_bg_model, v_all, vbg_all, subset=None, want_mops=True):
+        """ScoreSeqSet::calcLogOdds. Returns (mops|None, zoops, z)."""
+        sub = np.ascontiguousarray(subset, np.uint64) if subset is not None else None
+        nsub = len(sub) if sub is not None else self.nseq
+        ids = sub.astype(np.int64) if sub is not None else np.arange(self.nseq)
+        L = (self.offsets[1:] - self.offsets[:-1]).astype(np.int64)[ids]
+        zoops = np.zeros(nsub, np.float32)
+        z = np.zeros(nsub, np.uint64)
+        mops = np.zeros(int((L - W + 1).sum()), np.float32) if want_mops else None
+        v = np.ascontiguousarray(v_all, np.float32)
+        vb = np.ascontiguousarray(vbg_all, np.float32)
+        _check(load().bamm_score_logodds(self.h, _ptr(sub, _u64p), nsub, W, K, K_bg_model, _ptr(v, _f32p), _ptr(vb, _f32p),
+                                         _ptr(zoops, _f32p), _ptr(z, _u64p), _ptr(mops, _f32p)))
+        return mops, zoops, z
+
+    def close(self):
+        if self.h:
+            load().bamm_seqset_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EM:
+    """One EM problem on the device (bamm_em); mirrors the reference's EM class (src/refinement/EM.h:18-36)."""
+
+    def __init__(self, seqset, W, K, K_bg_model, subset=None):
+        self.seqset = seqset
+        self.W, self.K, self.K_bg_model, self.A = W, K, K_bg_model, seqset.A
+        sub = np.ascontiguousarray(subset, np.uint64) if subset is not None else None
+        self.nsub = len(sub) if sub is not None else seqset.nseq
+        h = _vp()
+        _check(load().bamm_em_create(seqset.h, _ptr(sub, _u64p), self.nsub, W, K, K_bg_model, C.byref(h)))
+        self.h = h
+        self.msize = model_size(self.A, K, W)
+
+    def set_model(self, v_all, vbg_all, alpha, q):
+        v = np.ascontiguousarray(v_all, np.float32)
+        vb = np.ascontiguousarray(vbg_all, np.float32)
+        al = np.ascontiguousarray(alpha, np.float32).ravel()
+        assert len(v) == self.msize and len(vb) == bg_size(self.A, self.K_bg_model) and len(al) == (self.K + 1) * self.W
+        _check(load().bamm_em_set_model(self.h, _ptr(v, _f32p), _ptr(vb, _f32p), _ptr(al, _f32p), C.c_float(q)))
+
+    def estep(self):
+        llh = C.c_float(0)
+        _check(load().bamm_em_estep(self.h, C.byref(llh)))
+        return llh.value
+
+    def mstep(self):
+        _check(load().bamm_em_mstep(self.h))
+
+    def optimize_q(self):
+        q = C.c_float(0)
+        _check(load().bamm_em_optimize_q(self.h, C.byref(q)))
+        return q.value
+
+    def optimize(self, optimize_q=False, epsilon=0.01, max_iter=1000):
+        it = C.c_int(0)
+        llh = np.zeros(max_iter, np.float32)
+        vd = np.zeros(max_iter, np.float32)
+        qt = np.zeros(max_iter, np.float32)
+        _check(load().bamm_em_optimize(self.h, int(optimize_q), C.c_float(epsilon), max_iter, C.byref(it),
+                                       _ptr(llh, _f32p), _ptr(vd, _f32p), _ptr(qt, _f32p)))
+        n = it.value
+        return dict(iterations=n, llh=llh[:n], vdiff=vd[:n], qtrace=qt[:n], v=self.model(), q=self.q())
+
+    def iterate(self, n_iter):
+        llh, vd = C.c_float(0), C.c_float(0)
+        _check(load().bamm_em_iterate(self.h, n_iter, C.byref(llh), C.byref(vd)))
+        return llh.value, vd.value
+
+    def model(self):
+        out = np.zeros(self.msize, np.float32)
+        _check(load().bamm_em_get_model(self.h, _ptr(out, _f32p)))
+        return out
+
+    def counts(self):
+        out = np.zeros(self.msize, np.float32)
+        _check(load().bamm_em_get_counts(self.h, _ptr(out, _f32p)))
+        return out
+
+    def s(self):
+        out = np.zeros(self.A ** (self.K + 1) * self.W, np.float32)
+        _check(load().bamm_em_get_s(self.h, _ptr(out, _f32p)))
+        return out
+
+    def q(self):
+        q = C.c_float(0)
+        _check(load().bamm_em_get_q(self.h, C.byref(q)))
+        return q.value
+
+    def r(self, first=0, count=None):
+        count = self.nsub - first if count is None else count
+        total = int(load().bamm_em_r_size(self.h))
+        out = np.zeros(total, np.float32)
+        _check(load().bamm_em_get_r(self.h, first, count, _ptr(out, _f32p)))
+        return out
+
+    def timing(self):
+        e, m = C.c_float(0), C.c_float(0)
+        _check(load().bamm_em_last_timing(self.h, C.byref(e), C.byref(m)))
+        return e.value, m.value
+
+    def loop_timing(self):
+        """(iterations, estep_ms, maccum_ms, update_ms, total_ms) of the last iterate() call, CUDA events on the EM stream."""
+        it = C.c_int(0)
+        e, m, up, t = C.c_float(0), C.c_float(0), C.c_float(0), C.c_float(0)
+        _check(load().bamm_em_loop_timing(self.h, C.byref(it), C.byref(e), C.byref(m), C.byref(up), C.byref(t)))
+        return it.value, e.value, m.value, up.value, t.value
+
+    def set_exchange_buffer(self, dev_ptr, words):
+        _check(load().bamm_em_set_exchange_buffer(self.h, _vp(dev_ptr), words))
+
+    # multi-GPU halves
+    def exchange_buffer(self):
+        p, w = _vp(), C.c_uint64(0)
+        _check(load().bamm_em_exchange_buffer(self.h, C.byref(p), C.byref(w)))
+        return p.value, w.value
+
+    def stream(self):
+        p = _vp()
+        _check(load().bamm_em_stream(self.h, C.byref(p)))
+        return p.value
+
+    def set_global_nseq(self, n):
+        _check(load().bamm_em_set_global_nseq(self.h, n))
+
+    def estep_local(self):
+        _check(load().bamm_em_estep_local(self.h))
+
+    def mstep_local(self):
+        _check(load().bamm_em_mstep_local(self.h))
+
+    def finish_iteration(self, optimize_q=False, sync=True):
+        if not sync and not optimize_q:
+            _check(load().bamm_em_finish_iteration(self.h, 0, None, None))
+            return None
+        llh, vd = C.c_float(0), C.c_float(0)
+        _check(load().bamm_em_finish_iteration(self.h, int(optimize_q), C.byref(llh), C.byref(vd)))
+        return llh.value, vd.value
+
+    def close(self):
+        if self.h:
+            load().bamm_em_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

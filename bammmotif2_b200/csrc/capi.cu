@@ -1,0 +1,730 @@
+// capi.cu — implementation of include/bamm_b200.h on top of kernels.cuh. Host plumbing only: device memory,
+// one CUDA stream per EM object, launches, scalar read-back. No CPU fallback: every compute entry point needs a device.
+#include "../../include/bamm_b200.h"
+#include "kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace bamm;
+
+// ------------------------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(e_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define REQUIRE(cond, ...) do { if (!(cond)) return fail(BAMM_E_INVALID, __VA_ARGS__); } while (0)
+
+static uint64_t ipow_u64(uint64_t b, int e) { uint64_t r = 1; while (e-- > 0) r *= b; return r; }
+
+// ------------------------------------------------------------------------------------------- objects
+struct IndexArray { void* d = nullptr; int bytes = 2; uint64_t Yn = 0; };
+
+struct bamm_seqset {
+    int device = 0;
+    int A = 4;
+    uint64_t nseq = 0, npos = 0, npatch = 0, maxL = 0, minL = 0;
+    uint8_t* d_codes = nullptr;
+    uint64_t* d_off = nullptr;
+    uint64_t* d_ppos = nullptr;
+    uint64_t* d_pkmer = nullptr;
+    std::vector<uint64_t> h_off;
+    std::map<int, IndexArray> index;   // per order K
+    std::mutex mu;
+    int sm_count = 148;
+};
+
+struct bamm_em {
+    bamm_seqset* ss = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> loop_ev;       // 4 per iteration of the last bamm_em_iterate call: E | M accumulate | reduce+update
+    int loop_iters = 0;
+    bool own_xbuf = true;
+    int W = 0, K = 0, K_bg_model = 0, K_bg = 0, A = 4;
+    uint32_t Yn = 0;            // A^(K+1)
+    uint32_t nbin = 0;          // W * Yn
+    uint64_t nsub = 0, rsize = 0, nseq_global = 0;
+    uint64_t model_size = 0, bg_size = 0;
+    ModelDims dims;
+    bool smem_tables = true;    // tables fit in shared memory
+    int grid_e = 0, grid_m = 0, block = 512;
+    size_t smem_e = 0, smem_m = 0;
+    // device
+    uint32_t* d_seq_ids = nullptr;
+    uint64_t* d_r_off = nullptr;
+    float* d_r = nullptr;
+    float* d_s = nullptr;         // [j][y]
+    float* d_v = nullptr;         // all orders
+    float* d_vK_prev = nullptr;
+    float* d_n = nullptr;         // all orders (float, reference layout)
+    float* d_vbg = nullptr;
+    float* d_alpha = nullptr;
+    unsigned long long* d_part = nullptr;   // per-CTA partial count tables
+    unsigned long long* d_xbuf = nullptr;   // [nbin] counts + [2] scalars  (the multi-GPU exchange buffer)
+    float* d_vdiff = nullptr;
+    // host (pinned)
+    unsigned long long* h_scal = nullptr;   // 2 scalars
+    float* h_vdiff = nullptr;
+    std::vector<uint64_t> h_r_off;
+    float q = 0.3f;
+    float llh = 0.0f;
+    bool model_set = false, s_valid = false, r_valid = false;
+    float t_e = 0, t_m = 0;
+};
+
+// ------------------------------------------------------------------------------------------- library / device
+extern "C" int bamm_version(void) { return 10000 * 0 + 100 * 1 + 0; }
+extern "C" const char* bamm_last_error(void) { return g_err; }
+extern "C" int bamm_device_count(int* count) {
+    REQUIRE(count, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return fail(BAMM_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    return BAMM_OK;
+}
+extern "C" int bamm_set_device(int device) { CU(cudaSetDevice(device)); return BAMM_OK; }
+extern "C" int bamm_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem) {
+    int dev; CU(cudaGetDevice(&dev));
+    cudaDeviceProp p; CU(cudaGetDeviceProperties(&p, dev));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = (uint64_t)p.totalGlobalMem;
+    return BAMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------- seqset
+extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets, uint64_t nseq, int A,
+                                  const uint64_t* patch_pos, const uint64_t* patch_kmer, uint64_t npatch,
+                                  bamm_seqset** out) {
+    REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    REQUIRE(codes && offsets, "codes/offsets is NULL");
+    REQUIRE(A >= 2 && A <= 6, "alphabet size %d not in [2,6]", A);
+    REQUIRE(offsets[0] == 0, "offsets[0] must be 0");
+    REQUIRE(nseq < (1ull << 32), "too many sequences");
+    REQUIRE(npatch == 0 || (patch_pos && patch_kmer), "patch arrays are NULL");
+    uint64_t maxL = 0, minL = ~0ull;
+    for (uint64_t n = 0; n < nseq; n++) {
+        REQUIRE(offsets[n + 1] >= offsets[n], "offsets not monotone at %llu", (unsigned long long)n);
+        uint64_t L = offsets[n + 1] - offsets[n];
+        if (L > maxL) maxL = L;
+        if (L < minL) minL = L;
+    }
+    const uint64_t npos = offsets[nseq];
+    for (uint64_t i = 0; i < npatch; i++) {
+        REQUIRE(patch_pos[i] < npos, "patch position out of range");
+        REQUIRE(i == 0 || patch_pos[i] > patch_pos[i - 1], "patch positions must be strictly increasing");
+    }
+    bamm_seqset* s = new (std::nothrow) bamm_seqset();
+    if (!s) return fail(BAMM_E_NOMEM, "host allocation failed");
+    int dev; cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { delete s; return fail(BAMM_E_CUDA, "no CUDA device: %s", cudaGetErrorString(e)); }
+    s->device = dev; s->A = A; s->nseq = nseq; s->npos = npos; s->npatch = npatch; s->maxL = maxL; s->minL = nseq ? minL : 0;
+    s->h_off.assign(offsets, offsets + nseq + 1);
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
+#define CUS(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { bamm_seqset_destroy(s); \
+    return fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); } } while (0)
+    CUS(cudaMalloc(&s->d_codes, npos ? npos : 1));
+    CUS(cudaMalloc(&s->d_off, (nseq + 1) * sizeof(uint64_t)));
+    CUS(cudaMemcpy(s->d_codes, codes, npos, cudaMemcpyHostToDevice));
+    CUS(cudaMemcpy(s->d_off, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (npatch) {
+        CUS(cudaMalloc(&s->d_ppos, npatch * sizeof(uint64_t)));
+        CUS(cudaMalloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
+        CUS(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CUS(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+#undef CUS
+    *out = s;
+    return BAMM_OK;
+}
+
+extern "C" void bamm_seqset_destroy(bamm_seqset* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (auto& kv : s->index) cudaFree(kv.second.d);
+    cudaFree(s->d_codes); cudaFree(s->d_off); cudaFree(s->d_ppos); cudaFree(s->d_pkmer);
+    delete s;
+}
+
+extern "C" int bamm_seqset_info(const bamm_seqset* s, uint64_t* nseq, uint64_t* npos, int* A) {
+    REQUIRE(s, "seqset is NULL");
+    if (nseq) *nseq = s->nseq;
+    if (npos) *npos = s->npos;
+    if (A) *A = s->A;
+    return BAMM_OK;
+}
+
+static int seqset_index_locked(bamm_seqset* s, int K, IndexArray** out) {
+    REQUIRE(K >= 0 && K <= 10, "order K=%d not in [0,10]", K);   // the reference hashes at most 11-mers (Sequence.cpp:36)
+    auto it = s->index.find(K);
+    if (it != s->index.end()) { if (out) *out = &it->second; return BAMM_OK; }
+    const uint64_t Yn = ipow_u64((uint64_t)s->A, K + 1);
+    REQUIRE(Yn <= (1ull << 31), "A^(K+1) too large");
+    IndexArray ia; ia.Yn = Yn; ia.bytes = (Yn <= 65536) ? 2 : 4;
+    CU(cudaSetDevice(s->device));
+    CU(cudaMalloc(&ia.d, (s->npos ? s->npos : 1) * (uint64_t)ia.bytes));
+    const int block = 256;
+    const int grid = s->sm_count * 8;
+    if (s->nseq) {
+        if (ia.bytes == 2) k_build_index<uint16_t><<<grid, block>>>(s->d_codes, s->d_off, s->nseq, s->A, K, Yn, (uint16_t*)ia.d);
+        else               k_build_index<uint32_t><<<grid, block>>>(s->d_codes, s->d_off, s->nseq, s->A, K, Yn, (uint32_t*)ia.d);
+    }
+    if (s->npatch) {
+        const int pg = (int)((s->npatch + 255) / 256);
+        if (ia.bytes == 2) k_patch_index<uint16_t><<<pg, 256>>>(s->d_ppos, s->d_pkmer, s->npatch, Yn, (uint16_t*)ia.d);
+        else               k_patch_index<uint32_t><<<pg, 256>>>(s->d_ppos, s->d_pkmer, s->npatch, Yn, (uint32_t*)ia.d);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(ia.d); return fail(BAMM_E_CUDA, "index build failed: %s", cudaGetErrorString(e)); }
+    auto ins = s->index.emplace(K, ia);
+    if (out) *out = &ins.first->second;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_seqset_index(bamm_seqset* s, int K) {
+    REQUIRE(s, "seqset is NULL");
+    std::lock_guard<std::mutex> g(s->mu);
+    return seqset_index_locked(s, K, nullptr);
+}
+
+extern "C" int bamm_seqset_get_index(bamm_seqset* s, int K, uint32_t* out) {
+    REQUIRE(s && out, "NULL argument");
+    IndexArray* ia;
+    { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
+    CU(cudaSetDevice(s->device));
+    if (ia->bytes == 4) { CU(cudaMemcpy(out, ia->d, s->npos * 4, cudaMemcpyDeviceToHost)); return BAMM_OK; }
+    std::vector<uint16_t> tmp(s->npos);
+    CU(cudaMemcpy(tmp.data(), ia->d, s->npos * 2, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < s->npos; i++) out[i] = tmp[i];
+    return BAMM_OK;
+}
+
+extern "C" int bamm_seqset_count_kmers(bamm_seqset* s, int K, uint64_t* n_all) {
+    REQUIRE(s && n_all, "NULL argument");
+    IndexArray* ia;
+    { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
+    CU(cudaSetDevice(s->device));
+    unsigned long long* d_cnt;
+    CU(cudaMalloc(&d_cnt, ia->Yn * 8));
+    CU(cudaMemset(d_cnt, 0, ia->Yn * 8));
+    if (s->npos) {
+        if (ia->bytes == 2) k_count_kmers<uint16_t><<<s->sm_count * 8, 256>>>((const uint16_t*)ia->d, s->npos, d_cnt);
+        else                k_count_kmers<uint32_t><<<s->sm_count * 8, 256>>>((const uint32_t*)ia->d, s->npos, d_cnt);
+    }
+    std::vector<uint64_t> top(ia->Yn);
+    cudaError_t e = cudaMemcpy(top.data(), d_cnt, ia->Yn * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_cnt);
+    if (e != cudaSuccess) return fail(BAMM_E_CUDA, "k-mer count failed: %s", cudaGetErrorString(e));
+    // every position contributes once to every order and y_{k-1} = y_k % A^k, so lower orders are folds
+    std::vector<uint64_t> off(K + 2, 0);
+    for (int k = 0; k <= K; k++) off[k + 1] = off[k] + ipow_u64(s->A, k + 1);
+    memset(n_all, 0, off[K + 1] * sizeof(uint64_t));
+    memcpy(n_all + off[K], top.data(), ia->Yn * 8);
+    for (int k = K; k > 0; k--) {
+        const uint64_t Yk = ipow_u64(s->A, k), Yk1 = Yk * s->A;
+        for (uint64_t y = 0; y < Yk1; y++) n_all[off[k - 1] + y % Yk] += n_all[off[k] + y];
+    }
+    return BAMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------- EM
+static void fill_dims(ModelDims& d, int A, int K, int W, int K_bg) {
+    memset(&d, 0, sizeof(d));
+    d.A = A; d.K = K; d.W = W; d.K_bg = K_bg;
+    uint64_t p = 1;
+    for (int i = 0; i < 16; i++) { d.Y[i] = (uint32_t)(p > 0xffffffffull ? 0xffffffffull : p); p *= A; }
+    uint32_t vo = 0, bo = 0;
+    for (int k = 0; k < 16; k++) {
+        d.voff[k] = vo; d.bgoff[k] = bo;
+        if (k <= K + 1) { vo += d.Y[k + 1 < 16 ? k + 1 : 15] * (uint32_t)W; }
+        if (k <= 12) bo += d.Y[k + 1 < 16 ? k + 1 : 15];
+    }
+}
+
+extern "C" void bamm_em_destroy(bamm_em* em) {
+    if (!em) return;
+    cudaSetDevice(em->device);
+    if (em->stream) cudaStreamSynchronize(em->stream);
+    cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_v);
+    cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
+    if (em->own_xbuf) cudaFree(em->d_xbuf);
+    cudaFree(em->d_vdiff);
+    for (cudaEvent_t e : em->loop_ev) cudaEventDestroy(e);
+    if (em->h_scal) cudaFreeHost(em->h_scal);
+    if (em->h_vdiff) cudaFreeHost(em->h_vdiff);
+    for (int i = 0; i < 4; i++) if (em->ev[i]) cudaEventDestroy(em->ev[i]);
+    if (em->stream) cudaStreamDestroy(em->stream);
+    delete em;
+}
+
+template <typename K> static int max_smem_optin(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
+                              bamm_em** out) {
+    REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    REQUIRE(s, "seqset is NULL");
+    REQUIRE(W >= 1 && W <= 32, "motif width W=%d not in [1,32]", W);
+    REQUIRE(K >= 0 && K <= 10 && K_bg_model >= 0 && K_bg_model <= 10, "order out of range");
+    if (!subset) nsub = s->nseq;
+    REQUIRE(nsub < (1ull << 32), "subset too large");
+    IndexArray* ia;
+    { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
+    REQUIRE(ia->Yn * (uint64_t)W < (1ull << 31), "table too large");
+    bamm_em* em = new (std::nothrow) bamm_em();
+    if (!em) return fail(BAMM_E_NOMEM, "host allocation failed");
+    em->ss = s; em->device = s->device; em->W = W; em->K = K; em->K_bg_model = K_bg_model;
+    em->K_bg = K_bg_model < K ? K_bg_model : K; em->A = s->A;
+    em->Yn = (uint32_t)ia->Yn; em->nbin = em->Yn * (uint32_t)W; em->nsub = nsub; em->nseq_global = nsub;
+    fill_dims(em->dims, s->A, K, W, em->K_bg);
+    em->model_size = em->dims.voff[K + 1];
+    em->bg_size = em->dims.bgoff[K_bg_model + 1];
+    em->h_r_off.resize(nsub + 1);
+    std::vector<uint32_t> ids(nsub);
+    em->h_r_off[0] = 0;
+    for (uint64_t i = 0; i < nsub; i++) {
+        const uint64_t n = subset ? subset[i] : i;
+        if (n >= s->nseq) { delete em; return fail(BAMM_E_INVALID, "subset[%llu]=%llu out of range", (unsigned long long)i, (unsigned long long)n); }
+        const uint64_t L = s->h_off[n + 1] - s->h_off[n];
+        if (L < (uint64_t)W) { delete em; return fail(BAMM_E_INVALID, "sequence %llu is shorter (L=%llu) than the motif (W=%d)", (unsigned long long)n, (unsigned long long)L, W); }
+        ids[i] = (uint32_t)n;
+        em->h_r_off[i + 1] = em->h_r_off[i] + L;
+    }
+    em->rsize = em->h_r_off[nsub];
+#define CUE(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { int code_ = e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA; \
+    fail(code_, "%s failed: %s", #call, cudaGetErrorString(e2_)); bamm_em_destroy(em); return code_; } } while (0)
+    CUE(cudaSetDevice(em->device));
+    CUE(cudaStreamCreateWithFlags(&em->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) CUE(cudaEventCreate(&em->ev[i]));
+    if (subset) {
+        CUE(cudaMalloc(&em->d_seq_ids, (nsub ? nsub : 1) * sizeof(uint32_t)));
+        CUE(cudaMemcpy(em->d_seq_ids, ids.data(), nsub * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    CUE(cudaMalloc(&em->d_r_off, (nsub + 1) * sizeof(uint64_t)));
+    CUE(cudaMemcpy(em->d_r_off, em->h_r_off.data(), (nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CUE(cudaMalloc(&em->d_r, (em->rsize ? em->rsize : 1) * sizeof(float)));
+    CUE(cudaMalloc(&em->d_s, (uint64_t)em->nbin * sizeof(float)));
+    CUE(cudaMalloc(&em->d_v, em->model_size * sizeof(float)));
+    CUE(cudaMalloc(&em->d_vK_prev, (uint64_t)em->nbin * sizeof(float)));
+    CUE(cudaMalloc(&em->d_n, em->model_size * sizeof(float)));
+    CUE(cudaMalloc(&em->d_vbg, em->bg_size * sizeof(float)));
+    CUE(cudaMalloc(&em->d_alpha, (uint64_t)(K + 1) * W * sizeof(float)));
+    CUE(cudaMalloc(&em->d_xbuf, ((uint64_t)em->nbin + 2) * sizeof(unsigned long long)));
+    CUE(cudaMemset(em->d_xbuf, 0, ((uint64_t)em->nbin + 2) * sizeof(unsigned long long)));
+    CUE(cudaMalloc(&em->d_vdiff, sizeof(float)));
+    CUE(cudaMallocHost(&em->h_scal, 2 * sizeof(unsigned long long)));
+    CUE(cudaMallocHost(&em->h_vdiff, sizeof(float)));
+    // launch geometry: persistent grid, one CTA of 512 threads per SM slot
+    const size_t table_bytes = (size_t)em->nbin * sizeof(float);
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, em->device);
+    em->smem_tables = table_bytes <= (size_t)max_optin;
+    const int sms = s->sm_count;
+    if (em->smem_tables) {
+        em->smem_e = table_bytes; em->smem_m = table_bytes;
+        int per_sm = (int)((size_t)(max_optin + 1024) / (table_bytes + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;             // 4 x 512 threads = 2048 = the SM's thread limit
+        em->grid_e = em->grid_m = sms * per_sm;
+        bool ok = true;
+        if (ia->bytes == 2) { ok &= !max_smem_optin(k_estep<uint16_t, true>, table_bytes); ok &= !max_smem_optin(k_mstep<uint16_t, true>, table_bytes); }
+        else                { ok &= !max_smem_optin(k_estep<uint32_t, true>, table_bytes); ok &= !max_smem_optin(k_mstep<uint32_t, true>, table_bytes); }
+        if (!ok) { fail(BAMM_E_CUDA, "cannot opt in to %zu bytes of shared memory", table_bytes); bamm_em_destroy(em); return BAMM_E_CUDA; }
+        CUE(cudaMalloc(&em->d_part, (uint64_t)em->grid_m * em->nbin * sizeof(unsigned long long)));
+    } else {
+        em->smem_e = em->smem_m = 0;
+        em->grid_e = em->grid_m = sms * 4;
+        CUE(cudaMalloc(&em->d_part, (uint64_t)em->nbin * sizeof(unsigned long long)));
+    }
+#undef CUE
+    *out = em;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* vbg_all, const float* alpha, float q) {
+    REQUIRE(em && v_all && vbg_all && alpha, "NULL argument");
+    REQUIRE(q > 0.0f && q < 1.0f, "q=%g not in (0,1)", (double)q);
+    CU(cudaSetDevice(em->device));
+    CU(cudaMemcpyAsync(em->d_v, v_all, em->model_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
+    CU(cudaMemcpyAsync(em->d_vbg, vbg_all, em->bg_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
+    CU(cudaMemcpyAsync(em->d_alpha, alpha, (uint64_t)(em->K + 1) * em->W * sizeof(float), cudaMemcpyHostToDevice, em->stream));
+    k_make_s<<<64, 256, 0, em->stream>>>(em->dims, em->d_v, em->d_vbg, em->d_s, em->d_vK_prev);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(em->stream));
+    em->q = q; em->model_set = true; em->s_valid = true; em->r_valid = false; em->llh = 0.0f;
+    return BAMM_OK;
+}
+
+static SubsetView view_of(const bamm_em* em) {
+    SubsetView sv; sv.seq_off = em->ss->d_off; sv.seq_ids = em->d_seq_ids; sv.r_off = em->d_r_off; sv.nsub = (uint32_t)em->nsub;
+    return sv;
+}
+
+static int launch_estep(bamm_em* em) {
+    IndexArray& ia = em->ss->index[em->K];
+    unsigned long long* scal = em->d_xbuf + em->nbin;
+    CU(cudaMemsetAsync(scal, 0, 2 * sizeof(unsigned long long), em->stream));
+    SubsetView sv = view_of(em);
+    if (em->nsub == 0) return BAMM_OK;
+    if (ia.bytes == 2) {
+        if (em->smem_tables) k_estep<uint16_t, true><<<em->grid_e, em->block, em->smem_e, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+        else                 k_estep<uint16_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+    } else {
+        if (em->smem_tables) k_estep<uint32_t, true><<<em->grid_e, em->block, em->smem_e, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+        else                 k_estep<uint32_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+    }
+    CU(cudaGetLastError());
+    return BAMM_OK;
+}
+
+static int launch_mstep_accumulate(bamm_em* em) {
+    IndexArray& ia = em->ss->index[em->K];
+    SubsetView sv = view_of(em);
+    const uint32_t nparts = em->smem_tables ? (uint32_t)em->grid_m : 1u;
+    CU(cudaMemsetAsync(em->d_part, 0, (uint64_t)nparts * em->nbin * sizeof(unsigned long long), em->stream));
+    if (em->nsub) {
+        if (ia.bytes == 2) {
+            if (em->smem_tables) k_mstep<uint16_t, true><<<em->grid_m, em->block, em->smem_m, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
+            else                 k_mstep<uint16_t, false><<<em->grid_m, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
+        } else {
+            if (em->smem_tables) k_mstep<uint32_t, true><<<em->grid_m, em->block, em->smem_m, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
+            else                 k_mstep<uint32_t, false><<<em->grid_m, em->block, 0, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
+        }
+        CU(cudaGetLastError());
+    }
+    return BAMM_OK;
+}
+
+static int launch_mstep_reduce(bamm_em* em) {
+    const uint32_t nparts = em->smem_tables ? (uint32_t)em->grid_m : 1u;
+    k_reduce_parts<<<(em->nbin + 255) / 256, 256, 0, em->stream>>>(em->d_part, nparts, em->nbin, em->d_xbuf);
+    CU(cudaGetLastError());
+    return BAMM_OK;
+}
+
+static int launch_mstep_local(bamm_em* em) {
+    int rc = launch_mstep_accumulate(em); if (rc) return rc;
+    return launch_mstep_reduce(em);
+}
+
+static int launch_update(bamm_em* em) {
+    k_update_model<<<1, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha, em->d_s, em->d_vdiff);
+    CU(cudaGetLastError());
+    return BAMM_OK;
+}
+
+static int read_scalars(bamm_em* em, bool want_vdiff) {
+    CU(cudaMemcpyAsync(em->h_scal, em->d_xbuf + em->nbin, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, em->stream));
+    if (want_vdiff) CU(cudaMemcpyAsync(em->h_vdiff, em->d_vdiff, sizeof(float), cudaMemcpyDeviceToHost, em->stream));
+    CU(cudaStreamSynchronize(em->stream));
+    em->llh = (float)((double)(long long)em->h_scal[0] * SC_INV_D);
+    return BAMM_OK;
+}
+
+static float q_from_rsum(const bamm_em* em) {     // reference: EM.cpp:515
+    const float N1 = (float)((double)(long long)em->h_scal[1] * SC_INV_D);
+    return ((float)em->nseq_global - N1 + 1.f) / ((float)em->nseq_global + 2.f);
+}
+
+extern "C" int bamm_em_estep_local(bamm_em* em) {
+    REQUIRE(em, "em is NULL");
+    if (!em->model_set) return fail(BAMM_E_STATE, "bamm_em_set_model has not been called");
+    CU(cudaSetDevice(em->device));
+    CU(cudaEventRecord(em->ev[0], em->stream));
+    int rc = launch_estep(em); if (rc) return rc;
+    CU(cudaEventRecord(em->ev[1], em->stream));
+    em->r_valid = true;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_estep(bamm_em* em, float* llh) {
+    int rc = bamm_em_estep_local(em); if (rc) return rc;
+    rc = read_scalars(em, false); if (rc) return rc;
+    if (llh) *llh = em->llh;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_mstep_local(bamm_em* em) {
+    REQUIRE(em, "em is NULL");
+    if (!em->r_valid) return fail(BAMM_E_STATE, "M-step needs the r of an E-step");
+    CU(cudaSetDevice(em->device));
+    CU(cudaEventRecord(em->ev[2], em->stream));
+    return launch_mstep_local(em);
+}
+
+extern "C" int bamm_em_finish_iteration(bamm_em* em, int optimize_q, float* llh, float* vdiff) {
+    REQUIRE(em, "em is NULL");
+    CU(cudaSetDevice(em->device));
+    int rc = launch_update(em); if (rc) return rc;
+    CU(cudaEventRecord(em->ev[3], em->stream));
+    if (!optimize_q && !llh && !vdiff) return BAMM_OK;      // stays asynchronous: no host round trip
+    rc = read_scalars(em, true); if (rc) return rc;
+    if (optimize_q) em->q = q_from_rsum(em);
+    if (llh) *llh = em->llh;
+    if (vdiff) *vdiff = *em->h_vdiff;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_set_exchange_buffer(bamm_em* em, void* dev_ptr, uint64_t words) {
+    REQUIRE(em && dev_ptr, "NULL argument");
+    REQUIRE(words == (uint64_t)em->nbin + 2, "exchange buffer must hold %llu 64-bit words", (unsigned long long)em->nbin + 2);
+    CU(cudaSetDevice(em->device));
+    CU(cudaStreamSynchronize(em->stream));
+    if (em->own_xbuf) cudaFree(em->d_xbuf);
+    em->d_xbuf = (unsigned long long*)dev_ptr; em->own_xbuf = false;
+    CU(cudaMemsetAsync(em->d_xbuf, 0, words * 8, em->stream));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_mstep(bamm_em* em) {
+    int rc = bamm_em_mstep_local(em); if (rc) return rc;
+    rc = launch_update(em); if (rc) return rc;
+    CU(cudaEventRecord(em->ev[3], em->stream));
+    CU(cudaStreamSynchronize(em->stream));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_optimize_q(bamm_em* em, float* q) {
+    REQUIRE(em, "em is NULL");
+    if (!em->r_valid) return fail(BAMM_E_STATE, "optimize_q needs the r of an E-step");
+    CU(cudaSetDevice(em->device));
+    int rc = read_scalars(em, false); if (rc) return rc;
+    em->q = q_from_rsum(em);
+    if (q) *q = em->q;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_optimize(bamm_em* em, int optimize_q, float epsilon, int max_iter, int* iterations,
+                                float* llh_trace, float* vdiff_trace, float* q_trace) {
+    REQUIRE(em, "em is NULL");
+    if (!em->model_set) return fail(BAMM_E_STATE, "bamm_em_set_model has not been called");
+    REQUIRE(max_iter >= 1, "max_iter must be >= 1");
+    CU(cudaSetDevice(em->device));
+    bool iterate = true;
+    int it = 0;
+    float llh_prev;
+    // reference: EM.cpp:79-118
+    while (iterate && it < max_iter) {
+        it++;
+        llh_prev = em->llh;
+        int rc = launch_estep(em); if (rc) return rc;
+        em->r_valid = true;
+        rc = launch_mstep_local(em); if (rc) return rc;
+        rc = launch_update(em); if (rc) return rc;
+        rc = read_scalars(em, true); if (rc) return rc;
+        if (optimize_q && it <= 5) em->q = q_from_rsum(em);
+        const float v_diff = *em->h_vdiff;
+        const float llh_diff = em->llh - llh_prev;
+        if (llh_trace) llh_trace[it - 1] = em->llh;
+        if (vdiff_trace) vdiff_trace[it - 1] = v_diff;
+        if (q_trace) q_trace[it - 1] = em->q;
+        if (v_diff < epsilon) iterate = false;
+        if (llh_diff < 0 && it > 10) iterate = false;
+    }
+    if (iterations) *iterations = it;
+    return BAMM_OK;
+}
+
+// launches of one iteration with optional event brackets (ev4 = 4 events or nullptr)
+static int launch_iteration(bamm_em* em, cudaEvent_t* ev4) {
+    if (ev4) CU(cudaEventRecord(ev4[0], em->stream));
+    int rc = launch_estep(em); if (rc) return rc;
+    if (ev4) CU(cudaEventRecord(ev4[1], em->stream));
+    IndexArray& ia = em->ss->index[em->K]; (void)ia;
+    rc = launch_mstep_accumulate(em); if (rc) return rc;
+    if (ev4) CU(cudaEventRecord(ev4[2], em->stream));
+    rc = launch_mstep_reduce(em); if (rc) return rc;
+    rc = launch_update(em); if (rc) return rc;
+    if (ev4) CU(cudaEventRecord(ev4[3], em->stream));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_iterate(bamm_em* em, int n_iter, float* llh_last, float* vdiff_last) {
+    REQUIRE(em, "em is NULL");
+    if (!em->model_set) return fail(BAMM_E_STATE, "bamm_em_set_model has not been called");
+    REQUIRE(n_iter >= 0, "n_iter must be >= 0");
+    CU(cudaSetDevice(em->device));
+    while ((int)em->loop_ev.size() < 4 * n_iter) { cudaEvent_t e; CU(cudaEventCreate(&e)); em->loop_ev.push_back(e); }
+    em->loop_iters = 0;
+    for (int it = 0; it < n_iter; it++) {
+        int rc = launch_iteration(em, &em->loop_ev[4 * it]); if (rc) return rc;
+    }
+    em->loop_iters = n_iter;
+    em->r_valid = n_iter > 0 || em->r_valid;
+    int rc = read_scalars(em, true); if (rc) return rc;
+    if (llh_last) *llh_last = em->llh;
+    if (vdiff_last) *vdiff_last = *em->h_vdiff;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_loop_timing(bamm_em* em, int* iters, float* estep_ms, float* maccum_ms, float* update_ms, float* total_ms) {
+    REQUIRE(em, "em is NULL");
+    CU(cudaSetDevice(em->device));
+    CU(cudaStreamSynchronize(em->stream));
+    float e = 0, m = 0, u = 0, t = 0, x;
+    for (int it = 0; it < em->loop_iters; it++) {
+        cudaEvent_t* ev = &em->loop_ev[4 * it];
+        CU(cudaEventElapsedTime(&x, ev[0], ev[1])); e += x;
+        CU(cudaEventElapsedTime(&x, ev[1], ev[2])); m += x;
+        CU(cudaEventElapsedTime(&x, ev[2], ev[3])); u += x;
+    }
+    if (em->loop_iters) CU(cudaEventElapsedTime(&t, em->loop_ev[0], em->loop_ev[4 * em->loop_iters - 1]));
+    if (iters) *iters = em->loop_iters;
+    if (estep_ms) *estep_ms = e;
+    if (maccum_ms) *maccum_ms = m;
+    if (update_ms) *update_ms = u;
+    if (total_ms) *total_ms = t;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_last_timing(bamm_em* em, float* estep_ms, float* mstep_ms) {
+    REQUIRE(em, "em is NULL");
+    CU(cudaSetDevice(em->device));
+    CU(cudaStreamSynchronize(em->stream));
+    float e = 0, m = 0;
+    if (cudaEventElapsedTime(&e, em->ev[0], em->ev[1]) != cudaSuccess) { e = 0; cudaGetLastError(); }
+    if (cudaEventElapsedTime(&m, em->ev[2], em->ev[3]) != cudaSuccess) { m = 0; cudaGetLastError(); }
+    if (estep_ms) *estep_ms = e;
+    if (mstep_ms) *mstep_ms = m;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_get_model(bamm_em* em, float* v_all) {
+    REQUIRE(em && v_all, "NULL argument");
+    CU(cudaSetDevice(em->device));
+    CU(cudaMemcpyAsync(v_all, em->d_v, em->model_size * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
+    CU(cudaStreamSynchronize(em->stream));
+    return BAMM_OK;
+}
+extern "C" int bamm_em_get_counts(bamm_em* em, float* n_all) {
+    REQUIRE(em && n_all, "NULL argument");
+    CU(cudaSetDevice(em->device));
+    CU(cudaMemcpyAsync(n_all, em->d_n, em->model_size * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
+    CU(cudaStreamSynchronize(em->stream));
+    return BAMM_OK;
+}
+extern "C" int bamm_em_get_s(bamm_em* em, float* s) {
+    REQUIRE(em && s, "NULL argument");
+    CU(cudaSetDevice(em->device));
+    std::vector<float> t(em->nbin);
+    CU(cudaMemcpyAsync(t.data(), em->d_s, (uint64_t)em->nbin * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
+    CU(cudaStreamSynchronize(em->stream));
+    for (uint32_t y = 0; y < em->Yn; y++) for (int j = 0; j < em->W; j++) s[(uint64_t)y * em->W + j] = t[(uint64_t)j * em->Yn + y];
+    return BAMM_OK;
+}
+extern "C" int bamm_em_get_q(bamm_em* em, float* q) { REQUIRE(em && q, "NULL argument"); *q = em->q; return BAMM_OK; }
+extern "C" uint64_t bamm_em_r_size(const bamm_em* em) { return em ? em->rsize : 0; }
+extern "C" int bamm_em_get_r(bamm_em* em, uint64_t first, uint64_t count, float* out) {
+    REQUIRE(em && out, "NULL argument");
+    REQUIRE(first + count <= em->nsub, "sequence range out of bounds");
+    if (!em->r_valid) return fail(BAMM_E_STATE, "no E-step has run");
+    CU(cudaSetDevice(em->device));
+    const uint64_t a = em->h_r_off[first], b = em->h_r_off[first + count];
+    CU(cudaMemcpyAsync(out, em->d_r + a, (b - a) * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
+    CU(cudaStreamSynchronize(em->stream));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_exchange_buffer(bamm_em* em, void** dev_ptr, uint64_t* words) {
+    REQUIRE(em && dev_ptr && words, "NULL argument");
+    *dev_ptr = em->d_xbuf; *words = (uint64_t)em->nbin + 2;
+    return BAMM_OK;
+}
+extern "C" int bamm_em_set_global_nseq(bamm_em* em, uint64_t n) { REQUIRE(em, "em is NULL"); em->nseq_global = n; return BAMM_OK; }
+extern "C" int bamm_em_stream(bamm_em* em, void** stream) { REQUIRE(em && stream, "NULL argument"); *stream = (void*)em->stream; return BAMM_OK; }
+
+// ------------------------------------------------------------------------------------------- scoring
+extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
+                                  const float* v_all, const float* vbg_all, float* zoops, uint64_t* z, float* mops) {
+    REQUIRE(s && v_all && vbg_all && zoops && z, "NULL argument");
+    REQUIRE(W >= 1 && W <= 32, "motif width W=%d not in [1,32]", W);
+    if (!subset) nsub = s->nseq;
+    IndexArray* ia;
+    { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
+    const int K_bg = K_bg_model < K ? K_bg_model : K;
+    ModelDims d; fill_dims(d, s->A, K, W, K_bg);
+    const uint32_t Yn = (uint32_t)ia->Yn, nbin = Yn * (uint32_t)W;
+    // Motif::calculateLogS (Motif.cpp:471-483) on the host: same libm logf as the reference; [j][y] layout
+    std::vector<float> slog(nbin);
+    {
+        const float* vK = v_all + d.voff[K]; const float* vb = vbg_all + d.bgoff[K_bg];
+        const uint32_t YB = d.Y[K_bg + 1];
+        for (uint32_t y = 0; y < Yn; y++) {
+            const float lb = logf(vb[y % YB]);
+            for (int j = 0; j < W; j++) slog[(uint64_t)j * Yn + y] = logf(vK[(uint64_t)y * W + j] + 1e-5f) - lb;
+        }
+    }
+    std::vector<uint32_t> ids(nsub);
+    std::vector<uint64_t> moff(nsub + 1, 0);
+    for (uint64_t i = 0; i < nsub; i++) {
+        const uint64_t n = subset ? subset[i] : i;
+        REQUIRE(n < s->nseq, "subset index out of range");
+        const uint64_t L = s->h_off[n + 1] - s->h_off[n];
+        REQUIRE(L >= (uint64_t)W, "sequence %llu is shorter than the motif", (unsigned long long)n);
+        ids[i] = (uint32_t)n; moff[i + 1] = moff[i] + (L - W + 1);
+    }
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    float *d_s = nullptr, *d_zoops = nullptr, *d_mops = nullptr; unsigned long long* d_z = nullptr;
+    uint32_t* d_ids = nullptr; uint64_t* d_moff = nullptr;
+    int rc = BAMM_OK;
+#define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
+    {
+        CUX(cudaMalloc(&d_s, (uint64_t)nbin * 4));
+        CUX(cudaMalloc(&d_zoops, (nsub ? nsub : 1) * 4));
+        CUX(cudaMalloc(&d_z, (nsub ? nsub : 1) * 8));
+        CUX(cudaMalloc(&d_ids, (nsub ? nsub : 1) * 4));
+        CUX(cudaMalloc(&d_moff, (nsub + 1) * 8));
+        if (mops) CUX(cudaMalloc(&d_mops, (moff[nsub] ? moff[nsub] : 1) * 4));
+        CUX(cudaMemcpyAsync(d_s, slog.data(), (uint64_t)nbin * 4, cudaMemcpyHostToDevice, st));
+        CUX(cudaMemcpyAsync(d_ids, ids.data(), nsub * 4, cudaMemcpyHostToDevice, st));
+        CUX(cudaMemcpyAsync(d_moff, moff.data(), (nsub + 1) * 8, cudaMemcpyHostToDevice, st));
+        SubsetView sv; sv.seq_off = s->d_off; sv.seq_ids = subset ? d_ids : nullptr; sv.r_off = nullptr; sv.nsub = (uint32_t)nsub;
+        int max_optin = 0;
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+        const size_t tb = (size_t)nbin * 4;
+        const bool smem = tb <= (size_t)max_optin;
+        int per_sm = smem ? (int)((size_t)(max_optin + 1024) / (tb + 1024)) : 4;
+        if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+        const int grid = s->sm_count * per_sm;
+        if (nsub) {
+            if (ia->bytes == 2) {
+                if (smem) { CUX(cudaFuncSetAttribute(k_score<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
+                            k_score<uint16_t, true><<<grid, 512, tb, st>>>((const uint16_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops); }
+                else        k_score<uint16_t, false><<<grid, 512, 0, st>>>((const uint16_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops);
+            } else {
+                if (smem) { CUX(cudaFuncSetAttribute(k_score<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
+                            k_score<uint32_t, true><<<grid, 512, tb, st>>>((const uint32_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops); }
+                else        k_score<uint32_t, false><<<grid, 512, 0, st>>>((const uint32_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops);
+            }
+            CUX(cudaGetLastError());
+        }
+        CUX(cudaMemcpyAsync(zoops, d_zoops, nsub * 4, cudaMemcpyDeviceToHost, st));
+        CUX(cudaMemcpyAsync(z, d_z, nsub * 8, cudaMemcpyDeviceToHost, st));
+        if (mops) CUX(cudaMemcpyAsync(mops, d_mops, moff[nsub] * 4, cudaMemcpyDeviceToHost, st));
+        CUX(cudaStreamSynchronize(st));
+    }
+done:
+#undef CUX
+    cudaFree(d_s); cudaFree(d_zoops); cudaFree(d_z); cudaFree(d_ids); cudaFree(d_moff); cudaFree(d_mops);
+    cudaStreamDestroy(st);
+    return rc;
+}

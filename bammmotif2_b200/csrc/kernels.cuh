@@ -1,0 +1,391 @@
+// kernels.cuh — sm_100a device code of the EM / scoring path.
+//
+// Data layout in HBM:
+//   Y      : order-K k-mer index per stored position, uint16 (A^(K+1) <= 65536) or uint32, all sequences
+//            concatenated in the seqset's order; y = kmer_[i] % A^(K+1) of the reference (Sequence.cpp:35-41).
+//   s      : odds table, TRANSPOSED to [j][y] (reference Motif::s_[y][j]) so that the 32 lanes of a warp, which
+//            look up the same motif column j for 32 different k-mers, spread over the shared-memory banks by y.
+//   r      : posteriors, float per stored position, reference index order (i = L-W-p, zero tail).
+//   counts : 64-bit fixed-point (scale 2^40) per (j,y); integer sums are associative, which makes the M-step
+//            bit-reproducible for any CTA schedule, any grid size and any number of GPUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bamm {
+
+constexpr int   FX_SHIFT      = 40;                       // counts: value * 2^40
+constexpr float FX_SCALE_F    = 1099511627776.0f;         // 2^40
+constexpr double FX_INV_D     = 1.0 / 1099511627776.0;
+constexpr double SC_SCALE_D   = 4294967296.0;             // scalars (llh, sum r): value * 2^32
+constexpr double SC_INV_D     = 1.0 / 4294967296.0;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k-mer index build: y[i] = (sum_{t=0..K} digit(code[i-t]) * A^t) mod A^(K+1), digit(0) = 0 (patched afterwards),
+// digit(c) = c-1 otherwise (also for the reverse-complemented N code 78, Alphabet.cpp:51). One warp per sequence.
+// reference: src/init/Sequence.cpp:35-41 followed by `% Y_[K+1]` at every consumer (e.g. EM.cpp:170).
+template <typename YT>
+__global__ void k_build_index(const uint8_t* __restrict__ codes, const uint64_t* __restrict__ off, uint64_t nseq,
+                              int A, int K, uint64_t Yn, YT* __restrict__ Y) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t n = warp; n < nseq; n += nwarps) {
+        const uint64_t base = off[n], L = off[n + 1] - base;
+        for (uint64_t i = lane; i < L; i += 32) {
+            uint64_t y = 0, pw = 1;
+            for (int t = 0; t <= K && (uint64_t)t <= i; t++) {
+                const uint32_t c = codes[base + i - t];
+                y += (uint64_t)(c ? c - 1 : 0) * pw;
+                pw *= (uint64_t)A;
+            }
+            Y[base + i] = (YT)(y % Yn);
+        }
+    }
+}
+
+template <typename YT>
+__global__ void k_patch_index(const uint64_t* __restrict__ ppos, const uint64_t* __restrict__ pkmer, uint64_t np,
+                              uint64_t Yn, YT* __restrict__ Y) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) Y[ppos[i]] = (YT)(pkmer[i] % Yn);
+}
+
+// top-order k-mer histogram over all positions (reference: BackgroundModel.cpp:26-42; lower orders are folds)
+template <typename YT>
+__global__ void k_count_kmers(const YT* __restrict__ Y, uint64_t npos, unsigned long long* __restrict__ cnt) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < npos; i += stride) atomicAdd(&cnt[Y[i]], 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sliding k-mer window of a warp: lane l holds y[p0+l] and y[p0+32+l]; the k-mer under motif column j of the
+// window that starts at p0+l is element l+j of that 64-entry strip (W <= 32), fetched with one shuffle.
+template <typename YT> struct Strip;
+template <> struct Strip<uint16_t> {
+    uint32_t packed;
+    __device__ __forceinline__ void load(const uint16_t* __restrict__ y, uint64_t p, uint64_t L) {
+        uint32_t a = (p < L) ? y[p] : 0u, b = (p + 32 < L) ? y[p + 32] : 0u;
+        packed = a | (b << 16);
+    }
+    __device__ __forceinline__ uint32_t get(int lane, int j) const {
+        const int src = lane + j;
+        const uint32_t t = __shfl_sync(FULL, packed, src & 31);
+        return (src < 32) ? (t & 0xffffu) : (t >> 16);
+    }
+};
+template <> struct Strip<uint32_t> {
+    uint32_t a, b;
+    __device__ __forceinline__ void load(const uint32_t* __restrict__ y, uint64_t p, uint64_t L) {
+        a = (p < L) ? y[p] : 0u; b = (p + 32 < L) ? y[p + 32] : 0u;
+    }
+    __device__ __forceinline__ uint32_t get(int lane, int j) const {
+        const int src = lane + j;
+        const uint32_t ta = __shfl_sync(FULL, a, src & 31), tb = __shfl_sync(FULL, b, src & 31);
+        return (src < 32) ? ta : tb;
+    }
+};
+
+struct SubsetView {
+    const uint64_t* seq_off;   // seqset offsets (nseq+1)
+    const uint32_t* seq_ids;   // subset -> seqset index, or nullptr for identity
+    const uint64_t* r_off;     // subset prefix sums of L (nsub+1)
+    uint32_t nsub;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// E-step. reference: EM::EStep, src/refinement/EM.cpp:139-200, in the gather form of SURVEY.md §8a-1:
+//   r[L-W-p] = ( prod_{j=0..min(W-1, L-W-p)} s[y(p+j)][j] ) * q/LW1 / norm,  norm = (1-q) + sum_p (...)
+// The product runs in ascending j from 1.0f like the reference's scatter loop (EM.cpp:167-176), the prior is
+// applied with one multiply (EM.cpp:180) and the normalisation is a true IEEE division (EM.cpp:186), so r differs
+// from the reference only through the summation order inside norm. One warp per sequence; lanes = window starts.
+// Scalars (log likelihood, sum of r for optimize_q) are accumulated per warp as 2^32 fixed point and added to
+// the exchange buffer with one 64-bit atomic per warp: integer sums => order-independent result.
+template <typename YT, bool SMEM>
+__global__ void __launch_bounds__(512)
+k_estep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float* __restrict__ s_g, float q,
+        float* __restrict__ r, unsigned long long* __restrict__ scal /* [0]=llh_fx, [1]=rsum_fx */) {
+    extern __shared__ float s_sh[];
+    const float* s = s_g;
+    if (SMEM) {
+        for (uint32_t i = threadIdx.x; i < (uint32_t)W * Yn; i += blockDim.x) s_sh[i] = s_g[i];
+        __syncthreads();
+        s = s_sh;
+    }
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    long long llh_fx = 0, rsum_fx = 0;
+    const float one_minus_q = 1.0f - q;
+    for (uint32_t i = warp; i < sv.nsub; i += nwarps) {
+        const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : i;
+        const uint64_t base = sv.seq_off[n], L = sv.seq_off[n + 1] - base;
+        const uint64_t LW1 = L - W + 1;
+        const YT* __restrict__ yn = Y + base;
+        float* __restrict__ rn = r + sv.r_off[i];
+        const float pos = q / (float)LW1;
+        float sum = 0.0f;
+        for (uint64_t p0 = 0; p0 < LW1; p0 += 32) {
+            const uint64_t p = p0 + lane;
+            Strip<YT> st; st.load(yn, p, L);
+            const int jmax = (p < LW1) ? (int)min((uint64_t)(W - 1), L - W - p) : -1;
+            float prod = 1.0f;
+            for (int j = 0; j < W; j++) {
+                const uint32_t y = st.get(lane, j);
+                if (j <= jmax) prod *= s[(uint32_t)j * Yn + y];
+            }
+            if (p < LW1) {
+                const float val = prod * pos;
+                rn[L - W - p] = val;
+                sum += val;
+            }
+        }
+        sum = warp_sum(sum);
+        const float norm = one_minus_q + sum;
+        __syncwarp();
+        for (uint64_t k = lane; k < L; k += 32) rn[k] = (k < LW1) ? __fdiv_rn(rn[k], norm) : 0.0f;
+        if (lane == 0) {
+            llh_fx += __double2ll_rn((double)logf(norm) * SC_SCALE_D);
+            rsum_fx += __double2ll_rn((double)__fdiv_rn(sum, norm) * SC_SCALE_D);
+        }
+    }
+    if (lane == 0) {
+        if (llh_fx) atomicAdd(&scal[0], (unsigned long long)llh_fx);
+        if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// M-step accumulation. reference: EM::MStep, src/refinement/EM.cpp:230-243, gather form:
+//   n[K][y(p+j)][j] += r[L-W-p]   for every window start p and j <= min(W-1, L-W-p).
+// Each r is converted ONCE to 2^40 fixed point (round to nearest) and added with native 32-bit integer shared
+// atomics to the low word of a CTA-private table; the returned old value tells whether the low word wrapped,
+// and the carry (plus the high word of large r) goes to the CTA's 64-bit partial table in global memory.
+// No floating-point atomics anywhere => the sum is exact in fixed point and independent of execution order.
+template <typename YT, bool SMEM>
+__global__ void __launch_bounds__(512)
+k_mstep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float* __restrict__ r,
+        unsigned long long* __restrict__ part /* SMEM: [gridDim.x][W*Yn]; else one [W*Yn] table */) {
+    extern __shared__ uint32_t lo_sh[];
+    const uint32_t nbin = (uint32_t)W * Yn;
+    unsigned long long* mypart = SMEM ? part + (uint64_t)blockIdx.x * nbin : part;
+    if (SMEM) {
+        for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) lo_sh[i] = 0u;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t i = warp; i < sv.nsub; i += nwarps) {
+        const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : i;
+        const uint64_t base = sv.seq_off[n], L = sv.seq_off[n + 1] - base;
+        const uint64_t LW1 = L - W + 1;
+        const YT* __restrict__ yn = Y + base;
+        const float* __restrict__ rn = r + sv.r_off[i];
+        for (uint64_t p0 = 0; p0 < LW1; p0 += 32) {
+            const uint64_t p = p0 + lane;
+            Strip<YT> st; st.load(yn, p, L);
+            int jmax = -1;
+            unsigned long long X = 0;
+            if (p < LW1) {
+                const float rv = rn[L - W - p];
+                if (rv > 0.0f) { X = __float2ull_rn(rv * FX_SCALE_F); jmax = (int)min((uint64_t)(W - 1), L - W - p); }
+                if (X == 0) jmax = -1;
+            }
+            const uint32_t xlo = (uint32_t)X, xhi = (uint32_t)(X >> 32);
+            for (int j = 0; j < W; j++) {
+                const uint32_t y = st.get(lane, j);
+                if (j <= jmax) {
+                    const uint32_t bin = (uint32_t)j * Yn + y;
+                    if (SMEM) {
+                        const uint32_t old = atomicAdd(&lo_sh[bin], xlo);
+                        const uint32_t h = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
+                        if (h) atomicAdd(&mypart[bin], (unsigned long long)h << 32);
+                    } else {
+                        atomicAdd(&mypart[bin], X);
+                    }
+                }
+            }
+        }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
+            const uint32_t v = lo_sh[i];
+            if (v) atomicAdd(&mypart[i], (unsigned long long)v);
+        }
+    }
+}
+
+// Sum of the per-CTA partial tables (integers: any order gives the same bits) into the exchange buffer.
+__global__ void k_reduce_parts(const unsigned long long* __restrict__ part, uint32_t nparts, uint32_t nbin,
+                               unsigned long long* __restrict__ xbuf) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbin) return;
+    unsigned long long acc = 0;
+    for (uint32_t c = 0; c < nparts; c++) acc += part[(uint64_t)c * nbin + b];
+    xbuf[b] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Model update, one CTA. reference: fold of the counts EM.cpp:247-254, Motif::updateV Motif.h:95-136,
+// convergence term EM.cpp:102-107, Motif::calculateLinearS Motif.cpp:485-494. Every formula keeps the
+// reference's operation order (compiled with -fmad=false); only sum|dv| is a tree instead of a serial sum.
+struct ModelDims { int A, K, W, K_bg; uint32_t Y[16]; uint32_t voff[16]; uint32_t bgoff[16]; };
+
+__global__ void __launch_bounds__(1024)
+k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn] fixed-point counts, [j][y] */,
+               float* __restrict__ n_all, float* __restrict__ v_all, float* __restrict__ vK_prev,
+               const float* __restrict__ vbg_all, const float* __restrict__ alpha,
+               float* __restrict__ s_lin /* [j][y] */, float* __restrict__ vdiff_out) {
+    const int W = d.W, K = d.K, A = d.A;
+    const uint32_t YK = d.Y[K + 1];
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    __shared__ float sumN[64];
+    __shared__ double red[32];
+    // top-order counts: fixed point -> float, [j][y] -> [y][j]
+    float* nK = n_all + d.voff[K];
+    for (uint32_t i = tid; i < YK * (uint32_t)W; i += nt) {
+        const uint32_t y = i / W, j = i % W;
+        nK[i] = (float)((double)(long long)xbuf[(uint32_t)j * YK + y] * FX_INV_D);
+    }
+    __syncthreads();
+    // fold to lower orders: n[k-1][y2][j] = ((0 + n[k][0*Y_k+y2][j]) + n[k][1*Y_k+y2][j]) + ...  (EM.cpp:247-254)
+    for (int k = K; k > 0; k--) {
+        const float* nk = n_all + d.voff[k];
+        float* nk1 = n_all + d.voff[k - 1];
+        const uint32_t Yk = d.Y[k];
+        for (uint32_t i = tid; i < Yk * (uint32_t)W; i += nt) {
+            const uint32_t y2 = i / W, j = i % W;
+            float acc = 0.0f;
+            for (int a = 0; a < A; a++) acc += nk[((uint32_t)a * Yk + y2) * W + j];
+            nk1[i] = acc;
+        }
+        __syncthreads();
+    }
+    // order 0 (Motif.h:101-118)
+    if (tid < (uint32_t)W) {
+        float sN = 0.0f;
+        for (int y = 0; y < A; y++) sN += n_all[y * W + tid];
+        sumN[tid] = sN;
+    }
+    __syncthreads();
+    double dsum = 0.0;
+    for (uint32_t i = tid; i < (uint32_t)A * W; i += nt) {
+        const uint32_t y = i / W, j = i % W;
+        const float nv = (n_all[i] + alpha[j] * vbg_all[y]) / (sumN[j] + alpha[j]);
+        if (K == 0) { dsum += (double)fabsf(nv - vK_prev[i]); vK_prev[i] = nv; }
+        v_all[i] = nv;
+    }
+    __syncthreads();
+    // orders 1..K (Motif.h:121-135)
+    for (int k = 1; k <= K; k++) {
+        float* vk = v_all + d.voff[k];
+        const float* vk1 = v_all + d.voff[k - 1];
+        const float* nk = n_all + d.voff[k];
+        const float* nk1 = n_all + d.voff[k - 1];
+        const float* ak = alpha + k * W;
+        const uint32_t Yk1 = d.Y[k + 1], Yk = d.Y[k];
+        for (uint32_t i = tid; i < Yk1 * (uint32_t)W; i += nt) {
+            const uint32_t y = i / W, j = i % W;
+            const uint32_t y2 = y % Yk, yk = y / A;
+            float nv;
+            if ((int)j < k) nv = vk1[y2 * W + j];
+            else nv = (nk[i] + ak[j] * vk1[y2 * W + j]) / (nk1[yk * W + j - 1] + ak[j]);
+            if (k == K) { dsum += (double)fabsf(nv - vK_prev[i]); vK_prev[i] = nv; }
+            vk[i] = nv;
+        }
+        __syncthreads();
+    }
+    // sum |dv|
+    for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(FULL, dsum, o);
+    if ((tid & 31) == 0) red[tid >> 5] = dsum;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (uint32_t w = 0; w < (nt >> 5); w++) t += red[w];
+        *vdiff_out = (float)t;
+    }
+    // next E-step's table (Motif.cpp:485-494), transposed to [j][y]
+    const float* vK = v_all + d.voff[K];
+    const float* vb = vbg_all + d.bgoff[d.K_bg];
+    const uint32_t YB = d.Y[d.K_bg + 1];
+    for (uint32_t i = tid; i < YK * (uint32_t)W; i += nt) {
+        const uint32_t y = i / W, j = i % W;
+        s_lin[(uint32_t)j * YK + y] = vK[i] / vb[y % YB];
+    }
+}
+
+// s table only (first E-step after set_model)
+__global__ void k_make_s(ModelDims d, const float* __restrict__ v_all, const float* __restrict__ vbg_all,
+                         float* __restrict__ s_lin, float* __restrict__ vK_prev) {
+    const int W = d.W, K = d.K;
+    const uint32_t YK = d.Y[K + 1], YB = d.Y[d.K_bg + 1];
+    const float* vK = v_all + d.voff[K];
+    const float* vb = vbg_all + d.bgoff[d.K_bg];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < YK * (uint32_t)W; i += gridDim.x * blockDim.x) {
+        const uint32_t y = i / W, j = i % W;
+        s_lin[(uint32_t)j * YK + y] = vK[i] / vb[y % YB];
+        vK_prev[i] = vK[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Scoring. reference: ScoreSeqSet::calcLogOdds, src/seq_scoring/ScoreSeqSet.cpp:25-67. Full windows (all W
+// columns, :49-54), float sum in ascending j from 0.0f (bit-identical to the reference for the same table),
+// per-sequence maximum with the FIRST maximal window winning (strict '>' scan, :59-62).
+template <typename YT, bool SMEM>
+__global__ void __launch_bounds__(512)
+k_score(const YT* __restrict__ Y, SubsetView sv, const uint64_t* __restrict__ mops_off, int W, uint32_t Yn,
+        const float* __restrict__ s_g, float* __restrict__ zoops, unsigned long long* __restrict__ z,
+        float* __restrict__ mops) {
+    extern __shared__ float s_sh[];
+    const float* s = s_g;
+    if (SMEM) {
+        for (uint32_t i = threadIdx.x; i < (uint32_t)W * Yn; i += blockDim.x) s_sh[i] = s_g[i];
+        __syncthreads();
+        s = s_sh;
+    }
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t i = warp; i < sv.nsub; i += nwarps) {
+        const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : i;
+        const uint64_t base = sv.seq_off[n], L = sv.seq_off[n + 1] - base;
+        const uint64_t LW1 = L - W + 1;
+        const YT* __restrict__ yn = Y + base;
+        float best = -3.402823466e+38f;   // -FLT_MAX, ScoreSeqSet.cpp:44
+        uint64_t bestp = 0;
+        for (uint64_t p0 = 0; p0 < LW1; p0 += 32) {
+            const uint64_t p = p0 + lane;
+            Strip<YT> st; st.load(yn, p, L);
+            float sc = 0.0f;
+            for (int j = 0; j < W; j++) {
+                const uint32_t y = st.get(lane, j);
+                sc += s[(uint32_t)j * Yn + y];
+            }
+            if (p < LW1) {
+                if (mops) mops[mops_off[i] + p] = sc;
+                if (sc > best) { best = sc; bestp = p; }
+            }
+        }
+        // lanes scanned ascending p with strict '>', so each lane holds its first maximum; combine: larger score
+        // wins, equal scores -> smaller position (what the serial scan would have kept).
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(FULL, best, o);
+            const uint64_t op = __shfl_xor_sync(FULL, bestp, o);
+            if (ob > best || (ob == best && op < bestp)) { best = ob; bestp = op; }
+        }
+        if (lane == 0) { zoops[i] = best; z[i] = bestp; }
+    }
+}
+
+}  // namespace bamm

@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the EM hot path (E-step + M-step + model update) on synthetic planted-motif data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|tiny] [--impl reference]
+
+A "step" is ONE EM iteration over the whole resident sequence set (E-step kernel, M-step accumulation kernel,
+count reduction + Motif::updateV + next odds table). Metric: bp.iter/s = (sum of input bases L0) x iterations /
+device time, order-K model on both strands (BASELINE.json). One process per GPU; under torchrun every rank holds
+its own shard (weak scaling) and the per-iteration exchange is one NCCL all-reduce (SUM, int64) of the fixed-point
+count table + 2 scalars, issued on the EM stream between the two halves of the iteration.
+
+JSON keys follow the driver's contract; extra objects:
+  roofline      dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json), algorithmic bytes 6 B/position/kernel
+  cpu_baseline  the reference's own EStep/MStep (oracle/_ref/ref_time, all host threads) on a bounded sample, rank 0, N=1
+  e2e           same metric through the C ABI from HOST buffers: upload + index build + K iterations + model read-back
+`--impl reference` times only the CPU reference arm on the same workload definition (bounded sample per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from bammmotif2_b200 import synth  # noqa: E402
+from bammmotif2_b200 import hostmodel  # noqa: E402
+
+METRIC = "EM bp·iter/s (order-k, both strands)"
+UNIT = "bp·iter/s"
+Q = 0.3   # reference default prior (Global.cpp:52)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--nseq", type=int, default=0, help="override sequences per GPU (debug)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="sequences in the CPU sample (default by workload)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            t = [x.strip() for x in l.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0])); mx = float(t[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, t[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm_sorted = sorted(sm)
+        return {"sm_mhz": sm_sorted[len(sm_sorted) // 2] if sm else None, "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_data(wl, nseq, seed, pinned=False):
+    """Returns dict(codes [nseq, L] uint8 (optionally pinned), offsets, patches, sites, fwd)."""
+    fwd, sites, _ = synth.planted_sequences(seed, nseq, wl["L0"], wl["W"])
+    L = 2 * wl["L0"] + 1
+    out = None
+    if pinned:
+        import torch
+        out = torch.empty((nseq, L), dtype=torch.uint8, pin_memory=True).numpy()
+    codes = synth.stored_both_strands(fwd, out=out)
+    ppos, pkmer = synth.middle_n_patches(codes, seed)
+    offsets = np.arange(nseq + 1, dtype=np.uint64) * np.uint64(L)
+    return dict(codes=codes, offsets=offsets, ppos=ppos, pkmer=pkmer, sites=sites, fwd=fwd, L=L)
+
+
+def initial_model(capi, ss, wl, sites):
+    """Background model from device k-mer counts (BackgroundModel.cpp:26-42, 441-472) + binding-site init."""
+    A = 4
+    n = ss.count_kmers(wl["K_bg"])
+    vbg = hostmodel.background_from_counts(n, A, wl["K_bg"], hostmodel.default_bg_alpha(wl["K_bg"]))
+    alpha = hostmodel.default_motif_alpha(wl["K"], wl["W"])
+    v0 = hostmodel.motif_from_sites(sites, A, wl["K"], alpha, vbg)
+    return v0, vbg, alpha
+
+
+def cpu_reference_run(wl, sample_nseq, seed, steps, warmup, threads):
+    """Runs the reference's own EStep/MStep (oracle/_ref/ref_time) on a bounded sample; falls back to the oracle
+    port (same OpenMP structure) when the reference build is not there. Returns dict for the JSON line."""
+    fwd, sites, _ = synth.planted_sequences(seed, sample_nseq, wl["L0"], wl["W"])
+    bp = int(fwd.size)
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_time")
+    sample = "%d x %d bp sample of %s (same generator, seed %d), W=%d K=%d, %d timed iterations" % (
+        sample_nseq, wl["L0"], wl["name"], seed, wl["W"], wl["K"], steps)
+    if os.path.exists(exe):
+        tmp = tempfile.mkdtemp(prefix="bamm_cpu_")
+        fa, bs = os.path.join(tmp, "s.fasta"), os.path.join(tmp, "sites.block")
+        synth.write_fasta(fa, fwd)
+        synth.write_sites(bs, sites)
+        env = dict(os.environ, BAMM_TIME_ITERS=str(steps), BAMM_TIME_WARMUP=str(warmup), OMP_NUM_THREADS=str(threads))
+        cmd = [exe, tmp, fa, "--bindingSiteFile", bs, "--EM", "-k", str(wl["K"]), "-K", str(wl["K_bg"]), "--threads", str(threads)]
+        out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
+        res = json.loads(out.strip().splitlines()[-1])
+        per_iter = res["per_iter_s"]
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+        return dict(kind="reference", cores=threads, sample=sample, bp=bp, per_iter_s=per_iter,
+                    estep_s=res["estep_s"], mstep_s=res["mstep_s"], value=bp * len(per_iter) / sum(per_iter))
+    # port: oracle restatement with the reference's OpenMP structure
+    from oracle import oracle as orc
+    codes = synth.stored_both_strands(fwd)
+    ppos, pkmer = synth.middle_n_patches(codes, seed)
+    kmer = synth.full_kmers(codes, ppos, pkmer)
+    offsets = np.arange(sample_nseq + 1, dtype=np.uint64) * np.uint64(codes.shape[1])
+    A = 4
+    nb, vbg = orc.bg_model(kmer, A, wl["K_bg"], hostmodel.default_bg_alpha(wl["K_bg"]))
+    alpha = hostmodel.default_motif_alpha(wl["K"], wl["W"])
+    v = hostmodel.motif_from_sites(sites, A, wl["K"], alpha, vbg)
+    r = np.zeros(len(kmer), np.float32)
+    n_all = np.zeros(orc.model_size(A, wl["K"], wl["W"]), np.float32)
+    per_iter = []
+    for it in range(warmup + steps):
+        s = orc.linear_s(v, vbg, A, wl["K"], min(wl["K"], wl["K_bg"]), wl["W"])
+        t0 = time.perf_counter()
+        orc.em_iteration_omp(kmer, offsets, A, wl["K"], wl["W"], s, Q, r, n_all, threads)
+        dt = time.perf_counter() - t0
+        orc.update_v(n_all, alpha.ravel(), vbg, A, wl["K"], wl["W"], v)
+        if it >= warmup:
+            per_iter.append(dt)
+    return dict(kind="port", cores=threads, sample=sample, bp=bp, per_iter_s=per_iter,
+                value=bp * len(per_iter) / sum(per_iter))
+
+
+def run_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample or wl["cpu_sample"]
+    t0 = time.perf_counter()
+    res = cpu_reference_run(wl, sample, args.seed, args.steps, max(args.warmup, 1), threads)
+    wall = time.perf_counter() - t0
+    ms = 1e3 * sum(res["per_iter_s"]) / len(res["per_iter_s"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "W": wl["W"], "K": wl["K"], "K_bg": wl["K_bg"], "step": "one EM iteration on the CPU sample",
+                   "sample_nseq": sample, "seed": args.seed},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    wl = dict(synth.WORKLOADS[args.workload], name=args.workload)
+    wl["cpu_sample"] = {"c3": 40_000, "c2": 50_000, "tiny": 2_000}[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from bammmotif2_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    capi.load()
+    capi._check(capi.load().bamm_set_device(local_rank))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    nseq = args.nseq or wl["nseq"]
+    A = 4
+    data = make_data(wl, nseq, args.seed + 1000 * rank, pinned=True)
+    bp_local = nseq * wl["L0"]
+    pos_local = nseq * data["L"]
+    bp_total = bp_local * world
+
+    # ---- resident run ---------------------------------------------------------------------------------------
+    ss = capi.SeqSet(data["codes"].reshape(-1), data["offsets"], A, data["ppos"], data["pkmer"])
+    v0, vbg, alpha = initial_model(capi, ss, wl, data["sites"])
+    em = capi.EM(ss, wl["W"], wl["K"], wl["K_bg"])
+    em.set_model(v0, vbg, alpha, Q)
+    stream = torch.cuda.ExternalStream(em.stream(), device=torch.device("cuda", local_rank))
+    xt = None
+    if world > 1:
+        words = em.exchange_buffer()[1]
+        xt = torch.zeros(words, dtype=torch.int64, device="cuda")
+        em.set_exchange_buffer(xt.data_ptr(), words)
+        em.set_global_nseq(nseq * world)
+
+    def run_iters(n):
+        if world == 1:
+            em.iterate(n)
+            return
+        with torch.cuda.stream(stream):
+            for _ in range(n):
+                em.estep_local()
+                em.mstep_local()
+                dist.all_reduce(xt, op=dist.ReduceOp.SUM)
+                em.finish_iteration(sync=False)
+        stream.synchronize()
+
+    run_iters(args.warmup)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run_iters(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = bp_total * args.steps / (ms_total * 1e-3)
+
+    # per-kernel device times (CUDA events on the EM stream, recorded by the library inside the timed loop)
+    roof = None
+    if world == 1:
+        iters, e_ms, m_ms, u_ms, _ = em.loop_timing()
+        peak, peak_src = peaks()
+        dom_name, dom_ms = ("k_mstep (M-step accumulation)", m_ms) if m_ms >= e_ms else ("k_estep (E-step)", e_ms)
+        bytes_per_launch = 6.0 * pos_local          # 2 B k-mer index + 4 B r per position, per kernel
+        ach = bytes_per_launch / (dom_ms / iters * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "estep_ms": e_ms / iters, "mstep_accum_ms": m_ms / iters, "reduce_update_ms": u_ms / iters,
+                "whole_iteration_frac_of_12B_roofline": (12.0 * pos_local / (ms_total / args.steps * 1e-3) / 1e9) / peak}
+    llh_after = None
+    if world == 1:
+        llh_after = em.iterate(0)[0]
+
+    # ---- end-to-end through the C ABI from host buffers -------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        em.close(); ss.close()
+        del em, ss
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ss2 = capi.SeqSet(data["codes"].reshape(-1), data["offsets"], A, data["ppos"], data["pkmer"])   # H2D from pinned host memory
+        em2 = capi.EM(ss2, wl["W"], wl["K"], wl["K_bg"])                                                 # builds the index on the device
+        em2.set_model(v0, vbg, alpha, Q)
+        if world > 1:
+            em2.set_exchange_buffer(xt.data_ptr(), em2.exchange_buffer()[1])
+            em2.set_global_nseq(nseq * world)
+            st2 = torch.cuda.ExternalStream(em2.stream(), device=torch.device("cuda", local_rank))
+            with torch.cuda.stream(st2):
+                for _ in range(args.steps):
+                    em2.estep_local(); em2.mstep_local()
+                    dist.all_reduce(xt, op=dist.ReduceOp.SUM)
+                    em2.finish_iteration(sync=False)
+            st2.synchronize()
+        else:
+            em2.iterate(args.steps)
+        vfinal = em2.model()                                                                              # D2H
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = data["codes"].nbytes + data["offsets"].nbytes + data["ppos"].nbytes + data["pkmer"].nbytes + v0.nbytes + vbg.nbytes + alpha.nbytes
+        d2h = vfinal.nbytes + 24
+        e2e = {"value": bp_total * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": dt,
+               "what": "bamm_seqset_create (H2D of codes from pinned host memory) + index build + bamm_em_create/set_model + "
+                       "%d iterations + bamm_em_get_model (D2H); upload amortised over the %d iterations" % (args.steps, args.steps)}
+        em2.close(); ss2.close()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            threads = os.cpu_count() or 1
+            res = cpu_reference_run(wl, args.cpu_sample or wl["cpu_sample"], args.seed, 3, 1, threads)
+            cpu = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]}
+        except Exception as ex:   # the baseline must never take the GPU number down with it
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(ex)[:200]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "nseq_per_gpu": nseq, "L0": wl["L0"], "W": wl["W"], "K": wl["K"], "K_bg": wl["K_bg"],
+                       "q": Q, "seed": args.seed, "step": "one EM iteration (E-step + M-step + updateV)",
+                       "positions_per_gpu": pos_local, "positions_iter_per_s": pos_local * world * args.steps / (ms_total * 1e-3),
+                       "l2": "inputs (%.1f GB index + r per GPU) exceed the 126 MB L2" % (6.0 * pos_local / 1e9) if 6.0 * pos_local > 2.0e8
+                             else "inputs fit in L2; no flush between iterations (EM iterates over resident data)",
+                       "parallelism": "sequence shards, dp%d" % world},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * args.steps,
+        }
+        if roof:
+            line["roofline"] = roof
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if llh_after is not None:
+            line["config"]["llh_after"] = llh_after
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,145 @@
+/*
+ * bamm_b200.h — C ABI of the B200-native EM-refinement / sequence-scoring path of BaMM!motif v2.
+ *
+ * The reference (soedinglab/BaMMmotif2) has no FFI: its hot path sits behind the public C++ classes
+ * EM, ScoreSeqSet and FDR. This header is the boundary a maintainer binds instead of
+ * the bodies of those methods; the C++ mirror classes in bammmotif2_b200/host/ do exactly that and
+ * INTEGRATION.md shows the binding. Everything is plain pointers and sizes; no torch / C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 (BAMM_OK) or a negative BAMM_E_* code; bamm_last_error() gives the text
+ *     (thread-local). The C++ wrappers print it to stderr and exit(1), the reference's error convention
+ *     (e.g. src/init/SequenceSet.cpp:144-149).
+ *   - model tables are flat float arrays in the reference's index order:
+ *       v_all   : for k=0..K, for y<A^(k+1), for j<W        (reference float*** Motif::v_[k][y][j], Motif.h:56)
+ *       vbg_all : for k=0..K_bg_model, for y<A^(k+1)        (reference float**  BackgroundModel::v_[k][y])
+ *       alpha   : [K+1][W]                                   (reference float**  Motif::A_[k][j])
+ *   - r is indexed like EM::r_[n][i] (src/refinement/EM.h:48-52): i = L-W-p for window start p, zero for
+ *     i >= L-W+1, L floats per sequence.
+ *   - objects are re-entrant across host threads as long as each thread uses its own bamm_em
+ *     (FDR::evaluateMotif runs folds concurrently, src/evaluation/FDR.cpp:37-38); a bamm_seqset is
+ *     immutable after bamm_seqset_index() and may be shared.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with BAMM_E_CUDA.
+ */
+#ifndef BAMM_B200_H_
+#define BAMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAMM_OK            0
+#define BAMM_E_INVALID    -1   /* bad argument (message says which) */
+#define BAMM_E_CUDA       -2   /* CUDA runtime error / no device */
+#define BAMM_E_NOMEM      -3   /* device or host allocation failed */
+#define BAMM_E_STATE      -4   /* call order violated (e.g. estep before set_model) */
+
+typedef struct bamm_seqset bamm_seqset;   /* sequences resident in HBM: codes + per-order k-mer index arrays */
+typedef struct bamm_em     bamm_em;       /* one EM problem: subset of a seqset, model, r, counts, workspaces */
+
+/* ---- library / device ----------------------------------------------------------------------- */
+int         bamm_version(void);                    /* 10000*major + 100*minor + patch */
+const char* bamm_last_error(void);                 /* text of the last failure on this thread */
+int         bamm_device_count(int* count);
+int         bamm_set_device(int device);           /* device used by objects created afterwards on this thread */
+int         bamm_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+
+/* ---- sequence set  (replaces Sequence::kmer_ / getKmer(), src/init/Sequence.cpp:35-41, Sequence.h:56-58) ---- */
+/*
+ * codes   : stored codes exactly as Sequence::sequence_ holds them (0 = N, 1..A, 78 for a reverse-complemented N;
+ *           both strands already laid out as fwd | 0 | revcomp, src/init/Sequence.cpp:10-14,91-99), all sequences
+ *           concatenated.
+ * offsets : nseq+1 prefix sums of the stored lengths L_n.
+ * patch_* : the positions whose k-mer hash cannot be derived from `codes` because a code-0 base draws
+ *           rand() % A per (position, order) pair (Sequence.cpp:38): global position index and the reference's
+ *           full 11-mer hash kmer_[i] for it. Sorted by position, at most one entry per position. May be empty.
+ */
+int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets, uint64_t nseq, int A,
+                       const uint64_t* patch_pos, const uint64_t* patch_kmer, uint64_t npatch,
+                       bamm_seqset** out);
+/* Builds (once; cached) the order-K index array y[i] = kmer_[i] % A^(K+1) on the device. */
+int bamm_seqset_index(bamm_seqset* s, int K);
+/* Copies the order-K index array back (npos entries, widened to uint32) — for bit-exact parity checks. */
+int bamm_seqset_get_index(bamm_seqset* s, int K, uint32_t* out);
+int bamm_seqset_info(const bamm_seqset* s, uint64_t* nseq, uint64_t* npos, int* A);
+/* Background k-mer counts n[k][y] for k<=K over all positions (BackgroundModel.cpp:26-42); out: sum_k A^(k+1). */
+int bamm_seqset_count_kmers(bamm_seqset* s, int K, uint64_t* n_all);
+void bamm_seqset_destroy(bamm_seqset* s);
+
+/* ---- EM  (replaces EM::EStep/MStep/optimize/optimize_q, src/refinement/EM.cpp:62-259,505-519) -------------- */
+/*
+ * subset : indices into the seqset (NULL = all sequences, in order); the EM object sees exactly these sequences
+ *          in this order (FDR training folds, src/evaluation/FDR.cpp:49-57). Every sequence must have L >= W
+ *          (the reference filters shorter ones before EM, src/refinement/mainBaMM.cpp:75-83).
+ * K_bg_model : order of the background model that will be passed to set_model; K_bg = min(K_bg_model, K) (EM.cpp:23).
+ */
+int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
+                   bamm_em** out);
+int bamm_em_set_model(bamm_em* em, const float* v_all, const float* vbg_all, const float* alpha, float q);
+/* EM::EStep (EM.cpp:139-200): refreshes s = v[K]/vbg, r and the log likelihood. */
+int bamm_em_estep(bamm_em* em, float* llh);
+/* EM::MStep (EM.cpp:217-259): counts from r, fold to lower orders, Motif::updateV (Motif.h:95-136). */
+int bamm_em_mstep(bamm_em* em);
+/* EM::optimize_q (EM.cpp:505-519) from the r of the last E-step. */
+int bamm_em_optimize_q(bamm_em* em, float* q);
+/*
+ * EM::optimize (EM.cpp:62-137) with the reference's stop rule: stop when sum|dv[K]| < epsilon, or the log
+ * likelihood dropped after iteration 10, or max_iter (reference constants 0.01 / 1000, EM.h:62-63).
+ * Traces may be NULL; when given they must hold max_iter floats. optimize_q != 0 re-estimates q during the
+ * first five iterations (EM.cpp:99).
+ */
+int bamm_em_optimize(bamm_em* em, int optimize_q, float epsilon, int max_iter, int* iterations,
+                     float* llh_trace, float* vdiff_trace, float* q_trace);
+/* n_iter full iterations (E, M, update) back to back without a host round trip; for throughput runs. */
+int bamm_em_iterate(bamm_em* em, int n_iter, float* llh_last, float* vdiff_last);
+int bamm_em_get_model(bamm_em* em, float* v_all);              /* current v, all orders */
+int bamm_em_get_counts(bamm_em* em, float* n_all);             /* n of the last M-step, all orders (EM::n_) */
+int bamm_em_get_s(bamm_em* em, float* s);                      /* s[y][j] of the last E-step (Motif::getS) */
+int bamm_em_get_q(bamm_em* em, float* q);
+int bamm_em_get_r(bamm_em* em, uint64_t first, uint64_t count, float* out);  /* r of subset sequences [first, first+count), concatenated */
+uint64_t bamm_em_r_size(const bamm_em* em);                    /* sum of L over the subset */
+/* device time of the last estep / mstep+update call in milliseconds (CUDA events on the EM stream) */
+int bamm_em_last_timing(bamm_em* em, float* estep_ms, float* mstep_ms);
+/* device times of the last bamm_em_iterate call, summed over its iterations (CUDA events on the EM stream):
+ * E-step kernel, M-step accumulation kernel, reduce + model update, and first-launch-to-last-completion. */
+int bamm_em_loop_timing(bamm_em* em, int* iters, float* estep_ms, float* maccum_ms, float* update_ms, float* total_ms);
+void bamm_em_destroy(bamm_em* em);
+
+/* ---- multi-GPU (sequences sharded over ranks, one process per GPU) ---------------------------- */
+/*
+ * The per-iteration exchange is a SUM over ranks of the integer (fixed-point) count table and two integer
+ * scalars (log likelihood, sum of r). The library exposes the device buffer that has to be summed; the host
+ * plumbing (torch.distributed / NCCL) all-reduces it in place between the two halves of an iteration:
+ *   bamm_em_estep_local + bamm_em_mstep_local  -> buffer holds this rank's partial sums (int64)
+ *   <all-reduce SUM int64 over `words` elements at `dev_ptr`>
+ *   bamm_em_finish_iteration                   -> fold / updateV / new s on every rank (bit-identical)
+ * Integer sums are associative, so the result does not depend on the rank count or the reduction order.
+ */
+int bamm_em_exchange_buffer(bamm_em* em, void** dev_ptr, uint64_t* words);
+/* Makes the EM object use caller-owned device memory (e.g. a torch tensor registered with NCCL) as its exchange buffer. */
+int bamm_em_set_exchange_buffer(bamm_em* em, void* dev_ptr, uint64_t words);
+int bamm_em_set_global_nseq(bamm_em* em, uint64_t nseq_all_ranks);   /* N in optimize_q's formula */
+int bamm_em_estep_local(bamm_em* em);
+int bamm_em_mstep_local(bamm_em* em);
+/* With optimize_q == 0 and llh == vdiff == NULL the call only enqueues work (no host round trip). */
+int bamm_em_finish_iteration(bamm_em* em, int optimize_q, float* llh, float* vdiff);
+/* CUDA stream (cudaStream_t as void*) the EM object launches on, so callers can order collectives after it */
+int bamm_em_stream(bamm_em* em, void** stream);
+
+/* ---- scoring  (replaces ScoreSeqSet::calcLogOdds, src/seq_scoring/ScoreSeqSet.cpp:25-67) ------------------- */
+/*
+ * Scores every window start of every subset sequence with s = log(v[K]+1e-5) - log(vbg) (Motif::calculateLogS,
+ * src/init/Motif.cpp:471-483; the table is built on the host with the same libm logf as the reference).
+ * zoops[n] = max score, z[n] = first argmax (strict '>' scan, ScoreSeqSet.cpp:59-62), mops (nullable) =
+ * all window scores, sum(L_n - W + 1) floats in sequence order.
+ */
+int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
+                       const float* v_all, const float* vbg_all, float* zoops, uint64_t* z, float* mops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAMM_B200_H_ */
