@@ -2,6 +2,7 @@
 // one CUDA stream per EM object, launches, scalar read-back. No CPU fallback: every compute entry point needs a device.
 #include "../../include/bamm_b200.h"
 #include "kernels.cuh"
+#include "packed.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -41,9 +42,16 @@ struct bamm_seqset {
     uint64_t* d_ppos = nullptr;
     uint64_t* d_pkmer = nullptr;
     std::vector<uint64_t> h_off;
-    std::map<int, IndexArray> index;   // per order K
+    std::map<int, IndexArray> index;   // per order K (built on demand: generic path, get_index, count_kmers)
     std::mutex mu;
     int sm_count = 148;
+    // 2-bit packed path (A == 4): per-sequence kind (0 irregular, 1 regular, 2 regular with the structural N)
+    std::vector<uint8_t> h_kind;
+    uint8_t* d_kind = nullptr;
+    PackedSeq* d_pseq = nullptr;
+    unsigned long long* d_words = nullptr;
+    uint64_t nwords = 0, nregular = 0;
+    std::map<int, uint16_t*> ypatch;   // per order K: [nseq][K+1] k-mer index at mid..mid+K
 };
 
 struct bamm_em {
@@ -60,9 +68,20 @@ struct bamm_em {
     uint64_t nsub = 0, rsize = 0, nseq_global = 0;
     uint64_t model_size = 0, bg_size = 0;
     ModelDims dims;
-    bool smem_tables = true;    // tables fit in shared memory
+    bool smem_tables = true;    // generic path: tables fit in shared memory
     int grid_e = 0, grid_m = 0, block = 512;
     size_t smem_e = 0, smem_m = 0;
+    // the subset is split into a packed list (regular 4-letter sequences) and a generic list (everything else)
+    uint32_t ngen = 0, npk = 0;
+    uint32_t* d_gen_ids = nullptr;  uint64_t* d_gen_roff = nullptr;
+    uint32_t* d_pk_ids = nullptr;   uint64_t* d_pk_roff = nullptr;
+    Plan plan;                  // tuple plan of the packed E-step
+    int nch = 0;                // register chunks of the packed E-step (32 windows each)
+    float* d_tab = nullptr;     // tuple table [C][Zn]
+    uint16_t* d_ypatch = nullptr;   // owned by the seqset
+    int grid_pe = 0, block_pe = 1024, grid_pm = 0;
+    size_t smem_pe = 0, smem_pm = 0;
+    uint32_t nparts = 1;
     // device
     uint32_t* d_seq_ids = nullptr;
     uint64_t* d_r_off = nullptr;
@@ -148,6 +167,41 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
         CUS(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CUS(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
     }
+    s->h_kind.assign(nseq, 0);
+    if (A == 4 && nseq) {
+        // classify + pack on the device (no host pass over the bases)
+        uint32_t* d_cover = nullptr;
+        CUS(cudaMalloc(&s->d_kind, nseq));
+        CUS(cudaMalloc(&d_cover, nseq * sizeof(uint32_t)));
+        CUS(cudaMemset(d_cover, 0, nseq * sizeof(uint32_t)));
+        k_classify<<<s->sm_count * 8, 256>>>(s->d_codes, s->d_off, nseq, s->d_kind);
+        if (npatch) k_check_patches<<<(unsigned)((npatch + 255) / 256), 256>>>(s->d_ppos, npatch, s->d_off, nseq, s->d_kind, d_cover);
+        k_finish_kinds<<<(unsigned)((nseq + 255) / 256), 256>>>(s->d_off, nseq, d_cover, s->d_kind);
+        cudaError_t ec = cudaMemcpy(s->h_kind.data(), s->d_kind, nseq, cudaMemcpyDeviceToHost);
+        cudaFree(d_cover);
+        CUS(ec);
+        std::vector<PackedSeq> ps(nseq);
+        uint64_t w = 0;
+        for (uint64_t n = 0; n < nseq; n++) {
+            PackedSeq q; q.word_off = 0; q.L = 0; q.mid = 0xffffffffu;
+            if (s->h_kind[n]) {
+                const uint64_t L = offsets[n + 1] - offsets[n];
+                q.word_off = w + 1; q.L = (uint32_t)L; q.mid = s->h_kind[n] == 2 ? (uint32_t)((L - 1) / 2) : 0xffffffffu;
+                w += (L + 31) / 32 + 3;                       // pad | data | pad pad
+                s->nregular++;
+            }
+            ps[n] = q;
+        }
+        s->nwords = w;
+        if (s->nregular) {
+            CUS(cudaMalloc(&s->d_pseq, nseq * sizeof(PackedSeq)));
+            CUS(cudaMemcpy(s->d_pseq, ps.data(), nseq * sizeof(PackedSeq), cudaMemcpyHostToDevice));
+            CUS(cudaMalloc(&s->d_words, w * sizeof(unsigned long long)));
+            k_pack<<<s->sm_count * 8, 256>>>(s->d_codes, s->d_off, nseq, s->d_kind, s->d_pseq, s->d_words);
+            CUS(cudaGetLastError());
+            CUS(cudaDeviceSynchronize());
+        }
+    }
 #undef CUS
     *out = s;
     return BAMM_OK;
@@ -157,6 +211,8 @@ extern "C" void bamm_seqset_destroy(bamm_seqset* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     for (auto& kv : s->index) cudaFree(kv.second.d);
+    for (auto& kv : s->ypatch) cudaFree(kv.second);
+    cudaFree(s->d_kind); cudaFree(s->d_pseq); cudaFree(s->d_words);
     cudaFree(s->d_codes); cudaFree(s->d_off); cudaFree(s->d_ppos); cudaFree(s->d_pkmer);
     delete s;
 }
@@ -201,6 +257,27 @@ extern "C" int bamm_seqset_index(bamm_seqset* s, int K) {
     REQUIRE(s, "seqset is NULL");
     std::lock_guard<std::mutex> g(s->mu);
     return seqset_index_locked(s, K, nullptr);
+}
+
+// per-order k-mer index at the K+1 positions after the structural N of every kind-2 sequence
+static int seqset_ypatch_locked(bamm_seqset* s, int K, uint16_t** out) {
+    auto it = s->ypatch.find(K);
+    if (it != s->ypatch.end()) { *out = it->second; return BAMM_OK; }
+    const uint64_t Yn = ipow_u64(4, K + 1);
+    REQUIRE(Yn <= 65536, "order too high for the packed path");
+    uint16_t* d = nullptr;
+    CU(cudaSetDevice(s->device));
+    const uint64_t bytes = (s->nseq ? s->nseq : 1) * (uint64_t)(K + 1) * sizeof(uint16_t);
+    CU(cudaMalloc(&d, bytes));
+    CU(cudaMemset(d, 0, bytes));
+    if (s->npatch) {
+        k_make_ypatch<<<(unsigned)((s->npatch + 255) / 256), 256>>>(s->d_ppos, s->d_pkmer, s->npatch, s->d_off, s->nseq, s->d_kind, K, Yn, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { cudaFree(d); return fail(BAMM_E_CUDA, "ypatch build failed: %s", cudaGetErrorString(e)); }
+    }
+    s->ypatch[K] = d;
+    *out = d;
+    return BAMM_OK;
 }
 
 extern "C" int bamm_seqset_get_index(bamm_seqset* s, int K, uint32_t* out) {
@@ -261,6 +338,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     if (!em) return;
     cudaSetDevice(em->device);
     if (em->stream) cudaStreamSynchronize(em->stream);
+    cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab);
     cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_v);
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
     if (em->own_xbuf) cudaFree(em->d_xbuf);
@@ -272,6 +350,8 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     if (em->stream) cudaStreamDestroy(em->stream);
     delete em;
 }
+
+static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only);
 
 template <typename K> static int max_smem_optin(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : -1;
@@ -286,20 +366,44 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     REQUIRE(K >= 0 && K <= 10 && K_bg_model >= 0 && K_bg_model <= 10, "order out of range");
     if (!subset) nsub = s->nseq;
     REQUIRE(nsub < (1ull << 32), "subset too large");
-    IndexArray* ia;
-    { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
-    REQUIRE(ia->Yn * (uint64_t)W < (1ull << 31), "table too large");
+    const uint64_t Yn64 = ipow_u64((uint64_t)s->A, K + 1);
+    REQUIRE(Yn64 * (uint64_t)W < (1ull << 31), "table too large");
     bamm_em* em = new (std::nothrow) bamm_em();
     if (!em) return fail(BAMM_E_NOMEM, "host allocation failed");
     em->ss = s; em->device = s->device; em->W = W; em->K = K; em->K_bg_model = K_bg_model;
     em->K_bg = K_bg_model < K ? K_bg_model : K; em->A = s->A;
-    em->Yn = (uint32_t)ia->Yn; em->nbin = em->Yn * (uint32_t)W; em->nsub = nsub; em->nseq_global = nsub;
+    em->Yn = (uint32_t)Yn64; em->nbin = em->Yn * (uint32_t)W; em->nsub = nsub; em->nseq_global = nsub;
     fill_dims(em->dims, s->A, K, W, em->K_bg);
     em->model_size = em->dims.voff[K + 1];
     em->bg_size = em->dims.bgoff[K_bg_model + 1];
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, em->device);
+    const int sms = s->sm_count;
+    const size_t table_bytes = (size_t)em->nbin * sizeof(float);
+    // ---- packed-path plan: tuple size T minimising lookups per window under the shared-memory budget
+    const size_t queue_bytes = (size_t)(512 / 32) * QCAP * sizeof(QEntry);
+    bool packed_ok = s->A == 4 && s->nregular > 0 && W + K <= 32 && Yn64 <= 65536 &&
+                     ((table_bytes + 15) & ~(size_t)15) + queue_bytes <= (size_t)max_optin && !getenv("BAMM_NO_PACKED");
+    if (packed_ok) {
+        int bestT = 1, bestC = W; size_t best_bytes = table_bytes;
+        int forceT = getenv("BAMM_TUPLE") ? atoi(getenv("BAMM_TUPLE")) : 0;
+        for (int T = 1; T <= 8; T++) {
+            const int C = (W + T - 1) / T;
+            if (K + C * T > 32 || K + T > 13 || C > 16) continue;
+            const size_t bytes = (size_t)C * ((size_t)1 << (2 * (K + T))) * sizeof(float);
+            if (bytes > (size_t)max_optin - 1024) continue;
+            if (forceT ? T == forceT : (C < bestC || (C == bestC && bytes < best_bytes))) { bestT = T; bestC = C; best_bytes = bytes; }
+        }
+        em->plan.W = W; em->plan.K = K; em->plan.T = bestT; em->plan.C = bestC;
+        em->plan.Yn = em->Yn; em->plan.Zn = (uint32_t)1 << (2 * (K + bestT)); em->plan.q = 0.3f;
+        em->smem_pe = best_bytes;
+    }
+    // ---- split the subset
     em->h_r_off.resize(nsub + 1);
-    std::vector<uint32_t> ids(nsub);
+    std::vector<uint32_t> ids(nsub), gen_ids, pk_ids;
+    std::vector<uint64_t> gen_roff, pk_roff;
     em->h_r_off[0] = 0;
+    uint64_t max_lw1_pk = 0;
     for (uint64_t i = 0; i < nsub; i++) {
         const uint64_t n = subset ? subset[i] : i;
         if (n >= s->nseq) { delete em; return fail(BAMM_E_INVALID, "subset[%llu]=%llu out of range", (unsigned long long)i, (unsigned long long)n); }
@@ -307,19 +411,33 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         if (L < (uint64_t)W) { delete em; return fail(BAMM_E_INVALID, "sequence %llu is shorter (L=%llu) than the motif (W=%d)", (unsigned long long)n, (unsigned long long)L, W); }
         ids[i] = (uint32_t)n;
         em->h_r_off[i + 1] = em->h_r_off[i] + L;
+        if (packed_ok && s->h_kind[n]) {
+            pk_ids.push_back((uint32_t)n); pk_roff.push_back(em->h_r_off[i]);
+            if (L - W + 1 > max_lw1_pk) max_lw1_pk = L - W + 1;
+        } else {
+            gen_ids.push_back((uint32_t)n); gen_roff.push_back(em->h_r_off[i]);
+        }
     }
     em->rsize = em->h_r_off[nsub];
+    em->ngen = (uint32_t)gen_ids.size(); em->npk = (uint32_t)pk_ids.size();
+    em->nch = max_lw1_pk <= 128 ? 4 : max_lw1_pk <= 256 ? 8 : max_lw1_pk <= 512 ? 16 : 32;
+    IndexArray* ia = nullptr;
+    if (em->ngen) { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) { delete em; return rc; } }
+    if (em->npk)  { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_ypatch_locked(s, K, &em->d_ypatch); if (rc) { delete em; return rc; } }
 #define CUE(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { int code_ = e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA; \
     fail(code_, "%s failed: %s", #call, cudaGetErrorString(e2_)); bamm_em_destroy(em); return code_; } } while (0)
     CUE(cudaSetDevice(em->device));
     CUE(cudaStreamCreateWithFlags(&em->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; i++) CUE(cudaEventCreate(&em->ev[i]));
-    if (subset) {
-        CUE(cudaMalloc(&em->d_seq_ids, (nsub ? nsub : 1) * sizeof(uint32_t)));
-        CUE(cudaMemcpy(em->d_seq_ids, ids.data(), nsub * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    }
-    CUE(cudaMalloc(&em->d_r_off, (nsub + 1) * sizeof(uint64_t)));
-    CUE(cudaMemcpy(em->d_r_off, em->h_r_off.data(), (nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    auto upload = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+        if (e == cudaSuccess && bytes) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+        return e;
+    };
+    CUE(upload(gen_ids.data(), gen_ids.size() * 4, (void**)&em->d_gen_ids));
+    CUE(upload(gen_roff.data(), gen_roff.size() * 8, (void**)&em->d_gen_roff));
+    CUE(upload(pk_ids.data(), pk_ids.size() * 4, (void**)&em->d_pk_ids));
+    CUE(upload(pk_roff.data(), pk_roff.size() * 8, (void**)&em->d_pk_roff));
     CUE(cudaMalloc(&em->d_r, (em->rsize ? em->rsize : 1) * sizeof(float)));
     CUE(cudaMalloc(&em->d_s, (uint64_t)em->nbin * sizeof(float)));
     CUE(cudaMalloc(&em->d_v, em->model_size * sizeof(float)));
@@ -332,30 +450,54 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     CUE(cudaMalloc(&em->d_vdiff, sizeof(float)));
     CUE(cudaMallocHost(&em->h_scal, 2 * sizeof(unsigned long long)));
     CUE(cudaMallocHost(&em->h_vdiff, sizeof(float)));
-    // launch geometry: persistent grid, one CTA of 512 threads per SM slot
-    const size_t table_bytes = (size_t)em->nbin * sizeof(float);
-    int max_optin = 0;
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, em->device);
-    em->smem_tables = table_bytes <= (size_t)max_optin;
-    const int sms = s->sm_count;
-    if (em->smem_tables) {
-        em->smem_e = table_bytes; em->smem_m = table_bytes;
-        int per_sm = (int)((size_t)(max_optin + 1024) / (table_bytes + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 4) per_sm = 4;             // 4 x 512 threads = 2048 = the SM's thread limit
-        em->grid_e = em->grid_m = sms * per_sm;
-        bool ok = true;
-        if (ia->bytes == 2) { ok &= !max_smem_optin(k_estep<uint16_t, true>, table_bytes); ok &= !max_smem_optin(k_mstep<uint16_t, true>, table_bytes); }
-        else                { ok &= !max_smem_optin(k_estep<uint32_t, true>, table_bytes); ok &= !max_smem_optin(k_mstep<uint32_t, true>, table_bytes); }
-        if (!ok) { fail(BAMM_E_CUDA, "cannot opt in to %zu bytes of shared memory", table_bytes); bamm_em_destroy(em); return BAMM_E_CUDA; }
-        CUE(cudaMalloc(&em->d_part, (uint64_t)em->grid_m * em->nbin * sizeof(unsigned long long)));
-    } else {
-        em->smem_e = em->smem_m = 0;
-        em->grid_e = em->grid_m = sms * 4;
-        CUE(cudaMalloc(&em->d_part, (uint64_t)em->nbin * sizeof(unsigned long long)));
+    em->nparts = 1;
+    // ---- generic path geometry (only when some sequence needs it): persistent grid of 512-thread CTAs
+    if (em->ngen) {
+        em->smem_tables = table_bytes <= (size_t)max_optin;
+        if (em->smem_tables) {
+            em->smem_e = table_bytes; em->smem_m = table_bytes;
+            int per_sm = (int)((size_t)(max_optin + 1024) / (table_bytes + 1024));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 4) per_sm = 4;             // 4 x 512 threads = 2048 = the SM's thread limit
+            em->grid_e = em->grid_m = sms * per_sm;
+            bool ok = true;
+            if (ia->bytes == 2) { ok &= !max_smem_optin(k_estep<uint16_t, true>, table_bytes); ok &= !max_smem_optin(k_mstep<uint16_t, true>, table_bytes); }
+            else                { ok &= !max_smem_optin(k_estep<uint32_t, true>, table_bytes); ok &= !max_smem_optin(k_mstep<uint32_t, true>, table_bytes); }
+            if (!ok) { fail(BAMM_E_CUDA, "cannot opt in to %zu bytes of shared memory", table_bytes); bamm_em_destroy(em); return BAMM_E_CUDA; }
+            em->nparts = (uint32_t)em->grid_m;
+        } else {
+            em->smem_e = em->smem_m = 0;
+            em->grid_e = em->grid_m = sms * 4;
+        }
     }
+    // ---- packed path geometry
+    if (em->npk) {
+        CUE(cudaMalloc(&em->d_tab, em->smem_pe));
+        em->block_pe = 1024;                        // 64 registers/thread => 1024 resident threads per SM: one CTA per SM
+        em->grid_pe = sms;
+        bool ok = true;
+        ok = !estep_packed_dispatch(em, nullptr, nullptr, true);
+        em->smem_pm = ((table_bytes + 15) & ~(size_t)15) + queue_bytes;
+        ok = ok && !max_smem_optin(k_mstep_packed, em->smem_pm);
+        if (!ok) { fail(BAMM_E_CUDA, "cannot opt in to shared memory for the packed kernels"); bamm_em_destroy(em); return BAMM_E_CUDA; }
+        int per_sm_m = (int)((size_t)(max_optin + 1024) / (em->smem_pm + 1024));
+        if (per_sm_m < 1) per_sm_m = 1;
+        if (per_sm_m > 4) per_sm_m = 4;
+        em->grid_pm = sms * per_sm_m;
+        if ((uint32_t)em->grid_pm > em->nparts) em->nparts = (uint32_t)em->grid_pm;
+    }
+    CUE(cudaMalloc(&em->d_part, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long)));
 #undef CUE
     *out = em;
+    return BAMM_OK;
+}
+
+static int launch_tuple_table(bamm_em* em) {
+    if (!em->npk) return BAMM_OK;
+    const Plan& pl = em->plan;
+    const uint32_t total = (uint32_t)pl.C * pl.Zn;
+    k_make_tuple_table<<<(total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184, 256, 0, em->stream>>>(em->d_s, pl.W, pl.K, pl.T, pl.C, pl.Yn, em->d_tab);
+    CU(cudaGetLastError());
     return BAMM_OK;
 }
 
@@ -368,39 +510,74 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
     CU(cudaMemcpyAsync(em->d_alpha, alpha, (uint64_t)(em->K + 1) * em->W * sizeof(float), cudaMemcpyHostToDevice, em->stream));
     k_make_s<<<64, 256, 0, em->stream>>>(em->dims, em->d_v, em->d_vbg, em->d_s, em->d_vK_prev);
     CU(cudaGetLastError());
+    { int rc = launch_tuple_table(em); if (rc) return rc; }
     CU(cudaStreamSynchronize(em->stream));
     em->q = q; em->model_set = true; em->s_valid = true; em->r_valid = false; em->llh = 0.0f;
     return BAMM_OK;
 }
 
+// k_estep_packed is instantiated for every lookup count C the planner can choose; optin_only sets the
+// shared-memory attribute instead of launching.
+template <int C> static int estep_packed_one(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only) {
+    if (optin_only) return max_smem_optin(k_estep_packed<C>, em->smem_pe);
+    k_estep_packed<C><<<em->grid_pe, em->block_pe, em->smem_pe, em->stream>>>(*pv, *pl, em->d_tab, em->d_s, em->d_r, em->d_xbuf + em->nbin);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only) {
+    switch (em->plan.C) {
+#define BAMM_CASE(c) case c: return estep_packed_one<c>(em, pv, pl, optin_only);
+        BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
+        BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
+#undef BAMM_CASE
+        default: return -1;
+    }
+}
+
 static SubsetView view_of(const bamm_em* em) {
-    SubsetView sv; sv.seq_off = em->ss->d_off; sv.seq_ids = em->d_seq_ids; sv.r_off = em->d_r_off; sv.nsub = (uint32_t)em->nsub;
+    SubsetView sv; sv.seq_off = em->ss->d_off; sv.seq_ids = em->d_gen_ids; sv.r_off = em->d_gen_roff; sv.nsub = em->ngen;
     return sv;
+}
+static PackedView pview_of(const bamm_em* em) {
+    PackedView pv; pv.words = em->ss->d_words; pv.seqs = em->ss->d_pseq; pv.ypatch = em->d_ypatch;
+    pv.seq_ids = em->d_pk_ids; pv.r_off = em->d_pk_roff; pv.nlist = em->npk;
+    return pv;
 }
 
 static int launch_estep(bamm_em* em) {
-    IndexArray& ia = em->ss->index[em->K];
     unsigned long long* scal = em->d_xbuf + em->nbin;
     CU(cudaMemsetAsync(scal, 0, 2 * sizeof(unsigned long long), em->stream));
-    SubsetView sv = view_of(em);
-    if (em->nsub == 0) return BAMM_OK;
-    if (ia.bytes == 2) {
-        if (em->smem_tables) k_estep<uint16_t, true><<<em->grid_e, em->block, em->smem_e, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
-        else                 k_estep<uint16_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
-    } else {
-        if (em->smem_tables) k_estep<uint32_t, true><<<em->grid_e, em->block, em->smem_e, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
-        else                 k_estep<uint32_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+    if (em->npk) {
+        PackedView pv = pview_of(em);
+        Plan pl = em->plan; pl.q = em->q;
+        if (estep_packed_dispatch(em, &pv, &pl, false)) return fail(BAMM_E_CUDA, "packed E-step launch failed");
+        CU(cudaGetLastError());
     }
-    CU(cudaGetLastError());
+    if (em->ngen) {
+        IndexArray& ia = em->ss->index[em->K];
+        SubsetView sv = view_of(em);
+        if (ia.bytes == 2) {
+            if (em->smem_tables) k_estep<uint16_t, true><<<em->grid_e, em->block, em->smem_e, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+            else                 k_estep<uint16_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+        } else {
+            if (em->smem_tables) k_estep<uint32_t, true><<<em->grid_e, em->block, em->smem_e, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+            else                 k_estep<uint32_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+        }
+        CU(cudaGetLastError());
+    }
     return BAMM_OK;
 }
 
 static int launch_mstep_accumulate(bamm_em* em) {
-    IndexArray& ia = em->ss->index[em->K];
-    SubsetView sv = view_of(em);
-    const uint32_t nparts = em->smem_tables ? (uint32_t)em->grid_m : 1u;
-    CU(cudaMemsetAsync(em->d_part, 0, (uint64_t)nparts * em->nbin * sizeof(unsigned long long), em->stream));
-    if (em->nsub) {
+    CU(cudaMemsetAsync(em->d_part, 0, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long), em->stream));
+    if (em->npk) {
+        PackedView pv = pview_of(em);
+        Plan pl = em->plan; pl.q = em->q;
+        k_mstep_packed<<<em->grid_pm, 512, em->smem_pm, em->stream>>>(pv, pl, em->d_r, em->d_part);
+        CU(cudaGetLastError());
+    }
+    if (em->ngen) {
+        IndexArray& ia = em->ss->index[em->K];
+        SubsetView sv = view_of(em);
         if (ia.bytes == 2) {
             if (em->smem_tables) k_mstep<uint16_t, true><<<em->grid_m, em->block, em->smem_m, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
             else                 k_mstep<uint16_t, false><<<em->grid_m, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
@@ -414,8 +591,7 @@ static int launch_mstep_accumulate(bamm_em* em) {
 }
 
 static int launch_mstep_reduce(bamm_em* em) {
-    const uint32_t nparts = em->smem_tables ? (uint32_t)em->grid_m : 1u;
-    k_reduce_parts<<<(em->nbin + 255) / 256, 256, 0, em->stream>>>(em->d_part, nparts, em->nbin, em->d_xbuf);
+    k_reduce_parts<<<(em->nbin + 255) / 256, 256, 0, em->stream>>>(em->d_part, em->nparts, em->nbin, em->d_xbuf);
     CU(cudaGetLastError());
     return BAMM_OK;
 }
@@ -428,7 +604,7 @@ static int launch_mstep_local(bamm_em* em) {
 static int launch_update(bamm_em* em) {
     k_update_model<<<1, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha, em->d_s, em->d_vdiff);
     CU(cudaGetLastError());
-    return BAMM_OK;
+    return launch_tuple_table(em);
 }
 
 static int read_scalars(bamm_em* em, bool want_vdiff) {
@@ -548,7 +724,6 @@ static int launch_iteration(bamm_em* em, cudaEvent_t* ev4) {
     if (ev4) CU(cudaEventRecord(ev4[0], em->stream));
     int rc = launch_estep(em); if (rc) return rc;
     if (ev4) CU(cudaEventRecord(ev4[1], em->stream));
-    IndexArray& ia = em->ss->index[em->K]; (void)ia;
     rc = launch_mstep_accumulate(em); if (rc) return rc;
     if (ev4) CU(cudaEventRecord(ev4[2], em->stream));
     rc = launch_mstep_reduce(em); if (rc) return rc;
@@ -657,11 +832,12 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
     REQUIRE(s && v_all && vbg_all && zoops && z, "NULL argument");
     REQUIRE(W >= 1 && W <= 32, "motif width W=%d not in [1,32]", W);
     if (!subset) nsub = s->nseq;
-    IndexArray* ia;
-    { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
+    REQUIRE(K >= 0 && K <= 10, "order K=%d not in [0,10]", K);
     const int K_bg = K_bg_model < K ? K_bg_model : K;
     ModelDims d; fill_dims(d, s->A, K, W, K_bg);
-    const uint32_t Yn = (uint32_t)ia->Yn, nbin = Yn * (uint32_t)W;
+    const uint64_t ia_Yn = ipow_u64((uint64_t)s->A, K + 1);
+    REQUIRE(ia_Yn * (uint64_t)W < (1ull << 31), "table too large");
+    const uint32_t Yn = (uint32_t)ia_Yn, nbin = Yn * (uint32_t)W;
     // Motif::calculateLogS (Motif.cpp:471-483) on the host: same libm logf as the reference; [j][y] layout
     std::vector<float> slog(nbin);
     {
@@ -672,48 +848,68 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
             for (int j = 0; j < W; j++) slog[(uint64_t)j * Yn + y] = logf(vK[(uint64_t)y * W + j] + 1e-5f) - lb;
         }
     }
-    std::vector<uint32_t> ids(nsub);
+    std::vector<uint32_t> gen_ids, gen_out, pk_ids, pk_out;
     std::vector<uint64_t> moff(nsub + 1, 0);
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+    const size_t tb = (size_t)nbin * 4;
+    const bool smem = tb <= (size_t)max_optin;
+    const bool packed_ok = s->A == 4 && s->nregular > 0 && W + K <= 32 && ia_Yn <= 65536 && smem && !getenv("BAMM_NO_PACKED");
     for (uint64_t i = 0; i < nsub; i++) {
         const uint64_t n = subset ? subset[i] : i;
         REQUIRE(n < s->nseq, "subset index out of range");
         const uint64_t L = s->h_off[n + 1] - s->h_off[n];
         REQUIRE(L >= (uint64_t)W, "sequence %llu is shorter than the motif", (unsigned long long)n);
-        ids[i] = (uint32_t)n; moff[i + 1] = moff[i] + (L - W + 1);
+        moff[i + 1] = moff[i] + (L - W + 1);
+        if (packed_ok && s->h_kind[n]) { pk_ids.push_back((uint32_t)n); pk_out.push_back((uint32_t)i); }
+        else { gen_ids.push_back((uint32_t)n); gen_out.push_back((uint32_t)i); }
     }
+    IndexArray* ia = nullptr;
+    uint16_t* d_yp = nullptr;
+    if (!gen_ids.empty()) { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
+    if (!pk_ids.empty())  { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_ypatch_locked(s, K, &d_yp); if (rc) return rc; }
     CU(cudaSetDevice(s->device));
     cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     float *d_s = nullptr, *d_zoops = nullptr, *d_mops = nullptr; unsigned long long* d_z = nullptr;
-    uint32_t* d_ids = nullptr; uint64_t* d_moff = nullptr;
+    uint32_t *d_gids = nullptr, *d_gout = nullptr, *d_pids = nullptr, *d_pout = nullptr; uint64_t* d_moff = nullptr;
     int rc = BAMM_OK;
 #define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
     {
         CUX(cudaMalloc(&d_s, (uint64_t)nbin * 4));
         CUX(cudaMalloc(&d_zoops, (nsub ? nsub : 1) * 4));
         CUX(cudaMalloc(&d_z, (nsub ? nsub : 1) * 8));
-        CUX(cudaMalloc(&d_ids, (nsub ? nsub : 1) * 4));
+        CUX(cudaMalloc(&d_gids, (gen_ids.size() ? gen_ids.size() : 1) * 4));
+        CUX(cudaMalloc(&d_gout, (gen_ids.size() ? gen_ids.size() : 1) * 4));
+        CUX(cudaMalloc(&d_pids, (pk_ids.size() ? pk_ids.size() : 1) * 4));
+        CUX(cudaMalloc(&d_pout, (pk_ids.size() ? pk_ids.size() : 1) * 4));
         CUX(cudaMalloc(&d_moff, (nsub + 1) * 8));
         if (mops) CUX(cudaMalloc(&d_mops, (moff[nsub] ? moff[nsub] : 1) * 4));
         CUX(cudaMemcpyAsync(d_s, slog.data(), (uint64_t)nbin * 4, cudaMemcpyHostToDevice, st));
-        CUX(cudaMemcpyAsync(d_ids, ids.data(), nsub * 4, cudaMemcpyHostToDevice, st));
+        CUX(cudaMemcpyAsync(d_gids, gen_ids.data(), gen_ids.size() * 4, cudaMemcpyHostToDevice, st));
+        CUX(cudaMemcpyAsync(d_gout, gen_out.data(), gen_out.size() * 4, cudaMemcpyHostToDevice, st));
+        CUX(cudaMemcpyAsync(d_pids, pk_ids.data(), pk_ids.size() * 4, cudaMemcpyHostToDevice, st));
+        CUX(cudaMemcpyAsync(d_pout, pk_out.data(), pk_out.size() * 4, cudaMemcpyHostToDevice, st));
         CUX(cudaMemcpyAsync(d_moff, moff.data(), (nsub + 1) * 8, cudaMemcpyHostToDevice, st));
-        SubsetView sv; sv.seq_off = s->d_off; sv.seq_ids = subset ? d_ids : nullptr; sv.r_off = nullptr; sv.nsub = (uint32_t)nsub;
-        int max_optin = 0;
-        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
-        const size_t tb = (size_t)nbin * 4;
-        const bool smem = tb <= (size_t)max_optin;
         int per_sm = smem ? (int)((size_t)(max_optin + 1024) / (tb + 1024)) : 4;
         if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
         const int grid = s->sm_count * per_sm;
-        if (nsub) {
+        if (!pk_ids.empty()) {
+            PackedView pv; pv.words = s->d_words; pv.seqs = s->d_pseq; pv.ypatch = d_yp; pv.seq_ids = d_pids; pv.r_off = nullptr; pv.nlist = (uint32_t)pk_ids.size();
+            Plan pl; pl.W = W; pl.K = K; pl.T = 1; pl.C = W; pl.Yn = Yn; pl.Zn = Yn; pl.q = 0.f;
+            CUX(cudaFuncSetAttribute(k_score_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
+            k_score_packed<<<grid, 512, tb, st>>>(pv, pl, d_moff, d_s, d_zoops, d_z, d_mops, d_pout);
+            CUX(cudaGetLastError());
+        }
+        if (!gen_ids.empty()) {
+            SubsetView sv; sv.seq_off = s->d_off; sv.seq_ids = d_gids; sv.r_off = nullptr; sv.nsub = (uint32_t)gen_ids.size();
             if (ia->bytes == 2) {
                 if (smem) { CUX(cudaFuncSetAttribute(k_score<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
-                            k_score<uint16_t, true><<<grid, 512, tb, st>>>((const uint16_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops); }
-                else        k_score<uint16_t, false><<<grid, 512, 0, st>>>((const uint16_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops);
+                            k_score<uint16_t, true><<<grid, 512, tb, st>>>((const uint16_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops, d_gout); }
+                else        k_score<uint16_t, false><<<grid, 512, 0, st>>>((const uint16_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops, d_gout);
             } else {
                 if (smem) { CUX(cudaFuncSetAttribute(k_score<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
-                            k_score<uint32_t, true><<<grid, 512, tb, st>>>((const uint32_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops); }
-                else        k_score<uint32_t, false><<<grid, 512, 0, st>>>((const uint32_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops);
+                            k_score<uint32_t, true><<<grid, 512, tb, st>>>((const uint32_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops, d_gout); }
+                else        k_score<uint32_t, false><<<grid, 512, 0, st>>>((const uint32_t*)ia->d, sv, d_moff, W, Yn, d_s, d_zoops, d_z, d_mops, d_gout);
             }
             CUX(cudaGetLastError());
         }
@@ -724,7 +920,7 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
     }
 done:
 #undef CUX
-    cudaFree(d_s); cudaFree(d_zoops); cudaFree(d_z); cudaFree(d_ids); cudaFree(d_moff); cudaFree(d_mops);
+    cudaFree(d_s); cudaFree(d_zoops); cudaFree(d_z); cudaFree(d_gids); cudaFree(d_gout); cudaFree(d_pids); cudaFree(d_pout); cudaFree(d_moff); cudaFree(d_mops);
     cudaStreamDestroy(st);
     return rc;
 }

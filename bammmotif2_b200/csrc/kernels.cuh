@@ -346,7 +346,7 @@ template <typename YT, bool SMEM>
 __global__ void __launch_bounds__(512)
 k_score(const YT* __restrict__ Y, SubsetView sv, const uint64_t* __restrict__ mops_off, int W, uint32_t Yn,
         const float* __restrict__ s_g, float* __restrict__ zoops, unsigned long long* __restrict__ z,
-        float* __restrict__ mops) {
+        float* __restrict__ mops, const uint32_t* __restrict__ out_idx /* list -> output slot, nullptr = identity */) {
     extern __shared__ float s_sh[];
     const float* s = s_g;
     if (SMEM) {
@@ -359,6 +359,7 @@ k_score(const YT* __restrict__ Y, SubsetView sv, const uint64_t* __restrict__ mo
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
     for (uint32_t i = warp; i < sv.nsub; i += nwarps) {
         const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : i;
+        const uint32_t oi = out_idx ? out_idx[i] : i;
         const uint64_t base = sv.seq_off[n], L = sv.seq_off[n + 1] - base;
         const uint64_t LW1 = L - W + 1;
         const YT* __restrict__ yn = Y + base;
@@ -373,7 +374,7 @@ k_score(const YT* __restrict__ Y, SubsetView sv, const uint64_t* __restrict__ mo
                 sc += s[(uint32_t)j * Yn + y];
             }
             if (p < LW1) {
-                if (mops) mops[mops_off[i] + p] = sc;
+                if (mops) mops[mops_off[oi] + p] = sc;
                 if (sc > best) { best = sc; bestp = p; }
             }
         }
@@ -384,7 +385,7 @@ k_score(const YT* __restrict__ Y, SubsetView sv, const uint64_t* __restrict__ mo
             const uint64_t op = __shfl_xor_sync(FULL, bestp, o);
             if (ob > best || (ob == best && op < bestp)) { best = ob; bestp = op; }
         }
-        if (lane == 0) { zoops[i] = best; z[i] = bestp; }
+        if (lane == 0) { zoops[oi] = best; z[oi] = bestp; }
     }
 }
 

@@ -1,0 +1,421 @@
+// packed.cuh — the fast path for the 4-letter alphabet: sequences as 2-bit packed base streams.
+//
+// Layout. A "regular" sequence (codes 1..4 everywhere, except optionally the structural N in the
+// middle of a both-strand sequence, Sequence.cpp:10-14) is stored as 64-bit words of 32 bases, FIRST base in the
+// most significant bits, preceded by one zero pad word and followed by two. The order-K k-mer index of the
+// reference, y(i) = sum_t c(i-t) 4^t (Sequence.cpp:35-41), is then literally a bit field of the stream: for a
+// window start p the 64-bit word  w = bases p-K .. p-K+31  gives  y(p+j) = (w >> (62-2K-2j)) & (4^(K+1)-1), and the
+// zero pad supplies the implicit leading 'A's of k-mers that start before the sequence does. No index array is read.
+//
+// E-step: tuple tables. T consecutive motif columns are folded into one lookup over the (K+T)-mer z that ends
+// at the tuple's last base:  tab[c][z] = prod_{t<T} s[cT+t][ (z >> 2(T-1-t)) & maskK ],  so a window costs
+// ceil(W/T) shared-memory lookups instead of W. Windows that cannot use tuples (the last W-1 truncated windows,
+// EM.cpp:167, and windows over the N whose k-mers hold rand() draws, Sequence.cpp:38) take an exact slow path
+// over the plain table in global memory.
+//
+// M-step: sparse. r is converted to 2^40 fixed point; every window whose r rounds to 0 contributes exactly
+// nothing, and in practice that is 60-95 % of all windows. Surviving (window, value) pairs are compacted into a
+// per-warp queue so that the scatter loop runs with full lanes.
+#pragma once
+#include "kernels.cuh"
+
+namespace bamm {
+
+struct PackedSeq {           // per regular sequence
+    uint64_t word_off;       // index of the sequence's FIRST DATA word (the pad word sits at word_off-1)
+    uint32_t L;              // stored length
+    uint32_t mid;            // position of the structural N, or 0xffffffff
+};
+
+struct PackedView {
+    const unsigned long long* words;   // packed stream
+    const PackedSeq* seqs;             // [nseq] (entries of irregular sequences are unused)
+    const uint16_t* ypatch;            // [nseq][K+1] order-K k-mer index at positions mid..mid+K (rand() draws inside)
+    const uint32_t* seq_ids;           // list -> seqset index
+    const uint64_t* r_off;             // list -> offset of the sequence's r
+    uint32_t nlist;
+};
+
+// ---- classification + packing (device side of bamm_seqset_create) --------------------------------------------------
+// kind: 0 irregular, 1 regular without N, 2 regular with exactly one 0 code at (L-1)/2, L odd
+__global__ void k_classify(const uint8_t* __restrict__ codes, const uint64_t* __restrict__ off, uint64_t nseq,
+                           uint8_t* __restrict__ kind) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t n = warp; n < nseq; n += nwarps) {
+        const uint64_t base = off[n], L = off[n + 1] - base;
+        const uint64_t mid = (L & 1) ? (L - 1) / 2 : ~0ull;
+        int bad = 0, zeros_at_mid = 0;
+        for (uint64_t i = lane; i < L; i += 32) {
+            const uint32_t c = codes[base + i];
+            if (c == 0) { if (i == mid) zeros_at_mid = 1; else bad = 1; }
+            else if (c > 4) bad = 1;
+        }
+        bad = __any_sync(FULL, bad);
+        zeros_at_mid = __any_sync(FULL, zeros_at_mid);
+        if (lane == 0) kind[n] = (bad || L == 0 || L >= 0xffffff00ull) ? 0 : (zeros_at_mid ? 2 : 1);
+    }
+}
+
+// every patch must sit at mid..mid+10 of a kind-2 sequence; anything else makes its sequence irregular.
+// cover[n] counts the patches that landed in the structural region.
+__global__ void k_check_patches(const uint64_t* __restrict__ ppos, uint64_t np, const uint64_t* __restrict__ off,
+                                uint64_t nseq, uint8_t* __restrict__ kind, uint32_t* __restrict__ cover) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const uint64_t pos = ppos[i];
+    uint64_t lo = 0, hi = nseq;                      // last n with off[n] <= pos
+    while (hi - lo > 1) { const uint64_t m = (lo + hi) >> 1; if (off[m] <= pos) lo = m; else hi = m; }
+    const uint64_t n = lo, L = off[n + 1] - off[n], local = pos - off[n];
+    const uint64_t mid = (L - 1) / 2;
+    if (kind[n] == 2 && local >= mid && local <= mid + 10) atomicAdd(&cover[n], 1u);
+    else kind[n] = 0;                                // benign race: every writer stores 0
+}
+
+__global__ void k_finish_kinds(const uint64_t* __restrict__ off, uint64_t nseq, const uint32_t* __restrict__ cover,
+                               uint8_t* __restrict__ kind) {
+    const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nseq) return;
+    if (kind[n] == 2) {
+        const uint64_t L = off[n + 1] - off[n], mid = (L - 1) / 2;
+        const uint64_t need = (L - mid < 11) ? L - mid : 11;      // positions mid..min(mid+10, L-1)
+        if (cover[n] != need) kind[n] = 0;                         // the caller did not patch the N: generic path
+    }
+}
+
+// one thread per output word; word index space is [0, total_words)
+__global__ void k_pack(const uint8_t* __restrict__ codes, const uint64_t* __restrict__ off, uint64_t nseq,
+                       const uint8_t* __restrict__ kind, const PackedSeq* __restrict__ seqs,
+                       unsigned long long* __restrict__ words) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t n = warp; n < nseq; n += nwarps) {
+        if (kind[n] == 0) continue;
+        const uint64_t base = off[n], L = off[n + 1] - base;
+        const uint64_t nw = (L + 31) / 32;
+        unsigned long long* dst = words + seqs[n].word_off;
+        if (lane == 0) { dst[-1] = 0ull; dst[nw] = 0ull; dst[nw + 1] = 0ull; }
+        for (uint64_t wi = lane; wi < nw; wi += 32) {
+            unsigned long long w = 0;
+            for (int b = 0; b < 32; b++) {
+                const uint64_t i = wi * 32 + b;
+                const uint32_t c = (i < L) ? codes[base + i] : 0u;
+                w = (w << 2) | (unsigned long long)(c ? c - 1 : 0);
+            }
+            dst[wi] = w;
+        }
+    }
+}
+
+__global__ void k_make_ypatch(const uint64_t* __restrict__ ppos, const uint64_t* __restrict__ pkmer, uint64_t np,
+                              const uint64_t* __restrict__ off, uint64_t nseq, const uint8_t* __restrict__ kind,
+                              int K, uint64_t Yn, uint16_t* __restrict__ ypatch) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const uint64_t pos = ppos[i];
+    uint64_t lo = 0, hi = nseq;
+    while (hi - lo > 1) { const uint64_t m = (lo + hi) >> 1; if (off[m] <= pos) lo = m; else hi = m; }
+    const uint64_t n = lo;
+    if (kind[n] != 2) return;
+    const uint64_t L = off[n + 1] - off[n], d = pos - off[n] - (L - 1) / 2;
+    if (d <= (uint64_t)K) ypatch[n * (uint64_t)(K + 1) + d] = (uint16_t)(pkmer[i] % Yn);
+}
+
+// ---- tables ------------------------------------------------------------------------------------------------------
+// tab[c][z] for c < C = ceil(W/T), z < 4^(K+T); s is the plain table [j][y]. LOG != 0: sums instead of products.
+__global__ void k_make_tuple_table(const float* __restrict__ s, int W, int K, int T, int C, uint32_t Yn,
+                                   float* __restrict__ tab) {
+    const uint32_t Zn = Yn << (2 * (T - 1));
+    const uint32_t maskK = Yn - 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)C * Zn; i += gridDim.x * blockDim.x) {
+        const uint32_t c = i / Zn, z = i % Zn;
+        float p = 1.0f;
+        for (int t = 0; t < T; t++) {
+            const int j = (int)c * T + t;
+            if (j < W) p *= s[(uint32_t)j * Yn + ((z >> (2 * (T - 1 - t))) & maskK)];
+        }
+        tab[i] = p;
+    }
+}
+
+// ---- window extraction ---------------------------------------------------------------------------------------------
+// 64-bit word holding bases b0 .. b0+31 of a sequence (b0 may be negative down to -32: pad word), from the three
+// stream words that surround the 32-window chunk starting at window p0 (prev = bases p0-32.., cur = p0.., next = p0+32..).
+__device__ __forceinline__ unsigned long long window_word(unsigned long long prev, unsigned long long cur,
+                                                          unsigned long long next, int rel /* b0 - p0, in [-32, 31] */) {
+    const unsigned long long hi = rel < 0 ? prev : cur;
+    const unsigned long long lo = rel < 0 ? cur : next;
+    const int sh = 2 * (rel < 0 ? rel + 32 : rel);          // 0..62
+    return sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+}
+
+__device__ __forceinline__ uint32_t field(unsigned long long w, int shift, uint32_t mask) {
+    return (uint32_t)(w >> shift) & mask;
+}
+
+struct Plan {                 // launch-invariant parameters of the packed kernels
+    int W, K, T, C;           // tuple size T, C = ceil(W/T) lookups per window
+    uint32_t Yn, Zn;          // 4^(K+1), 4^(K+T)
+    float q;
+};
+
+// ---- E-step --------------------------------------------------------------------------------------------------------
+// reference: EM::EStep, src/refinement/EM.cpp:139-200 (gather form). One warp per sequence, lanes =
+// window starts. The C tuple lookups of a window are fully unrolled (C is a template parameter); the 64-bit window
+// word is consumed from the top, 2T bits per lookup. Unnormalised posteriors go to r, the normaliser is reduced
+// over the warp, and a second sweep divides (the lines are still in L2).
+__device__ __forceinline__ float slow_window(const PackedView& pv, const Plan& pl, const float* __restrict__ tab,
+                                             const float* __restrict__ s_g, uint32_t n, unsigned long long w,
+                                             int p, int L, int mid) {
+    // exact product for a window that tuples cannot fully serve: whole tuples still come from the shared table,
+    // the truncated remainder and every tuple that touches the k-mers holding the N's rand() draws (positions
+    // mid..mid+K) are taken column by column from the plain table.
+    const int W = pl.W, K = pl.K, T = pl.T;
+    const int jmax = min(W - 1, L - W - p);
+    const uint32_t maskK = pl.Yn - 1, maskZ = pl.Zn - 1;
+    const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
+    float pr = 1.0f;
+    for (int c = 0, j0 = 0; j0 <= jmax; c++, j0 += T) {
+        const int e0 = p + j0, e1 = e0 + T - 1;
+        const bool whole = (j0 + T - 1 <= jmax) && !(over_n && e1 >= mid && e0 <= mid + K);
+        if (whole) {
+            pr *= tab[(uint32_t)c * pl.Zn + field(w, 64 - 2 * (K + T) - 2 * T * c, maskZ)];
+        } else {
+            for (int t = 0; t < T && j0 + t <= jmax; t++) {
+                const int j = j0 + t;
+                uint32_t y = field(w, 62 - 2 * K - 2 * j, maskK);
+                const int d = p + j - mid;
+                if (over_n && d >= 0 && d <= K) y = pv.ypatch[(uint64_t)n * (K + 1) + d];
+                pr *= __ldg(&s_g[(uint32_t)j * pl.Yn + y]);
+            }
+        }
+    }
+    return pr;
+}
+
+template <int C>
+__global__ void __launch_bounds__(1024, 1)
+k_estep_packed(PackedView pv, Plan pl, const float* __restrict__ tab_g /* [C][Zn] */, const float* __restrict__ s_g /* [W][Yn] */,
+               float* __restrict__ r, unsigned long long* __restrict__ scal) {
+    extern __shared__ float tab[];
+    for (uint32_t i = threadIdx.x; i < (uint32_t)C * pl.Zn; i += blockDim.x) tab[i] = tab_g[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const int W = pl.W, K = pl.K, T = pl.T;
+    const int zb = 2 * (K + T);                            // bits of one tuple index
+    const int roll = 2 * T;
+    const uint32_t zn_bytes = pl.Zn * 4u;
+    const char* tabc = reinterpret_cast<const char*>(tab);
+    long long llh_fx = 0, rsum_fx = 0;
+    const float one_minus_q = 1.0f - pl.q;
+    for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
+        const uint32_t n = pv.seq_ids[li];
+        const PackedSeq sq = pv.seqs[n];
+        const int L = (int)sq.L, LW1 = L - W + 1;
+        const int mid = (int)sq.mid;                       // -1 when there is no N
+        const unsigned long long* __restrict__ wd = pv.words + sq.word_off;
+        float* __restrict__ rn = r + pv.r_off[li];
+        const float pos = pl.q / (float)LW1;
+        const int tail0 = L - 2 * W + 2;                   // first truncated window (p > L-2W+1)
+        float sum = 0.0f;
+        for (int p0 = 0, ch = 0; p0 < LW1; p0 += 32, ch++) {
+            const int p = p0 + lane;
+            const unsigned long long w = window_word(wd[ch - 1], wd[ch], wd[ch + 1], lane - K);
+            uint32_t whi = (uint32_t)(w >> 32), wlo = (uint32_t)w;
+            float prod = 1.0f;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const uint32_t z4 = (whi >> (32 - zb)) << 2;
+                prod *= *reinterpret_cast<const float*>(tabc + (uint32_t)c * zn_bytes + z4);
+                whi = __funnelshift_l(wlo, whi, roll);
+                wlo <<= roll;
+            }
+            // chunks that hold windows tuples cannot serve (warp-uniform test): truncated tail / over the N
+            const bool chunk_slow = (p0 + 31 >= tail0) || (mid >= 0 && p0 <= mid + K && p0 + 31 + W - 1 >= mid);
+            if (chunk_slow) {
+                const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
+                if (p < LW1 && (p >= tail0 || over_n)) prod = slow_window(pv, pl, tab, s_g, n, w, p, L, mid);
+            }
+            if (p < LW1) {
+                const float val = prod * pos;
+                rn[L - W - p] = val;
+                sum += val;
+            }
+        }
+        sum = warp_sum(sum);
+        const float norm = one_minus_q + sum;
+        __syncwarp();
+        for (int k = lane; k < L; k += 32) rn[k] = (k < LW1) ? __fdiv_rn(rn[k], norm) : 0.0f;
+        if (lane == 0) {
+            llh_fx += __double2ll_rn((double)logf(norm) * SC_SCALE_D);
+            rsum_fx += __double2ll_rn((double)__fdiv_rn(sum, norm) * SC_SCALE_D);
+        }
+    }
+    if (lane == 0) {
+        if (llh_fx) atomicAdd(&scal[0], (unsigned long long)llh_fx);
+        if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);
+    }
+}
+
+// ---- M-step --------------------------------------------------------------------------------------------------------
+// reference: EM::MStep accumulation, src/refinement/EM.cpp:230-243 (gather form).
+// Pass 1 per warp: stream r (8 chunks of 32 windows in flight per lane), keep the windows whose r is at least half
+// a fixed-point unit (everything below rounds to exactly 0), compact them into the warp's ring queue.
+// Pass 2 whenever 32 entries are queued: each lane scatters one window's value into the W bins it touches.
+struct QEntry { uint32_t li, p; float rv; uint32_t pad; };
+constexpr int QCAP = 64;                       // ring entries per warp
+constexpr int M_UNROLL = 8;
+constexpr float FX_HALF_UNIT = 4.547473508864641e-13f;   // 2^-41: smallest r that rounds to a non-zero count
+
+__device__ __forceinline__ void scatter_window(const PackedView& pv, const Plan& pl, uint32_t* __restrict__ lo_sh,
+                                               unsigned long long* __restrict__ mypart, uint32_t li, int p, float rv) {
+    const int W = pl.W, K = pl.K;
+    const unsigned long long X = __float2ull_rn(rv * FX_SCALE_F);
+    if (X == 0) return;
+    const uint32_t n = pv.seq_ids[li];
+    const PackedSeq sq = pv.seqs[n];
+    const int L = (int)sq.L, mid = (int)sq.mid;
+    const unsigned long long* __restrict__ wd = pv.words + sq.word_off;
+    // word holding bases p-K .. p-K+31
+    const int b0 = p - K;
+    const int wi = b0 >> 5;                    // floor division (b0 >= -32)
+    const int bit = 2 * (b0 & 31);
+    const unsigned long long hi = wd[wi], lo = wd[wi + 1];
+    const unsigned long long w = bit ? ((hi << bit) | (lo >> (64 - bit))) : hi;
+    const uint32_t maskK = pl.Yn - 1;
+    const int jmax = min(W - 1, L - W - p);
+    const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
+    const uint32_t xlo = (uint32_t)X, xhi = (uint32_t)(X >> 32);
+    int sh = 62 - 2 * K;
+    uint32_t jb = 0;
+    for (int j = 0; j <= jmax; j++) {
+        uint32_t y = field(w, sh, maskK);
+        if (over_n) { const int d = p + j - mid; if (d >= 0 && d <= K) y = pv.ypatch[(uint64_t)n * (K + 1) + d]; }
+        const uint32_t bin = jb + y;
+        const uint32_t old = atomicAdd(&lo_sh[bin], xlo);
+        const uint32_t h = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
+        if (h) atomicAdd(&mypart[bin], (unsigned long long)h << 32);
+        sh -= 2; jb += pl.Yn;
+    }
+}
+
+__global__ void __launch_bounds__(512)
+k_mstep_packed(PackedView pv, Plan pl, const float* __restrict__ r, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+    extern __shared__ uint32_t smem_u32[];
+    const uint32_t nbin = (uint32_t)pl.W * pl.Yn;
+    uint32_t* lo_sh = smem_u32;
+    QEntry* queues = reinterpret_cast<QEntry*>(smem_u32 + ((nbin + 3) & ~3u));
+    unsigned long long* mypart = part + (uint64_t)blockIdx.x * nbin;
+    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) lo_sh[i] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    QEntry* q = queues + wib * QCAP;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wib;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const int W = pl.W;
+    uint32_t qhead = 0, qcount = 0;            // warp-uniform
+    for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
+        const uint32_t n = pv.seq_ids[li];
+        const int L = (int)pv.seqs[n].L, LW1 = L - W + 1;
+        const float* __restrict__ rn = r + pv.r_off[li];
+        for (int p0 = 0; p0 < LW1; p0 += 32 * M_UNROLL) {
+            float rv[M_UNROLL];
+#pragma unroll
+            for (int u = 0; u < M_UNROLL; u++) {
+                const int p = p0 + u * 32 + lane;
+                rv[u] = (p < LW1) ? __ldcs(&rn[L - W - p]) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < M_UNROLL; u++) {
+                const bool act = rv[u] >= FX_HALF_UNIT;
+                const unsigned m = __ballot_sync(FULL, act);
+                if (m == 0) continue;
+                if (act) {
+                    const uint32_t slot = (qhead + qcount + __popc(m & ((1u << lane) - 1))) & (QCAP - 1);
+                    q[slot].li = li; q[slot].p = (uint32_t)(p0 + u * 32 + lane); q[slot].rv = rv[u];
+                }
+                qcount += __popc(m);
+                __syncwarp();
+                if (qcount >= 32) {
+                    const QEntry e = q[(qhead + lane) & (QCAP - 1)];
+                    scatter_window(pv, pl, lo_sh, mypart, e.li, (int)e.p, e.rv);
+                    qhead = (qhead + 32) & (QCAP - 1); qcount -= 32;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    if (lane < (int)qcount) {
+        const QEntry e = q[(qhead + lane) & (QCAP - 1)];
+        scatter_window(pv, pl, lo_sh, mypart, e.li, (int)e.p, e.rv);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
+        const uint32_t v = lo_sh[i];
+        if (v) atomicAdd(&mypart[i], (unsigned long long)v);
+    }
+}
+
+// ---- scoring -------------------------------------------------------------------------------------------------------
+// reference: ScoreSeqSet::calcLogOdds, src/seq_scoring/ScoreSeqSet.cpp:25-67. Plain table, sum in ascending j from
+// 0.0f: bit-identical to the reference for the same table. Only the k-mer fetch differs from k_score.
+__global__ void __launch_bounds__(512)
+k_score_packed(PackedView pv, Plan pl, const uint64_t* __restrict__ mops_off, const float* __restrict__ s_g,
+               float* __restrict__ zoops, unsigned long long* __restrict__ z, float* __restrict__ mops, const uint32_t* __restrict__ out_idx) {
+    extern __shared__ float s_sh[];
+    for (uint32_t i = threadIdx.x; i < (uint32_t)pl.W * pl.Yn; i += blockDim.x) s_sh[i] = s_g[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const int W = pl.W, K = pl.K;
+    const uint32_t maskK = pl.Yn - 1;
+    for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
+        const uint32_t n = pv.seq_ids[li];
+        const uint32_t oi = out_idx[li];                   // position of this sequence in the caller's subset
+        const PackedSeq sq = pv.seqs[n];
+        const int L = (int)sq.L, LW1 = L - W + 1, mid = (int)sq.mid;
+        const unsigned long long* __restrict__ wd = pv.words + sq.word_off;
+        float best = -3.402823466e+38f;
+        int bestp = 0;
+        for (int p0 = 0; p0 < LW1; p0 += 32) {
+            const int p = p0 + lane, ch = p0 >> 5;
+            const unsigned long long w = window_word(wd[ch - 1], wd[ch], wd[ch + 1], lane - K);
+            const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
+            float sc = 0.0f;
+            int sh = 62 - 2 * K;
+            uint32_t jb = 0;
+            if (__any_sync(FULL, over_n)) {
+                for (int j = 0; j < W; j++) {
+                    uint32_t y = field(w, sh, maskK);
+                    const int d = p + j - mid;
+                    if (over_n && d >= 0 && d <= K) y = pv.ypatch[(uint64_t)n * (K + 1) + d];
+                    sc += s_sh[jb + y];
+                    sh -= 2; jb += pl.Yn;
+                }
+            } else {
+                for (int j = 0; j < W; j++) {
+                    sc += s_sh[jb + field(w, sh, maskK)];
+                    sh -= 2; jb += pl.Yn;
+                }
+            }
+            if (p < LW1) {
+                if (mops) mops[mops_off[oi] + p] = sc;
+                if (sc > best) { best = sc; bestp = p; }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(FULL, best, o);
+            const int op = __shfl_xor_sync(FULL, bestp, o);
+            if (ob > best || (ob == best && op < bestp)) { best = ob; bestp = op; }
+        }
+        if (lane == 0) { zoops[oi] = best; z[oi] = (unsigned long long)bestp; }
+    }
+}
+
+}  // namespace bamm
