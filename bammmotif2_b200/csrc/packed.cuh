@@ -165,36 +165,12 @@ struct Plan {                 // launch-invariant parameters of the packed kerne
 // reference: EM::EStep, src/refinement/EM.cpp:139-200 (gather form). One warp per sequence, lanes =
 // window starts. The C tuple lookups of a window are fully unrolled (C is a template parameter); the 64-bit window
 // word is consumed from the top, 2T bits per lookup. Unnormalised posteriors go to r, the normaliser is reduced
-// over the warp, and a second sweep divides (the lines are still in L2).
-__device__ __forceinline__ float slow_window(const PackedView& pv, const Plan& pl, const float* __restrict__ tab,
-                                             const float* __restrict__ s_g, uint32_t n, unsigned long long w,
-                                             int p, int L, int mid) {
-    // exact product for a window that tuples cannot fully serve: whole tuples still come from the shared table,
-    // the truncated remainder and every tuple that touches the k-mers holding the N's rand() draws (positions
-    // mid..mid+K) are taken column by column from the plain table.
-    const int W = pl.W, K = pl.K, T = pl.T;
-    const int jmax = min(W - 1, L - W - p);
-    const uint32_t maskK = pl.Yn - 1, maskZ = pl.Zn - 1;
-    const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
-    float pr = 1.0f;
-    for (int c = 0, j0 = 0; j0 <= jmax; c++, j0 += T) {
-        const int e0 = p + j0, e1 = e0 + T - 1;
-        const bool whole = (j0 + T - 1 <= jmax) && !(over_n && e1 >= mid && e0 <= mid + K);
-        if (whole) {
-            pr *= tab[(uint32_t)c * pl.Zn + field(w, 64 - 2 * (K + T) - 2 * T * c, maskZ)];
-        } else {
-            for (int t = 0; t < T && j0 + t <= jmax; t++) {
-                const int j = j0 + t;
-                uint32_t y = field(w, 62 - 2 * K - 2 * j, maskK);
-                const int d = p + j - mid;
-                if (over_n && d >= 0 && d <= K) y = pv.ypatch[(uint64_t)n * (K + 1) + d];
-                pr *= __ldg(&s_g[(uint32_t)j * pl.Yn + y]);
-            }
-        }
-    }
-    return pr;
-}
-
+// over the warp, and a second sweep scales by 1/norm (the lines are still in L2).
+//
+// Chunks that contain windows tuples cannot fully serve — the last W-1 truncated windows (EM.cpp:167) and the
+// windows over the k-mers that hold the N's rand() draws (positions mid..mid+K, Sequence.cpp:38) — run a masked
+// variant: per lane a bit mask of the tuples that are whole and untouched (taken from the shared table as usual)
+// and a bit mask of the single columns that must come from the plain table in global memory.
 template <int C>
 __global__ void __launch_bounds__(1024, 1)
 k_estep_packed(PackedView pv, Plan pl, const float* __restrict__ tab_g /* [C][Zn] */, const float* __restrict__ s_g /* [W][Yn] */,
@@ -209,6 +185,7 @@ k_estep_packed(PackedView pv, Plan pl, const float* __restrict__ tab_g /* [C][Zn
     const int zb = 2 * (K + T);                            // bits of one tuple index
     const int roll = 2 * T;
     const uint32_t zn_bytes = pl.Zn * 4u;
+    const uint32_t maskK = pl.Yn - 1;
     const char* tabc = reinterpret_cast<const char*>(tab);
     long long llh_fx = 0, rsum_fx = 0;
     const float one_minus_q = 1.0f - pl.q;
@@ -227,18 +204,50 @@ k_estep_packed(PackedView pv, Plan pl, const float* __restrict__ tab_g /* [C][Zn
             const unsigned long long w = window_word(wd[ch - 1], wd[ch], wd[ch + 1], lane - K);
             uint32_t whi = (uint32_t)(w >> 32), wlo = (uint32_t)w;
             float prod = 1.0f;
+            const bool chunk_slow = (p0 + 31 >= tail0) || (mid >= 0 && p0 <= mid + K && p0 + 31 + W - 1 >= mid);   // warp-uniform
+            if (!chunk_slow) {
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                const uint32_t z4 = (whi >> (32 - zb)) << 2;
-                prod *= *reinterpret_cast<const float*>(tabc + (uint32_t)c * zn_bytes + z4);
-                whi = __funnelshift_l(wlo, whi, roll);
-                wlo <<= roll;
-            }
-            // chunks that hold windows tuples cannot serve (warp-uniform test): truncated tail / over the N
-            const bool chunk_slow = (p0 + 31 >= tail0) || (mid >= 0 && p0 <= mid + K && p0 + 31 + W - 1 >= mid);
-            if (chunk_slow) {
+                for (int c = 0; c < C; c++) {
+                    const uint32_t z4 = (whi >> (32 - zb)) << 2;
+                    prod *= *reinterpret_cast<const float*>(tabc + (uint32_t)c * zn_bytes + z4);
+                    whi = __funnelshift_l(wlo, whi, roll);
+                    wlo <<= roll;
+                }
+            } else {
+                const int jmax = (p < LW1) ? min(W - 1, L - W - p) : -1;
+                const int cfull = (jmax + 1) / T;                               // whole tuples inside the truncation
+                uint32_t good = (1u << cfull) - 1u;
+                uint32_t cols = 0;
+                if (cfull * T <= jmax) cols = ((2u << jmax) - 1u) & ~((1u << (cfull * T)) - 1u);   // truncated remainder
                 const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
-                if (p < LW1 && (p >= tail0 || over_n)) prod = slow_window(pv, pl, tab, s_g, n, w, p, L, mid);
+                if (over_n) {
+                    // tuples c with p+cT+T-1 >= mid and p+cT <= mid+K
+                    const int a = mid - p - T + 1;
+                    const int c_lo = a <= 0 ? 0 : (a + T - 1) / T;
+                    const int c_hi = min(C - 1, (mid + K - p) / T);
+                    if (c_hi >= c_lo) {
+                        const uint32_t cm = ((2u << c_hi) - 1u) & ~((1u << c_lo) - 1u);
+                        const int jl = c_lo * T, jh = min(jmax, c_hi * T + T - 1);
+                        if (jh >= jl) cols |= ((2u << jh) - 1u) & ~((1u << jl) - 1u);
+                        good &= ~cm;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    const uint32_t z4 = (whi >> (32 - zb)) << 2;
+                    const float v = *reinterpret_cast<const float*>(tabc + (uint32_t)c * zn_bytes + z4);
+                    prod *= ((good >> c) & 1u) ? v : 1.0f;
+                    whi = __funnelshift_l(wlo, whi, roll);
+                    wlo <<= roll;
+                }
+                while (cols) {
+                    const int j = __ffs(cols) - 1;
+                    cols &= cols - 1u;
+                    uint32_t y = field(w, 62 - 2 * K - 2 * j, maskK);
+                    const int d = p + j - mid;
+                    if (over_n && d >= 0 && d <= K) y = pv.ypatch[(uint64_t)n * (K + 1) + d];
+                    prod *= __ldg(&s_g[(uint32_t)j * pl.Yn + y]);
+                }
             }
             if (p < LW1) {
                 const float val = prod * pos;
@@ -248,11 +257,12 @@ k_estep_packed(PackedView pv, Plan pl, const float* __restrict__ tab_g /* [C][Zn
         }
         sum = warp_sum(sum);
         const float norm = one_minus_q + sum;
+        const float rnorm = __frcp_rn(norm);
         __syncwarp();
-        for (int k = lane; k < L; k += 32) rn[k] = (k < LW1) ? __fdiv_rn(rn[k], norm) : 0.0f;
+        for (int k = lane; k < L; k += 32) rn[k] = (k < LW1) ? rn[k] * rnorm : 0.0f;
         if (lane == 0) {
             llh_fx += __double2ll_rn((double)logf(norm) * SC_SCALE_D);
-            rsum_fx += __double2ll_rn((double)__fdiv_rn(sum, norm) * SC_SCALE_D);
+            rsum_fx += __double2ll_rn((double)(sum * rnorm) * SC_SCALE_D);
         }
     }
     if (lane == 0) {
