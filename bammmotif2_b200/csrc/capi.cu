@@ -49,7 +49,7 @@ struct bamm_seqset {
     std::vector<uint8_t> h_kind;
     uint8_t* d_kind = nullptr;
     PackedSeq* d_pseq = nullptr;
-    unsigned long long* d_words = nullptr;
+    uint32_t* d_words = nullptr;        // 16 bases per word
     uint64_t nwords = 0, nregular = 0;
     std::map<int, uint16_t*> ypatch;   // per order K: [nseq][K+1] k-mer index at mid..mid+K
 };
@@ -186,8 +186,8 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
             PackedSeq q; q.word_off = 0; q.L = 0; q.mid = 0xffffffffu;
             if (s->h_kind[n]) {
                 const uint64_t L = offsets[n + 1] - offsets[n];
-                q.word_off = w + 1; q.L = (uint32_t)L; q.mid = s->h_kind[n] == 2 ? (uint32_t)((L - 1) / 2) : 0xffffffffu;
-                w += (L + 31) / 32 + 3;                       // pad | data | pad pad
+                q.word_off = w + 2; q.L = (uint32_t)L; q.mid = s->h_kind[n] == 2 ? (uint32_t)((L - 1) / 2) : 0xffffffffu;
+                w += (L + 15) / 16 + 8;                       // pad pad | data | 6 pads (the E-step prefetches ahead)
                 s->nregular++;
             }
             ps[n] = q;
@@ -196,7 +196,7 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
         if (s->nregular) {
             CUS(cudaMalloc(&s->d_pseq, nseq * sizeof(PackedSeq)));
             CUS(cudaMemcpy(s->d_pseq, ps.data(), nseq * sizeof(PackedSeq), cudaMemcpyHostToDevice));
-            CUS(cudaMalloc(&s->d_words, w * sizeof(unsigned long long)));
+            CUS(cudaMalloc(&s->d_words, w * sizeof(uint32_t)));
             k_pack<<<s->sm_count * 8, 256>>>(s->d_codes, s->d_off, nseq, s->d_kind, s->d_pseq, s->d_words);
             CUS(cudaGetLastError());
             CUS(cudaDeviceSynchronize());

@@ -1,8 +1,8 @@
 // packed.cuh — the fast path for the 4-letter alphabet: sequences as 2-bit packed base streams.
 //
 // Layout. A "regular" sequence (codes 1..4 everywhere, except optionally the structural N in the
-// middle of a both-strand sequence, Sequence.cpp:10-14) is stored as 64-bit words of 32 bases, FIRST base in the
-// most significant bits, preceded by one zero pad word and followed by two. The order-K k-mer index of the
+// middle of a both-strand sequence, Sequence.cpp:10-14) is stored as 32-bit words of 16 bases, FIRST base in the
+// most significant bits, preceded by two zero pad words (32 bases) and followed by six. The order-K k-mer index of the
 // reference, y(i) = sum_t c(i-t) 4^t (Sequence.cpp:35-41), is then literally a bit field of the stream: for a
 // window start p the 64-bit word  w = bases p-K .. p-K+31  gives  y(p+j) = (w >> (62-2K-2j)) & (4^(K+1)-1), and the
 // zero pad supplies the implicit leading 'A's of k-mers that start before the sequence does. No index array is read.
@@ -22,13 +22,13 @@
 namespace bamm {
 
 struct PackedSeq {           // per regular sequence
-    uint64_t word_off;       // index of the sequence's FIRST DATA word (the pad word sits at word_off-1)
+    uint64_t word_off;       // index of the sequence's FIRST DATA word (two zero pad words sit before it)
     uint32_t L;              // stored length
     uint32_t mid;            // position of the structural N, or 0xffffffff
 };
 
 struct PackedView {
-    const unsigned long long* words;   // packed stream
+    const uint32_t* words;             // packed stream, 16 bases per 32-bit word
     const PackedSeq* seqs;             // [nseq] (entries of irregular sequences are unused)
     const uint16_t* ypatch;            // [nseq][K+1] order-K k-mer index at positions mid..mid+K (rand() draws inside)
     const uint32_t* seq_ids;           // list -> seqset index
@@ -84,25 +84,26 @@ __global__ void k_finish_kinds(const uint64_t* __restrict__ off, uint64_t nseq, 
     }
 }
 
-// one thread per output word; word index space is [0, total_words)
+// one lane per output word (16 bases)
 __global__ void k_pack(const uint8_t* __restrict__ codes, const uint64_t* __restrict__ off, uint64_t nseq,
                        const uint8_t* __restrict__ kind, const PackedSeq* __restrict__ seqs,
-                       unsigned long long* __restrict__ words) {
+                       uint32_t* __restrict__ words) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     for (uint64_t n = warp; n < nseq; n += nwarps) {
         if (kind[n] == 0) continue;
         const uint64_t base = off[n], L = off[n + 1] - base;
-        const uint64_t nw = (L + 31) / 32;
-        unsigned long long* dst = words + seqs[n].word_off;
-        if (lane == 0) { dst[-1] = 0ull; dst[nw] = 0ull; dst[nw + 1] = 0ull; }
+        const uint64_t nw = (L + 15) / 16;
+        uint32_t* dst = words + seqs[n].word_off;
+        if (lane < 2) dst[-1 - lane] = 0u;
+        if (lane < 6) dst[nw + lane] = 0u;
         for (uint64_t wi = lane; wi < nw; wi += 32) {
-            unsigned long long w = 0;
-            for (int b = 0; b < 32; b++) {
-                const uint64_t i = wi * 32 + b;
+            uint32_t w = 0;
+            for (int b = 0; b < 16; b++) {
+                const uint64_t i = wi * 16 + b;
                 const uint32_t c = (i < L) ? codes[base + i] : 0u;
-                w = (w << 2) | (unsigned long long)(c ? c - 1 : 0);
+                w = (w << 2) | (c ? c - 1 : 0u);
             }
             dst[wi] = w;
         }
@@ -141,14 +142,17 @@ __global__ void k_make_tuple_table(const float* __restrict__ s, int W, int K, in
 }
 
 // ---- window extraction ---------------------------------------------------------------------------------------------
-// 64-bit word holding bases b0 .. b0+31 of a sequence (b0 may be negative down to -32: pad word), from the three
-// stream words that surround the 32-window chunk starting at window p0 (prev = bases p0-32.., cur = p0.., next = p0+32..).
-__device__ __forceinline__ unsigned long long window_word(unsigned long long prev, unsigned long long cur,
-                                                          unsigned long long next, int rel /* b0 - p0, in [-32, 31] */) {
-    const unsigned long long hi = rel < 0 ? prev : cur;
-    const unsigned long long lo = rel < 0 ? cur : next;
-    const int sh = 2 * (rel < 0 ? rel + 32 : rel);          // 0..62
-    return sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+// 64 bits holding bases b0 .. b0+31 of a sequence (b0 >= -32: the pad words supply leading zeros), as (hi, lo).
+__device__ __forceinline__ void window_bits(const uint32_t* __restrict__ wd, int b0, uint32_t& whi, uint32_t& wlo) {
+    const int wi = b0 >> 4;                      // floor
+    const int s = 2 * (b0 & 15);
+    const uint32_t t0 = wd[wi], t1 = wd[wi + 1], t2 = wd[wi + 2];
+    whi = __funnelshift_l(t1, t0, s);
+    wlo = __funnelshift_l(t2, t1, s);
+}
+__device__ __forceinline__ unsigned long long window_word(const uint32_t* __restrict__ wd, int b0) {
+    uint32_t hi, lo; window_bits(wd, b0, hi, lo);
+    return ((unsigned long long)hi << 32) | lo;
 }
 
 __device__ __forceinline__ uint32_t field(unsigned long long w, int shift, uint32_t mask) {
@@ -194,15 +198,21 @@ k_estep_packed(PackedView pv, Plan pl, const float* __restrict__ tab_g /* [C][Zn
         const PackedSeq sq = pv.seqs[n];
         const int L = (int)sq.L, LW1 = L - W + 1;
         const int mid = (int)sq.mid;                       // -1 when there is no N
-        const unsigned long long* __restrict__ wd = pv.words + sq.word_off;
+        // per-lane view of the stream: this lane's windows start at bases lane-K + 32*ch, i.e. always at the same
+        // bit offset sft inside a 32-bit word; three words are kept and two new ones are fetched per chunk
+        const uint32_t* __restrict__ wl = pv.words + sq.word_off + ((lane - K) >> 4);
+        const int sft = 2 * ((lane - K) & 15);
+        uint32_t t0 = wl[0], t1 = wl[1], t2 = wl[2];
         float* __restrict__ rn = r + pv.r_off[li];
         const float pos = pl.q / (float)LW1;
         const int tail0 = L - 2 * W + 2;                   // first truncated window (p > L-2W+1)
         float sum = 0.0f;
-        for (int p0 = 0, ch = 0; p0 < LW1; p0 += 32, ch++) {
+        for (int p0 = 0; p0 < LW1; p0 += 32) {
             const int p = p0 + lane;
-            const unsigned long long w = window_word(wd[ch - 1], wd[ch], wd[ch + 1], lane - K);
-            uint32_t whi = (uint32_t)(w >> 32), wlo = (uint32_t)w;
+            uint32_t whi = __funnelshift_l(t1, t0, sft), wlo = __funnelshift_l(t2, t1, sft);
+            const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
+            wl += 2;
+            t0 = t2; t1 = wl[1]; t2 = wl[2];
             float prod = 1.0f;
             const bool chunk_slow = (p0 + 31 >= tail0) || (mid >= 0 && p0 <= mid + K && p0 + 31 + W - 1 >= mid);   // warp-uniform
             if (!chunk_slow) {
@@ -273,43 +283,60 @@ k_estep_packed(PackedView pv, Plan pl, const float* __restrict__ tab_g /* [C][Zn
 
 // ---- M-step --------------------------------------------------------------------------------------------------------
 // reference: EM::MStep accumulation, src/refinement/EM.cpp:230-243 (gather form).
-// Pass 1 per warp: stream r (8 chunks of 32 windows in flight per lane), keep the windows whose r is at least half
-// a fixed-point unit (everything below rounds to exactly 0), compact them into the warp's ring queue.
-// Pass 2 whenever 32 entries are queued: each lane scatters one window's value into the W bins it touches.
-struct QEntry { uint32_t li, p; float rv; uint32_t pad; };
-constexpr int QCAP = 64;                       // ring entries per warp
-constexpr int M_UNROLL = 8;
+// Pass 1 per warp and sequence: stream r in batches of 256 windows (8 per lane; the next batch's loads are issued
+// before the current one is examined), keep the windows whose r is at least half a fixed-point unit (everything
+// below rounds to exactly 0 and contributes nothing) and compact them with a warp scan into the warp's ring queue.
+// Pass 2 whenever 32 entries are queued (and once more at the end of the sequence): each lane scatters one
+// window's value into the W bins it touches with native 32-bit shared atomics. Low-word wrap-arounds are collected
+// in a bit mask and carried into the CTA's 64-bit partial table after the loop, so the scatter loop is branch-free.
+struct QEntry { uint32_t p; float rv; };
+constexpr int QCAP = 256;                      // ring entries per warp (>= 31 + 128)
+constexpr int M_UNROLL = 8;                    // chunks of 32 windows in flight per lane
+constexpr int M_GROUP = 4;                     // chunks compacted per warp scan
 constexpr float FX_HALF_UNIT = 4.547473508864641e-13f;   // 2^-41: smallest r that rounds to a non-zero count
 
-__device__ __forceinline__ void scatter_window(const PackedView& pv, const Plan& pl, uint32_t* __restrict__ lo_sh,
-                                               unsigned long long* __restrict__ mypart, uint32_t li, int p, float rv) {
+struct SeqCtx { const uint32_t* wd; const uint16_t* yp; int L, mid; };
+
+__device__ __forceinline__ void scatter_window(const SeqCtx& sc, const Plan& pl, uint32_t* __restrict__ lo_sh,
+                                               unsigned long long* __restrict__ mypart, int p, float rv) {
     const int W = pl.W, K = pl.K;
     const unsigned long long X = __float2ull_rn(rv * FX_SCALE_F);
     if (X == 0) return;
-    const uint32_t n = pv.seq_ids[li];
-    const PackedSeq sq = pv.seqs[n];
-    const int L = (int)sq.L, mid = (int)sq.mid;
-    const unsigned long long* __restrict__ wd = pv.words + sq.word_off;
-    // word holding bases p-K .. p-K+31
-    const int b0 = p - K;
-    const int wi = b0 >> 5;                    // floor division (b0 >= -32)
-    const int bit = 2 * (b0 & 31);
-    const unsigned long long hi = wd[wi], lo = wd[wi + 1];
-    const unsigned long long w = bit ? ((hi << bit) | (lo >> (64 - bit))) : hi;
+    const int L = sc.L, mid = sc.mid;
+    const unsigned long long w = window_word(sc.wd, p - K);      // bases p-K .. p-K+31
     const uint32_t maskK = pl.Yn - 1;
     const int jmax = min(W - 1, L - W - p);
     const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
     const uint32_t xlo = (uint32_t)X, xhi = (uint32_t)(X >> 32);
     int sh = 62 - 2 * K;
     uint32_t jb = 0;
-    for (int j = 0; j <= jmax; j++) {
-        uint32_t y = field(w, sh, maskK);
-        if (over_n) { const int d = p + j - mid; if (d >= 0 && d <= K) y = pv.ypatch[(uint64_t)n * (K + 1) + d]; }
-        const uint32_t bin = jb + y;
-        const uint32_t old = atomicAdd(&lo_sh[bin], xlo);
-        const uint32_t h = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
-        if (h) atomicAdd(&mypart[bin], (unsigned long long)h << 32);
-        sh -= 2; jb += pl.Yn;
+    uint32_t carry = 0;                        // bit j: the low word of bin (j, y_j) wrapped
+    if (!over_n) {
+        for (int j = 0; j <= jmax; j++) {
+            const uint32_t old = atomicAdd(&lo_sh[jb + field(w, sh, maskK)], xlo);
+            carry |= ((uint32_t)(old + xlo) < old ? 1u : 0u) << j;
+            sh -= 2; jb += pl.Yn;
+        }
+    } else {
+        for (int j = 0; j <= jmax; j++) {
+            uint32_t y = field(w, sh, maskK);
+            const int d = p + j - mid;
+            if (d >= 0 && d <= K) y = sc.yp[d];
+            const uint32_t old = atomicAdd(&lo_sh[jb + y], xlo);
+            carry |= ((uint32_t)(old + xlo) < old ? 1u : 0u) << j;
+            sh -= 2; jb += pl.Yn;
+        }
+    }
+    // high words: large r (xhi != 0) touches every bin, otherwise only the bins whose low word wrapped
+    uint32_t todo = xhi ? (jmax >= 31 ? 0xffffffffu : ((2u << jmax) - 1u)) : carry;
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        uint32_t y = field(w, 62 - 2 * K - 2 * j, maskK);
+        const int d = p + j - mid;
+        if (over_n && d >= 0 && d <= K) y = sc.yp[d];
+        const uint32_t h = xhi + ((carry >> j) & 1u);
+        atomicAdd(&mypart[(uint32_t)j * pl.Yn + y], (unsigned long long)h << 32);
     }
 }
 
@@ -327,42 +354,64 @@ k_mstep_packed(PackedView pv, Plan pl, const float* __restrict__ r, unsigned lon
     QEntry* q = queues + wib * QCAP;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wib;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    const int W = pl.W;
-    uint32_t qhead = 0, qcount = 0;            // warp-uniform
+    const int W = pl.W, K = pl.K;
     for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
         const uint32_t n = pv.seq_ids[li];
-        const int L = (int)pv.seqs[n].L, LW1 = L - W + 1;
+        const PackedSeq sq = pv.seqs[n];
+        SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = (int)sq.L; sc.mid = (int)sq.mid;
+        const int L = sc.L, LW1 = L - W + 1;
         const float* __restrict__ rn = r + pv.r_off[li];
-        for (int p0 = 0; p0 < LW1; p0 += 32 * M_UNROLL) {
-            float rv[M_UNROLL];
+        uint32_t qhead = 0, qcount = 0;        // warp-uniform
+        // r index i = L-W-p runs over [0, LW1); lane takes i = i0 + u*32 + lane
+        float cur[M_UNROLL], nxt[M_UNROLL];
+#pragma unroll
+        for (int u = 0; u < M_UNROLL; u++) { const int i = u * 32 + lane; cur[u] = (i < LW1) ? __ldcs(&rn[i]) : 0.0f; }
+        for (int i0 = 0; i0 < LW1; i0 += 32 * M_UNROLL) {
 #pragma unroll
             for (int u = 0; u < M_UNROLL; u++) {
-                const int p = p0 + u * 32 + lane;
-                rv[u] = (p < LW1) ? __ldcs(&rn[L - W - p]) : 0.0f;
+                const int i = i0 + 32 * M_UNROLL + u * 32 + lane;
+                nxt[u] = (i < LW1) ? __ldcs(&rn[i]) : 0.0f;
             }
 #pragma unroll
-            for (int u = 0; u < M_UNROLL; u++) {
-                const bool act = rv[u] >= FX_HALF_UNIT;
-                const unsigned m = __ballot_sync(FULL, act);
-                if (m == 0) continue;
-                if (act) {
-                    const uint32_t slot = (qhead + qcount + __popc(m & ((1u << lane) - 1))) & (QCAP - 1);
-                    q[slot].li = li; q[slot].p = (uint32_t)(p0 + u * 32 + lane); q[slot].rv = rv[u];
-                }
-                qcount += __popc(m);
-                __syncwarp();
-                if (qcount >= 32) {
-                    const QEntry e = q[(qhead + lane) & (QCAP - 1)];
-                    scatter_window(pv, pl, lo_sh, mypart, e.li, (int)e.p, e.rv);
-                    qhead = (qhead + 32) & (QCAP - 1); qcount -= 32;
+            for (int g = 0; g < M_UNROLL; g += M_GROUP) {
+                uint32_t act = 0;
+#pragma unroll
+                for (int u = 0; u < M_GROUP; u++) act |= (cur[g + u] >= FX_HALF_UNIT ? 1u : 0u) << u;
+                if (__any_sync(FULL, act != 0)) {
+                    const uint32_t cnt = __popc(act);
+                    uint32_t incl = cnt;                                   // inclusive prefix of the per-lane counts
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+                    const uint32_t total = __shfl_sync(FULL, incl, 31);
+                    uint32_t slot = qhead + qcount + incl - cnt;
+#pragma unroll
+                    for (int u = 0; u < M_GROUP; u++) {
+                        if (act & (1u << u)) {
+                            QEntry& e = q[slot & (QCAP - 1)];
+                            e.p = (uint32_t)(L - W - (i0 + (g + u) * 32 + lane)); e.rv = cur[g + u];
+                            slot++;
+                        }
+                    }
+                    qcount += total;
+                    __syncwarp();
+                    while (qcount >= 32) {
+                        const QEntry e = q[(qhead + lane) & (QCAP - 1)];
+                        scatter_window(sc, pl, lo_sh, mypart, (int)e.p, e.rv);
+                        qhead = (qhead + 32) & (QCAP - 1); qcount -= 32;
+                    }
                     __syncwarp();
                 }
             }
+#pragma unroll
+            for (int u = 0; u < M_UNROLL; u++) cur[u] = nxt[u];
         }
-    }
-    if (lane < (int)qcount) {
-        const QEntry e = q[(qhead + lane) & (QCAP - 1)];
-        scatter_window(pv, pl, lo_sh, mypart, e.li, (int)e.p, e.rv);
+        if (qcount) {                          // flush the sequence's remainder (< 32 entries)
+            if (lane < (int)qcount) {
+                const QEntry e = q[(qhead + lane) & (QCAP - 1)];
+                scatter_window(sc, pl, lo_sh, mypart, (int)e.p, e.rv);
+            }
+            __syncwarp();
+        }
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
@@ -390,12 +439,12 @@ k_score_packed(PackedView pv, Plan pl, const uint64_t* __restrict__ mops_off, co
         const uint32_t oi = out_idx[li];                   // position of this sequence in the caller's subset
         const PackedSeq sq = pv.seqs[n];
         const int L = (int)sq.L, LW1 = L - W + 1, mid = (int)sq.mid;
-        const unsigned long long* __restrict__ wd = pv.words + sq.word_off;
+        const uint32_t* __restrict__ wd = pv.words + sq.word_off;
         float best = -3.402823466e+38f;
         int bestp = 0;
         for (int p0 = 0; p0 < LW1; p0 += 32) {
-            const int p = p0 + lane, ch = p0 >> 5;
-            const unsigned long long w = window_word(wd[ch - 1], wd[ch], wd[ch + 1], lane - K);
+            const int p = p0 + lane;
+            const unsigned long long w = window_word(wd, p - K);
             const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
             float sc = 0.0f;
             int sh = 62 - 2 * K;
