@@ -1,6 +1,8 @@
 """Builds the in-tree native artefacts of bammmotif2_b200 with nvcc / g++ (no torch, no JIT cache):
 
-    libbamm_b200.so   the C-ABI library (include/bamm_b200.h): csrc/capi.cu + csrc/kernels.cuh, sm_100a only
+    libbamm_b200.so   the C-ABI library (include/bamm_b200.h): csrc/capi.cu + csrc/*.cuh, sm_100a only
+    bin/BaMMmotif     the C++ host side (host/*.cpp: the reference's class surface over the C ABI) as the drop-in CLI
+    bin/host_check    test helper for the CPU-only parts of the host classes
 
 Run as `python -m bammmotif2_b200.build` or through __graft_entry__.build().
 """
@@ -39,7 +41,8 @@ def _newer(target, deps):
 
 def build_lib(force=False, verbose=False):
     srcs = [os.path.join(HERE, "csrc", "capi.cu")]
-    deps = srcs + [os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(ROOT, "include", "bamm_b200.h"), __file__]
+    deps = srcs + [os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "packed.cuh"),
+                   os.path.join(ROOT, "include", "bamm_b200.h"), __file__]
     if not force and _newer(LIB, deps):
         return LIB
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
@@ -49,8 +52,39 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+HOST_SOURCES = ["Alphabet", "SequenceSet", "BackgroundModel", "Motif", "MotifSet", "EM", "ScoreSeqSet", "SeqGenerator", "FDR", "Global"]
+# -ffp-contract=off: the host arithmetic (background model, site initialisation, p-values) follows the reference's
+# operation order in plain IEEE fp32, without fused multiply-adds
+HOST_FLAGS = ["-std=c++17", "-O2", "-Wall", "-ffp-contract=off"]
+
+
+def build_host(force=False):
+    """host/*.cpp -> bin/BaMMmotif and bin/host_check, linked against libbamm_b200.so (rpath $ORIGIN/..)."""
+    hdir, bdir, odir = os.path.join(HERE, "host"), os.path.join(HERE, "bin"), os.path.join(HERE, "build", "host")
+    os.makedirs(bdir, exist_ok=True)
+    os.makedirs(odir, exist_ok=True)
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    headers = [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")] + [os.path.join(ROOT, "include", "bamm_b200.h"), __file__]
+    objs = {}
+    for name in HOST_SOURCES + ["mainBaMM", "host_check"]:
+        src, obj = os.path.join(hdir, name + ".cpp"), os.path.join(odir, name + ".o")
+        if force or not _newer(obj, [src] + headers):
+            subprocess.check_call([gxx] + HOST_FLAGS + ["-c", src, "-o", obj], env=env)
+        objs[name] = obj
+    outs = []
+    for exe, main in (("BaMMmotif", "mainBaMM"), ("host_check", "host_check")):
+        out = os.path.join(bdir, exe)
+        deps = [objs[n] for n in HOST_SOURCES] + [objs[main]]
+        if force or not _newer(out, deps + [LIB]):
+            subprocess.check_call([gxx, "-o", out, objs[main]] + [objs[n] for n in HOST_SOURCES] +
+                                  ["-L" + HERE, "-lbamm_b200", "-Wl,-rpath,$ORIGIN/.."], env=env)
+        outs.append(out)
+    return outs
+
+
 def build_all(force=False, verbose=False):
-    return [build_lib(force, verbose)]
+    return [build_lib(force, verbose)] + build_host(force)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,239 @@
+#include "FDR.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+
+FDR::FDR( std::vector<Sequence*> posSeqs, std::vector<Sequence*> negSeqs, Motif* motif, BackgroundModel* bgModel, size_t cvFold,
+          bool mops, bool zoops, bool savePRs, bool savePvalues, bool saveLogOdds )
+    : posSeqs_( posSeqs ), negSeqs_( negSeqs ), q_( motif ? motif->getQ() : 0.f ), motif_( motif ), bgModel_( bgModel ), cvFold_( cvFold ),
+      mops_( mops ), zoops_( zoops ), savePRs_( savePRs ), savePvalues_( savePvalues ), saveLogOdds_( saveLogOdds ){}
+
+FDR::~FDR(){}
+
+// reference: FDR::evaluateMotif, src/evaluation/FDR.cpp:28-145.
+// Split: positives are dealt round-robin — of every complete block of cvFold consecutive sequences, member `fold` is
+// held out and the others train; a trailing incomplete block is dropped. Every fold scores the same negative subset,
+// every cvFold-th negative. The reference runs the folds on OpenMP threads and appends scores in completion order; the
+// statistics sort the scores first, so fold order does not matter. Folds run one after the other here: each already
+// fills the whole GPU, and the device objects they share are read-only.
+void FDR::evaluateMotif( bool EMoptimize, bool CGSoptimize, bool optimizeQ, bool advanceEM, float frac, size_t ){
+    if( CGSoptimize && !EMoptimize ){
+        std::cerr << "Error: collapsed Gibbs sampling (--CGS) is not part of the B200 path." << std::endl;
+        exit( 1 );
+    }
+    float updatedQ = q_;
+    std::vector<Sequence*> negSet;
+    for( size_t n = 0; n + cvFold_ <= negSeqs_.size(); n += cvFold_ ) negSet.push_back( negSeqs_[n] );
+
+    for( size_t fold = 0; fold < cvFold_; fold++ ){
+        Motif* motif = new Motif( *motif_ );
+        std::vector<Sequence*> testSet, trainSet;
+        for( size_t n = 0; n + cvFold_ <= posSeqs_.size(); n += cvFold_ ){
+            for( size_t f = 0; f < cvFold_; f++ ){
+                ( f != fold ? trainSet : testSet ).push_back( posSeqs_[n + f] );
+            }
+        }
+        if( EMoptimize ){
+            EM model( motif, bgModel_, trainSet, optimizeQ, false, frac );
+            if( advanceEM ) model.mask(); else model.optimize();
+            updatedQ = model.getQ();
+        }
+        ScoreSeqSet score_testset( motif, bgModel_, testSet );
+        score_testset.setKeepMops( mops_ );
+        score_testset.calcLogOdds();
+        ScoreSeqSet score_negset( motif, bgModel_, negSet );
+        score_negset.setKeepMops( mops_ );
+        score_negset.calcLogOdds();
+
+        if( mops_ ){
+            const std::vector<float>& p = score_testset.flatMopsScores();
+            posScoreAll_.insert( posScoreAll_.end(), p.begin(), p.end() );
+            const std::vector<float>& g = score_negset.flatMopsScores();
+            negScoreAll_.insert( negScoreAll_.end(), g.begin(), g.end() );
+        }
+        if( zoops_ ){
+            std::vector<float> z = score_testset.getZoopsScores();
+            posScoreMax_.insert( posScoreMax_.end(), z.begin(), z.end() );
+            z = score_negset.getZoopsScores();
+            negScoreMax_.insert( negScoreMax_.end(), z.begin(), z.end() );
+        }
+        delete motif;
+    }
+    q_ = updatedQ;
+    calculatePR();
+    if( savePvalues_ ){
+        fprintf( stderr, " ______________________\n|                      |\n|  calculate P-values  |\n|______________________|\n\n" );
+        calculatePvalues();
+    }
+}
+
+namespace {
+// The reference's merge walk reads one element past the end of a score vector once that vector is exhausted
+// (FDR.cpp:228-238). Such a read can never decide a branch when the vector holds posN (negN) scores, so it is served
+// as NaN (every comparison false) instead of touching foreign memory.
+inline float at( const std::vector<float>& v, size_t i ){
+    return i < v.size() ? v[i] : std::numeric_limits<float>::quiet_NaN();
+}
+}
+
+// reference: FDR::calculatePR, src/evaluation/FDR.cpp:147-276
+void FDR::calculatePR(){
+    const size_t posN = posSeqs_.size();
+    const size_t negN = negSeqs_.size();
+    const float mFold = ( float )negN / ( float )posN;
+
+    srand( 42 );                                    // tie-breaks below draw from a fresh libc stream (FDR.cpp:153)
+
+    if( mops_ ){
+        std::sort( posScoreAll_.begin(), posScoreAll_.end(), std::greater<float>() );
+        std::sort( negScoreAll_.begin(), negScoreAll_.end(), std::greater<float>() );
+        size_t idx_posAll = 0, idx_negAll = 0;
+        float E_TP_MOPS = 0.0f;
+        size_t idx_max = posN + negN;
+        const size_t len_all = posScoreAll_.size() + negScoreAll_.size();
+        for( size_t i = 0; i < len_all; i++ ){
+            if( at( posScoreAll_, idx_posAll ) > at( negScoreAll_, idx_negAll ) || idx_negAll == len_all ) idx_posAll++;
+            else idx_negAll++;
+            MOPS_TP_.push_back( ( float )idx_posAll - ( float )idx_negAll / mFold );
+            MOPS_FP_.push_back( ( float )idx_negAll / mFold );
+            if( E_TP_MOPS == MOPS_TP_[i] ) idx_max = i;
+            if( E_TP_MOPS < MOPS_TP_[i] ) E_TP_MOPS = MOPS_TP_[i];
+        }
+        for( size_t i = 0; i < idx_max && i < MOPS_TP_.size(); i++ ){
+            MOPS_FDR_.push_back( MOPS_FP_[i] / ( MOPS_TP_[i] + MOPS_FP_[i] ) );
+            MOPS_Rec_.push_back( MOPS_TP_[i] / E_TP_MOPS );
+        }
+        occ_mult_ = E_TP_MOPS / ( float )posN;
+    }
+
+    if( zoops_ ){
+        PN_Pvalue_.clear();
+        std::sort( posScoreMax_.begin(), posScoreMax_.end(), std::greater<float>() );
+        std::sort( negScoreMax_.begin(), negScoreMax_.end(), std::greater<float>() );
+
+        size_t idx_posMax = 0, idx_negMax = 0, min_idx_pos = 0;
+        const size_t posN_est = static_cast<size_t>( q_ * ( float )posN );
+        const size_t n_top = std::fmin( 100, negN / 10 );
+
+        float lambda = 1e-16f;                      // rate of the exponential tail fitted to the top negative scores
+        for( size_t l = 0; l < n_top; l++ ) lambda += negScoreMax_[l] - negScoreMax_[n_top];
+        lambda /= n_top;
+        assert( lambda > 0.f );
+
+        float Sl = 0.f;
+        for( size_t i = 0; i < posN + negN; i++ ){
+            const float ps = at( posScoreMax_, idx_posMax ), ns = at( negScoreMax_, idx_negMax );
+            if( ( ps > ns || idx_posMax == 0 || idx_negMax == negN ) && idx_posMax < posN ){
+                Sl = ps;
+                idx_posMax++;
+            } else if( ps == ns && rand() % 2 == 0 && idx_posMax < posN ){
+                Sl = ps;
+                idx_posMax++;
+            } else {
+                Sl = ns;
+                idx_negMax++;
+            }
+            const float TP = ( float )idx_posMax;
+            const float FP = ( float )idx_negMax / mFold;
+            ZOOPS_TP_.push_back( TP );
+            ZOOPS_FP_.push_back( FP );
+
+            float p_value;
+            if( Sl <= negScoreMax_[n_top] ){
+                // rank among the negatives, interpolated between the neighbouring negative scores
+                const float Sl_upper = *( std::lower_bound( negScoreMax_.begin(), negScoreMax_.end(), Sl, std::greater<float>() ) - 1 );
+                // (a score below every negative has no lower neighbour; the reference reads one past the end there —
+                //  the score itself is used instead, which puts the p-value at the top of the range)
+                auto lower = std::upper_bound( negScoreMax_.begin(), negScoreMax_.end(), Sl, std::greater<float>() );
+                const float Sl_lower = lower != negScoreMax_.end() ? *lower : Sl;
+                p_value = ( idx_negMax + ( Sl_upper - Sl ) / ( Sl_upper - Sl_lower + 1e-5 ) ) / ( float )negN;
+            } else {
+                p_value = n_top * expf( ( negScoreMax_[n_top] - Sl ) / lambda ) / negN;
+            }
+            PN_Pvalue_.push_back( p_value );
+            if( idx_posMax == posN_est ) min_idx_pos = i;
+            ZOOPS_FDR_.push_back( FP / ( TP + FP ) );
+            ZOOPS_Rec_.push_back( TP / ( float )posN );
+        }
+        occ_frac_ = 1.0f - ZOOPS_FP_[min_idx_pos] / ( float )posN;
+    }
+}
+
+// reference: FDR::calculatePvalues, src/evaluation/FDR.cpp:278-332
+void FDR::calculatePvalues(){
+    auto rank = []( std::vector<float>& neg, std::vector<float>& pos, std::vector<float>& out ){
+        std::sort( neg.begin(), neg.end(), std::less<float>() );
+        std::sort( pos.begin(), pos.end(), std::less<float>() );
+        for( size_t i = 0; i < pos.size(); i++ ){
+            const size_t low = std::distance( neg.begin(), std::lower_bound( neg.begin(), neg.end(), pos[i] ) );
+            const size_t up = std::distance( neg.begin(), std::upper_bound( neg.begin(), neg.end(), pos[i] ) );
+            float p = 1.0f - ( float )( up + low ) / ( 2.0f * ( float )neg.size() );
+            if( p < 1.e-6 ) p = 1.e-6;
+            if( p > 1.0f ) p = 1.0f;
+            out.push_back( p );
+        }
+    };
+    if( mops_ ) rank( negScoreAll_, posScoreAll_, MOPS_Pvalue_ );
+    if( zoops_ ) rank( negScoreMax_, posScoreMax_, ZOOPS_Pvalue_ );
+}
+
+void FDR::print(){}
+
+// file formats: reference FDR::write, src/evaluation/FDR.cpp:338-450
+void FDR::write( char* odir, std::string basename ){
+    const std::string opath = std::string( odir ) + '/' + basename;
+    if( savePRs_ ){
+        if( zoops_ ){
+            std::ofstream out( opath + ".zoops.stats" );
+            out << "TP" << '\t' << "FP" << '\t' << "FDR" << '\t' << "Recall" << '\t' << "p-value" << '\t'
+                << ( float )negSeqs_.size() / ( float )posSeqs_.size() << '\t' << occ_frac_ << std::endl;
+            for( size_t i = 0; i < ZOOPS_FDR_.size(); i++ ){
+                out << ZOOPS_TP_[i] << '\t' << ZOOPS_FP_[i] << '\t' << ZOOPS_FDR_[i] << '\t' << ZOOPS_Rec_[i] << '\t'
+                    << PN_Pvalue_[i] << '\t' << std::endl;
+            }
+        }
+        if( mops_ ){
+            std::ofstream out( opath + ".mops.stats" );
+            out << "TP" << '\t' << "FP" << '\t' << "FDR" << '\t' << "Recall" << '\t' << occ_mult_ << std::endl;
+            for( size_t i = 0; i < MOPS_FDR_.size(); i++ ){
+                out << MOPS_TP_[i] << '\t' << MOPS_FP_[i] << '\t' << MOPS_FDR_[i] << '\t' << MOPS_Rec_[i] << '\t' << std::endl;
+            }
+        }
+    }
+    if( savePvalues_ ){
+        if( zoops_ ){
+            std::ofstream out( opath + ".zoops.pvalues" );
+            for( float p : ZOOPS_Pvalue_ ) out << std::setprecision( 3 ) << p << std::endl;
+        }
+        if( mops_ ){
+            std::ofstream out( opath + ".mops.pvalues" );
+            for( float p : MOPS_Pvalue_ ) out << std::setprecision( 3 ) << p << std::endl;
+        }
+    }
+    if( saveLogOdds_ ){
+        if( zoops_ ){
+            std::ofstream out( opath + ".zoops.logOdds" );
+            out << "positive" << '\t' << "negative" << std::endl;
+            for( size_t i = 0; i < posScoreMax_.size(); i++ ){
+                out << std::setprecision( 6 ) << posScoreMax_[i] << '\t' << at( negScoreMax_, i * negSeqs_.size() / posSeqs_.size() ) << std::endl;
+            }
+        }
+        if( mops_ ){
+            std::ofstream out( opath + ".mops.logOdds" );
+            out << "positive" << '\t' << "negative" << std::endl;
+            for( size_t i = 0; i < posScoreAll_.size(); i++ ){
+                out << std::setprecision( 6 ) << posScoreAll_[i] << '\t' << at( negScoreAll_, i * negSeqs_.size() / posSeqs_.size() ) << std::endl;
+            }
+        }
+    }
+}
+
+void FDR::saveUnsortedLogOdds( std::string opath, std::vector<float> logOdds ){
+    std::ofstream ofile( opath );
+    for( size_t i = 0; i < logOdds.size(); i++ ) ofile << i + 1 << '\t' << std::setprecision( 6 ) << logOdds[i] << std::endl;
+}

@@ -1,0 +1,309 @@
+#include "Global.h"
+
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <sstream>
+
+#include "Util.h"
+
+char*               Global::outputDirectory = NULL;
+std::string         Global::outputFileBasename;
+char*               Global::posSequenceFilename = NULL;
+std::string         Global::posSequenceBasename;
+SequenceSet*        Global::posSequenceSet = NULL;
+char*               Global::negSequenceFilename = NULL;
+std::string         Global::negSequenceBasename;
+SequenceSet*        Global::negSequenceSet = NULL;
+bool                Global::negSeqGiven = false;
+bool                Global::genericNeg = false;
+std::string         Global::alphabetType = "STANDARD";
+bool                Global::ss = false;
+char*               Global::initialModelFilename = NULL;
+std::string         Global::initialModelBasename;
+std::string         Global::initialModelTag;
+size_t              Global::maxPWM = std::numeric_limits<size_t>::max();
+bool                Global::mops = false;
+bool                Global::zoops = true;
+size_t              Global::modelOrder = 2;
+std::vector<float>  Global::modelAlpha( 3, 1.f );
+float               Global::modelBeta = 7.0f;
+float               Global::modelGamma = 3.0f;
+std::vector<size_t> Global::addColumns( 2 );
+bool                Global::interpolateBG = true;
+char*               Global::bgModelFilename = NULL;
+bool                Global::bgModelGiven = false;
+size_t              Global::bgModelOrder = 2;
+std::vector<float>  Global::bgModelAlpha( 3, 1.f );
+bool                Global::EM = false;
+float               Global::q = 0.3f;
+bool                Global::optimizeQ = false;
+float               Global::f = 0.05f;
+bool                Global::CGS = false;
+bool                Global::advanceEM = false;
+bool                Global::FDR = false;
+size_t              Global::mFold = 1;
+size_t              Global::cvFold = 4;
+size_t              Global::sOrder = 2;
+bool                Global::scoreSeqset = false;
+float               Global::pvalCutoff = 0.0001f;
+bool                Global::verbose = false;
+bool                Global::debugMode = false;
+bool                Global::saveBaMMs = true;
+bool                Global::savePRs = true;
+bool                Global::savePvalues = false;
+bool                Global::saveLogOdds = false;
+bool                Global::saveInitialBaMMs = false;
+bool                Global::saveBgModel = false;
+size_t              Global::threads = 4;
+
+namespace {
+
+// "--name v1 v2", "-k v": every option keeps the values up to the next option. A token is an option when it starts
+// with '-' and does not look like a number.
+class Options {
+public:
+    Options( int n, char* a[] ){
+        std::string current;
+        for( int i = 1; i < n; i++ ){
+            const std::string t( a[i] );
+            const bool numeric = t.size() > 1 && t[0] == '-' && ( isdigit( ( unsigned char )t[1] ) || t[1] == '.' );
+            if( t.size() > 1 && t[0] == '-' && !numeric ){
+                current = t.substr( t[1] == '-' ? 2 : 1 );
+                values_[current];
+                argPtr_[current] = nullptr;
+            } else if( !current.empty() ){
+                values_[current].push_back( t );
+                if( !argPtr_[current] ) argPtr_[current] = a[i];
+            }
+        }
+    }
+    // a flag: true when either spelling is on the command line; consumed
+    bool present( const std::string& longName, char shortName = 0 ){
+        bool found = false;
+        for( const std::string& key : keys( longName, shortName ) ){
+            auto it = values_.find( key );
+            if( it != values_.end() ){ found = true; seen_[key] = true; }
+        }
+        return found;
+    }
+    template <typename T> bool value( const std::string& longName, char shortName, T& out ){
+        for( const std::string& key : keys( longName, shortName ) ){
+            auto it = values_.find( key );
+            if( it == values_.end() ) continue;
+            seen_[key] = true;
+            if( it->second.empty() ) return false;
+            std::stringstream in( it->second[0] );
+            in >> out;
+            return true;
+        }
+        return false;
+    }
+    bool cstr( const std::string& longName, char*& out ){
+        auto it = values_.find( longName );
+        if( it == values_.end() ) return false;
+        seen_[longName] = true;
+        if( !argPtr_[longName] ) return false;
+        out = argPtr_[longName];
+        return true;
+    }
+    template <typename T> bool list( const std::string& longName, char shortName, std::vector<T>& out ){
+        for( const std::string& key : keys( longName, shortName ) ){
+            auto it = values_.find( key );
+            if( it == values_.end() ) continue;
+            seen_[key] = true;
+            for( const std::string& s : it->second ){ std::stringstream in( s ); T v; in >> v; out.push_back( v ); }
+            return true;
+        }
+        return false;
+    }
+    bool leftovers() const {
+        for( const auto& kv : values_ ) if( !seen_.count( kv.first ) ) return true;
+        return false;
+    }
+private:
+    static std::vector<std::string> keys( const std::string& longName, char shortName ){
+        std::vector<std::string> k;
+        if( !longName.empty() ) k.push_back( longName );
+        if( shortName ) k.push_back( std::string( 1, shortName ) );
+        return k;
+    }
+    std::map<std::string, std::vector<std::string>> values_;
+    std::map<std::string, char*> argPtr_;
+    std::map<std::string, bool> seen_;
+};
+
+template <typename T> void fitLength( std::vector<T>& v, size_t n ){
+    if( v.size() > n ) v.resize( n );
+    else if( v.size() < n ) v.resize( n, v.back() );
+}
+
+}  // namespace
+
+void Global::init( int nargs, char* args[] ){
+    readArguments( nargs, args );
+    Alphabet::init( alphabetType.c_str() );
+    // positive set first, then the (by default identical) negative file: the order fixes the rand() stream of the
+    // N draws (reference: Global.cpp:105-106)
+    posSequenceSet = new SequenceSet( posSequenceFilename, ss );
+    negSequenceSet = new SequenceSet( negSequenceFilename, ss );
+    if( posSequenceSet->getSequences().size() < cvFold ){
+        std::cerr << "Error: Input sequences are too few for training! \n" << std::endl;
+        exit( 1 );
+    }
+}
+
+int Global::readArguments( int nargs, char* args[] ){
+    if( nargs < 3 ){
+        std::cerr << "Error: Arguments are missing! \n" << std::endl;
+        printHelp();
+        exit( 1 );
+    }
+    outputDirectory = args[1];
+    util::createDirectory( outputDirectory );
+    posSequenceFilename = args[2];
+    posSequenceBasename = util::baseName( posSequenceFilename );
+
+    Options opt( nargs - 2, args + 2 );
+    if( opt.present( "help", 'h' ) ){ printHelp(); exit( 1 ); }
+
+    if( !opt.value( "basename", 0, outputFileBasename ) ) outputFileBasename = posSequenceBasename;
+    bool ignored;
+    ignored = opt.present( "maskPosSequenceSet" );
+
+    if( opt.cstr( "negSeqFile", negSequenceFilename ) ) negSeqGiven = true;
+    else negSequenceFilename = posSequenceFilename;
+    negSequenceBasename = util::baseName( negSequenceFilename );
+    genericNeg = opt.present( "genericNeg" );
+
+    opt.value( "alphabet", 0, alphabetType );
+    ss = opt.present( "ss" );
+    { std::string unused; opt.value( "intensityFile", 0, unused ); }
+
+    if( opt.cstr( "bindingSiteFile", initialModelFilename ) )   initialModelTag = "bindingsites";
+    else if( opt.cstr( "PWMFile", initialModelFilename ) )      initialModelTag = "PWM";
+    else if( opt.cstr( "BaMMFile", initialModelFilename ) )     initialModelTag = "BaMM";
+    else {
+        fprintf( stderr, "Error: No initial model is provided.\n" );
+        exit( 1 );
+    }
+    initialModelBasename = util::baseName( initialModelFilename );
+
+    opt.value( "maxPWM", 0, maxPWM );
+    mops = opt.present( "mops" );
+    opt.value( "zoops", 0, zoops );
+
+    opt.value( "order", 'k', modelOrder );
+    std::vector<float> alphaList;
+    if( opt.list( "alpha", 'a', alphaList ) && !alphaList.empty() ){
+        modelAlpha = alphaList;
+        fitLength( modelAlpha, modelOrder + 1 );
+    } else {
+        fitLength( modelAlpha, modelOrder + 1 );
+        opt.value( "beta", 'b', modelBeta );
+        opt.value( "gamma", 'r', modelGamma );
+        for( size_t k = 1; k < modelOrder + 1; k++ ) modelAlpha[k] = modelBeta * powf( modelGamma, ( float )k );
+    }
+
+    std::vector<size_t> extend;
+    if( opt.list( "extend", 0, extend ) ){
+        if( extend.size() < 1 || extend.size() > 2 ){
+            fprintf( stderr, "--extend format error.\n" );
+            exit( 1 );
+        }
+        if( extend.size() == 1 ) extend.push_back( extend.back() );
+        addColumns = extend;
+    } else {
+        addColumns.assign( 2, 0 );
+    }
+
+    if( opt.cstr( "bgModelFile", bgModelFilename ) ) bgModelGiven = true;
+    opt.value( "Order", 'K', bgModelOrder );
+    std::vector<float> bgAlphaList;
+    if( opt.list( "Alpha", 'A', bgAlphaList ) && !bgAlphaList.empty() ){
+        bgModelAlpha = bgAlphaList;
+        fitLength( bgModelAlpha, bgModelOrder + 1 );
+    } else {
+        fitLength( bgModelAlpha, bgModelOrder + 1 );
+        for( size_t k = 1; k < bgModelOrder + 1; k++ ) bgModelAlpha[k] = 10.0f;
+    }
+
+    EM = opt.present( "EM" );
+    CGS = opt.present( "CGS" );
+    if( CGS ){
+        for( const char* sub : { "noInitialZ", "noAlphaOpti", "GibbsMH", "dissample", "noZSampling", "noQSampling" } ) ignored = opt.present( sub );
+    }
+    ignored = opt.present( "debugAlphas" );
+    ignored = opt.present( "generatePseudoSet" );
+
+    opt.value( "", 'q', q );
+    opt.value( "", 'f', f );
+
+    FDR = opt.present( "FDR" );
+    if( FDR ){
+        opt.value( "mFold", 'm', mFold );
+        opt.value( "cvFold", 'n', cvFold );
+        opt.value( "sOrder", 's', sOrder );
+    }
+    scoreSeqset = opt.present( "scoreSeqset" );
+    opt.value( "pvalCutoff", 0, pvalCutoff );
+
+    // presence decides: absent means false whatever the compiled-in default says
+    verbose = opt.present( "verbose" );
+    debugMode = opt.present( "debug" );
+    saveBaMMs = opt.present( "saveBaMMs" );
+    saveInitialBaMMs = opt.present( "saveInitialBaMMs" );
+    opt.value( "savePRs", 0, savePRs );
+    savePvalues = opt.present( "savePvalues" );
+    saveLogOdds = opt.present( "saveLogOdds" );
+    saveBgModel = opt.present( "saveBgModel" );
+    ignored = opt.present( "makeMovie" );
+    optimizeQ = opt.present( "optimizeQ" );
+    ignored = opt.present( "B2" );
+    ignored = opt.present( "B3" );
+    ignored = opt.present( "B3prime" );
+    advanceEM = opt.present( "advanceEM" );
+    opt.value( "threads", 0, threads );
+    ( void )ignored;
+
+    if( opt.leftovers() ){
+        printHelp();
+        std::cerr << "Oops! Unknown option(s) remaining... \n\n";
+        exit( 1 );
+    }
+    return 0;
+}
+
+void Global::destruct(){
+    Alphabet::destruct();
+    delete posSequenceSet;
+    delete negSequenceSet;
+    posSequenceSet = negSequenceSet = NULL;
+}
+
+void Global::printHelp(){
+    printf( "\nSYNOPSIS\n      BaMMmotif OUTDIR SEQFILE [OPTIONS]\n\n"
+            "  initial model:   --bindingSiteFile F | --PWMFile F [--maxPWM N] | --BaMMFile F     [--extend L [R]]\n"
+            "  model:           -k/--order K   -a/--alpha a0 a1 ..  |  -b/--beta B  -r/--gamma G   -q Q  --optimizeQ\n"
+            "  background:      -K/--Order K   -A/--Alpha ..   --bgModelFile F\n"
+            "  sequences:       --ss   --alphabet STANDARD|METHYLC|HYDROXYMETHYLC|EXTENDED   --negSeqFile F\n"
+            "  training:        --EM\n"
+            "  evaluation:      --FDR [-m/--mFold M] [-n/--cvFold N] [-s/--sOrder S]   --scoreSeqset [--pvalCutoff P]\n"
+            "  output:          --basename B --verbose --saveBaMMs --saveInitialBaMMs --savePRs 0|1 --savePvalues --saveLogOdds\n"
+            "  The EM / scoring work runs on one NVIDIA B200 through libbamm_b200.so; there is no CPU fallback.\n\n" );
+}
+
+void Global::printStat(){
+    std::cout << "Alphabet type is " << alphabetType;
+    std::cout << "\nGiven initial model is " << initialModelBasename;
+    std::cout << "\n\nGiven positive sequence set is " << posSequenceBasename << "\n\t" << posSequenceSet->getSequences().size()
+              << " sequences, max.length: " << posSequenceSet->getMaxL() << ", min.length: " << posSequenceSet->getMinL()
+              << "\n\tbase frequencies:";
+    for( size_t i = 0; i < Alphabet::getSize(); i++ ){
+        std::cout << ' ' << posSequenceSet->getBaseFrequencies()[i] << "(" << Alphabet::getAlphabet()[i] << ")";
+    }
+    std::cout << "\n\nModel order is " << modelOrder << ", background order is " << bgModelOrder << "\n";
+    if( EM ) std::cout << "\nOptimizer: EM.\n";
+    if( FDR ) std::cout << "\nFDR: " << cvFold << "-fold cross-validation, mFold = " << mFold << "\n";
+}

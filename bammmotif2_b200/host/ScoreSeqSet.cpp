@@ -1,0 +1,137 @@
+#include "ScoreSeqSet.h"
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+
+ScoreSeqSet::ScoreSeqSet( Motif* motif, BackgroundModel* bg, std::vector<Sequence*> seqSet )
+    : motif_( motif ), bg_( bg ), seqSet_( seqSet ), Y_( motif->getY() ){}
+
+ScoreSeqSet::~ScoreSeqSet(){}
+
+// reference: ScoreSeqSet::calcLogOdds, src/seq_scoring/ScoreSeqSet.cpp:25-67
+void ScoreSeqSet::calcLogOdds(){
+    const size_t K = motif_->getK();
+    const size_t W = motif_->getW();
+    const size_t K_bg = ( bg_->getOrder() < K ) ? bg_->getOrder() : K;
+    // the Motif's own table switches to log odds exactly as in the reference (callers read it through getS());
+    // the device builds the identical table from v with the same libm logf
+    motif_->calculateLogS( bg_->getV(), K_bg );
+
+    const size_t N = seqSet_.size();
+    zoops_scores_.assign( N, 0.0f );
+    z_.assign( N, 0 );
+    mops_off_.assign( N + 1, 0 );
+    for( size_t n = 0; n < N; n++ ) mops_off_[n + 1] = mops_off_[n] + ( seqSet_[n]->getL() - W + 1 );
+    if( keepMops_ ) mops_flat_.assign( mops_off_[N], 0.0f ); else mops_flat_.clear();
+    if( N == 0 ) return;
+
+    std::vector<uint64_t> indices;
+    bool whole = false;
+    SequenceSet* set = SequenceSet::commonSet( seqSet_, indices, &whole );
+    std::vector<uint64_t> z64( N );
+    BAMM_CHECK( bamm_score_logodds( set->device(), whole ? nullptr : indices.data(), N, static_cast<int>( W ), static_cast<int>( K ),
+                                    static_cast<int>( bg_->getOrder() ), motif_->flatV().data(), bg_->flatV().data(),
+                                    zoops_scores_.data(), z64.data(), keepMops_ ? mops_flat_.data() : nullptr ) );
+    for( size_t n = 0; n < N; n++ ) z_[n] = static_cast<size_t>( z64[n] );
+}
+
+std::vector<std::vector<float>> ScoreSeqSet::getMopsScores(){
+    std::vector<std::vector<float>> out( seqSet_.size() );
+    if( mops_flat_.empty() ) return out;
+    for( size_t n = 0; n < seqSet_.size(); n++ ){
+        out[n].assign( mops_flat_.begin() + mops_off_[n], mops_flat_.begin() + mops_off_[n + 1] );
+    }
+    return out;
+}
+
+// Rank p-values of window scores against the sorted negative scores with an exponential tail for the top ranks
+// (reference: ScoreSeqSet::calcPvalues, src/seq_scoring/ScoreSeqSet.cpp:70-126)
+void ScoreSeqSet::calcPvalues( std::vector<std::vector<float>> pos_scores, std::vector<float> neg_all_scores ){
+    const size_t posN = seqSet_.size();
+    const size_t negN = neg_all_scores.size();
+    mops_p_values_.assign( posN, std::vector<float>() );
+    mops_e_values_.assign( posN, std::vector<float>() );
+    const float eps = 1.0e-5;
+
+    std::sort( neg_all_scores.begin(), neg_all_scores.end(), std::less<float>() );
+    const size_t nTop = std::min( 100, ( int )negN / 10 );
+    const float S_ntop = neg_all_scores[nTop];
+    float lambda = 0.f;
+    for( size_t n = 0; n < nTop; n++ ) lambda += ( neg_all_scores[n] - S_ntop );
+    lambda = lambda / ( float )nTop;
+
+    for( size_t n = 0; n < posN; n++ ){
+        const size_t LW1 = seqSet_[n]->getL() - motif_->getW() + 1;
+        mops_p_values_[n].reserve( LW1 );
+        mops_e_values_[n].reserve( LW1 );
+        for( size_t i = 0; i < LW1; i++ ){
+            const float Sl = pos_scores[n][i];
+            const size_t FPl = std::distance( std::upper_bound( neg_all_scores.begin(), neg_all_scores.end(), Sl ), neg_all_scores.end() );
+            float p_value;
+            if( FPl == negN ){
+                p_value = 1.f;
+            } else if( FPl < 10 and fabs( lambda ) > eps ){
+                p_value = float( nTop ) / ( float )negN * expf( - ( Sl - S_ntop ) / lambda );
+            } else {
+                const float SlHigher = neg_all_scores[negN - FPl - 1];
+                const float SlLower = neg_all_scores[negN - FPl];
+                p_value = ( ( float )FPl + ( SlHigher - Sl + eps ) / ( SlHigher - SlLower + eps ) ) / ( float )negN;
+            }
+            mops_p_values_[n].push_back( p_value );
+            mops_e_values_[n].push_back( p_value * ( float )posN );
+        }
+    }
+    pval_is_calulated_ = true;
+}
+
+void ScoreSeqSet::printLogOdds(){
+    for( size_t n = 0; n < seqSet_.size(); n++ ){
+        std::cout << "seq " << n << ":" << std::endl << zoops_scores_[n] << '\t';
+        for( size_t i = mops_off_[n]; i < mops_off_[n + 1] && i < mops_flat_.size(); i++ ) std::cout << mops_flat_[i] << '\t';
+        std::cout << std::endl;
+    }
+}
+
+// .occurrence (reference: ScoreSeqSet::write, src/seq_scoring/ScoreSeqSet.cpp:245-291)
+void ScoreSeqSet::write( char* odir, std::string basename, float pvalCutoff, bool ss ){
+    assert( pval_is_calulated_ );
+    std::ofstream ofile( std::string( odir ) + '/' + basename + ".occurrence" );
+    ofile << "seq\tlength\tstrand\tstart..end\tpattern\tp-value\te-value" << std::endl;
+    const size_t W = motif_->getW();
+    for( size_t n = 0; n < seqSet_.size(); n++ ){
+        size_t seqlen = seqSet_[n]->getL();
+        if( !ss ) seqlen = ( seqlen - 1 ) / 2;
+        const size_t LW1 = seqSet_[n]->getL() - W + 1;
+        const uint8_t* codes = seqSet_[n]->getSequence();
+        for( size_t i = 0; i < LW1; i++ ){
+            if( mops_p_values_[n][i] < pvalCutoff ){
+                const size_t end = i + W;
+                ofile << seqSet_[n]->getHeader() << '\t' << seqlen << '\t' << ( ( i < seqlen ) ? '+' : '-' ) << '\t'
+                      << i + 1 << ".." << end << '\t';
+                for( size_t m = i; m < end; m++ ) ofile << Alphabet::getBase( codes[m] );
+                ofile << '\t' << std::setprecision( 3 ) << mops_p_values_[n][i] << '\t' << mops_e_values_[n][i] << std::endl;
+            }
+        }
+    }
+}
+
+// .logOddsZoops (reference: ScoreSeqSet::writeLogOdds, src/seq_scoring/ScoreSeqSet.cpp:293-331)
+void ScoreSeqSet::writeLogOdds( char* odir, std::string basename, bool ss ){
+    std::ofstream ofile( std::string( odir ) + '/' + basename + ".logOddsZoops" );
+    ofile << "seq\tlength\tstrand\tstart..end\tpattern\tzoops_score" << std::endl;
+    const size_t W = motif_->getW();
+    for( size_t n = 0; n < seqSet_.size(); n++ ){
+        size_t seqlen = seqSet_[n]->getL();
+        if( !ss ) seqlen = ( seqlen - 1 ) / 2;
+        const uint8_t* codes = seqSet_[n]->getSequence();
+        const size_t end = z_[n] + W;
+        ofile << seqSet_[n]->getHeader() << '\t' << seqlen << '\t' << ( ( z_[n] < seqlen ) ? '+' : '-' ) << '\t'
+              << z_[n] + 1 << ".." << end << '\t';
+        for( size_t m = z_[n]; m < end; m++ ) ofile << Alphabet::getBase( codes[m] );
+        ofile << '\t' << std::setprecision( 3 ) << zoops_scores_[n] << std::endl;
+    }
+}

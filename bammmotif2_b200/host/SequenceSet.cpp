@@ -1,0 +1,252 @@
+#include "SequenceSet.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <limits>
+
+namespace {
+inline size_t ipow( size_t base, size_t exp ){
+    size_t r = 1;
+    while( exp-- ) r *= base;
+    return r;
+}
+}
+
+SequenceSet::SequenceSet( std::string sequenceFilepath, bool singleStrand, std::string intensityFilepath )
+    : sequenceFilepath_( sequenceFilepath ), intensityFilepath_( intensityFilepath ){
+
+    if( !intensityFilepath.empty() ){
+        // reference: SequenceSet::readIntensities is a stub that exits (src/init/SequenceSet.cpp:227-231)
+        std::cerr << "Error: sequenceSet::readIntensities() is not implemented so far." << std::endl;
+        std::exit( 1 );
+    }
+    for( size_t k = 0; k < 12; k++ ) Y_.push_back( ipow( Alphabet::getSize(), k ) );
+    offsets_.push_back( 0 );
+
+    std::ifstream file( sequenceFilepath_.c_str() );
+    if( !file.is_open() ){
+        std::cerr << "Error: Cannot open FASTA file: " << sequenceFilepath_ << std::endl;
+        std::exit( 1 );
+    }
+    std::vector<size_t> baseCounts( Alphabet::getSize(), 0 );
+    size_t maxL = 0, minL = std::numeric_limits<size_t>::max();
+    std::string line, header, bases;
+    // a record is flushed when the next '>' line (or the end of the file) is reached; a header without bases is dropped
+    auto flush = [&](){
+        if( header.empty() ) return;
+        if( bases.empty() ){
+            std::cerr << "Warning: Ignore FASTA entry without sequence: " << sequenceFilepath_ << std::endl;
+        } else {
+            maxL = std::max( maxL, bases.length() );
+            minL = std::min( minL, bases.length() );
+            appendRecord( header, bases, singleStrand, baseCounts );
+            bases.clear();
+        }
+        header.clear();
+    };
+    while( std::getline( file, line ) ){
+        if( line.empty() ) continue;
+        if( line[0] == '>' ){
+            flush();
+            if( line.length() == 1 ){
+                header = ">";
+            } else {
+                // header runs to the first tab, and loses a trailing carriage return (reference :137-139)
+                header = line.substr( 0, line.find( '\t' ) );
+                header = header.substr( 0, header.find( '\r' ) );
+            }
+        } else if( !header.empty() ){
+            if( line.find( ' ' ) != std::string::npos ){
+                std::cerr << "Error: FASTA sequence contains space character: " << sequenceFilepath_ << std::endl;
+                std::exit( 1 );
+            }
+            bases += line;
+        } else {
+            std::cerr << "Error: Wrong FASTA format: " << sequenceFilepath_ << std::endl;
+            std::exit( 1 );
+        }
+    }
+    flush();
+    minL_ = minL;
+    maxL_ = maxL;
+
+    size_t total = 0;
+    for( size_t c : baseCounts ) total += c;
+    baseFrequencies_.resize( Alphabet::getSize() );
+    for( size_t a = 0; a < baseCounts.size(); a++ ){
+        baseFrequencies_[a] = static_cast<float>( baseCounts[a] ) / static_cast<float>( total );
+    }
+    finalize();
+}
+
+SequenceSet::SequenceSet( std::vector<uint8_t> storedCodes, std::vector<uint64_t> offsets, std::string header )
+    : codes_( std::move( storedCodes ) ), offsets_( std::move( offsets ) ), sharedHeader_( std::move( header ) ){
+    for( size_t k = 0; k < 12; k++ ) Y_.push_back( ipow( Alphabet::getSize(), k ) );
+    if( offsets_.empty() ) offsets_.push_back( 0 );
+    size_t maxL = 0, minL = std::numeric_limits<size_t>::max();
+    for( size_t n = 0; n + 1 < offsets_.size(); n++ ){
+        const size_t L = static_cast<size_t>( offsets_[n + 1] - offsets_[n] );
+        maxL = std::max( maxL, L );
+        minL = std::min( minL, L );
+        drawPatches( offsets_[n], offsets_[n + 1] );       // no-op (and no rand() call) when the record has no code 0
+    }
+    minL_ = minL;
+    maxL_ = maxL;
+    baseFrequencies_.assign( Alphabet::getSize(), 0.0f );
+    finalize();
+}
+
+SequenceSet::SequenceSet( Build, std::string header ) : sharedHeader_( std::move( header ) ){
+    for( size_t k = 0; k < 12; k++ ) Y_.push_back( ipow( Alphabet::getSize(), k ) );
+    offsets_.push_back( 0 );
+    minL_ = std::numeric_limits<size_t>::max();
+    baseFrequencies_.assign( Alphabet::getSize(), 0.0f );
+}
+
+void SequenceSet::appendStoredRecord( const uint8_t* storedCodes, size_t L ){
+    const uint64_t begin = codes_.size();
+    codes_.insert( codes_.end(), storedCodes, storedCodes + L );
+    offsets_.push_back( codes_.size() );
+    maxL_ = std::max( maxL_, L );
+    minL_ = std::min( minL_, L );
+    drawPatches( begin, codes_.size() );
+}
+
+void SequenceSet::finishBuild(){
+    handles_.clear();
+    finalize();
+}
+
+SequenceSet::~SequenceSet(){
+    if( device_ ) bamm_seqset_destroy( device_ );
+}
+
+void SequenceSet::appendRecord( const std::string& header, const std::string& bases, bool singleStrand,
+                                std::vector<size_t>& baseCounts ){
+    const size_t L0 = bases.length();
+    const uint64_t begin = codes_.size();
+    codes_.resize( begin + ( singleStrand ? L0 : 2 * L0 + 1 ), 0 );
+    uint8_t* dst = codes_.data() + begin;
+    for( size_t i = 0; i < L0; i++ ){
+        const uint8_t c = Alphabet::getCode( bases[i] );
+        dst[i] = c;
+        if( c ) baseCounts[c - 1]++;                       // undefined bases are not counted (reference :99-108)
+    }
+    if( !singleStrand ){
+        // forward | 0 | reverse complement  (reference: Sequence::appendRevComp, src/init/Sequence.cpp:91-99)
+        for( size_t i = 0; i < L0; i++ ) dst[2 * L0 - i] = Alphabet::getComplementCode( dst[i] );
+    }
+    headers_.push_back( header );
+    offsets_.push_back( codes_.size() );
+    drawPatches( begin, codes_.size() );
+}
+
+// Positions whose 11-mer hash contains a code-0 base: the reference replaces the 0 by rand() % A separately for every
+// (position, k) pair while it builds kmer_ (src/init/Sequence.cpp:35-41). The draws are made here in the same order
+// (records in file order, i ascending, bases of the k-mer from oldest to newest), so the libc rand() stream — and with
+// it every later consumer of rand() — stays aligned with the reference.
+void SequenceSet::drawPatches( uint64_t begin, uint64_t end ){
+    const uint8_t* c = codes_.data() + begin;
+    const size_t L = static_cast<size_t>( end - begin );
+    const size_t A = Y_[1];
+    size_t next = 0;                                        // first position not yet examined
+    for( size_t z = 0; z < L; z++ ){
+        if( c[z] != 0 ) continue;
+        const size_t last = std::min( L - 1, z + 10 );
+        for( size_t i = std::max( next, z ); i <= last; i++ ){
+            const size_t span = i < 10 ? i + 1 : 11;        // bases i-span+1 .. i
+            size_t h = 0;
+            for( size_t k = span; k > 0; k-- ){
+                const uint8_t code = c[i - k + 1];
+                const size_t digit = ( code == 0 ) ? static_cast<size_t>( rand() ) % A : static_cast<size_t>( code - 1 );
+                h += digit * Y_[k - 1];
+            }
+            patchPos_.push_back( begin + i );
+            patchKmer_.push_back( h );
+        }
+        next = std::max( next, last + 1 );
+    }
+}
+
+void SequenceSet::finalize(){
+    const size_t N = offsets_.size() - 1;
+    handles_.reserve( N );
+    for( size_t n = 0; n < N; n++ ) handles_.emplace_back( this, n );
+}
+
+std::vector<Sequence*> SequenceSet::getSequences(){
+    std::vector<Sequence*> out( handles_.size() );
+    for( size_t n = 0; n < handles_.size(); n++ ) out[n] = &handles_[n];
+    return out;
+}
+
+size_t SequenceSet::kmerAt( size_t n, size_t i ) const {
+    const uint64_t g = offsets_[n] + i;
+    auto it = std::lower_bound( patchPos_.begin(), patchPos_.end(), g );
+    if( it != patchPos_.end() && *it == g ) return static_cast<size_t>( patchKmer_[it - patchPos_.begin()] );
+    const uint8_t* c = codes_.data() + offsets_[n];
+    const size_t span = i < 10 ? i + 1 : 11;
+    size_t h = 0;
+    for( size_t t = 0; t < span; t++ ) h += static_cast<size_t>( c[i - t] - 1 ) * Y_[t];
+    return h;
+}
+
+size_t* SequenceSet::kmersOf( size_t n ){
+    std::call_once( kmersOnce_, [this](){
+        kmers_.assign( codes_.size(), 0 );
+        for( size_t s = 0; s + 1 < offsets_.size(); s++ ){
+            const uint8_t* c = codes_.data() + offsets_[s];
+            size_t* km = kmers_.data() + offsets_[s];
+            const size_t L = static_cast<size_t>( offsets_[s + 1] - offsets_[s] );
+            for( size_t i = 0; i < L; i++ ){
+                const size_t span = i < 10 ? i + 1 : 11;
+                size_t h = 0;
+                for( size_t t = 0; t < span; t++ ) h += static_cast<size_t>( c[i - t] - 1 ) * Y_[t];
+                km[i] = h;
+            }
+        }
+        for( size_t p = 0; p < patchPos_.size(); p++ ) kmers_[patchPos_[p]] = static_cast<size_t>( patchKmer_[p] );
+    } );
+    return kmers_.data() + offsets_[n];
+}
+
+bamm_seqset* SequenceSet::device(){
+    std::lock_guard<std::mutex> guard( deviceMutex_ );
+    if( !device_ ){
+        BAMM_CHECK( bamm_seqset_create( codes_.data(), offsets_.data(), offsets_.size() - 1, static_cast<int>( Alphabet::getSize() ),
+                                        patchPos_.data(), patchKmer_.data(), patchPos_.size(), &device_ ) );
+    }
+    return device_;
+}
+
+SequenceSet* SequenceSet::commonSet( const std::vector<Sequence*>& seqs, std::vector<uint64_t>& indices, bool* isWholeSet ){
+    indices.clear();
+    if( seqs.empty() ){
+        std::cerr << "Error: empty sequence list." << std::endl;
+        std::exit( 1 );
+    }
+    SequenceSet* set = seqs[0]->getSet();
+    indices.reserve( seqs.size() );
+    bool identity = seqs.size() == set->size();
+    for( size_t n = 0; n < seqs.size(); n++ ){
+        if( seqs[n]->getSet() != set ){
+            std::cerr << "Error: sequences of one EM / scoring call must come from one SequenceSet." << std::endl;
+            std::exit( 1 );
+        }
+        indices.push_back( seqs[n]->getIndex() );
+        identity = identity && seqs[n]->getIndex() == n;
+    }
+    if( isWholeSet ) *isWholeSet = identity;
+    return set;
+}
+
+void Sequence::print(){
+    std::cout << ">" << getHeader() << std::endl;
+    const uint8_t* c = getSequence();
+    for( size_t i = 0; i < getL(); i++ ) std::cout << Alphabet::getBase( c[i] );
+    std::cout << std::endl;
+}
+
+void SequenceSet::print(){}

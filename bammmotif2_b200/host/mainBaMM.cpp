@@ -1,0 +1,134 @@
+// BaMMmotif driver on the B200 path: same command line, same outputs as the reference's
+// src/refinement/mainBaMM.cpp (flow: background model -> initial motifs -> EM per motif -> optional occurrence scoring
+// -> optional cross-validated FDR). The Gibbs optimiser is not available here.
+#include <chrono>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+
+#include "EM.h"
+#include "FDR.h"
+#include "Global.h"
+#include "ScoreSeqSet.h"
+#include "SeqGenerator.h"
+
+int main( int nargs, char* args[] ){
+    auto t0_wall = std::chrono::high_resolution_clock::now();
+    std::cout << std::endl
+              << "======================================" << std::endl
+              << "=      Welcome to use BaMM!motif     =" << std::endl
+              << "=          Version 2.0 (B200 path)   =" << std::endl
+              << "======================================" << std::endl;
+
+    srand( 42 );                                    // reference: mainBaMM.cpp:22
+    Global::init( nargs, args );
+    if( Global::CGS ){
+        std::cerr << "Error: collapsed Gibbs sampling (--CGS) is not part of the B200 path; use --EM." << std::endl;
+        return 1;
+    }
+    if( const char* dev = getenv( "BAMM_DEVICE" ) ) BAMM_CHECK( bamm_set_device( atoi( dev ) ) );
+
+    std::vector<Sequence*> posSet = Global::posSequenceSet->getSequences();
+
+    BackgroundModel* bgModel = Global::bgModelGiven
+        ? new BackgroundModel( Global::bgModelFilename )
+        : new BackgroundModel( posSet, Global::bgModelOrder, Global::bgModelAlpha, Global::interpolateBG, Global::outputFileBasename );
+    bgModel->write( Global::outputDirectory, Global::outputFileBasename );      // always written (mainBaMM.cpp:51)
+
+    MotifSet motif_set( Global::initialModelFilename, Global::addColumns.at( 0 ), Global::addColumns.at( 1 ), Global::initialModelTag,
+                        Global::posSequenceSet, bgModel->getV(), Global::bgModelOrder, Global::modelOrder, Global::modelAlpha,
+                        Global::maxPWM, Global::q );
+
+    // sequences shorter than the widest motif cannot hold a window (mainBaMM.cpp:75-83)
+    {
+        std::vector<Sequence*> kept;
+        for( Sequence* s : posSet ) if( s->getL() >= motif_set.getMaxW() ) kept.push_back( s );
+        posSet.swap( kept );
+    }
+    const size_t posN = posSet.size();
+    if( posN < Global::cvFold ){
+        std::cerr << "There are " << posN << " sequences longer than input motif. Exit!\n";
+        exit( 1 );
+    }
+
+    // small sets get more negatives per positive (mainBaMM.cpp:100-106; `rest` is a bool in the reference)
+    const size_t minSeqN = 5000;
+    const bool rest = minSeqN % posSet.size();
+    if( posSet.size() < minSeqN ) Global::mFold = minSeqN / posSet.size() + rest;
+
+    // The reference samples the negative set on every run; nothing reads it (or the rand() state it leaves) unless
+    // --FDR / --scoreSeqset is given, so it is sampled only then.
+    std::unique_ptr<SequenceSet> negSequences;
+    std::vector<Sequence*> negSet;
+    if( Global::FDR || Global::scoreSeqset ){
+        SeqGenerator negseq( posSet, NULL, Global::sOrder, 1.0f, Global::genericNeg );
+        negSequences = negseq.sample_bgseqset_by_fold( Global::mFold );
+        negSet = negSequences->getSequences();
+    }
+
+    for( size_t n = 0; n < motif_set.getN(); n++ ){
+        Motif* motif = new Motif( *motif_set.getMotifs()[n] );
+        const std::string motifName = Global::outputFileBasename + "_motif_" + std::to_string( n + 1 );
+        if( Global::saveInitialBaMMs ){
+            motif->write( Global::outputDirectory, Global::outputFileBasename + "_init_motif_" + std::to_string( n + 1 ) );
+        }
+        if( Global::EM ){
+            EM model( motif, bgModel, posSet, Global::optimizeQ, Global::verbose, Global::f );
+            if( !Global::advanceEM ) model.optimize(); else model.mask();
+            if( Global::saveBaMMs ) model.write( Global::outputDirectory, motifName, Global::ss );
+            std::cout << "optimized q = " << model.getQ() << std::endl;
+        } else {
+            std::cout << "Note: the model is not optimized!\n";
+        }
+        motif->write( Global::outputDirectory, motifName );                        // always written (mainBaMM.cpp:169-170)
+
+        if( Global::scoreSeqset ){
+            BackgroundModel* bg = bgModel;
+            if( !Global::EM ){
+                if( Global::initialModelTag == "BaMM" ){
+                    if( Global::bgModelFilename == NULL ){
+                        std::cout << "No background Model file provided for initial search motif!\n";
+                        exit( 1 );
+                    }
+                    bg = new BackgroundModel( Global::bgModelFilename );
+                } else if( Global::initialModelTag == "PWM" ){
+                    Global::modelOrder = 0;
+                }
+            }
+            ScoreSeqSet scoreNegSet( motif, bgModel, negSet );
+            scoreNegSet.calcLogOdds();
+            if( Global::saveLogOdds ) scoreNegSet.writeLogOdds( Global::outputDirectory, Global::outputFileBasename + ".negSet", Global::ss );
+            std::vector<float> negScores = scoreNegSet.flatMopsScores();            // all window scores of all negatives
+
+            ScoreSeqSet scorePosSet( motif, bg, posSet );
+            scorePosSet.calcLogOdds();
+            if( Global::saveLogOdds ) scorePosSet.writeLogOdds( Global::outputDirectory, motifName, Global::ss );
+            scorePosSet.calcPvalues( scorePosSet.getMopsScores(), negScores );
+            scorePosSet.write( Global::outputDirectory, motifName, Global::pvalCutoff, Global::ss );
+            if( bg != bgModel ) delete bg;
+        }
+        delete motif;
+    }
+
+    if( Global::FDR ){
+        for( size_t n = 0; n < motif_set.getN(); n++ ){
+            Motif* motif = new Motif( *motif_set.getMotifs()[n] );
+            FDR fdr( posSet, negSet, motif, bgModel, Global::cvFold, Global::mops, Global::zoops,
+                     Global::savePRs, Global::savePvalues, Global::saveLogOdds );
+            fdr.evaluateMotif( Global::EM, Global::CGS, Global::optimizeQ, Global::advanceEM, Global::f );
+            fdr.write( Global::outputDirectory, Global::outputFileBasename + "_motif_" + std::to_string( n + 1 ) );
+            delete motif;
+        }
+    }
+
+    std::cout << std::endl << "******************" << std::endl << "*   Statistics   *" << std::endl << "******************" << std::endl;
+    Global::printStat();
+    auto t1_wall = std::chrono::high_resolution_clock::now();
+    auto t_diff = std::chrono::duration_cast<std::chrono::duration<double>>( t1_wall - t0_wall );
+    std::cout << std::endl << "------ Runtime: " << t_diff.count() << " seconds -------" << std::endl;
+
+    negSequences.reset();
+    delete bgModel;
+    Global::destruct();
+    return 0;
+}

@@ -1,0 +1,179 @@
+"""C++ host side (bammmotif2_b200/host: the reference's class surface over the C ABI).
+
+CPU tests (no device): FASTA parsing + encoding + N draws, background arithmetic and file format, binding-site
+initialisation, negative-set sampling and the FDR statistics, each against the golden vectors made from the reference
+(bit-exact: integer work and sequential fp32 host arithmetic in the reference's operation order).
+GPU tests (-m gpu): the drop-in CLI bin/BaMMmotif end to end against the files the reference wrote for the same command.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import CASES, Golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "bammmotif2_b200", "bin")
+
+
+@pytest.fixture(scope="module")
+def bins():
+    from bammmotif2_b200 import build
+    build.build_all()
+    return BIN
+
+
+def write_inputs(g, d, name="in"):
+    fa, bs = os.path.join(d, name + ".fasta"), os.path.join(d, "sites.block")
+    open(fa, "wb").write(bytes(g["fasta_text"]))
+    open(bs, "wb").write(bytes(g["sites_text"]))
+    return fa, bs
+
+
+def run(cmd, **kw):
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, **kw)
+    assert p.returncode == 0, "%s\n%s\n%s" % (" ".join(cmd), p.stdout[-2000:], p.stderr[-2000:])
+    return p
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fasta_encoding_and_kmers_bit_exact(bins, case, tmp_path):
+    g = Golden(case)
+    fa, _ = write_inputs(g, str(tmp_path))
+    run([os.path.join(bins, "host_check"), "encode", g.alphabet, fa, "1" if g.ss else "0", str(tmp_path)])
+    assert np.array_equal(np.fromfile(tmp_path / "codes.u8", np.uint8), g["pos_codes"])
+    assert np.array_equal(np.fromfile(tmp_path / "offsets.u64", np.uint64), g["pos_offsets"])
+    # includes the rand() draws for N bases: same libc stream, same order as the reference
+    assert np.array_equal(np.fromfile(tmp_path / "kmer.u64", np.uint64), g["pos_kmer"])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_background_and_site_init_bit_exact(bins, case, tmp_path):
+    g = Golden(case)
+    _, bs = write_inputs(g, str(tmp_path))
+    g["bg_n"].tofile(tmp_path / "bgn.u64")
+    g.bg_alpha().tofile(tmp_path / "abg.f32")
+    run([os.path.join(bins, "host_check"), "init", g.alphabet, str(g.K), str(g.K_bg_model), str(tmp_path / "bgn.u64"),
+         str(tmp_path / "abg.f32"), bs, repr(float(g.q)), str(tmp_path)])
+    assert np.array_equal(np.fromfile(tmp_path / "bg_v.f32", np.float32), g["bg_v"])
+    assert np.array_equal(np.fromfile(tmp_path / "v_init.f32", np.float32), g["m1_v_init"])
+    hb = [k for k in g.z.files if k.endswith("_hbcp") and "motif" not in k][0]
+    assert open(tmp_path / "check.hbcp", "rb").read() == bytes(g[hb])                 # file format is contract
+    assert open(tmp_path / "check.hbp", "rb").read() == bytes(g[hb[:-4] + "hbp"])
+
+
+def test_negative_sampling_bit_exact(bins, tmp_path):
+    g = Golden("syn_k3_fdr")
+    fa, _ = write_inputs(g, str(tmp_path))
+    run([os.path.join(bins, "host_check"), "neg", "STANDARD", fa, "0", str(g.meta["mFold"]), "2", str(tmp_path)])
+    assert np.array_equal(np.fromfile(tmp_path / "neg_codes.u8", np.uint8), g["neg_codes"])
+    assert np.array_equal(np.fromfile(tmp_path / "neg_offsets.u64", np.uint64), g["neg_offsets"])
+
+
+@pytest.mark.parametrize("case", ["jund_k2", "syn_k3_fdr"])
+def test_fdr_statistics_bit_exact(bins, case, tmp_path):
+    g = Golden(case)
+    g["m1_fdr_posScoreMax"].tofile(tmp_path / "pos.f32")
+    g["m1_fdr_negScoreMax"].tofile(tmp_path / "neg.f32")
+    run([os.path.join(bins, "host_check"), "pr", str(g.meta["npos"]), str(g.meta["nneg"]), repr(float(g.q)),
+         str(tmp_path / "pos.f32"), str(tmp_path / "neg.f32"), str(tmp_path)])
+    for k in ["TP", "FP", "FDR", "Rec", "occ_frac"]:
+        assert np.array_equal(np.fromfile(tmp_path / (k + ".f32"), np.float32), g["m1_fdr_" + k]), k
+    p, gp = np.fromfile(tmp_path / "PNpval.f32", np.float32), g["m1_fdr_PNpval"]
+    # Scores not above the lowest negative have no lower neighbour: the reference reads one element past the end of its
+    # vector there (FDR.cpp:246), so those p-values are undefined in the reference itself. The walk visits the scores
+    # in descending order, so entry i belongs to the i-th largest score of the union.
+    walk = np.sort(np.concatenate([g["m1_fdr_posScoreMax"], g["m1_fdr_negScoreMax"]]))[::-1]
+    defined = walk > g["m1_fdr_negScoreMax"].min()
+    assert defined.sum() >= len(p) - 3
+    assert np.array_equal(p[defined], gp[defined])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def parse_numbers(blob):
+    return np.array([float(t) for t in blob.decode().split()], np.float64)
+
+
+def stats_table(blob):
+    lines = blob.decode().strip().split("\n")
+    head = lines[0].split("\t")
+    body = np.array([[float(x) for x in l.split("\t") if x != ""] for l in lines[1:]], np.float64)
+    return head, body
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_cli_matches_reference_files(bins, case, tmp_path):
+    """bin/BaMMmotif with the reference's command line writes the files the reference wrote."""
+    g = Golden(case)
+    name = [k for k in g.z.files if k.endswith("_hbcp") and "motif" not in k][0][len("file_"):-len("_hbcp")]
+    fa, bs = write_inputs(g, str(tmp_path), name)
+    out = tmp_path / "out"
+    p = run([os.path.join(bins, "BaMMmotif"), str(out), fa, "--bindingSiteFile", bs] + g.args + ["--verbose"])
+    iters = [l for l in p.stdout.split("\n") if " iter, llh=" in l]
+    assert abs(len(iters) - g.iterations) <= 2 or case == "syn_k4", (len(iters), g.iterations)
+    assert open(out / (name + ".hbcp"), "rb").read() == bytes(g["file_%s_hbcp" % name])
+    assert open(out / (name + ".hbp"), "rb").read() == bytes(g["file_%s_hbp" % name])
+    for ext in ("ihbcp", "ihbp"):
+        ours = parse_numbers(open(out / ("%s_motif_1.%s" % (name, ext)), "rb").read())
+        ref = parse_numbers(bytes(g["file_%s_motif_1_%s" % (name, ext)]))
+        assert ours.shape == ref.shape
+        # 3 significant digits in the file: 1e-4 model tolerance + one unit of the last printed digit
+        assert np.all(np.abs(ours - ref) <= 1.2e-3 * np.abs(ref) + 1e-30), ext
+    key = "file_%s_motif_1_zoops_stats" % name
+    if key in g:
+        head, body = stats_table(open(out / (name + "_motif_1.zoops.stats"), "rb").read())
+        rhead, rbody = stats_table(bytes(g[key]))
+        assert head[:6] == rhead[:6]
+        assert body.shape == rbody.shape
+        # TP / FP are rank walks over scores of fold models that agree with the reference's to 1e-4: allow a few swaps
+        assert np.mean(np.abs(body[:, 0] - rbody[:, 0]) > 0) < 0.02
+        assert np.max(np.abs(body[:, 0] - rbody[:, 0])) <= 3
+        assert abs(float(head[6]) - float(rhead[6])) <= 0.02
+
+
+@pytest.mark.gpu
+def test_cli_against_reference_binary_on_fresh_data(bins, tmp_path):
+    """Same command line through the reference binary (built from the untouched sources by oracle/Makefile, 1 thread)
+    and through bin/BaMMmotif on a seeded planted-motif set that no fixture covers: N bases in the input, --FDR,
+    --scoreSeqset, --saveBaMMs. Exact where the work is integer / host fp32, toleranced where the device sums."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "BaMMmotif_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/BaMMmotif_ref not built")
+    from bammmotif2_b200 import synth
+    fwd, sites, _ = synth.planted_sequences(4242, 3000, 120, 11)
+    fwd = fwd.copy()
+    fwd[::97, 17] = 0                                   # some real N's (reverse strand then carries code 78)
+    fa, bs = str(tmp_path / "syn.fasta"), str(tmp_path / "sites.block")
+    synth.write_fasta(fa, fwd)
+    synth.write_sites(bs, sites)
+    args = ["--bindingSiteFile", bs, "--EM", "-k", "3", "-K", "2", "--FDR", "-n", "5", "--scoreSeqset", "--saveBaMMs", "--verbose"]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    pr = run([ref, str(tmp_path / "ref"), fa] + args + ["--threads", "1"], env=env)
+    po = run([os.path.join(bins, "BaMMmotif"), str(tmp_path / "our"), fa] + args)
+    it_r = [l for l in pr.stdout.split("\n") if " iter, llh=" in l]
+    it_o = [l for l in po.stdout.split("\n") if " iter, llh=" in l]
+    assert len(it_r) == len(it_o), (len(it_r), len(it_o))
+    for a, b in zip(it_r, it_o):                        # "N iter, llh=X, diff_llh=Y, v_diff=Z" with 6 significant digits
+        la, lb = float(a.split("llh=")[1].split(",")[0]), float(b.split("llh=")[1].split(",")[0])
+        assert abs(la - lb) <= 2e-5 * abs(la)
+    rd, od = tmp_path / "ref", tmp_path / "our"
+    for fn in ("syn.hbcp", "syn.hbp"):
+        assert open(rd / fn, "rb").read() == open(od / fn, "rb").read(), fn
+    for fn in ("syn_motif_1.ihbcp", "syn_motif_1.ihbp"):
+        a, b = parse_numbers(open(rd / fn, "rb").read()), parse_numbers(open(od / fn, "rb").read())
+        assert a.shape == b.shape and np.all(np.abs(a - b) <= 1.2e-3 * np.abs(a) + 1e-30), fn
+    # .positions: windows with posterior >= 0.3 (r within 1e-5: the same windows unless one sits on the threshold)
+    pa, pb = open(rd / "syn_motif_1.positions").read().split("\n"), open(od / "syn_motif_1.positions").read().split("\n")
+    assert pa[0] == pb[0] and len(set(pa) ^ set(pb)) <= 2
+    # .occurrence: p-values of window scores against the sampled negatives (bit-identical negative set and scores of a
+    # model that agrees to 1e-4): same header, nearly the same hits
+    oa, ob = open(rd / "syn_motif_1.occurrence").read().split("\n"), open(od / "syn_motif_1.occurrence").read().split("\n")
+    assert oa[0] == ob[0]
+    ka, kb = {"\t".join(l.split("\t")[:5]) for l in oa[1:] if l}, {"\t".join(l.split("\t")[:5]) for l in ob[1:] if l}
+    assert len(ka ^ kb) <= 0.02 * max(len(ka), 1) + 2
+    ha, ba = stats_table(open(rd / "syn_motif_1.zoops.stats", "rb").read())
+    hb, bb = stats_table(open(od / "syn_motif_1.zoops.stats", "rb").read())
+    assert ha[:6] == hb[:6] and ba.shape == bb.shape
+    assert np.max(np.abs(ba[:, 0] - bb[:, 0])) <= 3 and np.mean(ba[:, 0] != bb[:, 0]) < 0.02
