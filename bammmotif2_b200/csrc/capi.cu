@@ -301,8 +301,17 @@ extern "C" int bamm_seqset_count_kmers(bamm_seqset* s, int K, uint64_t* n_all) {
     CU(cudaMalloc(&d_cnt, ia->Yn * 8));
     CU(cudaMemset(d_cnt, 0, ia->Yn * 8));
     if (s->npos) {
-        if (ia->bytes == 2) k_count_kmers<uint16_t><<<s->sm_count * 8, 256>>>((const uint16_t*)ia->d, s->npos, d_cnt);
-        else                k_count_kmers<uint32_t><<<s->sm_count * 8, 256>>>((const uint32_t*)ia->d, s->npos, d_cnt);
+        const uint32_t Yn = (uint32_t)ia->Yn;
+        const bool smem = ia->Yn <= 12288 && s->npos / ((uint64_t)s->sm_count * 8) < 0xffffffffull;     // 48 KB of 32-bit bins
+        const size_t sh = smem ? (size_t)Yn * 4 : 0;
+        const int grid = s->sm_count * 8;
+        if (ia->bytes == 2) {
+            if (smem) k_count_kmers<uint16_t, true><<<grid, 256, sh>>>((const uint16_t*)ia->d, s->npos, Yn, d_cnt);
+            else      k_count_kmers<uint16_t, false><<<grid, 256>>>((const uint16_t*)ia->d, s->npos, Yn, d_cnt);
+        } else {
+            if (smem) k_count_kmers<uint32_t, true><<<grid, 256, sh>>>((const uint32_t*)ia->d, s->npos, Yn, d_cnt);
+            else      k_count_kmers<uint32_t, false><<<grid, 256>>>((const uint32_t*)ia->d, s->npos, Yn, d_cnt);
+        }
     }
     std::vector<uint64_t> top(ia->Yn);
     cudaError_t e = cudaMemcpy(top.data(), d_cnt, ia->Yn * 8, cudaMemcpyDeviceToHost);

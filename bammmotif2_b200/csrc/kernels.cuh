@@ -58,12 +58,26 @@ __global__ void k_patch_index(const uint64_t* __restrict__ ppos, const uint64_t*
     if (i < np) Y[ppos[i]] = (YT)(pkmer[i] % Yn);
 }
 
-// top-order k-mer histogram over all positions (reference: BackgroundModel.cpp:26-42; lower orders are folds)
-template <typename YT>
-__global__ void k_count_kmers(const YT* __restrict__ Y, uint64_t npos, unsigned long long* __restrict__ cnt) {
+// top-order k-mer histogram over all positions (reference: BackgroundModel.cpp:26-42; lower orders are folds).
+// SMEM: CTA-private 32-bit histogram in shared memory (a CTA sees far fewer than 2^32 positions), flushed with one
+// 64-bit global atomic per non-empty bin; otherwise global atomics directly.
+template <typename YT, bool SMEM>
+__global__ void k_count_kmers(const YT* __restrict__ Y, uint64_t npos, uint32_t Yn, unsigned long long* __restrict__ cnt) {
+    extern __shared__ uint32_t hist[];
+    if (SMEM) {
+        for (uint32_t b = threadIdx.x; b < Yn; b += blockDim.x) hist[b] = 0u;
+        __syncthreads();
+    }
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (; i < npos; i += stride) atomicAdd(&cnt[Y[i]], 1ull);
+    for (; i < npos; i += stride) {
+        if (SMEM) atomicAdd(&hist[Y[i]], 1u);
+        else atomicAdd(&cnt[Y[i]], 1ull);
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < Yn; b += blockDim.x) if (hist[b]) atomicAdd(&cnt[b], (unsigned long long)hist[b]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
