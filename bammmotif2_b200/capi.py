@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbamm_b200.so")
+LIB_PATH = os.environ.get("BAMM_LIB") or os.path.join(_HERE, "libbamm_b200.so")   # BAMM_LIB: kernel-variant experiments
 
 _u8p, _u32p, _u64p, _f32p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_float))
 _vp = C.c_void_p

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <new>
@@ -75,9 +76,18 @@ struct bamm_em {
     uint32_t ngen = 0, npk = 0;
     uint32_t* d_gen_ids = nullptr;  uint64_t* d_gen_roff = nullptr;
     uint32_t* d_pk_ids = nullptr;   uint64_t* d_pk_roff = nullptr;
-    Plan plan;                  // tuple plan of the packed E-step
-    int nch = 0;                // register chunks of the packed E-step (32 windows each)
-    float* d_tab = nullptr;     // tuple table [C][Zn]
+    Plan plan;                  // W, K, Yn for the packed M-step / scoring kernels
+    GroupPlan gplan;            // column groups of the packed E-step (chosen in set_model)
+    bool gfast = false;         // every group's bit field sits below bit 32 of the window word
+    size_t tab_capacity = 0;    // bytes available for the group tables (= opt-in shared memory)
+    float* d_tab = nullptr;     // group tables, concatenated
+    // active list (windows that survive the M-step's fixed-point rounding), one region per E-step warp
+    uint32_t nregions = 0;
+    ActiveEntry* d_act = nullptr;
+    bool list_w = false;        // width-specialised list kernel usable (two count tables fit shared memory)
+    int grid_pl = 0;
+    uint32_t *d_act_cnt = nullptr, *d_overflow = nullptr;
+    uint64_t* d_reg_off = nullptr;
     uint16_t* d_ypatch = nullptr;   // owned by the seqset
     int grid_pe = 0, block_pe = 1024, grid_pm = 0;
     size_t smem_pe = 0, smem_pm = 0;
@@ -347,6 +357,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     if (!em) return;
     cudaSetDevice(em->device);
     if (em->stream) cudaStreamSynchronize(em->stream);
+    cudaFree(em->d_act); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
     cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab);
     cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_v);
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
@@ -361,9 +372,77 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
 }
 
 static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only);
+static int mstep_list_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only);
 
 template <typename K> static int max_smem_optin(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : -1;
+}
+
+
+// ---- column-group planner of the packed E-step (packed.cuh, "column groups") -----------------------------------------
+// Cuts columns 0..W-1 into the fewest consecutive groups whose lookup tables (4^bases floats each) fit `budget` bytes.
+// reduced: columns j < K only depend on max(j, K_bg)+1 bases (true for every model produced by updateV; checked for
+// models passed to bamm_em_set_model). Returns false when even one column per group does not fit.
+static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget, GroupPlan& gp, bool& fast) {
+    auto ctx = [&](int j) { int c = j < K ? j : K; if (!reduced) c = K; return c > K_bg ? c : K_bg; };
+    auto first_base = [&](int a, int b) { int lo = 1 << 30; for (int j = a; j <= b; j++) lo = std::min(lo, j - ctx(j)); return lo; };
+    const double INF = 1e300;
+    auto bytes_of = [&](int a, int b) {               // table of the group covering columns a..b
+        const int nb = b - first_base(a, b) + 1;
+        return nb > 12 ? INF : 4.0 * (double)(1ull << (2 * nb));
+    };
+    // sfx[j][n]: least bytes covering columns [j,W) with n groups
+    std::vector<std::vector<double>> sfx(W + 1, std::vector<double>(MAXG + 1, INF));
+    std::vector<std::vector<int>> nxt(W + 1, std::vector<int>(MAXG + 1, -1));
+    sfx[W][0] = 0;
+    for (int j = W - 1; j >= 0; j--)
+        for (int n = 1; n <= MAXG; n++)
+            for (int e = j + 1; e <= W; e++) {
+                if (sfx[e][n - 1] >= INF) continue;
+                const double c = bytes_of(j, e - 1) + sfx[e][n - 1];
+                if (c < sfx[j][n]) { sfx[j][n] = c; nxt[j][n] = e; }
+            }
+    // fewest groups first; then a first group wide enough for the one-shift extraction (see `fast` below); then bytes
+    int G = -1, best_a1 = -1; bool best_fast = false; double best_bytes = INF;
+    for (int n = 1; n <= MAXG && G < 0; n++) {
+        for (int a1 = 1; a1 <= W; a1++) {
+            const double c = bytes_of(0, a1 - 1) + sfx[a1][n - 1];
+            if (c > (double)budget) continue;
+            const int d = std::max(0, 15 - K - (a1 - 1));
+            const bool f = d <= 31 - K - W;
+            if (G < 0 || (f && !best_fast) || (f == best_fast && c < best_bytes)) { G = n; best_a1 = a1; best_fast = f; best_bytes = c; }
+        }
+    }
+    if (G < 0) return false;
+    memset(&gp, 0, sizeof(gp));
+    gp.W = W; gp.K = K; gp.G = G; gp.Yn = 1u << (2 * (K + 1));
+    std::vector<int> cuts(G + 1);
+    cuts[0] = 0; cuts[1] = best_a1;
+    for (int g = 1, j = best_a1; g < G; g++) { j = nxt[j][G - g]; cuts[g + 1] = j; }
+    uint32_t base = 0;
+    for (int g = 0; g < G; g++) {
+        const int a = cuts[g], b = cuts[g + 1] - 1;
+        gp.col0[g] = a; gp.ncol[g] = b - a + 1; gp.lo[g] = first_base(a, b);
+        const int nb = b - gp.lo[g] + 1;
+        gp.base[g] = base;
+        gp.mask4[g] = (uint32_t)(((1ull << (2 * nb)) - 1ull) << 2);
+        gp.colmask[g] = (uint32_t)(((b >= 31 ? 0xffffffffull : ((2ull << b) - 1ull))) & ~((1ull << a) - 1ull));
+        base += 4u << (2 * nb);
+    }
+    gp.table_bytes = base;
+    // alignment of the window word: base p+hi sits at bit 62-2(hi+K+delta); the byte offset needs shift = 60-2(hi+K+delta) >= 0
+    const int hi0 = cuts[1] - 1;
+    int delta = 15 - K - hi0; if (delta < 0) delta = 0;
+    fast = delta <= 31 - K - W;
+    if (!fast) delta = 0;
+    gp.delta = delta;
+    for (int g = 0; g < G; g++) {
+        const int hi = cuts[g + 1] - 1;
+        const int sh = 60 - 2 * (hi + K + delta);
+        gp.shift[g] = (uint32_t)sh;
+        gp.shift2[g] = sh > 32 ? (uint32_t)(sh - 32) : 0u;
+    }
+    return true;
 }
 
 extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
@@ -389,23 +468,18 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, em->device);
     const int sms = s->sm_count;
     const size_t table_bytes = (size_t)em->nbin * sizeof(float);
-    // ---- packed-path plan: tuple size T minimising lookups per window under the shared-memory budget
+    // ---- packed path: possible when the column-group tables and the M-step's count table fit shared memory
     const size_t queue_bytes = (size_t)(512 / 32) * QCAP * sizeof(QEntry);
-    bool packed_ok = s->A == 4 && s->nregular > 0 && W + K <= 32 && Yn64 <= 65536 &&
+    bool packed_ok = s->A == 4 && s->nregular > 0 && W + K <= 31 && Yn64 <= 65536 &&
                      ((table_bytes + 15) & ~(size_t)15) + queue_bytes <= (size_t)max_optin && !getenv("BAMM_NO_PACKED");
+    em->tab_capacity = (size_t)max_optin;
+    if (getenv("BAMM_TABLE_BYTES")) em->tab_capacity = std::min(em->tab_capacity, (size_t)atol(getenv("BAMM_TABLE_BYTES")));
     if (packed_ok) {
-        int bestT = 1, bestC = W; size_t best_bytes = table_bytes;
-        int forceT = getenv("BAMM_TUPLE") ? atoi(getenv("BAMM_TUPLE")) : 0;
-        for (int T = 1; T <= 8; T++) {
-            const int C = (W + T - 1) / T;
-            if (K + C * T > 32 || K + T > 13 || C > 16) continue;
-            const size_t bytes = (size_t)C * ((size_t)1 << (2 * (K + T))) * sizeof(float);
-            if (bytes > (size_t)max_optin - 1024) continue;
-            if (forceT ? T == forceT : (C < bestC || (C == bestC && bytes < best_bytes))) { bestT = T; bestC = C; best_bytes = bytes; }
-        }
-        em->plan.W = W; em->plan.K = K; em->plan.T = bestT; em->plan.C = bestC;
-        em->plan.Yn = em->Yn; em->plan.Zn = (uint32_t)1 << (2 * (K + bestT)); em->plan.q = 0.3f;
-        em->smem_pe = best_bytes;
+        // both variants (with / without the reduced context of the leading columns) must be plannable
+        GroupPlan tmp; bool f;
+        packed_ok = make_group_plan(W, K, em->K_bg, false, em->tab_capacity, tmp, f);
+        em->plan.W = W; em->plan.K = K; em->plan.T = 1; em->plan.C = W;
+        em->plan.Yn = em->Yn; em->plan.Zn = em->Yn; em->plan.q = 0.3f;
     }
     // ---- split the subset
     em->h_r_off.resize(nsub + 1);
@@ -429,7 +503,6 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     }
     em->rsize = em->h_r_off[nsub];
     em->ngen = (uint32_t)gen_ids.size(); em->npk = (uint32_t)pk_ids.size();
-    em->nch = max_lw1_pk <= 128 ? 4 : max_lw1_pk <= 256 ? 8 : max_lw1_pk <= 512 ? 16 : 32;
     IndexArray* ia = nullptr;
     if (em->ngen) { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) { delete em; return rc; } }
     if (em->npk)  { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_ypatch_locked(s, K, &em->d_ypatch); if (rc) { delete em; return rc; } }
@@ -481,19 +554,44 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     }
     // ---- packed path geometry
     if (em->npk) {
-        CUE(cudaMalloc(&em->d_tab, em->smem_pe));
-        em->block_pe = 1024;                        // 64 registers/thread => 1024 resident threads per SM: one CTA per SM
+        CUE(cudaMalloc(&em->d_tab, em->tab_capacity));
+        em->block_pe = BAMM_E_THREADS;              // one CTA per SM: the group tables fill its shared memory
         em->grid_pe = sms;
-        bool ok = true;
-        ok = !estep_packed_dispatch(em, nullptr, nullptr, true);
         em->smem_pm = ((table_bytes + 15) & ~(size_t)15) + queue_bytes;
-        ok = ok && !max_smem_optin(k_mstep_packed, em->smem_pm);
+        bool ok = !max_smem_optin(k_mstep_packed, em->smem_pm) && !max_smem_optin(k_mstep_list, table_bytes);
         if (!ok) { fail(BAMM_E_CUDA, "cannot opt in to shared memory for the packed kernels"); bamm_em_destroy(em); return BAMM_E_CUDA; }
         int per_sm_m = (int)((size_t)(max_optin + 1024) / (em->smem_pm + 1024));
         if (per_sm_m < 1) per_sm_m = 1;
         if (per_sm_m > 4) per_sm_m = 4;
         em->grid_pm = sms * per_sm_m;
         if ((uint32_t)em->grid_pm > em->nparts) em->nparts = (uint32_t)em->grid_pm;
+        // active list: one region per E-step warp, sized as a fraction of the warp's windows (BAMM_LIST_FRAC, 0 = off)
+        const double frac = getenv("BAMM_LIST_FRAC") ? atof(getenv("BAMM_LIST_FRAC")) : 0.5;
+        if (frac > 0.0) {
+            em->nregions = (uint32_t)em->grid_pe * (uint32_t)(em->block_pe / 32);
+            std::vector<uint64_t> win(em->nregions, 0), reg(em->nregions + 1, 0);
+            for (size_t i = 0; i < pk_ids.size(); i++) {
+                const uint64_t n = pk_ids[i];
+                win[i % em->nregions] += s->h_off[n + 1] - s->h_off[n] - (uint64_t)W + 1;
+            }
+            for (uint32_t w = 0; w < em->nregions; w++) {
+                uint64_t cap = (uint64_t)(frac * (double)win[w]) + 256;
+                if (cap > win[w]) cap = win[w];
+                reg[w + 1] = reg[w] + cap;
+            }
+            const uint64_t total = reg[em->nregions] ? reg[em->nregions] : 1;
+            CUE(upload(reg.data(), reg.size() * 8, (void**)&em->d_reg_off));
+            CUE(cudaMalloc(&em->d_act, total * sizeof(ActiveEntry)));
+            CUE(cudaMalloc(&em->d_act_cnt, (uint64_t)em->nregions * 4));
+            CUE(cudaMemset(em->d_act_cnt, 0, (uint64_t)em->nregions * 4));
+            CUE(cudaMalloc(&em->d_overflow, 4));
+            CUE(cudaMemset(em->d_overflow, 0, 4));
+            // two 32-bit count tables per CTA; the high table sums at most 256 per listed window, far below 2^32 per CTA
+            em->grid_pl = sms;
+            em->list_w = (size_t)em->nbin * 8 <= (size_t)max_optin && total / (uint64_t)sms < (1ull << 23) && !getenv("BAMM_NO_LISTW") &&
+                         mstep_list_dispatch(em, nullptr, nullptr, true) == 0;
+            if (em->list_w && (uint32_t)em->grid_pl > em->nparts) em->nparts = (uint32_t)em->grid_pl;
+        }
     }
     CUE(cudaMalloc(&em->d_part, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long)));
 #undef CUE
@@ -503,17 +601,36 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
 
 static int launch_tuple_table(bamm_em* em) {
     if (!em->npk) return BAMM_OK;
-    const Plan& pl = em->plan;
-    const uint32_t total = (uint32_t)pl.C * pl.Zn;
-    k_make_tuple_table<<<(total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184, 256, 0, em->stream>>>(em->d_s, pl.W, pl.K, pl.T, pl.C, pl.Yn, em->d_tab);
+    const uint32_t total = em->gplan.table_bytes >> 2;
+    const uint32_t blocks = (total + 255) / 256;
+    k_make_group_tables<<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(em->d_s, em->gplan, em->d_tab);
     CU(cudaGetLastError());
     return BAMM_OK;
+}
+
+// true when every column j < K of v[K] only depends on the j+1 newest bases (what Motif::updateV produces, Motif.h:126-128)
+static bool leading_columns_are_copies(const bamm_em* em, const float* v_all) {
+    const int K = em->K, W = em->W;
+    const float* vK = v_all + em->dims.voff[K];
+    for (int j = 0; j < K && j < W; j++) {
+        const uint32_t period = em->dims.Y[j + 1];
+        for (uint32_t y = period; y < em->Yn; y++)
+            if (vK[(uint64_t)y * W + j] != vK[(uint64_t)(y % period) * W + j]) return false;
+    }
+    return true;
 }
 
 extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* vbg_all, const float* alpha, float q) {
     REQUIRE(em && v_all && vbg_all && alpha, "NULL argument");
     REQUIRE(q > 0.0f && q < 1.0f, "q=%g not in (0,1)", (double)q);
     CU(cudaSetDevice(em->device));
+    if (em->npk) {
+        const bool reduced = leading_columns_are_copies(em, v_all) && !getenv("BAMM_NO_REDUCED");
+        if (!make_group_plan(em->W, em->K, em->K_bg, reduced, em->tab_capacity, em->gplan, em->gfast))
+            return fail(BAMM_E_STATE, "no column-group plan fits shared memory");
+        em->smem_pe = em->gplan.table_bytes;
+        if (estep_packed_dispatch(em, nullptr, nullptr, true)) return fail(BAMM_E_CUDA, "cannot opt in to %zu bytes of shared memory", em->smem_pe);
+    }
     CU(cudaMemcpyAsync(em->d_v, v_all, em->model_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
     CU(cudaMemcpyAsync(em->d_vbg, vbg_all, em->bg_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
     CU(cudaMemcpyAsync(em->d_alpha, alpha, (uint64_t)(em->K + 1) * em->W * sizeof(float), cudaMemcpyHostToDevice, em->stream));
@@ -525,16 +642,22 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
     return BAMM_OK;
 }
 
-// k_estep_packed is instantiated for every lookup count C the planner can choose; optin_only sets the
-// shared-memory attribute instead of launching.
-template <int C> static int estep_packed_one(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only) {
-    if (optin_only) return max_smem_optin(k_estep_packed<C>, em->smem_pe);
-    k_estep_packed<C><<<em->grid_pe, em->block_pe, em->smem_pe, em->stream>>>(*pv, *pl, em->d_tab, em->d_s, em->d_r, em->d_xbuf + em->nbin);
+// k_estep_packed is instantiated for every group count the planner can choose, in both extraction modes;
+// optin_only sets the shared-memory attribute instead of launching.
+static ActiveList alist_of(const bamm_em* em) {
+    ActiveList al; al.ent = em->d_act; al.reg_off = em->d_reg_off;
+    al.cnt = em->d_act_cnt; al.overflow = em->d_overflow;
+    return al;
+}
+template <int G, bool FAST> static int estep_packed_one(bamm_em* em, const PackedView* pv, bool optin_only) {
+    if (optin_only) return max_smem_optin(k_estep_packed<G, FAST>, em->smem_pe);
+    GroupPlan gp = em->gplan; gp.q = em->q;
+    k_estep_packed<G, FAST><<<em->grid_pe, em->block_pe, em->smem_pe, em->stream>>>(*pv, gp, em->d_tab, em->d_s, em->d_r, em->d_xbuf + em->nbin, alist_of(em));
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
-static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only) {
-    switch (em->plan.C) {
-#define BAMM_CASE(c) case c: return estep_packed_one<c>(em, pv, pl, optin_only);
+static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, const Plan*, bool optin_only) {
+    switch (em->gplan.G) {
+#define BAMM_CASE(g) case g: return em->gfast ? estep_packed_one<g, true>(em, pv, optin_only) : estep_packed_one<g, false>(em, pv, optin_only);
         BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
         BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
 #undef BAMM_CASE
@@ -557,8 +680,8 @@ static int launch_estep(bamm_em* em) {
     CU(cudaMemsetAsync(scal, 0, 2 * sizeof(unsigned long long), em->stream));
     if (em->npk) {
         PackedView pv = pview_of(em);
-        Plan pl = em->plan; pl.q = em->q;
-        if (estep_packed_dispatch(em, &pv, &pl, false)) return fail(BAMM_E_CUDA, "packed E-step launch failed");
+        if (em->d_overflow) CU(cudaMemsetAsync(em->d_overflow, 0, 4, em->stream));
+        if (estep_packed_dispatch(em, &pv, nullptr, false)) return fail(BAMM_E_CUDA, "packed E-step launch failed");
         CU(cudaGetLastError());
     }
     if (em->ngen) {
@@ -576,12 +699,46 @@ static int launch_estep(bamm_em* em) {
     return BAMM_OK;
 }
 
+// width-specialised list M-step: one instantiation per motif width
+template <int WT> static int mstep_list_one(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only) {
+    const size_t smem = (size_t)em->nbin * 8;
+    if (optin_only) return max_smem_optin(k_mstep_list_w<WT>, smem);
+    k_mstep_list_w<WT><<<em->grid_pl, 1024, smem, em->stream>>>(*pv, *pl, alist_of(em), em->nregions, em->d_part);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+static int mstep_list_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only) {
+    switch (em->W) {
+#define BAMM_CASE(w) case w: return mstep_list_one<w>(em, pv, pl, optin_only);
+        BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
+        BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
+        BAMM_CASE(17) BAMM_CASE(18) BAMM_CASE(19) BAMM_CASE(20) BAMM_CASE(21) BAMM_CASE(22) BAMM_CASE(23) BAMM_CASE(24)
+        BAMM_CASE(25) BAMM_CASE(26) BAMM_CASE(27) BAMM_CASE(28) BAMM_CASE(29) BAMM_CASE(30) BAMM_CASE(31)
+#undef BAMM_CASE
+        default: return -1;
+    }
+}
+
 static int launch_mstep_accumulate(bamm_em* em) {
     CU(cudaMemsetAsync(em->d_part, 0, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long), em->stream));
     if (em->npk) {
         PackedView pv = pview_of(em);
         Plan pl = em->plan; pl.q = em->q;
-        k_mstep_packed<<<em->grid_pm, 512, em->smem_pm, em->stream>>>(pv, pl, em->d_r, em->d_part);
+        if (em->d_act && getenv("BAMM_DEBUG_LIST")) {
+            std::vector<uint32_t> c(em->nregions); uint32_t ov = 0;
+            cudaStreamSynchronize(em->stream);
+            cudaMemcpy(c.data(), em->d_act_cnt, (size_t)em->nregions * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(&ov, em->d_overflow, 4, cudaMemcpyDeviceToHost);
+            uint64_t tot = 0, mx = 0; for (uint32_t x : c) { tot += x; if (x > mx) mx = x; }
+            fprintf(stderr, "[bamm] active list: %llu entries (%.4f of r), max region %llu, overflow %u, G=%d fast=%d delta=%d table %u B\n",
+                    (unsigned long long)tot, (double)tot / (double)em->rsize, (unsigned long long)mx, ov, em->gplan.G, (int)em->gfast, em->gplan.delta, em->gplan.table_bytes);
+        }
+        if (em->d_act) {
+            // the E-step listed the windows that matter; the scan kernel only runs (device-side decision) if a region overflowed
+            if (em->list_w) { if (mstep_list_dispatch(em, &pv, &pl, false)) return fail(BAMM_E_CUDA, "list M-step launch failed"); }
+            else k_mstep_list<<<em->grid_pm, 512, (size_t)em->nbin * 4, em->stream>>>(pv, pl, alist_of(em), em->nregions, em->d_part);
+            CU(cudaGetLastError());
+        }
+        k_mstep_packed<<<em->grid_pm, 512, em->smem_pm, em->stream>>>(pv, pl, em->d_r, em->d_part, em->d_overflow);
         CU(cudaGetLastError());
     }
     if (em->ngen) {

@@ -124,18 +124,45 @@ __global__ void k_make_ypatch(const uint64_t* __restrict__ ppos, const uint64_t*
     if (d <= (uint64_t)K) ypatch[n * (uint64_t)(K + 1) + d] = (uint16_t)(pkmer[i] % Yn);
 }
 
-// ---- tables ------------------------------------------------------------------------------------------------------
-// tab[c][z] for c < C = ceil(W/T), z < 4^(K+T); s is the plain table [j][y]. LOG != 0: sums instead of products.
-__global__ void k_make_tuple_table(const float* __restrict__ s, int W, int K, int T, int C, uint32_t Yn,
-                                   float* __restrict__ tab) {
-    const uint32_t Zn = Yn << (2 * (T - 1));
-    const uint32_t maskK = Yn - 1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)C * Zn; i += gridDim.x * blockDim.x) {
-        const uint32_t c = i / Zn, z = i % Zn;
+// ---- column groups ------------------------------------------------------------------------------------------------
+// The W motif columns are cut into G consecutive groups; group g folds its columns into ONE table lookup over the
+// bases its columns depend on. Column j reads the (K+1)-mer ending at base p+j, but its value only depends on
+// ctx(j)+1 of those bases, ctx(j) = max(min(j,K), K_bg): for j < K the model's v[K][y][j] is a copy of the order-j
+// entry (Motif::updateV, Motif.h:126-128) and the background factor uses K_bg+1 bases (Motif.cpp:485-494). The first
+// group therefore reaches only K_bg bases left of the window and can be wider for the same table size
+// (C3: columns 0-4 in one 4^7 table). A host-side DP picks the cut with the fewest groups that fits shared memory.
+constexpr int MAXG = 16;
+struct GroupPlan {
+    int W, K, G, delta;          // window word starts at base p-K-delta
+    uint32_t Yn;                 // 4^(K+1)
+    float q;
+    uint32_t table_bytes;
+    uint32_t shift[MAXG];        // (w >> shift) & mask4 = byte offset of the group's entry
+    uint32_t shift2[MAXG];       // general mode: extra shift after the clamped funnel shift
+    uint32_t mask4[MAXG];
+    uint32_t base[MAXG];         // byte offset of the group's table
+    uint32_t colmask[MAXG];      // bit j for every column of the group
+    int col0[MAXG], ncol[MAXG], lo[MAXG];   // first column, column count, first base relative to the window start p
+};
+
+// tab[g][z] = prod_{j in group g} s[j][ y_j(z) ], product in ascending j from 1.0f; z holds bases p+lo .. p+hi
+// (newest base in the low digits), y_j = the part of the (K+1)-mer ending at p+j that lies inside the group's bases
+// (digits outside do not influence s[j][.], see above).
+__global__ void k_make_group_tables(const float* __restrict__ s, GroupPlan gp, float* __restrict__ tab) {
+    const uint32_t total = gp.table_bytes >> 2;
+    const uint32_t maskK = gp.Yn - 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int g = 0;
+        while (g + 1 < gp.G && i >= (gp.base[g + 1] >> 2)) g++;
+        const uint32_t z = i - (gp.base[g] >> 2);
+        const int hi = gp.col0[g] + gp.ncol[g] - 1;
         float p = 1.0f;
-        for (int t = 0; t < T; t++) {
-            const int j = (int)c * T + t;
-            if (j < W) p *= s[(uint32_t)j * Yn + ((z >> (2 * (T - 1 - t))) & maskK)];
+        for (int t = 0; t < gp.ncol[g]; t++) {
+            const int j = gp.col0[g] + t;
+            const int avail = j - gp.lo[g] + 1;                          // bases of the group up to column j
+            uint32_t y = (z >> (2 * (hi - j))) & maskK;
+            if (avail < gp.K + 1) y &= (1u << (2 * avail)) - 1u;
+            p *= s[(uint32_t)j * gp.Yn + y];
         }
         tab[i] = p;
     }
@@ -159,117 +186,222 @@ __device__ __forceinline__ uint32_t field(unsigned long long w, int shift, uint3
     return (uint32_t)(w >> shift) & mask;
 }
 
-struct Plan {                 // launch-invariant parameters of the packed kernels
-    int W, K, T, C;           // tuple size T, C = ceil(W/T) lookups per window
-    uint32_t Yn, Zn;          // 4^(K+1), 4^(K+T)
+struct Plan {                 // launch-invariant parameters of the packed M-step / scoring kernels
+    int W, K, T, C;
+    uint32_t Yn, Zn;          // 4^(K+1)
     float q;
 };
 
+// Windows whose posterior survives the M-step's fixed-point rounding, written by the E-step while it normalises:
+// one region per E-step warp (no atomics, no ordering requirement: the M-step sums integers).
+struct ActiveEntry { uint32_t li, p; float rv; uint32_t pad; };   // 16 bytes: one 128-bit store / load per entry
+struct ActiveList {
+    ActiveEntry* ent;         // entries (li = index into the packed list of the EM object, p = window start, rv = posterior)
+    const uint64_t* reg_off;  // [nregions+1] first entry of every region
+    uint32_t* cnt;            // [nregions] entries written
+    uint32_t* overflow;       // set when a region was too small: the M-step then scans r instead
+};
+constexpr float FX_HALF_UNIT = 4.547473508864641e-13f;   // 2^-41: smallest r that rounds to a non-zero count
+
+// shared-memory load at (per-lane byte offset) + (warp-uniform base): one LDS with a uniform-register base operand
+__device__ __forceinline__ float lds_f32(uint32_t off, uint32_t ubase) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(off + ubase));
+    return v;
+}
+
 // ---- E-step --------------------------------------------------------------------------------------------------------
 // reference: EM::EStep, src/refinement/EM.cpp:139-200 (gather form). One warp per sequence, lanes =
-// window starts. The C tuple lookups of a window are fully unrolled (C is a template parameter); the 64-bit window
-// word is consumed from the top, 2T bits per lookup. Unnormalised posteriors go to r, the normaliser is reduced
-// over the warp, and a second sweep scales by 1/norm (the lines are still in L2).
+// window starts. The G group lookups of a window are fully unrolled; the byte offset of group g's entry is a bit field
+// of the 64-bit window word: FAST (every field below bit 32 after the alignment shift delta): one funnel shift + one
+// mask per lookup; otherwise a clamped funnel shift plus a second shift. Unnormalised posteriors go to r, the
+// normaliser is reduced over the warp, and a second sweep scales by 1/norm (the lines are still in L2) and appends the
+// windows the M-step will need to the warp's region of the active list.
 //
-// Chunks that contain windows tuples cannot fully serve — the last W-1 truncated windows (EM.cpp:167) and the
+// Chunks that contain windows the group tables cannot fully serve — the last W-1 truncated windows (EM.cpp:167) and the
 // windows over the k-mers that hold the N's rand() draws (positions mid..mid+K, Sequence.cpp:38) — run a masked
-// variant: per lane a bit mask of the tuples that are whole and untouched (taken from the shared table as usual)
+// variant: per lane a bit mask of the groups that are whole and untouched (taken from the shared tables as usual)
 // and a bit mask of the single columns that must come from the plain table in global memory.
-template <int C>
-__global__ void __launch_bounds__(1024, 1)
-k_estep_packed(PackedView pv, Plan pl, const float* __restrict__ tab_g /* [C][Zn] */, const float* __restrict__ s_g /* [W][Yn] */,
-               float* __restrict__ r, unsigned long long* __restrict__ scal) {
+#ifndef BAMM_E_THREADS
+#define BAMM_E_THREADS 1024      // threads per CTA of the packed E-step (one CTA per SM: the tables fill shared memory)
+#endif
+#ifndef BAMM_E_UNROLL
+#define BAMM_E_UNROLL 1          // unroll factor of the fast chunk loop
+#endif
+#ifndef BAMM_E_PIN
+#define BAMM_E_PIN 0             // keep the per-group extraction constants in registers instead of re-reading the constant bank
+#endif
+template <int G, bool FAST>
+__global__ void __launch_bounds__(BAMM_E_THREADS, 1)
+k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g /* [W][Yn] */,
+               float* __restrict__ r, unsigned long long* __restrict__ scal, ActiveList al) {
     extern __shared__ float tab[];
-    for (uint32_t i = threadIdx.x; i < (uint32_t)C * pl.Zn; i += blockDim.x) tab[i] = tab_g[i];
+    for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    const int W = pl.W, K = pl.K, T = pl.T;
-    const int zb = 2 * (K + T);                            // bits of one tuple index
-    const int roll = 2 * T;
-    const uint32_t zn_bytes = pl.Zn * 4u;
-    const uint32_t maskK = pl.Yn - 1;
-    const char* tabc = reinterpret_cast<const char*>(tab);
+    const int W = gp.W, K = gp.K, KD = gp.K + gp.delta;
+    const uint32_t maskK = gp.Yn - 1;
+    const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);        // 32-bit shared-window address
     long long llh_fx = 0, rsum_fx = 0;
-    const float one_minus_q = 1.0f - pl.q;
+    const float one_minus_q = 1.0f - gp.q;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // this lane's windows start at bases lane-KD + 32*chunk: always the same word offset and bit offset in a word
+    constexpr int E_UNROLL = BAMM_E_UNROLL;
+    constexpr int SWEEP = 8;                                // r values per lane loaded together in the second sweep
+    const int lane_word = (lane - KD) >> 4;
+    const int sft = 2 * ((lane - KD) & 15);
+    uint32_t c_sh[G], c_mk[G], c_ab[G], c_s2[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        c_sh[g] = gp.shift[g]; c_mk[g] = gp.mask4[g]; c_ab[g] = tab_s + gp.base[g]; c_s2[g] = gp.shift2[g];
+#if BAMM_E_PIN
+        if (G <= BAMM_E_PIN) asm volatile("" : "+r"(c_sh[g]), "+r"(c_mk[g]), "+r"(c_ab[g]));
+#endif
+    }
+    bool emit = al.ent != nullptr;
+    ActiveEntry* __restrict__ lreg = emit ? al.ent + al.reg_off[warp] : nullptr;      // this warp's region
+    const uint32_t lcap = emit ? (uint32_t)(al.reg_off[warp + 1] - al.reg_off[warp]) : 0u;
+    uint32_t lpos = 0;                                      // entries written so far
     for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
         const uint32_t n = pv.seq_ids[li];
         const PackedSeq sq = pv.seqs[n];
         const int L = (int)sq.L, LW1 = L - W + 1;
         const int mid = (int)sq.mid;                       // -1 when there is no N
-        // per-lane view of the stream: this lane's windows start at bases lane-K + 32*ch, i.e. always at the same
-        // bit offset sft inside a 32-bit word; three words are kept and two new ones are fetched per chunk
-        const uint32_t* __restrict__ wl = pv.words + sq.word_off + ((lane - K) >> 4);
-        const int sft = 2 * ((lane - K) & 15);
+        // three stream words are kept and two new ones are fetched per chunk of 32 windows
+        const uint32_t* __restrict__ wl = pv.words + sq.word_off + lane_word;
         uint32_t t0 = wl[0], t1 = wl[1], t2 = wl[2];
         float* __restrict__ rn = r + pv.r_off[li];
-        const float pos = pl.q / (float)LW1;
+        float* __restrict__ rp = rn + (L - W - lane);      // r index of this lane's window; moves down 32 per chunk
+        const float pos = gp.q / (float)LW1;
         const int tail0 = L - 2 * W + 2;                   // first truncated window (p > L-2W+1)
+        // chunk schedule: [0,a1) fast | [a1,b1) over the N | [b1,a2) fast | [a2,nch) truncated tail. Every window of a
+        // fast chunk is a full, untouched window, so the fast loop carries no masks and no bounds checks.
+        const int nch = (LW1 + 31) >> 5;
+        const int a2 = min(nch, max(tail0, 0) >> 5);
+        int a1 = a2, b1 = a2;
+        if (mid >= 0) { a1 = min(a2, max(mid - W + 1, 0) >> 5); b1 = min(a2, ((mid + K) >> 5) + 1); }
         float sum = 0.0f;
-        for (int p0 = 0; p0 < LW1; p0 += 32) {
-            const int p = p0 + lane;
-            uint32_t whi = __funnelshift_l(t1, t0, sft), wlo = __funnelshift_l(t2, t1, sft);
-            const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
-            wl += 2;
-            t0 = t2; t1 = wl[1]; t2 = wl[2];
-            float prod = 1.0f;
-            const bool chunk_slow = (p0 + 31 >= tail0) || (mid >= 0 && p0 <= mid + K && p0 + 31 + W - 1 >= mid);   // warp-uniform
-            if (!chunk_slow) {
+        int c = 0;
+#pragma unroll 1
+        for (int seg = 0; seg < 4; seg++) {
+            const int cend = seg == 0 ? a1 : seg == 1 ? b1 : seg == 2 ? a2 : nch;
+            if (!(seg & 1)) {
+#pragma unroll E_UNROLL
+                for (; c < cend; c++) {
+                    const uint32_t whi = __funnelshift_l(t1, t0, sft), wlo = __funnelshift_l(t2, t1, sft);
+                    wl += 2;
+                    t0 = t2; t1 = wl[1]; t2 = wl[2];
+                    float prod = 1.0f;
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const uint32_t z4 = (whi >> (32 - zb)) << 2;
-                    prod *= *reinterpret_cast<const float*>(tabc + (uint32_t)c * zn_bytes + z4);
-                    whi = __funnelshift_l(wlo, whi, roll);
-                    wlo <<= roll;
+                    for (int g = 0; g < G; g++) {
+                        uint32_t off;
+                        if (FAST) off = __funnelshift_r(wlo, whi, c_sh[g]) & c_mk[g];
+                        else      off = (__funnelshift_rc(wlo, whi, c_sh[g]) >> c_s2[g]) & c_mk[g];
+                        prod *= lds_f32(off, c_ab[g]);
+                    }
+                    const float val = prod * pos;
+                    *rp = val;
+                    rp -= 32;
+                    sum += val;
                 }
             } else {
-                const int jmax = (p < LW1) ? min(W - 1, L - W - p) : -1;
-                const int cfull = (jmax + 1) / T;                               // whole tuples inside the truncation
-                uint32_t good = (1u << cfull) - 1u;
-                uint32_t cols = 0;
-                if (cfull * T <= jmax) cols = ((2u << jmax) - 1u) & ~((1u << (cfull * T)) - 1u);   // truncated remainder
-                const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
-                if (over_n) {
-                    // tuples c with p+cT+T-1 >= mid and p+cT <= mid+K
-                    const int a = mid - p - T + 1;
-                    const int c_lo = a <= 0 ? 0 : (a + T - 1) / T;
-                    const int c_hi = min(C - 1, (mid + K - p) / T);
-                    if (c_hi >= c_lo) {
-                        const uint32_t cm = ((2u << c_hi) - 1u) & ~((1u << c_lo) - 1u);
-                        const int jl = c_lo * T, jh = min(jmax, c_hi * T + T - 1);
-                        if (jh >= jl) cols |= ((2u << jh) - 1u) & ~((1u << jl) - 1u);
-                        good &= ~cm;
+#pragma unroll 1
+                for (; c < cend; c++) {
+                    const int p = (c << 5) + lane;
+                    const uint32_t whi = __funnelshift_l(t1, t0, sft), wlo = __funnelshift_l(t2, t1, sft);
+                    wl += 2;
+                    t0 = t2; t1 = wl[1]; t2 = wl[2];
+                    const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
+                    const int jmax = (p < LW1) ? min(W - 1, L - W - p) : -1;
+                    const uint32_t valid = jmax >= 0 ? (jmax >= 31 ? 0xffffffffu : ((2u << jmax) - 1u)) : 0u;
+                    uint32_t ncols = 0;                     // columns whose k-mer holds a rand() draw of the N
+                    const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
+                    if (over_n) {
+                        const int ja = max(mid - p, 0), jb = min(mid - p + K, W - 1);
+                        if (jb >= ja) ncols = ((jb >= 31 ? 0xffffffffu : ((2u << jb) - 1u))) & ~((1u << ja) - 1u);
                     }
-                }
+                    uint32_t cols = valid;
+                    float prod = 1.0f;
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const uint32_t z4 = (whi >> (32 - zb)) << 2;
-                    const float v = *reinterpret_cast<const float*>(tabc + (uint32_t)c * zn_bytes + z4);
-                    prod *= ((good >> c) & 1u) ? v : 1.0f;
-                    whi = __funnelshift_l(wlo, whi, roll);
-                    wlo <<= roll;
+                    for (int g = 0; g < G; g++) {
+                        const uint32_t cm = gp.colmask[g];
+                        const bool good = ((cm & ~valid) == 0u) && ((cm & ncols) == 0u);
+                        uint32_t off;
+                        if (FAST) off = __funnelshift_r(wlo, whi, c_sh[g]) & c_mk[g];
+                        else      off = (__funnelshift_rc(wlo, whi, c_sh[g]) >> c_s2[g]) & c_mk[g];
+                        const float v = lds_f32(off, c_ab[g]);
+                        prod *= good ? v : 1.0f;
+                        if (good) cols &= ~cm;
+                    }
+                    // the single columns are multiplied after the whole groups: a re-association of the reference's
+                    // ascending-j product, far inside the 1e-5 tolerance
+                    // four columns per round: their table loads are independent (one L2 round trip instead of four),
+                    // the multiplications stay in ascending column order
+                    while (cols) {
+                        float f[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            f[u] = 1.0f;
+                            if (cols) {
+                                const int j = __ffs(cols) - 1;
+                                cols &= cols - 1u;
+                                uint32_t y = field(w, 62 - 2 * KD - 2 * j, maskK);
+                                const int d = p + j - mid;
+                                if (over_n && d >= 0 && d <= K) y = pv.ypatch[(uint64_t)n * (K + 1) + d];
+                                f[u] = __ldg(&s_g[(uint32_t)j * gp.Yn + y]);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) prod *= f[u];
+                    }
+                    if (p < LW1) {
+                        const float val = prod * pos;
+                        *rp = val;
+                        sum += val;
+                    }
+                    rp -= 32;
                 }
-                while (cols) {
-                    const int j = __ffs(cols) - 1;
-                    cols &= cols - 1u;
-                    uint32_t y = field(w, 62 - 2 * K - 2 * j, maskK);
-                    const int d = p + j - mid;
-                    if (over_n && d >= 0 && d <= K) y = pv.ypatch[(uint64_t)n * (K + 1) + d];
-                    prod *= __ldg(&s_g[(uint32_t)j * pl.Yn + y]);
-                }
-            }
-            if (p < LW1) {
-                const float val = prod * pos;
-                rn[L - W - p] = val;
-                sum += val;
             }
         }
         sum = warp_sum(sum);
         const float norm = one_minus_q + sum;
         const float rnorm = __frcp_rn(norm);
         __syncwarp();
-        for (int k = lane; k < L; k += 32) rn[k] = (k < LW1) ? rn[k] * rnorm : 0.0f;
+        // second sweep: scale (the lines are still in L2), zero the tail, list the windows the M-step needs
+        float* __restrict__ rq = rn + lane;
+        for (int kb = 0; kb < L; kb += 32 * SWEEP) {         // warp-uniform trip counts: the ballot below needs every lane
+            float raw[SWEEP];
+#pragma unroll
+            for (int u = 0; u < SWEEP; u++) {                // all loads of the batch first: SWEEP L2 round trips in flight
+                const int k = kb + 32 * u + lane;
+                raw[u] = (k < LW1) ? rq[32 * u] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < SWEEP; u++) {
+                const int k = kb + 32 * u + lane;
+                const float v = raw[u] * rnorm;
+                if (k < L) rq[32 * u] = v;
+                if (emit && kb + 32 * u < L) {
+                    const bool act = v >= FX_HALF_UNIT;
+                    const uint32_t m = __ballot_sync(FULL, act);
+                    if (m) {
+                        const uint32_t cnt = __popc(m);
+                        if (lpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
+                        else {
+                            if (act) {
+                                const uint4 e = make_uint4(li, (uint32_t)(L - W - k), __float_as_uint(v), 0u);
+                                *reinterpret_cast<uint4*>(lreg + lpos + __popc(m & lt_mask)) = e;
+                            }
+                            lpos += cnt;
+                        }
+                    }
+                }
+            }
+            rq += 32 * SWEEP;
+        }
+        __syncwarp();
         if (lane == 0) {
             llh_fx += __double2ll_rn((double)logf(norm) * SC_SCALE_D);
             rsum_fx += __double2ll_rn((double)(sum * rnorm) * SC_SCALE_D);
@@ -279,6 +411,7 @@ k_estep_packed(PackedView pv, Plan pl, const float* __restrict__ tab_g /* [C][Zn
         if (llh_fx) atomicAdd(&scal[0], (unsigned long long)llh_fx);
         if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);
     }
+    if (al.ent != nullptr) al.cnt[warp] = lpos;             // every lane holds the same count
 }
 
 // ---- M-step --------------------------------------------------------------------------------------------------------
@@ -293,8 +426,6 @@ struct QEntry { uint32_t p; float rv; };
 constexpr int QCAP = 256;                      // ring entries per warp (>= 31 + 128)
 constexpr int M_UNROLL = 8;                    // chunks of 32 windows in flight per lane
 constexpr int M_GROUP = 4;                     // chunks compacted per warp scan
-constexpr float FX_HALF_UNIT = 4.547473508864641e-13f;   // 2^-41: smallest r that rounds to a non-zero count
-
 struct SeqCtx { const uint32_t* wd; const uint16_t* yp; int L, mid; };
 
 __device__ __forceinline__ void scatter_window(const SeqCtx& sc, const Plan& pl, uint32_t* __restrict__ lo_sh,
@@ -341,8 +472,10 @@ __device__ __forceinline__ void scatter_window(const SeqCtx& sc, const Plan& pl,
 }
 
 __global__ void __launch_bounds__(512)
-k_mstep_packed(PackedView pv, Plan pl, const float* __restrict__ r, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+k_mstep_packed(PackedView pv, Plan pl, const float* __restrict__ r, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */,
+               const uint32_t* __restrict__ list_overflow /* nullptr, or: run only when the active list overflowed */) {
     extern __shared__ uint32_t smem_u32[];
+    if (list_overflow != nullptr && *list_overflow == 0u) return;          // k_mstep_list does the work
     const uint32_t nbin = (uint32_t)pl.W * pl.Yn;
     uint32_t* lo_sh = smem_u32;
     QEntry* queues = reinterpret_cast<QEntry*>(smem_u32 + ((nbin + 3) & ~3u));
@@ -417,6 +550,115 @@ k_mstep_packed(PackedView pv, Plan pl, const float* __restrict__ r, unsigned lon
     for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
         const uint32_t v = lo_sh[i];
         if (v) atomicAdd(&mypart[i], (unsigned long long)v);
+    }
+}
+
+// M-step from the E-step's active list: every lane scatters one listed window; no scan of r, full lanes throughout.
+__global__ void __launch_bounds__(512)
+k_mstep_list(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+    extern __shared__ uint32_t smem_u32[];
+    if (*al.overflow != 0u) return;                                        // k_mstep_packed scans r instead
+    const uint32_t nbin = (uint32_t)pl.W * pl.Yn;
+    uint32_t* lo_sh = smem_u32;
+    unsigned long long* mypart = part + (uint64_t)blockIdx.x * nbin;
+    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) lo_sh[i] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const int K = pl.K;
+    for (uint32_t rg = warp; rg < nregions; rg += nwarps) {
+        const uint32_t cnt = al.cnt[rg];
+        const uint64_t base = al.reg_off[rg];
+        // warp-uniform batch loop with an explicit reconvergence point: lanes that finish a window early (short tail
+        // windows, no carries) must not run ahead into the next batch on their own
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            if (e < cnt) {
+                const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(al.ent + base + e));
+                const uint32_t li = raw.x, p = raw.y;
+                const float rv = __uint_as_float(raw.z);
+                const uint32_t n = pv.seq_ids[li];
+                const PackedSeq sq = pv.seqs[n];
+                SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = (int)sq.L; sc.mid = (int)sq.mid;
+                scatter_window(sc, pl, lo_sh, mypart, (int)p, rv);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
+        const uint32_t v = lo_sh[i];
+        if (v) atomicAdd(&mypart[i], (unsigned long long)v);
+    }
+}
+
+// Width-specialised list M-step. The motif width is a template parameter, so the W scatter steps of a window are
+// fully unrolled with immediate shifts: the window word is right-aligned once (its last base in the lowest bits) and
+// column j's k-mer is the bit field at 2(W-1-j). Two CTA-private shared tables: low 32 bits of the 2^-40 fixed-point
+// sums, and a second table that collects the high parts (r >= 2^-8) and the wrap-arounds of the low words — no global
+// atomics while scattering. Windows over the N (patched k-mers) take the generic routine.
+template <int WT>
+__global__ void __launch_bounds__(1024, 1)
+k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+    extern __shared__ uint32_t smem_u32[];
+    if (*al.overflow != 0u) return;                                        // k_mstep_packed scans r instead
+    const uint32_t nbin = (uint32_t)WT * pl.Yn;
+    uint32_t* lo_sh = smem_u32;
+    uint32_t* hi_sh = smem_u32 + nbin;
+    unsigned long long* mypart = part + (uint64_t)blockIdx.x * nbin;
+    for (uint32_t i = threadIdx.x; i < 2 * nbin; i += blockDim.x) smem_u32[i] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const int K = pl.K;
+    const uint32_t maskK = pl.Yn - 1;
+    const int ralign = 62 - 2 * (K + WT - 1);                              // right-alignment shift of the window word
+    for (uint32_t rg = warp; rg < nregions; rg += nwarps) {
+        const uint32_t cnt = al.cnt[rg];
+        const ActiveEntry* __restrict__ ent = al.ent + al.reg_off[rg];
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {                        // warp-uniform batches, reconverged below
+            const uint32_t e = e0 + lane;
+            if (e < cnt) {
+                const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(ent + e));
+                const uint32_t li = raw.x;
+                const int p = (int)raw.y;
+                const float rv = __uint_as_float(raw.z);
+                const uint32_t n = pv.seq_ids[li];
+                const PackedSeq sq = pv.seqs[n];
+                const int L = (int)sq.L, mid = (int)sq.mid;
+                const bool over_n = mid >= 0 && p <= mid + K && p + WT - 1 >= mid;
+                if (over_n) {
+                    SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = L; sc.mid = mid;
+                    scatter_window(sc, pl, lo_sh, mypart, p, rv);
+                } else {
+                    const unsigned long long X = __float2ull_rn(rv * FX_SCALE_F);
+                    const uint32_t xlo = (uint32_t)X, xhi = (uint32_t)(X >> 32);
+                    const unsigned long long u = window_word(pv.words + sq.word_off, p - K) >> ralign;
+                    const uint32_t ulo = (uint32_t)u, uhi = (uint32_t)(u >> 32);
+                    const int jmax = min(WT - 1, L - WT - p);                // truncated tail windows stop early (EM.cpp:236)
+#pragma unroll
+                    for (int j = 0; j < WT; j++) {
+                        constexpr int dummy = 0; (void)dummy;
+                        const int sh = 2 * (WT - 1 - j);
+                        const uint32_t y = (sh >= 32 ? (uhi >> (sh - 32)) : __funnelshift_r(ulo, uhi, sh)) & maskK;
+                        if (j <= jmax) {
+                            const uint32_t bin = (uint32_t)j * pl.Yn + y;
+                            const uint32_t old = atomicAdd(&lo_sh[bin], xlo);
+                            const uint32_t h = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
+                            if (h) atomicAdd(&hi_sh[bin], h);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
+        const unsigned long long v = (unsigned long long)lo_sh[i] + ((unsigned long long)hi_sh[i] << 32);
+        if (v) atomicAdd(&mypart[i], v);
     }
 }
 
