@@ -84,6 +84,8 @@ struct bamm_em {
     // active list (windows that survive the M-step's fixed-point rounding), one region per E-step warp
     uint32_t nregions = 0;
     ActiveEntry* d_act = nullptr;
+    float* d_scale = nullptr;   // 1/normaliser per packed-list sequence (the packed E-step leaves r unnormalised)
+    bool r_scaled = true;       // r already holds normalised values
     bool list_w = false;        // width-specialised list kernel usable (two count tables fit shared memory)
     int grid_pl = 0;
     uint32_t *d_act_cnt = nullptr, *d_overflow = nullptr;
@@ -357,7 +359,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     if (!em) return;
     cudaSetDevice(em->device);
     if (em->stream) cudaStreamSynchronize(em->stream);
-    cudaFree(em->d_act); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
+    cudaFree(em->d_act); cudaFree(em->d_scale); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
     cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab);
     cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_v);
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
@@ -521,6 +523,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     CUE(upload(pk_ids.data(), pk_ids.size() * 4, (void**)&em->d_pk_ids));
     CUE(upload(pk_roff.data(), pk_roff.size() * 8, (void**)&em->d_pk_roff));
     CUE(cudaMalloc(&em->d_r, (em->rsize ? em->rsize : 1) * sizeof(float)));
+    CUE(cudaMemset(em->d_r, 0, (em->rsize ? em->rsize : 1) * sizeof(float)));   // the packed E-step never touches the tail i >= LW1
     CUE(cudaMalloc(&em->d_s, (uint64_t)em->nbin * sizeof(float)));
     CUE(cudaMalloc(&em->d_v, em->model_size * sizeof(float)));
     CUE(cudaMalloc(&em->d_vK_prev, (uint64_t)em->nbin * sizeof(float)));
@@ -555,6 +558,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     // ---- packed path geometry
     if (em->npk) {
         CUE(cudaMalloc(&em->d_tab, em->tab_capacity));
+        CUE(cudaMalloc(&em->d_scale, (size_t)em->npk * sizeof(float)));
         em->block_pe = BAMM_E_THREADS;              // one CTA per SM: the group tables fill its shared memory
         em->grid_pe = sms;
         em->smem_pm = ((table_bytes + 15) & ~(size_t)15) + queue_bytes;
@@ -645,7 +649,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
 // k_estep_packed is instantiated for every group count the planner can choose, in both extraction modes;
 // optin_only sets the shared-memory attribute instead of launching.
 static ActiveList alist_of(const bamm_em* em) {
-    ActiveList al; al.ent = em->d_act; al.reg_off = em->d_reg_off;
+    ActiveList al; al.ent = em->d_act; al.scale = em->d_scale; al.reg_off = em->d_reg_off;
     al.cnt = em->d_act_cnt; al.overflow = em->d_overflow;
     return al;
 }
@@ -682,6 +686,7 @@ static int launch_estep(bamm_em* em) {
         PackedView pv = pview_of(em);
         if (em->d_overflow) CU(cudaMemsetAsync(em->d_overflow, 0, 4, em->stream));
         if (estep_packed_dispatch(em, &pv, nullptr, false)) return fail(BAMM_E_CUDA, "packed E-step launch failed");
+        em->r_scaled = false;
         CU(cudaGetLastError());
     }
     if (em->ngen) {
@@ -738,7 +743,7 @@ static int launch_mstep_accumulate(bamm_em* em) {
             else k_mstep_list<<<em->grid_pm, 512, (size_t)em->nbin * 4, em->stream>>>(pv, pl, alist_of(em), em->nregions, em->d_part);
             CU(cudaGetLastError());
         }
-        k_mstep_packed<<<em->grid_pm, 512, em->smem_pm, em->stream>>>(pv, pl, em->d_r, em->d_part, em->d_overflow);
+        k_mstep_packed<<<em->grid_pm, 512, em->smem_pm, em->stream>>>(pv, pl, em->d_r, em->d_part, em->d_overflow, em->r_scaled ? nullptr : em->d_scale);
         CU(cudaGetLastError());
     }
     if (em->ngen) {
@@ -978,6 +983,11 @@ extern "C" int bamm_em_get_r(bamm_em* em, uint64_t first, uint64_t count, float*
     REQUIRE(first + count <= em->nsub, "sequence range out of bounds");
     if (!em->r_valid) return fail(BAMM_E_STATE, "no E-step has run");
     CU(cudaSetDevice(em->device));
+    if (!em->r_scaled) {            // the packed E-step keeps r unnormalised; finish it before it leaves the device
+        k_normalise_r<<<em->ss->sm_count * 8, 256, 0, em->stream>>>(pview_of(em), em->W, em->d_scale, em->d_r);
+        CU(cudaGetLastError());
+        em->r_scaled = true;
+    }
     const uint64_t a = em->h_r_off[first], b = em->h_r_off[first + count];
     CU(cudaMemcpyAsync(out, em->d_r + a, (b - a) * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
     CU(cudaStreamSynchronize(em->stream));

@@ -196,7 +196,8 @@ struct Plan {                 // launch-invariant parameters of the packed M-ste
 // one region per E-step warp (no atomics, no ordering requirement: the M-step sums integers).
 struct ActiveEntry { uint32_t li, p; float rv; uint32_t pad; };   // 16 bytes: one 128-bit store / load per entry
 struct ActiveList {
-    ActiveEntry* ent;         // entries (li = index into the packed list of the EM object, p = window start, rv = posterior)
+    ActiveEntry* ent;         // entries (li = index into the packed list of the EM object, p = window start, rv = UNNORMALISED posterior)
+    float* scale;             // [nlist] 1/normaliser of every list sequence: posterior = rv * scale[li]
     const uint64_t* reg_off;  // [nregions+1] first entry of every region
     uint32_t* cnt;            // [nregions] entries written
     uint32_t* overflow;       // set when a region was too small: the M-step then scans r instead
@@ -214,9 +215,9 @@ __device__ __forceinline__ float lds_f32(uint32_t off, uint32_t ubase) {
 // reference: EM::EStep, src/refinement/EM.cpp:139-200 (gather form). One warp per sequence, lanes =
 // window starts. The G group lookups of a window are fully unrolled; the byte offset of group g's entry is a bit field
 // of the 64-bit window word: FAST (every field below bit 32 after the alignment shift delta): one funnel shift + one
-// mask per lookup; otherwise a clamped funnel shift plus a second shift. Unnormalised posteriors go to r, the
-// normaliser is reduced over the warp, and a second sweep scales by 1/norm (the lines are still in L2) and appends the
-// windows the M-step will need to the warp's region of the active list.
+// mask per lookup; otherwise a clamped funnel shift plus a second shift. ONE pass: unnormalised posteriors go to r and,
+// when they can reach the M-step's threshold, to the warp's region of the active list; the warp reduces the normaliser
+// and stores its reciprocal per sequence. Normalisation is a multiplication by that factor wherever r is consumed.
 //
 // Chunks that contain windows the group tables cannot fully serve — the last W-1 truncated windows (EM.cpp:167) and the
 // windows over the k-mers that hold the N's rand() draws (positions mid..mid+K, Sequence.cpp:38) — run a masked
@@ -249,7 +250,8 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
     const uint32_t lt_mask = (1u << lane) - 1u;
     // this lane's windows start at bases lane-KD + 32*chunk: always the same word offset and bit offset in a word
     constexpr int E_UNROLL = BAMM_E_UNROLL;
-    constexpr int SWEEP = 8;                                // r values per lane loaded together in the second sweep
+    // a window can only reach the M-step's threshold r >= 2^-41 if val >= 2^-41 (1-q): norm >= 1-q (margin for rounding)
+    const float thr0 = FX_HALF_UNIT * (1.0f - gp.q) * 0.999f;
     const int lane_word = (lane - KD) >> 4;
     const int sft = 2 * ((lane - KD) & 15);
     uint32_t c_sh[G], c_mk[G], c_ab[G], c_s2[G];
@@ -305,6 +307,18 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                     *rp = val;
                     rp -= 32;
                     sum += val;
+                    if (emit) {
+                        const bool act = val >= thr0;
+                        const uint32_t m = __ballot_sync(FULL, act);
+                        if (m) {
+                            const uint32_t cnt = __popc(m);
+                            if (lpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
+                            else {
+                                if (act) *reinterpret_cast<uint4*>(lreg + lpos + __popc(m & lt_mask)) = make_uint4(li, (uint32_t)((c << 5) + lane), __float_as_uint(val), 0u);
+                                lpos += cnt;
+                            }
+                        }
+                    }
                 }
             } else {
 #pragma unroll 1
@@ -356,53 +370,35 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
 #pragma unroll
                         for (int u = 0; u < 4; u++) prod *= f[u];
                     }
+                    float val = 0.0f;
                     if (p < LW1) {
-                        const float val = prod * pos;
+                        val = prod * pos;
                         *rp = val;
                         sum += val;
                     }
                     rp -= 32;
+                    if (emit) {
+                        const bool act = val >= thr0;
+                        const uint32_t m = __ballot_sync(FULL, act);
+                        if (m) {
+                            const uint32_t cnt = __popc(m);
+                            if (lpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
+                            else {
+                                if (act) *reinterpret_cast<uint4*>(lreg + lpos + __popc(m & lt_mask)) = make_uint4(li, (uint32_t)p, __float_as_uint(val), 0u);
+                                lpos += cnt;
+                            }
+                        }
+                    }
                 }
             }
         }
         sum = warp_sum(sum);
         const float norm = one_minus_q + sum;
         const float rnorm = __frcp_rn(norm);
-        __syncwarp();
-        // second sweep: scale (the lines are still in L2), zero the tail, list the windows the M-step needs
-        float* __restrict__ rq = rn + lane;
-        for (int kb = 0; kb < L; kb += 32 * SWEEP) {         // warp-uniform trip counts: the ballot below needs every lane
-            float raw[SWEEP];
-#pragma unroll
-            for (int u = 0; u < SWEEP; u++) {                // all loads of the batch first: SWEEP L2 round trips in flight
-                const int k = kb + 32 * u + lane;
-                raw[u] = (k < LW1) ? rq[32 * u] : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < SWEEP; u++) {
-                const int k = kb + 32 * u + lane;
-                const float v = raw[u] * rnorm;
-                if (k < L) rq[32 * u] = v;
-                if (emit && kb + 32 * u < L) {
-                    const bool act = v >= FX_HALF_UNIT;
-                    const uint32_t m = __ballot_sync(FULL, act);
-                    if (m) {
-                        const uint32_t cnt = __popc(m);
-                        if (lpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
-                        else {
-                            if (act) {
-                                const uint4 e = make_uint4(li, (uint32_t)(L - W - k), __float_as_uint(v), 0u);
-                                *reinterpret_cast<uint4*>(lreg + lpos + __popc(m & lt_mask)) = e;
-                            }
-                            lpos += cnt;
-                        }
-                    }
-                }
-            }
-            rq += 32 * SWEEP;
-        }
-        __syncwarp();
+        // r keeps the unnormalised values; the factor is applied by whoever reads them (list / scan M-step,
+        // k_normalise_r before r leaves the device). The tail beyond LW1 is zero since allocation.
         if (lane == 0) {
+            al.scale[li] = rnorm;
             llh_fx += __double2ll_rn((double)logf(norm) * SC_SCALE_D);
             rsum_fx += __double2ll_rn((double)(sum * rnorm) * SC_SCALE_D);
         }
@@ -412,6 +408,19 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
         if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);
     }
     if (al.ent != nullptr) al.cnt[warp] = lpos;             // every lane holds the same count
+}
+
+// r <- r * scale for every packed-list sequence: run before r leaves the device (bamm_em_get_r). One warp per sequence.
+__global__ void k_normalise_r(PackedView pv, int W, const float* __restrict__ scale, float* __restrict__ r) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
+        const int LW1 = (int)pv.seqs[pv.seq_ids[li]].L - W + 1;
+        const float f = scale[li];
+        float* __restrict__ rn = r + pv.r_off[li];
+        for (int k = lane; k < LW1; k += 32) rn[k] *= f;
+    }
 }
 
 // ---- M-step --------------------------------------------------------------------------------------------------------
@@ -473,7 +482,8 @@ __device__ __forceinline__ void scatter_window(const SeqCtx& sc, const Plan& pl,
 
 __global__ void __launch_bounds__(512)
 k_mstep_packed(PackedView pv, Plan pl, const float* __restrict__ r, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */,
-               const uint32_t* __restrict__ list_overflow /* nullptr, or: run only when the active list overflowed */) {
+               const uint32_t* __restrict__ list_overflow /* nullptr, or: run only when the active list overflowed */,
+               const float* __restrict__ scale /* nullptr when r is already normalised, else 1/normaliser per list sequence */) {
     extern __shared__ uint32_t smem_u32[];
     if (list_overflow != nullptr && *list_overflow == 0u) return;          // k_mstep_list does the work
     const uint32_t nbin = (uint32_t)pl.W * pl.Yn;
@@ -498,12 +508,13 @@ k_mstep_packed(PackedView pv, Plan pl, const float* __restrict__ r, unsigned lon
         // r index i = L-W-p runs over [0, LW1); lane takes i = i0 + u*32 + lane
         float cur[M_UNROLL], nxt[M_UNROLL];
 #pragma unroll
-        for (int u = 0; u < M_UNROLL; u++) { const int i = u * 32 + lane; cur[u] = (i < LW1) ? __ldcs(&rn[i]) : 0.0f; }
+        const float sc_f = scale ? scale[li] : 1.0f;      // x * 1.0f is exact: one code path for both states of r
+        for (int u = 0; u < M_UNROLL; u++) { const int i = u * 32 + lane; cur[u] = (i < LW1) ? __ldcs(&rn[i]) * sc_f : 0.0f; }
         for (int i0 = 0; i0 < LW1; i0 += 32 * M_UNROLL) {
 #pragma unroll
             for (int u = 0; u < M_UNROLL; u++) {
                 const int i = i0 + 32 * M_UNROLL + u * 32 + lane;
-                nxt[u] = (i < LW1) ? __ldcs(&rn[i]) : 0.0f;
+                nxt[u] = (i < LW1) ? __ldcs(&rn[i]) * sc_f : 0.0f;
             }
 #pragma unroll
             for (int g = 0; g < M_UNROLL; g += M_GROUP) {
@@ -577,7 +588,7 @@ k_mstep_list(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigned 
             if (e < cnt) {
                 const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(al.ent + base + e));
                 const uint32_t li = raw.x, p = raw.y;
-                const float rv = __uint_as_float(raw.z);
+                const float rv = __uint_as_float(raw.z) * al.scale[li];
                 const uint32_t n = pv.seq_ids[li];
                 const PackedSeq sq = pv.seqs[n];
                 SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = (int)sq.L; sc.mid = (int)sq.mid;
@@ -624,7 +635,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigne
                 const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(ent + e));
                 const uint32_t li = raw.x;
                 const int p = (int)raw.y;
-                const float rv = __uint_as_float(raw.z);
+                const float rv = __uint_as_float(raw.z) * al.scale[li];
                 const uint32_t n = pv.seq_ids[li];
                 const PackedSeq sq = pv.seqs[n];
                 const int L = (int)sq.L, mid = (int)sq.mid;
@@ -635,9 +646,9 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigne
                 } else {
                     const unsigned long long X = __float2ull_rn(rv * FX_SCALE_F);
                     const uint32_t xlo = (uint32_t)X, xhi = (uint32_t)(X >> 32);
-                    const unsigned long long u = window_word(pv.words + sq.word_off, p - K) >> ralign;
+                    const unsigned long long u = X ? window_word(pv.words + sq.word_off, p - K) >> ralign : 0ull;
                     const uint32_t ulo = (uint32_t)u, uhi = (uint32_t)(u >> 32);
-                    const int jmax = min(WT - 1, L - WT - p);                // truncated tail windows stop early (EM.cpp:236)
+                    const int jmax = X ? min(WT - 1, L - WT - p) : -1;       // truncated tail windows stop early (EM.cpp:236)
 #pragma unroll
                     for (int j = 0; j < WT; j++) {
                         constexpr int dummy = 0; (void)dummy;
