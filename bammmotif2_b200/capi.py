@@ -44,6 +44,7 @@ SIGNATURES = {
     "bamm_em_last_timing": (C.c_int, [_vp, _f32p, _f32p]),
     "bamm_em_loop_timing": (C.c_int, [_vp, C.POINTER(C.c_int), _f32p, _f32p, _f32p, _f32p]),
     "bamm_em_set_exchange_buffer": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "bamm_em_launch_count": (C.c_int, [_vp, _u64p]),
     "bamm_em_destroy": (None, [_vp]),
     "bamm_em_exchange_buffer": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),
     "bamm_em_set_global_nseq": (C.c_int, [_vp, C.c_uint64]),
@@ -254,6 +255,11 @@ class EM:
         e, m, up, t = C.c_float(0), C.c_float(0), C.c_float(0), C.c_float(0)
         _check(load().bamm_em_loop_timing(self.h, C.byref(it), C.byref(e), C.byref(m), C.byref(up), C.byref(t)))
         return it.value, e.value, m.value, up.value, t.value
+
+    def launch_count(self):
+        n = C.c_uint64(0)
+        _check(load().bamm_em_launch_count(self.h, C.byref(n)))
+        return n.value
 
     def set_exchange_buffer(self, dev_ptr, words):
         _check(load().bamm_em_set_exchange_buffer(self.h, _vp(dev_ptr), words))

@@ -86,6 +86,7 @@ struct bamm_em {
     ActiveEntry* d_act = nullptr;
     float* d_scale = nullptr;   // 1/normaliser per packed-list sequence (the packed E-step leaves r unnormalised)
     bool r_scaled = true;       // r already holds normalised values
+    uint64_t launches = 0;      // kernels launched by this object (bench.py reports them)
     bool list_w = false;        // width-specialised list kernel usable (two count tables fit shared memory)
     int grid_pl = 0;
     uint32_t *d_act_cnt = nullptr, *d_overflow = nullptr;
@@ -680,6 +681,7 @@ static PackedView pview_of(const bamm_em* em) {
 }
 
 static int launch_estep(bamm_em* em) {
+    em->launches += (em->npk ? 1 : 0) + (em->ngen ? 1 : 0);
     unsigned long long* scal = em->d_xbuf + em->nbin;
     CU(cudaMemsetAsync(scal, 0, 2 * sizeof(unsigned long long), em->stream));
     if (em->npk) {
@@ -724,6 +726,7 @@ static int mstep_list_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl
 }
 
 static int launch_mstep_accumulate(bamm_em* em) {
+    em->launches += (em->npk ? (em->d_act ? 2 : 1) : 0) + (em->ngen ? 1 : 0);
     CU(cudaMemsetAsync(em->d_part, 0, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long), em->stream));
     if (em->npk) {
         PackedView pv = pview_of(em);
@@ -762,6 +765,7 @@ static int launch_mstep_accumulate(bamm_em* em) {
 }
 
 static int launch_mstep_reduce(bamm_em* em) {
+    em->launches += 1;
     k_reduce_parts<<<(em->nbin + 255) / 256, 256, 0, em->stream>>>(em->d_part, em->nparts, em->nbin, em->d_xbuf);
     CU(cudaGetLastError());
     return BAMM_OK;
@@ -773,6 +777,7 @@ static int launch_mstep_local(bamm_em* em) {
 }
 
 static int launch_update(bamm_em* em) {
+    em->launches += 1 + (em->npk ? 1 : 0);
     k_update_model<<<1, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha, em->d_s, em->d_vdiff);
     CU(cudaGetLastError());
     return launch_tuple_table(em);
@@ -1000,6 +1005,7 @@ extern "C" int bamm_em_exchange_buffer(bamm_em* em, void** dev_ptr, uint64_t* wo
     return BAMM_OK;
 }
 extern "C" int bamm_em_set_global_nseq(bamm_em* em, uint64_t n) { REQUIRE(em, "em is NULL"); em->nseq_global = n; return BAMM_OK; }
+extern "C" int bamm_em_launch_count(bamm_em* em, uint64_t* kernels) { REQUIRE(em && kernels, "NULL argument"); *kernels = em->launches; return BAMM_OK; }
 extern "C" int bamm_em_stream(bamm_em* em, void** stream) { REQUIRE(em && stream, "NULL argument"); *stream = (void*)em->stream; return BAMM_OK; }
 
 // ------------------------------------------------------------------------------------------- scoring

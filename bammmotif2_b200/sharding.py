@@ -1,0 +1,72 @@
+"""Host-side logic of the multi-GPU path: which sequences a rank owns and what the ranks exchange.
+
+Sequences are independent in the E-step (per-sequence normalisation, EM.cpp:149-196) and the M-step is a sum over
+sequences (EM.cpp:231-243), so ranks own contiguous blocks of whole sequences, balanced by stored length. The only
+per-iteration exchange is a SUM over ranks of the library's exchange buffer (bamm_em_exchange_buffer): int64 words,
+  [0, W*A^(K+1))   counts n[K][y][j] in 2^-40 fixed point, laid out [j][y]
+  [nbin]           log likelihood in 2^-32 fixed point
+  [nbin+1]         sum of all posteriors in 2^-32 fixed point (optimize_q, EM.cpp:505-519)
+Integer sums are associative: the reduced buffer — and with it the model every rank computes from it — does not depend
+on the rank count or the reduction order.
+"""
+import numpy as np
+
+COUNT_SCALE = float(2 ** 40)
+SCALAR_SCALE = float(2 ** 32)
+
+
+def shard_bounds(lengths, world_size):
+    """Contiguous [start, end) sequence ranges, one per rank, whole sequences only, balanced by sum of lengths:
+    rank r ends at the first sequence boundary at or after r+1 equal shares of the total (FASTA order is preserved
+    inside a shard, so r indexing is unchanged)."""
+    lengths = np.asarray(lengths, np.int64)
+    n = len(lengths)
+    if world_size <= 1 or n == 0:
+        return [(0, n)] + [(n, n)] * (max(world_size, 1) - 1)
+    csum = np.cumsum(lengths)
+    total = int(csum[-1])
+    bounds, start = [], 0
+    for r in range(world_size):
+        if r == world_size - 1:
+            end = n
+        else:
+            target = total * (r + 1) / world_size
+            end = int(np.searchsorted(csum, target, side="left")) + 1
+            end = min(max(end, start), n)
+        bounds.append((start, end))
+        start = end
+    return bounds
+
+
+def exchange_words(A, K, W):
+    return W * A ** (K + 1) + 2
+
+
+def pack_exchange(counts_jy_fx, llh, rsum):
+    """counts_jy_fx: int64 [W*Yn] fixed-point counts in [j][y] order; returns the int64 exchange buffer."""
+    buf = np.empty(len(counts_jy_fx) + 2, np.int64)
+    buf[:-2] = counts_jy_fx
+    buf[-2] = np.int64(np.rint(float(llh) * SCALAR_SCALE))
+    buf[-1] = np.int64(np.rint(float(rsum) * SCALAR_SCALE))
+    return buf
+
+
+def unpack_exchange(buf, A, K, W):
+    """Returns (n[K] as float32 in the reference's [y][j] order, llh, sum of posteriors)."""
+    Yn = A ** (K + 1)
+    buf = np.asarray(buf, np.int64)
+    nK = (buf[:W * Yn].astype(np.float64) / COUNT_SCALE).astype(np.float32).reshape(W, Yn).T.copy()
+    return nK, np.float32(buf[W * Yn] / SCALAR_SCALE), np.float32(buf[W * Yn + 1] / SCALAR_SCALE)
+
+
+def allreduce_exchange(tensor, group=None):
+    """In-place SUM of the exchange buffer over all ranks (torch.distributed: NCCL on the GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+    return tensor
+
+
+def optimize_q(nseq_global, rsum):
+    """reference: EM::optimize_q, src/refinement/EM.cpp:515 (formula kept as is), with the GLOBAL sequence count"""
+    f = np.float32
+    return (f(nseq_global) - f(rsum) + f(1.0)) / (f(nseq_global) + f(2.0))

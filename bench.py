@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 from bammmotif2_b200 import synth  # noqa: E402
 from bammmotif2_b200 import hostmodel  # noqa: E402
+from bammmotif2_b200 import sharding  # noqa: E402
 
 METRIC = "EM bp·iter/s (order-k, both strands)"
 UNIT = "bp·iter/s"
@@ -60,6 +61,19 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic(workload, nseq, mstep_dominant):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json,
+    written by tools/ncu_traffic.py); only valid for the workload and size that capture was taken on."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        if t.get("workload") == workload and int(t.get("nseq", -1)) == int(nseq):
+            return t["mstep_bytes" if mstep_dominant else "estep_bytes"]
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -258,7 +272,7 @@ def main():
             for _ in range(n):
                 em.estep_local()
                 em.mstep_local()
-                dist.all_reduce(xt, op=dist.ReduceOp.SUM)
+                sharding.allreduce_exchange(xt)
                 em.finish_iteration(sync=False)
         stream.synchronize()
 
@@ -271,9 +285,11 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = em.launch_count()
     e0.record(stream)
     run_iters(args.steps)
     e1.record(stream)
+    launches = em.launch_count() - launches0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -292,10 +308,10 @@ def main():
         iters, e_ms, m_ms, u_ms, _ = em.loop_timing()
         peak, peak_src = peaks()
         dom_name, dom_ms = ("k_mstep (M-step accumulation)", m_ms) if m_ms >= e_ms else ("k_estep (E-step)", e_ms)
-        bytes_per_launch = 6.0 * pos_local          # 2 B k-mer index + 4 B r per position, per kernel
+        bytes_per_launch = 6.0 * pos_local          # ALGORITHMIC: 2 B k-mer index + 4 B r per position, per kernel
         ach = bytes_per_launch / (dom_ms / iters * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": measured_traffic(args.workload, nseq, m_ms >= e_ms), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "estep_ms": e_ms / iters, "mstep_accum_ms": m_ms / iters, "reduce_update_ms": u_ms / iters,
                 "whole_iteration_frac_of_12B_roofline": (12.0 * pos_local / (ms_total / args.steps * 1e-3) / 1e9) / peak}
@@ -315,18 +331,20 @@ def main():
         ss2 = capi.SeqSet(data["codes"].reshape(-1), data["offsets"], A, data["ppos"], data["pkmer"])   # H2D from pinned host memory
         em2 = capi.EM(ss2, wl["W"], wl["K"], wl["K_bg"])                                                 # builds the index on the device
         em2.set_model(v0, vbg, alpha, Q)
+        # every iteration ends with a device->host read of its result (log likelihood + sum|dv|), like EM::optimize's loop
         if world > 1:
             em2.set_exchange_buffer(xt.data_ptr(), em2.exchange_buffer()[1])
             em2.set_global_nseq(nseq * world)
             st2 = torch.cuda.ExternalStream(em2.stream(), device=torch.device("cuda", local_rank))
-            with torch.cuda.stream(st2):
-                for _ in range(args.steps):
+            for _ in range(args.steps):
+                with torch.cuda.stream(st2):
                     em2.estep_local(); em2.mstep_local()
-                    dist.all_reduce(xt, op=dist.ReduceOp.SUM)
-                    em2.finish_iteration(sync=False)
-            st2.synchronize()
+                    sharding.allreduce_exchange(xt)
+                e2e_llh, e2e_vdiff = em2.finish_iteration(sync=True)
         else:
-            em2.iterate(args.steps)
+            for _ in range(args.steps):
+                em2.estep_local(); em2.mstep_local()
+                e2e_llh, e2e_vdiff = em2.finish_iteration(sync=True)
         vfinal = em2.model()                                                                              # D2H
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -335,11 +353,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         h2d = data["codes"].nbytes + data["offsets"].nbytes + data["ppos"].nbytes + data["pkmer"].nbytes + v0.nbytes + vbg.nbytes + alpha.nbytes
-        d2h = vfinal.nbytes + 24
+        d2h = vfinal.nbytes + 20 * args.steps
         e2e = {"value": bp_total * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps, "seconds": dt,
                "what": "bamm_seqset_create (H2D of codes from pinned host memory) + index build + bamm_em_create/set_model + "
-                       "%d iterations + bamm_em_get_model (D2H); upload amortised over the %d iterations" % (args.steps, args.steps)}
+                       "%d iterations, each read back (llh, sum|dv|) + bamm_em_get_model (D2H); upload amortised over the %d iterations" % (args.steps, args.steps)}
         em2.close(); ss2.close()
 
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------------------
@@ -363,7 +381,7 @@ def main():
                        "l2": "inputs (%.1f GB index + r per GPU) exceed the 126 MB L2" % (6.0 * pos_local / 1e9) if 6.0 * pos_local > 2.0e8
                              else "inputs fit in L2; no flush between iterations (EM iterates over resident data)",
                        "parallelism": "sequence shards, dp%d" % world},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         }
         if roof:
             line["roofline"] = roof

@@ -106,6 +106,8 @@ int bamm_em_last_timing(bamm_em* em, float* estep_ms, float* mstep_ms);
 /* device times of the last bamm_em_iterate call, summed over its iterations (CUDA events on the EM stream):
  * E-step kernel, M-step accumulation kernel, reduce + model update, and first-launch-to-last-completion. */
 int bamm_em_loop_timing(bamm_em* em, int* iters, float* estep_ms, float* maccum_ms, float* update_ms, float* total_ms);
+/* number of CUDA kernels this object has launched so far (E-step, M-step, reduce, update, table kernels) */
+int bamm_em_launch_count(bamm_em* em, uint64_t* kernels);
 void bamm_em_destroy(bamm_em* em);
 
 /* ---- multi-GPU (sequences sharded over ranks, one process per GPU) ---------------------------- */
