@@ -100,6 +100,7 @@ struct bamm_em {
     uint64_t* d_r_off = nullptr;
     float* d_r = nullptr;
     float* d_s = nullptr;         // [j][y]
+    float* d_sT = nullptr;        // the same table in the reference's [y][j] order (row gathers of the patched k-mers)
     float* d_v = nullptr;         // all orders
     float* d_vK_prev = nullptr;
     float* d_n = nullptr;         // all orders (float, reference layout)
@@ -362,7 +363,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     if (em->stream) cudaStreamSynchronize(em->stream);
     cudaFree(em->d_act); cudaFree(em->d_scale); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
     cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab);
-    cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_v);
+    cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_sT); cudaFree(em->d_v);
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
     if (em->own_xbuf) cudaFree(em->d_xbuf);
     cudaFree(em->d_vdiff);
@@ -526,6 +527,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     CUE(cudaMalloc(&em->d_r, (em->rsize ? em->rsize : 1) * sizeof(float)));
     CUE(cudaMemset(em->d_r, 0, (em->rsize ? em->rsize : 1) * sizeof(float)));   // the packed E-step never touches the tail i >= LW1
     CUE(cudaMalloc(&em->d_s, (uint64_t)em->nbin * sizeof(float)));
+    CUE(cudaMalloc(&em->d_sT, (uint64_t)em->nbin * sizeof(float)));
     CUE(cudaMalloc(&em->d_v, em->model_size * sizeof(float)));
     CUE(cudaMalloc(&em->d_vK_prev, (uint64_t)em->nbin * sizeof(float)));
     CUE(cudaMalloc(&em->d_n, em->model_size * sizeof(float)));
@@ -639,7 +641,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
     CU(cudaMemcpyAsync(em->d_v, v_all, em->model_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
     CU(cudaMemcpyAsync(em->d_vbg, vbg_all, em->bg_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
     CU(cudaMemcpyAsync(em->d_alpha, alpha, (uint64_t)(em->K + 1) * em->W * sizeof(float), cudaMemcpyHostToDevice, em->stream));
-    k_make_s<<<64, 256, 0, em->stream>>>(em->dims, em->d_v, em->d_vbg, em->d_s, em->d_vK_prev);
+    k_make_s<<<64, 256, 0, em->stream>>>(em->dims, em->d_v, em->d_vbg, em->d_s, em->d_sT, em->d_vK_prev);
     CU(cudaGetLastError());
     { int rc = launch_tuple_table(em); if (rc) return rc; }
     CU(cudaStreamSynchronize(em->stream));
@@ -657,7 +659,7 @@ static ActiveList alist_of(const bamm_em* em) {
 template <int G, bool FAST> static int estep_packed_one(bamm_em* em, const PackedView* pv, bool optin_only) {
     if (optin_only) return max_smem_optin(k_estep_packed<G, FAST>, em->smem_pe);
     GroupPlan gp = em->gplan; gp.q = em->q;
-    k_estep_packed<G, FAST><<<em->grid_pe, em->block_pe, em->smem_pe, em->stream>>>(*pv, gp, em->d_tab, em->d_s, em->d_r, em->d_xbuf + em->nbin, alist_of(em));
+    k_estep_packed<G, FAST><<<em->grid_pe, em->block_pe, em->smem_pe, em->stream>>>(*pv, gp, em->d_tab, em->d_s, em->d_sT, em->d_r, em->d_xbuf + em->nbin, alist_of(em));
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, const Plan*, bool optin_only) {
@@ -778,7 +780,7 @@ static int launch_mstep_local(bamm_em* em) {
 
 static int launch_update(bamm_em* em) {
     em->launches += 1 + (em->npk ? 1 : 0);
-    k_update_model<<<1, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha, em->d_s, em->d_vdiff);
+    k_update_model<<<1, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha, em->d_s, em->d_sT, em->d_vdiff);
     CU(cudaGetLastError());
     return launch_tuple_table(em);
 }

@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(1024)
 k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn] fixed-point counts, [j][y] */,
                float* __restrict__ n_all, float* __restrict__ v_all, float* __restrict__ vK_prev,
                const float* __restrict__ vbg_all, const float* __restrict__ alpha,
-               float* __restrict__ s_lin /* [j][y] */, float* __restrict__ vdiff_out) {
+               float* __restrict__ s_lin /* [j][y] */, float* __restrict__ s_rows /* [y][j], same values */,
+               float* __restrict__ vdiff_out) {
     const int W = d.W, K = d.K, A = d.A;
     const uint32_t YK = d.Y[K + 1];
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
@@ -334,20 +335,24 @@ k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn
     const uint32_t YB = d.Y[d.K_bg + 1];
     for (uint32_t i = tid; i < YK * (uint32_t)W; i += nt) {
         const uint32_t y = i / W, j = i % W;
-        s_lin[(uint32_t)j * YK + y] = vK[i] / vb[y % YB];
+        const float sv = vK[i] / vb[y % YB];
+        s_lin[(uint32_t)j * YK + y] = sv;
+        s_rows[i] = sv;
     }
 }
 
 // s table only (first E-step after set_model)
 __global__ void k_make_s(ModelDims d, const float* __restrict__ v_all, const float* __restrict__ vbg_all,
-                         float* __restrict__ s_lin, float* __restrict__ vK_prev) {
+                         float* __restrict__ s_lin, float* __restrict__ s_rows, float* __restrict__ vK_prev) {
     const int W = d.W, K = d.K;
     const uint32_t YK = d.Y[K + 1], YB = d.Y[d.K_bg + 1];
     const float* vK = v_all + d.voff[K];
     const float* vb = vbg_all + d.bgoff[d.K_bg];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < YK * (uint32_t)W; i += gridDim.x * blockDim.x) {
         const uint32_t y = i / W, j = i % W;
-        s_lin[(uint32_t)j * YK + y] = vK[i] / vb[y % YB];
+        const float sv = vK[i] / vb[y % YB];
+        s_lin[(uint32_t)j * YK + y] = sv;
+        s_rows[i] = sv;
         vK_prev[i] = vK[i];
     }
 }

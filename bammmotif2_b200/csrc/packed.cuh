@@ -235,7 +235,7 @@ __device__ __forceinline__ float lds_f32(uint32_t off, uint32_t ubase) {
 template <int G, bool FAST>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g /* [W][Yn] */,
-               float* __restrict__ r, unsigned long long* __restrict__ scal, ActiveList al) {
+               const float* __restrict__ s_rows /* [Yn][W] */, float* __restrict__ r, unsigned long long* __restrict__ scal, ActiveList al) {
     extern __shared__ float tab[];
     for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
     __syncthreads();
@@ -351,8 +351,26 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                     }
                     // the single columns are multiplied after the whole groups: a re-association of the reference's
                     // ascending-j product, far inside the 1e-5 tolerance
-                    // four columns per round: their table loads are independent (one L2 round trip instead of four),
-                    // the multiplications stay in ascending column order
+                    // (a) columns whose k-mer holds a draw of the N: the K+1 patched k-mers are the same for the whole
+                    //     sequence, so for each of them the lanes read neighbouring elements of ONE row of the [y][j]
+                    //     copy of the table — a coalesced load instead of a 32-way gather
+                    if (__any_sync(FULL, over_n)) {
+                        for (int d0 = 0; d0 <= K; d0 += 4) {
+                            float f[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int d = d0 + u, j = mid + d - p;
+                                f[u] = 1.0f;
+                                if (d <= K && over_n && j >= 0 && j <= jmax)
+                                    f[u] = __ldg(&s_rows[(uint64_t)pv.ypatch[(uint64_t)n * (K + 1) + d] * W + j]);
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) prod *= f[u];
+                        }
+                        cols &= ~ncols;
+                    }
+                    // (b) the other single columns (partial group of a truncated window, unpatched neighbours inside a
+                    //     group the N broke), four per round so that their gathers are in flight together
                     while (cols) {
                         float f[4];
 #pragma unroll
@@ -361,10 +379,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                             if (cols) {
                                 const int j = __ffs(cols) - 1;
                                 cols &= cols - 1u;
-                                uint32_t y = field(w, 62 - 2 * KD - 2 * j, maskK);
-                                const int d = p + j - mid;
-                                if (over_n && d >= 0 && d <= K) y = pv.ypatch[(uint64_t)n * (K + 1) + d];
-                                f[u] = __ldg(&s_g[(uint32_t)j * gp.Yn + y]);
+                                f[u] = __ldg(&s_g[(uint32_t)j * gp.Yn + field(w, 62 - 2 * KD - 2 * j, maskK)]);
                             }
                         }
 #pragma unroll
