@@ -522,8 +522,8 @@ k_mstep_packed(PackedView pv, Plan pl, const float* __restrict__ r, unsigned lon
         uint32_t qhead = 0, qcount = 0;        // warp-uniform
         // r index i = L-W-p runs over [0, LW1); lane takes i = i0 + u*32 + lane
         float cur[M_UNROLL], nxt[M_UNROLL];
-#pragma unroll
         const float sc_f = scale ? scale[li] : 1.0f;      // x * 1.0f is exact: one code path for both states of r
+#pragma unroll
         for (int u = 0; u < M_UNROLL; u++) { const int i = u * 32 + lane; cur[u] = (i < LW1) ? __ldcs(&rn[i]) * sc_f : 0.0f; }
         for (int i0 = 0; i0 < LW1; i0 += 32 * M_UNROLL) {
 #pragma unroll
@@ -619,6 +619,27 @@ k_mstep_list(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigned 
     }
 }
 
+// one scatter step on explicit shared-window addresses: predicated 32-bit add to the low table, wrap-around detection from
+// the returned old value, predicated add of (high part + carry) to the high table hioff bytes further — no branches
+__device__ __forceinline__ void atoms_add_carry(uint32_t addr, uint32_t hioff, uint32_t xlo, uint32_t xhi, bool valid) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, c, z;\n\t"
+        ".reg .u32 o, s, h, a2;\n\t"
+        "setp.ne.u32 p, %4, 0;\n\t"
+        "mov.u32 o, 0;\n\t"
+        "@p atom.shared.add.u32 o, [%0], %2;\n\t"
+        "add.u32 s, o, %2;\n\t"
+        "setp.lt.u32 c, s, o;\n\t"
+        "selp.u32 h, 1, 0, c;\n\t"
+        "add.u32 h, h, %3;\n\t"
+        "setp.ne.and.u32 z, h, 0, p;\n\t"
+        "add.u32 a2, %0, %1;\n\t"
+        "@z red.shared.add.u32 [a2], h;\n\t"
+        "}"
+        :: "r"(addr), "r"(hioff), "r"(xlo), "r"(xhi), "r"((uint32_t)valid) : "memory");
+}
+
 // Width-specialised list M-step. The motif width is a template parameter, so the W scatter steps of a window are
 // fully unrolled with immediate shifts: the window word is right-aligned once (its last base in the lowest bits) and
 // column j's k-mer is the bit field at 2(W-1-j). Two CTA-private shared tables: low 32 bits of the 2^-40 fixed-point
@@ -641,6 +662,8 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigne
     const int K = pl.K;
     const uint32_t maskK = pl.Yn - 1;
     const int ralign = 62 - 2 * (K + WT - 1);                              // right-alignment shift of the window word
+    const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh);
+    const uint32_t hi_off = nbin * 4u, yn4 = pl.Yn * 4u;
     for (uint32_t rg = warp; rg < nregions; rg += nwarps) {
         const uint32_t cnt = al.cnt[rg];
         const ActiveEntry* __restrict__ ent = al.ent + al.reg_off[rg];
@@ -664,17 +687,13 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigne
                     const unsigned long long u = X ? window_word(pv.words + sq.word_off, p - K) >> ralign : 0ull;
                     const uint32_t ulo = (uint32_t)u, uhi = (uint32_t)(u >> 32);
                     const int jmax = X ? min(WT - 1, L - WT - p) : -1;       // truncated tail windows stop early (EM.cpp:236)
+                    uint32_t col_s = lo_s;                                   // shared address of column j's first bin
 #pragma unroll
                     for (int j = 0; j < WT; j++) {
-                        constexpr int dummy = 0; (void)dummy;
                         const int sh = 2 * (WT - 1 - j);
                         const uint32_t y = (sh >= 32 ? (uhi >> (sh - 32)) : __funnelshift_r(ulo, uhi, sh)) & maskK;
-                        if (j <= jmax) {
-                            const uint32_t bin = (uint32_t)j * pl.Yn + y;
-                            const uint32_t old = atomicAdd(&lo_sh[bin], xlo);
-                            const uint32_t h = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
-                            if (h) atomicAdd(&hi_sh[bin], h);
-                        }
+                        atoms_add_carry(col_s + (y << 2), hi_off, xlo, xhi, j <= jmax);
+                        col_s += yn4;
                     }
                 }
             }

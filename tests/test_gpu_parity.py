@@ -195,3 +195,94 @@ def test_error_paths(capi):
     e0 = capi.EM(ss, 7, 0, 0, subset=np.zeros(0, np.uint64))
     e0.set_model(g["m1_v_init"], g["bg_v"], g["m1_alpha"], g.q)
     assert e0.estep() == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# kernel variants and size-independent properties
+
+def _run_variant(capi, g, env, iters=3):
+    """First `iters` iterations with environment switches that select another kernel path for the same arithmetic."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        ss = make_seqset(capi, g)
+        em = capi.EM(ss, g.W, g.K, g.K_bg_model)
+        em.set_model(g["m1_v_init"], g["bg_v"], g["m1_alpha"], g.q)
+        llh = [em.estep()]
+        r1 = em.r()
+        em.mstep()
+        n1 = em.counts()
+        em.iterate(iters - 1)
+        return dict(llh=llh, r1=r1, n1=n1, v=em.model(), n=em.counts())
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("case", ["jund_k2", "syn_k2_N", "syn_k4", "syn_k3_fdr"])
+def test_kernel_paths_agree(capi, case):
+    """Packed path with the active list (default), with an overflowing list (device-side fall-back to the scan
+    M-step), without the list, without the reduced leading context, and the generic index-array path: the M-step sums
+    the same fixed-point integers on every path, so counts are BIT-identical wherever the E-step is; E-step variants
+    differ only by the association of the column products (1e-5 tolerance)."""
+    g = Golden(case)
+    base = _run_variant(capi, g, {})
+    for env, same_estep in (({"BAMM_LIST_FRAC": "0"}, True), ({"BAMM_LIST_FRAC": "0.000001"}, True),
+                            ({"BAMM_NO_LISTW": "1"}, True), ({"BAMM_NO_REDUCED": "1"}, False),
+                            ({"BAMM_TABLE_BYTES": "40000"}, False), ({"BAMM_NO_PACKED": "1"}, False)):
+        alt = _run_variant(capi, g, env)
+        if same_estep:
+            assert np.array_equal(alt["r1"], base["r1"]), env
+            assert np.array_equal(alt["n1"], base["n1"]), env
+            assert np.array_equal(alt["v"], base["v"]) and np.array_equal(alt["n"], base["n"]), env
+        else:
+            assert_rel(alt["r1"], base["r1"], RTOL, what="r %s" % env)
+            assert_rel(alt["n1"], base["n1"], RTOL, atol=1e-9, what="n %s" % env)
+            assert_rel(alt["v"], base["v"], 1e-4, what="v %s" % env)
+        assert_rel(alt["llh"], base["llh"], RTOL, what="llh %s" % env)
+
+
+def test_properties_at_scale(capi):
+    """Size-independent checks on a set far larger than the fixtures (40k x 500 bp, W=20, K=4, both strands):
+    posteriors of a sequence sum to 1 - (1-q)/norm < 1, the zero tail is intact, every count column sums to the
+    posterior mass of the windows that reach it (truncation rule of EM.cpp:236), the model rows stay near-normalised."""
+    from bammmotif2_b200 import synth, hostmodel
+    nseq, L0, W, K, Kbg, A, q = 40000, 500, 20, 4, 2, 4, 0.3
+    fwd, sites, _ = synth.planted_sequences(99, nseq, L0, W)
+    codes = synth.stored_both_strands(fwd)
+    ppos, pkmer = synth.middle_n_patches(codes, 99)
+    L = codes.shape[1]
+    offsets = np.arange(nseq + 1, dtype=np.uint64) * np.uint64(L)
+    ss = capi.SeqSet(codes.ravel(), offsets, A, ppos, pkmer)
+    vbg = hostmodel.background_from_counts(ss.count_kmers(Kbg), A, Kbg, hostmodel.default_bg_alpha(Kbg))
+    alpha = hostmodel.default_motif_alpha(K, W)
+    v0 = hostmodel.motif_from_sites(sites, A, K, alpha, vbg)
+    em = capi.EM(ss, W, K, Kbg)
+    em.set_model(v0, vbg, alpha, q)
+    em.iterate(2)
+    llh = em.estep()
+    r = em.r().reshape(nseq, L)
+    LW1 = L - W + 1
+    assert np.all(r[:, LW1:] == 0) and np.all(r >= 0)
+    mass = r.sum(axis=1, dtype=np.float64)
+    assert np.all(mass < 1.0) and np.all(mass > 0.0)
+    norm = (1.0 - q) / (1.0 - mass)                                   # from r0 = (1-q)/norm = 1 - sum_i r_i
+    assert abs(np.log(norm).sum() - llh) <= 1e-4 * abs(llh)
+    em.mstep()
+    n = em.counts()
+    off = hostmodel.v_offsets(A, K, W)
+    nK = n[off[K]:off[K + 1]].reshape(A ** (K + 1), W).astype(np.float64)
+    # column j receives r[L-W-p] from every window start p with j <= min(W-1, L-W-p)  <=>  r index i >= j
+    tail_mass = r[:, :LW1].sum(axis=0, dtype=np.float64)             # by r index i
+    for j in range(W):
+        expect = tail_mass[j:].sum()
+        assert abs(nK[:, j].sum() - expect) <= 1e-6 * expect, j
+    v = em.model()
+    vK = v[off[K]:off[K + 1]].reshape(A ** (K + 1), W)
+    sums = vK.reshape(A ** K, A, W).sum(axis=1)                       # over the newest base, per context and column
+    # (approximately: the denominator n[K-1][context][j-1] counts windows by their previous column, Motif.h:130-133)
+    assert np.all(np.abs(sums[:, K:] - 1.0) < 2e-2)
