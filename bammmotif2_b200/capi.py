@@ -52,6 +52,8 @@ SIGNATURES = {
     "bamm_em_mstep_local": (C.c_int, [_vp]),
     "bamm_em_finish_iteration": (C.c_int, [_vp, C.c_int, _f32p, _f32p]),
     "bamm_em_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "bamm_em_peer_alloc": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "bamm_em_peer_attach": (C.c_int, [_vp, _vp]),
     "bamm_score_logodds": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _u64p, _f32p]),
 }
 
@@ -274,6 +276,17 @@ class EM:
         p = _vp()
         _check(load().bamm_em_stream(self.h, C.byref(p)))
         return p.value
+
+    def peer_alloc(self, rank, world):
+        """Allocates this rank's NVLink receive buffer; returns its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        _check(load().bamm_em_peer_alloc(self.h, rank, world, C.cast(buf, _vp)))
+        return buf.raw
+
+    def peer_attach(self, handles):
+        """handles: world x 64 bytes (rank order). Afterwards mstep_local pushes to every rank over NVLink."""
+        buf = C.create_string_buffer(bytes(handles), len(handles))
+        _check(load().bamm_em_peer_attach(self.h, C.cast(buf, _vp)))
 
     def set_global_nseq(self, n):
         _check(load().bamm_em_set_global_nseq(self.h, n))

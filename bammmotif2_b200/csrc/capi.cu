@@ -87,6 +87,14 @@ struct bamm_em {
     float* d_scale = nullptr;   // 1/normaliser per packed-list sequence (the packed E-step leaves r unnormalised)
     bool r_scaled = true;       // r already holds normalised values
     uint64_t launches = 0;      // kernels launched by this object (bench.py reports them)
+    // NVLink peer exchange (multi-GPU): local receive buffer [2][world][nbin+2] + flags, peers' buffers mapped through CUDA IPC
+    int peer_rank = 0, peer_world = 0;
+    bool peer_attached = false;
+    unsigned char* d_peer_local = nullptr;      // slots, then flags
+    void* peer_mapped[MAX_PEERS] = {nullptr};   // cudaIpcOpenMemHandle results (to close)
+    PeerPtrs peer_ptrs;
+    uint32_t peer_epoch = 0;
+    unsigned int* d_peer_done = nullptr;
     bool list_w = false;        // width-specialised list kernel usable (two count tables fit shared memory)
     int grid_pl = 0;
     uint32_t *d_act_cnt = nullptr, *d_overflow = nullptr;
@@ -361,6 +369,8 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     if (!em) return;
     cudaSetDevice(em->device);
     if (em->stream) cudaStreamSynchronize(em->stream);
+    for (int p = 0; p < MAX_PEERS; p++) if (em->peer_mapped[p]) cudaIpcCloseMemHandle(em->peer_mapped[p]);
+    cudaFree(em->d_peer_local); cudaFree(em->d_peer_done);
     cudaFree(em->d_act); cudaFree(em->d_scale); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
     cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab);
     cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_sT); cudaFree(em->d_v);
@@ -768,6 +778,20 @@ static int launch_mstep_accumulate(bamm_em* em) {
 
 static int launch_mstep_reduce(bamm_em* em) {
     em->launches += 1;
+    if (em->peer_attached) {
+        // fused reduce + NVLink push to every rank, then wait-and-sum on this rank (no collective call, no host)
+        em->peer_epoch++;
+        const uint32_t parity = em->peer_epoch & 1u, words = em->nbin + 2;
+        k_reduce_push<<<(words + 255) / 256, 256, 0, em->stream>>>(em->d_part, em->nparts, em->nbin, em->d_xbuf + em->nbin, em->peer_ptrs,
+                                                                   em->peer_rank, em->peer_world, parity, em->peer_epoch, em->d_peer_done);
+        CU(cudaGetLastError());
+        const size_t slot_bytes = (size_t)2 * em->peer_world * words * sizeof(unsigned long long);
+        k_peer_sum<<<(words + 255) / 256, 256, 0, em->stream>>>((const unsigned long long*)em->d_peer_local, (const unsigned int*)(em->d_peer_local + slot_bytes),
+                                                                em->peer_world, em->nbin, parity, em->peer_epoch, em->d_xbuf);
+        CU(cudaGetLastError());
+        em->launches += 1;
+        return BAMM_OK;
+    }
     k_reduce_parts<<<(em->nbin + 255) / 256, 256, 0, em->stream>>>(em->d_part, em->nparts, em->nbin, em->d_xbuf);
     CU(cudaGetLastError());
     return BAMM_OK;
@@ -1009,6 +1033,53 @@ extern "C" int bamm_em_exchange_buffer(bamm_em* em, void** dev_ptr, uint64_t* wo
 extern "C" int bamm_em_set_global_nseq(bamm_em* em, uint64_t n) { REQUIRE(em, "em is NULL"); em->nseq_global = n; return BAMM_OK; }
 extern "C" int bamm_em_launch_count(bamm_em* em, uint64_t* kernels) { REQUIRE(em && kernels, "NULL argument"); *kernels = em->launches; return BAMM_OK; }
 extern "C" int bamm_em_stream(bamm_em* em, void** stream) { REQUIRE(em && stream, "NULL argument"); *stream = (void*)em->stream; return BAMM_OK; }
+
+
+// ---- NVLink peer exchange ------------------------------------------------------------------------------------------
+extern "C" int bamm_em_peer_alloc(bamm_em* em, int rank, int world, void* ipc_handle_out) {
+    REQUIRE(em && ipc_handle_out, "NULL argument");
+    REQUIRE(world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world, "rank %d / world %d out of range (max %d ranks)", rank, world, MAX_PEERS);
+    REQUIRE(!em->d_peer_local, "peer buffer already allocated");
+    CU(cudaSetDevice(em->device));
+    const size_t words = (size_t)em->nbin + 2;
+    const size_t slot_bytes = (size_t)2 * world * words * sizeof(unsigned long long);
+    const size_t bytes = slot_bytes + MAX_PEERS * sizeof(unsigned int);
+    CU(cudaMalloc(&em->d_peer_local, bytes));
+    CU(cudaMemset(em->d_peer_local, 0, bytes));
+    CU(cudaMalloc(&em->d_peer_done, sizeof(unsigned int)));
+    CU(cudaMemset(em->d_peer_done, 0, sizeof(unsigned int)));
+    CU(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, em->d_peer_local));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    em->peer_rank = rank; em->peer_world = world;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_peer_attach(bamm_em* em, const void* ipc_handles) {
+    REQUIRE(em && ipc_handles, "NULL argument");
+    if (!em->d_peer_local) return fail(BAMM_E_STATE, "bamm_em_peer_alloc has not been called");
+    CU(cudaSetDevice(em->device));
+    const size_t words = (size_t)em->nbin + 2;
+    const size_t slot_bytes = (size_t)2 * em->peer_world * words * sizeof(unsigned long long);
+    for (int p = 0; p < em->peer_world; p++) {
+        unsigned char* base = em->d_peer_local;
+        if (p != em->peer_rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const unsigned char*)ipc_handles + (size_t)p * sizeof(h), sizeof(h));
+            void* mapped = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(BAMM_E_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", p, cudaGetErrorString(e));
+            em->peer_mapped[p] = mapped;
+            base = (unsigned char*)mapped;
+        }
+        em->peer_ptrs.slots[p] = (unsigned long long*)base;
+        em->peer_ptrs.flags[p] = (unsigned int*)(base + slot_bytes);
+    }
+    em->peer_attached = true;
+    return BAMM_OK;
+}
 
 // ------------------------------------------------------------------------------------------- scoring
 extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,

@@ -250,6 +250,60 @@ __global__ void k_reduce_parts(const unsigned long long* __restrict__ part, uint
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Multi-GPU exchange over NVLink peer memory, fused into the tail of the M-step: the reduction of
+// the per-CTA partial tables writes this rank's sums straight into slot [rank] of EVERY rank's receive buffer (peer
+// stores through CUDA-IPC mapped pointers) and the last CTA to finish publishes the iteration's epoch in every rank's
+// flag array. k_peer_sum on each rank then waits for all flags and adds the slots in rank order — the same integers
+// on every rank, hence bit-identical models without a collective library call or a host round trip.
+// Receive buffers are double-buffered by epoch parity: a rank can run at most one iteration ahead of its peers.
+constexpr int MAX_PEERS = 16;
+struct PeerPtrs { unsigned long long* slots[MAX_PEERS]; unsigned int* flags[MAX_PEERS]; };
+
+__global__ void k_reduce_push(const unsigned long long* __restrict__ part, uint32_t nparts, uint32_t nbin,
+                              const unsigned long long* __restrict__ scal /* 2 scalars of the E-step */,
+                              PeerPtrs pp, int rank, int world, uint32_t parity, uint32_t epoch, unsigned int* __restrict__ done) {
+    const uint32_t words = nbin + 2;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < words) {
+        unsigned long long acc = 0;
+        if (b < nbin) for (uint32_t c = 0; c < nparts; c++) acc += part[(uint64_t)c * nbin + b];
+        else acc = scal[b - nbin];
+        const uint64_t at = ((uint64_t)parity * world + rank) * words + b;
+        for (int p = 0; p < world; p++) pp.slots[p][at] = acc;
+    }
+    __threadfence_system();                       // this CTA's peer stores are visible before it counts itself done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) {              // last CTA: everything of this rank has landed
+            *done = 0u;
+            __threadfence_system();
+            for (int p = 0; p < world; p++) {
+                volatile unsigned int* f = pp.flags[p] + rank;
+                *f = epoch;
+            }
+            __threadfence_system();
+        }
+    }
+}
+
+__global__ void k_peer_sum(const unsigned long long* __restrict__ slots /* [2][world][words] local */, const unsigned int* flags /* [world] local */,
+                           int world, uint32_t nbin, uint32_t parity, uint32_t epoch, unsigned long long* __restrict__ xbuf) {
+    const uint32_t words = nbin + 2;
+    if (threadIdx.x < (unsigned)world) {
+        const volatile unsigned int* f = flags + threadIdx.x;
+        while ((int)(*f - epoch) < 0) __nanosleep(200);      // epochs only grow; wrap-safe comparison
+    }
+    __syncthreads();
+    __threadfence_system();
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= words) return;
+    unsigned long long acc = 0;
+    for (int p = 0; p < world; p++) acc += __ldcv(&slots[((uint64_t)parity * world + p) * words + b]);
+    xbuf[b] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Model update, one CTA. reference: fold of the counts EM.cpp:247-254, Motif::updateV Motif.h:95-136,
 // convergence term EM.cpp:102-107, Motif::calculateLinearS Motif.cpp:485-494. Every formula keeps the
 // reference's operation order (compiled with -fmad=false); only sum|dv| is a tree instead of a serial sum.

@@ -16,10 +16,13 @@ WORKLOADS = {
 }
 
 
-def planted_sequences(seed, nseq, L0, W, A=4, plant_frac=0.5, nsites=500):
-    """Returns (fwd codes [nseq, L0] uint8 in 1..A, sites [nsites, W] uint8 in 1..A, pwm [W, A])."""
+def planted_sequences(seed, nseq, L0, W, A=4, plant_frac=0.5, nsites=500, motif_seed=None):
+    """Returns (fwd codes [nseq, L0] uint8 in 1..A, sites [nsites, W] uint8 in 1..A, pwm [W, A]).
+    motif_seed: seed of the PWM and of the binding-site block (default: `seed`). Shards of ONE data set (multi-GPU runs)
+    share the motif_seed and differ in `seed`, which draws the background, the planted positions and strands."""
     rng = np.random.default_rng(seed)
-    pwm = rng.dirichlet(np.full(A, 0.3), size=W)
+    mrng = rng if motif_seed is None else np.random.default_rng(motif_seed)
+    pwm = mrng.dirichlet(np.full(A, 0.3), size=W)
     cdf = np.cumsum(pwm, axis=1)
     fwd = rng.integers(1, A + 1, size=(nseq, L0), dtype=np.uint8)
     nplant = int(nseq * plant_frac)
@@ -34,7 +37,7 @@ def planted_sequences(seed, nseq, L0, W, A=4, plant_frac=0.5, nsites=500):
     start = rng.integers(0, L0 - W + 1, size=nplant)
     cols = start[:, None] + np.arange(W)[None, :]
     fwd[rows[:, None], cols] = site + 1
-    us = rng.random((nsites, W))
+    us = (rng if motif_seed is None else mrng).random((nsites, W))
     sites = np.minimum((us[:, :, None] > cdf[None, :, :]).sum(axis=2), A - 1).astype(np.uint8) + 1
     return fwd, sites, pwm
 

@@ -127,9 +127,9 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_data(wl, nseq, seed, pinned=False):
+def make_data(wl, nseq, seed, pinned=False, motif_seed=None):
     """Returns dict(codes [nseq, L] uint8 (optionally pinned), offsets, patches, sites, fwd)."""
-    fwd, sites, _ = synth.planted_sequences(seed, nseq, wl["L0"], wl["W"])
+    fwd, sites, _ = synth.planted_sequences(seed, nseq, wl["L0"], wl["W"], motif_seed=motif_seed)
     L = 2 * wl["L0"] + 1
     out = None
     if pinned:
@@ -141,10 +141,13 @@ def make_data(wl, nseq, seed, pinned=False):
     return dict(codes=codes, offsets=offsets, ppos=ppos, pkmer=pkmer, sites=sites, fwd=fwd, L=L)
 
 
-def initial_model(capi, ss, wl, sites):
-    """Background model from device k-mer counts (BackgroundModel.cpp:26-42, 441-472) + binding-site init."""
+def initial_model(capi, ss, wl, sites, reduce_counts=None):
+    """Background model from device k-mer counts (BackgroundModel.cpp:26-42, 441-472) + binding-site init.
+    reduce_counts: sums the count vector over ranks, so that every shard starts from the same model."""
     A = 4
     n = ss.count_kmers(wl["K_bg"])
+    if reduce_counts is not None:
+        n = reduce_counts(n)
     vbg = hostmodel.background_from_counts(n, A, wl["K_bg"], hostmodel.default_bg_alpha(wl["K_bg"]))
     alpha = hostmodel.default_motif_alpha(wl["K"], wl["W"])
     v0 = hostmodel.motif_from_sites(sites, A, wl["K"], alpha, vbg)
@@ -246,23 +249,49 @@ def main():
 
     nseq = args.nseq or wl["nseq"]
     A = 4
-    data = make_data(wl, nseq, args.seed + 1000 * rank, pinned=True)
+    # every rank holds a shard of ONE data set: same planted motif and binding sites, its own sequences
+    data = make_data(wl, nseq, args.seed + 1000 * rank, pinned=True, motif_seed=args.seed if world > 1 else None)
     bp_local = nseq * wl["L0"]
     pos_local = nseq * data["L"]
     bp_total = bp_local * world
 
     # ---- resident run ---------------------------------------------------------------------------------------
     ss = capi.SeqSet(data["codes"].reshape(-1), data["offsets"], A, data["ppos"], data["pkmer"])
-    v0, vbg, alpha = initial_model(capi, ss, wl, data["sites"])
+    def sum_over_ranks(counts):
+        t = torch.from_numpy(counts.astype(np.int64)).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy().astype(np.uint64)
+
+    v0, vbg, alpha = initial_model(capi, ss, wl, data["sites"], sum_over_ranks if world > 1 else None)
     em = capi.EM(ss, wl["W"], wl["K"], wl["K_bg"])
     em.set_model(v0, vbg, alpha, Q)
     stream = torch.cuda.ExternalStream(em.stream(), device=torch.device("cuda", local_rank))
     xt = None
+    exchange = "none"
+
+    def attach_peers(e):
+        """NVLink peer exchange (fused into the M-step's reduction kernel); False if CUDA IPC is not available here."""
+        try:
+            mine = torch.frombuffer(bytearray(e.peer_alloc(rank, world)), dtype=torch.uint8).cuda()
+            allh = torch.empty(world * 64, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allh, mine)
+            e.peer_attach(allh.cpu().numpy().tobytes())
+            ok = torch.ones(1, device="cuda")
+        except Exception as ex:                       # noqa: BLE001 - any failure means: use the NCCL exchange
+            sys.stderr.write("rank %d: peer exchange unavailable (%s)\n" % (rank, ex))
+            ok = torch.zeros(1, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return bool(ok.item() > 0)
+
     if world > 1:
-        words = em.exchange_buffer()[1]
-        xt = torch.zeros(words, dtype=torch.int64, device="cuda")
-        em.set_exchange_buffer(xt.data_ptr(), words)
         em.set_global_nseq(nseq * world)
+        if os.environ.get("BAMM_EXCHANGE", "peer") == "peer" and attach_peers(em):
+            exchange = "nvlink-peer (fused into the M-step reduce kernel)"
+        else:
+            words = em.exchange_buffer()[1]
+            xt = torch.zeros(words, dtype=torch.int64, device="cuda")
+            em.set_exchange_buffer(xt.data_ptr(), words)
+            exchange = "nccl all-reduce (int64)"
 
     def run_iters(n):
         if world == 1:
@@ -272,7 +301,8 @@ def main():
             for _ in range(n):
                 em.estep_local()
                 em.mstep_local()
-                sharding.allreduce_exchange(xt)
+                if xt is not None:
+                    sharding.allreduce_exchange(xt)
                 em.finish_iteration(sync=False)
         stream.synchronize()
 
@@ -333,13 +363,18 @@ def main():
         em2.set_model(v0, vbg, alpha, Q)
         # every iteration ends with a device->host read of its result (log likelihood + sum|dv|), like EM::optimize's loop
         if world > 1:
-            em2.set_exchange_buffer(xt.data_ptr(), em2.exchange_buffer()[1])
             em2.set_global_nseq(nseq * world)
+            peer2 = xt is None and attach_peers(em2)
+            if not peer2:
+                if xt is None:
+                    xt = torch.zeros(em2.exchange_buffer()[1], dtype=torch.int64, device="cuda")
+                em2.set_exchange_buffer(xt.data_ptr(), em2.exchange_buffer()[1])
             st2 = torch.cuda.ExternalStream(em2.stream(), device=torch.device("cuda", local_rank))
             for _ in range(args.steps):
                 with torch.cuda.stream(st2):
                     em2.estep_local(); em2.mstep_local()
-                    sharding.allreduce_exchange(xt)
+                    if not peer2:
+                        sharding.allreduce_exchange(xt)
                 e2e_llh, e2e_vdiff = em2.finish_iteration(sync=True)
         else:
             for _ in range(args.steps):
@@ -380,7 +415,7 @@ def main():
                        "positions_per_gpu": pos_local, "positions_iter_per_s": pos_local * world * args.steps / (ms_total * 1e-3),
                        "l2": "inputs (%.1f GB index + r per GPU) exceed the 126 MB L2" % (6.0 * pos_local / 1e9) if 6.0 * pos_local > 2.0e8
                              else "inputs fit in L2; no flush between iterations (EM iterates over resident data)",
-                       "parallelism": "sequence shards, dp%d" % world},
+                       "parallelism": "sequence shards, dp%d" % world, "exchange": exchange},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         }
         if roof:

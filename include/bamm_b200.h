@@ -128,6 +128,16 @@ int bamm_em_estep_local(bamm_em* em);
 int bamm_em_mstep_local(bamm_em* em);
 /* With optimize_q == 0 and llh == vdiff == NULL the call only enqueues work (no host round trip). */
 int bamm_em_finish_iteration(bamm_em* em, int optimize_q, float* llh, float* vdiff);
+/*
+ * NVLink peer exchange: instead of an external all-reduce, the M-step's reduction kernel writes this rank's sums directly
+ * into every rank's receive buffer (CUDA-IPC mapped peer memory) and bamm_em_finish_iteration waits for all ranks on the
+ * device. Call bamm_em_peer_alloc on every rank, exchange the 64-byte handles (any transport), pass all of them
+ * (world x 64 bytes, rank order) to bamm_em_peer_attach; afterwards the iteration is
+ *   bamm_em_estep_local ; bamm_em_mstep_local ; bamm_em_finish_iteration      (no collective call in between)
+ * Every rank must run the same number of iterations. Up to 16 ranks on one NVLink domain.
+ */
+int bamm_em_peer_alloc(bamm_em* em, int rank, int world, void* ipc_handle_out /* 64 bytes */);
+int bamm_em_peer_attach(bamm_em* em, const void* ipc_handles /* world * 64 bytes */);
 /* CUDA stream (cudaStream_t as void*) the EM object launches on, so callers can order collectives after it */
 int bamm_em_stream(bamm_em* em, void** stream);
 
