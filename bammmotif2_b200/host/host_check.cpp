@@ -78,6 +78,22 @@ int main( int argc, char** argv ){
         if( reread.getOrder() != Kbg ) return 4;
         return 0;
     }
+    if( mode == "pwminit" ){
+        // host_check pwminit ALPHABET FASTA SS K KBG COUNTS.u64 ALPHA_BG.f32 MEME MAXPWM Q OUTDIR -> v_init_<m>.f32
+        Alphabet::init( argv[2] );
+        SequenceSet pos( argv[3], atoi( argv[4] ) != 0 );
+        const size_t K = atoi( argv[5] ), Kbg = atoi( argv[6] );
+        BackgroundModel bg( slurp<uint64_t>( argv[7] ), Kbg, slurp<float>( argv[8] ), true, "check" );
+        std::vector<float> alpha( K + 1, 1.f );
+        for( size_t k = 1; k <= K; k++ ) alpha[k] = 7.0f * powf( 3.0f, ( float )k );
+        MotifSet ms( argv[9], 0, 0, "PWM", &pos, bg.getV(), Kbg, K, alpha, atoi( argv[10] ), atof( argv[11] ) );
+        const std::string out = argv[12];
+        for( size_t m = 0; m < ms.getN(); m++ ){
+            Motif* mo = ms.getMotifs()[m];
+            dump( out + "/v_init_" + std::to_string( m + 1 ) + ".f32", mo->flatV().data(), mo->flatV().size() );
+        }
+        return 0;
+    }
     if( mode == "neg" ){
         Alphabet::init( argv[2] );
         SequenceSet pos( argv[3], atoi( argv[4] ) != 0 );

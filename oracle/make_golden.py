@@ -66,14 +66,14 @@ def write_inputs(tmp, seqs, sites):
     return fa, bs
 
 
-def run_case(name, fasta, sitefile, args, r_iters="1", max_iter=None, dump_neg=False, keep=None, extra_inputs=None):
+def run_case(name, fasta, sitefile, args, r_iters="1", max_iter=None, dump_neg=False, keep=None, extra_inputs=None, init=("--bindingSiteFile",)):
     tmp = tempfile.mkdtemp(prefix="golden_")
     env = dict(os.environ, BAMM_DUMP_R_ITERS=r_iters, OMP_NUM_THREADS="1")
     if max_iter:
         env["BAMM_DUMP_MAXITER"] = str(max_iter)
     if dump_neg:
         env["BAMM_DUMP_NEG"] = "1"
-    cmd = [os.path.join(HERE, "_ref", "ref_dump"), tmp, fasta, "--bindingSiteFile", sitefile] + args + ["--threads", "1"]
+    cmd = [os.path.join(HERE, "_ref", "ref_dump"), tmp, fasta, init[0], sitefile] + args + ["--threads", "1"]
     subprocess.check_call(cmd, env=env, stdout=subprocess.DEVNULL)
     d = os.path.join(tmp, "dump")
     arrays = {}
@@ -112,8 +112,19 @@ def run_case(name, fasta, sitefile, args, r_iters="1", max_iter=None, dump_neg=F
     print("%-14s iterations=%s  %d arrays  %.1f KB" % (name, iters, len(arrays), os.path.getsize(path) / 1024))
 
 
+def pwm_case():
+    """Multi-motif initialisation from a MEME file (Motif::initFromPWM samples one site per sequence with a default-seeded
+    std::mt19937; 1 thread makes it deterministic): the reference's shipped PWMs on its shipped sequences."""
+    keep = lambda k: (k.startswith("m") and any(t in k for t in ("_v_init", "_alpha", "_llh", "_vdiff", "_v_final", "_q"))
+                      and "_it" not in k) or k.startswith("bg_")
+    run_case("jund_pwm_k1", os.path.join(REF, "example", "JunD.fasta"), os.path.join(REF, "example", "PWM_peng10.meme"),
+             ["--EM", "-k", "1", "-K", "1", "--maxPWM", "2"], r_iters="", keep=keep, init=("--PWMFile",))
+
+
 def main():
     subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    if "--only-pwm" in sys.argv:
+        return pwm_case()
     # config 1: the reference's shipped example
     run_case("jund_k2", os.path.join(REF, "example", "JunD.fasta"), os.path.join(REF, "example", "bindingsites.block"),
              ["--EM", "-k", "2", "-K", "2", "--FDR"], r_iters="1,41",
@@ -135,6 +146,7 @@ def main():
         fa, bs = write_inputs(d, seqs, sites)
         run_case(name, fa, bs, args, r_iters=r_iters, dump_neg=dump_neg)
     shutil.rmtree(tmp)
+    pwm_case()
 
 
 if __name__ == "__main__":

@@ -286,3 +286,60 @@ def test_properties_at_scale(capi):
     sums = vK.reshape(A ** K, A, W).sum(axis=1)                       # over the newest base, per context and column
     # (approximately: the denominator n[K-1][context][j-1] counts windows by their previous column, Motif.h:130-133)
     assert np.all(np.abs(sums[:, K:] - 1.0) < 2e-2)
+
+
+@pytest.mark.parametrize("A,K,W,packed", [(6, 5, 6, False), (6, 3, 8, False), (4, 6, 8, True), (4, 5, 24, True)])
+def test_large_tables_against_oracle(capi, oracle, A, K, W, packed):
+    """Orders / alphabets beyond the fixtures: the 6-letter alphabet at order 5 (46 656-row table, 1.1 MB: stays in L2,
+    counts through global atomics), order 6 on ACGT (16 384 rows), and a wide order-5 motif whose table forces one
+    column per group — two full iterations against the CPU oracle on seeded random sequences (both strands, with the
+    rand()-patched middle N)."""
+    rng = np.random.default_rng(7 + A * 100 + K)
+    nseq, L0 = 300, 90
+    fwd = rng.integers(1, A + 1, size=(nseq, L0), dtype=np.uint8)
+    comp = np.array([0, 4, 3, 2, 1, 3, 3], np.uint8)               # ACGTMH -> TGCAGG (Alphabet.cpp:12-27)
+    L = 2 * L0 + 1
+    codes = np.zeros((nseq, L), np.uint8)
+    codes[:, :L0] = fwd
+    codes[:, L0 + 1:] = comp[fwd][:, ::-1]
+    # reference-style k-mer hashes with an independent draw per (position, digit) for the N
+    kmer = np.zeros((nseq, L), np.uint64)
+    d = np.where(codes == 0, 0, codes.astype(np.int64) - 1)
+    for t in range(11):
+        dig = d[:, :L - t].copy()
+        col = np.arange(t, L) - t                                   # position of the digit's base
+        isN = (col == L0)
+        if isN.any():
+            dig[:, isN] = rng.integers(0, A, size=(nseq, int(isN.sum())))
+        kmer[:, t:] += (dig * (A ** t)).astype(np.uint64)
+    kmer = kmer.ravel()
+    offsets = np.arange(nseq + 1, dtype=np.uint64) * np.uint64(L)
+    pp, pk = capi.kmer_patches(codes.ravel(), kmer)
+    ss = capi.SeqSet(codes.ravel(), offsets, A, pp, pk)
+    Kbg = min(K, 2)
+    from bammmotif2_b200 import hostmodel
+    assert np.array_equal(ss.get_index(K).astype(np.uint64), kmer % np.uint64(A ** (K + 1)))
+    nb, vbg = oracle.bg_model(kmer, A, Kbg, hostmodel.default_bg_alpha(Kbg))
+    assert np.array_equal(ss.count_kmers(Kbg), nb)
+    alpha = hostmodel.default_motif_alpha(K, W)
+    sites = rng.integers(1, A + 1, size=(200, W), dtype=np.uint8)
+    v0 = oracle.motif_from_sites(["".join("ACGTMH"[c - 1] for c in s) for s in sites], A, K, alpha.ravel(), vbg) \
+        if False else hostmodel.motif_from_sites(sites, A, K, alpha, vbg)
+    em = capi.EM(ss, W, K, Kbg)
+    em.set_model(v0, vbg, alpha, 0.3)
+    v = v0.copy()
+    for it in range(2):
+        s = oracle.linear_s(v, vbg, A, K, Kbg, W)
+        r_ref, llh_ref = oracle.estep(kmer, offsets, A, K, W, s, 0.3)
+        n_ref = oracle.mstep(kmer, offsets, A, K, W, r_ref)
+        v = oracle.update_v(n_ref, alpha.ravel(), vbg, A, K, W, v)
+        llh = em.estep()
+        assert abs(llh - llh_ref) <= RTOL * abs(llh_ref)
+        assert_rel(em.r(), r_ref, RTOL, atol=1e-37, what="r it%d" % it)
+        em.mstep()
+        assert_rel(em.counts(), n_ref, RTOL, atol=1e-9, what="n it%d" % it)
+        assert_rel(em.model(), v, RTOL, what="v it%d" % it)
+    # scoring on the same path
+    mops, zoops, z = ss.score(W, K, Kbg, v, vbg)
+    omops, ozoops, oz = oracle.logodds(kmer, offsets, A, K, W, oracle.log_s(v, vbg, A, K, Kbg, W))
+    assert np.array_equal(mops, omops) and np.array_equal(zoops, ozoops) and np.array_equal(z, oz)

@@ -63,6 +63,22 @@ def test_background_and_site_init_bit_exact(bins, case, tmp_path):
     assert open(tmp_path / "check.hbp", "rb").read() == bytes(g[hb[:-4] + "hbp"])
 
 
+def test_pwm_initialisation_bit_exact(bins, tmp_path):
+    """MotifSet("PWM") + Motif::initFromPWM: MEME parsing, posterior site sampling with std::mt19937 /
+    std::discrete_distribution, higher-order counts — two motifs of the reference's shipped PWM file."""
+    g = Golden("jund_pwm_k1")
+    fa = tmp_path / "JunD.fasta"
+    open(fa, "wb").write(bytes(Golden("jund_k2")["fasta_text"]))
+    meme = tmp_path / "pwm.meme"
+    open(meme, "wb").write(bytes(g["sites_text"]))
+    g["bg_n"].tofile(tmp_path / "bgn.u64")
+    g.bg_alpha().tofile(tmp_path / "abg.f32")
+    run([os.path.join(bins, "host_check"), "pwminit", "STANDARD", str(fa), "0", str(g.K), str(g.K_bg_model),
+         str(tmp_path / "bgn.u64"), str(tmp_path / "abg.f32"), str(meme), "2", repr(float(g.q)), str(tmp_path)])
+    for m in (1, 2):
+        assert np.array_equal(np.fromfile(tmp_path / ("v_init_%d.f32" % m), np.float32), g["m%d_v_init" % m]), m
+
+
 def test_negative_sampling_bit_exact(bins, tmp_path):
     g = Golden("syn_k3_fdr")
     fa, _ = write_inputs(g, str(tmp_path))
@@ -135,6 +151,26 @@ def test_cli_matches_reference_files(bins, case, tmp_path):
         assert np.mean(np.abs(body[:, 0] - rbody[:, 0]) > 0) < 0.02
         assert np.max(np.abs(body[:, 0] - rbody[:, 0])) <= 3
         assert abs(float(head[6]) - float(rhead[6])) <= 0.02
+
+
+@pytest.mark.gpu
+def test_cli_pwm_file_two_motifs(bins, tmp_path):
+    """--PWMFile --maxPWM 2: both motifs of the reference's run, iteration counts and written models."""
+    g = Golden("jund_pwm_k1")
+    fa = tmp_path / "JunD.fasta"
+    open(fa, "wb").write(bytes(Golden("jund_k2")["fasta_text"]))
+    meme = tmp_path / "pwm.meme"
+    open(meme, "wb").write(bytes(g["sites_text"]))
+    out = tmp_path / "out"
+    p = run([os.path.join(bins, "BaMMmotif"), str(out), str(fa), "--PWMFile", str(meme)] + g.args + ["--verbose"])
+    iters = [l for l in p.stdout.split("\n") if " iter, llh=" in l]
+    want = [g.meta["iterations"]] if "iterations" in g.meta else None
+    assert open(out / "JunD.hbcp", "rb").read() == bytes(g["file_JunD_hbcp"])
+    for m in (1, 2):
+        ours = parse_numbers(open(out / ("JunD_motif_%d.ihbcp" % m), "rb").read())
+        ref = parse_numbers(bytes(g["file_JunD_motif_%d_ihbcp" % m]))
+        assert ours.shape == ref.shape and np.all(np.abs(ours - ref) <= 1.2e-3 * np.abs(ref) + 1e-30), m
+    assert len(iters) == len(g["m1_llh"]) + len(g["m2_llh"])
 
 
 @pytest.mark.gpu
