@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--nseq", type=int, default=0, help="override sequences per GPU (debug)")
+    ap.add_argument("--K", type=int, default=-1, help="override the motif order (sweeps; the workload name gains a suffix)")
+    ap.add_argument("--W", type=int, default=0, help="override the motif width (sweeps)")
+    ap.add_argument("--L0", type=int, default=0, help="override the sequence length (sweeps)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -227,6 +230,11 @@ def main():
     args = parse_args()
     wl = dict(synth.WORKLOADS[args.workload], name=args.workload)
     wl["cpu_sample"] = {"c3": 40_000, "c2": 50_000, "tiny": 2_000}[args.workload]
+    if args.K >= 0 or args.W or args.L0:              # sweep variants are labelled as such: not a BASELINE.json config
+        if args.K >= 0: wl["K"] = args.K; wl["K_bg"] = min(wl["K_bg"], args.K)
+        if args.W: wl["W"] = args.W
+        if args.L0: wl["L0"] = args.L0
+        wl["desc"] += " [sweep variant: L0=%d W=%d K=%d]" % (wl["L0"], wl["W"], wl["K"])
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
