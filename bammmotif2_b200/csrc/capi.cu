@@ -95,13 +95,13 @@ struct bamm_em {
     PeerPtrs peer_ptrs;
     uint32_t peer_epoch = 0;
     unsigned int* d_peer_done = nullptr;
-    bool list_w = false;        // width-specialised list kernel usable (two count tables fit shared memory)
-    int grid_pl = 0;
+    int m_nc = 0, m_nsplit = 1; // packed M-step: columns per CTA and number of column splits (packed.cuh, "column split")
+    int grid_pl = 0;            // CTAs of the packed M-step kernels (a multiple of m_nsplit)
     uint32_t *d_act_cnt = nullptr, *d_overflow = nullptr;
     uint64_t* d_reg_off = nullptr;
     uint16_t* d_ypatch = nullptr;   // owned by the seqset
-    int grid_pe = 0, block_pe = 1024, grid_pm = 0;
-    size_t smem_pe = 0, smem_pm = 0;
+    int grid_pe = 0, block_pe = 1024;
+    size_t smem_pe = 0;
     uint32_t nparts = 1;
     // device
     uint32_t* d_seq_ids = nullptr;
@@ -386,7 +386,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
 }
 
 static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only);
-static int mstep_list_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only);
+static int mstep_w_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, int mode);
 
 template <typename K> static int max_smem_optin(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : -1;
@@ -483,9 +483,9 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     const int sms = s->sm_count;
     const size_t table_bytes = (size_t)em->nbin * sizeof(float);
     // ---- packed path: possible when the column-group tables and the M-step's count table fit shared memory
-    const size_t queue_bytes = (size_t)(512 / 32) * QCAP * sizeof(QEntry);
+    // (the M-step needs two 32-bit count tables of at least one column: 4^(K+1) * 8 bytes)
     bool packed_ok = s->A == 4 && s->nregular > 0 && W + K <= 31 && Yn64 <= 65536 &&
-                     ((table_bytes + 15) & ~(size_t)15) + queue_bytes <= (size_t)max_optin && !getenv("BAMM_NO_PACKED");
+                     Yn64 * 8 <= (uint64_t)max_optin && !getenv("BAMM_NO_PACKED");
     em->tab_capacity = (size_t)max_optin;
     if (getenv("BAMM_TABLE_BYTES")) em->tab_capacity = std::min(em->tab_capacity, (size_t)atol(getenv("BAMM_TABLE_BYTES")));
     if (packed_ok) {
@@ -574,14 +574,21 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         CUE(cudaMalloc(&em->d_scale, (size_t)em->npk * sizeof(float)));
         em->block_pe = BAMM_E_THREADS;              // one CTA per SM: the group tables fill its shared memory
         em->grid_pe = sms;
-        em->smem_pm = ((table_bytes + 15) & ~(size_t)15) + queue_bytes;
-        bool ok = !max_smem_optin(k_mstep_packed, em->smem_pm) && !max_smem_optin(k_mstep_list, table_bytes);
-        if (!ok) { fail(BAMM_E_CUDA, "cannot opt in to shared memory for the packed kernels"); bamm_em_destroy(em); return BAMM_E_CUDA; }
-        int per_sm_m = (int)((size_t)(max_optin + 1024) / (em->smem_pm + 1024));
-        if (per_sm_m < 1) per_sm_m = 1;
-        if (per_sm_m > 4) per_sm_m = 4;
-        em->grid_pm = sms * per_sm_m;
-        if ((uint32_t)em->grid_pm > em->nparts) em->nparts = (uint32_t)em->grid_pm;
+        // M-step geometry: as many columns per CTA as two 32-bit tables allow, the fewest splits, columns spread evenly
+        {
+            int nc_max = (int)((size_t)max_optin / ((size_t)em->Yn * 8));
+            if (getenv("BAMM_M_COLS")) nc_max = std::max(1, std::min(nc_max, atoi(getenv("BAMM_M_COLS"))));
+            if (nc_max > W) nc_max = W;
+            em->m_nsplit = (W + nc_max - 1) / nc_max;
+            em->m_nc = (W + em->m_nsplit - 1) / em->m_nsplit;
+            em->grid_pl = std::max(1, sms / em->m_nsplit) * em->m_nsplit;
+            // the high table sums at most 257 per sequence and bin (the posteriors of a sequence sum to <= 1)
+            if ((uint64_t)em->npk / (uint64_t)(em->grid_pl / em->m_nsplit) >= (1ull << 23)) {
+                fail(BAMM_E_INVALID, "too many sequences for one device"); bamm_em_destroy(em); return BAMM_E_INVALID;
+            }
+            if (mstep_w_dispatch(em, nullptr, nullptr, 0)) { fail(BAMM_E_CUDA, "cannot opt in to shared memory for the packed M-step"); bamm_em_destroy(em); return BAMM_E_CUDA; }
+            if ((uint32_t)em->grid_pl > em->nparts) em->nparts = (uint32_t)em->grid_pl;
+        }
         // active list: one region per E-step warp, sized as a fraction of the warp's windows (BAMM_LIST_FRAC, 0 = off)
         const double frac = getenv("BAMM_LIST_FRAC") ? atof(getenv("BAMM_LIST_FRAC")) : 0.5;
         if (frac > 0.0) {
@@ -599,15 +606,10 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             const uint64_t total = reg[em->nregions] ? reg[em->nregions] : 1;
             CUE(upload(reg.data(), reg.size() * 8, (void**)&em->d_reg_off));
             CUE(cudaMalloc(&em->d_act, total * sizeof(ActiveEntry)));
-            CUE(cudaMalloc(&em->d_act_cnt, (uint64_t)em->nregions * 4));
-            CUE(cudaMemset(em->d_act_cnt, 0, (uint64_t)em->nregions * 4));
+            CUE(cudaMalloc(&em->d_act_cnt, (uint64_t)em->nregions * 8));         // front counts, then back counts
+            CUE(cudaMemset(em->d_act_cnt, 0, (uint64_t)em->nregions * 8));
             CUE(cudaMalloc(&em->d_overflow, 4));
             CUE(cudaMemset(em->d_overflow, 0, 4));
-            // two 32-bit count tables per CTA; the high table sums at most 256 per listed window, far below 2^32 per CTA
-            em->grid_pl = sms;
-            em->list_w = (size_t)em->nbin * 8 <= (size_t)max_optin && total / (uint64_t)sms < (1ull << 23) && !getenv("BAMM_NO_LISTW") &&
-                         mstep_list_dispatch(em, nullptr, nullptr, true) == 0;
-            if (em->list_w && (uint32_t)em->grid_pl > em->nparts) em->nparts = (uint32_t)em->grid_pl;
         }
     }
     CUE(cudaMalloc(&em->d_part, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long)));
@@ -663,7 +665,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
 // optin_only sets the shared-memory attribute instead of launching.
 static ActiveList alist_of(const bamm_em* em) {
     ActiveList al; al.ent = em->d_act; al.scale = em->d_scale; al.reg_off = em->d_reg_off;
-    al.cnt = em->d_act_cnt; al.overflow = em->d_overflow;
+    al.cnt = em->d_act_cnt; al.cnt_back = em->d_act_cnt ? em->d_act_cnt + em->nregions : nullptr; al.overflow = em->d_overflow;
     return al;
 }
 template <int G, bool FAST> static int estep_packed_one(bamm_em* em, const PackedView* pv, bool optin_only) {
@@ -718,16 +720,19 @@ static int launch_estep(bamm_em* em) {
     return BAMM_OK;
 }
 
-// width-specialised list M-step: one instantiation per motif width
-template <int WT> static int mstep_list_one(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only) {
-    const size_t smem = (size_t)em->nbin * 8;
-    if (optin_only) return max_smem_optin(k_mstep_list_w<WT>, smem);
-    k_mstep_list_w<WT><<<em->grid_pl, 1024, smem, em->stream>>>(*pv, *pl, alist_of(em), em->nregions, em->d_part);
+// packed M-step kernels: one instantiation per column count of a CTA. mode 0: opt in to the shared memory of both kernels,
+// 1: launch the list kernel, 2: launch the scan kernel (conditional on the list's overflow flag when there is a list)
+template <int NC> static int mstep_w_one(bamm_em* em, const PackedView* pv, const Plan* pl, int mode) {
+    const size_t smem = (size_t)NC * em->Yn * 8;
+    if (mode == 0) return max_smem_optin(k_mstep_list_w<NC>, smem) | max_smem_optin(k_mstep_scan_w<NC>, smem);
+    if (mode == 1) k_mstep_list_w<NC><<<em->grid_pl, 1024, smem, em->stream>>>(*pv, *pl, alist_of(em), em->nregions, em->m_nsplit, em->d_part);
+    else k_mstep_scan_w<NC><<<em->grid_pl, 1024, smem, em->stream>>>(*pv, *pl, em->d_r, em->r_scaled ? nullptr : em->d_scale,
+                                                                    em->d_act ? em->d_overflow : nullptr, em->m_nsplit, em->d_part);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
-static int mstep_list_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only) {
-    switch (em->W) {
-#define BAMM_CASE(w) case w: return mstep_list_one<w>(em, pv, pl, optin_only);
+static int mstep_w_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, int mode) {
+    switch (em->m_nc) {
+#define BAMM_CASE(w) case w: return mstep_w_one<w>(em, pv, pl, mode);
         BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
         BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
         BAMM_CASE(17) BAMM_CASE(18) BAMM_CASE(19) BAMM_CASE(20) BAMM_CASE(21) BAMM_CASE(22) BAMM_CASE(23) BAMM_CASE(24)
@@ -744,22 +749,18 @@ static int launch_mstep_accumulate(bamm_em* em) {
         PackedView pv = pview_of(em);
         Plan pl = em->plan; pl.q = em->q;
         if (em->d_act && getenv("BAMM_DEBUG_LIST")) {
-            std::vector<uint32_t> c(em->nregions); uint32_t ov = 0;
+            std::vector<uint32_t> c(2 * (size_t)em->nregions); uint32_t ov = 0;
             cudaStreamSynchronize(em->stream);
-            cudaMemcpy(c.data(), em->d_act_cnt, (size_t)em->nregions * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(c.data(), em->d_act_cnt, (size_t)em->nregions * 8, cudaMemcpyDeviceToHost);
             cudaMemcpy(&ov, em->d_overflow, 4, cudaMemcpyDeviceToHost);
             uint64_t tot = 0, mx = 0; for (uint32_t x : c) { tot += x; if (x > mx) mx = x; }
             fprintf(stderr, "[bamm] active list: %llu entries (%.4f of r), max region %llu, overflow %u, G=%d fast=%d delta=%d table %u B\n",
                     (unsigned long long)tot, (double)tot / (double)em->rsize, (unsigned long long)mx, ov, em->gplan.G, (int)em->gfast, em->gplan.delta, em->gplan.table_bytes);
         }
-        if (em->d_act) {
-            // the E-step listed the windows that matter; the scan kernel only runs (device-side decision) if a region overflowed
-            if (em->list_w) { if (mstep_list_dispatch(em, &pv, &pl, false)) return fail(BAMM_E_CUDA, "list M-step launch failed"); }
-            else k_mstep_list<<<em->grid_pm, 512, (size_t)em->nbin * 4, em->stream>>>(pv, pl, alist_of(em), em->nregions, em->d_part);
-            CU(cudaGetLastError());
-        }
-        k_mstep_packed<<<em->grid_pm, 512, em->smem_pm, em->stream>>>(pv, pl, em->d_r, em->d_part, em->d_overflow, em->r_scaled ? nullptr : em->d_scale);
-        CU(cudaGetLastError());
+        // the E-step listed the windows that matter; the scan kernel only does work (device-side decision) if a region
+        // overflowed, or when there is no list
+        if (em->d_act && mstep_w_dispatch(em, &pv, &pl, 1)) return fail(BAMM_E_CUDA, "list M-step launch failed");
+        if (mstep_w_dispatch(em, &pv, &pl, 2)) return fail(BAMM_E_CUDA, "scan M-step launch failed");
     }
     if (em->ngen) {
         IndexArray& ia = em->ss->index[em->K];

@@ -199,7 +199,8 @@ struct ActiveList {
     ActiveEntry* ent;         // entries (li = index into the packed list of the EM object, p = window start, rv = UNNORMALISED posterior)
     float* scale;             // [nlist] 1/normaliser of every list sequence: posterior = rv * scale[li]
     const uint64_t* reg_off;  // [nregions+1] first entry of every region
-    uint32_t* cnt;            // [nregions] entries written
+    uint32_t* cnt;            // [nregions] entries written at the front of the region (full windows of the fast chunks)
+    uint32_t* cnt_back;       // [nregions] entries written at the back, downwards (windows of the masked chunks)
     uint32_t* overflow;       // set when a region was too small: the M-step then scans r instead
 };
 constexpr float FX_HALF_UNIT = 4.547473508864641e-13f;   // 2^-41: smallest r that rounds to a non-zero count
@@ -265,7 +266,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
     bool emit = al.ent != nullptr;
     ActiveEntry* __restrict__ lreg = emit ? al.ent + al.reg_off[warp] : nullptr;      // this warp's region
     const uint32_t lcap = emit ? (uint32_t)(al.reg_off[warp + 1] - al.reg_off[warp]) : 0u;
-    uint32_t lpos = 0;                                      // entries written so far
+    uint32_t lpos = 0, bpos = 0;                            // entries written so far at the front / at the back (downwards)
     for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
         const uint32_t n = pv.seq_ids[li];
         const PackedSeq sq = pv.seqs[n];
@@ -312,7 +313,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                         const uint32_t m = __ballot_sync(FULL, act);
                         if (m) {
                             const uint32_t cnt = __popc(m);
-                            if (lpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
+                            if (lpos + bpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
                             else {
                                 if (act) *reinterpret_cast<uint4*>(lreg + lpos + __popc(m & lt_mask)) = make_uint4(li, (uint32_t)((c << 5) + lane), __float_as_uint(val), 0u);
                                 lpos += cnt;
@@ -397,10 +398,10 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                         const uint32_t m = __ballot_sync(FULL, act);
                         if (m) {
                             const uint32_t cnt = __popc(m);
-                            if (lpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
-                            else {
-                                if (act) *reinterpret_cast<uint4*>(lreg + lpos + __popc(m & lt_mask)) = make_uint4(li, (uint32_t)p, __float_as_uint(val), 0u);
-                                lpos += cnt;
+                            if (lpos + bpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
+                            else {                              // windows of the masked chunks go to the back of the region
+                                bpos += cnt;
+                                if (act) *reinterpret_cast<uint4*>(lreg + (lcap - bpos) + __popc(m & lt_mask)) = make_uint4(li, (uint32_t)p, __float_as_uint(val), 0u);
                             }
                         }
                     }
@@ -422,7 +423,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
         if (llh_fx) atomicAdd(&scal[0], (unsigned long long)llh_fx);
         if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);
     }
-    if (al.ent != nullptr) al.cnt[warp] = lpos;             // every lane holds the same count
+    if (al.ent != nullptr) { al.cnt[warp] = lpos; al.cnt_back[warp] = bpos; }   // every lane holds the same counts
 }
 
 // r <- r * scale for every packed-list sequence: run before r leaves the device (bamm_em_get_r). One warp per sequence.
@@ -440,271 +441,250 @@ __global__ void k_normalise_r(PackedView pv, int W, const float* __restrict__ sc
 
 // ---- M-step --------------------------------------------------------------------------------------------------------
 // reference: EM::MStep accumulation, src/refinement/EM.cpp:230-243 (gather form).
-// Pass 1 per warp and sequence: stream r in batches of 256 windows (8 per lane; the next batch's loads are issued
-// before the current one is examined), keep the windows whose r is at least half a fixed-point unit (everything
-// below rounds to exactly 0 and contributes nothing) and compact them with a warp scan into the warp's ring queue.
-// Pass 2 whenever 32 entries are queued (and once more at the end of the sequence): each lane scatters one
-// window's value into the W bins it touches with native 32-bit shared atomics. Low-word wrap-arounds are collected
-// in a bit mask and carried into the CTA's 64-bit partial table after the loop, so the scatter loop is branch-free.
-struct QEntry { uint32_t p; float rv; };
-constexpr int QCAP = 256;                      // ring entries per warp (>= 31 + 128)
-constexpr int M_UNROLL = 8;                    // chunks of 32 windows in flight per lane
-constexpr int M_GROUP = 4;                     // chunks compacted per warp scan
+// Every posterior is converted to 2^-40 fixed point; a window whose posterior rounds to 0 contributes exactly nothing.
+// Each lane scatters one window's value into the bins (j, y(p+j)) it touches with native 32-bit shared atomics on two
+// CTA-private tables: the low 32 bits of the sums, and a second table that collects the high parts (r >= 2^-8) and the
+// wrap-arounds of the low words — no global atomics while scattering, integer sums only, so the counts are
+// bit-reproducible for any grid, schedule, kernel variant or GPU count.
+//
+// Column split: a CTA owns NC consecutive motif columns [j0, j0+NC), j0 = (blockIdx.x % nsplit) * NC, so that its two
+// tables (NC * 4^(K+1) * 8 bytes) fit shared memory for every order the packed stream supports; the CTAs of one split
+// together walk all windows. nsplit = 1, NC = W whenever the whole table fits (K <= 4 at W = 20).
+//
+// Two sources of windows: the E-step's active list (sparse posteriors: full lanes, no scan of r) and a scan of r
+// (dense posteriors, list switched off or overflowed).
 struct SeqCtx { const uint32_t* wd; const uint16_t* yp; int L, mid; };
 
-__device__ __forceinline__ void scatter_window(const SeqCtx& sc, const Plan& pl, uint32_t* __restrict__ lo_sh,
-                                               unsigned long long* __restrict__ mypart, int p, float rv) {
-    const int W = pl.W, K = pl.K;
-    const unsigned long long X = __float2ull_rn(rv * FX_SCALE_F);
+// Shared atomics cannot be predicated on sm_100a (ptxas wraps every guarded ATOMS in a BSSY / BRA / BSYNC region), so
+// the scatter of a full window is written without guards: the low-word atomic of every column is unconditional — lanes
+// without a value add 0, which changes nothing — and only the rare add to the high table (r >= 2^-8, or a wrap-around of
+// the low word detected from the returned old value) sits behind a branch.
+__device__ __forceinline__ uint32_t atoms_add_ret(uint32_t addr, uint32_t x) {
+    uint32_t o;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(addr), "r"(x) : "memory");
+    return o;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, uint32_t h) {
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(h) : "memory");
+}
+// guarded single step for the slow paths (windows over the N, truncated windows)
+__device__ __forceinline__ void atoms_add_carry(uint32_t addr, uint32_t hioff, uint32_t xlo, uint32_t xhi) {
+    const uint32_t old = atoms_add_ret(addr, xlo);
+    const uint32_t h = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
+    if (h) reds_add(addr + hioff, h);
+}
+
+// the NC columns of one window, fully unrolled: `up` holds the window's bases right-aligned so that column j0+jj's k-mer
+// is the bit field at 2(NC-1-jj). MASKED = false: every column exists (full window, full split) — no per-column test at all.
+// MASKED = true: columns jj > jrel_max add 0 (truncated tail windows, EM.cpp:236; columns past W in the last split).
+// Batches of M_BATCH columns: first the low-word atomics of the batch, then the carries / high parts from the returned
+// values, so several atomics of a lane are in flight.
+constexpr int M_BATCH = 8;
+template <int NC, bool MASKED>
+__device__ __forceinline__ void scatter_cols(unsigned long long up, uint32_t maskK, uint32_t lo_s, uint32_t hi_off, uint32_t yn4,
+                                             uint32_t xlo, uint32_t xhi, int jrel_max) {
+    const uint32_t ulo = (uint32_t)up, uhi = (uint32_t)(up >> 32);
+    const bool hi_nz = xhi != 0u;
+#pragma unroll
+    for (int g0 = 0; g0 < NC; g0 += M_BATCH) {
+        uint32_t adr[M_BATCH], old[M_BATCH];
+#pragma unroll
+        for (int k = 0; k < M_BATCH; k++) {
+            const int jj = g0 + k;
+            if (jj < NC) {
+                const int sh = 2 * (NC - 1 - jj);
+                const uint32_t y = (sh >= 32 ? (uhi >> (sh - 32)) : __funnelshift_r(ulo, uhi, sh)) & maskK;
+                adr[k] = lo_s + (uint32_t)jj * yn4 + (y << 2);
+                old[k] = atoms_add_ret(adr[k], (!MASKED || jj <= jrel_max) ? xlo : 0u);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < M_BATCH; k++) {
+            const int jj = g0 + k;
+            if (jj < NC) {
+                const bool on = !MASKED || jj <= jrel_max;
+                const bool carry = on && (uint32_t)~old[k] < xlo;          // old + xlo wrapped
+                if (carry || (on && hi_nz)) reds_add(adr[k] + hi_off, xhi + (carry ? 1u : 0u));
+            }
+        }
+    }
+}
+
+// slow path, one window per lane with a run-time column loop: windows over the N, whose k-mers at positions mid..mid+K
+// hold rand() draws (Sequence.cpp:38) and come from the patch list, and the truncated last W-1 windows (EM.cpp:236)
+__device__ __forceinline__ void scatter_window_slow(const SeqCtx& sc, const Plan& pl, uint32_t lo_s, uint32_t hi_off, int j0, int nc,
+                                                    int p, unsigned long long X) {
     if (X == 0) return;
-    const int L = sc.L, mid = sc.mid;
+    const int W = pl.W, K = pl.K;
     const unsigned long long w = window_word(sc.wd, p - K);      // bases p-K .. p-K+31
     const uint32_t maskK = pl.Yn - 1;
-    const int jmax = min(W - 1, L - W - p);
-    const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
+    const int jmax = min(min(W - 1, sc.L - W - p), j0 + nc - 1);
     const uint32_t xlo = (uint32_t)X, xhi = (uint32_t)(X >> 32);
-    int sh = 62 - 2 * K;
-    uint32_t jb = 0;
-    uint32_t carry = 0;                        // bit j: the low word of bin (j, y_j) wrapped
-    if (!over_n) {
-        for (int j = 0; j <= jmax; j++) {
-            const uint32_t old = atomicAdd(&lo_sh[jb + field(w, sh, maskK)], xlo);
-            carry |= ((uint32_t)(old + xlo) < old ? 1u : 0u) << j;
-            sh -= 2; jb += pl.Yn;
-        }
-    } else {
-        for (int j = 0; j <= jmax; j++) {
-            uint32_t y = field(w, sh, maskK);
-            const int d = p + j - mid;
-            if (d >= 0 && d <= K) y = sc.yp[d];
-            const uint32_t old = atomicAdd(&lo_sh[jb + y], xlo);
-            carry |= ((uint32_t)(old + xlo) < old ? 1u : 0u) << j;
-            sh -= 2; jb += pl.Yn;
-        }
-    }
-    // high words: large r (xhi != 0) touches every bin, otherwise only the bins whose low word wrapped
-    uint32_t todo = xhi ? (jmax >= 31 ? 0xffffffffu : ((2u << jmax) - 1u)) : carry;
-    while (todo) {
-        const int j = __ffs(todo) - 1;
-        todo &= todo - 1u;
+    for (int j = j0; j <= jmax; j++) {
         uint32_t y = field(w, 62 - 2 * K - 2 * j, maskK);
-        const int d = p + j - mid;
-        if (over_n && d >= 0 && d <= K) y = sc.yp[d];
-        const uint32_t h = xhi + ((carry >> j) & 1u);
-        atomicAdd(&mypart[(uint32_t)j * pl.Yn + y], (unsigned long long)h << 32);
+        const int d = p + j - sc.mid;
+        if (sc.mid >= 0 && d >= 0 && d <= K) y = sc.yp[d];
+        atoms_add_carry(lo_s + (((uint32_t)(j - j0) * pl.Yn + y) << 2), hi_off, xlo, xhi);
     }
 }
 
-__global__ void __launch_bounds__(512)
-k_mstep_packed(PackedView pv, Plan pl, const float* __restrict__ r, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */,
-               const uint32_t* __restrict__ list_overflow /* nullptr, or: run only when the active list overflowed */,
-               const float* __restrict__ scale /* nullptr when r is already normalised, else 1/normaliser per list sequence */) {
-    extern __shared__ uint32_t smem_u32[];
-    if (list_overflow != nullptr && *list_overflow == 0u) return;          // k_mstep_list does the work
-    const uint32_t nbin = (uint32_t)pl.W * pl.Yn;
-    uint32_t* lo_sh = smem_u32;
-    QEntry* queues = reinterpret_cast<QEntry*>(smem_u32 + ((nbin + 3) & ~3u));
-    unsigned long long* mypart = part + (uint64_t)blockIdx.x * nbin;
-    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) lo_sh[i] = 0u;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    QEntry* q = queues + wib * QCAP;
-    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + wib;
-    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    const int W = pl.W, K = pl.K;
-    for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
-        const uint32_t n = pv.seq_ids[li];
-        const PackedSeq sq = pv.seqs[n];
-        SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = (int)sq.L; sc.mid = (int)sq.mid;
-        const int L = sc.L, LW1 = L - W + 1;
-        const float* __restrict__ rn = r + pv.r_off[li];
-        uint32_t qhead = 0, qcount = 0;        // warp-uniform
-        // r index i = L-W-p runs over [0, LW1); lane takes i = i0 + u*32 + lane
-        float cur[M_UNROLL], nxt[M_UNROLL];
-        const float sc_f = scale ? scale[li] : 1.0f;      // x * 1.0f is exact: one code path for both states of r
-#pragma unroll
-        for (int u = 0; u < M_UNROLL; u++) { const int i = u * 32 + lane; cur[u] = (i < LW1) ? __ldcs(&rn[i]) * sc_f : 0.0f; }
-        for (int i0 = 0; i0 < LW1; i0 += 32 * M_UNROLL) {
-#pragma unroll
-            for (int u = 0; u < M_UNROLL; u++) {
-                const int i = i0 + 32 * M_UNROLL + u * 32 + lane;
-                nxt[u] = (i < LW1) ? __ldcs(&rn[i]) * sc_f : 0.0f;
-            }
-#pragma unroll
-            for (int g = 0; g < M_UNROLL; g += M_GROUP) {
-                uint32_t act = 0;
-#pragma unroll
-                for (int u = 0; u < M_GROUP; u++) act |= (cur[g + u] >= FX_HALF_UNIT ? 1u : 0u) << u;
-                if (__any_sync(FULL, act != 0)) {
-                    const uint32_t cnt = __popc(act);
-                    uint32_t incl = cnt;                                   // inclusive prefix of the per-lane counts
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-                    const uint32_t total = __shfl_sync(FULL, incl, 31);
-                    uint32_t slot = qhead + qcount + incl - cnt;
-#pragma unroll
-                    for (int u = 0; u < M_GROUP; u++) {
-                        if (act & (1u << u)) {
-                            QEntry& e = q[slot & (QCAP - 1)];
-                            e.p = (uint32_t)(L - W - (i0 + (g + u) * 32 + lane)); e.rv = cur[g + u];
-                            slot++;
-                        }
-                    }
-                    qcount += total;
-                    __syncwarp();
-                    while (qcount >= 32) {
-                        const QEntry e = q[(qhead + lane) & (QCAP - 1)];
-                        scatter_window(sc, pl, lo_sh, mypart, (int)e.p, e.rv);
-                        qhead = (qhead + 32) & (QCAP - 1); qcount -= 32;
-                    }
-                    __syncwarp();
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < M_UNROLL; u++) cur[u] = nxt[u];
-        }
-        if (qcount) {                          // flush the sequence's remainder (< 32 entries)
-            if (lane < (int)qcount) {
-                const QEntry e = q[(qhead + lane) & (QCAP - 1)];
-                scatter_window(sc, pl, lo_sh, mypart, (int)e.p, e.rv);
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
-        const uint32_t v = lo_sh[i];
-        if (v) atomicAdd(&mypart[i], (unsigned long long)v);
+// CTA-private tables -> this CTA's slice of the partial-count array (only the CTA's own columns; the rest stays zero)
+__device__ __forceinline__ void flush_cols(const uint32_t* lo_sh, const uint32_t* hi_sh, uint32_t nb, uint32_t Yn, int j0, int W,
+                                           unsigned long long* __restrict__ mypart) {
+    const uint32_t lim = (uint32_t)max(0, min((int)(nb / Yn), W - j0)) * Yn;
+    for (uint32_t i = threadIdx.x; i < lim; i += blockDim.x) {
+        const unsigned long long v = (unsigned long long)lo_sh[i] + ((unsigned long long)hi_sh[i] << 32);
+        if (v) mypart[(uint32_t)j0 * Yn + i] = v;
     }
 }
 
-// M-step from the E-step's active list: every lane scatters one listed window; no scan of r, full lanes throughout.
-__global__ void __launch_bounds__(512)
-k_mstep_list(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
-    extern __shared__ uint32_t smem_u32[];
-    if (*al.overflow != 0u) return;                                        // k_mstep_packed scans r instead
-    const uint32_t nbin = (uint32_t)pl.W * pl.Yn;
-    uint32_t* lo_sh = smem_u32;
-    unsigned long long* mypart = part + (uint64_t)blockIdx.x * nbin;
-    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) lo_sh[i] = 0u;
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    const int K = pl.K;
-    for (uint32_t rg = warp; rg < nregions; rg += nwarps) {
-        const uint32_t cnt = al.cnt[rg];
-        const uint64_t base = al.reg_off[rg];
-        // warp-uniform batch loop with an explicit reconvergence point: lanes that finish a window early (short tail
-        // windows, no carries) must not run ahead into the next batch on their own
-        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
-            const uint32_t e = e0 + lane;
-            if (e < cnt) {
-                const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(al.ent + base + e));
-                const uint32_t li = raw.x, p = raw.y;
-                const float rv = __uint_as_float(raw.z) * al.scale[li];
-                const uint32_t n = pv.seq_ids[li];
-                const PackedSeq sq = pv.seqs[n];
-                SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = (int)sq.L; sc.mid = (int)sq.mid;
-                scatter_window(sc, pl, lo_sh, mypart, (int)p, rv);
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
-        const uint32_t v = lo_sh[i];
-        if (v) atomicAdd(&mypart[i], (unsigned long long)v);
-    }
-}
-
-// one scatter step on explicit shared-window addresses: predicated 32-bit add to the low table, wrap-around detection from
-// the returned old value, predicated add of (high part + carry) to the high table hioff bytes further — no branches
-__device__ __forceinline__ void atoms_add_carry(uint32_t addr, uint32_t hioff, uint32_t xlo, uint32_t xhi, bool valid) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, c, z;\n\t"
-        ".reg .u32 o, s, h, a2;\n\t"
-        "setp.ne.u32 p, %4, 0;\n\t"
-        "mov.u32 o, 0;\n\t"
-        "@p atom.shared.add.u32 o, [%0], %2;\n\t"
-        "add.u32 s, o, %2;\n\t"
-        "setp.lt.u32 c, s, o;\n\t"
-        "selp.u32 h, 1, 0, c;\n\t"
-        "add.u32 h, h, %3;\n\t"
-        "setp.ne.and.u32 z, h, 0, p;\n\t"
-        "add.u32 a2, %0, %1;\n\t"
-        "@z red.shared.add.u32 [a2], h;\n\t"
-        "}"
-        :: "r"(addr), "r"(hioff), "r"(xlo), "r"(xhi), "r"((uint32_t)valid) : "memory");
-}
-
-// Width-specialised list M-step. The motif width is a template parameter, so the W scatter steps of a window are
-// fully unrolled with immediate shifts: the window word is right-aligned once (its last base in the lowest bits) and
-// column j's k-mer is the bit field at 2(W-1-j). Two CTA-private shared tables: low 32 bits of the 2^-40 fixed-point
-// sums, and a second table that collects the high parts (r >= 2^-8) and the wrap-arounds of the low words — no global
-// atomics while scattering. Windows over the N (patched k-mers) take the generic routine.
-template <int WT>
+// M-step from the E-step's active list: every lane scatters one listed window.
+template <int NC>
 __global__ void __launch_bounds__(1024, 1)
-k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsplit, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
     extern __shared__ uint32_t smem_u32[];
-    if (*al.overflow != 0u) return;                                        // k_mstep_packed scans r instead
-    const uint32_t nbin = (uint32_t)WT * pl.Yn;
+    if (*al.overflow != 0u) return;                                        // k_mstep_scan_w scans r instead
+    const uint32_t nb = (uint32_t)NC * pl.Yn;
     uint32_t* lo_sh = smem_u32;
-    uint32_t* hi_sh = smem_u32 + nbin;
-    unsigned long long* mypart = part + (uint64_t)blockIdx.x * nbin;
-    for (uint32_t i = threadIdx.x; i < 2 * nbin; i += blockDim.x) smem_u32[i] = 0u;
+    uint32_t* hi_sh = smem_u32 + nb;
+    for (uint32_t i = threadIdx.x; i < 2 * nb; i += blockDim.x) smem_u32[i] = 0u;
     __syncthreads();
+    const int split = (int)(blockIdx.x % (uint32_t)nsplit), j0 = split * NC;
     const int lane = threadIdx.x & 31;
-    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    const int K = pl.K;
+    const uint32_t warp = (blockIdx.x / (uint32_t)nsplit) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = (gridDim.x / (uint32_t)nsplit) * (blockDim.x >> 5);
+    const int W = pl.W, K = pl.K;
     const uint32_t maskK = pl.Yn - 1;
-    const int ralign = 62 - 2 * (K + WT - 1);                              // right-alignment shift of the window word
+    const int ralign = 62 - 2 * (K + W - 1);                               // right-alignment of the window word (last base lowest)
+    const int e2 = 2 * (W - j0 - NC);                                      // then column j0+NC-1 lowest (negative: split reaches past W)
     const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh);
-    const uint32_t hi_off = nbin * 4u, yn4 = pl.Yn * 4u;
+    const uint32_t hi_off = nb * 4u, yn4 = pl.Yn * 4u;
+    const int nc_valid = min(NC, W - j0);
+    const bool split_full = nc_valid == NC;                                // CTA-uniform
     for (uint32_t rg = warp; rg < nregions; rg += nwarps) {
-        const uint32_t cnt = al.cnt[rg];
         const ActiveEntry* __restrict__ ent = al.ent + al.reg_off[rg];
-        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {                        // warp-uniform batches, reconverged below
+        // front of the region: full windows away from the N, written by the E-step's fast chunks — the unguarded path
+        const uint32_t cnt = al.cnt[rg];
+        for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {                        // warp-uniform batches
             const uint32_t e = e0 + lane;
+            unsigned long long X = 0ull, up = 0ull;                        // lanes past the end add 0 to column bins
+            int jrel_max = -1;
             if (e < cnt) {
                 const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(ent + e));
+                const uint32_t li = raw.x;
+                const float rv = __uint_as_float(raw.z) * al.scale[li];
+                X = __float2ull_rn(rv * FX_SCALE_F);
+                const unsigned long long u = window_word(pv.words + pv.seqs[pv.seq_ids[li]].word_off, (int)raw.y - K) >> ralign;
+                up = e2 >= 0 ? u >> e2 : u << (-e2);
+                jrel_max = NC;
+            }
+            if (split_full) scatter_cols<NC, false>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), 0);
+            else scatter_cols<NC, true>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), min(jrel_max, nc_valid - 1));
+        }
+        // back of the region (filled downwards): windows of the E-step's masked chunks — truncated tail windows, windows
+        // over the N, and the full windows that share their chunks
+        const uint32_t cntb = al.cnt_back[rg];
+        const ActiveEntry* __restrict__ entb = al.ent + al.reg_off[rg + 1] - cntb;
+        for (uint32_t e0 = 0; e0 < cntb; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            unsigned long long X = 0ull, up = 0ull;
+            int jrel_max = -1;
+            if (e < cntb) {
+                const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(entb + e));
                 const uint32_t li = raw.x;
                 const int p = (int)raw.y;
                 const float rv = __uint_as_float(raw.z) * al.scale[li];
                 const uint32_t n = pv.seq_ids[li];
                 const PackedSeq sq = pv.seqs[n];
                 const int L = (int)sq.L, mid = (int)sq.mid;
-                const bool over_n = mid >= 0 && p <= mid + K && p + WT - 1 >= mid;
-                if (over_n) {
+                X = __float2ull_rn(rv * FX_SCALE_F);
+                if (mid >= 0 && p <= mid + K && p + W - 1 >= mid) {        // patched k-mers: slow path
                     SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = L; sc.mid = mid;
-                    scatter_window(sc, pl, lo_sh, mypart, p, rv);
+                    scatter_window_slow(sc, pl, lo_s, hi_off, j0, NC, p, X);
+                    X = 0ull;
                 } else {
-                    const unsigned long long X = __float2ull_rn(rv * FX_SCALE_F);
-                    const uint32_t xlo = (uint32_t)X, xhi = (uint32_t)(X >> 32);
-                    const unsigned long long u = X ? window_word(pv.words + sq.word_off, p - K) >> ralign : 0ull;
-                    const uint32_t ulo = (uint32_t)u, uhi = (uint32_t)(u >> 32);
-                    const int jmax = X ? min(WT - 1, L - WT - p) : -1;       // truncated tail windows stop early (EM.cpp:236)
-                    uint32_t col_s = lo_s;                                   // shared address of column j's first bin
-#pragma unroll
-                    for (int j = 0; j < WT; j++) {
-                        const int sh = 2 * (WT - 1 - j);
-                        const uint32_t y = (sh >= 32 ? (uhi >> (sh - 32)) : __funnelshift_r(ulo, uhi, sh)) & maskK;
-                        atoms_add_carry(col_s + (y << 2), hi_off, xlo, xhi, j <= jmax);
-                        col_s += yn4;
-                    }
+                    const unsigned long long u = window_word(pv.words + sq.word_off, p - K) >> ralign;
+                    up = e2 >= 0 ? u >> e2 : u << (-e2);
+                    jrel_max = min(min(W - 1, L - W - p) - j0, nc_valid - 1);
                 }
             }
             __syncwarp();
+            scatter_cols<NC, true>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), jrel_max);
         }
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
-        const unsigned long long v = (unsigned long long)lo_sh[i] + ((unsigned long long)hi_sh[i] << 32);
-        if (v) atomicAdd(&mypart[i], v);
+    flush_cols(lo_sh, hi_sh, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
+}
+
+// M-step from r itself: one warp per sequence, lanes = 32 consecutive window starts, the packed stream is followed with the
+// E-step's rolling three-word fetch. Chunks without a surviving posterior are skipped after one vote.
+// only_if: nullptr, or a device flag — the kernel runs only when it is non-zero (active list overflowed).
+// scale: nullptr when r is already normalised, else 1/normaliser per list sequence.
+template <int NC>
+__global__ void __launch_bounds__(1024, 1)
+k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float* __restrict__ scale, const uint32_t* __restrict__ only_if,
+               int nsplit, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+    extern __shared__ uint32_t smem_u32[];
+    if (only_if != nullptr && *only_if == 0u) return;                      // k_mstep_list_w did the work
+    const uint32_t nb = (uint32_t)NC * pl.Yn;
+    uint32_t* lo_sh = smem_u32;
+    uint32_t* hi_sh = smem_u32 + nb;
+    for (uint32_t i = threadIdx.x; i < 2 * nb; i += blockDim.x) smem_u32[i] = 0u;
+    __syncthreads();
+    const int split = (int)(blockIdx.x % (uint32_t)nsplit), j0 = split * NC;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x / (uint32_t)nsplit) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = (gridDim.x / (uint32_t)nsplit) * (blockDim.x >> 5);
+    const int W = pl.W, K = pl.K;
+    const uint32_t maskK = pl.Yn - 1;
+    const int ralign = 62 - 2 * (K + W - 1);
+    const int e2 = 2 * (W - j0 - NC);
+    const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh);
+    const uint32_t hi_off = nb * 4u, yn4 = pl.Yn * 4u;
+    const int nc_valid = min(NC, W - j0);
+    const bool split_full = nc_valid == NC;                                // CTA-uniform
+    const int lane_word = (lane - K) >> 4;                                 // this lane's windows start at bases lane-K + 32*chunk
+    const int sft = 2 * ((lane - K) & 15);
+    for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
+        const uint32_t n = pv.seq_ids[li];
+        const PackedSeq sq = pv.seqs[n];
+        const int L = (int)sq.L, LW1 = L - W + 1, mid = (int)sq.mid;
+        const uint32_t* __restrict__ wl = pv.words + sq.word_off + lane_word;
+        uint32_t t0 = wl[0], t1 = wl[1], t2 = wl[2];
+        const float* __restrict__ rp = r + pv.r_off[li] + (L - W - lane);  // r index of this lane's window; moves down 32 per chunk
+        const float sc_f = scale ? scale[li] : 1.0f;                       // x * 1.0f is exact: one code path for both states of r
+        const int nch = (LW1 + 31) >> 5;
+        int cn0 = nch, cn1 = -1;                                           // chunks that hold windows over the N
+        if (mid >= 0) { cn0 = max(mid - W + 1, 0) >> 5; cn1 = (mid + K) >> 5; }
+        const int ctail = max(L - 2 * W + 2, 0) >> 5;                      // first chunk with a truncated window (p > L-2W+1)
+        float rv_next = lane < LW1 ? __ldcs(rp) : 0.0f;
+        for (int c = 0; c < nch; c++) {
+            const int p = (c << 5) + lane;
+            const uint32_t whi = __funnelshift_l(t1, t0, sft), wlo = __funnelshift_l(t2, t1, sft);
+            wl += 2;
+            t0 = t2; t1 = wl[1]; t2 = wl[2];
+            const float rv = rv_next * sc_f;
+            rp -= 32;
+            rv_next = (p + 32 < LW1) ? __ldcs(rp) : 0.0f;
+            unsigned long long X = __float2ull_rn(rv * FX_SCALE_F);
+            if (!__any_sync(FULL, X != 0ull)) continue;
+            const unsigned long long u = (((unsigned long long)whi << 32) | wlo) >> ralign;
+            const unsigned long long up = e2 >= 0 ? u >> e2 : u << (-e2);
+            if ((c >= cn0 && c <= cn1) || c >= ctail || !split_full) {     // windows over the N / truncated windows / partial split
+                if (mid >= 0 && p <= mid + K && p + W - 1 >= mid) {
+                    SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = L; sc.mid = mid;
+                    scatter_window_slow(sc, pl, lo_s, hi_off, j0, NC, p, X);
+                    X = 0ull;
+                }
+                __syncwarp();
+                scatter_cols<NC, true>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), min(min(W - 1, L - W - p) - j0, nc_valid - 1));
+            } else {
+                scatter_cols<NC, false>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), 0);
+            }
+        }
     }
+    __syncthreads();
+    flush_cols(lo_sh, hi_sh, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
 }
 
 // ---- scoring -------------------------------------------------------------------------------------------------------

@@ -226,13 +226,15 @@ def _run_variant(capi, g, env, iters=3):
 @pytest.mark.parametrize("case", ["jund_k2", "syn_k2_N", "syn_k4", "syn_k3_fdr"])
 def test_kernel_paths_agree(capi, case):
     """Packed path with the active list (default), with an overflowing list (device-side fall-back to the scan
-    M-step), without the list, without the reduced leading context, and the generic index-array path: the M-step sums
+    M-step), without the list, with the M-step's columns split over CTAs (list and scan kernels), without the reduced
+    leading context, and the generic index-array path: the M-step sums
     the same fixed-point integers on every path, so counts are BIT-identical wherever the E-step is; E-step variants
     differ only by the association of the column products (1e-5 tolerance)."""
     g = Golden(case)
     base = _run_variant(capi, g, {})
     for env, same_estep in (({"BAMM_LIST_FRAC": "0"}, True), ({"BAMM_LIST_FRAC": "0.000001"}, True),
-                            ({"BAMM_NO_LISTW": "1"}, True), ({"BAMM_NO_REDUCED": "1"}, False),
+                            ({"BAMM_M_COLS": "3"}, True), ({"BAMM_M_COLS": "4", "BAMM_LIST_FRAC": "0"}, True),
+                            ({"BAMM_NO_REDUCED": "1"}, False),
                             ({"BAMM_TABLE_BYTES": "40000"}, False), ({"BAMM_NO_PACKED": "1"}, False)):
         alt = _run_variant(capi, g, env)
         if same_estep:
