@@ -77,10 +77,11 @@ struct bamm_em {
     uint32_t* d_gen_ids = nullptr;  uint64_t* d_gen_roff = nullptr;
     uint32_t* d_pk_ids = nullptr;   uint64_t* d_pk_roff = nullptr;
     Plan plan;                  // W, K, Yn for the packed M-step / scoring kernels
-    GroupPlan gplan;            // column groups of the packed E-step (chosen in set_model)
-    bool gfast = false;         // every group's bit field sits below bit 32 of the window word
+    std::vector<GroupPlan> gplans;   // column groups of the packed E-step, one plan per column pass (chosen in set_model)
+    std::vector<char> gfast;         // per pass: every group's bit field sits below bit 32 of the window word
     size_t tab_capacity = 0;    // bytes available for the group tables (= opt-in shared memory)
-    float* d_tab = nullptr;     // group tables, concatenated
+    float* d_tab = nullptr;     // group tables, concatenated; tab_capacity bytes per pass
+    size_t tab_passes = 0;      // passes d_tab has room for
     // active list (windows that survive the M-step's fixed-point rounding), one region per E-step warp
     uint32_t nregions = 0;
     ActiveEntry* d_act = nullptr;
@@ -385,7 +386,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     delete em;
 }
 
-static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, bool optin_only);
+static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, size_t pass, bool optin_only);
 static int mstep_w_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, int mode);
 
 template <typename K> static int max_smem_optin(K kernel, size_t bytes) {
@@ -397,7 +398,7 @@ template <typename K> static int max_smem_optin(K kernel, size_t bytes) {
 // Cuts columns 0..W-1 into the fewest consecutive groups whose lookup tables (4^bases floats each) fit `budget` bytes.
 // reduced: columns j < K only depend on max(j, K_bg)+1 bases (true for every model produced by updateV; checked for
 // models passed to bamm_em_set_model). Returns false when even one column per group does not fit.
-static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget, GroupPlan& gp, bool& fast) {
+static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget, int ca, int cb, GroupPlan& gp, bool& fast) {
     auto ctx = [&](int j) { int c = j < K ? j : K; if (!reduced) c = K; return c > K_bg ? c : K_bg; };
     auto first_base = [&](int a, int b) { int lo = 1 << 30; for (int j = a; j <= b; j++) lo = std::min(lo, j - ctx(j)); return lo; };
     const double INF = 1e300;
@@ -408,10 +409,10 @@ static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget,
     // sfx[j][n]: least bytes covering columns [j,W) with n groups
     std::vector<std::vector<double>> sfx(W + 1, std::vector<double>(MAXG + 1, INF));
     std::vector<std::vector<int>> nxt(W + 1, std::vector<int>(MAXG + 1, -1));
-    sfx[W][0] = 0;
-    for (int j = W - 1; j >= 0; j--)
+    sfx[cb][0] = 0;
+    for (int j = cb - 1; j >= ca; j--)
         for (int n = 1; n <= MAXG; n++)
-            for (int e = j + 1; e <= W; e++) {
+            for (int e = j + 1; e <= cb; e++) {
                 if (sfx[e][n - 1] >= INF) continue;
                 const double c = bytes_of(j, e - 1) + sfx[e][n - 1];
                 if (c < sfx[j][n]) { sfx[j][n] = c; nxt[j][n] = e; }
@@ -419,8 +420,8 @@ static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget,
     // fewest groups first; then a first group wide enough for the one-shift extraction (see `fast` below); then bytes
     int G = -1, best_a1 = -1; bool best_fast = false; double best_bytes = INF;
     for (int n = 1; n <= MAXG && G < 0; n++) {
-        for (int a1 = 1; a1 <= W; a1++) {
-            const double c = bytes_of(0, a1 - 1) + sfx[a1][n - 1];
+        for (int a1 = ca + 1; a1 <= cb; a1++) {
+            const double c = bytes_of(ca, a1 - 1) + sfx[a1][n - 1];
             if (c > (double)budget) continue;
             const int d = std::max(0, 15 - K - (a1 - 1));
             const bool f = d <= 31 - K - W;
@@ -431,7 +432,7 @@ static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget,
     memset(&gp, 0, sizeof(gp));
     gp.W = W; gp.K = K; gp.G = G; gp.Yn = 1u << (2 * (K + 1));
     std::vector<int> cuts(G + 1);
-    cuts[0] = 0; cuts[1] = best_a1;
+    cuts[0] = ca; cuts[1] = best_a1;
     for (int g = 1, j = best_a1; g < G; g++) { j = nxt[j][G - g]; cuts[g + 1] = j; }
     uint32_t base = 0;
     for (int g = 0; g < G; g++) {
@@ -444,6 +445,8 @@ static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget,
         base += 4u << (2 * nb);
     }
     gp.table_bytes = base;
+    gp.passmask = (uint32_t)(((cb >= 32 ? 0x100000000ull : (1ull << cb)) - 1ull) & ~((1ull << ca) - 1ull));
+    gp.pass_first = ca == 0; gp.pass_last = cb == W;
     // alignment of the window word: base p+hi sits at bit 62-2(hi+K+delta); the byte offset needs shift = 60-2(hi+K+delta) >= 0
     const int hi0 = cuts[1] - 1;
     int delta = 15 - K - hi0; if (delta < 0) delta = 0;
@@ -455,6 +458,33 @@ static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget,
         const int sh = 60 - 2 * (hi + K + delta);
         gp.shift[g] = (uint32_t)sh;
         gp.shift2[g] = sh > 32 ? (uint32_t)(sh - 32) : 0u;
+    }
+    return true;
+}
+
+// Column passes: the fewest lookups per window over all cuts of [0,W) into consecutive column ranges whose group tables
+// fit `budget` each; every extra pass costs one read and one write of r, weighted like PASS_COST lookups.
+static bool plan_passes(int W, int K, int K_bg, bool reduced, size_t budget, std::vector<GroupPlan>& plans, std::vector<char>& fast) {
+    const int PASS_COST = 3, INF = 1 << 28;
+    std::vector<int> best(W + 1, INF), from(W + 1, -1);
+    best[0] = 0;
+    GroupPlan gp; bool f;
+    if (make_group_plan(W, K, K_bg, reduced, budget, 0, W, gp, f)) { plans.assign(1, gp); fast.assign(1, (char)f); return true; }
+    for (int b = 1; b <= W; b++)
+        for (int a = 0; a < b; a++) {
+            if (best[a] >= INF || !make_group_plan(W, K, K_bg, reduced, budget, a, b, gp, f)) continue;
+            const int c = best[a] + gp.G + PASS_COST;
+            if (c < best[b]) { best[b] = c; from[b] = a; }
+        }
+    if (best[W] >= INF) return false;
+    std::vector<int> cuts;
+    for (int b = W; b > 0; b = from[b]) cuts.push_back(b);
+    cuts.push_back(0);
+    std::reverse(cuts.begin(), cuts.end());
+    plans.clear(); fast.clear();
+    for (size_t i = 0; i + 1 < cuts.size(); i++) {
+        make_group_plan(W, K, K_bg, reduced, budget, cuts[i], cuts[i + 1], gp, f);
+        plans.push_back(gp); fast.push_back((char)f);
     }
     return true;
 }
@@ -490,8 +520,8 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     if (getenv("BAMM_TABLE_BYTES")) em->tab_capacity = std::min(em->tab_capacity, (size_t)atol(getenv("BAMM_TABLE_BYTES")));
     if (packed_ok) {
         // both variants (with / without the reduced context of the leading columns) must be plannable
-        GroupPlan tmp; bool f;
-        packed_ok = make_group_plan(W, K, em->K_bg, false, em->tab_capacity, tmp, f);
+        std::vector<GroupPlan> tmp; std::vector<char> f;
+        packed_ok = plan_passes(W, K, em->K_bg, false, em->tab_capacity, tmp, f);
         em->plan.W = W; em->plan.K = K; em->plan.T = 1; em->plan.C = W;
         em->plan.Yn = em->Yn; em->plan.Zn = em->Yn; em->plan.q = 0.3f;
     }
@@ -570,7 +600,6 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     }
     // ---- packed path geometry
     if (em->npk) {
-        CUE(cudaMalloc(&em->d_tab, em->tab_capacity));
         CUE(cudaMalloc(&em->d_scale, (size_t)em->npk * sizeof(float)));
         em->block_pe = BAMM_E_THREADS;              // one CTA per SM: the group tables fill its shared memory
         em->grid_pe = sms;
@@ -620,10 +649,12 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
 
 static int launch_tuple_table(bamm_em* em) {
     if (!em->npk) return BAMM_OK;
-    const uint32_t total = em->gplan.table_bytes >> 2;
-    const uint32_t blocks = (total + 255) / 256;
-    k_make_group_tables<<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(em->d_s, em->gplan, em->d_tab);
-    CU(cudaGetLastError());
+    for (size_t i = 0; i < em->gplans.size(); i++) {
+        const uint32_t total = em->gplans[i].table_bytes >> 2;
+        const uint32_t blocks = (total + 255) / 256;
+        k_make_group_tables<<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(em->d_s, em->gplans[i], (float*)((char*)em->d_tab + i * em->tab_capacity));
+        CU(cudaGetLastError());
+    }
     return BAMM_OK;
 }
 
@@ -645,10 +676,16 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
     CU(cudaSetDevice(em->device));
     if (em->npk) {
         const bool reduced = leading_columns_are_copies(em, v_all) && !getenv("BAMM_NO_REDUCED");
-        if (!make_group_plan(em->W, em->K, em->K_bg, reduced, em->tab_capacity, em->gplan, em->gfast))
+        if (!plan_passes(em->W, em->K, em->K_bg, reduced, em->tab_capacity, em->gplans, em->gfast))
             return fail(BAMM_E_STATE, "no column-group plan fits shared memory");
-        em->smem_pe = em->gplan.table_bytes;
-        if (estep_packed_dispatch(em, nullptr, nullptr, true)) return fail(BAMM_E_CUDA, "cannot opt in to %zu bytes of shared memory", em->smem_pe);
+        if (em->gplans.size() > em->tab_passes) {
+            CU(cudaStreamSynchronize(em->stream));
+            cudaFree(em->d_tab); em->d_tab = nullptr; em->tab_passes = 0;
+            CU(cudaMalloc(&em->d_tab, em->gplans.size() * em->tab_capacity));
+            em->tab_passes = em->gplans.size();
+        }
+        for (size_t i = 0; i < em->gplans.size(); i++)
+            if (estep_packed_dispatch(em, nullptr, i, true)) return fail(BAMM_E_CUDA, "cannot opt in to %u bytes of shared memory", em->gplans[i].table_bytes);
     }
     CU(cudaMemcpyAsync(em->d_v, v_all, em->model_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
     CU(cudaMemcpyAsync(em->d_vbg, vbg_all, em->bg_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
@@ -668,15 +705,21 @@ static ActiveList alist_of(const bamm_em* em) {
     al.cnt = em->d_act_cnt; al.cnt_back = em->d_act_cnt ? em->d_act_cnt + em->nregions : nullptr; al.overflow = em->d_overflow;
     return al;
 }
-template <int G, bool FAST> static int estep_packed_one(bamm_em* em, const PackedView* pv, bool optin_only) {
-    if (optin_only) return max_smem_optin(k_estep_packed<G, FAST>, em->smem_pe);
-    GroupPlan gp = em->gplan; gp.q = em->q;
-    k_estep_packed<G, FAST><<<em->grid_pe, em->block_pe, em->smem_pe, em->stream>>>(*pv, gp, em->d_tab, em->d_s, em->d_sT, em->d_r, em->d_xbuf + em->nbin, alist_of(em));
+template <int G, bool FAST, bool MULTI> static int estep_packed_one(bamm_em* em, const PackedView* pv, size_t pass, bool optin_only) {
+    GroupPlan gp = em->gplans[pass]; gp.q = em->q;
+    if (optin_only) return max_smem_optin(k_estep_packed<G, FAST, MULTI>, gp.table_bytes);
+    k_estep_packed<G, FAST, MULTI><<<em->grid_pe, em->block_pe, gp.table_bytes, em->stream>>>(*pv, gp, (const float*)((const char*)em->d_tab + pass * em->tab_capacity),
+                                                                                       em->d_s, em->d_sT, em->d_r, em->d_xbuf + em->nbin, alist_of(em));
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
-static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, const Plan*, bool optin_only) {
-    switch (em->gplan.G) {
-#define BAMM_CASE(g) case g: return em->gfast ? estep_packed_one<g, true>(em, pv, optin_only) : estep_packed_one<g, false>(em, pv, optin_only);
+template <int G> static int estep_packed_g(bamm_em* em, const PackedView* pv, size_t pass, bool optin_only) {
+    const bool multi = em->gplans.size() > 1;
+    if (em->gfast[pass]) return multi ? estep_packed_one<G, true, true>(em, pv, pass, optin_only) : estep_packed_one<G, true, false>(em, pv, pass, optin_only);
+    return multi ? estep_packed_one<G, false, true>(em, pv, pass, optin_only) : estep_packed_one<G, false, false>(em, pv, pass, optin_only);
+}
+static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, size_t pass, bool optin_only) {
+    switch (em->gplans[pass].G) {
+#define BAMM_CASE(g) case g: return estep_packed_g<g>(em, pv, pass, optin_only);
         BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
         BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
 #undef BAMM_CASE
@@ -695,13 +738,14 @@ static PackedView pview_of(const bamm_em* em) {
 }
 
 static int launch_estep(bamm_em* em) {
-    em->launches += (em->npk ? 1 : 0) + (em->ngen ? 1 : 0);
+    em->launches += (em->npk ? em->gplans.size() : 0) + (em->ngen ? 1 : 0);
     unsigned long long* scal = em->d_xbuf + em->nbin;
     CU(cudaMemsetAsync(scal, 0, 2 * sizeof(unsigned long long), em->stream));
     if (em->npk) {
         PackedView pv = pview_of(em);
         if (em->d_overflow) CU(cudaMemsetAsync(em->d_overflow, 0, 4, em->stream));
-        if (estep_packed_dispatch(em, &pv, nullptr, false)) return fail(BAMM_E_CUDA, "packed E-step launch failed");
+        for (size_t pass = 0; pass < em->gplans.size(); pass++)
+            if (estep_packed_dispatch(em, &pv, pass, false)) return fail(BAMM_E_CUDA, "packed E-step launch failed");
         em->r_scaled = false;
         CU(cudaGetLastError());
     }
@@ -755,7 +799,7 @@ static int launch_mstep_accumulate(bamm_em* em) {
             cudaMemcpy(&ov, em->d_overflow, 4, cudaMemcpyDeviceToHost);
             uint64_t tot = 0, mx = 0; for (uint32_t x : c) { tot += x; if (x > mx) mx = x; }
             fprintf(stderr, "[bamm] active list: %llu entries (%.4f of r), max region %llu, overflow %u, G=%d fast=%d delta=%d table %u B\n",
-                    (unsigned long long)tot, (double)tot / (double)em->rsize, (unsigned long long)mx, ov, em->gplan.G, (int)em->gfast, em->gplan.delta, em->gplan.table_bytes);
+                    (unsigned long long)tot, (double)tot / (double)em->rsize, (unsigned long long)mx, ov, em->gplans[0].G, (int)em->gfast[0], em->gplans[0].delta, em->gplans[0].table_bytes);
         }
         // the E-step listed the windows that matter; the scan kernel only does work (device-side decision) if a region
         // overflowed, or when there is no list

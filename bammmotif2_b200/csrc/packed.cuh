@@ -143,6 +143,10 @@ struct GroupPlan {
     uint32_t base[MAXG];         // byte offset of the group's table
     uint32_t colmask[MAXG];      // bit j for every column of the group
     int col0[MAXG], ncol[MAXG], lo[MAXG];   // first column, column count, first base relative to the window start p
+    // column passes: when the tables of all W columns do not fit shared memory (orders >= 5 with wide motifs) the E-step
+    // runs once per pass over a column range; the partial product of the earlier passes travels through r
+    uint32_t passmask;           // bit j for every column of this pass (all W columns in a single-pass plan)
+    int pass_first, pass_last;
 };
 
 // tab[g][z] = prod_{j in group g} s[j][ y_j(z) ], product in ascending j from 1.0f; z holds bases p+lo .. p+hi
@@ -233,7 +237,7 @@ __device__ __forceinline__ float lds_f32(uint32_t off, uint32_t ubase) {
 #ifndef BAMM_E_PIN
 #define BAMM_E_PIN 0             // keep the per-group extraction constants in registers instead of re-reading the constant bank
 #endif
-template <int G, bool FAST>
+template <int G, bool FAST, bool MULTI>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g /* [W][Yn] */,
                const float* __restrict__ s_rows /* [Yn][W] */, float* __restrict__ r, unsigned long long* __restrict__ scal, ActiveList al) {
@@ -263,7 +267,9 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
         if (G <= BAMM_E_PIN) asm volatile("" : "+r"(c_sh[g]), "+r"(c_mk[g]), "+r"(c_ab[g]));
 #endif
     }
-    bool emit = al.ent != nullptr;
+    const bool first = !MULTI || gp.pass_first != 0, last = !MULTI || gp.pass_last != 0;    // CTA-uniform
+    const uint32_t passmask = MULTI ? gp.passmask : 0xffffffffu;
+    bool emit = al.ent != nullptr && last;
     ActiveEntry* __restrict__ lreg = emit ? al.ent + al.reg_off[warp] : nullptr;      // this warp's region
     const uint32_t lcap = emit ? (uint32_t)(al.reg_off[warp + 1] - al.reg_off[warp]) : 0u;
     uint32_t lpos = 0, bpos = 0;                            // entries written so far at the front / at the back (downwards)
@@ -297,6 +303,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                     wl += 2;
                     t0 = t2; t1 = wl[1]; t2 = wl[2];
                     float prod = 1.0f;
+                    if (MULTI && !first) prod = *rp;            // product over the columns of the earlier passes
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         uint32_t off;
@@ -304,6 +311,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                         else      off = (__funnelshift_rc(wlo, whi, c_sh[g]) >> c_s2[g]) & c_mk[g];
                         prod *= lds_f32(off, c_ab[g]);
                     }
+                    if (MULTI && !last) { *rp = prod; rp -= 32; continue; }
                     const float val = prod * pos;
                     *rp = val;
                     rp -= 32;
@@ -330,15 +338,16 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                     t0 = t2; t1 = wl[1]; t2 = wl[2];
                     const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
                     const int jmax = (p < LW1) ? min(W - 1, L - W - p) : -1;
-                    const uint32_t valid = jmax >= 0 ? (jmax >= 31 ? 0xffffffffu : ((2u << jmax) - 1u)) : 0u;
+                    const uint32_t valid = (jmax >= 0 ? (jmax >= 31 ? 0xffffffffu : ((2u << jmax) - 1u)) : 0u) & passmask;
                     uint32_t ncols = 0;                     // columns whose k-mer holds a rand() draw of the N
                     const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
                     if (over_n) {
                         const int ja = max(mid - p, 0), jb = min(mid - p + K, W - 1);
-                        if (jb >= ja) ncols = ((jb >= 31 ? 0xffffffffu : ((2u << jb) - 1u))) & ~((1u << ja) - 1u);
+                        if (jb >= ja) ncols = ((jb >= 31 ? 0xffffffffu : ((2u << jb) - 1u))) & ~((1u << ja) - 1u) & passmask;
                     }
                     uint32_t cols = valid;
                     float prod = 1.0f;
+                    if (MULTI && !first && p < LW1) prod = *rp;
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         const uint32_t cm = gp.colmask[g];
@@ -362,7 +371,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                             for (int u = 0; u < 4; u++) {
                                 const int d = d0 + u, j = mid + d - p;
                                 f[u] = 1.0f;
-                                if (d <= K && over_n && j >= 0 && j <= jmax)
+                                if (d <= K && over_n && j >= 0 && j <= jmax && (!MULTI || ((passmask >> j) & 1u)))
                                     f[u] = __ldg(&s_rows[(uint64_t)pv.ypatch[(uint64_t)n * (K + 1) + d] * W + j]);
                             }
 #pragma unroll
@@ -388,9 +397,12 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                     }
                     float val = 0.0f;
                     if (p < LW1) {
-                        val = prod * pos;
-                        *rp = val;
-                        sum += val;
+                        if (MULTI && !last) *rp = prod;
+                        else {
+                            val = prod * pos;
+                            *rp = val;
+                            sum += val;
+                        }
                     }
                     rp -= 32;
                     if (emit) {
@@ -408,6 +420,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                 }
             }
         }
+        if (MULTI && !last) continue;
         sum = warp_sum(sum);
         const float norm = one_minus_q + sum;
         const float rnorm = __frcp_rn(norm);
@@ -423,7 +436,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
         if (llh_fx) atomicAdd(&scal[0], (unsigned long long)llh_fx);
         if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);
     }
-    if (al.ent != nullptr) { al.cnt[warp] = lpos; al.cnt_back[warp] = bpos; }   // every lane holds the same counts
+    if (al.ent != nullptr && last) { al.cnt[warp] = lpos; al.cnt_back[warp] = bpos; }   // every lane holds the same counts
 }
 
 // r <- r * scale for every packed-list sequence: run before r leaves the device (bamm_em_get_r). One warp per sequence.

@@ -227,7 +227,8 @@ def _run_variant(capi, g, env, iters=3):
 def test_kernel_paths_agree(capi, case):
     """Packed path with the active list (default), with an overflowing list (device-side fall-back to the scan
     M-step), without the list, with the M-step's columns split over CTAs (list and scan kernels), without the reduced
-    leading context, and the generic index-array path: the M-step sums
+    leading context, with table budgets that force more column groups or several column passes of the E-step, and the
+    generic index-array path: the M-step sums
     the same fixed-point integers on every path, so counts are BIT-identical wherever the E-step is; E-step variants
     differ only by the association of the column products (1e-5 tolerance)."""
     g = Golden(case)
@@ -235,7 +236,8 @@ def test_kernel_paths_agree(capi, case):
     for env, same_estep in (({"BAMM_LIST_FRAC": "0"}, True), ({"BAMM_LIST_FRAC": "0.000001"}, True),
                             ({"BAMM_M_COLS": "3"}, True), ({"BAMM_M_COLS": "4", "BAMM_LIST_FRAC": "0"}, True),
                             ({"BAMM_NO_REDUCED": "1"}, False),
-                            ({"BAMM_TABLE_BYTES": "40000"}, False), ({"BAMM_NO_PACKED": "1"}, False)):
+                            ({"BAMM_TABLE_BYTES": "40000"}, False), ({"BAMM_TABLE_BYTES": "5000"}, False),
+                            ({"BAMM_TABLE_BYTES": "9000", "BAMM_M_COLS": "2"}, False), ({"BAMM_NO_PACKED": "1"}, False)):
         alt = _run_variant(capi, g, env)
         if same_estep:
             assert np.array_equal(alt["r1"], base["r1"]), env
