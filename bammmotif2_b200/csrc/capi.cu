@@ -219,7 +219,7 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
         if (s->nregular) {
             CUS(cudaMalloc(&s->d_pseq, nseq * sizeof(PackedSeq)));
             CUS(cudaMemcpy(s->d_pseq, ps.data(), nseq * sizeof(PackedSeq), cudaMemcpyHostToDevice));
-            CUS(cudaMalloc(&s->d_words, w * sizeof(uint32_t)));
+            CUS(cudaMalloc(&s->d_words, (w + 16) * sizeof(uint32_t)));    // slack: the rolling fetch of the last sequence runs a few words ahead
             k_pack<<<s->sm_count * 8, 256>>>(s->d_codes, s->d_off, nseq, s->d_kind, s->d_pseq, s->d_words);
             CUS(cudaGetLastError());
             CUS(cudaDeviceSynchronize());
@@ -423,8 +423,7 @@ static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget,
         for (int a1 = ca + 1; a1 <= cb; a1++) {
             const double c = bytes_of(ca, a1 - 1) + sfx[a1][n - 1];
             if (c > (double)budget) continue;
-            const int d = std::max(0, 15 - K - (a1 - 1));
-            const bool f = d <= 31 - K - W;
+            const bool f = std::max(K - ca, 15 - (a1 - 1)) <= 31 - cb;
             if (G < 0 || (f && !best_fast) || (f == best_fast && c < best_bytes)) { G = n; best_a1 = a1; best_fast = f; best_bytes = c; }
         }
     }
@@ -447,15 +446,19 @@ static bool make_group_plan(int W, int K, int K_bg, bool reduced, size_t budget,
     gp.table_bytes = base;
     gp.passmask = (uint32_t)(((cb >= 32 ? 0x100000000ull : (1ull << cb)) - 1ull) & ~((1ull << ca) - 1ull));
     gp.pass_first = ca == 0; gp.pass_last = cb == W;
-    // alignment of the window word: base p+hi sits at bit 62-2(hi+K+delta); the byte offset needs shift = 60-2(hi+K+delta) >= 0
+    // alignment of the window word (32 bases from p-kd): base p+hi sits at bit 62-2(hi+kd); the byte offset of a group's
+    // entry needs shift = 60-2(hi+kd) >= 0, i.e. kd <= 31-cb; the oldest base any column of the pass reads is p+ca-K, i.e.
+    // kd >= K-ca; the one-shift extraction needs every shift <= 31, i.e. kd >= 15-hi0
     const int hi0 = cuts[1] - 1;
-    int delta = 15 - K - hi0; if (delta < 0) delta = 0;
-    fast = delta <= 31 - K - W;
-    if (!fast) delta = 0;
-    gp.delta = delta;
+    const int kd_min = K - ca, kd_max = 31 - cb;
+    if (kd_min > kd_max) return false;
+    const int kd_fast = std::max(kd_min, 15 - hi0);
+    fast = kd_fast <= kd_max;
+    const int kd = fast ? kd_fast : kd_min;
+    gp.kd = kd;
     for (int g = 0; g < G; g++) {
         const int hi = cuts[g + 1] - 1;
-        const int sh = 60 - 2 * (hi + K + delta);
+        const int sh = 60 - 2 * (hi + kd);
         gp.shift[g] = (uint32_t)sh;
         gp.shift2[g] = sh > 32 ? (uint32_t)(sh - 32) : 0u;
     }
@@ -514,7 +517,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     const size_t table_bytes = (size_t)em->nbin * sizeof(float);
     // ---- packed path: possible when the column-group tables and the M-step's count table fit shared memory
     // (the M-step needs two 32-bit count tables of at least one column: 4^(K+1) * 8 bytes)
-    bool packed_ok = s->A == 4 && s->nregular > 0 && W + K <= 31 && Yn64 <= 65536 &&
+    bool packed_ok = s->A == 4 && s->nregular > 0 && Yn64 <= 65536 &&
                      Yn64 * 8 <= (uint64_t)max_optin && !getenv("BAMM_NO_PACKED");
     em->tab_capacity = (size_t)max_optin;
     if (getenv("BAMM_TABLE_BYTES")) em->tab_capacity = std::min(em->tab_capacity, (size_t)atol(getenv("BAMM_TABLE_BYTES")));
@@ -605,7 +608,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         em->grid_pe = sms;
         // M-step geometry: as many columns per CTA as two 32-bit tables allow, the fewest splits, columns spread evenly
         {
-            int nc_max = (int)((size_t)max_optin / ((size_t)em->Yn * 8));
+            int nc_max = std::min(32 - K, (int)((size_t)max_optin / ((size_t)em->Yn * 8)));   // K + columns <= 32 bases of one window word
             if (getenv("BAMM_M_COLS")) nc_max = std::max(1, std::min(nc_max, atoi(getenv("BAMM_M_COLS"))));
             if (nc_max > W) nc_max = W;
             em->m_nsplit = (W + nc_max - 1) / nc_max;
@@ -780,7 +783,7 @@ static int mstep_w_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, i
         BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
         BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
         BAMM_CASE(17) BAMM_CASE(18) BAMM_CASE(19) BAMM_CASE(20) BAMM_CASE(21) BAMM_CASE(22) BAMM_CASE(23) BAMM_CASE(24)
-        BAMM_CASE(25) BAMM_CASE(26) BAMM_CASE(27) BAMM_CASE(28) BAMM_CASE(29) BAMM_CASE(30) BAMM_CASE(31)
+        BAMM_CASE(25) BAMM_CASE(26) BAMM_CASE(27) BAMM_CASE(28) BAMM_CASE(29) BAMM_CASE(30) BAMM_CASE(31) BAMM_CASE(32)
 #undef BAMM_CASE
         default: return -1;
     }
@@ -799,7 +802,7 @@ static int launch_mstep_accumulate(bamm_em* em) {
             cudaMemcpy(&ov, em->d_overflow, 4, cudaMemcpyDeviceToHost);
             uint64_t tot = 0, mx = 0; for (uint32_t x : c) { tot += x; if (x > mx) mx = x; }
             fprintf(stderr, "[bamm] active list: %llu entries (%.4f of r), max region %llu, overflow %u, G=%d fast=%d delta=%d table %u B\n",
-                    (unsigned long long)tot, (double)tot / (double)em->rsize, (unsigned long long)mx, ov, em->gplans[0].G, (int)em->gfast[0], em->gplans[0].delta, em->gplans[0].table_bytes);
+                    (unsigned long long)tot, (double)tot / (double)em->rsize, (unsigned long long)mx, ov, em->gplans[0].G, (int)em->gfast[0], em->gplans[0].kd, em->gplans[0].table_bytes);
         }
         // the E-step listed the windows that matter; the scan kernel only does work (device-side decision) if a region
         // overflowed, or when there is no list

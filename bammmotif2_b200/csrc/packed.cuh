@@ -133,7 +133,7 @@ __global__ void k_make_ypatch(const uint64_t* __restrict__ ppos, const uint64_t*
 // (C3: columns 0-4 in one 4^7 table). A host-side DP picks the cut with the fewest groups that fits shared memory.
 constexpr int MAXG = 16;
 struct GroupPlan {
-    int W, K, G, delta;          // window word starts at base p-K-delta
+    int W, K, G, kd;             // window word = the 32 bases starting at base p-kd (kd may be negative in later column passes)
     uint32_t Yn;                 // 4^(K+1)
     float q;
     uint32_t table_bytes;
@@ -247,7 +247,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    const int W = gp.W, K = gp.K, KD = gp.K + gp.delta;
+    const int W = gp.W, K = gp.K, KD = gp.kd;
     const uint32_t maskK = gp.Yn - 1;
     const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);        // 32-bit shared-window address
     long long llh_fx = 0, rsum_fx = 0;
@@ -529,12 +529,12 @@ __device__ __forceinline__ void scatter_window_slow(const SeqCtx& sc, const Plan
                                                     int p, unsigned long long X) {
     if (X == 0) return;
     const int W = pl.W, K = pl.K;
-    const unsigned long long w = window_word(sc.wd, p - K);      // bases p-K .. p-K+31
+    const unsigned long long w = window_word(sc.wd, p + j0 - K); // bases p+j0-K .. p+j0-K+31
     const uint32_t maskK = pl.Yn - 1;
     const int jmax = min(min(W - 1, sc.L - W - p), j0 + nc - 1);
     const uint32_t xlo = (uint32_t)X, xhi = (uint32_t)(X >> 32);
     for (int j = j0; j <= jmax; j++) {
-        uint32_t y = field(w, 62 - 2 * K - 2 * j, maskK);
+        uint32_t y = field(w, 62 - 2 * K - 2 * (j - j0), maskK);
         const int d = p + j - sc.mid;
         if (sc.mid >= 0 && d >= 0 && d <= K) y = sc.yp[d];
         atoms_add_carry(lo_s + (((uint32_t)(j - j0) * pl.Yn + y) << 2), hi_off, xlo, xhi);
@@ -568,8 +568,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
     const uint32_t nwarps = (gridDim.x / (uint32_t)nsplit) * (blockDim.x >> 5);
     const int W = pl.W, K = pl.K;
     const uint32_t maskK = pl.Yn - 1;
-    const int ralign = 62 - 2 * (K + W - 1);                               // right-alignment of the window word (last base lowest)
-    const int e2 = 2 * (W - j0 - NC);                                      // then column j0+NC-1 lowest (negative: split reaches past W)
+    const int ralign = 62 - 2 * (K + NC - 1);                              // word = bases p+j0-K ..: column j0+NC-1's last base lowest
     const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh);
     const uint32_t hi_off = nb * 4u, yn4 = pl.Yn * 4u;
     const int nc_valid = min(NC, W - j0);
@@ -587,8 +586,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
                 const uint32_t li = raw.x;
                 const float rv = __uint_as_float(raw.z) * al.scale[li];
                 X = __float2ull_rn(rv * FX_SCALE_F);
-                const unsigned long long u = window_word(pv.words + pv.seqs[pv.seq_ids[li]].word_off, (int)raw.y - K) >> ralign;
-                up = e2 >= 0 ? u >> e2 : u << (-e2);
+                up = window_word(pv.words + pv.seqs[pv.seq_ids[li]].word_off, (int)raw.y + j0 - K) >> ralign;
                 jrel_max = NC;
             }
             if (split_full) scatter_cols<NC, false>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), 0);
@@ -616,8 +614,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
                     scatter_window_slow(sc, pl, lo_s, hi_off, j0, NC, p, X);
                     X = 0ull;
                 } else {
-                    const unsigned long long u = window_word(pv.words + sq.word_off, p - K) >> ralign;
-                    up = e2 >= 0 ? u >> e2 : u << (-e2);
+                    up = window_word(pv.words + sq.word_off, p + j0 - K) >> ralign;
                     jrel_max = min(min(W - 1, L - W - p) - j0, nc_valid - 1);
                 }
             }
@@ -650,14 +647,13 @@ k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float*
     const uint32_t nwarps = (gridDim.x / (uint32_t)nsplit) * (blockDim.x >> 5);
     const int W = pl.W, K = pl.K;
     const uint32_t maskK = pl.Yn - 1;
-    const int ralign = 62 - 2 * (K + W - 1);
-    const int e2 = 2 * (W - j0 - NC);
+    const int ralign = 62 - 2 * (K + NC - 1);
     const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh);
     const uint32_t hi_off = nb * 4u, yn4 = pl.Yn * 4u;
     const int nc_valid = min(NC, W - j0);
     const bool split_full = nc_valid == NC;                                // CTA-uniform
-    const int lane_word = (lane - K) >> 4;                                 // this lane's windows start at bases lane-K + 32*chunk
-    const int sft = 2 * ((lane - K) & 15);
+    const int lane_word = (lane + j0 - K) >> 4;                            // this lane's words start at bases lane+j0-K + 32*chunk
+    const int sft = 2 * ((lane + j0 - K) & 15);
     for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
         const uint32_t n = pv.seq_ids[li];
         const PackedSeq sq = pv.seqs[n];
@@ -681,8 +677,7 @@ k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float*
             rv_next = (p + 32 < LW1) ? __ldcs(rp) : 0.0f;
             unsigned long long X = __float2ull_rn(rv * FX_SCALE_F);
             if (!__any_sync(FULL, X != 0ull)) continue;
-            const unsigned long long u = (((unsigned long long)whi << 32) | wlo) >> ralign;
-            const unsigned long long up = e2 >= 0 ? u >> e2 : u << (-e2);
+            const unsigned long long up = (((unsigned long long)whi << 32) | wlo) >> ralign;
             if ((c >= cn0 && c <= cn1) || c >= ctail || !split_full) {     // windows over the N / truncated windows / partial split
                 if (mid >= 0 && p <= mid + K && p + W - 1 >= mid) {
                     SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = L; sc.mid = mid;

@@ -289,11 +289,13 @@ def test_properties_at_scale(capi):
     assert np.all(np.isfinite(v)) and np.all(v > 0) and np.all(v <= 1.0)   # Motif.h:116 asserts v <= 1 for order 0
 
 
-@pytest.mark.parametrize("A,K,W,packed", [(6, 5, 6, False), (6, 3, 8, False), (4, 6, 8, True), (4, 5, 24, True)])
+@pytest.mark.parametrize("A,K,W,packed", [(6, 5, 6, False), (6, 3, 8, False), (4, 6, 8, True), (4, 5, 24, True),
+                                          (4, 4, 31, True), (4, 2, 32, True), (4, 6, 28, True), (4, 0, 32, True)])
 def test_large_tables_against_oracle(capi, oracle, A, K, W, packed):
     """Orders / alphabets beyond the fixtures: the 6-letter alphabet at order 5 (46 656-row table, 1.1 MB: stays in L2,
     counts through global atomics), order 6 on ACGT (16 384 rows), and a wide order-5 motif whose table forces one
-    column per group — two full iterations against the CPU oracle on seeded random sequences (both strands, with the
+    column per group, and motifs so wide that window + context exceed one 32-base window word (column passes of the
+    E-step, column splits of the M-step, each with its own word alignment) — two full iterations against the CPU oracle on seeded random sequences (both strands, with the
     rand()-patched middle N)."""
     rng = np.random.default_rng(7 + A * 100 + K)
     nseq, L0 = 300, 90
@@ -328,14 +330,18 @@ def test_large_tables_against_oracle(capi, oracle, A, K, W, packed):
         if False else hostmodel.motif_from_sites(sites, A, K, alpha, vbg)
     em = capi.EM(ss, W, K, Kbg)
     em.set_model(v0, vbg, alpha, 0.3)
-    v = v0.copy()
     for it in range(2):
+        # per-iteration parity: the oracle starts every iteration from the model the device holds (a product of up to 32
+        # table entries amplifies last-bit differences of the previous iteration's model beyond the per-iteration tolerance)
+        v = em.model()
         s = oracle.linear_s(v, vbg, A, K, Kbg, W)
         r_ref, llh_ref = oracle.estep(kmer, offsets, A, K, W, s, 0.3)
         n_ref = oracle.mstep(kmer, offsets, A, K, W, r_ref)
         v = oracle.update_v(n_ref, alpha.ravel(), vbg, A, K, W, v)
         llh = em.estep()
-        assert abs(llh - llh_ref) <= RTOL * abs(llh_ref)
+        # llh is a sum of nseq terms logf(norm_n) of either sign (it nearly cancels for the K=0 case): 1e-5 relative on
+        # the sum plus one fp32 rounding (6e-8 of a norm close to 1) per term
+        assert abs(llh - llh_ref) <= RTOL * abs(llh_ref) + 1e-7 * nseq
         assert_rel(em.r(), r_ref, RTOL, atol=1e-37, what="r it%d" % it)
         em.mstep()
         assert_rel(em.counts(), n_ref, RTOL, atol=1e-9, what="n it%d" % it)
