@@ -28,6 +28,10 @@ SIGNATURES = {
     "bamm_seqset_info": (C.c_int, [_vp, _u64p, _u64p, C.POINTER(C.c_int)]),
     "bamm_seqset_count_kmers": (C.c_int, [_vp, C.c_int, _u64p]),
     "bamm_seqset_destroy": (None, [_vp]),
+    "bamm_seqset_get_codes": (C.c_int, [_vp, _u8p]),
+    "bamm_seqset_get_offsets": (C.c_int, [_vp, _u64p]),
+    "bamm_seqset_sample_negatives": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.POINTER(_vp)]),
+    "bamm_rand_stream": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_int32)]),
     "bamm_em_create": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "bamm_em_set_model": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_float]),
     "bamm_em_estep": (C.c_int, [_vp, _f32p]),
@@ -102,6 +106,13 @@ def device_count():
     return n.value if rc == 0 else 0
 
 
+def rand_stream(seed, first, count):
+    """rand() draws [first, first+count) after srand(seed), re-created on the device (glibc TYPE_3 generator)."""
+    out = np.zeros(int(count), np.int32)
+    _check(load().bamm_rand_stream(int(seed), int(first), int(count), out.ctypes.data_as(C.POINTER(C.c_int32))))
+    return out
+
+
 def kmer_patches(codes, kmer):
     """Positions whose hash depends on rand() draws for a code-0 base (Sequence.cpp:38): every position within
     10 after a 0 code (k-mer hashes span 11 bases) — of the same sequence or not does not matter, a superset is
@@ -130,6 +141,31 @@ class SeqSet:
         self.h = h
         self.nseq = len(self.offsets) - 1
         self.npos = int(self.offsets[-1])
+
+    @classmethod
+    def _adopt(cls, h, A):
+        """Wraps a set created by the library on the device (bamm_seqset_sample_negatives)."""
+        self = cls.__new__(cls)
+        self.h = h
+        self.A = int(A)
+        nseq, npos, a = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        _check(load().bamm_seqset_info(h, C.byref(nseq), C.byref(npos), C.byref(a)))
+        self.nseq, self.npos = int(nseq.value), int(npos.value)
+        self.offsets = np.zeros(self.nseq + 1, np.uint64)
+        _check(load().bamm_seqset_get_offsets(h, _ptr(self.offsets, _u64p)))
+        self.codes = None
+        return self
+
+    def sample_negatives(self, fold, seed=42):
+        """Device-side SeqGenerator::sample_bgseqset_by_fold (bit-identical to the reference's libc rand() stream)."""
+        h = _vp()
+        _check(load().bamm_seqset_sample_negatives(self.h, int(fold), int(seed), C.byref(h)))
+        return SeqSet._adopt(h, self.A)
+
+    def get_codes(self):
+        out = np.zeros(self.npos, np.uint8)
+        _check(load().bamm_seqset_get_codes(self.h, _ptr(out, _u8p)))
+        return out
 
     def index(self, K):
         _check(load().bamm_seqset_index(self.h, K))

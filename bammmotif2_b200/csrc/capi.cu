@@ -3,6 +3,7 @@
 #include "../../include/bamm_b200.h"
 #include "kernels.cuh"
 #include "packed.cuh"
+#include "negatives.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -149,16 +150,15 @@ extern "C" int bamm_device_info(int* sm_count, int* cc_major, int* cc_minor, uin
 }
 
 // ------------------------------------------------------------------------------------------- seqset
-extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets, uint64_t nseq, int A,
-                                  const uint64_t* patch_pos, const uint64_t* patch_kmer, uint64_t npatch,
-                                  bamm_seqset** out) {
+extern "C" void bamm_seqset_destroy(bamm_seqset* s);
+// host bookkeeping + device allocation of codes / offsets (codes are filled by the caller: H2D copy or a device kernel)
+static int seqset_new(const uint64_t* offsets, uint64_t nseq, int A, bamm_seqset** out) {
     REQUIRE(out, "out is NULL");
     *out = nullptr;
-    REQUIRE(codes && offsets, "codes/offsets is NULL");
+    REQUIRE(offsets, "offsets is NULL");
     REQUIRE(A >= 2 && A <= 6, "alphabet size %d not in [2,6]", A);
     REQUIRE(offsets[0] == 0, "offsets[0] must be 0");
     REQUIRE(nseq < (1ull << 32), "too many sequences");
-    REQUIRE(npatch == 0 || (patch_pos && patch_kmer), "patch arrays are NULL");
     uint64_t maxL = 0, minL = ~0ull;
     for (uint64_t n = 0; n < nseq; n++) {
         REQUIRE(offsets[n + 1] >= offsets[n], "offsets not monotone at %llu", (unsigned long long)n);
@@ -167,32 +167,27 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
         if (L < minL) minL = L;
     }
     const uint64_t npos = offsets[nseq];
-    for (uint64_t i = 0; i < npatch; i++) {
-        REQUIRE(patch_pos[i] < npos, "patch position out of range");
-        REQUIRE(i == 0 || patch_pos[i] > patch_pos[i - 1], "patch positions must be strictly increasing");
-    }
     bamm_seqset* s = new (std::nothrow) bamm_seqset();
     if (!s) return fail(BAMM_E_NOMEM, "host allocation failed");
     int dev; cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { delete s; return fail(BAMM_E_CUDA, "no CUDA device: %s", cudaGetErrorString(e)); }
-    s->device = dev; s->A = A; s->nseq = nseq; s->npos = npos; s->npatch = npatch; s->maxL = maxL; s->minL = nseq ? minL : 0;
+    s->device = dev; s->A = A; s->nseq = nseq; s->npos = npos; s->npatch = 0; s->maxL = maxL; s->minL = nseq ? minL : 0;
     s->h_off.assign(offsets, offsets + nseq + 1);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
 #define CUS(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { bamm_seqset_destroy(s); \
     return fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); } } while (0)
     CUS(cudaMalloc(&s->d_codes, npos ? npos : 1));
     CUS(cudaMalloc(&s->d_off, (nseq + 1) * sizeof(uint64_t)));
-    CUS(cudaMemcpy(s->d_codes, codes, npos, cudaMemcpyHostToDevice));
     CUS(cudaMemcpy(s->d_off, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    if (npatch) {
-        CUS(cudaMalloc(&s->d_ppos, npatch * sizeof(uint64_t)));
-        CUS(cudaMalloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
-        CUS(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
-        CUS(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    }
+    *out = s;
+    return BAMM_OK;
+}
+
+// classification + 2-bit packing on the device (no host pass over the bases); d_codes and the patch list are in place
+static int seqset_finish(bamm_seqset* s) {
+    const uint64_t nseq = s->nseq, npatch = s->npatch;
     s->h_kind.assign(nseq, 0);
-    if (A == 4 && nseq) {
-        // classify + pack on the device (no host pass over the bases)
+    if (s->A == 4 && nseq) {
         uint32_t* d_cover = nullptr;
         CUS(cudaMalloc(&s->d_kind, nseq));
         CUS(cudaMalloc(&d_cover, nseq * sizeof(uint32_t)));
@@ -208,7 +203,7 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
         for (uint64_t n = 0; n < nseq; n++) {
             PackedSeq q; q.word_off = 0; q.L = 0; q.mid = 0xffffffffu;
             if (s->h_kind[n]) {
-                const uint64_t L = offsets[n + 1] - offsets[n];
+                const uint64_t L = s->h_off[n + 1] - s->h_off[n];
                 q.word_off = w + 2; q.L = (uint32_t)L; q.mid = s->h_kind[n] == 2 ? (uint32_t)((L - 1) / 2) : 0xffffffffu;
                 w += (L + 15) / 16 + 8;                       // pad pad | data | 6 pads (the E-step prefetches ahead)
                 s->nregular++;
@@ -225,10 +220,36 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
             CUS(cudaDeviceSynchronize());
         }
     }
-#undef CUS
+    return BAMM_OK;
+}
+
+extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets, uint64_t nseq, int A,
+                                  const uint64_t* patch_pos, const uint64_t* patch_kmer, uint64_t npatch,
+                                  bamm_seqset** out) {
+    REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    REQUIRE(codes && offsets, "codes/offsets is NULL");
+    REQUIRE(npatch == 0 || (patch_pos && patch_kmer), "patch arrays are NULL");
+    bamm_seqset* s = nullptr;
+    { int rc = seqset_new(offsets, nseq, A, &s); if (rc) return rc; }
+    const uint64_t npos = s->npos;
+    for (uint64_t i = 0; i < npatch; i++) {
+        if (patch_pos[i] >= npos) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, "patch position out of range"); }
+        if (i && patch_pos[i] <= patch_pos[i - 1]) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, "patch positions must be strictly increasing"); }
+    }
+    s->npatch = npatch;
+    CUS(cudaMemcpy(s->d_codes, codes, npos, cudaMemcpyHostToDevice));
+    if (npatch) {
+        CUS(cudaMalloc(&s->d_ppos, npatch * sizeof(uint64_t)));
+        CUS(cudaMalloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
+        CUS(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CUS(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    { int rc = seqset_finish(s); if (rc) return rc; }
     *out = s;
     return BAMM_OK;
 }
+#undef CUS
 
 extern "C" void bamm_seqset_destroy(bamm_seqset* s) {
     if (!s) return;
@@ -1126,6 +1147,146 @@ extern "C" int bamm_em_peer_attach(bamm_em* em, const void* ipc_handles) {
         em->peer_ptrs.flags[p] = (unsigned int*)(base + slot_bytes);
     }
     em->peer_attached = true;
+    return BAMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------- negative sampling
+// glibc srandom_r(seed) for the TYPE_3 generator: the 31 words u_m = r[3+m] the recurrence starts from, and x^(2^b)
+// modulo its characteristic polynomial (negatives.cuh)
+struct LfgTables { uint32_t u0[LFG_N]; uint32_t pw[LFG_NPOW * LFG_N]; };
+static void lfg_tables(uint32_t seed, LfgTables& t) {
+    int32_t r[34];
+    r[0] = seed ? (int32_t)seed : 1;
+    for (int i = 1; i < 31; i++) {
+        const long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        long w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        r[i] = (int32_t)w;
+    }
+    for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+    for (int m = 0; m < LFG_N; m++) t.u0[m] = (uint32_t)r[3 + m];
+    for (int k = 0; k < LFG_N; k++) t.pw[k] = k == 1 ? 1u : 0u;                     // x
+    for (int b = 1; b < LFG_NPOW; b++) {
+        uint32_t* cur = t.pw + b * LFG_N;
+        memcpy(cur, t.pw + (b - 1) * LFG_N, LFG_N * sizeof(uint32_t));
+        lfg_poly_mul(cur, t.pw + (b - 1) * LFG_N);
+    }
+}
+
+extern "C" int bamm_rand_stream(uint32_t seed, uint64_t first, uint64_t count, int32_t* out) {
+    REQUIRE(out || count == 0, "out is NULL");
+    REQUIRE(first + count + 400 < (1ull << (LFG_NPOW - 1)), "draw index out of range");
+    if (!count) return BAMM_OK;
+    LfgTables t; lfg_tables(seed, t);
+    uint32_t* d_t = nullptr; int* d_out = nullptr;
+    CU(cudaMalloc(&d_t, sizeof(t)));
+    cudaError_t e = cudaMalloc(&d_out, count * sizeof(int));
+    if (e != cudaSuccess) { cudaFree(d_t); return fail(BAMM_E_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    cudaMemcpy(d_t, &t, sizeof(t), cudaMemcpyHostToDevice);
+    const uint64_t threads = std::min<uint64_t>(count, 148ull * 1024ull), per = (count + threads - 1) / threads;
+    k_rand_stream<<<(unsigned)((threads + 127) / 128), 128>>>(d_t, d_t + LFG_N, first, count, per, d_out);
+    e = cudaMemcpy(out, d_out, count * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_t); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(BAMM_E_CUDA, "rand stream kernel failed: %s", cudaGetErrorString(e));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, uint64_t fold, uint32_t seed, bamm_seqset** out) {
+    REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    REQUIRE(pos, "seqset is NULL");
+    REQUIRE(fold >= 1, "fold must be at least 1");
+    REQUIRE(pos->nseq >= 1 && pos->nseq * fold < (1ull << 32), "number of negative sequences out of range");
+    REQUIRE(pos->minL >= 1, "empty template sequence");
+    REQUIRE(pos->npos * fold + 400 < (1ull << (LFG_NPOW - 1)), "too many draws");
+    CU(cudaSetDevice(pos->device));
+    NegDims d; d.A = pos->A; d.Y1 = (uint32_t)pos->A; d.Y2 = d.Y1 * d.Y1; d.Y3 = d.Y2 * d.Y1; d.total = d.Y1 + d.Y2 + d.Y3;
+    IndexArray* ia = nullptr;
+    { std::lock_guard<std::mutex> g(pos->mu); int rc = seqset_index_locked(pos, 2, &ia); if (rc) return rc; }
+    const uint16_t* Y2 = (const uint16_t*)ia->d;
+    const float pc = 20.0f;                                   // SeqGenerator.cpp:30-32: A_[k] = 20 for every order
+    unsigned long long* d_cnt = nullptr; float *d_v = nullptr, *d_rb = nullptr; uint32_t *d_lfg = nullptr, *d_flags = nullptr;
+    bamm_seqset* neg = nullptr;
+    int rc = BAMM_OK;
+#define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
+    {
+        // set-wide frequencies (SeqGenerator::calculate_kmer_frequency, SeqGenerator.cpp:63-112): counts on the device, the
+        // 84 probabilities on the host in the reference's operation order
+        CUX(cudaMalloc(&d_cnt, d.total * sizeof(unsigned long long)));
+        CUX(cudaMemset(d_cnt, 0, d.total * sizeof(unsigned long long)));
+        k_neg_count_set<<<pos->sm_count * 8, 256>>>(Y2, pos->d_off, pos->nseq, d, d_cnt);
+        CUX(cudaGetLastError());
+        std::vector<unsigned long long> cnt(d.total);
+        CUX(cudaMemcpy(cnt.data(), d_cnt, d.total * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        std::vector<float> v(d.total), rb0(d.Y1);
+        const unsigned long long *n0 = cnt.data(), *n1 = n0 + d.Y1, *n2 = n1 + d.Y2;
+        float *v0 = v.data(), *v1 = v0 + d.Y1, *v2 = v1 + d.Y2;
+        size_t normFactor = 0;
+        for (uint32_t y = 0; y < d.Y1; y++) normFactor += n0[y];
+        float sum = 0.0f;
+        for (uint32_t y = 0; y < d.Y1; y++) {
+            v0[y] = ((float)n0[y] + pc * 0.25f) / ((float)normFactor + pc);
+            sum += v0[y];
+            rb0[y] = sum;
+        }
+        for (uint32_t y = 0; y < d.Y2; y++) v1[y] = ((float)n1[y] + pc * v0[y % d.Y1]) / ((float)n0[y / d.Y1] + pc);
+        for (uint32_t y = 0; y < d.Y3; y++) v2[y] = ((float)n2[y] + pc * v1[y % d.Y2]) / ((float)n1[y / d.Y1] + pc);
+        CUX(cudaMalloc(&d_v, (d.total + d.Y1) * sizeof(float)));
+        CUX(cudaMemcpy(d_v, v.data(), d.total * sizeof(float), cudaMemcpyHostToDevice));
+        CUX(cudaMemcpy(d_v + d.total, rb0.data(), d.Y1 * sizeof(float), cudaMemcpyHostToDevice));
+        // per-template bars
+        CUX(cudaMalloc(&d_rb, pos->nseq * (uint64_t)(d.Y2 + d.Y3) * sizeof(float)));
+        k_neg_models<<<pos->sm_count * 16, 128>>>(Y2, pos->d_off, pos->nseq, d, d_v, pc, d_rb);
+        CUX(cudaGetLastError());
+        // the negative set: `fold` records per template, each of the template's stored length
+        const uint64_t nneg = pos->nseq * fold;
+        std::vector<uint64_t> noff(nneg + 1);
+        noff[0] = 0;
+        for (uint64_t i = 0, g = 0; i < pos->nseq; i++) {
+            const uint64_t L = pos->h_off[i + 1] - pos->h_off[i];
+            for (uint64_t m = 0; m < fold; m++, g++) noff[g + 1] = noff[g] + L;
+        }
+        rc = seqset_new(noff.data(), nneg, pos->A, &neg);
+        if (rc) goto done;
+        LfgTables t; lfg_tables(seed, t);
+        CUX(cudaMalloc(&d_lfg, sizeof(t)));
+        CUX(cudaMemcpy(d_lfg, &t, sizeof(t), cudaMemcpyHostToDevice));
+        CUX(cudaMalloc(&d_flags, sizeof(uint32_t)));
+        CUX(cudaMemset(d_flags, 0, sizeof(uint32_t)));
+        const uint64_t want = (uint64_t)pos->sm_count * 2048ull;
+        const uint64_t per = (nneg + want - 1) / want;
+        const uint64_t threads = (nneg + per - 1) / per;
+        k_neg_sample<<<(unsigned)((threads + NEG_THREADS - 1) / NEG_THREADS), NEG_THREADS>>>(pos->d_off, pos->nseq, fold, d, d_v + d.total, d_rb,
+                                                                                          d_lfg, d_lfg + LFG_N, per, neg->d_codes, d_flags);
+        CUX(cudaGetLastError());
+        uint32_t flags = 0;
+        CUX(cudaMemcpy(&flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost));
+        if (flags) {
+            rc = fail(BAMM_E_STATE, "a sampled sequence starts with an undetermined base (draw above the last cumulative bar): "
+                                    "the reference's rand() stream diverges here, use the host sampler for this set");
+            goto done;
+        }
+        rc = seqset_finish(neg);
+        if (rc) { neg = nullptr; goto done; }                  // seqset_finish destroys the set on failure
+    }
+done:
+#undef CUX
+    cudaFree(d_cnt); cudaFree(d_v); cudaFree(d_rb); cudaFree(d_lfg); cudaFree(d_flags);
+    if (rc) { if (neg) bamm_seqset_destroy(neg); return rc; }
+    *out = neg;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_seqset_get_codes(bamm_seqset* s, uint8_t* out) {
+    REQUIRE(s && out, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpy(out, s->d_codes, s->npos, cudaMemcpyDeviceToHost));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_seqset_get_offsets(const bamm_seqset* s, uint64_t* out) {
+    REQUIRE(s && out, "NULL argument");
+    memcpy(out, s->h_off.data(), (s->nseq + 1) * sizeof(uint64_t));
     return BAMM_OK;
 }
 

@@ -17,6 +17,7 @@
 // nothing, and in practice that is 60-95 % of all windows. Surviving (window, value) pairs are compacted into a
 // per-warp queue so that the scatter loop runs with full lanes.
 #pragma once
+#include <type_traits>
 #include "kernels.cuh"
 
 namespace bamm {
@@ -253,12 +254,9 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
     long long llh_fx = 0, rsum_fx = 0;
     const float one_minus_q = 1.0f - gp.q;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    // this lane's windows start at bases lane-KD + 32*chunk: always the same word offset and bit offset in a word
     constexpr int E_UNROLL = BAMM_E_UNROLL;
     // a window can only reach the M-step's threshold r >= 2^-41 if val >= 2^-41 (1-q): norm >= 1-q (margin for rounding)
     const float thr0 = FX_HALF_UNIT * (1.0f - gp.q) * 0.999f;
-    const int lane_word = (lane - KD) >> 4;
-    const int sft = 2 * ((lane - KD) & 15);
     uint32_t c_sh[G], c_mk[G], c_ab[G], c_s2[G];
 #pragma unroll
     for (int g = 0; g < G; g++) {
@@ -278,32 +276,48 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
         const PackedSeq sq = pv.seqs[n];
         const int L = (int)sq.L, LW1 = L - W + 1;
         const int mid = (int)sq.mid;                       // -1 when there is no N
-        // three stream words are kept and two new ones are fetched per chunk of 32 windows
-        const uint32_t* __restrict__ wl = pv.words + sq.word_off + lane_word;
-        uint32_t t0 = wl[0], t1 = wl[1], t2 = wl[2];
+        const uint32_t* __restrict__ wseq = pv.words + sq.word_off;
         float* __restrict__ rn = r + pv.r_off[li];
-        float* __restrict__ rp = rn + (L - W - lane);      // r index of this lane's window; moves down 32 per chunk
         const float pos = gp.q / (float)LW1;
-        const int tail0 = L - 2 * W + 2;                   // first truncated window (p > L-2W+1)
-        // chunk schedule: [0,a1) fast | [a1,b1) over the N | [b1,a2) fast | [a2,nch) truncated tail. Every window of a
-        // fast chunk is a full, untouched window, so the fast loop carries no masks and no bounds checks.
-        const int nch = (LW1 + 31) >> 5;
-        const int a2 = min(nch, max(tail0, 0) >> 5);
-        int a1 = a2, b1 = a2;
-        if (mid >= 0) { a1 = min(a2, max(mid - W + 1, 0) >> 5); b1 = min(a2, ((mid + K) >> 5) + 1); }
+        // windows that need the masked path: [n0,n1) over the N's patched k-mers (clipped to the tail), [tl,LW1) the truncated
+        // tail (p > L-2W+1). Segment schedule [0,b1) fast | [b1,b2) masked | [b2,b3) fast | [b3,LW1) masked; every window of
+        // a fast segment is a full, untouched window. Two candidates: cuts at the exact ranges (fewest masked chunks, but a
+        // partial chunk at the end of each fast segment) or cuts rounded outwards to multiples of 32 (every fast chunk full,
+        // more windows in masked chunks); a masked chunk costs about SLOW_COST fast chunks.
+        const int tl = min(max(L - 2 * W + 2, 0), LW1);
+        int b1 = tl, b2 = tl, b3 = tl;
+        if (mid >= 0) { b1 = min(max(mid - W + 1, 0), tl); b2 = min(mid + K + 1, tl); }
+        {
+            constexpr int SLOW_COST = 4;
+            const int a1 = b1 & ~31, a3 = tl & ~31, a2 = min((b2 + 31) & ~31, a3);
+            const int cost_exact = ((b1 + 31) >> 5) + ((b3 - b2 + 31) >> 5) + SLOW_COST * (((b2 - b1 + 31) >> 5) + ((LW1 - b3 + 31) >> 5));
+            const int cost_align = (a1 >> 5) + ((a3 - a2) >> 5) + SLOW_COST * (((a2 - a1) >> 5) + ((LW1 - a3 + 31) >> 5));
+            if (cost_align <= cost_exact) { b1 = a1; b2 = a2; b3 = a3; }
+        }
         float sum = 0.0f;
-        int c = 0;
 #pragma unroll 1
         for (int seg = 0; seg < 4; seg++) {
-            const int cend = seg == 0 ? a1 : seg == 1 ? b1 : seg == 2 ? a2 : nch;
+            const int p0 = seg == 0 ? 0 : seg == 1 ? b1 : seg == 2 ? b2 : b3;
+            const int pe = seg == 0 ? b1 : seg == 1 ? b2 : seg == 2 ? b3 : LW1;
+            if (p0 >= pe) continue;
+            // this lane's windows start at p0+lane + 32*chunk; its window word starts KD bases earlier. Three stream words are
+            // kept and two new ones are fetched per chunk of 32 windows.
+            const int bb = p0 + lane - KD;
+            const uint32_t* __restrict__ wl = wseq + (bb >> 4);
+            const int sft = 2 * (bb & 15);
+            uint32_t t0 = wl[0], t1 = wl[1], t2 = wl[2];
+            int p = p0 + lane;
+            float* __restrict__ rp = rn + (L - W - p);     // r index of this lane's window; moves down 32 per chunk
             if (!(seg & 1)) {
-#pragma unroll E_UNROLL
-                for (; c < cend; c++) {
+                // fast chunk: G table lookups, no masks; `tail` = the partial last chunk of the segment (lanes p >= pe are off)
+                auto fast_chunk = [&](auto tail_tag) {
+                    constexpr bool TAILC = decltype(tail_tag)::value;
                     const uint32_t whi = __funnelshift_l(t1, t0, sft), wlo = __funnelshift_l(t2, t1, sft);
                     wl += 2;
                     t0 = t2; t1 = wl[1]; t2 = wl[2];
+                    const bool on = !TAILC || p < pe;
                     float prod = 1.0f;
-                    if (MULTI && !first) prod = *rp;            // product over the columns of the earlier passes
+                    if (MULTI && !first && on) prod = *rp;      // product over the columns of the earlier passes
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         uint32_t off;
@@ -311,33 +325,37 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                         else      off = (__funnelshift_rc(wlo, whi, c_sh[g]) >> c_s2[g]) & c_mk[g];
                         prod *= lds_f32(off, c_ab[g]);
                     }
-                    if (MULTI && !last) { *rp = prod; rp -= 32; continue; }
-                    const float val = prod * pos;
-                    *rp = val;
-                    rp -= 32;
-                    sum += val;
-                    if (emit) {
-                        const bool act = val >= thr0;
-                        const uint32_t m = __ballot_sync(FULL, act);
-                        if (m) {
-                            const uint32_t cnt = __popc(m);
-                            if (lpos + bpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
-                            else {
-                                if (act) *reinterpret_cast<uint4*>(lreg + lpos + __popc(m & lt_mask)) = make_uint4(li, (uint32_t)((c << 5) + lane), __float_as_uint(val), 0u);
-                                lpos += cnt;
+                    if (MULTI && !last) { if (on) *rp = prod; }
+                    else {
+                        const float val = on ? prod * pos : 0.0f;
+                        if (on) *rp = val;
+                        sum += val;
+                        if (emit) {
+                            const bool act = val >= thr0;
+                            const uint32_t m = __ballot_sync(FULL, act);
+                            if (m) {
+                                const uint32_t cnt = __popc(m);
+                                if (lpos + bpos + cnt > lcap) { emit = false; *al.overflow = 1u; }
+                                else {
+                                    if (act) *reinterpret_cast<uint4*>(lreg + lpos + __popc(m & lt_mask)) = make_uint4(li, (uint32_t)p, __float_as_uint(val), 0u);
+                                    lpos += cnt;
+                                }
                             }
                         }
                     }
-                }
+                    rp -= 32; p += 32;
+                };
+#pragma unroll E_UNROLL
+                for (int c = (pe - p0) >> 5; c > 0; c--) fast_chunk(std::false_type{});
+                if ((pe - p0) & 31) fast_chunk(std::true_type{});
             } else {
 #pragma unroll 1
-                for (; c < cend; c++) {
-                    const int p = (c << 5) + lane;
+                for (int c = (pe - p0 + 31) >> 5; c > 0; c--) {
                     const uint32_t whi = __funnelshift_l(t1, t0, sft), wlo = __funnelshift_l(t2, t1, sft);
                     wl += 2;
                     t0 = t2; t1 = wl[1]; t2 = wl[2];
                     const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
-                    const int jmax = (p < LW1) ? min(W - 1, L - W - p) : -1;
+                    const int jmax = (p < pe) ? min(W - 1, L - W - p) : -1;
                     const uint32_t valid = (jmax >= 0 ? (jmax >= 31 ? 0xffffffffu : ((2u << jmax) - 1u)) : 0u) & passmask;
                     uint32_t ncols = 0;                     // columns whose k-mer holds a rand() draw of the N
                     const bool over_n = mid >= 0 && p <= mid + K && p + W - 1 >= mid;
@@ -347,7 +365,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                     }
                     uint32_t cols = valid;
                     float prod = 1.0f;
-                    if (MULTI && !first && p < LW1) prod = *rp;
+                    if (MULTI && !first && p < pe) prod = *rp;
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         const uint32_t cm = gp.colmask[g];
@@ -396,7 +414,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                         for (int u = 0; u < 4; u++) prod *= f[u];
                     }
                     float val = 0.0f;
-                    if (p < LW1) {
+                    if (p < pe) {
                         if (MULTI && !last) *rp = prod;
                         else {
                             val = prod * pos;
@@ -404,7 +422,6 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                             sum += val;
                         }
                     }
-                    rp -= 32;
                     if (emit) {
                         const bool act = val >= thr0;
                         const uint32_t m = __ballot_sync(FULL, act);
@@ -417,6 +434,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
                             }
                         }
                     }
+                    rp -= 32; p += 32;
                 }
             }
         }

@@ -367,8 +367,10 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         ss2 = capi.SeqSet(data["codes"].reshape(-1), data["offsets"], A, data["ppos"], data["pkmer"])   # H2D from pinned host memory
+        t1 = time.perf_counter()
         em2 = capi.EM(ss2, wl["W"], wl["K"], wl["K_bg"])                                                 # builds the index on the device
         em2.set_model(v0, vbg, alpha, Q)
+        t2 = time.perf_counter()
         # every iteration ends with a device->host read of its result (log likelihood + sum|dv|), like EM::optimize's loop
         if world > 1:
             em2.set_global_nseq(nseq * world)
@@ -391,6 +393,7 @@ def main():
         vfinal = em2.model()                                                                              # D2H
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        phases = {"seqset_create_s": t1 - t0, "em_create_set_model_s": t2 - t1, "iterations_s": time.perf_counter() - t2}
         if world > 1:
             t = torch.tensor([dt], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -398,7 +401,7 @@ def main():
         h2d = data["codes"].nbytes + data["offsets"].nbytes + data["ppos"].nbytes + data["pkmer"].nbytes + v0.nbytes + vbg.nbytes + alpha.nbytes
         d2h = vfinal.nbytes + 20 * args.steps
         e2e = {"value": bp_total * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-               "d2h_bytes_per_step": d2h / args.steps, "seconds": dt,
+               "d2h_bytes_per_step": d2h / args.steps, "seconds": dt, "phases": phases,
                "what": "bamm_seqset_create (H2D of codes from pinned host memory) + index build + bamm_em_create/set_model + "
                        "%d iterations, each read back (llh, sum|dv|) + bamm_em_get_model (D2H); upload amortised over the %d iterations" % (args.steps, args.steps)}
         em2.close(); ss2.close()

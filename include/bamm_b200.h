@@ -67,6 +67,21 @@ int bamm_seqset_get_index(bamm_seqset* s, int K, uint32_t* out);
 int bamm_seqset_info(const bamm_seqset* s, uint64_t* nseq, uint64_t* npos, int* A);
 /* Background k-mer counts n[k][y] for k<=K over all positions (BackgroundModel.cpp:26-42); out: sum_k A^(k+1). */
 int bamm_seqset_count_kmers(bamm_seqset* s, int K, uint64_t* n_all);
+/* Stored codes / offsets of a set back on the host (npos bytes / nseq+1 entries) - sets created on the device. */
+int bamm_seqset_get_codes(bamm_seqset* s, uint8_t* out);
+int bamm_seqset_get_offsets(const bamm_seqset* s, uint64_t* out);
+/*
+ * Negative (background) set sampled ON THE DEVICE  (replaces SeqGenerator::sample_bgseqset_by_fold with genericNeg = false,
+ * src/seq_generator/SeqGenerator.cpp:63-206, 285-348; called from src/refinement/mainBaMM.cpp:100-116 and FDR):
+ * for every sequence of `pos` (in order) `fold` single-stranded records of the same stored length, drawn from the set-wide
+ * order-2 k-mer model rescaled by the template's own k-mer counts. The bases are BIT-IDENTICAL to the reference's: the
+ * device re-creates the libc rand() stream after srand(seed) (the reference seeds 42, SeqGenerator.cpp:33-34) and jumps to
+ * every record's first draw. Returns BAMM_E_STATE in the (about 1 in 10^7 records) case where the reference's own draw
+ * sequence would diverge from one-draw-per-base; the caller then samples on the host.
+ */
+int bamm_seqset_sample_negatives(bamm_seqset* pos, uint64_t fold, uint32_t seed, bamm_seqset** out);
+/* draws [first, first+count) of rand() after srand(seed), computed on the device (test hook for the generator above) */
+int bamm_rand_stream(uint32_t seed, uint64_t first, uint64_t count, int32_t* out);
 void bamm_seqset_destroy(bamm_seqset* s);
 
 /* ---- EM  (replaces EM::EStep/MStep/optimize/optimize_q, src/refinement/EM.cpp:62-259,505-519) -------------- */

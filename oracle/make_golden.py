@@ -121,10 +121,31 @@ def pwm_case():
              ["--EM", "-k", "1", "-K", "1", "--maxPWM", "2"], r_iters="", keep=keep, init=("--PWMFile",))
 
 
+def neg_cases():
+    """Negative sets only (SeqGenerator::sample_bgseqset_by_fold after srand(42), as mainBaMM.cpp:100-116 calls it): ragged
+    both-strand templates with real N's, the 6-letter alphabet, single-stranded templates. One EM iteration keeps it short."""
+    keep = lambda k: k in ("neg_codes", "neg_offsets", "pos_codes", "pos_offsets", "pos_kmer")
+    tmp = tempfile.mkdtemp(prefix="golden_in_")
+    cases = [
+        ("neg_ragged_N", dict(seed=21, nseq=25, L0=34, W=6, n_frac=0.03, lower=True, ragged=7), ["--EM", "-k", "1", "-K", "1"]),
+        ("neg_ext", dict(seed=22, nseq=20, L0=30, W=6, alphabet="EXTENDED"), ["--EM", "-k", "1", "-K", "1", "--alphabet", "EXTENDED"]),
+        ("neg_ss", dict(seed=23, nseq=28, L0=45, W=6), ["--EM", "-k", "1", "-K", "1", "--ss"]),
+    ]
+    for name, kw, args in cases:
+        seqs, sites = synth(**kw)
+        d = os.path.join(tmp, name)
+        os.makedirs(d)
+        fa, bs = write_inputs(d, seqs, sites)
+        run_case(name, fa, bs, args, r_iters="", max_iter=1, dump_neg=True, keep=keep)
+    shutil.rmtree(tmp)
+
+
 def main():
     subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
     if "--only-pwm" in sys.argv:
         return pwm_case()
+    if "--only-neg" in sys.argv:
+        return neg_cases()
     # config 1: the reference's shipped example
     run_case("jund_k2", os.path.join(REF, "example", "JunD.fasta"), os.path.join(REF, "example", "bindingsites.block"),
              ["--EM", "-k", "2", "-K", "2", "--FDR"], r_iters="1,41",
@@ -147,6 +168,7 @@ def main():
         run_case(name, fa, bs, args, r_iters=r_iters, dump_neg=dump_neg)
     shutil.rmtree(tmp)
     pwm_case()
+    neg_cases()
 
 
 if __name__ == "__main__":

@@ -350,3 +350,39 @@ def test_large_tables_against_oracle(capi, oracle, A, K, W, packed):
     mops, zoops, z = ss.score(W, K, Kbg, v, vbg)
     omops, ozoops, oz = oracle.logodds(kmer, offsets, A, K, W, oracle.log_s(v, vbg, A, K, Kbg, W))
     assert np.array_equal(mops, omops) and np.array_equal(zoops, ozoops) and np.array_equal(z, oz)
+
+
+def test_device_rand_stream_is_libc_rand(capi):
+    """The device re-creation of glibc's rand() (additive lagged-Fibonacci TYPE_3, jump-ahead by polynomial powers) against
+    libc itself: the first draws after srand(42) and a block far into the stream reached by running libc there."""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(42)
+    n_skip, n_take = 300_000, 4000
+    ref = np.array([libc.rand() for _ in range(n_skip + n_take)], np.int32)
+    assert np.array_equal(capi.rand_stream(42, 0, 5000), ref[:5000])
+    assert np.array_equal(capi.rand_stream(42, n_skip, n_take), ref[n_skip:])
+    assert np.array_equal(capi.rand_stream(42, 12345, 77), ref[12345:12345 + 77])
+    libc.srand(7)
+    assert np.array_equal(capi.rand_stream(7, 0, 64), np.array([libc.rand() for _ in range(64)], np.int32))
+
+
+NEG_CASES = ["syn_k3_fdr", "neg_ragged_N", "neg_ext", "neg_ss"]
+
+
+@pytest.mark.parametrize("case", NEG_CASES)
+def test_device_negative_sampling_bit_exact(capi, case):
+    """bamm_seqset_sample_negatives against the negative set the reference itself sampled (SeqGenerator.cpp:188-206 after
+    srand(42)): every base identical."""
+    g = Golden(case)
+    pp, pk = capi.kmer_patches(g["pos_codes"], g["pos_kmer"])
+    ss = capi.SeqSet(g["pos_codes"], g["pos_offsets"], g.A, pp, pk)
+    fold = g.meta["mFold"]
+    neg = ss.sample_negatives(fold)
+    assert np.array_equal(neg.offsets, g["neg_offsets"])
+    assert np.array_equal(neg.get_codes(), g["neg_codes"])
+    # the sampled set is a first-class seqset: its k-mer index equals the reference's hashes of the sampled records
+    if "neg_kmer" in g:
+        K = min(g.K, 3)
+        assert np.array_equal(neg.get_index(K).astype(np.uint64), g["neg_kmer"] % np.uint64(g.A ** (K + 1)))
+    neg.close(); ss.close()
