@@ -58,6 +58,7 @@ SIGNATURES = {
     "bamm_em_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "bamm_em_peer_alloc": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "bamm_em_peer_attach": (C.c_int, [_vp, _vp]),
+    "bamm_score_last_timing": (C.c_int, [_f32p]),
     "bamm_score_logodds": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _u64p, _f32p]),
 }
 
@@ -111,6 +112,12 @@ def rand_stream(seed, first, count):
     out = np.zeros(int(count), np.int32)
     _check(load().bamm_rand_stream(int(seed), int(first), int(count), out.ctypes.data_as(C.POINTER(C.c_int32))))
     return out
+
+
+def score_last_ms():
+    t = C.c_float(0)
+    _check(load().bamm_score_last_timing(C.byref(t)))
+    return float(t.value)
 
 
 def kmer_patches(codes, kmer):
@@ -184,11 +191,13 @@ class SeqSet:
         """ScoreSeqSet::calcLogOdds. Returns (mops|None, zoops, z)."""
         sub = np.ascontiguousarray(subset, np.uint64) if subset is not None else None
         nsub = len(sub) if sub is not None else self.nseq
-        ids = sub.astype(np.int64) if sub is not None else np.arange(self.nseq)
-        L = (self.offsets[1:] - self.offsets[:-1]).astype(np.int64)[ids]
-        zoops = np.zeros(nsub, np.float32)
-        z = np.zeros(nsub, np.uint64)
-        mops = np.zeros(int((L - W + 1).sum()), np.float32) if want_mops else None
+        zoops = np.empty(nsub, np.float32)
+        z = np.empty(nsub, np.uint64)
+        mops = None
+        if want_mops:
+            ids = sub.astype(np.int64) if sub is not None else np.arange(self.nseq)
+            L = (self.offsets[1:] - self.offsets[:-1]).astype(np.int64)[ids]
+            mops = np.zeros(int((L - W + 1).sum()), np.float32)
         v = np.ascontiguousarray(v_all, np.float32)
         vb = np.ascontiguousarray(vbg_all, np.float32)
         _check(load().bamm_score_logodds(self.h, _ptr(sub, _u64p), nsub, W, K, K_bg_model, _ptr(v, _f32p), _ptr(vb, _f32p),

@@ -22,6 +22,7 @@ using namespace bamm;
 
 // ------------------------------------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
+static thread_local float g_score_ms = 0.0f;      // device time of the scoring kernels of the last bamm_score_logodds call on this thread
 static int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
@@ -1313,7 +1314,8 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
         }
     }
     std::vector<uint32_t> gen_ids, gen_out, pk_ids, pk_out;
-    std::vector<uint64_t> moff(nsub + 1, 0);
+    pk_ids.reserve(nsub); pk_out.reserve(nsub);
+    std::vector<uint64_t> moff(mops ? nsub + 1 : 1, 0);      // window offsets of the subset: only the MOPS output needs them
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
     const size_t tb = (size_t)nbin * 4;
@@ -1324,16 +1326,18 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
         REQUIRE(n < s->nseq, "subset index out of range");
         const uint64_t L = s->h_off[n + 1] - s->h_off[n];
         REQUIRE(L >= (uint64_t)W, "sequence %llu is shorter than the motif", (unsigned long long)n);
-        moff[i + 1] = moff[i] + (L - W + 1);
+        if (mops) moff[i + 1] = moff[i] + (L - W + 1);
         if (packed_ok && s->h_kind[n]) { pk_ids.push_back((uint32_t)n); pk_out.push_back((uint32_t)i); }
         else { gen_ids.push_back((uint32_t)n); gen_out.push_back((uint32_t)i); }
     }
+    const bool identity_out = gen_ids.empty();               // every sequence on the packed path: list index == output index
     IndexArray* ia = nullptr;
     uint16_t* d_yp = nullptr;
     if (!gen_ids.empty()) { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
     if (!pk_ids.empty())  { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_ypatch_locked(s, K, &d_yp); if (rc) return rc; }
     CU(cudaSetDevice(s->device));
     cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float *d_s = nullptr, *d_zoops = nullptr, *d_mops = nullptr; unsigned long long* d_z = nullptr;
     uint32_t *d_gids = nullptr, *d_gout = nullptr, *d_pids = nullptr, *d_pout = nullptr; uint64_t* d_moff = nullptr;
     int rc = BAMM_OK;
@@ -1345,23 +1349,25 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
         CUX(cudaMalloc(&d_gids, (gen_ids.size() ? gen_ids.size() : 1) * 4));
         CUX(cudaMalloc(&d_gout, (gen_ids.size() ? gen_ids.size() : 1) * 4));
         CUX(cudaMalloc(&d_pids, (pk_ids.size() ? pk_ids.size() : 1) * 4));
-        CUX(cudaMalloc(&d_pout, (pk_ids.size() ? pk_ids.size() : 1) * 4));
-        CUX(cudaMalloc(&d_moff, (nsub + 1) * 8));
+        CUX(cudaMalloc(&d_pout, (pk_ids.size() && !identity_out ? pk_ids.size() : 1) * 4));
+        CUX(cudaMalloc(&d_moff, moff.size() * 8));
         if (mops) CUX(cudaMalloc(&d_mops, (moff[nsub] ? moff[nsub] : 1) * 4));
         CUX(cudaMemcpyAsync(d_s, slog.data(), (uint64_t)nbin * 4, cudaMemcpyHostToDevice, st));
         CUX(cudaMemcpyAsync(d_gids, gen_ids.data(), gen_ids.size() * 4, cudaMemcpyHostToDevice, st));
         CUX(cudaMemcpyAsync(d_gout, gen_out.data(), gen_out.size() * 4, cudaMemcpyHostToDevice, st));
         CUX(cudaMemcpyAsync(d_pids, pk_ids.data(), pk_ids.size() * 4, cudaMemcpyHostToDevice, st));
-        CUX(cudaMemcpyAsync(d_pout, pk_out.data(), pk_out.size() * 4, cudaMemcpyHostToDevice, st));
-        CUX(cudaMemcpyAsync(d_moff, moff.data(), (nsub + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (!identity_out) CUX(cudaMemcpyAsync(d_pout, pk_out.data(), pk_out.size() * 4, cudaMemcpyHostToDevice, st));
+        CUX(cudaMemcpyAsync(d_moff, moff.data(), moff.size() * 8, cudaMemcpyHostToDevice, st));
         int per_sm = smem ? (int)((size_t)(max_optin + 1024) / (tb + 1024)) : 4;
         if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
         const int grid = s->sm_count * per_sm;
+        CUX(cudaEventCreate(&ev0)); CUX(cudaEventCreate(&ev1));
+        CUX(cudaEventRecord(ev0, st));
         if (!pk_ids.empty()) {
             PackedView pv; pv.words = s->d_words; pv.seqs = s->d_pseq; pv.ypatch = d_yp; pv.seq_ids = d_pids; pv.r_off = nullptr; pv.nlist = (uint32_t)pk_ids.size();
             Plan pl; pl.W = W; pl.K = K; pl.T = 1; pl.C = W; pl.Yn = Yn; pl.Zn = Yn; pl.q = 0.f;
             CUX(cudaFuncSetAttribute(k_score_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
-            k_score_packed<<<grid, 512, tb, st>>>(pv, pl, d_moff, d_s, d_zoops, d_z, d_mops, d_pout);
+            k_score_packed<<<grid, 512, tb, st>>>(pv, pl, d_moff, d_s, d_zoops, d_z, d_mops, identity_out ? nullptr : d_pout);
             CUX(cudaGetLastError());
         }
         if (!gen_ids.empty()) {
@@ -1377,14 +1383,24 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
             }
             CUX(cudaGetLastError());
         }
+        CUX(cudaEventRecord(ev1, st));
         CUX(cudaMemcpyAsync(zoops, d_zoops, nsub * 4, cudaMemcpyDeviceToHost, st));
         CUX(cudaMemcpyAsync(z, d_z, nsub * 8, cudaMemcpyDeviceToHost, st));
         if (mops) CUX(cudaMemcpyAsync(mops, d_mops, moff[nsub] * 4, cudaMemcpyDeviceToHost, st));
         CUX(cudaStreamSynchronize(st));
+        CUX(cudaEventElapsedTime(&g_score_ms, ev0, ev1));
     }
 done:
 #undef CUX
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
     cudaFree(d_s); cudaFree(d_zoops); cudaFree(d_z); cudaFree(d_gids); cudaFree(d_gout); cudaFree(d_pids); cudaFree(d_pout); cudaFree(d_moff); cudaFree(d_mops);
     cudaStreamDestroy(st);
     return rc;
+}
+
+extern "C" int bamm_score_last_timing(float* kernel_ms) {
+    REQUIRE(kernel_ms, "NULL argument");
+    *kernel_ms = g_score_ms;
+    return BAMM_OK;
 }

@@ -729,7 +729,7 @@ k_score_packed(PackedView pv, Plan pl, const uint64_t* __restrict__ mops_off, co
     const uint32_t maskK = pl.Yn - 1;
     for (uint32_t li = warp; li < pv.nlist; li += nwarps) {
         const uint32_t n = pv.seq_ids[li];
-        const uint32_t oi = out_idx[li];                   // position of this sequence in the caller's subset
+        const uint32_t oi = out_idx ? out_idx[li] : li;    // position of this sequence in the caller's subset
         const PackedSeq sq = pv.seqs[n];
         const int L = (int)sq.L, LW1 = L - W + 1, mid = (int)sq.mid;
         const uint32_t* __restrict__ wd = pv.words + sq.word_off;

@@ -98,6 +98,34 @@ SequenceSet::SequenceSet( std::vector<uint8_t> storedCodes, std::vector<uint64_t
     finalize();
 }
 
+SequenceSet::SequenceSet( DeviceBuilt, bamm_seqset* deviceSet, std::string header ) : sharedHeader_( std::move( header ) ){
+    for( size_t k = 0; k < 12; k++ ) Y_.push_back( ipow( Alphabet::getSize(), k ) );
+    uint64_t nseq = 0, npos = 0; int A = 0;
+    BAMM_CHECK( bamm_seqset_info( deviceSet, &nseq, &npos, &A ) );
+    offsets_.assign( nseq + 1, 0 );
+    BAMM_CHECK( bamm_seqset_get_offsets( deviceSet, offsets_.data() ) );
+    size_t maxL = 0, minL = std::numeric_limits<size_t>::max();
+    for( size_t n = 0; n < nseq; n++ ){
+        const size_t L = static_cast<size_t>( offsets_[n + 1] - offsets_[n] );
+        maxL = std::max( maxL, L );
+        minL = std::min( minL, L );
+    }
+    minL_ = minL;
+    maxL_ = maxL;
+    baseFrequencies_.assign( Alphabet::getSize(), 0.0f );
+    device_ = deviceSet;
+    codesOnDevice_ = true;
+    finalize();
+}
+
+void SequenceSet::fetchCodes(){
+    std::lock_guard<std::mutex> guard( codesMutex_ );
+    if( !codesOnDevice_ ) return;
+    codes_.resize( static_cast<size_t>( offsets_.back() ) );
+    BAMM_CHECK( bamm_seqset_get_codes( device_, codes_.data() ) );
+    codesOnDevice_ = false;
+}
+
 SequenceSet::SequenceSet( Build, std::string header ) : sharedHeader_( std::move( header ) ){
     for( size_t k = 0; k < 12; k++ ) Y_.push_back( ipow( Alphabet::getSize(), k ) );
     offsets_.push_back( 0 );
@@ -182,7 +210,8 @@ std::vector<Sequence*> SequenceSet::getSequences(){
     return out;
 }
 
-size_t SequenceSet::kmerAt( size_t n, size_t i ) const {
+size_t SequenceSet::kmerAt( size_t n, size_t i ){
+    ensureCodes();
     const uint64_t g = offsets_[n] + i;
     auto it = std::lower_bound( patchPos_.begin(), patchPos_.end(), g );
     if( it != patchPos_.end() && *it == g ) return static_cast<size_t>( patchKmer_[it - patchPos_.begin()] );
@@ -195,6 +224,7 @@ size_t SequenceSet::kmerAt( size_t n, size_t i ) const {
 
 size_t* SequenceSet::kmersOf( size_t n ){
     std::call_once( kmersOnce_, [this](){
+        ensureCodes();
         kmers_.assign( codes_.size(), 0 );
         for( size_t s = 0; s + 1 < offsets_.size(); s++ ){
             const uint8_t* c = codes_.data() + offsets_[s];

@@ -32,7 +32,7 @@ public:
     size_t          getL() const;           // stored length: 2*L0+1 on both strands
     std::string     getHeader() const;
     size_t*         getKmer();              // reference kmer_ (11-mer hash per position); materialised on first use
-    size_t          kmerAt( size_t i ) const;   // same value for one position, without materialising the array
+    size_t          kmerAt( size_t i );         // same value for one position, without materialising the array
 
     float           getIntensity() const    { return intensity_; }
     float           getWeight() const       { return weight_; }
@@ -60,6 +60,10 @@ public:
     // made right after each record, like the reference's Sequence constructor does
     struct Build {};
     SequenceSet( Build, std::string header );
+    // adopts a set that was CREATED ON THE DEVICE (bamm_seqset_sample_negatives): offsets come back now, the stored codes only
+    // if a host-side consumer asks for them (getSequence(), codes(), getKmer())
+    struct DeviceBuilt {};
+    SequenceSet( DeviceBuilt, bamm_seqset* deviceSet, std::string header );
     void appendStoredRecord( const uint8_t* storedCodes, size_t L );
     void finishBuild();
     ~SequenceSet();
@@ -76,12 +80,12 @@ public:
 
     // ---- arena access (host wrappers, tests) ----
     size_t                  size() const            { return offsets_.size() - 1; }
-    const std::vector<uint8_t>&  codes() const      { return codes_; }
+    const std::vector<uint8_t>&  codes()            { ensureCodes(); return codes_; }
     const std::vector<uint64_t>& offsets() const    { return offsets_; }
     const std::vector<uint64_t>& patchPositions() const { return patchPos_; }
     const std::vector<uint64_t>& patchKmers() const { return patchKmer_; }
     const std::string&      headerOf( size_t n ) const { return headers_.empty() ? sharedHeader_ : headers_[n]; }
-    size_t                  kmerAt( size_t n, size_t i ) const;   // reference kmer_[i] of sequence n
+    size_t                  kmerAt( size_t n, size_t i );         // reference kmer_[i] of sequence n
     size_t*                 kmersOf( size_t n );    // materialises the whole set's kmer_ on first call
 
     // the set resident in HBM (created on first use; shared by every EM / ScoreSeqSet / BackgroundModel that uses it)
@@ -96,6 +100,8 @@ private:
                                           std::vector<size_t>& baseCounts );
     void                    drawPatches( uint64_t begin, uint64_t end );
     void                    finalize();
+    void                    ensureCodes()           { if( codesOnDevice_ ) fetchCodes(); }
+    void                    fetchCodes();           // device-built set: stored codes device -> host, once
 
     std::string             sequenceFilepath_;
     std::string             intensityFilepath_;
@@ -111,13 +117,15 @@ private:
     std::vector<size_t>     kmers_;                 // lazily materialised reference kmer_ for all positions
     std::once_flag          kmersOnce_;
     bamm_seqset*            device_ = nullptr;
+    bool                    codesOnDevice_ = false; // device-built set whose codes_ has not been fetched yet
+    std::mutex              codesMutex_;
     std::mutex              deviceMutex_;
 };
 
-inline uint8_t*     Sequence::getSequence()     { return const_cast<uint8_t*>( set_->codes_.data() ) + set_->offsets_[index_]; }
+inline uint8_t*     Sequence::getSequence()     { set_->ensureCodes(); return const_cast<uint8_t*>( set_->codes_.data() ) + set_->offsets_[index_]; }
 inline size_t       Sequence::getL() const      { return static_cast<size_t>( set_->offsets_[index_ + 1] - set_->offsets_[index_] ); }
 inline std::string  Sequence::getHeader() const { return set_->headerOf( index_ ); }
 inline size_t*      Sequence::getKmer()         { return set_->kmersOf( index_ ); }
-inline size_t       Sequence::kmerAt( size_t i ) const { return set_->kmerAt( index_, i ); }
+inline size_t       Sequence::kmerAt( size_t i )  { return set_->kmerAt( index_, i ); }
 
 #endif

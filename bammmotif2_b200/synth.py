@@ -12,6 +12,9 @@ WORKLOADS = {
     # name: nseq, L0, W, K (motif order), K_bg (background order)   -- BASELINE.json configs[1], configs[2]
     "c2": dict(nseq=50_000, L0=200, W=12, K=2, K_bg=2, desc="synthetic 50k x 200 bp, planted W=12, order-2 motif / order-2 background"),
     "c3": dict(nseq=1_000_000, L0=500, W=20, K=4, K_bg=2, desc="synthetic 1M x 500 bp, order-4 motif W=20, both strands"),
+    # BASELINE.json configs[3]: --FDR, 5 folds, mFold=10 sampled negatives, order 3; one "step" scores one fold's test set
+    "c4": dict(nseq=1_000_000, L0=500, W=12, K=3, K_bg=2, mfold=10, cvfold=5,
+               desc="synthetic 1M x 500 bp positives, 10x sampled negatives (device), order-3 W=12, one fold of 5-fold FDR scoring (ZOOPS)"),
     "tiny": dict(nseq=2_000, L0=100, W=10, K=2, K_bg=2, desc="smoke-sized planted-motif set"),
 }
 

@@ -226,9 +226,161 @@ def run_reference_arm(args, wl, rank):
     print(json.dumps(line), flush=True)
 
 
+# ---- config 4: the FDR data path (negative sampling + scoring) -------------------------------------------------------
+C4_METRIC = "FDR scoring sequences/s (order-3, ZOOPS, one cross-validation fold)"
+C4_UNIT = "sequences/s"
+
+
+def c4_reference(wl, sample_nseq, seed, steps, warmup):
+    """The reference's own negative sampling + ScoreSeqSet::calcLogOdds (serial in the reference, ScoreSeqSet.cpp:40) on a
+    bounded sample of the positives with the same mFold (oracle/_ref/ref_time, BAMM_TIME_MODE=fdr)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_time")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/ref_time is not built")
+    fwd, sites, _ = synth.planted_sequences(seed, sample_nseq, wl["L0"], wl["W"])
+    tmp = tempfile.mkdtemp(prefix="bamm_cpu_")
+    fa, bs = os.path.join(tmp, "s.fasta"), os.path.join(tmp, "sites.block")
+    synth.write_fasta(fa, fwd)
+    synth.write_sites(bs, sites)
+    env = dict(os.environ, BAMM_TIME_ITERS=str(steps), BAMM_TIME_WARMUP=str(warmup), BAMM_TIME_MODE="fdr", OMP_NUM_THREADS="1")
+    cmd = [exe, tmp, fa, "--bindingSiteFile", bs, "--EM", "-k", str(wl["K"]), "-K", str(wl["K_bg"]), "-m", str(wl["mfold"]), "--threads", "1"]
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    res = json.loads(out.strip().splitlines()[-1])
+    nseq_scored = res["npos_seq"] + res["nneg_seq"]
+    per = res["per_iter_s"]
+    return dict(kind="reference", cores=1, value=nseq_scored * len(per) / sum(per), per_iter_s=per,
+                positions_per_s=res["positions_scored"] * len(per) / sum(per),
+                neg_bases_per_s=(res["positions_scored"] - res["npos_seq"] * (2 * wl["L0"] + 1)) / res["sample_neg_s"],
+                sample="%d x %d bp positives + %d sampled negatives (mFold %d; the reference raises mFold for sets below 5000 "
+                       "sequences, mainBaMM.cpp:102-106), W=%d K=%d, calcLogOdds of all of them, %d timed passes, 1 thread "
+                       "(the reference scores serially)" % (res["npos_seq"], wl["L0"], res["nneg_seq"], res["mfold"], wl["W"], wl["K"], len(per)))
+
+
+def run_c4(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_sample = args.cpu_sample or 2_000
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        t0 = time.perf_counter()
+        res = c4_reference(wl, cpu_sample, args.seed, args.steps, max(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": C4_METRIC, "value": res["value"], "unit": C4_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(res["per_iter_s"]) / len(res["per_iter_s"]), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "W": wl["W"], "K": wl["K"], "K_bg": wl["K_bg"], "positions_scored_per_s": res["positions_per_s"],
+                       "negative_bases_sampled_per_s": res["neg_bases_per_s"]},
+            "cpu_baseline": {"value": res["value"], "unit": C4_UNIT, "cores": 1, "kind": "reference", "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": C4_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}), flush=True)
+        return 0
+    import torch
+    import torch.distributed as dist
+    from bammmotif2_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    capi._check(capi.load().bamm_set_device(local_rank))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    nseq = args.nseq or wl["nseq"]
+    A, W, K, Kbg, mfold, cv = 4, wl["W"], wl["K"], wl["K_bg"], wl["mfold"], wl["cvfold"]
+    data = make_data(wl, nseq, args.seed + 1000 * rank, pinned=True, motif_seed=args.seed if world > 1 else None)
+    L = data["L"]
+    ss = capi.SeqSet(data["codes"].reshape(-1), data["offsets"], A, data["ppos"], data["pkmer"])
+    v0, vbg, alpha = initial_model(capi, ss, wl, data["sites"], None)
+    em = capi.EM(ss, W, K, Kbg)
+    em.set_model(v0, vbg, alpha, Q)
+    em.iterate(3)                                       # a few EM iterations: the model a fold would score with
+    v = em.model()
+    em.close()
+    # negative set on the device (bit-identical to the reference's host sampler)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    neg = ss.sample_negatives(mfold)
+    torch.cuda.synchronize()
+    t_neg = time.perf_counter() - t0
+    # one fold: its share of the positives (FDR.cpp:49-57) and every cv-th negative (FDR.cpp:58-60)
+    n_fold = nseq // cv
+    pos_sub = np.arange(0, n_fold, dtype=np.uint64)
+    neg_sub = np.arange(0, neg.nseq, cv, dtype=np.uint64)
+    nscored = len(pos_sub) + len(neg_sub)
+    positions = nscored * L
+    launches = 0
+
+    def step():
+        nonlocal launches
+        _, zp, _ = ss.score(W, K, Kbg, v, vbg, subset=pos_sub, want_mops=False)
+        k1 = capi.score_last_ms()
+        _, zn, _ = neg.score(W, K, Kbg, v, vbg, subset=neg_sub, want_mops=False)
+        launches += 2
+        return k1 + capi.score_last_ms(), zp, zn
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    kernel_ms, t0 = 0.0, time.perf_counter()
+    for _ in range(args.steps):
+        ms, zp, zn = step()
+        kernel_ms += ms
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([kernel_ms, wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kernel_ms, wall = float(t[0].item()), float(t[1].item())
+    peak, peak_src = peaks()
+    value = nscored * world * args.steps / (kernel_ms * 1e-3)
+    e2e_value = nscored * world * args.steps / wall
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            res = c4_reference(wl, cpu_sample, args.seed, 2, 1)
+            cpu = {"value": res["value"], "unit": C4_UNIT, "cores": 1, "kind": "reference", "sample": res["sample"],
+                   "positions_scored_per_s": res["positions_per_s"], "negative_bases_sampled_per_s": res["neg_bases_per_s"]}
+        except Exception as ex:   # noqa: BLE001
+            cpu = {"value": None, "unit": C4_UNIT, "cores": 1, "kind": "unavailable", "sample": str(ex)[:200]}
+    if rank == 0:
+        alg = 2.0 * positions                                  # SURVEY.md §8d: ZOOPS-only scoring reads the 2 B index per position
+        ach = alg / (kernel_ms / args.steps * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": C4_METRIC, "value": value, "unit": C4_UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "positives_per_gpu": nseq, "negatives_per_gpu": neg.nseq, "L_stored": L, "W": W, "K": K, "K_bg": Kbg,
+                       "mfold": mfold, "cvfold": cv, "sequences_scored_per_step": nscored, "positions_scored_per_s": positions * world * args.steps / (kernel_ms * 1e-3),
+                       "negative_sampling": {"seconds": t_neg, "bases_per_s": neg.npos / t_neg,
+                                             "what": "bamm_seqset_sample_negatives: k-mer counts, per-template models, rand() jump-ahead, sampling, classification + 2-bit packing"},
+                       "l2": "inputs (%.1f GB packed bases per step) exceed the 126 MB L2" % (positions / 4 / 1e9), "seed": args.seed,
+                       "step": "bamm_score_logodds of one fold's test positives + every %d-th negative (ZOOPS max + argmax per sequence)" % cv},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": C4_UNIT, "h2d_bytes_per_step": int(8 * nscored + 4 * (len(v) + len(vbg))),
+                    "d2h_bytes_per_step": int(12 * nscored), "seconds": wall,
+                    "what": "the same calls timed on the host clock: subset ids + model H2D, table build, kernels, ZOOPS scores + argmax D2H"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_score_packed", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "note": "W shared-memory lookups per window bound this kernel, not HBM (the scores must be bit-identical sums in ascending j)"},
+            "cpu_baseline": cpu}), flush=True)
+    neg.close(); ss.close()
+    return 0
+
+
 def main():
     args = parse_args()
     wl = dict(synth.WORKLOADS[args.workload], name=args.workload)
+    if args.workload == "c4":
+        return run_c4(args, wl)
     wl["cpu_sample"] = {"c3": 40_000, "c2": 50_000, "tiny": 2_000}[args.workload]
     if args.K >= 0 or args.W or args.L0:              # sweep variants are labelled as such: not a BASELINE.json config
         if args.K >= 0: wl["K"] = args.K; wl["K_bg"] = min(wl["K_bg"], args.K)

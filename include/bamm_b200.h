@@ -166,6 +166,9 @@ int bamm_em_stream(bamm_em* em, void** stream);
 int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
                        const float* v_all, const float* vbg_all, float* zoops, uint64_t* z, float* mops);
 
+/* device time (CUDA events on the scoring stream) of the scoring kernels of the last bamm_score_logodds call of this thread */
+int bamm_score_last_timing(float* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

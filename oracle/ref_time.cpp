@@ -36,6 +36,8 @@
 #define private public
 #include "refinement/Global.h"
 #include "refinement/EM.h"
+#include "seq_scoring/ScoreSeqSet.h"
+#include "seq_generator/SeqGenerator.h"
 #undef private
 
 int main(int nargs, char* args[]) {
@@ -59,6 +61,38 @@ int main(int nargs, char* args[]) {
         size_t L = posSet[n]->getL();
         positions += L;
         bp += Global::ss ? L : (L - 1) / 2;
+    }
+    // BAMM_TIME_MODE=fdr: the FDR data path of config 4 instead of EM — negative-set sampling (SeqGenerator.cpp:188-206) and
+    // ScoreSeqSet::calcLogOdds (ScoreSeqSet.cpp:25-67) on positives + sampled negatives, timed separately
+    if (getenv("BAMM_TIME_MODE") && !strcmp(getenv("BAMM_TIME_MODE"), "fdr")) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        SeqGenerator negseq(posSet, NULL, Global::sOrder, 1.0f, Global::genericNeg);
+        std::vector<std::unique_ptr<Sequence>> negSeqs = negseq.sample_bgseqset_by_fold(Global::mFold);
+        auto t1 = std::chrono::high_resolution_clock::now();
+        std::vector<Sequence*> all(posSet);
+        size_t npos_scored = 0;
+        for (size_t n = 0; n < negSeqs.size(); n++) all.push_back(negSeqs[n].get());
+        for (size_t n = 0; n < all.size(); n++) npos_scored += all[n]->getL();
+        double ts = 0;
+        std::vector<double> per;
+        for (int i = 0; i < warm + iters; i++) {
+            ScoreSeqSet sc(motif, bgModel, all);
+            auto a = std::chrono::high_resolution_clock::now();
+            sc.calcLogOdds();
+            auto b = std::chrono::high_resolution_clock::now();
+            if (i >= warm) { per.push_back(std::chrono::duration<double>(b - a).count()); ts += per.back(); }
+        }
+        fflush(stdout);
+        dup2(saved, 1);
+        FILE* out = fdopen(saved, "w");
+        fprintf(out, "{\"mode\": \"fdr\", \"iters\": %d, \"threads\": %zu, \"npos_seq\": %zu, \"nneg_seq\": %zu, \"mfold\": %zu, "
+                     "\"positions_scored\": %zu, \"W\": %zu, \"K\": %zu, \"sample_neg_s\": %.6f, \"score_s\": %.6f, \"per_iter_s\": [",
+                iters, Global::threads, posSet.size(), negSeqs.size(), Global::mFold, npos_scored, motif->getW(), motif->getK(),
+                std::chrono::duration<double>(t1 - t0).count(), ts);
+        for (size_t i = 0; i < per.size(); i++) fprintf(out, "%s%.6f", i ? ", " : "", per[i]);
+        fprintf(out, "]}\n");
+        fflush(out);
+        return 0;
     }
     EM model(motif, bgModel, posSet, false, false, Global::f);
     for (int i = 0; i < warm; i++) { model.EStep(); model.MStep(); }

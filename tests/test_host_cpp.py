@@ -80,6 +80,19 @@ def test_pwm_initialisation_bit_exact(bins, tmp_path):
 
 
 def test_negative_sampling_bit_exact(bins, tmp_path):
+    """The serial host sampler (kept as the fall-back of the device sampler, SeqGenerator.cpp of the host side)."""
+    g = Golden("syn_k3_fdr")
+    fa, _ = write_inputs(g, str(tmp_path))
+    run([os.path.join(bins, "host_check"), "neg", "STANDARD", fa, "0", str(g.meta["mFold"]), "2", str(tmp_path)],
+        env=dict(os.environ, BAMM_HOST_NEGATIVES="1"))
+    assert np.array_equal(np.fromfile(tmp_path / "neg_codes.u8", np.uint8), g["neg_codes"])
+    assert np.array_equal(np.fromfile(tmp_path / "neg_offsets.u64", np.uint64), g["neg_offsets"])
+
+
+@pytest.mark.gpu
+def test_negative_sampling_device_path_bit_exact(bins, tmp_path):
+    """The same call through the host classes with the device sampler (SeqGenerator -> bamm_seqset_sample_negatives ->
+    device-built SequenceSet whose codes come back lazily)."""
     g = Golden("syn_k3_fdr")
     fa, _ = write_inputs(g, str(tmp_path))
     run([os.path.join(bins, "host_check"), "neg", "STANDARD", fa, "0", str(g.meta["mFold"]), "2", str(tmp_path)])
