@@ -15,6 +15,6 @@ echo "== ncu launch list"
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_launches_bench.log 2>&1
 echo "== ncu full (E-step and M-step, c3)"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_estep_packed|k_mstep_list' -s 2 -c 2 -f -o gpurun_out/${TAG}_prof \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'k_estep_packed|k_mstep_list_w' -s 2 -c 2 -f -o gpurun_out/${TAG}_prof \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_prof_bench.log 2>&1
 ls -la gpurun_out
