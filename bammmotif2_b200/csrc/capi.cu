@@ -31,6 +31,19 @@ static int fail(int code, const char* fmt, ...) {
     return fail(e_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define REQUIRE(cond, ...) do { if (!(cond)) return fail(BAMM_E_INVALID, __VA_ARGS__); } while (0)
 
+// BAMM_TRACE=1: wall-clock phases of the set-up calls on stderr (diagnostics of the end-to-end path)
+#include <chrono>
+struct Trace {
+    bool on; const char* what; std::chrono::steady_clock::time_point t0;
+    explicit Trace(const char* w) : on(getenv("BAMM_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* phase) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bamm trace] %s: %s %.2f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 static uint64_t ipow_u64(uint64_t b, int e) { uint64_t r = 1; while (e-- > 0) r *= b; return r; }
 
 // ------------------------------------------------------------------------------------------- objects
@@ -232,21 +245,27 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
     REQUIRE(codes && offsets, "codes/offsets is NULL");
     REQUIRE(npatch == 0 || (patch_pos && patch_kmer), "patch arrays are NULL");
     bamm_seqset* s = nullptr;
+    Trace tr("seqset_create");
     { int rc = seqset_new(offsets, nseq, A, &s); if (rc) return rc; }
+    tr.mark("host checks + alloc + offsets H2D");
     const uint64_t npos = s->npos;
     for (uint64_t i = 0; i < npatch; i++) {
         if (patch_pos[i] >= npos) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, "patch position out of range"); }
         if (i && patch_pos[i] <= patch_pos[i - 1]) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, "patch positions must be strictly increasing"); }
     }
     s->npatch = npatch;
+    tr.mark("patch list checks");
     CUS(cudaMemcpy(s->d_codes, codes, npos, cudaMemcpyHostToDevice));
+    tr.mark("codes H2D");
     if (npatch) {
         CUS(cudaMalloc(&s->d_ppos, npatch * sizeof(uint64_t)));
         CUS(cudaMalloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
         CUS(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CUS(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
     }
+    tr.mark("patch list H2D");
     { int rc = seqset_finish(s); if (rc) return rc; }
+    tr.mark("classify + pack");
     *out = s;
     return BAMM_OK;
 }
@@ -521,6 +540,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     REQUIRE(s, "seqset is NULL");
     REQUIRE(W >= 1 && W <= 32, "motif width W=%d not in [1,32]", W);
     REQUIRE(K >= 0 && K <= 10 && K_bg_model >= 0 && K_bg_model <= 10, "order out of range");
+    Trace tr("em_create");
     if (!subset) nsub = s->nseq;
     REQUIRE(nsub < (1ull << 32), "subset too large");
     const uint64_t Yn64 = ipow_u64((uint64_t)s->A, K + 1);
@@ -572,6 +592,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     }
     em->rsize = em->h_r_off[nsub];
     em->ngen = (uint32_t)gen_ids.size(); em->npk = (uint32_t)pk_ids.size();
+    tr.mark("subset split (host)");
     IndexArray* ia = nullptr;
     if (em->ngen) { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) { delete em; return rc; } }
     if (em->npk)  { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_ypatch_locked(s, K, &em->d_ypatch); if (rc) { delete em; return rc; } }
@@ -589,8 +610,10 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     CUE(upload(gen_roff.data(), gen_roff.size() * 8, (void**)&em->d_gen_roff));
     CUE(upload(pk_ids.data(), pk_ids.size() * 4, (void**)&em->d_pk_ids));
     CUE(upload(pk_roff.data(), pk_roff.size() * 8, (void**)&em->d_pk_roff));
+    tr.mark("index / ypatch + id uploads");
     CUE(cudaMalloc(&em->d_r, (em->rsize ? em->rsize : 1) * sizeof(float)));
     CUE(cudaMemset(em->d_r, 0, (em->rsize ? em->rsize : 1) * sizeof(float)));   // the packed E-step never touches the tail i >= LW1
+    tr.mark("r alloc + memset");
     CUE(cudaMalloc(&em->d_s, (uint64_t)em->nbin * sizeof(float)));
     CUE(cudaMalloc(&em->d_sT, (uint64_t)em->nbin * sizeof(float)));
     CUE(cudaMalloc(&em->d_v, em->model_size * sizeof(float)));
@@ -666,8 +689,10 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             CUE(cudaMemset(em->d_overflow, 0, 4));
         }
     }
+    tr.mark("model buffers + active list");
     CUE(cudaMalloc(&em->d_part, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long)));
 #undef CUE
+    tr.mark("partials");
     *out = em;
     return BAMM_OK;
 }

@@ -7,15 +7,16 @@
 // window start p the 64-bit word  w = bases p-K .. p-K+31  gives  y(p+j) = (w >> (62-2K-2j)) & (4^(K+1)-1), and the
 // zero pad supplies the implicit leading 'A's of k-mers that start before the sequence does. No index array is read.
 //
-// E-step: tuple tables. T consecutive motif columns are folded into one lookup over the (K+T)-mer z that ends
-// at the tuple's last base:  tab[c][z] = prod_{t<T} s[cT+t][ (z >> 2(T-1-t)) & maskK ],  so a window costs
-// ceil(W/T) shared-memory lookups instead of W. Windows that cannot use tuples (the last W-1 truncated windows,
-// EM.cpp:167, and windows over the N whose k-mers hold rand() draws, Sequence.cpp:38) take an exact slow path
-// over the plain table in global memory.
+// E-step: column groups. Consecutive motif columns are folded into one lookup over the bases they depend on,
+//   tab[g][z] = prod_{j in group g} s[j][ y_j(z) ],  so a window costs G shared-memory lookups instead of W. Windows that
+// cannot use whole groups (the last W-1 truncated windows, EM.cpp:167, and windows over the N whose k-mers hold rand()
+// draws, Sequence.cpp:38) take a masked path that mixes whole groups with single columns of the plain table. When the
+// tables of all W columns do not fit shared memory the kernel runs once per column range ("column passes").
 //
-// M-step: sparse. r is converted to 2^40 fixed point; every window whose r rounds to 0 contributes exactly
-// nothing, and in practice that is 60-95 % of all windows. Surviving (window, value) pairs are compacted into a
-// per-warp queue so that the scatter loop runs with full lanes.
+// M-step: sparse or dense. r is converted to 2^40 fixed point; every window whose r rounds to 0 contributes exactly
+// nothing. The E-step lists the surviving (window, value) pairs per warp; the list kernel scatters them with full
+// lanes. When the posteriors are dense (list overflow) a scan kernel walks r instead. Both use unguarded 32-bit shared
+// atomics on CTA-private low / high tables, optionally split by motif column over the CTAs.
 #pragma once
 #include <type_traits>
 #include "kernels.cuh"
