@@ -249,12 +249,7 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
     { int rc = seqset_new(offsets, nseq, A, &s); if (rc) return rc; }
     tr.mark("host checks + alloc + offsets H2D");
     const uint64_t npos = s->npos;
-    for (uint64_t i = 0; i < npatch; i++) {
-        if (patch_pos[i] >= npos) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, "patch position out of range"); }
-        if (i && patch_pos[i] <= patch_pos[i - 1]) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, "patch positions must be strictly increasing"); }
-    }
     s->npatch = npatch;
-    tr.mark("patch list checks");
     CUS(cudaMemcpy(s->d_codes, codes, npos, cudaMemcpyHostToDevice));
     tr.mark("codes H2D");
     if (npatch) {
@@ -262,8 +257,17 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
         CUS(cudaMalloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
         CUS(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CUS(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        // the list must be strictly increasing and inside the set: checked on the device (11 entries per both-strand sequence)
+        uint32_t* d_bad = nullptr; uint32_t bad = 0;
+        CUS(cudaMalloc(&d_bad, sizeof(uint32_t)));
+        cudaMemset(d_bad, 0, sizeof(uint32_t));
+        k_validate_patches<<<(unsigned)((npatch + 255) / 256), 256>>>(s->d_ppos, npatch, npos, d_bad);
+        cudaError_t ev = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+        cudaFree(d_bad);
+        CUS(ev);
+        if (bad) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, bad & 1u ? "patch position out of range" : "patch positions must be strictly increasing"); }
     }
-    tr.mark("patch list H2D");
+    tr.mark("patch list H2D + checks");
     { int rc = seqset_finish(s); if (rc) return rc; }
     tr.mark("classify + pack");
     *out = s;

@@ -60,6 +60,15 @@ __global__ void k_classify(const uint8_t* __restrict__ codes, const uint64_t* __
     }
 }
 
+// patch list contract of bamm_seqset_create: positions inside the set (bit 0 of *bad otherwise) and strictly increasing (bit 1)
+__global__ void k_validate_patches(const uint64_t* __restrict__ ppos, uint64_t np, uint64_t npos, uint32_t* __restrict__ bad) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const uint64_t p = ppos[i];
+    if (p >= npos) atomicOr(bad, 1u);
+    if (i && p <= ppos[i - 1]) atomicOr(bad, 2u);
+}
+
 // every patch must sit at mid..mid+10 of a kind-2 sequence; anything else makes its sequence irregular.
 // cover[n] counts the patches that landed in the structural region.
 __global__ void k_check_patches(const uint64_t* __restrict__ ppos, uint64_t np, const uint64_t* __restrict__ off,

@@ -140,6 +140,12 @@ def make_data(wl, nseq, seed, pinned=False, motif_seed=None):
         out = torch.empty((nseq, L), dtype=torch.uint8, pin_memory=True).numpy()
     codes = synth.stored_both_strands(fwd, out=out)
     ppos, pkmer = synth.middle_n_patches(codes, seed)
+    if pinned:                                   # every input of the end-to-end path starts in pinned host memory
+        import torch
+        pp = torch.empty(len(ppos), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+        pk = torch.empty(len(pkmer), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+        pp[:] = ppos; pk[:] = pkmer
+        ppos, pkmer = pp, pk
     offsets = np.arange(nseq + 1, dtype=np.uint64) * np.uint64(L)
     return dict(codes=codes, offsets=offsets, ppos=ppos, pkmer=pkmer, sites=sites, fwd=fwd, L=L)
 

@@ -191,6 +191,14 @@ def test_error_paths(capi):
     short = capi.SeqSet(codes, np.array([0, 3, 7], np.uint64), 4)
     with pytest.raises(capi.BammError):
         capi.EM(short, 4, 0, 0)
+    # the patch list must be inside the set and strictly increasing (checked on the device)
+    with pytest.raises(capi.BammError, match="out of range"):
+        capi.SeqSet(codes, np.array([0, 3, 7], np.uint64), 4, np.array([2, 9], np.uint64), np.array([5, 6], np.uint64))
+    with pytest.raises(capi.BammError, match="strictly increasing"):
+        capi.SeqSet(codes, np.array([0, 3, 7], np.uint64), 4, np.array([4, 4], np.uint64), np.array([5, 6], np.uint64))
+    # a negative set needs at least one draw per record
+    with pytest.raises(capi.BammError):
+        short.sample_negatives(0)
     # empty subset is legal and a no-op
     e0 = capi.EM(ss, 7, 0, 0, subset=np.zeros(0, np.uint64))
     e0.set_model(g["m1_v_init"], g["bg_v"], g["m1_alpha"], g.q)
