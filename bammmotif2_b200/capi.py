@@ -187,12 +187,17 @@ class SeqSet:
         _check(load().bamm_seqset_count_kmers(self.h, K, _ptr(out, _u64p)))
         return out
 
-    def score(self, W, K, K_bg_model, v_all, vbg_all, subset=None, want_mops=True):
-        """ScoreSeqSet::calcLogOdds. Returns (mops|None, zoops, z)."""
+    def score(self, W, K, K_bg_model, v_all, vbg_all, subset=None, want_mops=True, out=None):
+        """ScoreSeqSet::calcLogOdds. Returns (mops|None, zoops, z). out: optional (zoops float32[nsub], z uint64[nsub]) buffers
+        to fill (e.g. pinned host memory) instead of fresh arrays."""
         sub = np.ascontiguousarray(subset, np.uint64) if subset is not None else None
         nsub = len(sub) if sub is not None else self.nseq
-        zoops = np.empty(nsub, np.float32)
-        z = np.empty(nsub, np.uint64)
+        if out is not None:
+            zoops, z = out
+            assert zoops.dtype == np.float32 and z.dtype == np.uint64 and len(zoops) == nsub and len(z) == nsub
+        else:
+            zoops = np.empty(nsub, np.float32)
+            z = np.empty(nsub, np.uint64)
         mops = None
         if want_mops:
             ids = sub.astype(np.int64) if sub is not None else np.arange(self.nseq)

@@ -37,6 +37,7 @@ struct Trace {
     bool on; const char* what; std::chrono::steady_clock::time_point t0;
     explicit Trace(const char* w) : on(getenv("BAMM_TRACE") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
     void mark(const char* phase) {
+        if (getenv("BAMM_SYNC_MARKS")) cudaDeviceSynchronize();
         if (!on) return;
         cudaDeviceSynchronize();
         const auto t1 = std::chrono::steady_clock::now();
@@ -706,19 +707,18 @@ static int launch_tuple_table(bamm_em* em) {
     for (size_t i = 0; i < em->gplans.size(); i++) {
         const uint32_t total = em->gplans[i].table_bytes >> 2;
         const uint32_t blocks = (total + 255) / 256;
-        k_make_group_tables<<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(em->d_s, em->gplans[i], (float*)((char*)em->d_tab + i * em->tab_capacity));
+        k_make_group_tables<false><<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(em->d_s, em->gplans[i], (float*)((char*)em->d_tab + i * em->tab_capacity));
         CU(cudaGetLastError());
     }
     return BAMM_OK;
 }
 
 // true when every column j < K of v[K] only depends on the j+1 newest bases (what Motif::updateV produces, Motif.h:126-128)
-static bool leading_columns_are_copies(const bamm_em* em, const float* v_all) {
-    const int K = em->K, W = em->W;
-    const float* vK = v_all + em->dims.voff[K];
+static bool leading_columns_are_copies(const ModelDims& dims, int K, int W, uint32_t Yn, const float* v_all) {
+    const float* vK = v_all + dims.voff[K];
     for (int j = 0; j < K && j < W; j++) {
-        const uint32_t period = em->dims.Y[j + 1];
-        for (uint32_t y = period; y < em->Yn; y++)
+        const uint32_t period = dims.Y[j + 1];
+        for (uint32_t y = period; y < Yn; y++)
             if (vK[(uint64_t)y * W + j] != vK[(uint64_t)(y % period) * W + j]) return false;
     }
     return true;
@@ -729,7 +729,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
     REQUIRE(q > 0.0f && q < 1.0f, "q=%g not in (0,1)", (double)q);
     CU(cudaSetDevice(em->device));
     if (em->npk) {
-        const bool reduced = leading_columns_are_copies(em, v_all) && !getenv("BAMM_NO_REDUCED");
+        const bool reduced = leading_columns_are_copies(em->dims, em->K, em->W, em->Yn, v_all) && !getenv("BAMM_NO_REDUCED");
         if (!plan_passes(em->W, em->K, em->K_bg, reduced, em->tab_capacity, em->gplans, em->gfast))
             return fail(BAMM_E_STATE, "no column-group plan fits shared memory");
         if (em->gplans.size() > em->tab_passes) {
@@ -1321,10 +1321,31 @@ extern "C" int bamm_seqset_get_offsets(const bamm_seqset* s, uint64_t* out) {
 }
 
 // ------------------------------------------------------------------------------------------- scoring
+template <int G, bool FAST>
+static int score_zoops_one(const GroupPlan& gp, int sms, cudaStream_t st, const PackedView& pv, const float* d_tab, const float* d_s, float two_eps,
+                           float* d_zoops, unsigned long long* d_z, const uint32_t* d_out, size_t plain_bytes) {
+    const size_t smem = (size_t)gp.table_bytes + plain_bytes;
+    if (cudaFuncSetAttribute(k_score_zoops_packed<G, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    k_score_zoops_packed<G, FAST><<<sms, 1024, smem, st>>>(pv, gp, d_tab, d_s, two_eps, d_zoops, d_z, d_out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+static int score_zoops_dispatch(const GroupPlan& gp, bool fast, int sms, cudaStream_t st, const PackedView& pv, const float* d_tab, const float* d_s,
+                                float two_eps, float* d_zoops, unsigned long long* d_z, const uint32_t* d_out, size_t plain_bytes) {
+    switch (gp.G) {
+#define BAMM_CASE(g) case g: return fast ? score_zoops_one<g, true>(gp, sms, st, pv, d_tab, d_s, two_eps, d_zoops, d_z, d_out, plain_bytes) \
+                                         : score_zoops_one<g, false>(gp, sms, st, pv, d_tab, d_s, two_eps, d_zoops, d_z, d_out, plain_bytes);
+        BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
+        BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
+#undef BAMM_CASE
+        default: return -1;
+    }
+}
+
 extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
                                   const float* v_all, const float* vbg_all, float* zoops, uint64_t* z, float* mops) {
     REQUIRE(s && v_all && vbg_all && zoops && z, "NULL argument");
     REQUIRE(W >= 1 && W <= 32, "motif width W=%d not in [1,32]", W);
+    Trace tr("score_logodds");
     if (!subset) nsub = s->nseq;
     REQUIRE(K >= 0 && K <= 10, "order K=%d not in [0,10]", K);
     const int K_bg = K_bg_model < K ? K_bg_model : K;
@@ -1350,6 +1371,13 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
     const size_t tb = (size_t)nbin * 4;
     const bool smem = tb <= (size_t)max_optin;
     const bool packed_ok = s->A == 4 && s->nregular > 0 && W + K <= 32 && ia_Yn <= 65536 && smem && !getenv("BAMM_NO_PACKED");
+    if (!mops && packed_ok && s->nregular == s->nseq && s->minL >= (uint64_t)W) {
+        // whole set regular and long enough (e.g. a sampled negative set): no per-sequence look-ups, the subset is the list
+        pk_ids.resize(nsub);
+        uint64_t worst = 0;
+        for (uint64_t i = 0; i < nsub; i++) { const uint64_t n = subset ? subset[i] : i; pk_ids[i] = (uint32_t)n; worst = n > worst ? n : worst; }
+        REQUIRE(nsub == 0 || worst < s->nseq, "subset index out of range");
+    } else
     for (uint64_t i = 0; i < nsub; i++) {
         const uint64_t n = subset ? subset[i] : i;
         REQUIRE(n < s->nseq, "subset index out of range");
@@ -1360,14 +1388,30 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
         else { gen_ids.push_back((uint32_t)n); gen_out.push_back((uint32_t)i); }
     }
     const bool identity_out = gen_ids.empty();               // every sequence on the packed path: list index == output index
+    tr.mark("log table + subset split (host)");
+    // ZOOPS-only calls on the packed path: prune with column-group tables, re-score exactly near the running maximum
+    // (k_score_zoops_packed). eps bounds |cheap - exact|: both are fp32 sums of the same W table entries (|entry| <= S) in
+    // different associations, each within (W-1) * 2^-24 * W * S of the real sum; factor 1.5 for slack.
+    GroupPlan zplan; bool zfast = false, zoops_fast = false; float two_eps = 0.0f;
+    if (!mops && !pk_ids.empty() && !getenv("BAMM_NO_ZOOPS_FAST")) {
+        float S = 0.0f;
+        for (uint32_t i = 0; i < nbin; i++) { const float a = fabsf(slog[i]); if (!(a <= 3.0e38f)) { S = -1.0f; break; } if (a > S) S = a; }
+        const bool reduced = leading_columns_are_copies(d, K, W, Yn, v_all);
+        if (S >= 0.0f && tb + 4096 < (size_t)max_optin &&
+            make_group_plan(W, K, K_bg, reduced, (size_t)max_optin - tb, 0, W, zplan, zfast)) {
+            zoops_fast = true;
+            two_eps = 2.0f * 1.5f * 2.0f * (float)W * (float)W * S * 5.9604645e-8f;
+        }
+    }
     IndexArray* ia = nullptr;
     uint16_t* d_yp = nullptr;
     if (!gen_ids.empty()) { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
     if (!pk_ids.empty())  { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_ypatch_locked(s, K, &d_yp); if (rc) return rc; }
+    tr.mark("plan + index");
     CU(cudaSetDevice(s->device));
     cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float *d_s = nullptr, *d_zoops = nullptr, *d_mops = nullptr; unsigned long long* d_z = nullptr;
+    float *d_s = nullptr, *d_zoops = nullptr, *d_mops = nullptr, *d_ztab = nullptr; unsigned long long* d_z = nullptr;
     uint32_t *d_gids = nullptr, *d_gout = nullptr, *d_pids = nullptr, *d_pout = nullptr; uint64_t* d_moff = nullptr;
     int rc = BAMM_OK;
 #define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
@@ -1391,13 +1435,24 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
         if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
         const int grid = s->sm_count * per_sm;
         CUX(cudaEventCreate(&ev0)); CUX(cudaEventCreate(&ev1));
+        tr.mark("alloc + H2D");
         CUX(cudaEventRecord(ev0, st));
         if (!pk_ids.empty()) {
             PackedView pv; pv.words = s->d_words; pv.seqs = s->d_pseq; pv.ypatch = d_yp; pv.seq_ids = d_pids; pv.r_off = nullptr; pv.nlist = (uint32_t)pk_ids.size();
             Plan pl; pl.W = W; pl.K = K; pl.T = 1; pl.C = W; pl.Yn = Yn; pl.Zn = Yn; pl.q = 0.f;
-            CUX(cudaFuncSetAttribute(k_score_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
-            k_score_packed<<<grid, 512, tb, st>>>(pv, pl, d_moff, d_s, d_zoops, d_z, d_mops, identity_out ? nullptr : d_pout);
-            CUX(cudaGetLastError());
+            if (zoops_fast) {
+                CUX(cudaMalloc(&d_ztab, zplan.table_bytes));
+                const uint32_t total = zplan.table_bytes >> 2, blocks = (total + 255) / 256;
+                k_make_group_tables<true><<<blocks < 1184 ? blocks : 1184, 256, 0, st>>>(d_s, zplan, d_ztab);
+                CUX(cudaGetLastError());
+                if (score_zoops_dispatch(zplan, zfast, s->sm_count, st, pv, d_ztab, d_s, two_eps, d_zoops, d_z, identity_out ? nullptr : d_pout, tb)) {
+                    rc = fail(BAMM_E_CUDA, "ZOOPS scoring launch failed: %s", cudaGetErrorString(cudaGetLastError())); goto done;
+                }
+            } else {
+                CUX(cudaFuncSetAttribute(k_score_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
+                k_score_packed<<<grid, 512, tb, st>>>(pv, pl, d_moff, d_s, d_zoops, d_z, d_mops, identity_out ? nullptr : d_pout);
+                CUX(cudaGetLastError());
+            }
         }
         if (!gen_ids.empty()) {
             SubsetView sv; sv.seq_off = s->d_off; sv.seq_ids = d_gids; sv.r_off = nullptr; sv.nsub = (uint32_t)gen_ids.size();
@@ -1413,16 +1468,19 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
             CUX(cudaGetLastError());
         }
         CUX(cudaEventRecord(ev1, st));
+        tr.mark("kernels");
         CUX(cudaMemcpyAsync(zoops, d_zoops, nsub * 4, cudaMemcpyDeviceToHost, st));
         CUX(cudaMemcpyAsync(z, d_z, nsub * 8, cudaMemcpyDeviceToHost, st));
         if (mops) CUX(cudaMemcpyAsync(mops, d_mops, moff[nsub] * 4, cudaMemcpyDeviceToHost, st));
         CUX(cudaStreamSynchronize(st));
         CUX(cudaEventElapsedTime(&g_score_ms, ev0, ev1));
+        tr.mark("D2H");
     }
 done:
 #undef CUX
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    cudaFree(d_ztab);
     cudaFree(d_s); cudaFree(d_zoops); cudaFree(d_z); cudaFree(d_gids); cudaFree(d_gout); cudaFree(d_pids); cudaFree(d_pout); cudaFree(d_moff); cudaFree(d_mops);
     cudaStreamDestroy(st);
     return rc;

@@ -4,6 +4,8 @@ against (a) the committed golden vectors produced by the reference itself and (b
 Tolerances (BASELINE.json north_star): k-mer indices / site indexing bit-exact; posteriors r, log likelihood and
 model probabilities v within 1e-5 relative per iteration; final model within 1e-4 after the reference's stop rule.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -358,6 +360,40 @@ def test_large_tables_against_oracle(capi, oracle, A, K, W, packed):
     mops, zoops, z = ss.score(W, K, Kbg, v, vbg)
     omops, ozoops, oz = oracle.logodds(kmer, offsets, A, K, W, oracle.log_s(v, vbg, A, K, Kbg, W))
     assert np.array_equal(mops, omops) and np.array_equal(zoops, ozoops) and np.array_equal(z, oz)
+    # ZOOPS-only call: prune-and-verify kernel on the packed path, same bits
+    _, zoops2, z2 = ss.score(W, K, Kbg, v, vbg, want_mops=False)
+    assert np.array_equal(zoops2, ozoops) and np.array_equal(z2, oz)
+
+
+def test_zoops_pruned_scoring_equals_full_scoring_at_scale(capi):
+    """k_score_zoops_packed (column-group bound + exact re-scoring near the running maximum) against the plain kernel on
+    30k x 300 bp with a trained order-3 model, both strands (windows over the N included) and a single-stranded sampled
+    negative set: maxima and first arg-max positions must be bit-identical."""
+    from bammmotif2_b200 import synth, hostmodel
+    nseq, L0, W, K, Kbg, A = 30000, 300, 12, 3, 2, 4
+    fwd, sites, _ = synth.planted_sequences(5, nseq, L0, W)
+    codes = synth.stored_both_strands(fwd)
+    ppos, pkmer = synth.middle_n_patches(codes, 5)
+    offsets = np.arange(nseq + 1, dtype=np.uint64) * np.uint64(codes.shape[1])
+    ss = capi.SeqSet(codes.ravel(), offsets, A, ppos, pkmer)
+    vbg = hostmodel.background_from_counts(ss.count_kmers(Kbg), A, Kbg, hostmodel.default_bg_alpha(Kbg))
+    alpha = hostmodel.default_motif_alpha(K, W)
+    em = capi.EM(ss, W, K, Kbg)
+    em.set_model(hostmodel.motif_from_sites(sites, A, K, alpha, vbg), vbg, alpha, 0.3)
+    em.iterate(5)
+    v = em.model()
+    neg = ss.sample_negatives(2)
+    for sset in (ss, neg):
+        _, zf, pf = sset.score(W, K, Kbg, v, vbg, want_mops=False)
+        os.environ["BAMM_NO_ZOOPS_FAST"] = "1"
+        try:
+            _, zs, ps = sset.score(W, K, Kbg, v, vbg, want_mops=False)
+        finally:
+            del os.environ["BAMM_NO_ZOOPS_FAST"]
+        assert np.array_equal(zf, zs) and np.array_equal(pf, ps)
+        sub = np.arange(0, sset.nseq, 3, dtype=np.uint64)
+        _, zsub, psub = sset.score(W, K, Kbg, v, vbg, subset=sub, want_mops=False)
+        assert np.array_equal(zsub, zf[::3]) and np.array_equal(psub, pf[::3])
 
 
 def test_device_rand_stream_is_libc_rand(capi):
