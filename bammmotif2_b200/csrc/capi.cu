@@ -113,6 +113,7 @@ struct bamm_em {
     uint32_t peer_epoch = 0;
     unsigned int* d_peer_done = nullptr;
     int m_nc = 0, m_nsplit = 1; // packed M-step: columns per CTA and number of column splits (packed.cuh, "column split")
+    MTables m_tab = {1, 0};     // table copies per CTA (orders 0 and 1) and their stride in words
     int grid_pl = 0;            // CTAs of the packed M-step kernels (a multiple of m_nsplit)
     uint32_t *d_act_cnt = nullptr, *d_overflow = nullptr;
     uint64_t* d_reg_off = nullptr;
@@ -664,6 +665,16 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             em->m_nsplit = (W + nc_max - 1) / nc_max;
             em->m_nc = (W + em->m_nsplit - 1) / em->m_nsplit;
             em->grid_pl = std::max(1, sms / em->m_nsplit) * em->m_nsplit;
+            // table copies for tiny tables (same-address atomics serialise): 32 copies at order 0, 8 at order 1
+            {
+                const uint32_t nb = (uint32_t)em->m_nc * em->Yn;
+                uint32_t nrep = em->Yn <= 4 ? 32u : em->Yn <= 16 ? 8u : 1u;
+                if (getenv("BAMM_M_REPLICAS")) nrep = (uint32_t)std::max(1, atoi(getenv("BAMM_M_REPLICAS")));
+                while (nrep & (nrep - 1)) nrep &= nrep - 1;                 // power of two
+                while (nrep > 1 && (size_t)2 * nrep * (((nb + 30) / 32) * 32 + 1) * 4 > (size_t)max_optin) nrep >>= 1;
+                em->m_tab.nrep = nrep;
+                em->m_tab.rstride = nrep > 1 ? ((nb + 30) / 32) * 32 + 1 : nb;
+            }
             // the high table sums at most 257 per sequence and bin (the posteriors of a sequence sum to <= 1)
             if ((uint64_t)em->npk / (uint64_t)(em->grid_pl / em->m_nsplit) >= (1ull << 23)) {
                 fail(BAMM_E_INVALID, "too many sequences for one device"); bamm_em_destroy(em); return BAMM_E_INVALID;
@@ -821,11 +832,11 @@ static int launch_estep(bamm_em* em) {
 // packed M-step kernels: one instantiation per column count of a CTA. mode 0: opt in to the shared memory of both kernels,
 // 1: launch the list kernel, 2: launch the scan kernel (conditional on the list's overflow flag when there is a list)
 template <int NC> static int mstep_w_one(bamm_em* em, const PackedView* pv, const Plan* pl, int mode) {
-    const size_t smem = (size_t)NC * em->Yn * 8;
+    const size_t smem = (size_t)2 * em->m_tab.nrep * em->m_tab.rstride * 4;
     if (mode == 0) return max_smem_optin(k_mstep_list_w<NC>, smem) | max_smem_optin(k_mstep_scan_w<NC>, smem);
-    if (mode == 1) k_mstep_list_w<NC><<<em->grid_pl, 1024, smem, em->stream>>>(*pv, *pl, alist_of(em), em->nregions, em->m_nsplit, em->d_part);
+    if (mode == 1) k_mstep_list_w<NC><<<em->grid_pl, 1024, smem, em->stream>>>(*pv, *pl, alist_of(em), em->nregions, em->m_nsplit, em->m_tab, em->d_part);
     else k_mstep_scan_w<NC><<<em->grid_pl, 1024, smem, em->stream>>>(*pv, *pl, em->d_r, em->r_scaled ? nullptr : em->d_scale,
-                                                                    em->d_act ? em->d_overflow : nullptr, em->m_nsplit, em->d_part);
+                                                                    em->d_act ? em->d_overflow : nullptr, em->m_nsplit, em->m_tab, em->d_part);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 static int mstep_w_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, int mode) {

@@ -571,11 +571,18 @@ __device__ __forceinline__ void scatter_window_slow(const SeqCtx& sc, const Plan
 }
 
 // CTA-private tables -> this CTA's slice of the partial-count array (only the CTA's own columns; the rest stays zero)
-__device__ __forceinline__ void flush_cols(const uint32_t* lo_sh, const uint32_t* hi_sh, uint32_t nb, uint32_t Yn, int j0, int W,
+// Replicas: for tiny tables (orders 0 and 1: 4 or 16 bins per column) most lanes of a warp hit the same few addresses and
+// the atomics serialise; the CTA then keeps nrep copies of both tables (lane l uses copy l % nrep, copies rstride words
+// apart with rstride = 1 mod 32 so that equal bins of different copies fall into different banks) and sums them here.
+struct MTables { uint32_t nrep, rstride; };      // rstride >= NC * Yn
+__device__ __forceinline__ void flush_cols(const uint32_t* lo_sh, MTables mt, uint32_t nb, uint32_t Yn, int j0, int W,
                                            unsigned long long* __restrict__ mypart) {
+    const uint32_t* hi_sh = lo_sh + mt.nrep * mt.rstride;
     const uint32_t lim = (uint32_t)max(0, min((int)(nb / Yn), W - j0)) * Yn;
     for (uint32_t i = threadIdx.x; i < lim; i += blockDim.x) {
-        const unsigned long long v = (unsigned long long)lo_sh[i] + ((unsigned long long)hi_sh[i] << 32);
+        unsigned long long lo = 0, hi = 0;
+        for (uint32_t rp = 0; rp < mt.nrep; rp++) { lo += lo_sh[rp * mt.rstride + i]; hi += hi_sh[rp * mt.rstride + i]; }
+        const unsigned long long v = lo + (hi << 32);
         if (v) mypart[(uint32_t)j0 * Yn + i] = v;
     }
 }
@@ -583,13 +590,12 @@ __device__ __forceinline__ void flush_cols(const uint32_t* lo_sh, const uint32_t
 // M-step from the E-step's active list: every lane scatters one listed window.
 template <int NC>
 __global__ void __launch_bounds__(1024, 1)
-k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsplit, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsplit, MTables mt, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
     extern __shared__ uint32_t smem_u32[];
     if (*al.overflow != 0u) return;                                        // k_mstep_scan_w scans r instead
     const uint32_t nb = (uint32_t)NC * pl.Yn;
     uint32_t* lo_sh = smem_u32;
-    uint32_t* hi_sh = smem_u32 + nb;
-    for (uint32_t i = threadIdx.x; i < 2 * nb; i += blockDim.x) smem_u32[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < 2 * mt.nrep * mt.rstride; i += blockDim.x) smem_u32[i] = 0u;
     __syncthreads();
     const int split = (int)(blockIdx.x % (uint32_t)nsplit), j0 = split * NC;
     const int lane = threadIdx.x & 31;
@@ -598,8 +604,8 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
     const int W = pl.W, K = pl.K;
     const uint32_t maskK = pl.Yn - 1;
     const int ralign = 62 - 2 * (K + NC - 1);                              // word = bases p+j0-K ..: column j0+NC-1's last base lowest
-    const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh);
-    const uint32_t hi_off = nb * 4u, yn4 = pl.Yn * 4u;
+    const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh) + ((uint32_t)lane & (mt.nrep - 1u)) * mt.rstride * 4u;   // this lane's copy
+    const uint32_t hi_off = mt.nrep * mt.rstride * 4u, yn4 = pl.Yn * 4u;
     const int nc_valid = min(NC, W - j0);
     const bool split_full = nc_valid == NC;                                // CTA-uniform
     for (uint32_t rg = warp; rg < nregions; rg += nwarps) {
@@ -652,7 +658,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
         }
     }
     __syncthreads();
-    flush_cols(lo_sh, hi_sh, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
+    flush_cols(lo_sh, mt, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
 }
 
 // M-step from r itself: one warp per sequence, lanes = 32 consecutive window starts, the packed stream is followed with the
@@ -662,13 +668,12 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
 template <int NC>
 __global__ void __launch_bounds__(1024, 1)
 k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float* __restrict__ scale, const uint32_t* __restrict__ only_if,
-               int nsplit, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+               int nsplit, MTables mt, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
     extern __shared__ uint32_t smem_u32[];
     if (only_if != nullptr && *only_if == 0u) return;                      // k_mstep_list_w did the work
     const uint32_t nb = (uint32_t)NC * pl.Yn;
     uint32_t* lo_sh = smem_u32;
-    uint32_t* hi_sh = smem_u32 + nb;
-    for (uint32_t i = threadIdx.x; i < 2 * nb; i += blockDim.x) smem_u32[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < 2 * mt.nrep * mt.rstride; i += blockDim.x) smem_u32[i] = 0u;
     __syncthreads();
     const int split = (int)(blockIdx.x % (uint32_t)nsplit), j0 = split * NC;
     const int lane = threadIdx.x & 31;
@@ -677,8 +682,8 @@ k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float*
     const int W = pl.W, K = pl.K;
     const uint32_t maskK = pl.Yn - 1;
     const int ralign = 62 - 2 * (K + NC - 1);
-    const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh);
-    const uint32_t hi_off = nb * 4u, yn4 = pl.Yn * 4u;
+    const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh) + ((uint32_t)lane & (mt.nrep - 1u)) * mt.rstride * 4u;   // this lane's copy
+    const uint32_t hi_off = mt.nrep * mt.rstride * 4u, yn4 = pl.Yn * 4u;
     const int nc_valid = min(NC, W - j0);
     const bool split_full = nc_valid == NC;                                // CTA-uniform
     const int lane_word = (lane + j0 - K) >> 4;                            // this lane's words start at bases lane+j0-K + 32*chunk
@@ -721,7 +726,7 @@ k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float*
         }
     }
     __syncthreads();
-    flush_cols(lo_sh, hi_sh, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
+    flush_cols(lo_sh, mt, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
 }
 
 // ---- scoring -------------------------------------------------------------------------------------------------------

@@ -233,7 +233,7 @@ def _run_variant(capi, g, env, iters=3):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("case", ["jund_k2", "syn_k2_N", "syn_k4", "syn_k3_fdr"])
+@pytest.mark.parametrize("case", ["jund_k2", "syn_k2_N", "syn_k4", "syn_k3_fdr", "syn_k0", "syn_ss_k1_q"])
 def test_kernel_paths_agree(capi, case):
     """Packed path with the active list (default), with an overflowing list (device-side fall-back to the scan
     M-step), without the list, with the M-step's columns split over CTAs (list and scan kernels), without the reduced
@@ -245,6 +245,7 @@ def test_kernel_paths_agree(capi, case):
     base = _run_variant(capi, g, {})
     for env, same_estep in (({"BAMM_LIST_FRAC": "0"}, True), ({"BAMM_LIST_FRAC": "0.000001"}, True),
                             ({"BAMM_M_COLS": "3"}, True), ({"BAMM_M_COLS": "4", "BAMM_LIST_FRAC": "0"}, True),
+                            ({"BAMM_M_REPLICAS": "4"}, True), ({"BAMM_M_REPLICAS": "32", "BAMM_M_COLS": "2", "BAMM_LIST_FRAC": "0"}, True),
                             ({"BAMM_NO_REDUCED": "1"}, False),
                             ({"BAMM_TABLE_BYTES": "40000"}, False), ({"BAMM_TABLE_BYTES": "5000"}, False),
                             ({"BAMM_TABLE_BYTES": "9000", "BAMM_M_COLS": "2"}, False), ({"BAMM_NO_PACKED": "1"}, False)):
