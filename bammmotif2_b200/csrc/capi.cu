@@ -135,6 +135,7 @@ struct bamm_em {
     unsigned long long* d_part = nullptr;   // per-CTA partial count tables
     unsigned long long* d_xbuf = nullptr;   // [nbin] counts + [2] scalars  (the multi-GPU exchange buffer)
     float* d_vdiff = nullptr;
+    double* d_vdiff_part = nullptr;         // per-CTA partial sums of the clustered model update
     // host (pinned)
     unsigned long long* h_scal = nullptr;   // 2 scalars
     float* h_vdiff = nullptr;
@@ -424,7 +425,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_sT); cudaFree(em->d_v);
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
     if (em->own_xbuf) cudaFree(em->d_xbuf);
-    cudaFree(em->d_vdiff);
+    cudaFree(em->d_vdiff); cudaFree(em->d_vdiff_part);
     for (cudaEvent_t e : em->loop_ev) cudaEventDestroy(e);
     if (em->h_scal) cudaFreeHost(em->h_scal);
     if (em->h_vdiff) cudaFreeHost(em->h_vdiff);
@@ -630,6 +631,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     CUE(cudaMalloc(&em->d_xbuf, ((uint64_t)em->nbin + 2) * sizeof(unsigned long long)));
     CUE(cudaMemset(em->d_xbuf, 0, ((uint64_t)em->nbin + 2) * sizeof(unsigned long long)));
     CUE(cudaMalloc(&em->d_vdiff, sizeof(float)));
+    CUE(cudaMalloc(&em->d_vdiff_part, 16 * sizeof(double)));
     CUE(cudaMallocHost(&em->h_scal, 2 * sizeof(unsigned long long)));
     CUE(cudaMallocHost(&em->h_vdiff, sizeof(float)));
     em->nparts = 1;
@@ -914,7 +916,12 @@ static int launch_mstep_local(bamm_em* em) {
 
 static int launch_update(bamm_em* em) {
     em->launches += 1 + (em->npk ? 1 : 0);
-    k_update_model<<<1, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha, em->d_s, em->d_sT, em->d_vdiff);
+    // large tables: one thread-block cluster of 8 CTAs instead of one CTA
+    if ((uint64_t)em->nbin >= 16384 && em->d_vdiff_part && !getenv("BAMM_NO_CLUSTER_UPDATE"))
+        k_update_model_cluster<<<UPDATE_CLUSTER, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha,
+                                                                      em->d_s, em->d_sT, em->d_vdiff, em->d_vdiff_part);
+    else
+        k_update_model<<<1, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha, em->d_s, em->d_sT, em->d_vdiff);
     CU(cudaGetLastError());
     return launch_tuple_table(em);
 }

@@ -10,6 +10,7 @@
 //            bit-reproducible for any CTA schedule, any grid size and any number of GPUs.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 namespace bamm {
@@ -309,15 +310,24 @@ __global__ void k_peer_sum(const unsigned long long* __restrict__ slots /* [2][w
 // reference's operation order (compiled with -fmad=false); only sum|dv| is a tree instead of a serial sum.
 struct ModelDims { int A, K, W, K_bg; uint32_t Y[16]; uint32_t voff[16]; uint32_t bgoff[16]; };
 
-__global__ void __launch_bounds__(1024)
-k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn] fixed-point counts, [j][y] */,
+// CL = 1: one CTA, phases separated by __syncthreads. CL = 8: one thread-block cluster of 8 CTAs (large tables, orders >= 4
+// or the 6-letter alphabet): the same phases over 8 x 1024 threads, separated by the cluster barrier (release / acquire at
+// cluster scope makes the other CTAs' global writes visible); sum|dv| goes through per-CTA partials summed in rank order.
+template <int CL>
+__device__ __forceinline__ void update_sync() {
+    if (CL == 1) __syncthreads();
+    else cooperative_groups::this_cluster().sync();
+}
+template <int CL>
+__device__ __forceinline__ void update_model_body(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn] fixed-point counts, [j][y] */,
                float* __restrict__ n_all, float* __restrict__ v_all, float* __restrict__ vK_prev,
                const float* __restrict__ vbg_all, const float* __restrict__ alpha,
                float* __restrict__ s_lin /* [j][y] */, float* __restrict__ s_rows /* [y][j], same values */,
-               float* __restrict__ vdiff_out) {
+               float* __restrict__ vdiff_out, double* __restrict__ vdiff_part /* [CL], CL > 1 only */) {
     const int W = d.W, K = d.K, A = d.A;
     const uint32_t YK = d.Y[K + 1];
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t crank = CL == 1 ? 0u : cooperative_groups::this_cluster().block_rank();
+    const uint32_t tid = crank * blockDim.x + threadIdx.x, nt = CL * blockDim.x;
     __shared__ float sumN[64];
     __shared__ double red[32];
     // top-order counts: fixed point -> float, [j][y] -> [y][j]
@@ -326,7 +336,7 @@ k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn
         const uint32_t y = i / W, j = i % W;
         nK[i] = (float)((double)(long long)xbuf[(uint32_t)j * YK + y] * FX_INV_D);
     }
-    __syncthreads();
+    update_sync<CL>();
     // fold to lower orders: n[k-1][y2][j] = ((0 + n[k][0*Y_k+y2][j]) + n[k][1*Y_k+y2][j]) + ...  (EM.cpp:247-254)
     for (int k = K; k > 0; k--) {
         const float* nk = n_all + d.voff[k];
@@ -338,13 +348,13 @@ k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn
             for (int a = 0; a < A; a++) acc += nk[((uint32_t)a * Yk + y2) * W + j];
             nk1[i] = acc;
         }
-        __syncthreads();
+        update_sync<CL>();
     }
     // order 0 (Motif.h:101-118)
-    if (tid < (uint32_t)W) {
+    if (threadIdx.x < (uint32_t)W) {                      // every CTA keeps its own copy of the column sums
         float sN = 0.0f;
-        for (int y = 0; y < A; y++) sN += n_all[y * W + tid];
-        sumN[tid] = sN;
+        for (int y = 0; y < A; y++) sN += n_all[y * W + threadIdx.x];
+        sumN[threadIdx.x] = sN;
     }
     __syncthreads();
     double dsum = 0.0;
@@ -354,7 +364,7 @@ k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn
         if (K == 0) { dsum += (double)fabsf(nv - vK_prev[i]); vK_prev[i] = nv; }
         v_all[i] = nv;
     }
-    __syncthreads();
+    update_sync<CL>();
     // orders 1..K (Motif.h:121-135)
     for (int k = 1; k <= K; k++) {
         float* vk = v_all + d.voff[k];
@@ -372,16 +382,24 @@ k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn
             if (k == K) { dsum += (double)fabsf(nv - vK_prev[i]); vK_prev[i] = nv; }
             vk[i] = nv;
         }
-        __syncthreads();
+        update_sync<CL>();
     }
     // sum |dv|
     for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(FULL, dsum, o);
-    if ((tid & 31) == 0) red[tid >> 5] = dsum;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dsum;
     __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         double t = 0.0;
-        for (uint32_t w = 0; w < (nt >> 5); w++) t += red[w];
-        *vdiff_out = (float)t;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) t += red[w];
+        if (CL == 1) *vdiff_out = (float)t; else vdiff_part[crank] = t;
+    }
+    if (CL > 1) {
+        update_sync<CL>();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int c = 0; c < CL; c++) t += vdiff_part[c];
+            *vdiff_out = (float)t;
+        }
     }
     // next E-step's table (Motif.cpp:485-494), transposed to [j][y]
     const float* vK = v_all + d.voff[K];
@@ -393,6 +411,20 @@ k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf /* [W*Yn
         s_lin[(uint32_t)j * YK + y] = sv;
         s_rows[i] = sv;
     }
+}
+
+__global__ void __launch_bounds__(1024)
+k_update_model(ModelDims d, const unsigned long long* __restrict__ xbuf, float* __restrict__ n_all, float* __restrict__ v_all,
+               float* __restrict__ vK_prev, const float* __restrict__ vbg_all, const float* __restrict__ alpha,
+               float* __restrict__ s_lin, float* __restrict__ s_rows, float* __restrict__ vdiff_out) {
+    update_model_body<1>(d, xbuf, n_all, v_all, vK_prev, vbg_all, alpha, s_lin, s_rows, vdiff_out, nullptr);
+}
+constexpr int UPDATE_CLUSTER = 8;
+__global__ void __cluster_dims__(UPDATE_CLUSTER, 1, 1) __launch_bounds__(1024)
+k_update_model_cluster(ModelDims d, const unsigned long long* __restrict__ xbuf, float* __restrict__ n_all, float* __restrict__ v_all,
+                       float* __restrict__ vK_prev, const float* __restrict__ vbg_all, const float* __restrict__ alpha,
+                       float* __restrict__ s_lin, float* __restrict__ s_rows, float* __restrict__ vdiff_out, double* __restrict__ vdiff_part) {
+    update_model_body<UPDATE_CLUSTER>(d, xbuf, n_all, v_all, vK_prev, vbg_all, alpha, s_lin, s_rows, vdiff_out, vdiff_part);
 }
 
 // s table only (first E-step after set_model)
