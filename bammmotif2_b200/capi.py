@@ -30,7 +30,7 @@ SIGNATURES = {
     "bamm_seqset_destroy": (None, [_vp]),
     "bamm_seqset_get_codes": (C.c_int, [_vp, _u8p]),
     "bamm_seqset_get_offsets": (C.c_int, [_vp, _u64p]),
-    "bamm_seqset_sample_negatives": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.POINTER(_vp)]),
+    "bamm_seqset_sample_negatives": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_vp)]),
     "bamm_rand_stream": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_int32)]),
     "bamm_em_create": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "bamm_em_set_model": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_float]),
@@ -163,10 +163,12 @@ class SeqSet:
         self.codes = None
         return self
 
-    def sample_negatives(self, fold, seed=42):
-        """Device-side SeqGenerator::sample_bgseqset_by_fold (bit-identical to the reference's libc rand() stream)."""
+    def sample_negatives(self, fold, seed=42, subset=None):
+        """Device-side SeqGenerator::sample_bgseqset_by_fold (bit-identical to the reference's libc rand() stream);
+        subset: template sequences (indices into this set, in sampling order), default all."""
         h = _vp()
-        _check(load().bamm_seqset_sample_negatives(self.h, int(fold), int(seed), C.byref(h)))
+        sub = np.ascontiguousarray(subset, np.uint64) if subset is not None else None
+        _check(load().bamm_seqset_sample_negatives(self.h, _ptr(sub, _u64p), len(sub) if sub is not None else 0, int(fold), int(seed), C.byref(h)))
         return SeqSet._adopt(h, self.A)
 
     def get_codes(self):

@@ -1239,30 +1239,48 @@ extern "C" int bamm_rand_stream(uint32_t seed, uint64_t first, uint64_t count, i
     return BAMM_OK;
 }
 
-extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, uint64_t fold, uint32_t seed, bamm_seqset** out) {
+extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t fold, uint32_t seed, bamm_seqset** out) {
     REQUIRE(out, "out is NULL");
     *out = nullptr;
     REQUIRE(pos, "seqset is NULL");
     REQUIRE(fold >= 1, "fold must be at least 1");
-    REQUIRE(pos->nseq >= 1 && pos->nseq * fold < (1ull << 32), "number of negative sequences out of range");
-    REQUIRE(pos->minL >= 1, "empty template sequence");
-    REQUIRE(pos->npos * fold + 400 < (1ull << (LFG_NPOW - 1)), "too many draws");
+    if (!subset) nsub = pos->nseq;
+    REQUIRE(nsub >= 1 && nsub * fold < (1ull << 32), "number of negative sequences out of range");
+    // the template list: prefix sums of its lengths (= draw offsets / fold) and, for a true subset, its sequence ids
+    std::vector<uint64_t> toff(nsub + 1, 0);
+    std::vector<uint32_t> tids(subset ? nsub : 0);
+    for (uint64_t i = 0; i < nsub; i++) {
+        const uint64_t n = subset ? subset[i] : i;
+        REQUIRE(n < pos->nseq, "subset index out of range");
+        const uint64_t L = pos->h_off[n + 1] - pos->h_off[n];
+        REQUIRE(L >= 1, "empty template sequence");
+        toff[i + 1] = toff[i] + L;
+        if (subset) tids[i] = (uint32_t)n;
+    }
+    REQUIRE(toff[nsub] * fold + 400 < (1ull << (LFG_NPOW - 1)), "too many draws");
     CU(cudaSetDevice(pos->device));
     NegDims d; d.A = pos->A; d.Y1 = (uint32_t)pos->A; d.Y2 = d.Y1 * d.Y1; d.Y3 = d.Y2 * d.Y1; d.total = d.Y1 + d.Y2 + d.Y3;
     IndexArray* ia = nullptr;
     { std::lock_guard<std::mutex> g(pos->mu); int rc = seqset_index_locked(pos, 2, &ia); if (rc) return rc; }
     const uint16_t* Y2 = (const uint16_t*)ia->d;
     const float pc = 20.0f;                                   // SeqGenerator.cpp:30-32: A_[k] = 20 for every order
-    unsigned long long* d_cnt = nullptr; float *d_v = nullptr, *d_rb = nullptr; uint32_t *d_lfg = nullptr, *d_flags = nullptr;
+    unsigned long long* d_cnt = nullptr; float *d_v = nullptr, *d_rb = nullptr; uint32_t *d_lfg = nullptr, *d_flags = nullptr, *d_tids = nullptr;
+    uint64_t* d_toff = nullptr;
     bamm_seqset* neg = nullptr;
     int rc = BAMM_OK;
 #define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
     {
         // set-wide frequencies (SeqGenerator::calculate_kmer_frequency, SeqGenerator.cpp:63-112): counts on the device, the
         // 84 probabilities on the host in the reference's operation order
+        if (subset) {
+            CUX(cudaMalloc(&d_tids, nsub * sizeof(uint32_t)));
+            CUX(cudaMemcpy(d_tids, tids.data(), nsub * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+        CUX(cudaMalloc(&d_toff, (nsub + 1) * sizeof(uint64_t)));
+        CUX(cudaMemcpy(d_toff, toff.data(), (nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CUX(cudaMalloc(&d_cnt, d.total * sizeof(unsigned long long)));
         CUX(cudaMemset(d_cnt, 0, d.total * sizeof(unsigned long long)));
-        k_neg_count_set<<<pos->sm_count * 8, 256>>>(Y2, pos->d_off, pos->nseq, d, d_cnt);
+        k_neg_count_set<<<pos->sm_count * 8, 256>>>(Y2, pos->d_off, d_tids, nsub, d, d_cnt);
         CUX(cudaGetLastError());
         std::vector<unsigned long long> cnt(d.total);
         CUX(cudaMemcpy(cnt.data(), d_cnt, d.total * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -1283,15 +1301,15 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, uint64_t fold, uin
         CUX(cudaMemcpy(d_v, v.data(), d.total * sizeof(float), cudaMemcpyHostToDevice));
         CUX(cudaMemcpy(d_v + d.total, rb0.data(), d.Y1 * sizeof(float), cudaMemcpyHostToDevice));
         // per-template bars
-        CUX(cudaMalloc(&d_rb, pos->nseq * (uint64_t)(d.Y2 + d.Y3) * sizeof(float)));
-        k_neg_models<<<pos->sm_count * 16, 128>>>(Y2, pos->d_off, pos->nseq, d, d_v, pc, d_rb);
+        CUX(cudaMalloc(&d_rb, nsub * (uint64_t)(d.Y2 + d.Y3) * sizeof(float)));
+        k_neg_models<<<pos->sm_count * 16, 128>>>(Y2, pos->d_off, d_tids, nsub, d, d_v, pc, d_rb);
         CUX(cudaGetLastError());
         // the negative set: `fold` records per template, each of the template's stored length
-        const uint64_t nneg = pos->nseq * fold;
+        const uint64_t nneg = nsub * fold;
         std::vector<uint64_t> noff(nneg + 1);
         noff[0] = 0;
-        for (uint64_t i = 0, g = 0; i < pos->nseq; i++) {
-            const uint64_t L = pos->h_off[i + 1] - pos->h_off[i];
+        for (uint64_t i = 0, g = 0; i < nsub; i++) {
+            const uint64_t L = toff[i + 1] - toff[i];
             for (uint64_t m = 0; m < fold; m++, g++) noff[g + 1] = noff[g] + L;
         }
         rc = seqset_new(noff.data(), nneg, pos->A, &neg);
@@ -1304,7 +1322,7 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, uint64_t fold, uin
         const uint64_t want = (uint64_t)pos->sm_count * 2048ull;
         const uint64_t per = (nneg + want - 1) / want;
         const uint64_t threads = (nneg + per - 1) / per;
-        k_neg_sample<<<(unsigned)((threads + NEG_THREADS - 1) / NEG_THREADS), NEG_THREADS>>>(pos->d_off, pos->nseq, fold, d, d_v + d.total, d_rb,
+        k_neg_sample<<<(unsigned)((threads + NEG_THREADS - 1) / NEG_THREADS), NEG_THREADS>>>(d_toff, nsub, fold, d, d_v + d.total, d_rb,
                                                                                           d_lfg, d_lfg + LFG_N, per, neg->d_codes, d_flags);
         CUX(cudaGetLastError());
         uint32_t flags = 0;
@@ -1319,7 +1337,7 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, uint64_t fold, uin
     }
 done:
 #undef CUX
-    cudaFree(d_cnt); cudaFree(d_v); cudaFree(d_rb); cudaFree(d_lfg); cudaFree(d_flags);
+    cudaFree(d_cnt); cudaFree(d_v); cudaFree(d_rb); cudaFree(d_lfg); cudaFree(d_flags); cudaFree(d_tids); cudaFree(d_toff);
     if (rc) { if (neg) bamm_seqset_destroy(neg); return rc; }
     *out = neg;
     return BAMM_OK;

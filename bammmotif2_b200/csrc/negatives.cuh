@@ -34,8 +34,8 @@ constexpr int LFG_NPOW = 48;    // x^(2^b) for b < 48
 // ---- (1) set-wide k-mer counts: n[k][kmer[j] % A^(k+1)] for j >= k   (SeqGenerator.cpp:73-84) ----------------------
 // Y2: order-2 index array of the positive set (kmer % A^3, N draws patched in). One warp per sequence.
 __global__ void __launch_bounds__(256)
-k_neg_count_set(const uint16_t* __restrict__ Y2, const uint64_t* __restrict__ off, uint64_t nseq, NegDims d,
-                unsigned long long* __restrict__ cnt /* [total] */) {
+k_neg_count_set(const uint16_t* __restrict__ Y2, const uint64_t* __restrict__ off, const uint32_t* __restrict__ ids /* nullable: template list */,
+                uint64_t nseq, NegDims d, unsigned long long* __restrict__ cnt /* [total] */) {
     __shared__ uint32_t hist[NEG_MAXTOT];
     for (uint32_t b = threadIdx.x; b < d.total; b += blockDim.x) hist[b] = 0u;
     __syncthreads();
@@ -43,7 +43,8 @@ k_neg_count_set(const uint16_t* __restrict__ Y2, const uint64_t* __restrict__ of
     const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
     for (uint64_t n = warp; n < nseq; n += nwarps) {
-        const uint64_t base = off[n], L = off[n + 1] - base;
+        const uint64_t sid = ids ? ids[n] : n;
+        const uint64_t base = off[sid], L = off[sid + 1] - base;
         for (uint64_t j = lane; j < L; j += 32) {
             const uint32_t y = Y2[base + j];
             atomicAdd(&hist[y % d.Y1], 1u);
@@ -59,7 +60,7 @@ k_neg_count_set(const uint16_t* __restrict__ Y2, const uint64_t* __restrict__ of
 // vset: set-wide probabilities v_[k][y], tables concatenated. pc: pseudo-count weight A_[k] (20 for every k).
 // rb: [nseq][Y2 + Y3]. One warp per template: the lanes count, lane 0 does the (strictly ordered) float arithmetic.
 __global__ void __launch_bounds__(128)
-k_neg_models(const uint16_t* __restrict__ Y2, const uint64_t* __restrict__ off, uint64_t nseq, NegDims d,
+k_neg_models(const uint16_t* __restrict__ Y2, const uint64_t* __restrict__ off, const uint32_t* __restrict__ ids, uint64_t nseq, NegDims d,
              const float* __restrict__ vset, float pc, float* __restrict__ rb) {
     __shared__ uint32_t hist_all[4][NEG_MAXTOT];
     __shared__ float vs1_all[4][36];
@@ -72,7 +73,8 @@ k_neg_models(const uint16_t* __restrict__ Y2, const uint64_t* __restrict__ off, 
     for (uint64_t n = warp; n < nseq; n += nwarps) {
         for (uint32_t b = lane; b < d.total; b += 32) hist[b] = 0u;
         __syncwarp();
-        const uint64_t base = off[n], L = off[n + 1] - base;
+        const uint64_t sid = ids ? ids[n] : n;
+        const uint64_t base = off[sid], L = off[sid + 1] - base;
         for (uint64_t j = lane; j < L; j += 32) {
             const uint32_t y = Y2[base + j];
             atomicAdd(&hist[y % d.Y1], 1u);
@@ -174,7 +176,7 @@ __global__ void k_rand_stream(const uint32_t* __restrict__ u0, const uint32_t* _
 // draw in 10^7; the Sequence constructor would then consume extra rand() calls): the caller falls back to the host path.
 constexpr int NEG_THREADS = 128;
 __global__ void __launch_bounds__(NEG_THREADS)
-k_neg_sample(const uint64_t* __restrict__ off, uint64_t nseq, uint64_t fold, NegDims d, const float* __restrict__ rb0,
+k_neg_sample(const uint64_t* __restrict__ off /* [nseq+1] prefix sums of the TEMPLATE LIST's lengths */, uint64_t nseq, uint64_t fold, NegDims d, const float* __restrict__ rb0,
              const float* __restrict__ rb, const uint32_t* __restrict__ u0, const uint32_t* __restrict__ pw,
              uint64_t per_thread, uint8_t* __restrict__ codes, uint32_t* __restrict__ flags) {
     __shared__ uint32_t st_sh[LFG_N][NEG_THREADS];

@@ -138,25 +138,24 @@ std::unique_ptr<SequenceSet> SeqGenerator::sample_bgseqset_by_fold( size_t fold 
         std::cerr << "Error: negative-set sampling on re-scaled frequencies supports --sOrder 2 only." << std::endl;
         exit( 1 );
     }
-    // Device path: when the templates are one whole resident set, the library samples the identical negative set on the
-    // GPU (same k-mer models, same libc rand() stream re-created by jump-ahead; bamm_seqset_sample_negatives). It declines
-    // (BAMM_E_STATE) in the one-in-10^7 case where the reference's own draw order leaves the one-draw-per-base pattern;
-    // the serial host sampler below then produces the set. BAMM_HOST_NEGATIVES=1 forces the host sampler.
+    // The library samples the identical negative set on the GPU (same k-mer models, same libc rand() stream re-created by
+    // jump-ahead; bamm_seqset_sample_negatives). It declines (BAMM_E_STATE) only in the one-in-10^7-records case where the
+    // reference's own draw order leaves the one-draw-per-base pattern (a first base above the last cumulative bar makes its
+    // Sequence constructor consume extra draws); the reference's serial loop below then produces the set, so the result
+    // is the reference's in every case. BAMM_HOST_NEGATIVES=1 (tests) forces that loop. No device => the call exits.
     if( !genericNeg_ && !getenv( "BAMM_HOST_NEGATIVES" ) ){
         std::vector<uint64_t> indices;
         bool whole = false;
         SequenceSet* tmpl = SequenceSet::commonSet( seqs_, indices, &whole );
-        if( whole ){
-            bamm_seqset* h = nullptr;
-            const int rc = bamm_seqset_sample_negatives( tmpl->device(), fold, 42, &h );
-            if( rc == BAMM_OK ){
-                srand( 42 );                                    // the stream position after sampling is never consumed (FDR re-seeds, FDR.cpp:153)
-                return std::unique_ptr<SequenceSet>( new SequenceSet( SequenceSet::DeviceBuilt(), h, "> bg_seq" ) );
-            }
-            if( rc != BAMM_E_STATE ){
-                std::cerr << "Error: " << bamm_last_error() << std::endl;
-                exit( 1 );
-            }
+        bamm_seqset* h = nullptr;
+        const int rc = bamm_seqset_sample_negatives( tmpl->device(), whole ? NULL : indices.data(), indices.size(), fold, 42, &h );
+        if( rc == BAMM_OK ){
+            srand( 42 );                                        // the stream position after sampling is never consumed (FDR re-seeds, FDR.cpp:153)
+            return std::unique_ptr<SequenceSet>( new SequenceSet( SequenceSet::DeviceBuilt(), h, "> bg_seq" ) );
+        }
+        if( rc != BAMM_E_STATE ){
+            std::cerr << "Error: " << bamm_last_error() << std::endl;
+            exit( 1 );
         }
     }
     std::unique_ptr<SequenceSet> negset( new SequenceSet( SequenceSet::Build(), "> bg_seq" ) );

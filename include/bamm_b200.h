@@ -73,13 +73,15 @@ int bamm_seqset_get_offsets(const bamm_seqset* s, uint64_t* out);
 /*
  * Negative (background) set sampled ON THE DEVICE  (replaces SeqGenerator::sample_bgseqset_by_fold with genericNeg = false,
  * src/seq_generator/SeqGenerator.cpp:63-206, 285-348; called from src/refinement/mainBaMM.cpp:100-116 and FDR):
- * for every sequence of `pos` (in order) `fold` single-stranded records of the same stored length, drawn from the set-wide
+ * for every template — the sequences `subset[0..nsub)` of `pos` in that order, or all of them when subset is NULL (the driver
+ * filters sequences shorter than the motif before sampling, mainBaMM.cpp:75-83) — `fold` single-stranded records of the same stored length, drawn from the set-wide
  * order-2 k-mer model rescaled by the template's own k-mer counts. The bases are BIT-IDENTICAL to the reference's: the
  * device re-creates the libc rand() stream after srand(seed) (the reference seeds 42, SeqGenerator.cpp:33-34) and jumps to
  * every record's first draw. Returns BAMM_E_STATE in the (about 1 in 10^7 records) case where the reference's own draw
  * sequence would diverge from one-draw-per-base; the caller then samples on the host.
  */
-int bamm_seqset_sample_negatives(bamm_seqset* pos, uint64_t fold, uint32_t seed, bamm_seqset** out);
+int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t fold, uint32_t seed,
+                                 bamm_seqset** out);
 /* draws [first, first+count) of rand() after srand(seed), computed on the device (test hook for the generator above) */
 int bamm_rand_stream(uint32_t seed, uint64_t first, uint64_t count, int32_t* out);
 void bamm_seqset_destroy(bamm_seqset* s);

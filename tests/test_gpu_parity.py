@@ -397,6 +397,22 @@ def test_zoops_pruned_scoring_equals_full_scoring_at_scale(capi):
         assert np.array_equal(zsub, zf[::3]) and np.array_equal(psub, pf[::3])
 
 
+def test_device_negative_sampling_of_a_template_subset(capi):
+    """Templates given as an index subset of a resident set (the driver filters short sequences before sampling,
+    mainBaMM.cpp:75-83) must give the set that the same sequences give as a set of their own (that path is pinned to the
+    reference above)."""
+    g = Golden("neg_ss")
+    off = g["pos_offsets"].astype(np.int64)
+    ss = capi.SeqSet(g["pos_codes"], g["pos_offsets"], g.A)
+    sub = np.array([n for n in range(ss.nseq) if n % 3 != 1][::-1], np.uint64)          # a subset in another order
+    codes = np.concatenate([g["pos_codes"][off[n]:off[n + 1]] for n in sub])
+    soff = np.zeros(len(sub) + 1, np.uint64)
+    soff[1:] = np.cumsum([off[n + 1] - off[n] for n in sub])
+    own = capi.SeqSet(codes, soff, g.A)
+    a, b = ss.sample_negatives(7, subset=sub), own.sample_negatives(7)
+    assert np.array_equal(a.offsets, b.offsets) and np.array_equal(a.get_codes(), b.get_codes())
+
+
 def test_device_rand_stream_is_libc_rand(capi):
     """The device re-creation of glibc's rand() (additive lagged-Fibonacci TYPE_3, jump-ahead by polynomial powers) against
     libc itself: the first draws after srand(42) and a block far into the stream reached by running libc there."""
