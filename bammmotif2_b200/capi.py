@@ -59,6 +59,8 @@ SIGNATURES = {
     "bamm_em_peer_alloc": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "bamm_em_peer_attach": (C.c_int, [_vp, _vp]),
     "bamm_score_last_timing": (C.c_int, [_f32p]),
+    "bamm_sort_scores": (C.c_int, [_f32p, C.c_uint64, C.c_int]),
+    "bamm_mops_pvalues": (C.c_int, [_f32p, C.c_uint64, _f32p, C.c_uint64, C.c_uint64, _f32p, _f32p]),
     "bamm_score_logodds": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _u64p, _f32p]),
 }
 
@@ -112,6 +114,20 @@ def rand_stream(seed, first, count):
     out = np.zeros(int(count), np.int32)
     _check(load().bamm_rand_stream(int(seed), int(first), int(count), out.ctypes.data_as(C.POINTER(C.c_int32))))
     return out
+
+
+def sort_scores(scores, descending=False):
+    a = np.ascontiguousarray(scores, np.float32).copy()
+    _check(load().bamm_sort_scores(_ptr(a, _f32p), len(a), 1 if descending else 0))
+    return a
+
+
+def mops_pvalues(neg_scores, pos_scores, n_pos_sequences):
+    neg = np.ascontiguousarray(neg_scores, np.float32)
+    pos = np.ascontiguousarray(pos_scores, np.float32)
+    p, e = np.empty(len(pos), np.float32), np.empty(len(pos), np.float32)
+    _check(load().bamm_mops_pvalues(_ptr(neg, _f32p), len(neg), _ptr(pos, _f32p), len(pos), int(n_pos_sequences), _ptr(p, _f32p), _ptr(e, _f32p)))
+    return p, e
 
 
 def score_last_ms():

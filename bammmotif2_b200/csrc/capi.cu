@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 #include "packed.cuh"
 #include "negatives.cuh"
+#include "stats.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -1526,4 +1527,79 @@ extern "C" int bamm_score_last_timing(float* kernel_ms) {
     REQUIRE(kernel_ms, "NULL argument");
     *kernel_ms = g_score_ms;
     return BAMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------- score statistics (row f-1)
+static int device_sort_f32(float* d_keys, uint64_t n, bool descending, cudaStream_t st) {
+    if (n < 2) return BAMM_OK;
+    REQUIRE(n < (1ull << 31), "too many scores for one sort call");
+    float* d_alt = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0;
+    cudaError_t e = cudaMalloc(&d_alt, n * sizeof(float));
+    if (e != cudaSuccess) return fail(BAMM_E_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    cub::DoubleBuffer<float> buf(d_keys, d_alt);
+    if (descending) cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, buf, (int)n, 0, 32, st);
+    else            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, buf, (int)n, 0, 32, st);
+    e = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
+    if (e == cudaSuccess) {
+        if (descending) e = cub::DeviceRadixSort::SortKeysDescending(d_tmp, tmp_bytes, buf, (int)n, 0, 32, st);
+        else            e = cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, buf, (int)n, 0, 32, st);
+    }
+    if (e == cudaSuccess && buf.Current() != d_keys) e = cudaMemcpyAsync(d_keys, buf.Current(), n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_alt); cudaFree(d_tmp);
+    if (e != cudaSuccess) return fail(BAMM_E_CUDA, "device sort failed: %s", cudaGetErrorString(e));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_sort_scores(float* scores, uint64_t n, int descending) {
+    REQUIRE(scores || n == 0, "scores is NULL");
+    if (n < 2) return BAMM_OK;
+    float* d = nullptr;
+    CU(cudaMalloc(&d, n * sizeof(float)));
+    cudaError_t e = cudaMemcpy(d, scores, n * sizeof(float), cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? device_sort_f32(d, n, descending != 0, 0) : fail(BAMM_E_CUDA, "H2D failed: %s", cudaGetErrorString(e));
+    if (!rc) { e = cudaMemcpy(scores, d, n * sizeof(float), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(BAMM_E_CUDA, "D2H failed: %s", cudaGetErrorString(e)); }
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int bamm_mops_pvalues(const float* neg_scores, uint64_t nneg, const float* pos_scores, uint64_t npos, uint64_t n_pos_sequences,
+                                 float* p_values, float* e_values) {
+    REQUIRE(neg_scores && nneg >= 1, "no negative scores");
+    REQUIRE((pos_scores && p_values && e_values) || npos == 0, "NULL argument");
+    float *d_neg = nullptr, *d_pos = nullptr, *d_p = nullptr, *d_e = nullptr;
+    int rc = BAMM_OK;
+    const uint64_t CH = 1ull << 26;                                 // positive scores go through in chunks of 64M
+    const uint64_t chn = npos < CH ? (npos ? npos : 1) : CH;
+#define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
+    {
+        CUX(cudaMalloc(&d_neg, nneg * sizeof(float)));
+        CUX(cudaMemcpy(d_neg, neg_scores, nneg * sizeof(float), cudaMemcpyHostToDevice));
+        rc = device_sort_f32(d_neg, nneg, false, 0);
+        if (rc) goto done;
+        // rate parameter of the exponential tail from the first nTop sorted values, in the reference's order (ScoreSeqSet.cpp:88-96)
+        const size_t nTop = (size_t)std::min(100, (int)nneg / 10);
+        std::vector<float> head(nTop + 1);
+        CUX(cudaMemcpy(head.data(), d_neg, (nTop + 1) * sizeof(float), cudaMemcpyDeviceToHost));
+        const float S_ntop = head[nTop];
+        float lambda = 0.f;
+        for (size_t n = 0; n < nTop; n++) lambda += (head[n] - S_ntop);
+        lambda = lambda / (float)nTop;
+        CUX(cudaMalloc(&d_pos, chn * sizeof(float)));
+        CUX(cudaMalloc(&d_p, chn * sizeof(float)));
+        CUX(cudaMalloc(&d_e, chn * sizeof(float)));
+        int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        for (uint64_t b = 0; b < npos; b += CH) {
+            const uint64_t m = std::min(CH, npos - b);
+            CUX(cudaMemcpy(d_pos, pos_scores + b, m * sizeof(float), cudaMemcpyHostToDevice));
+            k_mops_pvalues<<<sms * 8, 256>>>(d_neg, nneg, d_pos, m, S_ntop, lambda, (float)nTop, (float)n_pos_sequences, d_p, d_e);
+            CUX(cudaGetLastError());
+            CUX(cudaMemcpy(p_values + b, d_p, m * sizeof(float), cudaMemcpyDeviceToHost));
+            CUX(cudaMemcpy(e_values + b, d_e, m * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+    }
+done:
+#undef CUX
+    cudaFree(d_neg); cudaFree(d_pos); cudaFree(d_p); cudaFree(d_e);
+    return rc;
 }

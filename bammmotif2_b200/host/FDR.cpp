@@ -8,6 +8,18 @@
 #include <iostream>
 #include <limits>
 
+// Score vectors of cross-validation runs reach 10^7 (ZOOPS) to 10^10 (MOPS) entries: those are sorted by the device radix
+// sort behind bamm_sort_scores; a few thousand values are not worth the PCIe round trip. Same result either way.
+static void sortScores( std::vector<float>& v, bool descending ){
+    if( v.size() >= ( 1u << 16 ) ){
+        BAMM_CHECK( bamm_sort_scores( v.data(), v.size(), descending ? 1 : 0 ) );
+    } else if( descending ){
+        std::sort( v.begin(), v.end(), std::greater<float>() );
+    } else {
+        std::sort( v.begin(), v.end(), std::less<float>() );
+    }
+}
+
 FDR::FDR( std::vector<Sequence*> posSeqs, std::vector<Sequence*> negSeqs, Motif* motif, BackgroundModel* bgModel, size_t cvFold,
           bool mops, bool zoops, bool savePRs, bool savePvalues, bool saveLogOdds )
     : posSeqs_( posSeqs ), negSeqs_( negSeqs ), q_( motif ? motif->getQ() : 0.f ), motif_( motif ), bgModel_( bgModel ), cvFold_( cvFold ),
@@ -90,8 +102,8 @@ void FDR::calculatePR(){
     srand( 42 );                                    // tie-breaks below draw from a fresh libc stream (FDR.cpp:153)
 
     if( mops_ ){
-        std::sort( posScoreAll_.begin(), posScoreAll_.end(), std::greater<float>() );
-        std::sort( negScoreAll_.begin(), negScoreAll_.end(), std::greater<float>() );
+        sortScores( posScoreAll_, true );
+        sortScores( negScoreAll_, true );
         size_t idx_posAll = 0, idx_negAll = 0;
         float E_TP_MOPS = 0.0f;
         size_t idx_max = posN + negN;
@@ -113,8 +125,8 @@ void FDR::calculatePR(){
 
     if( zoops_ ){
         PN_Pvalue_.clear();
-        std::sort( posScoreMax_.begin(), posScoreMax_.end(), std::greater<float>() );
-        std::sort( negScoreMax_.begin(), negScoreMax_.end(), std::greater<float>() );
+        sortScores( posScoreMax_, true );
+        sortScores( negScoreMax_, true );
 
         size_t idx_posMax = 0, idx_negMax = 0, min_idx_pos = 0;
         const size_t posN_est = static_cast<size_t>( q_ * ( float )posN );
@@ -167,8 +179,8 @@ void FDR::calculatePR(){
 // reference: FDR::calculatePvalues, src/evaluation/FDR.cpp:278-332
 void FDR::calculatePvalues(){
     auto rank = []( std::vector<float>& neg, std::vector<float>& pos, std::vector<float>& out ){
-        std::sort( neg.begin(), neg.end(), std::less<float>() );
-        std::sort( pos.begin(), pos.end(), std::less<float>() );
+        sortScores( neg, false );
+        sortScores( pos, false );
         for( size_t i = 0; i < pos.size(); i++ ){
             const size_t low = std::distance( neg.begin(), std::lower_bound( neg.begin(), neg.end(), pos[i] ) );
             const size_t up = std::distance( neg.begin(), std::upper_bound( neg.begin(), neg.end(), pos[i] ) );

@@ -51,39 +51,27 @@ std::vector<std::vector<float>> ScoreSeqSet::getMopsScores(){
 // Rank p-values of window scores against the sorted negative scores with an exponential tail for the top ranks
 // (reference: ScoreSeqSet::calcPvalues, src/seq_scoring/ScoreSeqSet.cpp:70-126)
 void ScoreSeqSet::calcPvalues( std::vector<std::vector<float>> pos_scores, std::vector<float> neg_all_scores ){
+    // The sort of all negative window scores and the per-window rank search run on the device (bamm_mops_pvalues restates
+    // ScoreSeqSet.cpp:85-124: ascending sort, rate parameter from the first nTop sorted values, upper_bound per window,
+    // exponential tail / linear interpolation); the host only flattens and scatters the vectors.
     const size_t posN = seqSet_.size();
-    const size_t negN = neg_all_scores.size();
     mops_p_values_.assign( posN, std::vector<float>() );
     mops_e_values_.assign( posN, std::vector<float>() );
-    const float eps = 1.0e-5;
-
-    std::sort( neg_all_scores.begin(), neg_all_scores.end(), std::less<float>() );
-    const size_t nTop = std::min( 100, ( int )negN / 10 );
-    const float S_ntop = neg_all_scores[nTop];
-    float lambda = 0.f;
-    for( size_t n = 0; n < nTop; n++ ) lambda += ( neg_all_scores[n] - S_ntop );
-    lambda = lambda / ( float )nTop;
-
+    std::vector<uint64_t> off( posN + 1, 0 );
     for( size_t n = 0; n < posN; n++ ){
         const size_t LW1 = seqSet_[n]->getL() - motif_->getW() + 1;
-        mops_p_values_[n].reserve( LW1 );
-        mops_e_values_[n].reserve( LW1 );
-        for( size_t i = 0; i < LW1; i++ ){
-            const float Sl = pos_scores[n][i];
-            const size_t FPl = std::distance( std::upper_bound( neg_all_scores.begin(), neg_all_scores.end(), Sl ), neg_all_scores.end() );
-            float p_value;
-            if( FPl == negN ){
-                p_value = 1.f;
-            } else if( FPl < 10 and fabs( lambda ) > eps ){
-                p_value = float( nTop ) / ( float )negN * expf( - ( Sl - S_ntop ) / lambda );
-            } else {
-                const float SlHigher = neg_all_scores[negN - FPl - 1];
-                const float SlLower = neg_all_scores[negN - FPl];
-                p_value = ( ( float )FPl + ( SlHigher - Sl + eps ) / ( SlHigher - SlLower + eps ) ) / ( float )negN;
-            }
-            mops_p_values_[n].push_back( p_value );
-            mops_e_values_[n].push_back( p_value * ( float )posN );
+        if( pos_scores[n].size() < LW1 ){
+            std::cerr << "Error: calcPvalues needs the scores of every window (sequence " << n << ")." << std::endl;
+            exit( 1 );
         }
+        off[n + 1] = off[n] + LW1;
+    }
+    std::vector<float> flat( off[posN] ), p( off[posN] ), e( off[posN] );
+    for( size_t n = 0; n < posN; n++ ) std::copy( pos_scores[n].begin(), pos_scores[n].begin() + ( off[n + 1] - off[n] ), flat.begin() + off[n] );
+    BAMM_CHECK( bamm_mops_pvalues( neg_all_scores.data(), neg_all_scores.size(), flat.data(), flat.size(), posN, p.data(), e.data() ) );
+    for( size_t n = 0; n < posN; n++ ){
+        mops_p_values_[n].assign( p.begin() + off[n], p.begin() + off[n + 1] );
+        mops_e_values_[n].assign( e.begin() + off[n], e.begin() + off[n + 1] );
     }
     pval_is_calulated_ = true;
 }

@@ -4,6 +4,7 @@
 //   host_check init    ALPHABET K KBG COUNTS.u64 ALPHA_BG.f32 SITES Q OUTDIR   -> bg_v.f32 v_init.f32 p_init.f32 (+ .hbcp/.hbp/.ihbcp/.ihbp files)
 //   host_check neg     ALPHABET FASTA SS MFOLD SORDER OUTDIR                   -> neg_codes.u8 neg_offsets.u64
 //   host_check pr      POSN NEGN Q POS.f32 NEG.f32 OUTDIR                      -> TP FP FDR Rec PNpval occ_frac (.f32)
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -35,6 +36,15 @@ int main( int argc, char** argv ){
     if( argc < 3 ) return 2;
     const std::string mode = argv[1];
     srand( 42 );
+    if( mode == "parse" ){                                   // timing of the FASTA reader alone
+        Alphabet::init( argv[2] );
+        const auto t0 = std::chrono::steady_clock::now();
+        SequenceSet set( argv[3], atoi( argv[4] ) != 0 );
+        const auto t1 = std::chrono::steady_clock::now();
+        std::cout << set.size() << " records, " << set.codes().size() << " stored codes, "
+                  << std::chrono::duration<double>( t1 - t0 ).count() << " s" << std::endl;
+        return 0;
+    }
     if( mode == "encode" ){
         Alphabet::init( argv[2] );
         SequenceSet set( argv[3], atoi( argv[4] ) != 0 );

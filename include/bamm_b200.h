@@ -168,6 +168,16 @@ int bamm_em_stream(bamm_em* em, void** stream);
 int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
                        const float* v_all, const float* vbg_all, float* zoops, uint64_t* z, float* mops);
 
+/* ---- score statistics   ---------------------------------------------------------------- */
+/* Sorts n scores in place (host buffer in and out) with a device radix sort: the std::sort calls of FDR::calculatePR
+ * (src/evaluation/FDR.cpp:161-162, 207-208) and ScoreSeqSet::calcPvalues (src/seq_scoring/ScoreSeqSet.cpp:85). */
+int bamm_sort_scores(float* scores, uint64_t n, int descending);
+/* ScoreSeqSet::calcPvalues (src/seq_scoring/ScoreSeqSet.cpp:70-126): p-value and e-value of every positive window score
+ * against ALL negative window scores (sorted on the device; exponential tail for the best scores, linear interpolation
+ * between neighbouring negatives otherwise). expf is the device's: results agree with the host's within a few ulp. */
+int bamm_mops_pvalues(const float* neg_scores, uint64_t nneg, const float* pos_scores, uint64_t npos, uint64_t n_pos_sequences,
+                      float* p_values, float* e_values);
+
 /* device time (CUDA events on the scoring stream) of the scoring kernels of the last bamm_score_logodds call of this thread */
 int bamm_score_last_timing(float* kernel_ms);
 

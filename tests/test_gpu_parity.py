@@ -447,3 +447,40 @@ def test_device_negative_sampling_bit_exact(capi, case):
         K = min(g.K, 3)
         assert np.array_equal(neg.get_index(K).astype(np.uint64), g["neg_kmer"] % np.uint64(g.A ** (K + 1)))
     neg.close(); ss.close()
+
+
+def test_device_sort_and_mops_pvalues(capi):
+    """Row f-1: bamm_sort_scores against numpy (bit-identical multiset and order) and bamm_mops_pvalues against a restatement
+    of ScoreSeqSet::calcPvalues (ScoreSeqSet.cpp:70-126) in numpy float32 — rank search exact, interpolation branch within
+    one rounding, exponential-tail branch within a few ulp of expf."""
+    rng = np.random.default_rng(11)
+    x = rng.normal(0, 3, 300_001).astype(np.float32)
+    x[::1000] = x[5]                                              # ties
+    assert np.array_equal(capi.sort_scores(x), np.sort(x))
+    assert np.array_equal(capi.sort_scores(x, descending=True), np.sort(x)[::-1])
+    neg = rng.normal(-6, 3, 200_000).astype(np.float32)
+    pos = np.concatenate([rng.normal(-6, 3, 50_000), rng.normal(4, 3, 500), [neg.max() + 1, neg.min() - 1, neg.max(), neg.min()]]).astype(np.float32)
+    p, e = capi.mops_pvalues(neg, pos, 777)
+    s = np.sort(neg)
+    negN = len(s)
+    nTop = min(100, negN // 10)
+    S_ntop = s[nTop]
+    lam = np.float32(0)
+    for n in range(nTop):
+        lam = np.float32(lam + np.float32(s[n] - S_ntop))
+    lam = np.float32(lam / np.float32(nTop))
+    FPl = negN - np.searchsorted(s, pos, side="right")
+    eps = np.float32(1e-5)
+    ref = np.empty(len(pos), np.float32)
+    one = FPl == negN
+    tail = (~one) & (FPl < 10) & (abs(lam) > eps)
+    lin = ~(one | tail)
+    ref[one] = 1.0
+    ref[tail] = (np.float32(nTop) / np.float32(negN)) * np.exp((-(pos[tail] - S_ntop) / lam).astype(np.float32)).astype(np.float32)
+    hi, lo = s[negN - FPl[lin] - 1], s[negN - FPl[lin]]
+    ref[lin] = (FPl[lin].astype(np.float32) + (hi - pos[lin] + eps) / (hi - lo + eps)) / np.float32(negN)
+    assert one.sum() >= 1 and tail.sum() >= 1 and lin.sum() > 1000
+    assert np.array_equal(p[one], ref[one])
+    assert np.all(np.abs(p[lin] - ref[lin]) <= 2e-7 * np.abs(ref[lin]))
+    assert np.all(np.abs(p[tail] - ref[tail]) <= 2e-6 * np.abs(ref[tail]))
+    assert np.array_equal(e, (p * np.float32(777)).astype(np.float32))
