@@ -686,22 +686,36 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             if ((uint32_t)em->grid_pl > em->nparts) em->nparts = (uint32_t)em->grid_pl;
         }
         // active list: one region per E-step warp, sized as a fraction of the warp's windows (BAMM_LIST_FRAC, 0 = off)
-        const double frac = getenv("BAMM_LIST_FRAC") ? atof(getenv("BAMM_LIST_FRAC")) : 0.5;
+        double frac = getenv("BAMM_LIST_FRAC") ? atof(getenv("BAMM_LIST_FRAC")) : 0.5;
+        std::vector<uint64_t> reg;
         if (frac > 0.0) {
             em->nregions = (uint32_t)em->grid_pe * (uint32_t)(em->block_pe / 32);
-            std::vector<uint64_t> win(em->nregions, 0), reg(em->nregions + 1, 0);
+            std::vector<uint64_t> win(em->nregions, 0);
+            reg.assign((size_t)em->nregions + 1, 0);
             for (size_t i = 0; i < pk_ids.size(); i++) {
                 const uint64_t n = pk_ids[i];
                 win[i % em->nregions] += s->h_off[n + 1] - s->h_off[n] - (uint64_t)W + 1;
             }
-            for (uint32_t w = 0; w < em->nregions; w++) {
-                uint64_t cap = (uint64_t)(frac * (double)win[w]) + 256;
-                if (cap > win[w]) cap = win[w];
-                reg[w + 1] = reg[w] + cap;
+            // the list is an accelerator, not a requirement: when memory is short its capacity is halved (down to 1/32 of
+            // the windows), below that the M-step scans r
+            for (;;) {
+                for (uint32_t w = 0; w < em->nregions; w++) {
+                    uint64_t cap = (uint64_t)(frac * (double)win[w]) + 256;
+                    if (cap > win[w]) cap = win[w];
+                    reg[w + 1] = reg[w] + cap;
+                }
+                const uint64_t total = reg[em->nregions] ? reg[em->nregions] : 1;
+                const cudaError_t ea = cudaMalloc(&em->d_act, total * sizeof(ActiveEntry));
+                if (ea == cudaSuccess) break;
+                cudaGetLastError();
+                em->d_act = nullptr;
+                if (ea != cudaErrorMemoryAllocation) CUE(ea);
+                frac *= 0.5;
+                if (frac < 1.0 / 32.0) break;
             }
-            const uint64_t total = reg[em->nregions] ? reg[em->nregions] : 1;
+        }
+        if (em->d_act) {
             CUE(upload(reg.data(), reg.size() * 8, (void**)&em->d_reg_off));
-            CUE(cudaMalloc(&em->d_act, total * sizeof(ActiveEntry)));
             CUE(cudaMalloc(&em->d_act_cnt, (uint64_t)em->nregions * 8));         // front counts, then back counts
             CUE(cudaMemset(em->d_act_cnt, 0, (uint64_t)em->nregions * 8));
             CUE(cudaMalloc(&em->d_overflow, 4));

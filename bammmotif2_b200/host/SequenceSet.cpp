@@ -33,6 +33,13 @@ SequenceSet::SequenceSet( std::string sequenceFilepath, bool singleStrand, std::
     std::vector<size_t> baseCounts( Alphabet::getSize(), 0 );
     size_t maxL = 0, minL = std::numeric_limits<size_t>::max();
     std::string line, header, bases;
+    {   // one allocation for the code arena instead of repeated growth: the stored codes are at most the file size
+        // (single strand) or twice the file size (both strands: forward | 0 | reverse complement, headers >= 2 bytes)
+        file.seekg( 0, std::ios::end );
+        const std::streamoff bytes = file.tellg();
+        file.seekg( 0, std::ios::beg );
+        if( bytes > 0 ) codes_.reserve( static_cast<size_t>( bytes ) * ( singleStrand ? 1 : 2 ) );
+    }
     // a record is flushed when the next '>' line (or the end of the file) is reached; a header without bases is dropped
     auto flush = [&](){
         if( header.empty() ) return;
