@@ -1273,6 +1273,7 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
         if (subset) tids[i] = (uint32_t)n;
     }
     REQUIRE(toff[nsub] * fold + 400 < (1ull << (LFG_NPOW - 1)), "too many draws");
+    Trace tr("sample_negatives");
     CU(cudaSetDevice(pos->device));
     NegDims d; d.A = pos->A; d.Y1 = (uint32_t)pos->A; d.Y2 = d.Y1 * d.Y1; d.Y3 = d.Y2 * d.Y1; d.total = d.Y1 + d.Y2 + d.Y3;
     IndexArray* ia = nullptr;
@@ -1295,6 +1296,7 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
         CUX(cudaMemcpy(d_toff, toff.data(), (nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CUX(cudaMalloc(&d_cnt, d.total * sizeof(unsigned long long)));
         CUX(cudaMemset(d_cnt, 0, d.total * sizeof(unsigned long long)));
+        tr.mark("order-2 index + template list");
         k_neg_count_set<<<pos->sm_count * 8, 256>>>(Y2, pos->d_off, d_tids, nsub, d, d_cnt);
         CUX(cudaGetLastError());
         std::vector<unsigned long long> cnt(d.total);
@@ -1327,8 +1329,10 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
             const uint64_t L = toff[i + 1] - toff[i];
             for (uint64_t m = 0; m < fold; m++, g++) noff[g + 1] = noff[g] + L;
         }
+        tr.mark("set-wide model + per-template bars + offsets (host)");
         rc = seqset_new(noff.data(), nneg, pos->A, &neg);
         if (rc) goto done;
+        tr.mark("seqset_new (alloc + offsets H2D)");
         LfgTables t; lfg_tables(seed, t);
         CUX(cudaMalloc(&d_lfg, sizeof(t)));
         CUX(cudaMemcpy(d_lfg, &t, sizeof(t), cudaMemcpyHostToDevice));
@@ -1347,7 +1351,9 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
                                     "the reference's rand() stream diverges here, use the host sampler for this set");
             goto done;
         }
+        tr.mark("sampling kernel");
         rc = seqset_finish(neg);
+        tr.mark("classify + pack");
         if (rc) { neg = nullptr; goto done; }                  // seqset_finish destroys the set on failure
     }
 done:

@@ -388,6 +388,8 @@ def run_c4(args, wl):
                          "note": "W shared-memory lookups per window bound this kernel, not HBM (the scores must be bit-identical sums in ascending j)"},
             "cpu_baseline": cpu}), flush=True)
     neg.close(); ss.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 
