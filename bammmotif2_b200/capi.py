@@ -30,6 +30,10 @@ SIGNATURES = {
     "bamm_seqset_destroy": (None, [_vp]),
     "bamm_seqset_get_codes": (C.c_int, [_vp, _u8p]),
     "bamm_seqset_get_offsets": (C.c_int, [_vp, _u64p]),
+    "bamm_seqset_encode_text": (C.c_int, [C.c_char_p, C.c_uint64, _vp, C.c_uint64, _u64p, _u32p, C.c_uint64, C.c_int, C.c_int, _u8p, _u8p, _u64p, _u64p, C.POINTER(_vp)]),
+    "bamm_seqset_forward_zeros": (C.c_int, [_vp, _u64p]),
+    "bamm_seqset_code_windows": (C.c_int, [_vp, _u64p, _u64p, _u64p, C.c_uint64, _u8p]),
+    "bamm_seqset_finish_patches": (C.c_int, [_vp, _u64p, _u64p, C.c_uint64]),
     "bamm_seqset_sample_negatives": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_vp)]),
     "bamm_rand_stream": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_int32)]),
     "bamm_em_create": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),

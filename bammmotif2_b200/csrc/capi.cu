@@ -5,6 +5,7 @@
 #include "packed.cuh"
 #include "negatives.cuh"
 #include "stats.cuh"
+#include "fasta.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -70,6 +71,9 @@ struct bamm_seqset {
     uint32_t* d_words = nullptr;        // 16 bases per word
     uint64_t nwords = 0, nregular = 0;
     std::map<int, uint16_t*> ypatch;   // per order K: [nseq][K+1] k-mer index at mid..mid+K
+    // sets encoded from FASTA text on the device: stored positions of the forward undefined bases, until the patches arrive
+    uint64_t* d_zero_pos = nullptr;
+    uint64_t n_zero_fwd = 0;
 };
 
 struct bamm_em {
@@ -284,7 +288,7 @@ extern "C" void bamm_seqset_destroy(bamm_seqset* s) {
     cudaSetDevice(s->device);
     for (auto& kv : s->index) cudaFree(kv.second.d);
     for (auto& kv : s->ypatch) cudaFree(kv.second);
-    cudaFree(s->d_kind); cudaFree(s->d_pseq); cudaFree(s->d_words);
+    cudaFree(s->d_kind); cudaFree(s->d_pseq); cudaFree(s->d_words); cudaFree(s->d_zero_pos);
     cudaFree(s->d_codes); cudaFree(s->d_off); cudaFree(s->d_ppos); cudaFree(s->d_pkmer);
     delete s;
 }
@@ -1622,4 +1626,104 @@ done:
 #undef CUX
     cudaFree(d_neg); cudaFree(d_pos); cudaFree(d_p); cudaFree(d_e);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------- FASTA text -> device set (row f-3)
+static_assert(sizeof(FastaSeg) == 24, "FastaSeg layout is part of the C ABI (bamm_fasta_seg)");
+
+extern "C" int bamm_seqset_encode_text(const char* text, uint64_t nbytes, const bamm_fasta_seg* segs, uint64_t nseg,
+                                       const uint64_t* offsets, const uint32_t* rec_L0, uint64_t nrec, int single_strand, int A,
+                                       const uint8_t* base2code, const uint8_t* code2comp, uint64_t* base_counts, uint64_t* n_forward_zeros,
+                                       bamm_seqset** out) {
+    REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    REQUIRE(text && segs && offsets && rec_L0 && base2code && code2comp && base_counts && n_forward_zeros, "NULL argument");
+    REQUIRE(A >= 2 && A <= 6, "alphabet size %d not in [2,6]", A);
+    Trace tr("encode_text");
+    bamm_seqset* s = nullptr;
+    { int rc = seqset_new(offsets, nrec, A, &s); if (rc) return rc; }
+    uint8_t *d_text = nullptr, *d_lut = nullptr; FastaSeg* d_segs = nullptr; uint32_t* d_L0 = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    int rc = BAMM_OK;
+    const uint64_t zero_cap = std::max<uint64_t>(1024, s->npos / 16);          // forward undefined bases kept (more => error below)
+#define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
+    {
+        CUX(cudaMalloc(&d_text, nbytes ? nbytes : 1));
+        CUX(cudaMemcpy(d_text, text, nbytes, cudaMemcpyHostToDevice));
+        CUX(cudaMalloc(&d_segs, (nseg ? nseg : 1) * sizeof(FastaSeg)));
+        CUX(cudaMemcpy(d_segs, segs, nseg * sizeof(FastaSeg), cudaMemcpyHostToDevice));
+        CUX(cudaMalloc(&d_L0, (nrec ? nrec : 1) * sizeof(uint32_t)));
+        CUX(cudaMemcpy(d_L0, rec_L0, nrec * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUX(cudaMalloc(&d_lut, 512));
+        CUX(cudaMemcpy(d_lut, base2code, 256, cudaMemcpyHostToDevice));
+        CUX(cudaMemcpy(d_lut + 256, code2comp, 256, cudaMemcpyHostToDevice));
+        CUX(cudaMalloc(&d_cnt, 16 * sizeof(unsigned long long)));
+        CUX(cudaMemset(d_cnt, 0, 16 * sizeof(unsigned long long)));
+        CUX(cudaMalloc(&s->d_zero_pos, zero_cap * sizeof(unsigned long long)));
+        tr.mark("alloc + text H2D");
+        if (nseg) {
+            k_fasta_encode<<<s->sm_count * 8, 256>>>(d_text, d_segs, nseg, s->d_off, d_L0, single_strand, d_lut, d_lut + 256, A, s->d_codes,
+                                                     d_cnt, (unsigned long long*)s->d_zero_pos, zero_cap, d_cnt + 8);
+            CUX(cudaGetLastError());
+        }
+        unsigned long long h[16];
+        CUX(cudaMemcpy(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
+        tr.mark("encode kernel");
+        for (int a = 0; a < A; a++) base_counts[a] = h[a];
+        if (h[8] > zero_cap) { rc = fail(BAMM_E_INVALID, "more than 1/16 of the bases are undefined: use the host encoder"); goto done; }
+        s->n_zero_fwd = h[8];
+        *n_forward_zeros = h[8];
+    }
+done:
+#undef CUX
+    cudaFree(d_text); cudaFree(d_segs); cudaFree(d_L0); cudaFree(d_lut); cudaFree(d_cnt);
+    if (rc) { bamm_seqset_destroy(s); return rc; }
+    *out = s;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_seqset_forward_zeros(bamm_seqset* s, uint64_t* positions) {
+    REQUIRE(s && (positions || s->n_zero_fwd == 0), "NULL argument");
+    if (s->n_zero_fwd) CU(cudaMemcpy(positions, s->d_zero_pos, s->n_zero_fwd * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_seqset_code_windows(bamm_seqset* s, const uint64_t* zpos, const uint64_t* zbeg, const uint64_t* zend, uint64_t nz, uint8_t* windows) {
+    REQUIRE(s && ((zpos && zbeg && zend && windows) || nz == 0), "NULL argument");
+    if (!nz) return BAMM_OK;
+    uint64_t* d = nullptr; uint8_t* d_w = nullptr;
+    CU(cudaMalloc(&d, 3 * nz * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc(&d_w, nz * 21);
+    if (e == cudaSuccess) e = cudaMemcpy(d, zpos, nz * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + nz, zbeg, nz * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + 2 * nz, zend, nz * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_zero_windows<<<(unsigned)((nz * 21 + 255) / 256), 256>>>(s->d_codes, d, d + nz, d + 2 * nz, nz, d_w);
+        e = cudaMemcpy(windows, d_w, nz * 21, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d); cudaFree(d_w);
+    if (e != cudaSuccess) return fail(BAMM_E_CUDA, "code windows failed: %s", cudaGetErrorString(e));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_seqset_finish_patches(bamm_seqset* s, const uint64_t* patch_pos, const uint64_t* patch_kmer, uint64_t npatch) {
+    REQUIRE(s && ((patch_pos && patch_kmer) || npatch == 0), "NULL argument");
+    REQUIRE(!s->d_pseq && !s->d_kind, "the set is already finished");
+    cudaFree(s->d_zero_pos); s->d_zero_pos = nullptr;
+    s->npatch = npatch;
+    if (npatch) {
+        CU(cudaMalloc(&s->d_ppos, npatch * sizeof(uint64_t)));
+        CU(cudaMalloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
+        CU(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        uint32_t* d_bad = nullptr; uint32_t bad = 0;
+        CU(cudaMalloc(&d_bad, sizeof(uint32_t)));
+        cudaMemset(d_bad, 0, sizeof(uint32_t));
+        k_validate_patches<<<(unsigned)((npatch + 255) / 256), 256>>>(s->d_ppos, npatch, s->npos, d_bad);
+        cudaError_t ev = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+        cudaFree(d_bad);
+        CU(ev);
+        if (bad) return fail(BAMM_E_INVALID, bad & 1u ? "patch position out of range" : "patch positions must be strictly increasing");
+    }
+    return seqset_finish(s);                                   // destroys the set on failure
 }

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <limits>
@@ -29,6 +30,16 @@ SequenceSet::SequenceSet( std::string sequenceFilepath, bool singleStrand, std::
     if( !file.is_open() ){
         std::cerr << "Error: Cannot open FASTA file: " << sequenceFilepath_ << std::endl;
         std::exit( 1 );
+    }
+    {   // large files: the bases are encoded on the device (readFastaDevice); BAMM_DEVICE_FASTA=1 / 0 forces either reader
+        file.seekg( 0, std::ios::end );
+        const std::streamoff bytes = file.tellg();
+        file.seekg( 0, std::ios::beg );
+        const char* force = getenv( "BAMM_DEVICE_FASTA" );
+        if( force ? atoi( force ) != 0 : bytes >= ( std::streamoff( 1 ) << 26 ) ){
+            readFastaDevice( file, static_cast<size_t>( bytes ), singleStrand );
+            return;
+        }
     }
     std::vector<size_t> baseCounts( Alphabet::getSize(), 0 );
     size_t maxL = 0, minL = std::numeric_limits<size_t>::max();
@@ -176,6 +187,151 @@ void SequenceSet::appendRecord( const std::string& header, const std::string& ba
     headers_.push_back( header );
     offsets_.push_back( codes_.size() );
     drawPatches( begin, codes_.size() );
+}
+
+// The FASTA reader with the per-base work on the device (bamm_seqset_encode_text): the host finds lines and headers with
+// the same rules as the loop above (reference: SequenceSet::readFASTA, src/init/SequenceSet.cpp:67-225), ships the raw
+// text, gets the base counts back, and draws the rand()-dependent k-mer hashes around undefined bases from the 21-code
+// neighbourhoods the device returns — the same draws in the same order as drawPatches() makes from the host arena.
+// The stored codes stay on the device until a host consumer asks for them.
+void SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singleStrand ){
+    std::string text( bytes, '\0' );
+    file.read( &text[0], static_cast<std::streamsize>( bytes ) );
+    text.resize( static_cast<size_t>( file.gcount() ) );
+    const char* t = text.data();
+    const size_t n = text.size();
+
+    std::vector<bamm_fasta_seg> segs, pending;
+    std::vector<uint32_t> recL0;
+    std::string header;
+    bool haveHeader = false;
+    uint64_t L0 = 0;
+    size_t maxL = 0, minL = std::numeric_limits<size_t>::max();
+    auto flush = [&](){
+        if( !haveHeader ) return;
+        if( L0 == 0 ){
+            std::cerr << "Warning: Ignore FASTA entry without sequence: " << sequenceFilepath_ << std::endl;
+        } else {
+            if( L0 >= ( 1ull << 31 ) ){ std::cerr << "Error: sequence too long: " << sequenceFilepath_ << std::endl; std::exit( 1 ); }
+            const uint32_t rec = static_cast<uint32_t>( recL0.size() );
+            for( bamm_fasta_seg& sg : pending ){ sg.rec = rec; segs.push_back( sg ); }
+            recL0.push_back( static_cast<uint32_t>( L0 ) );
+            headers_.push_back( header );
+            offsets_.push_back( offsets_.back() + ( singleStrand ? L0 : 2 * L0 + 1 ) );
+            maxL = std::max<size_t>( maxL, L0 );
+            minL = std::min<size_t>( minL, L0 );
+        }
+        pending.clear();
+        L0 = 0;
+        haveHeader = false;
+    };
+    for( size_t pos = 0; pos < n; ){
+        const char* nl = static_cast<const char*>( memchr( t + pos, '\n', n - pos ) );
+        const size_t end = nl ? static_cast<size_t>( nl - t ) : n;
+        const size_t len = end - pos;
+        if( len ){
+            if( t[pos] == '>' ){
+                flush();
+                if( len == 1 ){
+                    header = ">";
+                } else {
+                    const char* tab = static_cast<const char*>( memchr( t + pos, '\t', len ) );
+                    size_t hl = tab ? static_cast<size_t>( tab - ( t + pos ) ) : len;
+                    const char* cr = static_cast<const char*>( memchr( t + pos, '\r', hl ) );
+                    if( cr ) hl = static_cast<size_t>( cr - ( t + pos ) );
+                    header.assign( t + pos, hl );
+                }
+                haveHeader = true;
+            } else if( haveHeader ){
+                if( memchr( t + pos, ' ', len ) ){
+                    std::cerr << "Error: FASTA sequence contains space character: " << sequenceFilepath_ << std::endl;
+                    std::exit( 1 );
+                }
+                bamm_fasta_seg sg; sg.text_off = pos; sg.len = static_cast<uint32_t>( len ); sg.rec = 0; sg.dst = L0;
+                pending.push_back( sg );
+                L0 += len;
+            } else {
+                std::cerr << "Error: Wrong FASTA format: " << sequenceFilepath_ << std::endl;
+                std::exit( 1 );
+            }
+        }
+        pos = end + 1;
+    }
+    flush();
+    // stored lengths, as the host reader reports them
+    size_t maxStored = 0, minStored = std::numeric_limits<size_t>::max();
+    for( uint32_t l : recL0 ){
+        const size_t L = singleStrand ? l : 2 * static_cast<size_t>( l ) + 1;
+        maxStored = std::max( maxStored, L ); minStored = std::min( minStored, L );
+    }
+    maxL_ = recL0.empty() ? 0 : maxL;
+    minL_ = recL0.empty() ? std::numeric_limits<size_t>::max() : minL;
+    ( void )maxStored; ( void )minStored;
+
+    const size_t A = Alphabet::getSize();
+    uint8_t lut[256], comp[256];
+    for( int c = 0; c < 256; c++ ){ lut[c] = Alphabet::getCode( static_cast<char>( c ) ); comp[c] = Alphabet::getComplementCode( static_cast<uint8_t>( c ) ); }
+    std::vector<uint64_t> counts( A, 0 );
+    uint64_t nzeroFwd = 0;
+    const size_t N = recL0.size();
+    BAMM_CHECK( bamm_seqset_encode_text( t, n, segs.data(), segs.size(), offsets_.data(), recL0.data(), N, singleStrand ? 1 : 0,
+                                         static_cast<int>( A ), lut, comp, counts.data(), &nzeroFwd, &device_ ) );
+    size_t total = 0;
+    for( uint64_t c : counts ) total += c;
+    baseFrequencies_.resize( A );
+    for( size_t a = 0; a < A; a++ ) baseFrequencies_[a] = static_cast<float>( counts[a] ) / static_cast<float>( total );
+
+    // undefined bases in ascending stored position: the forward ones the device found, plus the structural N of each record
+    std::vector<uint64_t> zpos( nzeroFwd );
+    BAMM_CHECK( bamm_seqset_forward_zeros( device_, zpos.data() ) );
+    std::sort( zpos.begin(), zpos.end() );
+    if( !singleStrand ){
+        std::vector<uint64_t> merged;
+        merged.reserve( zpos.size() + N );
+        size_t zi = 0;
+        for( size_t r = 0; r < N; r++ ){
+            const uint64_t mid = offsets_[r] + recL0[r];
+            while( zi < zpos.size() && zpos[zi] < mid ) merged.push_back( zpos[zi++] );
+            merged.push_back( mid );
+        }
+        while( zi < zpos.size() ) merged.push_back( zpos[zi++] );
+        zpos.swap( merged );
+    }
+    std::vector<uint64_t> zbeg( zpos.size() ), zend( zpos.size() );
+    {
+        size_t r = 0;
+        for( size_t k = 0; k < zpos.size(); k++ ){
+            while( offsets_[r + 1] <= zpos[k] ) r++;
+            zbeg[k] = offsets_[r]; zend[k] = offsets_[r + 1];
+        }
+    }
+    std::vector<uint8_t> win( zpos.size() * 21 );
+    BAMM_CHECK( bamm_seqset_code_windows( device_, zpos.data(), zbeg.data(), zend.data(), zpos.size(), win.data() ) );
+    // the draws of drawPatches(), from the windows: records in order, undefined bases ascending, positions z..z+10 not yet
+    // hashed, bases of each 11-mer from the oldest to the newest
+    patchPos_.reserve( zpos.size() * 11 ); patchKmer_.reserve( zpos.size() * 11 );
+    uint64_t next = 0, curBeg = ~0ull;
+    for( size_t k = 0; k < zpos.size(); k++ ){
+        if( zbeg[k] != curBeg ){ curBeg = zbeg[k]; next = 0; }
+        const uint8_t* w = win.data() + k * 21;                 // w[10 + d] = code at z + d
+        const uint64_t z = zpos[k] - curBeg, L = zend[k] - curBeg;
+        const uint64_t last = std::min<uint64_t>( L - 1, z + 10 );
+        for( uint64_t i = std::max( next, z ); i <= last; i++ ){
+            const size_t span = i < 10 ? static_cast<size_t>( i ) + 1 : 11;
+            size_t h = 0;
+            for( size_t kk = span; kk > 0; kk-- ){
+                const uint8_t code = w[10 + static_cast<long long>( i - kk + 1 ) - static_cast<long long>( z )];
+                const size_t digit = ( code == 0 ) ? static_cast<size_t>( rand() ) % A : static_cast<size_t>( code - 1 );
+                h += digit * Y_[kk - 1];
+            }
+            patchPos_.push_back( curBeg + i );
+            patchKmer_.push_back( h );
+        }
+        next = std::max( next, last + 1 );
+    }
+    BAMM_CHECK( bamm_seqset_finish_patches( device_, patchPos_.data(), patchKmer_.data(), patchPos_.size() ) );
+    codesOnDevice_ = true;
+    finalize();
 }
 
 // Positions whose 11-mer hash contains a code-0 base: the reference replaces the 0 by rand() % A separately for every

@@ -14,6 +14,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <fstream>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -98,6 +99,7 @@ private:
     friend class Sequence;
     void                    appendRecord( const std::string& header, const std::string& bases, bool singleStrand,
                                           std::vector<size_t>& baseCounts );
+    void                    readFastaDevice( std::ifstream& file, size_t bytes, bool singleStrand );
     void                    drawPatches( uint64_t begin, uint64_t end );
     void                    finalize();
     void                    ensureCodes()           { if( codesOnDevice_ ) fetchCodes(); }

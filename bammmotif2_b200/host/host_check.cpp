@@ -41,8 +41,15 @@ int main( int argc, char** argv ){
         const auto t0 = std::chrono::steady_clock::now();
         SequenceSet set( argv[3], atoi( argv[4] ) != 0 );
         const auto t1 = std::chrono::steady_clock::now();
-        std::cout << set.size() << " records, " << set.codes().size() << " stored codes, "
-                  << std::chrono::duration<double>( t1 - t0 ).count() << " s" << std::endl;
+        double resident = -1.0;
+        if( argc > 5 ){                                      // ... and until the set is resident on the device
+            set.device();
+            resident = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+        }
+        std::cout << set.size() << " records, " << set.offsets().back() << " stored codes, reader "
+                  << std::chrono::duration<double>( t1 - t0 ).count() << " s";
+        if( resident >= 0.0 ) std::cout << ", resident on the device after " << resident << " s";
+        std::cout << std::endl;
         return 0;
     }
     if( mode == "encode" ){

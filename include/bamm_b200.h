@@ -168,6 +168,34 @@ int bamm_em_stream(bamm_em* em, void** stream);
 int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
                        const float* v_all, const float* vbg_all, float* zoops, uint64_t* z, float* mops);
 
+/* ---- FASTA text -> sequence set on the device   ------------------------------------------ */
+/*
+ * Replaces the per-base work of SequenceSet::readFASTA / Sequence::Sequence / appendRevComp (src/init/SequenceSet.cpp:67-225,
+ * src/init/Sequence.cpp:4-43, 91-99): the caller finds the lines of the file (headers stay on the host) and passes the raw
+ * text; encoding through the alphabet tables (Alphabet.cpp:10-55), the forward | 0 | reverse-complement layout and the base
+ * counts (SequenceSet.cpp:99-108) happen on the device. The k-mer hashes around undefined bases depend on libc rand() draws
+ * (Sequence.cpp:35-41) and therefore come back from the host as the usual patch list:
+ *     bamm_seqset_encode_text    -> set (not yet usable), base counts, number of forward undefined bases
+ *     bamm_seqset_forward_zeros  -> their stored positions (unordered); the structural N of both-strand records is implied
+ *     bamm_seqset_code_windows   -> the 21 stored codes around any positions (0xff outside [beg,end)), for the host's hashes
+ *     bamm_seqset_finish_patches -> patch list in, set classified + packed and ready (destroyed on failure)
+ */
+typedef struct bamm_fasta_seg {     /* one sequence line of the file */
+    uint64_t text_off;              /* first byte in `text` */
+    uint32_t len;                   /* bytes of the line = bases (line terminator excluded, a '\r' counts like the reference counts it) */
+    uint32_t rec;                   /* record index */
+    uint64_t dst;                   /* bases of the record before this line */
+} bamm_fasta_seg;
+int bamm_seqset_encode_text(const char* text, uint64_t nbytes, const bamm_fasta_seg* segs, uint64_t nseg,
+                            const uint64_t* offsets /* nrec+1 stored offsets */, const uint32_t* rec_L0 /* bases per record */,
+                            uint64_t nrec, int single_strand, int A, const uint8_t* base2code /* [256] */,
+                            const uint8_t* code2comp /* [256] */, uint64_t* base_counts /* [A] out */, uint64_t* n_forward_zeros,
+                            bamm_seqset** out);
+int bamm_seqset_forward_zeros(bamm_seqset* s, uint64_t* positions);
+int bamm_seqset_code_windows(bamm_seqset* s, const uint64_t* pos, const uint64_t* beg, const uint64_t* end, uint64_t n,
+                             uint8_t* windows /* [n][21] */);
+int bamm_seqset_finish_patches(bamm_seqset* s, const uint64_t* patch_pos, const uint64_t* patch_kmer, uint64_t npatch);
+
 /* ---- score statistics   ---------------------------------------------------------------- */
 /* Sorts n scores in place (host buffer in and out) with a device radix sort: the std::sort calls of FDR::calculatePR
  * (src/evaluation/FDR.cpp:161-162, 207-208) and ScoreSeqSet::calcPvalues (src/seq_scoring/ScoreSeqSet.cpp:85). */

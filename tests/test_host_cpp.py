@@ -31,6 +31,22 @@ def write_inputs(g, d, name="in"):
     return fa, bs
 
 
+def parse_fasta_text(text):
+    recs, h, sq = [], None, []
+    for line in text.split("\n"):
+        if not line:
+            continue
+        if line[0] == ">":
+            if h is not None and sq:
+                recs.append((h, "".join(sq)))
+            h, sq = line, []
+        else:
+            sq.append(line)
+    if h is not None and sq:
+        recs.append((h, "".join(sq)))
+    return recs
+
+
 def run(cmd, **kw):
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, **kw)
     assert p.returncode == 0, "%s\n%s\n%s" % (" ".join(cmd), p.stdout[-2000:], p.stderr[-2000:])
@@ -46,6 +62,37 @@ def test_fasta_encoding_and_kmers_bit_exact(bins, case, tmp_path):
     assert np.array_equal(np.fromfile(tmp_path / "offsets.u64", np.uint64), g["pos_offsets"])
     # includes the rand() draws for N bases: same libc stream, same order as the reference
     assert np.array_equal(np.fromfile(tmp_path / "kmer.u64", np.uint64), g["pos_kmer"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES + ["neg_ragged_N", "neg_ext", "neg_ss"])
+def test_fasta_encoding_on_the_device_bit_exact(bins, case, tmp_path):
+    """Row f-3: the same reader with the per-base work on the device (raw text up, codes encoded / mirrored / counted by
+    k_fasta_encode, rand()-dependent hashes from the 21-code windows): codes, offsets, every k-mer hash and the base
+    frequencies equal the reference's; also with CRLF line ends and sequences wrapped over several lines."""
+    g = Golden(case)
+    fa, _ = write_inputs(g, str(tmp_path))
+    env = dict(os.environ, BAMM_DEVICE_FASTA="1")
+    run([os.path.join(bins, "host_check"), "encode", g.alphabet, fa, "1" if g.ss else "0", str(tmp_path)], env=env)
+    assert np.array_equal(np.fromfile(tmp_path / "codes.u8", np.uint8), g["pos_codes"])
+    assert np.array_equal(np.fromfile(tmp_path / "offsets.u64", np.uint64), g["pos_offsets"])
+    assert np.array_equal(np.fromfile(tmp_path / "kmer.u64", np.uint64), g["pos_kmer"])
+    freq = np.fromfile(tmp_path / "basefreq.f32", np.float32)
+    # the host reader on a re-wrapped, CRLF copy of the file (a '\r' is an undefined base for both readers, like in the reference)
+    recs = parse_fasta_text(open(fa).read())
+    alt = tmp_path / "alt.fasta"
+    with open(alt, "w", newline="") as f:
+        for h, sq in recs:
+            f.write(h + "\r\n")
+            for i in range(0, len(sq), 37):
+                f.write(sq[i:i + 37] + "\r\n")
+    d_host, d_dev = tmp_path / "h", tmp_path / "d"
+    d_host.mkdir(); d_dev.mkdir()
+    run([os.path.join(bins, "host_check"), "encode", g.alphabet, str(alt), "1" if g.ss else "0", str(d_host)], env=dict(os.environ, BAMM_DEVICE_FASTA="0"))
+    run([os.path.join(bins, "host_check"), "encode", g.alphabet, str(alt), "1" if g.ss else "0", str(d_dev)], env=env)
+    for fn in ("codes.u8", "offsets.u64", "kmer.u64", "basefreq.f32"):
+        assert open(d_host / fn, "rb").read() == open(d_dev / fn, "rb").read(), fn
+    assert len(freq) == g.A
 
 
 @pytest.mark.parametrize("case", CASES)
