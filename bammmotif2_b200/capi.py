@@ -42,6 +42,7 @@ SIGNATURES = {
     "bamm_em_mstep": (C.c_int, [_vp]),
     "bamm_em_optimize_q": (C.c_int, [_vp, _f32p]),
     "bamm_em_optimize": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int), _f32p, _f32p, _f32p]),
+    "bamm_em_mask": (C.c_int, [_vp, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_int), _f32p, _u64p, _f32p]),
     "bamm_em_iterate": (C.c_int, [_vp, C.c_int, _f32p, _f32p]),
     "bamm_em_get_model": (C.c_int, [_vp, _f32p]),
     "bamm_em_get_counts": (C.c_int, [_vp, _f32p]),
@@ -285,6 +286,12 @@ class EM:
                                        _ptr(llh, _f32p), _ptr(vd, _f32p), _ptr(qt, _f32p)))
         n = it.value
         return dict(iterations=n, llh=llh[:n], vdiff=vd[:n], qtrace=qt[:n], v=self.model(), q=self.q())
+
+    def mask(self, f=0.05, epsilon=0.01, max_iter=1000):
+        """EM::mask (--advanceEM). Returns dict(iterations, llh, nkept, cutoff, v)."""
+        it, llh, nk, cut = C.c_int(0), C.c_float(0), C.c_uint64(0), C.c_float(0)
+        _check(load().bamm_em_mask(self.h, f, epsilon, max_iter, C.byref(it), C.byref(llh), C.byref(nk), C.byref(cut)))
+        return dict(iterations=it.value, llh=llh.value, nkept=nk.value, cutoff=cut.value, v=self.model())
 
     def iterate(self, n_iter):
         llh, vd = C.c_float(0), C.c_float(0)

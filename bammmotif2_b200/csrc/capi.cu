@@ -6,6 +6,7 @@
 #include "negatives.cuh"
 #include "stats.cuh"
 #include "fasta.cuh"
+#include "mask.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -141,6 +142,10 @@ struct bamm_em {
     unsigned long long* d_xbuf = nullptr;   // [nbin] counts + [2] scalars  (the multi-GPU exchange buffer)
     float* d_vdiff = nullptr;
     double* d_vdiff_part = nullptr;         // per-CTA partial sums of the clustered model update
+    // EM::mask workspaces (created by the first bamm_em_mask call)
+    uint32_t* d_m_ids = nullptr; uint64_t* d_m_roff = nullptr; uint64_t* d_m_woff = nullptr;
+    uint64_t* d_m_seloff = nullptr; uint32_t* d_m_sel = nullptr;
+    std::vector<uint32_t> h_ids;            // subset -> seqset index (all sequences of the subset, in order)
     // host (pinned)
     unsigned long long* h_scal = nullptr;   // 2 scalars
     float* h_vdiff = nullptr;
@@ -431,6 +436,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
     if (em->own_xbuf) cudaFree(em->d_xbuf);
     cudaFree(em->d_vdiff); cudaFree(em->d_vdiff_part);
+    cudaFree(em->d_m_ids); cudaFree(em->d_m_roff); cudaFree(em->d_m_woff); cudaFree(em->d_m_seloff); cudaFree(em->d_m_sel);
     for (cudaEvent_t e : em->loop_ev) cudaEventDestroy(e);
     if (em->h_scal) cudaFreeHost(em->h_scal);
     if (em->h_vdiff) cudaFreeHost(em->h_vdiff);
@@ -603,6 +609,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         }
     }
     em->rsize = em->h_r_off[nsub];
+    em->h_ids = ids;
     em->ngen = (uint32_t)gen_ids.size(); em->npk = (uint32_t)pk_ids.size();
     tr.mark("subset split (host)");
     IndexArray* ia = nullptr;
@@ -1054,6 +1061,130 @@ extern "C" int bamm_em_optimize(bamm_em* em, int optimize_q, float epsilon, int 
         if (llh_diff < 0 && it > 10) iterate = false;
     }
     if (iterations) *iterations = it;
+    return BAMM_OK;
+}
+
+static int device_sort_f32(float* d_keys, uint64_t n, bool descending, cudaStream_t st);
+// EM::mask (EM.cpp:261-503, --advanceEM) on the device; see mask.cuh. Single GPU, without optimizeQ.
+template <typename YT>
+static int mask_run(bamm_em* em, const YT* Y, float f, float epsilon, int max_iter, int* iterations, uint64_t* nkept_out, float* cutoff_out) {
+    bamm_seqset* s = em->ss;
+    const int W = em->W, sms = s->sm_count;
+    const uint64_t nsub = em->nsub;
+    MaskView mv; mv.seq_off = s->d_off; mv.seq_ids = em->d_m_ids; mv.r_off = em->d_m_roff; mv.nsub = (uint32_t)nsub;
+    cudaStream_t st = em->stream;
+    // (1) order-0 table s0[y][j] = v[0][y][j] / vbg[0][y] (EM.cpp:271-275) on the host from the device model
+    std::vector<float> v0((size_t)em->A * W), vb0(em->A), s0((size_t)em->A * W);
+    CU(cudaMemcpyAsync(v0.data(), em->d_v, v0.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(vb0.data(), em->d_vbg, vb0.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int y = 0; y < em->A; y++) for (int j = 0; j < W; j++) s0[(size_t)y * W + j] = v0[(size_t)y * W + j] / vb0[y];
+    float* d_s0 = nullptr; float* d_all = nullptr; uint32_t* d_cnt = nullptr;
+    int rc = BAMM_OK;
+    uint64_t pos_count = 0;
+    std::vector<uint64_t> woff(nsub + 1, 0);
+    for (uint64_t i = 0; i < nsub; i++) woff[i + 1] = woff[i] + (em->h_r_off[i + 1] - em->h_r_off[i]) - (uint64_t)W + 1;
+    pos_count = woff[nsub];
+#define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
+    {
+        CUX(cudaMalloc(&d_s0, s0.size() * sizeof(float)));
+        CUX(cudaMemcpyAsync(d_s0, s0.data(), s0.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (!em->d_m_woff) CUX(cudaMalloc(&em->d_m_woff, (nsub + 1) * sizeof(uint64_t)));
+        CUX(cudaMemcpyAsync(em->d_m_woff, woff.data(), (nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        CUX(cudaMemsetAsync(em->d_r, 0, (em->rsize ? em->rsize : 1) * sizeof(float), st));       // the reference's calloc
+        k_mask_phase1<YT><<<sms * 8, 256, 0, st>>>(Y, mv, W, (uint32_t)em->A, d_s0, em->q, em->d_r);
+        CUX(cudaGetLastError());
+        // (2) threshold: descending sort of every window's r, value at rank floor(float(count) * f)  (EM.cpp:318-334)
+        CUX(cudaMalloc(&d_all, (pos_count ? pos_count : 1) * sizeof(float)));
+        k_mask_gather<<<sms * 8, 256, 0, st>>>(mv, W, em->d_m_woff, em->d_r, d_all);
+        CUX(cudaGetLastError());
+        rc = device_sort_f32(d_all, pos_count, true, st);
+        if (rc) goto done;
+        const size_t rank = (size_t)((float)pos_count * f);
+        if (rank >= pos_count) { rc = fail(BAMM_E_INVALID, "fraction f=%g selects no threshold", (double)f); goto done; }
+        float cutoff = 0.0f;
+        CUX(cudaMemcpy(&cutoff, d_all + rank, sizeof(float), cudaMemcpyDeviceToHost));
+        cudaFree(d_all); d_all = nullptr;
+        CUX(cudaMalloc(&d_cnt, (nsub ? nsub : 1) * sizeof(uint32_t)));
+        k_mask_select<false><<<sms * 8, 256, 0, st>>>(mv, em->d_m_woff, em->d_r, cutoff, d_cnt, nullptr, nullptr);
+        CUX(cudaGetLastError());
+        std::vector<uint32_t> cnt(nsub);
+        CUX(cudaMemcpyAsync(cnt.data(), d_cnt, nsub * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUX(cudaStreamSynchronize(st));
+        std::vector<uint64_t> seloff(nsub + 1, 0);
+        for (uint64_t i = 0; i < nsub; i++) seloff[i + 1] = seloff[i] + cnt[i];
+        cudaFree(em->d_m_seloff); cudaFree(em->d_m_sel); em->d_m_seloff = nullptr; em->d_m_sel = nullptr;
+        CUX(cudaMalloc(&em->d_m_seloff, (nsub + 1) * sizeof(uint64_t)));
+        CUX(cudaMalloc(&em->d_m_sel, (seloff[nsub] ? seloff[nsub] : 1) * sizeof(uint32_t)));
+        CUX(cudaMemcpyAsync(em->d_m_seloff, seloff.data(), (nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        k_mask_select<true><<<sms * 8, 256, 0, st>>>(mv, em->d_m_woff, em->d_r, cutoff, nullptr, em->d_m_seloff, em->d_m_sel);
+        CUX(cudaGetLastError());
+        if (nkept_out) *nkept_out = seloff[nsub];
+        if (cutoff_out) *cutoff_out = cutoff;
+        // (3) EM over the kept windows (EM.cpp:363-495): E, M, fold + updateV + next s, the stop rule of optimize()
+        int max_optin = 0;
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, em->device);
+        const size_t tb = (size_t)em->nbin * 4;
+        const bool smem = tb <= (size_t)max_optin && em->nparts > 1;
+        int grid_m = sms * 2;
+        if (smem) {
+            grid_m = std::min<int>((int)em->nparts, sms * std::max(1, std::min(4, (int)((size_t)(max_optin + 1024) / (tb + 1024)))));
+            CUX(cudaFuncSetAttribute(k_mask_mstep<YT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
+        }
+        unsigned long long* scal = em->d_xbuf + em->nbin;
+        bool iterate = true;
+        int it = 0;
+        float llh_prev;
+        em->llh = 0.0f;                                             // EM.h:61: the member starts at 0
+        while (iterate && it < max_iter) {
+            it++;
+            llh_prev = em->llh;
+            CUX(cudaMemsetAsync(scal, 0, 2 * sizeof(unsigned long long), st));
+            k_mask_estep<YT><<<sms * 8, 256, 0, st>>>(Y, mv, W, em->Yn, em->d_s, em->q, em->d_m_seloff, em->d_m_sel, em->d_r, scal);
+            CUX(cudaGetLastError());
+            CUX(cudaMemsetAsync(em->d_part, 0, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long), st));
+            if (smem) k_mask_mstep<YT, true><<<grid_m, 512, tb, st>>>(Y, mv, W, em->Yn, em->d_m_seloff, em->d_m_sel, em->d_r, em->d_part);
+            else      k_mask_mstep<YT, false><<<grid_m, 512, 0, st>>>(Y, mv, W, em->Yn, em->d_m_seloff, em->d_m_sel, em->d_r, em->d_part);
+            CUX(cudaGetLastError());
+            em->launches += 2;
+            rc = launch_mstep_reduce(em); if (rc) goto done;
+            rc = launch_update(em); if (rc) goto done;
+            rc = read_scalars(em, true); if (rc) goto done;
+            const float v_diff = *em->h_vdiff;
+            const float llh_diff = em->llh - llh_prev;
+            if (v_diff < epsilon) iterate = false;
+            if (llh_diff < 0 && it > 10) iterate = false;
+        }
+        if (iterations) *iterations = it;
+        em->r_valid = true; em->r_scaled = true;
+    }
+done:
+#undef CUX
+    cudaFree(d_s0); cudaFree(d_all); cudaFree(d_cnt);
+    return rc;
+}
+
+extern "C" int bamm_em_mask(bamm_em* em, float f, float epsilon, int max_iter, int* iterations, float* llh, uint64_t* n_kept, float* r_cutoff) {
+    REQUIRE(em, "em is NULL");
+    if (!em->model_set) return fail(BAMM_E_STATE, "bamm_em_set_model has not been called");
+    REQUIRE(max_iter >= 1, "max_iter must be >= 1");
+    REQUIRE(f > 0.0f && f < 1.0f, "fraction f=%g not in (0,1)", (double)f);
+    REQUIRE(em->W >= 2, "EM::mask needs a motif of at least two columns");     // the reference reads pos_[L] for W = 1
+    REQUIRE(em->nsub >= 1, "empty sequence subset");
+    REQUIRE(!em->peer_attached, "EM::mask runs on one device");
+    CU(cudaSetDevice(em->device));
+    IndexArray* ia = nullptr;
+    { std::lock_guard<std::mutex> g(em->ss->mu); int rc = seqset_index_locked(em->ss, em->K, &ia); if (rc) return rc; }
+    if (!em->d_m_ids) {
+        CU(cudaMalloc(&em->d_m_ids, em->nsub * sizeof(uint32_t)));
+        CU(cudaMalloc(&em->d_m_roff, (em->nsub + 1) * sizeof(uint64_t)));
+        CU(cudaMemcpy(em->d_m_ids, em->h_ids.data(), em->nsub * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(em->d_m_roff, em->h_r_off.data(), (em->nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    int rc = ia->bytes == 2 ? mask_run<uint16_t>(em, (const uint16_t*)ia->d, f, epsilon, max_iter, iterations, n_kept, r_cutoff)
+                            : mask_run<uint32_t>(em, (const uint32_t*)ia->d, f, epsilon, max_iter, iterations, n_kept, r_cutoff);
+    if (rc) return rc;
+    if (llh) *llh = em->llh;
     return BAMM_OK;
 }
 

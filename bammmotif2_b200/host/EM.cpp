@@ -85,9 +85,33 @@ int EM::optimize(){
     return 0;
 }
 
+// reference: EM::mask, src/refinement/EM.cpp:261-503 (the "advanced EM" of --advanceEM): order-0 E-step over all windows,
+// threshold that keeps the fraction f_ of them, EM over the kept windows. All three phases run behind bamm_em_mask.
 int EM::mask(){
-    std::cerr << "Error: EM::mask (--advanceEM) is not part of the B200 EM path." << std::endl;
-    exit( 1 );
+    auto t0_wall = std::chrono::high_resolution_clock::now();
+    if( optimizeQ_ ){
+        // the reference calls optimize_q() inside its per-sequence loop (EM.cpp:316), i.e. on responsibilities that are
+        // partly stale and partly not yet computed; that order dependence is not reproduced
+        std::cerr << "Error: --advanceEM cannot be combined with --optimizeQ on the B200 path." << std::endl;
+        exit( 1 );
+    }
+    uploadModel();
+    int iterations = 0;
+    float llh = 0.0f, cutoff = 0.0f;
+    uint64_t kept = 0;
+    BAMM_CHECK( bamm_em_mask( dev_, f_, epsilon_, static_cast<int>( maxEMIterations_ ), &iterations, &llh, &kept, &cutoff ) );
+    iterations_ = static_cast<size_t>( iterations );
+    llikelihood_ = llh;
+    if( verbose_ ) std::cout << iterations << " iterations on " << kept << " windows (r >= " << cutoff << ")" << std::endl;
+    BAMM_CHECK( bamm_em_get_model( dev_, motif_->flatV().data() ) );
+    BAMM_CHECK( bamm_em_get_s( dev_, motif_->flatS().data() ) );
+    motif_->calculateP();
+    rFresh_ = false;
+    nFresh_ = false;
+    auto t1_wall = std::chrono::high_resolution_clock::now();
+    auto t_diff = std::chrono::duration_cast<std::chrono::duration<double>>( t1_wall - t0_wall );
+    std::cout << "\n--- Runtime for EM: " << t_diff.count() << " seconds ---\n";
+    return 0;
 }
 
 void EM::fetchR(){

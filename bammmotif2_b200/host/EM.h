@@ -22,7 +22,7 @@ public:
     EM& operator=( const EM& ) = delete;
 
     int         optimize();             // EM loop with the reference's stop rule (EM.cpp:62-137)
-    int         mask();                 // advanced EM (EM.cpp:261-503): not on the B200 path, exits with an error
+    int         mask();                 // advanced EM (EM.cpp:261-503) behind bamm_em_mask; not with optimizeQ
     void        print();
     void        write( char* odir, std::string basename, bool ss );
 

@@ -110,6 +110,15 @@ int bamm_em_optimize_q(bamm_em* em, float* q);
  */
 int bamm_em_optimize(bamm_em* em, int optimize_q, float epsilon, int max_iter, int* iterations,
                      float* llh_trace, float* vdiff_trace, float* q_trace);
+/*
+ * EM::mask (src/refinement/EM.cpp:261-503, the "advanced EM" of --advanceEM) without optimizeQ: one
+ * order-0 E-step over all windows, the threshold that keeps the fraction f of them with the largest responsibility, then EM
+ * over the kept windows with the stop rule of optimize(). The reference's quirks are kept (window p = 0 unscored in the first
+ * phase, prior 0 for a kept window i = 0, r[0] divided once more per iteration). Afterwards get_model / get_counts / get_r /
+ * llh describe the final state like after bamm_em_optimize. One device only.
+ */
+int bamm_em_mask(bamm_em* em, float f, float epsilon, int max_iter, int* iterations, float* llh, uint64_t* n_kept,
+                 float* r_cutoff);
 /* n_iter full iterations (E, M, update) back to back without a host round trip; for throughput runs. */
 int bamm_em_iterate(bamm_em* em, int n_iter, float* llh_last, float* vdiff_last);
 int bamm_em_get_model(bamm_em* em, float* v_all);              /* current v, all orders */

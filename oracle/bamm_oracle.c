@@ -349,6 +349,128 @@ ORC_API int orc_em_optimize(const uint64_t* kmer, const uint64_t* offsets, uint6
     return it;
 }
 
+/* reference: src/refinement/EM.cpp:261-503 (mask, the "advanced EM" of --advanceEM) without optimizeQ:
+ * (1) one E-step with the order-0 model over all windows (full products; the window at p = 0 keeps the bare prior because
+ *     the loop bound j < min(W, ij) skips it, :300-303), ascending-i normaliser;
+ * (2) the cutoff that keeps the fraction f of all windows with the largest r (descending sort, :318-345);
+ * (3) EM over the kept windows only, full W-column products and counts (no truncated windows here), the position prior read
+ *     at pos_[LW1 - i] (so the window i = 0, when kept, gets prior 0: :417), r[0] divided by the normaliser once more (:422),
+ *     the stop rule of optimize().
+ * r: sum(L_n) floats, zero-initialised by the caller like the reference's calloc. Returns the iteration count. */
+static int cmp_float_desc(const void* a, const void* b) {
+    const float x = *(const float*)a, y = *(const float*)b;
+    return (x < y) - (x > y);
+}
+ORC_API int orc_em_mask(const uint64_t* kmer, const uint64_t* offsets, uint64_t nseq, int A, int K, int W, int K_bg_model,
+                        const float* vbg_all, const float* alpha, float* v_all, float q, float f, float epsilon, int max_iter,
+                        float* r, float* llh_out, float* cutoff_out, uint64_t* nkept_out, float* n_all_out) {
+    int K_bg = K_bg_model < K ? K_bg_model : K;
+    uint64_t YK1 = orc_ipow(A, K + 1), Y1 = (uint64_t)A;
+    size_t total = v_offset(A, K + 1, W);
+    float* s = (float*)calloc(YK1 * (size_t)W, sizeof(float));
+    float* n_all = (float*)calloc(total, sizeof(float));
+    float* v_before = (float*)malloc(YK1 * (size_t)W * sizeof(float));
+    float* vK = v_all + v_offset(A, K, W);
+    uint64_t npos = offsets[nseq];
+    float* pos = (float*)calloc(npos ? npos : 1, sizeof(float));
+    /* (1) */
+    for (uint64_t y = 0; y < Y1; y++) for (int j = 0; j < W; j++) s[y * W + j] = v_all[y * W + j] / vbg_all[y];
+    uint64_t pos_count = 0;
+    for (uint64_t n = 0; n < nseq; n++) {
+        uint64_t L = offsets[n + 1] - offsets[n], LW1 = L - W + 1;
+        const uint64_t* km = kmer + offsets[n];
+        float* rn = r + offsets[n]; float* pn = pos + offsets[n];
+        float normFactor = 1.0f - q;
+        float pos_i = q / (float)LW1;
+        for (uint64_t i = 0; i < LW1; i++) { rn[i] = 1.0f; pn[i] = pos_i; }
+        for (uint64_t ij = 0; ij < L; ij++) {
+            uint64_t y = km[ij] % Y1;
+            uint64_t padding = ((int)(ij - L + W) > 0) * (ij - L + W);
+            for (uint64_t j = padding; j < ((uint64_t)W < ij ? (uint64_t)W : ij); j++) rn[L - W - ij + j] *= s[y * W + j];
+        }
+        for (uint64_t i = 0; i < LW1; i++) { rn[i] *= pn[L - W - i]; normFactor += rn[i]; }
+        for (uint64_t i = 0; i < LW1; i++) rn[i] /= normFactor;
+        pos_count += LW1;
+    }
+    /* (2) */
+    float* r_all = (float*)malloc((pos_count ? pos_count : 1) * sizeof(float));
+    { uint64_t c = 0; for (uint64_t n = 0; n < nseq; n++) { uint64_t L = offsets[n + 1] - offsets[n]; for (uint64_t i = 0; i < L - W + 1; i++) r_all[c++] = r[offsets[n] + i]; } }
+    qsort(r_all, pos_count, sizeof(float), cmp_float_desc);
+    float r_cutoff = r_all[(size_t)((float)pos_count * f)];
+    free(r_all);
+    uint64_t* ri_off = (uint64_t*)calloc(nseq + 1, sizeof(uint64_t));
+    for (uint64_t n = 0; n < nseq; n++) {
+        uint64_t L = offsets[n + 1] - offsets[n], c = 0;
+        for (uint64_t i = 0; i < L - W + 1; i++) if (r[offsets[n] + i] >= r_cutoff) c++;
+        ri_off[n + 1] = ri_off[n] + c;
+    }
+    uint64_t* ri = (uint64_t*)malloc((ri_off[nseq] ? ri_off[nseq] : 1) * sizeof(uint64_t));
+    for (uint64_t n = 0; n < nseq; n++) {
+        uint64_t L = offsets[n + 1] - offsets[n], c = ri_off[n];
+        for (uint64_t i = 0; i < L - W + 1; i++) if (r[offsets[n] + i] >= r_cutoff) ri[c++] = i;
+    }
+    if (cutoff_out) *cutoff_out = r_cutoff;
+    if (nkept_out) *nkept_out = ri_off[nseq];
+    /* (3) */
+    float llh = 0.0f, llh_prev;
+    int iterate = 1, it = 0;
+    while (iterate && it < max_iter) {
+        it++;
+        llh_prev = llh;
+        memcpy(v_before, vK, YK1 * (size_t)W * sizeof(float));
+        float llikelihood = 0.0f;
+        orc_linear_s(v_all, vbg_all, A, K, K_bg, W, s);
+        for (uint64_t n = 0; n < nseq; n++) {
+            uint64_t L = offsets[n + 1] - offsets[n], LW1 = L - W + 1;
+            const uint64_t* km = kmer + offsets[n];
+            float* rn = r + offsets[n]; float* pn = pos + offsets[n];
+            float normFactor = 1.0f - q;
+            float pos_i = q / (float)LW1;
+            for (uint64_t x = ri_off[n]; x < ri_off[n + 1]; x++) { rn[ri[x]] = 1.0f; pn[ri[x]] = pos_i; }
+            for (uint64_t x = ri_off[n]; x < ri_off[n + 1]; x++) {
+                uint64_t i = ri[x];
+                for (int j = 0; j < W; j++) { uint64_t y = km[L - W - i + j] % YK1; rn[i] *= s[y * W + j]; }
+                rn[i] *= pn[LW1 - i];
+                normFactor += rn[i];
+            }
+            rn[0] /= normFactor;
+            for (uint64_t x = ri_off[n]; x < ri_off[n + 1]; x++) rn[ri[x]] /= normFactor;
+            for (uint64_t i = LW1; i < L; i++) rn[i] = 0.0f;
+            llikelihood += logf(normFactor);
+        }
+        llh = llikelihood;
+        memset(n_all, 0, total * sizeof(float));
+        float* nK = n_all + v_offset(A, K, W);
+        for (uint64_t n = 0; n < nseq; n++) {
+            uint64_t L = offsets[n + 1] - offsets[n];
+            const uint64_t* km = kmer + offsets[n];
+            const float* rn = r + offsets[n];
+            for (uint64_t x = ri_off[n]; x < ri_off[n + 1]; x++) {
+                uint64_t i = ri[x];
+                for (int j = 0; j < W; j++) { uint64_t y = km[L - W - i + j] % YK1; nK[y * W + j] += rn[i]; }
+            }
+        }
+        uint64_t Y[16]; Y[0] = 1; for (int k = 1; k < 16; k++) Y[k] = Y[k - 1] * (uint64_t)A;
+        for (int k = K; k > 0; k--) {
+            float* nk = n_all + v_offset(A, k, W); float* nk1 = n_all + v_offset(A, k - 1, W);
+            for (uint64_t y = 0; y < Y[k + 1]; y++) {
+                uint64_t y2 = y % Y[k];
+                for (int j = 0; j < W; j++) nk1[y2 * W + j] += nk[y * W + j];
+            }
+        }
+        orc_update_v(n_all, alpha, vbg_all, A, K, W, v_all);
+        float v_diff = 0.0f;
+        for (size_t i = 0; i < YK1 * (size_t)W; i++) v_diff += fabsf(vK[i] - v_before[i]);
+        float llh_diff = llh - llh_prev;
+        if (v_diff < epsilon) iterate = 0;
+        if (llh_diff < 0 && it > 10) iterate = 0;
+    }
+    if (llh_out) *llh_out = llh;
+    if (n_all_out) memcpy(n_all_out, n_all, total * sizeof(float));
+    free(s); free(n_all); free(v_before); free(pos); free(ri_off); free(ri);
+    return it;
+}
+
 /* ---------------------------------------------------------------- ScoreSeqSet ---------- */
 /* reference: src/seq_scoring/ScoreSeqSet.cpp:25-67 (calcLogOdds) given the log table s (calculateLogS).
  * mops: sum(L_n - W + 1) floats (may be NULL), zoops/z: nseq entries. */

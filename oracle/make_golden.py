@@ -66,9 +66,12 @@ def write_inputs(tmp, seqs, sites):
     return fa, bs
 
 
-def run_case(name, fasta, sitefile, args, r_iters="1", max_iter=None, dump_neg=False, keep=None, extra_inputs=None, init=("--bindingSiteFile",)):
+def run_case(name, fasta, sitefile, args, r_iters="1", max_iter=None, dump_neg=False, keep=None, extra_inputs=None, init=("--bindingSiteFile",),
+             dump_mask=False):
     tmp = tempfile.mkdtemp(prefix="golden_")
     env = dict(os.environ, BAMM_DUMP_R_ITERS=r_iters, OMP_NUM_THREADS="1")
+    if dump_mask:
+        env["BAMM_DUMP_MASK"] = "1"
     if max_iter:
         env["BAMM_DUMP_MAXITER"] = str(max_iter)
     if dump_neg:
@@ -140,8 +143,27 @@ def neg_cases():
     shutil.rmtree(tmp)
 
 
+def mask_cases():
+    """EM::mask (--advanceEM) from the binding-site initial model: final model, r, counts and log likelihood of the reference."""
+    keep = lambda k: k.startswith("pos_") or k.startswith("bg_") or k in ("m1_v_init", "m1_alpha") or "_mask_" in k
+    tmp = tempfile.mkdtemp(prefix="golden_in_")
+    cases = [
+        ("mask_k2", dict(seed=31, nseq=60, L0=70, W=8), ["--EM", "-k", "2", "-K", "2"]),
+        ("mask_k3_ss", dict(seed=32, nseq=50, L0=90, W=10, n_frac=0.02), ["--EM", "-k", "3", "-K", "2", "--ss", "-q", "0.4"]),
+    ]
+    for name, kw, args in cases:
+        seqs, sites = synth(**kw)
+        d = os.path.join(tmp, name)
+        os.makedirs(d)
+        fa, bs = write_inputs(d, seqs, sites)
+        run_case(name, fa, bs, args, r_iters="", max_iter=1, keep=keep, dump_mask=True)
+    shutil.rmtree(tmp)
+
+
 def main():
     subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    if "--only-mask" in sys.argv:
+        return mask_cases()
     if "--only-pwm" in sys.argv:
         return pwm_case()
     if "--only-neg" in sys.argv:
@@ -169,6 +191,7 @@ def main():
     shutil.rmtree(tmp)
     pwm_case()
     neg_cases()
+    mask_cases()
 
 
 if __name__ == "__main__":

@@ -181,6 +181,23 @@ def em_optimize(kmer, offsets, A, K, W, K_bg_model, vbg_all, alpha, v_all, q, op
     return dict(v=v, q=float(qio.value), iterations=int(it), llh=llh[:it], vdiff=vd[:it], qtrace=qt[:it], n=n_all, r=r)
 
 
+def em_mask(kmer, offsets, A, K, W, K_bg_model, vbg_all, alpha, v_all, q, f=0.2, epsilon=0.01, max_iter=1000):
+    """EM::mask (EM.cpp:261-503, --advanceEM) without optimizeQ. Returns dict(iterations, v, r, llh, cutoff, nkept, n)."""
+    L = lib()
+    kmer = np.ascontiguousarray(kmer, np.uint64); offsets = np.ascontiguousarray(offsets, np.uint64)
+    v = np.ascontiguousarray(v_all, np.float32).copy()
+    vbg = np.ascontiguousarray(vbg_all, np.float32); al = np.ascontiguousarray(alpha, np.float32)
+    r = np.zeros(int(offsets[-1]), np.float32)
+    n_all = np.zeros(model_size(A, K, W), np.float32)
+    llh = C.c_float(0); cut = C.c_float(0); nk = C.c_uint64(0)
+    L.orc_em_mask.restype = C.c_int
+    it = L.orc_em_mask(_p(kmer, C.c_uint64), _p(offsets, C.c_uint64), C.c_uint64(len(offsets) - 1), A, K, W, K_bg_model,
+                       _p(vbg, C.c_float), _p(al, C.c_float), _p(v, C.c_float), C.c_float(q), C.c_float(f),
+                       C.c_float(epsilon), max_iter, _p(r, C.c_float), C.byref(llh), C.byref(cut), C.byref(nk),
+                       _p(n_all, C.c_float))
+    return dict(iterations=it, v=v, r=r, llh=llh.value, cutoff=cut.value, nkept=nk.value, n=n_all)
+
+
 def logodds(kmer, offsets, A, K, W, s, want_mops=True):
     """reference: src/seq_scoring/ScoreSeqSet.cpp:25-67. Returns (mops|None, zoops, z)."""
     nseq = len(offsets) - 1

@@ -224,6 +224,18 @@ int main(int nargs, char* args[]) {
             dump_f32(mp + "p_final", flat_v(motif->p_, K, W, Y));
             fprintf(meta, "motif %zu iterations %zu\n", m + 1, ref_iters);
         }
+        // EM::mask (--advanceEM, EM.cpp:261-503) from the same initial motif: final model, r, log likelihood
+        if (getenv("BAMM_DUMP_MASK")) {
+            Motif* motif_m = new Motif(*motif_set.getMotifs()[m]);
+            EM model(motif_m, bgModel, posSet, false, false, Global::f);
+            model.mask();
+            dump_f32(mp + "mask_v_final", flat_v(motif_m->getV(), K, W, Y));
+            std::vector<float> r;
+            for (size_t n = 0; n < posSet.size(); n++) for (size_t i = 0; i < posSet[n]->getL(); i++) r.push_back(model.r_[n][i]);
+            dump_f32(mp + "mask_r", r);
+            std::vector<float> l(1, model.llikelihood_); dump_f32(mp + "mask_llh", l);
+            dump_f32(mp + "mask_n", flat_v(model.n_, K, W, Y));
+        }
         motif->write(Global::outputDirectory, Global::outputFileBasename + "_motif_" + std::to_string(m + 1));
 
         // scoring of the positive set with the (learned) motif

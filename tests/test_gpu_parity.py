@@ -484,3 +484,24 @@ def test_device_sort_and_mops_pvalues(capi):
     assert np.all(np.abs(p[lin] - ref[lin]) <= 2e-7 * np.abs(ref[lin]))
     assert np.all(np.abs(p[tail] - ref[tail]) <= 2e-6 * np.abs(ref[tail]))
     assert np.array_equal(e, (p * np.float32(777)).astype(np.float32))
+
+
+@pytest.mark.parametrize("case", ["mask_k2", "mask_k3_ss"])
+def test_mask_advanced_em_against_reference(capi, oracle, case):
+    """Row f-4: bamm_em_mask against the reference's EM::mask (goldens made by ref_dump, f = 0.05). The first phase and the
+    selection are exact (same kept windows, same threshold); the iterations agree like the ordinary EM: same iteration
+    count, model within 1e-4, counts / r / llh within 1e-5-level tolerances."""
+    g = Golden(case)
+    ss = make_seqset(capi, g)
+    em = capi.EM(ss, g.W, g.K, g.K_bg_model)
+    em.set_model(g["m1_v_init"], g["bg_v"], g["m1_alpha"], g.q)
+    res = em.mask(f=0.05)
+    ref = oracle.em_mask(g["pos_kmer"], g["pos_offsets"], g.A, g.K, g.W, g.K_bg_model, g["bg_v"], g["m1_alpha"], g["m1_v_init"], float(g.q), f=0.05)
+    assert res["nkept"] == ref["nkept"] and np.float32(res["cutoff"]) == np.float32(ref["cutoff"])
+    assert res["iterations"] == ref["iterations"]
+    assert_rel(res["v"], g["m1_mask_v_final"], 1e-4, what="v")
+    assert abs(res["llh"] - float(g["m1_mask_llh"][0])) <= 1e-4 * abs(float(g["m1_mask_llh"][0]))
+    assert_rel(em.counts(), g["m1_mask_n"], 1e-4, atol=1e-8, what="n")
+    r, r_ref = em.r(), g["m1_mask_r"]
+    assert np.array_equal(r == 0, r_ref == 0)
+    assert_rel(r, r_ref, 2e-4, atol=1e-30, what="r")

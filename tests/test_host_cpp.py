@@ -281,3 +281,25 @@ def test_cli_against_reference_binary_on_fresh_data(bins, tmp_path):
     # (TP is cumulative: one swapped pair shifts a long stretch of rows by one, so only the size of the shift is bounded)
     assert np.max(np.abs(ba[:, 0] - bb[:, 0])) <= 0.005 * 3000
     assert abs(float(ha[6]) - float(hb[6])) <= 0.02                        # occurrence fraction in the header
+
+
+@pytest.mark.gpu
+def test_cli_advance_em_against_reference_binary(bins, tmp_path):
+    """--advanceEM (EM::mask) through both binaries on a seeded planted-motif set: the written models agree to the printed
+    digits."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "BaMMmotif_ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/BaMMmotif_ref not built")
+    from bammmotif2_b200 import synth
+    fwd, sites, _ = synth.planted_sequences(777, 1500, 100, 10)
+    fa, bs = str(tmp_path / "syn.fasta"), str(tmp_path / "sites.block")
+    synth.write_fasta(fa, fwd)
+    synth.write_sites(bs, sites)
+    args = ["--bindingSiteFile", bs, "--EM", "-k", "2", "-K", "2", "--advanceEM"]
+    run([ref, str(tmp_path / "ref"), fa] + args + ["--threads", "1"], env=dict(os.environ, OMP_NUM_THREADS="1"))
+    run([os.path.join(bins, "BaMMmotif"), str(tmp_path / "our"), fa] + args)
+    for fn in ("syn.hbcp", "syn.hbp"):
+        assert open(tmp_path / "ref" / fn, "rb").read() == open(tmp_path / "our" / fn, "rb").read(), fn
+    for fn in ("syn_motif_1.ihbcp", "syn_motif_1.ihbp"):
+        a, b = parse_numbers(open(tmp_path / "ref" / fn, "rb").read()), parse_numbers(open(tmp_path / "our" / fn, "rb").read())
+        assert a.shape == b.shape and np.all(np.abs(a - b) <= 1.2e-3 * np.abs(a) + 1e-30), fn

@@ -89,3 +89,16 @@ def test_double_accumulation_close_to_float(oracle):
     nf = oracle.mstep(g["pos_kmer"], g["pos_offsets"], g.A, g.K, g.W, r)
     nd = oracle.mstep(g["pos_kmer"], g["pos_offsets"], g.A, g.K, g.W, r, accumulate_double=True)
     assert np.allclose(nf, nd, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["mask_k2", "mask_k3_ss"])
+def test_oracle_mask_matches_reference_bit_exact(case):
+    """orc_em_mask (restatement of EM::mask, EM.cpp:261-503, --advanceEM with the driver's default f = 0.05) against the
+    reference's own mask() run single-threaded: final model, responsibilities, counts and log likelihood, every bit."""
+    from oracle import oracle as orc
+    g = Golden(case)
+    res = orc.em_mask(g["pos_kmer"], g["pos_offsets"], g.A, g.K, g.W, g.K_bg_model, g["bg_v"], g["m1_alpha"], g["m1_v_init"], float(g.q), f=0.05)
+    assert np.array_equal(res["v"], g["m1_mask_v_final"])
+    assert np.array_equal(res["r"], g["m1_mask_r"])
+    assert np.array_equal(res["n"], g["m1_mask_n"])
+    assert np.float32(res["llh"]) == g["m1_mask_llh"][0]
