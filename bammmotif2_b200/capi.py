@@ -64,6 +64,7 @@ SIGNATURES = {
     "bamm_em_peer_alloc": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "bamm_em_peer_attach": (C.c_int, [_vp, _vp]),
     "bamm_score_last_timing": (C.c_int, [_f32p]),
+    "bamm_seqset_sample_pwm_sites": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, _f32p, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_int32), _u64p]),
     "bamm_sort_scores": (C.c_int, [_f32p, C.c_uint64, C.c_int]),
     "bamm_mops_pvalues": (C.c_int, [_f32p, C.c_uint64, _f32p, C.c_uint64, C.c_uint64, _f32p, _f32p]),
     "bamm_score_logodds": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _u64p, _f32p]),

@@ -1858,3 +1858,61 @@ extern "C" int bamm_seqset_finish_patches(bamm_seqset* s, const uint64_t* patch_
     }
     return seqset_finish(s);                                   // destroys the set on failure
 }
+
+// ------------------------------------------------------------------------------------------- Motif::initFromPWM sampling (row f-4)
+extern "C" int bamm_seqset_sample_pwm_sites(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int asize,
+                                            const float* score, float q, const double* uniforms, int32_t* n_all, uint64_t* z_out) {
+    REQUIRE(s && score && uniforms && n_all, "NULL argument");
+    REQUIRE(W >= 1 && W <= 32, "motif width W=%d not in [1,32]", W);
+    REQUIRE(K >= 0 && K <= 10, "order K=%d not in [0,10]", K);
+    REQUIRE(asize >= 1 && asize <= 6, "PWM alphabet size %d not in [1,6]", asize);
+    if (!subset) nsub = s->nseq;
+    REQUIRE(nsub < (1ull << 32), "subset too large");
+    ModelDims d; fill_dims(d, s->A, K, W, 0);
+    const size_t msize = d.voff[K + 1];
+    std::vector<uint32_t> ids(nsub);
+    uint64_t maxL = 0;
+    for (uint64_t i = 0; i < nsub; i++) {
+        const uint64_t n = subset ? subset[i] : i;
+        REQUIRE(n < s->nseq, "subset index out of range");
+        const uint64_t L = s->h_off[n + 1] - s->h_off[n];
+        REQUIRE(L >= (uint64_t)W, "sequence %llu is shorter than the motif", (unsigned long long)n);
+        ids[i] = (uint32_t)n;
+        maxL = std::max(maxL, L);
+    }
+    const int Kidx = K > 1 ? K : 1;                              // kmer % asize needs an index whose modulus asize divides (6^2 = 36 for the 4-letter PWM on ACGTMH)
+    IndexArray* ia = nullptr;
+    { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, Kidx, &ia); if (rc) return rc; }
+    CU(cudaSetDevice(s->device));
+    const int grid = s->sm_count * 8, warps = grid * 8;
+    const uint64_t stride = ((maxL + 1 + 31) / 32) * 32;
+    uint32_t *d_ids = nullptr, *d_voff = nullptr; float *d_score = nullptr, *d_scratch = nullptr; double* d_u = nullptr; int* d_n = nullptr;
+    unsigned long long* d_z = nullptr;
+    int rc = BAMM_OK;
+#define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
+    {
+        CUX(cudaMalloc(&d_ids, (nsub ? nsub : 1) * 4));
+        CUX(cudaMemcpy(d_ids, ids.data(), nsub * 4, cudaMemcpyHostToDevice));
+        CUX(cudaMalloc(&d_voff, 16 * 4));
+        CUX(cudaMemcpy(d_voff, d.voff, 16 * 4, cudaMemcpyHostToDevice));
+        CUX(cudaMalloc(&d_score, (size_t)asize * W * 4));
+        CUX(cudaMemcpy(d_score, score, (size_t)asize * W * 4, cudaMemcpyHostToDevice));
+        CUX(cudaMalloc(&d_u, (nsub ? nsub : 1) * 8));
+        CUX(cudaMemcpy(d_u, uniforms, nsub * 8, cudaMemcpyHostToDevice));
+        CUX(cudaMalloc(&d_scratch, (uint64_t)warps * stride * 4));
+        CUX(cudaMalloc(&d_n, msize * 4));
+        CUX(cudaMemset(d_n, 0, msize * 4));
+        if (z_out) CUX(cudaMalloc(&d_z, (nsub ? nsub : 1) * 8));
+        if (ia->bytes == 2) k_pwm_sample_sites<uint16_t><<<grid, 256>>>((const uint16_t*)ia->d, s->d_off, d_ids, (uint32_t)nsub, W, K, (uint32_t)s->A, (uint32_t)asize,
+                                                                        d_score, q, d_u, d_scratch, stride, d_n, d_voff, d_z);
+        else                k_pwm_sample_sites<uint32_t><<<grid, 256>>>((const uint32_t*)ia->d, s->d_off, d_ids, (uint32_t)nsub, W, K, (uint32_t)s->A, (uint32_t)asize,
+                                                                        d_score, q, d_u, d_scratch, stride, d_n, d_voff, d_z);
+        CUX(cudaGetLastError());
+        CUX(cudaMemcpy(n_all, d_n, msize * 4, cudaMemcpyDeviceToHost));
+        if (z_out) CUX(cudaMemcpy(z_out, d_z, nsub * 8, cudaMemcpyDeviceToHost));
+    }
+done:
+#undef CUX
+    cudaFree(d_ids); cudaFree(d_voff); cudaFree(d_score); cudaFree(d_u); cudaFree(d_scratch); cudaFree(d_n); cudaFree(d_z);
+    return rc;
+}

@@ -176,3 +176,73 @@ k_mask_mstep(const YT* __restrict__ Y, MaskView mv, int W, uint32_t Yn, const ui
 }
 
 }  // namespace bamm
+
+namespace bamm {
+
+// ---- Motif::initFromPWM, the sampling step (src/init/Motif.cpp:236-299) -------------------------------
+// Per sequence: posterior of the motif start over the LW1 windows plus "no motif" from the order-0 odds `score` (float, the
+// reference's operation order: products in ascending j, normaliser summed for i = 1..LW1 and then the no-motif term), one
+// site z drawn from it the way libstdc++'s std::discrete_distribution does (probabilities and cumulative sums in double, last
+// sum forced to 1.0, lower_bound of a uniform double that the HOST takes from std::mt19937 in sequence order), and the
+// k-mer counts n[k][y][j] += 1 of the sampled site for every order k <= K. Y: index array of order >= max(K,1).
+// One warp per sequence; scratch: one row of max(LW1)+1 floats per warp.
+template <typename YT>
+__global__ void __launch_bounds__(256)
+k_pwm_sample_sites(const YT* __restrict__ Y, const uint64_t* __restrict__ seq_off, const uint32_t* __restrict__ ids, uint32_t nsub,
+                   int W, int K, uint32_t A, uint32_t asize, const float* __restrict__ score_g /* [asize][W] */, float q,
+                   const double* __restrict__ uniforms, float* __restrict__ scratch, uint64_t scratch_stride,
+                   int* __restrict__ n_all, const uint32_t* __restrict__ voff /* [K+2] */, unsigned long long* __restrict__ z_out) {
+    __shared__ float score[6 * 32];
+    for (uint32_t i = threadIdx.x; i < asize * (uint32_t)W; i += blockDim.x) score[i] = score_g[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    float* __restrict__ r = scratch + (uint64_t)warp * scratch_stride;
+    for (uint32_t li = warp; li < nsub; li += nwarps) {
+        const uint32_t n = ids[li];
+        const uint64_t base = seq_off[n], L = seq_off[n + 1] - base, LW1 = L - W + 1;
+        const YT* __restrict__ yn = Y + base;
+        const float pos0 = 1.0f - q, pos1 = q / (float)LW1;
+        for (uint64_t i = 1 + lane; i <= LW1; i += 32) {
+            float v = 1.0f;
+            for (int j = 0; j < W; j++) v *= score[((uint32_t)yn[i - 1 + j] % asize) * W + j];
+            r[i] = v * pos1;
+        }
+        __syncwarp();
+        float norm = 0.0f;
+        if (lane == 0) {
+            for (uint64_t i = 1; i <= LW1; i++) norm += r[i];
+            r[0] = pos0;
+            norm += r[0];
+        }
+        norm = __shfl_sync(FULL, norm, 0);
+        __syncwarp();
+        for (uint64_t i = lane; i <= LW1; i += 32) r[i] /= norm;
+        __syncwarp();
+        unsigned long long z = 0;
+        if (lane == 0) {
+            double sum = 0.0;
+            for (uint64_t i = 0; i <= LW1; i++) sum += (double)r[i];
+            const double p = uniforms[li];
+            double run = 0.0;
+            z = LW1;                                                        // the last cumulative sum is forced to 1.0
+            for (uint64_t i = 0; i < LW1; i++) {
+                run += (double)r[i] / sum;
+                if (!(run < p)) { z = i; break; }                           // lower_bound: first cumulative sum >= p
+            }
+        }
+        z = __shfl_sync(FULL, z, 0);
+        if (z_out && lane == 0) z_out[li] = z;
+        if (z > 0) {
+            uint32_t Yk1 = A;
+            for (int k = 0; k <= K; k++) {
+                for (int j = lane; j < W; j += 32) atomicAdd(&n_all[voff[k] + ((uint32_t)yn[z - 1 + j] % Yk1) * W + j], 1);
+                Yk1 *= A;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace bamm

@@ -4,6 +4,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <limits>
 #include <random>
 #include <sstream>
 
@@ -152,6 +153,22 @@ void Motif::initFromPWM( float** PWM, size_t asize, SequenceSet* posSeqset, floa
     for( Sequence* s : posSet ){ if( s->getL() < W_ ) count++; else kept.push_back( s ); }
     if( count > 0 ) std::cout << "Note: " << count << " short sequences have been neglected for sampling PWM." << std::endl;
 
+    // Large sets: the posteriors, the draws and the counting run on the device (bamm_seqset_sample_pwm_sites); the host
+    // only advances the generator the way std::discrete_distribution would (one generate_canonical<double,53> per
+    // sequence, in order). BAMM_DEVICE_PWMINIT=1 / 0 forces either path.
+    const char* force = getenv( "BAMM_DEVICE_PWMINIT" );
+    if( !kept.empty() && ( force ? atoi( force ) != 0 : kept.size() >= 20000 ) ){
+        std::vector<double> uniforms( kept.size() );
+        for( size_t n = 0; n < kept.size(); n++ ) uniforms[n] = std::generate_canonical<double, std::numeric_limits<double>::digits>( rngx );
+        std::vector<uint64_t> indices;
+        bool whole = false;
+        SequenceSet* set = SequenceSet::commonSet( kept, indices, &whole );
+        static_assert( sizeof( int ) == sizeof( int32_t ), "count table type" );
+        BAMM_CHECK( bamm_seqset_sample_pwm_sites( set->device(), whole ? NULL : indices.data(), indices.size(), static_cast<int>( W_ ),
+                                                  static_cast<int>( K_ ), static_cast<int>( asize ), score.data(), q, uniforms.data(),
+                                                  reinterpret_cast<int32_t*>( n_.data() ), NULL ) );
+        kept.clear();                                            // nothing left for the host loop
+    }
     for( size_t n = 0; n < kept.size(); n++ ){
         const size_t LW1 = kept[n]->getL() - W_ + 1;
         size_t* kmer = kept[n]->getKmer();

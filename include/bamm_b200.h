@@ -205,6 +205,17 @@ int bamm_seqset_code_windows(bamm_seqset* s, const uint64_t* pos, const uint64_t
                              uint8_t* windows /* [n][21] */);
 int bamm_seqset_finish_patches(bamm_seqset* s, const uint64_t* patch_pos, const uint64_t* patch_kmer, uint64_t npatch);
 
+/*
+ * The sampling step of Motif::initFromPWM (src/init/Motif.cpp:236-299): for every listed sequence the
+ * posterior of the motif start under the order-0 odds `score[y][j] = v[0][y][j] / vbg[0][y]` (y < asize, the PWM's alphabet
+ * size; k-mers are reduced modulo asize like the reference does), one site per sequence drawn like std::discrete_distribution
+ * draws it from `uniforms[n]` (the caller takes them from std::mt19937 with std::generate_canonical<double,53>, in sequence
+ * order), and the integer k-mer counts n[k][y][j] of the sampled sites for all orders k <= K (flat, the model's index order).
+ * z_out (nullable): the sampled outcome per sequence, 0 = no motif, z = window start + 1.
+ */
+int bamm_seqset_sample_pwm_sites(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int asize,
+                                 const float* score, float q, const double* uniforms, int32_t* n_all, uint64_t* z_out);
+
 /* ---- score statistics   ---------------------------------------------------------------- */
 /* Sorts n scores in place (host buffer in and out) with a device radix sort: the std::sort calls of FDR::calculatePR
  * (src/evaluation/FDR.cpp:161-162, 207-208) and ScoreSeqSet::calcPvalues (src/seq_scoring/ScoreSeqSet.cpp:85). */

@@ -126,6 +126,24 @@ def test_pwm_initialisation_bit_exact(bins, tmp_path):
         assert np.array_equal(np.fromfile(tmp_path / ("v_init_%d.f32" % m), np.float32), g["m%d_v_init" % m]), m
 
 
+@pytest.mark.gpu
+def test_pwm_initialisation_on_the_device_bit_exact(bins, tmp_path):
+    """Row f-4: the sampling step of Motif::initFromPWM on the device (float posteriors in the reference's order, the draw of
+    std::discrete_distribution restated in double, integer k-mer counts): the initial models equal the reference's."""
+    g = Golden("jund_pwm_k1")
+    fa = tmp_path / "JunD.fasta"
+    open(fa, "wb").write(bytes(Golden("jund_k2")["fasta_text"]))
+    meme = tmp_path / "pwm.meme"
+    open(meme, "wb").write(bytes(g["sites_text"]))
+    g["bg_n"].tofile(tmp_path / "bgn.u64")
+    g.bg_alpha().tofile(tmp_path / "abg.f32")
+    run([os.path.join(bins, "host_check"), "pwminit", "STANDARD", str(fa), "0", str(g.K), str(g.K_bg_model),
+         str(tmp_path / "bgn.u64"), str(tmp_path / "abg.f32"), str(meme), "2", repr(float(g.q)), str(tmp_path)],
+        env=dict(os.environ, BAMM_DEVICE_PWMINIT="1"))
+    for m in (1, 2):
+        assert np.array_equal(np.fromfile(tmp_path / ("v_init_%d.f32" % m), np.float32), g["m%d_v_init" % m]), m
+
+
 def test_negative_sampling_bit_exact(bins, tmp_path):
     """The serial host sampler (kept as the fall-back of the device sampler, SeqGenerator.cpp of the host side)."""
     g = Golden("syn_k3_fdr")
