@@ -5,6 +5,7 @@
 #include "packed.cuh"
 #include "negatives.cuh"
 #include "stats.cuh"
+#include <cub/device/device_scan.cuh>
 #include "fasta.cuh"
 #include "mask.cuh"
 
@@ -211,11 +212,19 @@ static int seqset_new(const uint64_t* offsets, uint64_t nseq, int A, bamm_seqset
 }
 
 // classification + 2-bit packing on the device (no host pass over the bases); d_codes and the patch list are in place
-static int seqset_finish(bamm_seqset* s) {
+// known_regular: the caller vouches that every code is in 1..4 (a set the library sampled itself): no classification pass
+static int seqset_finish(bamm_seqset* s, bool known_regular = false) {
     const uint64_t nseq = s->nseq, npatch = s->npatch;
+    Trace tr("seqset_finish");
     s->h_kind.assign(nseq, 0);
+    if (s->A == 4 && nseq && known_regular) {
+        CUS(cudaMalloc(&s->d_kind, nseq));
+        CUS(cudaMemset(s->d_kind, 1, nseq));
+        s->h_kind.assign(nseq, 1);
+    }
     if (s->A == 4 && nseq) {
         uint32_t* d_cover = nullptr;
+        if (!known_regular) {
         CUS(cudaMalloc(&s->d_kind, nseq));
         CUS(cudaMalloc(&d_cover, nseq * sizeof(uint32_t)));
         CUS(cudaMemset(d_cover, 0, nseq * sizeof(uint32_t)));
@@ -225,26 +234,36 @@ static int seqset_finish(bamm_seqset* s) {
         cudaError_t ec = cudaMemcpy(s->h_kind.data(), s->d_kind, nseq, cudaMemcpyDeviceToHost);
         cudaFree(d_cover);
         CUS(ec);
-        std::vector<PackedSeq> ps(nseq);
-        uint64_t w = 0;
-        for (uint64_t n = 0; n < nseq; n++) {
-            PackedSeq q; q.word_off = 0; q.L = 0; q.mid = 0xffffffffu;
-            if (s->h_kind[n]) {
-                const uint64_t L = s->h_off[n + 1] - s->h_off[n];
-                q.word_off = w + 2; q.L = (uint32_t)L; q.mid = s->h_kind[n] == 2 ? (uint32_t)((L - 1) / 2) : 0xffffffffu;
-                w += (L + 15) / 16 + 8;                       // pad pad | data | 6 pads (the E-step prefetches ahead)
-                s->nregular++;
-            }
-            ps[n] = q;
         }
-        s->nwords = w;
+        tr.mark("classify + kinds D2H");
+        // packed-stream layout on the device: word counts -> exclusive scan -> PackedSeq records (no host pass, no upload)
+        for (uint64_t n = 0; n < nseq; n++) s->nregular += s->h_kind[n] != 0;
         if (s->nregular) {
-            CUS(cudaMalloc(&s->d_pseq, nseq * sizeof(PackedSeq)));
-            CUS(cudaMemcpy(s->d_pseq, ps.data(), nseq * sizeof(PackedSeq), cudaMemcpyHostToDevice));
-            CUS(cudaMalloc(&s->d_words, (w + 16) * sizeof(uint32_t)));    // slack: the rolling fetch of the last sequence runs a few words ahead
+            unsigned long long* d_wc = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0;
+            CUS(cudaMalloc(&d_wc, (nseq + 1) * 2 * sizeof(unsigned long long)));
+            unsigned long long* d_scan = d_wc + nseq + 1;
+            CUS(cudaMemset(d_wc + nseq, 0, sizeof(unsigned long long)));            // sentinel: the scan's last entry is the total
+            k_word_counts<<<(unsigned)((nseq + 255) / 256), 256>>>(s->d_off, nseq, s->d_kind, d_wc);
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wc, d_scan, (int)(nseq + 1));
+            cudaError_t es = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
+            if (es == cudaSuccess) es = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_wc, d_scan, (int)(nseq + 1));
+            unsigned long long w = 0;
+            if (es == cudaSuccess) es = cudaMemcpy(&w, d_scan + nseq, sizeof(w), cudaMemcpyDeviceToHost);
+            if (es == cudaSuccess) es = cudaMalloc(&s->d_pseq, nseq * sizeof(PackedSeq));
+            if (es == cudaSuccess) {
+                k_fill_pseq<<<(unsigned)((nseq + 255) / 256), 256>>>(s->d_off, nseq, s->d_kind, d_scan, s->d_pseq);
+                es = cudaGetLastError();
+            }
+            cudaFree(d_tmp); cudaFree(d_wc);
+            CUS(es);
+            s->nwords = w;
+            tr.mark("layout scan");
+            CUS(cudaMalloc(&s->d_words, (w + 16) * sizeof(uint32_t)));
+            tr.mark("words alloc");    // slack: the rolling fetch of the last sequence runs a few words ahead
             k_pack<<<s->sm_count * 8, 256>>>(s->d_codes, s->d_off, nseq, s->d_kind, s->d_pseq, s->d_words);
             CUS(cudaGetLastError());
             CUS(cudaDeviceSynchronize());
+            tr.mark("pack kernel");
         }
     }
     return BAMM_OK;
@@ -1487,7 +1506,7 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
             goto done;
         }
         tr.mark("sampling kernel");
-        rc = seqset_finish(neg);
+        rc = seqset_finish(neg, true);                         // sampled codes are 1..A by construction (flags checked above)
         tr.mark("classify + pack");
         if (rc) { neg = nullptr; goto done; }                  // seqset_finish destroys the set on failure
     }

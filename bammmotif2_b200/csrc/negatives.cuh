@@ -197,6 +197,10 @@ k_neg_sample(const uint64_t* __restrict__ off /* [nseq+1] prefix sums of the TEM
     int idx = 0;
     const uint32_t A = d.Y1;
     bool bad = false;
+    // the thread's negatives are contiguous in the output: whole 32-bit words are stored at once, single bytes only at the
+    // unaligned head and tail of its range
+    const uint64_t head_end = (o + 3) & ~3ull;                  // first 4-byte aligned output offset of this thread
+    uint32_t acc = 0;
     for (; g < gend; g++) {
         const float* __restrict__ rb1 = rb + tmpl * (uint64_t)(d.Y2 + d.Y3);
         const float* __restrict__ rb2 = rb1 + d.Y2;
@@ -217,7 +221,12 @@ k_neg_sample(const uint64_t* __restrict__ off /* [nseq+1] prefix sums of the TEM
                 code = A;
                 for (uint32_t a = 0; a + 1 < A; a++) if (rnd <= bar[a]) { code = a + 1; break; }
             }
-            codes[o + i] = (uint8_t)code;
+            const uint64_t a = o + i;
+            if (a < head_end) codes[a] = (uint8_t)code;
+            else {
+                acc |= code << (8 * (uint32_t)(a & 3));
+                if ((a & 3) == 3) { *reinterpret_cast<uint32_t*>(codes + (a - 3)) = acc; acc = 0; }
+            }
             c2 = c1; c1 = code - 1;
         }
         o += L;
@@ -226,6 +235,7 @@ k_neg_sample(const uint64_t* __restrict__ off /* [nseq+1] prefix sums of the TEM
             if (tmpl < nseq) { tbase = off[tmpl]; L = off[tmpl + 1] - tbase; }
         }
     }
+    if (o > head_end) for (uint64_t a = o & ~3ull; a < o; a++) codes[a] = (uint8_t)(acc >> (8 * (uint32_t)(a & 3)));   // tail bytes of a partial word
     if (bad) flags[0] = 1u;
 }
 

@@ -95,6 +95,26 @@ __global__ void k_finish_kinds(const uint64_t* __restrict__ off, uint64_t nseq, 
     }
 }
 
+// words of every regular sequence in the packed stream: data words + 2 pad words in front + 6 behind (0 for irregular ones)
+__global__ void k_word_counts(const uint64_t* __restrict__ off, uint64_t nseq, const uint8_t* __restrict__ kind, unsigned long long* __restrict__ wc) {
+    const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nseq) return;
+    const uint64_t L = off[n + 1] - off[n];
+    wc[n] = kind[n] ? (L + 15) / 16 + 8 : 0ull;
+}
+// PackedSeq records from the exclusive scan of the word counts
+__global__ void k_fill_pseq(const uint64_t* __restrict__ off, uint64_t nseq, const uint8_t* __restrict__ kind,
+                            const unsigned long long* __restrict__ wscan, PackedSeq* __restrict__ seqs) {
+    const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nseq) return;
+    PackedSeq q; q.word_off = 0; q.L = 0; q.mid = 0xffffffffu;
+    if (kind[n]) {
+        const uint64_t L = off[n + 1] - off[n];
+        q.word_off = wscan[n] + 2; q.L = (uint32_t)L; q.mid = kind[n] == 2 ? (uint32_t)((L - 1) / 2) : 0xffffffffu;
+    }
+    seqs[n] = q;
+}
+
 // one lane per output word (16 bases)
 __global__ void k_pack(const uint8_t* __restrict__ codes, const uint64_t* __restrict__ off, uint64_t nseq,
                        const uint8_t* __restrict__ kind, const PackedSeq* __restrict__ seqs,
