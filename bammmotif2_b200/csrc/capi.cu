@@ -35,6 +35,35 @@ static int fail(int code, const char* fmt, ...) {
     return fail(e_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define REQUIRE(cond, ...) do { if (!(cond)) return fail(BAMM_E_INVALID, __VA_ARGS__); } while (0)
 
+// Device memory comes from the device's default memory pool (cudaMallocAsync) with an unlimited release threshold: buffers a
+// finished object gives back stay mapped, so creating the next sequence set / EM object / scoring call does not pay the
+// driver's map-and-zero cost again (measured: the same 1-12 GB allocations vary between 3 ms and 150 ms with cudaMalloc
+// after a large cudaFree). cudaFree() returns pool memory to the pool. Falls back to cudaMalloc where pools are missing.
+static cudaError_t pool_malloc(void** p, size_t bytes) {
+    static thread_local int ready_dev = -1;
+    static thread_local bool usable = false;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (ready_dev != dev) {
+        int supported = 0;
+        usable = !getenv("BAMM_NO_MEMPOOL") && cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && supported;
+        if (usable) {
+            cudaMemPool_t pool;
+            unsigned long long thr = ~0ull;
+            usable = cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess &&
+                     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess;
+        }
+        cudaGetLastError();
+        ready_dev = dev;
+    }
+    if (!usable) return cudaMalloc(p, bytes);
+    e = cudaMallocAsync(p, bytes, 0);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(0);                          // the buffer is used from other (non-blocking) streams right away
+}
+template <typename T> static cudaError_t dev_malloc(T** p, size_t bytes) { return pool_malloc(reinterpret_cast<void**>(p), bytes); }
+
 // BAMM_TRACE=1: wall-clock phases of the set-up calls on stderr (diagnostics of the end-to-end path)
 #include <chrono>
 struct Trace {
@@ -204,8 +233,8 @@ static int seqset_new(const uint64_t* offsets, uint64_t nseq, int A, bamm_seqset
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
 #define CUS(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { bamm_seqset_destroy(s); \
     return fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); } } while (0)
-    CUS(cudaMalloc(&s->d_codes, npos ? npos : 1));
-    CUS(cudaMalloc(&s->d_off, (nseq + 1) * sizeof(uint64_t)));
+    CUS(dev_malloc(&s->d_codes, npos ? npos : 1));
+    CUS(dev_malloc(&s->d_off, (nseq + 1) * sizeof(uint64_t)));
     CUS(cudaMemcpy(s->d_off, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     *out = s;
     return BAMM_OK;
@@ -218,15 +247,15 @@ static int seqset_finish(bamm_seqset* s, bool known_regular = false) {
     Trace tr("seqset_finish");
     s->h_kind.assign(nseq, 0);
     if (s->A == 4 && nseq && known_regular) {
-        CUS(cudaMalloc(&s->d_kind, nseq));
+        CUS(dev_malloc(&s->d_kind, nseq));
         CUS(cudaMemset(s->d_kind, 1, nseq));
         s->h_kind.assign(nseq, 1);
     }
     if (s->A == 4 && nseq) {
         uint32_t* d_cover = nullptr;
         if (!known_regular) {
-        CUS(cudaMalloc(&s->d_kind, nseq));
-        CUS(cudaMalloc(&d_cover, nseq * sizeof(uint32_t)));
+        CUS(dev_malloc(&s->d_kind, nseq));
+        CUS(dev_malloc(&d_cover, nseq * sizeof(uint32_t)));
         CUS(cudaMemset(d_cover, 0, nseq * sizeof(uint32_t)));
         k_classify<<<s->sm_count * 8, 256>>>(s->d_codes, s->d_off, nseq, s->d_kind);
         if (npatch) k_check_patches<<<(unsigned)((npatch + 255) / 256), 256>>>(s->d_ppos, npatch, s->d_off, nseq, s->d_kind, d_cover);
@@ -240,16 +269,16 @@ static int seqset_finish(bamm_seqset* s, bool known_regular = false) {
         for (uint64_t n = 0; n < nseq; n++) s->nregular += s->h_kind[n] != 0;
         if (s->nregular) {
             unsigned long long* d_wc = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0;
-            CUS(cudaMalloc(&d_wc, (nseq + 1) * 2 * sizeof(unsigned long long)));
+            CUS(dev_malloc(&d_wc, (nseq + 1) * 2 * sizeof(unsigned long long)));
             unsigned long long* d_scan = d_wc + nseq + 1;
             CUS(cudaMemset(d_wc + nseq, 0, sizeof(unsigned long long)));            // sentinel: the scan's last entry is the total
             k_word_counts<<<(unsigned)((nseq + 255) / 256), 256>>>(s->d_off, nseq, s->d_kind, d_wc);
             cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wc, d_scan, (int)(nseq + 1));
-            cudaError_t es = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
+            cudaError_t es = dev_malloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
             if (es == cudaSuccess) es = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_wc, d_scan, (int)(nseq + 1));
             unsigned long long w = 0;
             if (es == cudaSuccess) es = cudaMemcpy(&w, d_scan + nseq, sizeof(w), cudaMemcpyDeviceToHost);
-            if (es == cudaSuccess) es = cudaMalloc(&s->d_pseq, nseq * sizeof(PackedSeq));
+            if (es == cudaSuccess) es = dev_malloc(&s->d_pseq, nseq * sizeof(PackedSeq));
             if (es == cudaSuccess) {
                 k_fill_pseq<<<(unsigned)((nseq + 255) / 256), 256>>>(s->d_off, nseq, s->d_kind, d_scan, s->d_pseq);
                 es = cudaGetLastError();
@@ -258,7 +287,7 @@ static int seqset_finish(bamm_seqset* s, bool known_regular = false) {
             CUS(es);
             s->nwords = w;
             tr.mark("layout scan");
-            CUS(cudaMalloc(&s->d_words, (w + 16) * sizeof(uint32_t)));
+            CUS(dev_malloc(&s->d_words, (w + 16) * sizeof(uint32_t)));
             tr.mark("words alloc");    // slack: the rolling fetch of the last sequence runs a few words ahead
             k_pack<<<s->sm_count * 8, 256>>>(s->d_codes, s->d_off, nseq, s->d_kind, s->d_pseq, s->d_words);
             CUS(cudaGetLastError());
@@ -285,13 +314,13 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
     CUS(cudaMemcpy(s->d_codes, codes, npos, cudaMemcpyHostToDevice));
     tr.mark("codes H2D");
     if (npatch) {
-        CUS(cudaMalloc(&s->d_ppos, npatch * sizeof(uint64_t)));
-        CUS(cudaMalloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
+        CUS(dev_malloc(&s->d_ppos, npatch * sizeof(uint64_t)));
+        CUS(dev_malloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
         CUS(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CUS(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
         // the list must be strictly increasing and inside the set: checked on the device (11 entries per both-strand sequence)
         uint32_t* d_bad = nullptr; uint32_t bad = 0;
-        CUS(cudaMalloc(&d_bad, sizeof(uint32_t)));
+        CUS(dev_malloc(&d_bad, sizeof(uint32_t)));
         cudaMemset(d_bad, 0, sizeof(uint32_t));
         k_validate_patches<<<(unsigned)((npatch + 255) / 256), 256>>>(s->d_ppos, npatch, npos, d_bad);
         cudaError_t ev = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
@@ -333,7 +362,7 @@ static int seqset_index_locked(bamm_seqset* s, int K, IndexArray** out) {
     REQUIRE(Yn <= (1ull << 31), "A^(K+1) too large");
     IndexArray ia; ia.Yn = Yn; ia.bytes = (Yn <= 65536) ? 2 : 4;
     CU(cudaSetDevice(s->device));
-    CU(cudaMalloc(&ia.d, (s->npos ? s->npos : 1) * (uint64_t)ia.bytes));
+    CU(dev_malloc(&ia.d, (s->npos ? s->npos : 1) * (uint64_t)ia.bytes));
     const int block = 256;
     const int grid = s->sm_count * 8;
     if (s->nseq) {
@@ -368,7 +397,7 @@ static int seqset_ypatch_locked(bamm_seqset* s, int K, uint16_t** out) {
     uint16_t* d = nullptr;
     CU(cudaSetDevice(s->device));
     const uint64_t bytes = (s->nseq ? s->nseq : 1) * (uint64_t)(K + 1) * sizeof(uint16_t);
-    CU(cudaMalloc(&d, bytes));
+    CU(dev_malloc(&d, bytes));
     CU(cudaMemset(d, 0, bytes));
     if (s->npatch) {
         k_make_ypatch<<<(unsigned)((s->npatch + 255) / 256), 256>>>(s->d_ppos, s->d_pkmer, s->npatch, s->d_off, s->nseq, s->d_kind, K, Yn, d);
@@ -398,7 +427,7 @@ extern "C" int bamm_seqset_count_kmers(bamm_seqset* s, int K, uint64_t* n_all) {
     { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
     CU(cudaSetDevice(s->device));
     unsigned long long* d_cnt;
-    CU(cudaMalloc(&d_cnt, ia->Yn * 8));
+    CU(dev_malloc(&d_cnt, ia->Yn * 8));
     CU(cudaMemset(d_cnt, 0, ia->Yn * 8));
     if (s->npos) {
         const uint32_t Yn = (uint32_t)ia->Yn;
@@ -611,8 +640,19 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     em->h_r_off.resize(nsub + 1);
     std::vector<uint32_t> ids(nsub), gen_ids, pk_ids;
     std::vector<uint64_t> gen_roff, pk_roff;
+    pk_ids.reserve(nsub); pk_roff.reserve(nsub);
     em->h_r_off[0] = 0;
     uint64_t max_lw1_pk = 0;
+    if (!subset && packed_ok && s->nregular == s->nseq && s->minL >= (uint64_t)W) {
+        // the whole set, every sequence regular and long enough: identity lists without per-sequence decisions
+        pk_ids.resize(nsub); pk_roff.resize(nsub);
+        for (uint64_t i = 0; i < nsub; i++) {
+            ids[i] = (uint32_t)i; pk_ids[i] = (uint32_t)i;
+            pk_roff[i] = s->h_off[i];                           // prefix sums of L of the whole set = its offsets
+            em->h_r_off[i + 1] = s->h_off[i + 1];
+        }
+        max_lw1_pk = s->maxL - (uint64_t)W + 1;
+    } else
     for (uint64_t i = 0; i < nsub; i++) {
         const uint64_t n = subset ? subset[i] : i;
         if (n >= s->nseq) { delete em; return fail(BAMM_E_INVALID, "subset[%llu]=%llu out of range", (unsigned long long)i, (unsigned long long)n); }
@@ -640,7 +680,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     CUE(cudaStreamCreateWithFlags(&em->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; i++) CUE(cudaEventCreate(&em->ev[i]));
     auto upload = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
-        cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+        cudaError_t e = dev_malloc(dst, bytes ? bytes : 16);
         if (e == cudaSuccess && bytes) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
         return e;
     };
@@ -649,20 +689,20 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     CUE(upload(pk_ids.data(), pk_ids.size() * 4, (void**)&em->d_pk_ids));
     CUE(upload(pk_roff.data(), pk_roff.size() * 8, (void**)&em->d_pk_roff));
     tr.mark("index / ypatch + id uploads");
-    CUE(cudaMalloc(&em->d_r, (em->rsize ? em->rsize : 1) * sizeof(float)));
+    CUE(dev_malloc(&em->d_r, (em->rsize ? em->rsize : 1) * sizeof(float)));
     CUE(cudaMemset(em->d_r, 0, (em->rsize ? em->rsize : 1) * sizeof(float)));   // the packed E-step never touches the tail i >= LW1
     tr.mark("r alloc + memset");
-    CUE(cudaMalloc(&em->d_s, (uint64_t)em->nbin * sizeof(float)));
-    CUE(cudaMalloc(&em->d_sT, (uint64_t)em->nbin * sizeof(float)));
-    CUE(cudaMalloc(&em->d_v, em->model_size * sizeof(float)));
-    CUE(cudaMalloc(&em->d_vK_prev, (uint64_t)em->nbin * sizeof(float)));
-    CUE(cudaMalloc(&em->d_n, em->model_size * sizeof(float)));
-    CUE(cudaMalloc(&em->d_vbg, em->bg_size * sizeof(float)));
-    CUE(cudaMalloc(&em->d_alpha, (uint64_t)(K + 1) * W * sizeof(float)));
-    CUE(cudaMalloc(&em->d_xbuf, ((uint64_t)em->nbin + 2) * sizeof(unsigned long long)));
+    CUE(dev_malloc(&em->d_s, (uint64_t)em->nbin * sizeof(float)));
+    CUE(dev_malloc(&em->d_sT, (uint64_t)em->nbin * sizeof(float)));
+    CUE(dev_malloc(&em->d_v, em->model_size * sizeof(float)));
+    CUE(dev_malloc(&em->d_vK_prev, (uint64_t)em->nbin * sizeof(float)));
+    CUE(dev_malloc(&em->d_n, em->model_size * sizeof(float)));
+    CUE(dev_malloc(&em->d_vbg, em->bg_size * sizeof(float)));
+    CUE(dev_malloc(&em->d_alpha, (uint64_t)(K + 1) * W * sizeof(float)));
+    CUE(dev_malloc(&em->d_xbuf, ((uint64_t)em->nbin + 2) * sizeof(unsigned long long)));
     CUE(cudaMemset(em->d_xbuf, 0, ((uint64_t)em->nbin + 2) * sizeof(unsigned long long)));
-    CUE(cudaMalloc(&em->d_vdiff, sizeof(float)));
-    CUE(cudaMalloc(&em->d_vdiff_part, 16 * sizeof(double)));
+    CUE(dev_malloc(&em->d_vdiff, sizeof(float)));
+    CUE(dev_malloc(&em->d_vdiff_part, 16 * sizeof(double)));
     CUE(cudaMallocHost(&em->h_scal, 2 * sizeof(unsigned long long)));
     CUE(cudaMallocHost(&em->h_vdiff, sizeof(float)));
     em->nparts = 1;
@@ -687,7 +727,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     }
     // ---- packed path geometry
     if (em->npk) {
-        CUE(cudaMalloc(&em->d_scale, (size_t)em->npk * sizeof(float)));
+        CUE(dev_malloc(&em->d_scale, (size_t)em->npk * sizeof(float)));
         em->block_pe = BAMM_E_THREADS;              // one CTA per SM: the group tables fill its shared memory
         em->grid_pe = sms;
         // M-step geometry: as many columns per CTA as two 32-bit tables allow, the fewest splits, columns spread evenly
@@ -735,7 +775,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
                     reg[w + 1] = reg[w] + cap;
                 }
                 const uint64_t total = reg[em->nregions] ? reg[em->nregions] : 1;
-                const cudaError_t ea = cudaMalloc(&em->d_act, total * sizeof(ActiveEntry));
+                const cudaError_t ea = dev_malloc(&em->d_act, total * sizeof(ActiveEntry));
                 if (ea == cudaSuccess) break;
                 cudaGetLastError();
                 em->d_act = nullptr;
@@ -746,14 +786,14 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         }
         if (em->d_act) {
             CUE(upload(reg.data(), reg.size() * 8, (void**)&em->d_reg_off));
-            CUE(cudaMalloc(&em->d_act_cnt, (uint64_t)em->nregions * 8));         // front counts, then back counts
+            CUE(dev_malloc(&em->d_act_cnt, (uint64_t)em->nregions * 8));         // front counts, then back counts
             CUE(cudaMemset(em->d_act_cnt, 0, (uint64_t)em->nregions * 8));
-            CUE(cudaMalloc(&em->d_overflow, 4));
+            CUE(dev_malloc(&em->d_overflow, 4));
             CUE(cudaMemset(em->d_overflow, 0, 4));
         }
     }
     tr.mark("model buffers + active list");
-    CUE(cudaMalloc(&em->d_part, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long)));
+    CUE(dev_malloc(&em->d_part, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long)));
 #undef CUE
     tr.mark("partials");
     *out = em;
@@ -793,7 +833,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
         if (em->gplans.size() > em->tab_passes) {
             CU(cudaStreamSynchronize(em->stream));
             cudaFree(em->d_tab); em->d_tab = nullptr; em->tab_passes = 0;
-            CU(cudaMalloc(&em->d_tab, em->gplans.size() * em->tab_capacity));
+            CU(dev_malloc(&em->d_tab, em->gplans.size() * em->tab_capacity));
             em->tab_passes = em->gplans.size();
         }
         for (size_t i = 0; i < em->gplans.size(); i++)
@@ -1106,15 +1146,15 @@ static int mask_run(bamm_em* em, const YT* Y, float f, float epsilon, int max_it
     pos_count = woff[nsub];
 #define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
     {
-        CUX(cudaMalloc(&d_s0, s0.size() * sizeof(float)));
+        CUX(dev_malloc(&d_s0, s0.size() * sizeof(float)));
         CUX(cudaMemcpyAsync(d_s0, s0.data(), s0.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-        if (!em->d_m_woff) CUX(cudaMalloc(&em->d_m_woff, (nsub + 1) * sizeof(uint64_t)));
+        if (!em->d_m_woff) CUX(dev_malloc(&em->d_m_woff, (nsub + 1) * sizeof(uint64_t)));
         CUX(cudaMemcpyAsync(em->d_m_woff, woff.data(), (nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         CUX(cudaMemsetAsync(em->d_r, 0, (em->rsize ? em->rsize : 1) * sizeof(float), st));       // the reference's calloc
         k_mask_phase1<YT><<<sms * 8, 256, 0, st>>>(Y, mv, W, (uint32_t)em->A, d_s0, em->q, em->d_r);
         CUX(cudaGetLastError());
         // (2) threshold: descending sort of every window's r, value at rank floor(float(count) * f)  (EM.cpp:318-334)
-        CUX(cudaMalloc(&d_all, (pos_count ? pos_count : 1) * sizeof(float)));
+        CUX(dev_malloc(&d_all, (pos_count ? pos_count : 1) * sizeof(float)));
         k_mask_gather<<<sms * 8, 256, 0, st>>>(mv, W, em->d_m_woff, em->d_r, d_all);
         CUX(cudaGetLastError());
         rc = device_sort_f32(d_all, pos_count, true, st);
@@ -1124,7 +1164,7 @@ static int mask_run(bamm_em* em, const YT* Y, float f, float epsilon, int max_it
         float cutoff = 0.0f;
         CUX(cudaMemcpy(&cutoff, d_all + rank, sizeof(float), cudaMemcpyDeviceToHost));
         cudaFree(d_all); d_all = nullptr;
-        CUX(cudaMalloc(&d_cnt, (nsub ? nsub : 1) * sizeof(uint32_t)));
+        CUX(dev_malloc(&d_cnt, (nsub ? nsub : 1) * sizeof(uint32_t)));
         k_mask_select<false><<<sms * 8, 256, 0, st>>>(mv, em->d_m_woff, em->d_r, cutoff, d_cnt, nullptr, nullptr);
         CUX(cudaGetLastError());
         std::vector<uint32_t> cnt(nsub);
@@ -1133,8 +1173,8 @@ static int mask_run(bamm_em* em, const YT* Y, float f, float epsilon, int max_it
         std::vector<uint64_t> seloff(nsub + 1, 0);
         for (uint64_t i = 0; i < nsub; i++) seloff[i + 1] = seloff[i] + cnt[i];
         cudaFree(em->d_m_seloff); cudaFree(em->d_m_sel); em->d_m_seloff = nullptr; em->d_m_sel = nullptr;
-        CUX(cudaMalloc(&em->d_m_seloff, (nsub + 1) * sizeof(uint64_t)));
-        CUX(cudaMalloc(&em->d_m_sel, (seloff[nsub] ? seloff[nsub] : 1) * sizeof(uint32_t)));
+        CUX(dev_malloc(&em->d_m_seloff, (nsub + 1) * sizeof(uint64_t)));
+        CUX(dev_malloc(&em->d_m_sel, (seloff[nsub] ? seloff[nsub] : 1) * sizeof(uint32_t)));
         CUX(cudaMemcpyAsync(em->d_m_seloff, seloff.data(), (nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         k_mask_select<true><<<sms * 8, 256, 0, st>>>(mv, em->d_m_woff, em->d_r, cutoff, nullptr, em->d_m_seloff, em->d_m_sel);
         CUX(cudaGetLastError());
@@ -1195,8 +1235,8 @@ extern "C" int bamm_em_mask(bamm_em* em, float f, float epsilon, int max_iter, i
     IndexArray* ia = nullptr;
     { std::lock_guard<std::mutex> g(em->ss->mu); int rc = seqset_index_locked(em->ss, em->K, &ia); if (rc) return rc; }
     if (!em->d_m_ids) {
-        CU(cudaMalloc(&em->d_m_ids, em->nsub * sizeof(uint32_t)));
-        CU(cudaMalloc(&em->d_m_roff, (em->nsub + 1) * sizeof(uint64_t)));
+        CU(dev_malloc(&em->d_m_ids, em->nsub * sizeof(uint32_t)));
+        CU(dev_malloc(&em->d_m_roff, (em->nsub + 1) * sizeof(uint64_t)));
         CU(cudaMemcpy(em->d_m_ids, em->h_ids.data(), em->nsub * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(em->d_m_roff, em->h_r_off.data(), (em->nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
     }
@@ -1330,7 +1370,7 @@ extern "C" int bamm_em_peer_alloc(bamm_em* em, int rank, int world, void* ipc_ha
     const size_t words = (size_t)em->nbin + 2;
     const size_t slot_bytes = (size_t)2 * world * words * sizeof(unsigned long long);
     const size_t bytes = slot_bytes + MAX_PEERS * sizeof(unsigned int);
-    CU(cudaMalloc(&em->d_peer_local, bytes));
+    CU(cudaMalloc(&em->d_peer_local, bytes));            // CUDA IPC needs a plain allocation
     CU(cudaMemset(em->d_peer_local, 0, bytes));
     CU(cudaMalloc(&em->d_peer_done, sizeof(unsigned int)));
     CU(cudaMemset(em->d_peer_done, 0, sizeof(unsigned int)));
@@ -1396,8 +1436,8 @@ extern "C" int bamm_rand_stream(uint32_t seed, uint64_t first, uint64_t count, i
     if (!count) return BAMM_OK;
     LfgTables t; lfg_tables(seed, t);
     uint32_t* d_t = nullptr; int* d_out = nullptr;
-    CU(cudaMalloc(&d_t, sizeof(t)));
-    cudaError_t e = cudaMalloc(&d_out, count * sizeof(int));
+    CU(dev_malloc(&d_t, sizeof(t)));
+    cudaError_t e = dev_malloc(&d_out, count * sizeof(int));
     if (e != cudaSuccess) { cudaFree(d_t); return fail(BAMM_E_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
     cudaMemcpy(d_t, &t, sizeof(t), cudaMemcpyHostToDevice);
     const uint64_t threads = std::min<uint64_t>(count, 148ull * 1024ull), per = (count + threads - 1) / threads;
@@ -1443,12 +1483,12 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
         // set-wide frequencies (SeqGenerator::calculate_kmer_frequency, SeqGenerator.cpp:63-112): counts on the device, the
         // 84 probabilities on the host in the reference's operation order
         if (subset) {
-            CUX(cudaMalloc(&d_tids, nsub * sizeof(uint32_t)));
+            CUX(dev_malloc(&d_tids, nsub * sizeof(uint32_t)));
             CUX(cudaMemcpy(d_tids, tids.data(), nsub * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
-        CUX(cudaMalloc(&d_toff, (nsub + 1) * sizeof(uint64_t)));
+        CUX(dev_malloc(&d_toff, (nsub + 1) * sizeof(uint64_t)));
         CUX(cudaMemcpy(d_toff, toff.data(), (nsub + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_cnt, d.total * sizeof(unsigned long long)));
+        CUX(dev_malloc(&d_cnt, d.total * sizeof(unsigned long long)));
         CUX(cudaMemset(d_cnt, 0, d.total * sizeof(unsigned long long)));
         tr.mark("order-2 index + template list");
         k_neg_count_set<<<pos->sm_count * 8, 256>>>(Y2, pos->d_off, d_tids, nsub, d, d_cnt);
@@ -1468,11 +1508,11 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
         }
         for (uint32_t y = 0; y < d.Y2; y++) v1[y] = ((float)n1[y] + pc * v0[y % d.Y1]) / ((float)n0[y / d.Y1] + pc);
         for (uint32_t y = 0; y < d.Y3; y++) v2[y] = ((float)n2[y] + pc * v1[y % d.Y2]) / ((float)n1[y / d.Y1] + pc);
-        CUX(cudaMalloc(&d_v, (d.total + d.Y1) * sizeof(float)));
+        CUX(dev_malloc(&d_v, (d.total + d.Y1) * sizeof(float)));
         CUX(cudaMemcpy(d_v, v.data(), d.total * sizeof(float), cudaMemcpyHostToDevice));
         CUX(cudaMemcpy(d_v + d.total, rb0.data(), d.Y1 * sizeof(float), cudaMemcpyHostToDevice));
         // per-template bars
-        CUX(cudaMalloc(&d_rb, nsub * (uint64_t)(d.Y2 + d.Y3) * sizeof(float)));
+        CUX(dev_malloc(&d_rb, nsub * (uint64_t)(d.Y2 + d.Y3) * sizeof(float)));
         k_neg_models<<<pos->sm_count * 16, 128>>>(Y2, pos->d_off, d_tids, nsub, d, d_v, pc, d_rb);
         CUX(cudaGetLastError());
         // the negative set: `fold` records per template, each of the template's stored length
@@ -1488,9 +1528,9 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
         if (rc) goto done;
         tr.mark("seqset_new (alloc + offsets H2D)");
         LfgTables t; lfg_tables(seed, t);
-        CUX(cudaMalloc(&d_lfg, sizeof(t)));
+        CUX(dev_malloc(&d_lfg, sizeof(t)));
         CUX(cudaMemcpy(d_lfg, &t, sizeof(t), cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_flags, sizeof(uint32_t)));
+        CUX(dev_malloc(&d_flags, sizeof(uint32_t)));
         CUX(cudaMemset(d_flags, 0, sizeof(uint32_t)));
         const uint64_t want = (uint64_t)pos->sm_count * 2048ull;
         const uint64_t per = (nneg + want - 1) / want;
@@ -1627,15 +1667,15 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
     int rc = BAMM_OK;
 #define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
     {
-        CUX(cudaMalloc(&d_s, (uint64_t)nbin * 4));
-        CUX(cudaMalloc(&d_zoops, (nsub ? nsub : 1) * 4));
-        CUX(cudaMalloc(&d_z, (nsub ? nsub : 1) * 8));
-        CUX(cudaMalloc(&d_gids, (gen_ids.size() ? gen_ids.size() : 1) * 4));
-        CUX(cudaMalloc(&d_gout, (gen_ids.size() ? gen_ids.size() : 1) * 4));
-        CUX(cudaMalloc(&d_pids, (pk_ids.size() ? pk_ids.size() : 1) * 4));
-        CUX(cudaMalloc(&d_pout, (pk_ids.size() && !identity_out ? pk_ids.size() : 1) * 4));
-        CUX(cudaMalloc(&d_moff, moff.size() * 8));
-        if (mops) CUX(cudaMalloc(&d_mops, (moff[nsub] ? moff[nsub] : 1) * 4));
+        CUX(dev_malloc(&d_s, (uint64_t)nbin * 4));
+        CUX(dev_malloc(&d_zoops, (nsub ? nsub : 1) * 4));
+        CUX(dev_malloc(&d_z, (nsub ? nsub : 1) * 8));
+        CUX(dev_malloc(&d_gids, (gen_ids.size() ? gen_ids.size() : 1) * 4));
+        CUX(dev_malloc(&d_gout, (gen_ids.size() ? gen_ids.size() : 1) * 4));
+        CUX(dev_malloc(&d_pids, (pk_ids.size() ? pk_ids.size() : 1) * 4));
+        CUX(dev_malloc(&d_pout, (pk_ids.size() && !identity_out ? pk_ids.size() : 1) * 4));
+        CUX(dev_malloc(&d_moff, moff.size() * 8));
+        if (mops) CUX(dev_malloc(&d_mops, (moff[nsub] ? moff[nsub] : 1) * 4));
         CUX(cudaMemcpyAsync(d_s, slog.data(), (uint64_t)nbin * 4, cudaMemcpyHostToDevice, st));
         CUX(cudaMemcpyAsync(d_gids, gen_ids.data(), gen_ids.size() * 4, cudaMemcpyHostToDevice, st));
         CUX(cudaMemcpyAsync(d_gout, gen_out.data(), gen_out.size() * 4, cudaMemcpyHostToDevice, st));
@@ -1652,7 +1692,7 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
             PackedView pv; pv.words = s->d_words; pv.seqs = s->d_pseq; pv.ypatch = d_yp; pv.seq_ids = d_pids; pv.r_off = nullptr; pv.nlist = (uint32_t)pk_ids.size();
             Plan pl; pl.W = W; pl.K = K; pl.T = 1; pl.C = W; pl.Yn = Yn; pl.Zn = Yn; pl.q = 0.f;
             if (zoops_fast) {
-                CUX(cudaMalloc(&d_ztab, zplan.table_bytes));
+                CUX(dev_malloc(&d_ztab, zplan.table_bytes));
                 const uint32_t total = zplan.table_bytes >> 2, blocks = (total + 255) / 256;
                 k_make_group_tables<true><<<blocks < 1184 ? blocks : 1184, 256, 0, st>>>(d_s, zplan, d_ztab);
                 CUX(cudaGetLastError());
@@ -1708,12 +1748,12 @@ static int device_sort_f32(float* d_keys, uint64_t n, bool descending, cudaStrea
     if (n < 2) return BAMM_OK;
     REQUIRE(n < (1ull << 31), "too many scores for one sort call");
     float* d_alt = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0;
-    cudaError_t e = cudaMalloc(&d_alt, n * sizeof(float));
+    cudaError_t e = dev_malloc(&d_alt, n * sizeof(float));
     if (e != cudaSuccess) return fail(BAMM_E_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
     cub::DoubleBuffer<float> buf(d_keys, d_alt);
     if (descending) cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, buf, (int)n, 0, 32, st);
     else            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, buf, (int)n, 0, 32, st);
-    e = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
+    e = dev_malloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
     if (e == cudaSuccess) {
         if (descending) e = cub::DeviceRadixSort::SortKeysDescending(d_tmp, tmp_bytes, buf, (int)n, 0, 32, st);
         else            e = cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, buf, (int)n, 0, 32, st);
@@ -1729,7 +1769,7 @@ extern "C" int bamm_sort_scores(float* scores, uint64_t n, int descending) {
     REQUIRE(scores || n == 0, "scores is NULL");
     if (n < 2) return BAMM_OK;
     float* d = nullptr;
-    CU(cudaMalloc(&d, n * sizeof(float)));
+    CU(dev_malloc(&d, n * sizeof(float)));
     cudaError_t e = cudaMemcpy(d, scores, n * sizeof(float), cudaMemcpyHostToDevice);
     int rc = e == cudaSuccess ? device_sort_f32(d, n, descending != 0, 0) : fail(BAMM_E_CUDA, "H2D failed: %s", cudaGetErrorString(e));
     if (!rc) { e = cudaMemcpy(scores, d, n * sizeof(float), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(BAMM_E_CUDA, "D2H failed: %s", cudaGetErrorString(e)); }
@@ -1747,7 +1787,7 @@ extern "C" int bamm_mops_pvalues(const float* neg_scores, uint64_t nneg, const f
     const uint64_t chn = npos < CH ? (npos ? npos : 1) : CH;
 #define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
     {
-        CUX(cudaMalloc(&d_neg, nneg * sizeof(float)));
+        CUX(dev_malloc(&d_neg, nneg * sizeof(float)));
         CUX(cudaMemcpy(d_neg, neg_scores, nneg * sizeof(float), cudaMemcpyHostToDevice));
         rc = device_sort_f32(d_neg, nneg, false, 0);
         if (rc) goto done;
@@ -1759,9 +1799,9 @@ extern "C" int bamm_mops_pvalues(const float* neg_scores, uint64_t nneg, const f
         float lambda = 0.f;
         for (size_t n = 0; n < nTop; n++) lambda += (head[n] - S_ntop);
         lambda = lambda / (float)nTop;
-        CUX(cudaMalloc(&d_pos, chn * sizeof(float)));
-        CUX(cudaMalloc(&d_p, chn * sizeof(float)));
-        CUX(cudaMalloc(&d_e, chn * sizeof(float)));
+        CUX(dev_malloc(&d_pos, chn * sizeof(float)));
+        CUX(dev_malloc(&d_p, chn * sizeof(float)));
+        CUX(dev_malloc(&d_e, chn * sizeof(float)));
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
         for (uint64_t b = 0; b < npos; b += CH) {
             const uint64_t m = std::min(CH, npos - b);
@@ -1798,18 +1838,18 @@ extern "C" int bamm_seqset_encode_text(const char* text, uint64_t nbytes, const 
     const uint64_t zero_cap = std::max<uint64_t>(1024, s->npos / 16);          // forward undefined bases kept (more => error below)
 #define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
     {
-        CUX(cudaMalloc(&d_text, nbytes ? nbytes : 1));
+        CUX(dev_malloc(&d_text, nbytes ? nbytes : 1));
         CUX(cudaMemcpy(d_text, text, nbytes, cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_segs, (nseg ? nseg : 1) * sizeof(FastaSeg)));
+        CUX(dev_malloc(&d_segs, (nseg ? nseg : 1) * sizeof(FastaSeg)));
         CUX(cudaMemcpy(d_segs, segs, nseg * sizeof(FastaSeg), cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_L0, (nrec ? nrec : 1) * sizeof(uint32_t)));
+        CUX(dev_malloc(&d_L0, (nrec ? nrec : 1) * sizeof(uint32_t)));
         CUX(cudaMemcpy(d_L0, rec_L0, nrec * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_lut, 512));
+        CUX(dev_malloc(&d_lut, 512));
         CUX(cudaMemcpy(d_lut, base2code, 256, cudaMemcpyHostToDevice));
         CUX(cudaMemcpy(d_lut + 256, code2comp, 256, cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_cnt, 16 * sizeof(unsigned long long)));
+        CUX(dev_malloc(&d_cnt, 16 * sizeof(unsigned long long)));
         CUX(cudaMemset(d_cnt, 0, 16 * sizeof(unsigned long long)));
-        CUX(cudaMalloc(&s->d_zero_pos, zero_cap * sizeof(unsigned long long)));
+        CUX(dev_malloc(&s->d_zero_pos, zero_cap * sizeof(unsigned long long)));
         tr.mark("alloc + text H2D");
         if (nseg) {
             k_fasta_encode<<<s->sm_count * 8, 256>>>(d_text, d_segs, nseg, s->d_off, d_L0, single_strand, d_lut, d_lut + 256, A, s->d_codes,
@@ -1842,8 +1882,8 @@ extern "C" int bamm_seqset_code_windows(bamm_seqset* s, const uint64_t* zpos, co
     REQUIRE(s && ((zpos && zbeg && zend && windows) || nz == 0), "NULL argument");
     if (!nz) return BAMM_OK;
     uint64_t* d = nullptr; uint8_t* d_w = nullptr;
-    CU(cudaMalloc(&d, 3 * nz * sizeof(uint64_t)));
-    cudaError_t e = cudaMalloc(&d_w, nz * 21);
+    CU(dev_malloc(&d, 3 * nz * sizeof(uint64_t)));
+    cudaError_t e = dev_malloc(&d_w, nz * 21);
     if (e == cudaSuccess) e = cudaMemcpy(d, zpos, nz * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d + nz, zbeg, nz * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d + 2 * nz, zend, nz * 8, cudaMemcpyHostToDevice);
@@ -1862,12 +1902,12 @@ extern "C" int bamm_seqset_finish_patches(bamm_seqset* s, const uint64_t* patch_
     cudaFree(s->d_zero_pos); s->d_zero_pos = nullptr;
     s->npatch = npatch;
     if (npatch) {
-        CU(cudaMalloc(&s->d_ppos, npatch * sizeof(uint64_t)));
-        CU(cudaMalloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
+        CU(dev_malloc(&s->d_ppos, npatch * sizeof(uint64_t)));
+        CU(dev_malloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
         CU(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
         uint32_t* d_bad = nullptr; uint32_t bad = 0;
-        CU(cudaMalloc(&d_bad, sizeof(uint32_t)));
+        CU(dev_malloc(&d_bad, sizeof(uint32_t)));
         cudaMemset(d_bad, 0, sizeof(uint32_t));
         k_validate_patches<<<(unsigned)((npatch + 255) / 256), 256>>>(s->d_ppos, npatch, s->npos, d_bad);
         cudaError_t ev = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
@@ -1910,18 +1950,18 @@ extern "C" int bamm_seqset_sample_pwm_sites(bamm_seqset* s, const uint64_t* subs
     int rc = BAMM_OK;
 #define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
     {
-        CUX(cudaMalloc(&d_ids, (nsub ? nsub : 1) * 4));
+        CUX(dev_malloc(&d_ids, (nsub ? nsub : 1) * 4));
         CUX(cudaMemcpy(d_ids, ids.data(), nsub * 4, cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_voff, 16 * 4));
+        CUX(dev_malloc(&d_voff, 16 * 4));
         CUX(cudaMemcpy(d_voff, d.voff, 16 * 4, cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_score, (size_t)asize * W * 4));
+        CUX(dev_malloc(&d_score, (size_t)asize * W * 4));
         CUX(cudaMemcpy(d_score, score, (size_t)asize * W * 4, cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_u, (nsub ? nsub : 1) * 8));
+        CUX(dev_malloc(&d_u, (nsub ? nsub : 1) * 8));
         CUX(cudaMemcpy(d_u, uniforms, nsub * 8, cudaMemcpyHostToDevice));
-        CUX(cudaMalloc(&d_scratch, (uint64_t)warps * stride * 4));
-        CUX(cudaMalloc(&d_n, msize * 4));
+        CUX(dev_malloc(&d_scratch, (uint64_t)warps * stride * 4));
+        CUX(dev_malloc(&d_n, msize * 4));
         CUX(cudaMemset(d_n, 0, msize * 4));
-        if (z_out) CUX(cudaMalloc(&d_z, (nsub ? nsub : 1) * 8));
+        if (z_out) CUX(dev_malloc(&d_z, (nsub ? nsub : 1) * 8));
         if (ia->bytes == 2) k_pwm_sample_sites<uint16_t><<<grid, 256>>>((const uint16_t*)ia->d, s->d_off, d_ids, (uint32_t)nsub, W, K, (uint32_t)s->A, (uint32_t)asize,
                                                                         d_score, q, d_u, d_scratch, stride, d_n, d_voff, d_z);
         else                k_pwm_sample_sites<uint32_t><<<grid, 256>>>((const uint32_t*)ia->d, s->d_off, d_ids, (uint32_t)nsub, W, K, (uint32_t)s->A, (uint32_t)asize,

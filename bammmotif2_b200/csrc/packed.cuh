@@ -49,16 +49,36 @@ __global__ void k_classify(const uint8_t* __restrict__ codes, const uint64_t* __
         const uint64_t base = off[n], L = off[n + 1] - base;
         const uint64_t mid = (L & 1) ? (L - 1) / 2 : ~0ull;
         int bad = 0, zeros_at_mid = 0;
-        for (uint64_t i = lane; i < L; i += 32) {
-            const uint32_t c = codes[base + i];
+        auto check = [&](uint64_t i, uint32_t c) {
             if (c == 0) { if (i == mid) zeros_at_mid = 1; else bad = 1; }
             else if (c > 4) bad = 1;
+        };
+        // unaligned head and tail byte by byte, the aligned interior four codes per load: a word is suspicious when one of
+        // its bytes is 0 or above 4 (bit tricks), only then its bytes are looked at one by one
+        const uint64_t a0 = (base + 3) & ~3ull, a1 = (base + L) & ~3ull;     // aligned interior [a0, a1) in global offsets
+        if (a0 >= a1) {
+            for (uint64_t i = lane; i < L; i += 32) check(i, codes[base + i]);
+        } else {
+            for (uint64_t g = base + lane; g < a0; g += 32) check(g - base, codes[g]);
+            for (uint64_t g = a1 + lane; g < base + L; g += 32) check(g - base, codes[g]);
+            const uint32_t* __restrict__ w4 = reinterpret_cast<const uint32_t*>(codes + a0);
+            const uint64_t nw = (a1 - a0) >> 2;
+            for (uint64_t k = lane; k < nw; k += 32) {
+                const uint32_t w = w4[k];
+                const uint32_t zero = (w - 0x01010101u) & ~w & 0x80808080u;
+                const uint32_t big = (((w & 0x7f7f7f7fu) + 0x7b7b7b7bu) | w) & 0x80808080u;
+                if (zero | big) {
+                    const uint64_t i = a0 - base + (k << 2);
+                    check(i, w & 0xffu); check(i + 1, (w >> 8) & 0xffu); check(i + 2, (w >> 16) & 0xffu); check(i + 3, w >> 24);
+                }
+            }
         }
         bad = __any_sync(FULL, bad);
         zeros_at_mid = __any_sync(FULL, zeros_at_mid);
         if (lane == 0) kind[n] = (bad || L == 0 || L >= 0xffffff00ull) ? 0 : (zeros_at_mid ? 2 : 1);
     }
 }
+
 
 // patch list contract of bamm_seqset_create: positions inside the set (bit 0 of *bad otherwise) and strictly increasing (bit 1)
 __global__ void k_validate_patches(const uint64_t* __restrict__ ppos, uint64_t np, uint64_t npos, uint32_t* __restrict__ bad) {
