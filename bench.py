@@ -383,9 +383,10 @@ def run_c4(args, wl):
                     "d2h_bytes_per_step": int(12 * nscored), "seconds": wall,
                     "what": "the same calls timed on the host clock: subset ids + model H2D, table build, kernels, ZOOPS scores + argmax D2H"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_score_packed", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "roofline": {"bound": "hbm", "kernel": "k_score_zoops_packed", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                         "note": "W shared-memory lookups per window bound this kernel, not HBM (the scores must be bit-identical sums in ascending j)"},
+                         "note": "issue-bound: column-group bound per window (G shared-memory lookups) + exact ascending-j re-scoring of the "
+                                 "few windows near the maximum; the scores stay bit-identical to the reference"},
             "cpu_baseline": cpu}), flush=True)
     neg.close(); ss.close()
     if world > 1:
