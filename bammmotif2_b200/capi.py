@@ -35,6 +35,8 @@ SIGNATURES = {
     "bamm_seqset_code_windows": (C.c_int, [_vp, _u64p, _u64p, _u64p, C.c_uint64, _u8p]),
     "bamm_seqset_finish_patches": (C.c_int, [_vp, _u64p, _u64p, C.c_uint64]),
     "bamm_seqset_sample_negatives": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(_vp)]),
+    "bamm_seqset_negative_kmer_counts": (C.c_int, [_vp, _u64p, C.c_uint64, _u64p]),
+    "bamm_seqset_sample_negatives_shard": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, _u64p, C.POINTER(_vp)]),
     "bamm_rand_stream": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_int32)]),
     "bamm_em_create": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "bamm_em_set_model": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_float]),
@@ -191,6 +193,19 @@ class SeqSet:
         h = _vp()
         sub = np.ascontiguousarray(subset, np.uint64) if subset is not None else None
         _check(load().bamm_seqset_sample_negatives(self.h, _ptr(sub, _u64p), len(sub) if sub is not None else 0, int(fold), int(seed), C.byref(h)))
+        return SeqSet._adopt(h, self.A)
+
+    def negative_kmer_counts(self):
+        """This shard's k-mer counters for the set-wide model of the negative sampler (orders 0..2 concatenated)."""
+        out = np.zeros(self.A + self.A ** 2 + self.A ** 3, np.uint64)
+        _check(load().bamm_seqset_negative_kmer_counts(self.h, None, 0, _ptr(out, _u64p)))
+        return out
+
+    def sample_negatives_shard(self, fold, draw_offset, global_counts, seed=42):
+        """One shard of a negative set sampled over several devices (see include/bamm_b200.h)."""
+        h = _vp()
+        gc = np.ascontiguousarray(global_counts, np.uint64)
+        _check(load().bamm_seqset_sample_negatives_shard(self.h, None, 0, int(fold), int(seed), int(draw_offset), _ptr(gc, _u64p), C.byref(h)))
         return SeqSet._adopt(h, self.A)
 
     def get_codes(self):

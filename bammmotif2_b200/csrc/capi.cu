@@ -1448,8 +1448,30 @@ extern "C" int bamm_rand_stream(uint32_t seed, uint64_t first, uint64_t count, i
     return BAMM_OK;
 }
 
+static int sample_negatives_impl(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t fold, uint32_t seed, uint64_t draw_offset,
+                                 const uint64_t* global_counts, uint64_t* local_counts_out, bamm_seqset** out);
+
 extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t fold, uint32_t seed, bamm_seqset** out) {
-    REQUIRE(out, "out is NULL");
+    return sample_negatives_impl(pos, subset, nsub, fold, seed, 0, nullptr, nullptr, out);
+}
+
+extern "C" int bamm_seqset_negative_kmer_counts(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t* counts) {
+    REQUIRE(counts, "counts is NULL");
+    return sample_negatives_impl(pos, subset, nsub, 1, 42, 0, nullptr, counts, nullptr);
+}
+
+extern "C" int bamm_seqset_sample_negatives_shard(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t fold, uint32_t seed,
+                                                  uint64_t draw_offset, const uint64_t* global_counts, bamm_seqset** out) {
+    REQUIRE(global_counts, "global_counts is NULL");
+    return sample_negatives_impl(pos, subset, nsub, fold, seed, draw_offset, global_counts, nullptr, out);
+}
+
+// out == nullptr: only the template list's k-mer counts are wanted (local_counts_out)
+static int sample_negatives_impl(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t fold, uint32_t seed, uint64_t draw_offset,
+                                 const uint64_t* global_counts, uint64_t* local_counts_out, bamm_seqset** out) {
+    REQUIRE(out || local_counts_out, "out is NULL");
+    bamm_seqset* dummy_out = nullptr;
+    if (!out) out = &dummy_out;
     *out = nullptr;
     REQUIRE(pos, "seqset is NULL");
     REQUIRE(fold >= 1, "fold must be at least 1");
@@ -1466,7 +1488,7 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
         toff[i + 1] = toff[i] + L;
         if (subset) tids[i] = (uint32_t)n;
     }
-    REQUIRE(toff[nsub] * fold + 400 < (1ull << (LFG_NPOW - 1)), "too many draws");
+    REQUIRE(draw_offset + toff[nsub] * fold + 400 < (1ull << (LFG_NPOW - 1)), "too many draws");
     Trace tr("sample_negatives");
     CU(cudaSetDevice(pos->device));
     NegDims d; d.A = pos->A; d.Y1 = (uint32_t)pos->A; d.Y2 = d.Y1 * d.Y1; d.Y3 = d.Y2 * d.Y1; d.total = d.Y1 + d.Y2 + d.Y3;
@@ -1495,6 +1517,11 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
         CUX(cudaGetLastError());
         std::vector<unsigned long long> cnt(d.total);
         CUX(cudaMemcpy(cnt.data(), d_cnt, d.total * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (local_counts_out) {                                // the caller sums these over the shards of one set
+            for (uint32_t b = 0; b < d.total; b++) local_counts_out[b] = cnt[b];
+            goto done;
+        }
+        if (global_counts) for (uint32_t b = 0; b < d.total; b++) cnt[b] = global_counts[b];
         std::vector<float> v(d.total), rb0(d.Y1);
         const unsigned long long *n0 = cnt.data(), *n1 = n0 + d.Y1, *n2 = n1 + d.Y2;
         float *v0 = v.data(), *v1 = v0 + d.Y1, *v2 = v1 + d.Y2;
@@ -1536,7 +1563,7 @@ extern "C" int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* su
         const uint64_t per = (nneg + want - 1) / want;
         const uint64_t threads = (nneg + per - 1) / per;
         k_neg_sample<<<(unsigned)((threads + NEG_THREADS - 1) / NEG_THREADS), NEG_THREADS>>>(d_toff, nsub, fold, d, d_v + d.total, d_rb,
-                                                                                          d_lfg, d_lfg + LFG_N, per, neg->d_codes, d_flags);
+                                                                                          d_lfg, d_lfg + LFG_N, per, draw_offset, neg->d_codes, d_flags);
         CUX(cudaGetLastError());
         uint32_t flags = 0;
         CUX(cudaMemcpy(&flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost));

@@ -178,7 +178,8 @@ constexpr int NEG_THREADS = 128;
 __global__ void __launch_bounds__(NEG_THREADS)
 k_neg_sample(const uint64_t* __restrict__ off /* [nseq+1] prefix sums of the TEMPLATE LIST's lengths */, uint64_t nseq, uint64_t fold, NegDims d, const float* __restrict__ rb0,
              const float* __restrict__ rb, const uint32_t* __restrict__ u0, const uint32_t* __restrict__ pw,
-             uint64_t per_thread, uint8_t* __restrict__ codes, uint32_t* __restrict__ flags) {
+             uint64_t per_thread, uint64_t draw0 /* draws consumed by the templates of earlier shards */, uint8_t* __restrict__ codes,
+             uint32_t* __restrict__ flags) {
     __shared__ uint32_t st_sh[LFG_N][NEG_THREADS];
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nneg = nseq * fold;
@@ -190,7 +191,7 @@ k_neg_sample(const uint64_t* __restrict__ off /* [nseq+1] prefix sums of the TEM
     uint64_t o = fold * tbase + m * L;                           // byte offset of negative g = index of its first draw
     {
         uint32_t st[LFG_N];
-        lfg_jump(o + 310ull, u0, pw, st);
+        lfg_jump(draw0 + o + 310ull, u0, pw, st);
 #pragma unroll 1
         for (int k = 0; k < LFG_N; k++) st_sh[k][threadIdx.x] = st[k];
     }

@@ -308,7 +308,14 @@ def run_c4(args, wl):
     # negative set on the device (bit-identical to the reference's host sampler)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    neg = ss.sample_negatives(mfold)
+    if world > 1:
+        # shards of ONE negative set: set-wide k-mer counts summed over the ranks, every rank starts at its draw offset, so
+        # the union of the shards is the set a single device (and the reference) samples for the union of the positives
+        cnt = torch.from_numpy(ss.negative_kmer_counts().astype(np.int64)).cuda()
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        neg = ss.sample_negatives_shard(mfold, rank * nseq * L * mfold, cnt.cpu().numpy().astype(np.uint64))
+    else:
+        neg = ss.sample_negatives(mfold)
     torch.cuda.synchronize()
     t_neg = time.perf_counter() - t0
     # one fold: its share of the positives (FDR.cpp:49-57) and every cv-th negative (FDR.cpp:58-60)

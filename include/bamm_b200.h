@@ -82,6 +82,15 @@ int bamm_seqset_get_offsets(const bamm_seqset* s, uint64_t* out);
  */
 int bamm_seqset_sample_negatives(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t fold, uint32_t seed,
                                  bamm_seqset** out);
+/*
+ * The same negative set sampled in shards (one process per GPU, every rank holds a contiguous block of the templates): the
+ * set-wide k-mer counts are a sum over ranks (bamm_seqset_negative_kmer_counts gives this rank's A + A^2 + A^3 counters, orders
+ * 0, 1, 2 concatenated; all-reduce them), and a rank's first record starts at draw `draw_offset` = fold * (stored bases of all
+ * templates on earlier ranks). The concatenation of the shards is bit-identical to the set one device samples alone.
+ */
+int bamm_seqset_negative_kmer_counts(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t* counts);
+int bamm_seqset_sample_negatives_shard(bamm_seqset* pos, const uint64_t* subset, uint64_t nsub, uint64_t fold, uint32_t seed,
+                                       uint64_t draw_offset, const uint64_t* global_counts, bamm_seqset** out);
 /* draws [first, first+count) of rand() after srand(seed), computed on the device (test hook for the generator above) */
 int bamm_rand_stream(uint32_t seed, uint64_t first, uint64_t count, int32_t* out);
 void bamm_seqset_destroy(bamm_seqset* s);

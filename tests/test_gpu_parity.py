@@ -413,6 +413,27 @@ def test_device_negative_sampling_of_a_template_subset(capi):
     assert np.array_equal(a.offsets, b.offsets) and np.array_equal(a.get_codes(), b.get_codes())
 
 
+@pytest.mark.parametrize("case", ["neg_ragged_N", "syn_k3_fdr"])
+def test_device_negative_sampling_in_shards_equals_the_whole(capi, case):
+    """Multi-GPU form of the sampler: two shards of the templates, set-wide k-mer counts summed over the shards, the second
+    shard starting at its draw offset — the concatenation is the reference's negative set, bit for bit."""
+    g = Golden(case)
+    off = g["pos_offsets"].astype(np.int64)
+    nseq = len(off) - 1
+    cut = nseq // 3
+    shards = []
+    for lo, hi in ((0, cut), (cut, nseq)):
+        codes = g["pos_codes"][off[lo]:off[hi]]
+        kmer = g["pos_kmer"][off[lo]:off[hi]]
+        pp, pk = capi.kmer_patches(codes, kmer)
+        shards.append(capi.SeqSet(codes, (off[lo:hi + 1] - off[lo]).astype(np.uint64), g.A, pp, pk))
+    counts = shards[0].negative_kmer_counts() + shards[1].negative_kmer_counts()
+    fold = g.meta["mFold"]
+    a = shards[0].sample_negatives_shard(fold, 0, counts)
+    b = shards[1].sample_negatives_shard(fold, fold * int(off[cut]), counts)
+    assert np.array_equal(np.concatenate([a.get_codes(), b.get_codes()]), g["neg_codes"])
+
+
 def test_device_rand_stream_is_libc_rand(capi):
     """The device re-creation of glibc's rand() (additive lagged-Fibonacci TYPE_3, jump-ahead by polynomial powers) against
     libc itself: the first draws after srand(42) and a block far into the stream reached by running libc there."""
