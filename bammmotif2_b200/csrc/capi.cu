@@ -859,6 +859,7 @@ static ActiveList alist_of(const bamm_em* em) {
 }
 template <int G, bool FAST, bool MULTI> static int estep_packed_one(bamm_em* em, const PackedView* pv, size_t pass, bool optin_only) {
     GroupPlan gp = em->gplans[pass]; gp.q = em->q;
+    gp.thr0 = FX_HALF_UNIT * (1.0f - em->q) * 0.999f;
     if (optin_only) return max_smem_optin(k_estep_packed<G, FAST, MULTI>, gp.table_bytes);
     k_estep_packed<G, FAST, MULTI><<<em->grid_pe, em->block_pe, gp.table_bytes, em->stream>>>(*pv, gp, (const float*)((const char*)em->d_tab + pass * em->tab_capacity),
                                                                                        em->d_s, em->d_sT, em->d_r, em->d_xbuf + em->nbin, alist_of(em));

@@ -198,6 +198,7 @@ struct GroupPlan {
     // runs once per pass over a column range; the partial product of the earlier passes travels through r
     uint32_t passmask;           // bit j for every column of this pass (all W columns in a single-pass plan)
     int pass_first, pass_last;
+    float thr0;                  // 2^-41 (1-q) 0.999: smallest unnormalised value that can reach the M-step's threshold (norm >= 1-q)
 };
 
 // tab[g][z] = prod_{j in group g} s[j][ y_j(z) ], product in ascending j from 1.0f; z holds bases p+lo .. p+hi
@@ -304,10 +305,11 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
     const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);        // 32-bit shared-window address
     long long llh_fx = 0, rsum_fx = 0;
     const float one_minus_q = 1.0f - gp.q;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
     constexpr int E_UNROLL = BAMM_E_UNROLL;
     // a window can only reach the M-step's threshold r >= 2^-41 if val >= 2^-41 (1-q): norm >= 1-q (margin for rounding)
-    const float thr0 = FX_HALF_UNIT * (1.0f - gp.q) * 0.999f;
+    const float thr0 = gp.thr0;
     uint32_t c_sh[G], c_mk[G], c_ab[G], c_s2[G];
 #pragma unroll
     for (int g = 0; g < G; g++) {
