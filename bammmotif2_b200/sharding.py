@@ -70,3 +70,25 @@ def optimize_q(nseq_global, rsum):
     """reference: EM::optimize_q, src/refinement/EM.cpp:515 (formula kept as is), with the GLOBAL sequence count"""
     f = np.float32
     return (f(nseq_global) - f(rsum) + f(1.0)) / (f(nseq_global) + f(2.0))
+
+
+# ---- negative-set sampling in shards (bamm_seqset_sample_negatives_shard) ------------------------------------------------
+def negative_draw_offset(lengths, bounds, rank, fold):
+    """First rand() draw of a rank's shard of the negative set: every sampled base consumes one draw
+    (SeqGenerator.cpp:285-348) and every template of stored length L yields `fold` records of length L, so the shard of
+    rank r starts after fold * (stored bases of all templates on earlier ranks)."""
+    lengths = np.asarray(lengths, np.int64)
+    return int(fold) * int(lengths[:bounds[rank][0]].sum())
+
+
+def negative_kmer_counts(codes_kmer_order2, offsets, A):
+    """Host restatement of the counters bamm_seqset_negative_kmer_counts returns for one shard (orders 0, 1, 2
+    concatenated; positions j >= k only, SeqGenerator.cpp:73-84) from the order-2 k-mer indices kmer % A^3."""
+    y = np.asarray(codes_kmer_order2, np.int64)
+    off = np.asarray(offsets, np.int64)
+    out = np.zeros(A + A * A + A ** 3, np.int64)
+    local = np.arange(len(y), dtype=np.int64) - np.repeat(off[:-1], np.diff(off))
+    out[:A] = np.bincount(y % A, minlength=A)
+    out[A:A + A * A] = np.bincount((y % (A * A))[local >= 1], minlength=A * A)
+    out[A + A * A:] = np.bincount(y[local >= 2], minlength=A ** 3)
+    return out

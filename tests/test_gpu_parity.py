@@ -428,6 +428,9 @@ def test_device_negative_sampling_in_shards_equals_the_whole(capi, case):
         pp, pk = capi.kmer_patches(codes, kmer)
         shards.append(capi.SeqSet(codes, (off[lo:hi + 1] - off[lo]).astype(np.uint64), g.A, pp, pk))
     counts = shards[0].negative_kmer_counts() + shards[1].negative_kmer_counts()
+    from bammmotif2_b200 import sharding
+    whole = sharding.negative_kmer_counts((g["pos_kmer"] % np.uint64(g.A ** 3)).astype(np.int64), off, g.A)
+    assert np.array_equal(counts.astype(np.int64), whole)                  # device counters == host restatement (gloo test)
     fold = g.meta["mFold"]
     a = shards[0].sample_negatives_shard(fold, 0, counts)
     b = shards[1].sample_negatives_shard(fold, fold * int(off[cut]), counts)

@@ -107,3 +107,40 @@ def test_two_rank_exchange_equals_single_process(case, tmp_path, oracle):
     v = oracle.update_v(n_all, g["m1_alpha"], g["bg_v"], g.A, g.K, g.W, g["m1_v_init"].copy())
     ref = g["m1_v_it1"]
     assert np.all(np.abs(v - ref) <= 1e-5 * np.abs(ref))
+
+
+def _neg_worker(rank, world, port, case, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from util import Golden
+    g = Golden(case)
+    off = g["pos_offsets"].astype(np.int64)
+    L = np.diff(off)
+    bounds = sharding.shard_bounds(L, world)
+    lo, hi = bounds[rank]
+    y2 = (g["pos_kmer"][off[lo]:off[hi]] % np.uint64(g.A ** 3)).astype(np.int64)
+    cnt = torch.from_numpy(sharding.negative_kmer_counts(y2, off[lo:hi + 1] - off[lo], g.A))
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    out[rank] = (cnt.numpy().copy(), sharding.negative_draw_offset(L, bounds, rank, g.meta["mFold"]), hi - lo)
+    dist.destroy_process_group()
+
+
+def test_negative_sampling_shards_gloo():
+    """Host logic of the sharded negative sampler on two gloo ranks: the all-reduced k-mer counters equal the whole set's,
+    and the draw offsets tile the reference's rand() stream without gap or overlap."""
+    from util import Golden
+    case = "neg_ragged_N"
+    g = Golden(case)
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_neg_worker, args=(world, 29533, case, out), nprocs=world, join=True)
+    off = g["pos_offsets"].astype(np.int64)
+    whole = sharding.negative_kmer_counts((g["pos_kmer"] % np.uint64(g.A ** 3)).astype(np.int64), off, g.A)
+    assert np.array_equal(out[0][0], whole) and np.array_equal(out[1][0], whole)
+    L = np.diff(off)
+    fold = g.meta["mFold"]
+    assert out[0][1] == 0
+    assert out[1][1] == fold * int(L[:out[0][2]].sum())
+    assert out[1][1] + fold * int(L[out[0][2]:].sum()) == len(g["neg_codes"])       # one draw per sampled base
