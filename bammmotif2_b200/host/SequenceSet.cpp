@@ -37,8 +37,12 @@ SequenceSet::SequenceSet( std::string sequenceFilepath, bool singleStrand, std::
         file.seekg( 0, std::ios::beg );
         const char* force = getenv( "BAMM_DEVICE_FASTA" );
         if( force ? atoi( force ) != 0 : bytes >= ( std::streamoff( 1 ) << 26 ) ){
-            readFastaDevice( file, static_cast<size_t>( bytes ), singleStrand );
-            return;
+            if( readFastaDevice( file, static_cast<size_t>( bytes ), singleStrand ) ) return;
+            // more than 1/16 of the bases undefined (the device keeps a bounded list of them): this reader handles the file
+            file.clear();
+            file.seekg( 0, std::ios::beg );
+            offsets_.assign( 1, 0 );
+            headers_.clear();
         }
     }
     std::vector<size_t> baseCounts( Alphabet::getSize(), 0 );
@@ -194,7 +198,7 @@ void SequenceSet::appendRecord( const std::string& header, const std::string& ba
 // text, gets the base counts back, and draws the rand()-dependent k-mer hashes around undefined bases from the 21-code
 // neighbourhoods the device returns — the same draws in the same order as drawPatches() makes from the host arena.
 // The stored codes stay on the device until a host consumer asks for them.
-void SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singleStrand ){
+bool SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singleStrand ){
     std::string text( bytes, '\0' );
     file.read( &text[0], static_cast<std::streamsize>( bytes ) );
     text.resize( static_cast<size_t>( file.gcount() ) );
@@ -274,8 +278,18 @@ void SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singl
     std::vector<uint64_t> counts( A, 0 );
     uint64_t nzeroFwd = 0;
     const size_t N = recL0.size();
-    BAMM_CHECK( bamm_seqset_encode_text( t, n, segs.data(), segs.size(), offsets_.data(), recL0.data(), N, singleStrand ? 1 : 0,
-                                         static_cast<int>( A ), lut, comp, counts.data(), &nzeroFwd, &device_ ) );
+    {
+        const int rc = bamm_seqset_encode_text( t, n, segs.data(), segs.size(), offsets_.data(), recL0.data(), N, singleStrand ? 1 : 0,
+                                                static_cast<int>( A ), lut, comp, counts.data(), &nzeroFwd, &device_ );
+        if( rc == BAMM_E_INVALID && std::string( bamm_last_error() ).find( "undefined" ) != std::string::npos ){
+            device_ = nullptr;
+            return false;
+        }
+        if( rc != BAMM_OK ){
+            std::cerr << "Error: " << bamm_last_error() << std::endl;
+            std::exit( 1 );
+        }
+    }
     size_t total = 0;
     for( uint64_t c : counts ) total += c;
     baseFrequencies_.resize( A );
@@ -332,6 +346,7 @@ void SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singl
     BAMM_CHECK( bamm_seqset_finish_patches( device_, patchPos_.data(), patchKmer_.data(), patchPos_.size() ) );
     codesOnDevice_ = true;
     finalize();
+    return true;
 }
 
 // Positions whose 11-mer hash contains a code-0 base: the reference replaces the 0 by rand() % A separately for every

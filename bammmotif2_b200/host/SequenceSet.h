@@ -99,7 +99,7 @@ private:
     friend class Sequence;
     void                    appendRecord( const std::string& header, const std::string& bases, bool singleStrand,
                                           std::vector<size_t>& baseCounts );
-    void                    readFastaDevice( std::ifstream& file, size_t bytes, bool singleStrand );
+    bool                    readFastaDevice( std::ifstream& file, size_t bytes, bool singleStrand );   // false: too many undefined bases, use the host loop
     void                    drawPatches( uint64_t begin, uint64_t end );
     void                    finalize();
     void                    ensureCodes()           { if( codesOnDevice_ ) fetchCodes(); }

@@ -95,6 +95,24 @@ def test_fasta_encoding_on_the_device_bit_exact(bins, case, tmp_path):
     assert len(freq) == g.A
 
 
+@pytest.mark.gpu
+def test_fasta_with_many_undefined_bases_falls_back_to_the_host_reader(bins, tmp_path):
+    """The device encoder keeps a bounded list of undefined bases (1/16 of the text); a file above that is read by the
+    host loop instead, with the same result as when the host loop is asked for directly."""
+    rng = np.random.default_rng(11)
+    fa = tmp_path / "n.fasta"
+    with open(fa, "w") as f:
+        for i in range(300):
+            f.write(">s%d\n" % i)
+            f.write("".join(rng.choice(list("ACGTNNN"), size=int(rng.integers(40, 90)))) + "\n")
+    d_host, d_dev = tmp_path / "h", tmp_path / "d"
+    d_host.mkdir(); d_dev.mkdir()
+    run([os.path.join(bins, "host_check"), "encode", "STANDARD", str(fa), "0", str(d_host)], env=dict(os.environ, BAMM_DEVICE_FASTA="0"))
+    run([os.path.join(bins, "host_check"), "encode", "STANDARD", str(fa), "0", str(d_dev)], env=dict(os.environ, BAMM_DEVICE_FASTA="1"))
+    for fn in ("codes.u8", "offsets.u64", "kmer.u64", "basefreq.f32"):
+        assert open(d_host / fn, "rb").read() == open(d_dev / fn, "rb").read(), fn
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_background_and_site_init_bit_exact(bins, case, tmp_path):
     g = Golden(case)
