@@ -21,6 +21,7 @@ SIGNATURES = {
     "bamm_last_error": (C.c_char_p, []),
     "bamm_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "bamm_set_device": (C.c_int, [C.c_int]),
+    "bamm_plan_describe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64, _u64p]),
     "bamm_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _u64p]),
     "bamm_seqset_create": (C.c_int, [_u8p, _u64p, C.c_uint64, C.c_int, _u64p, _u64p, C.c_uint64, C.POINTER(_vp)]),
     "bamm_seqset_index": (C.c_int, [_vp, C.c_int]),
@@ -115,6 +116,28 @@ def device_count():
     n = C.c_int(0)
     rc = load().bamm_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+def plan_describe(W, K, K_bg=0, reduced=True, budget=227 * 1024):
+    """Column-group plan of the packed E-step as a list of passes (host arithmetic only, works without a GPU):
+    [{G, kd, fast, table_bytes, ca, cb, first, last, groups: [{col0, ncol, lo, shift, shift2, mask4, base, colmask}]}];
+    [] when no packed plan fits the budget."""
+    out = np.zeros(1 + 32 * (8 + 8 * 16), np.int32)
+    used = C.c_uint64(0)
+    _check(load().bamm_plan_describe(int(W), int(K), int(K_bg), 1 if reduced else 0, int(budget),
+                                     out.ctypes.data_as(C.POINTER(C.c_int32)), len(out), C.byref(used)))
+    o = out[:used.value].astype(np.int64)
+    passes, i = [], 1
+    for _ in range(int(o[0])):
+        G, kd, fast, tb, ca, cb, first, last = (int(x) for x in o[i:i + 8])
+        i += 8
+        groups = []
+        for _g in range(G):
+            c0, nc, lo, sh, sh2, m4, base, cm = (int(x) for x in o[i:i + 8])
+            i += 8
+            groups.append(dict(col0=c0, ncol=nc, lo=lo, shift=sh, shift2=sh2, mask4=m4 & 0xffffffff, base=base, colmask=cm & 0xffffffff))
+        passes.append(dict(G=G, kd=kd, fast=bool(fast), table_bytes=tb, ca=ca, cb=cb, first=bool(first), last=bool(last), groups=groups))
+    return passes
 
 
 def rand_stream(seed, first, count):

@@ -599,6 +599,36 @@ static bool plan_passes(int W, int K, int K_bg, bool reduced, size_t budget, std
     return true;
 }
 
+// The plan as plain numbers (no device work): what bamm_em_create / bamm_em_set_model would choose for these parameters.
+extern "C" int bamm_plan_describe(int W, int K, int K_bg_model, int reduced, uint64_t table_budget_bytes, int32_t* out, uint64_t cap,
+                                  uint64_t* n_used) {
+    REQUIRE(out && n_used, "NULL argument");
+    REQUIRE(W >= 1 && W <= 32, "motif width W=%d not in [1,32]", W);
+    REQUIRE(K >= 0 && K <= 10 && K_bg_model >= 0 && K_bg_model <= 10, "order out of range");
+    std::vector<GroupPlan> plans; std::vector<char> fast;
+    *n_used = 0;
+    const int K_bg = K_bg_model < K ? K_bg_model : K;          // as in bamm_em_create (reference EM.cpp:23)
+    if (!plan_passes(W, K, K_bg, reduced != 0, (size_t)table_budget_bytes, plans, fast)) { REQUIRE(cap >= 1, "buffer too small"); out[0] = 0; *n_used = 1; return BAMM_OK; }
+    uint64_t n = 1;
+    for (const GroupPlan& gp : plans) n += 8 + 8 * (uint64_t)gp.G;
+    REQUIRE(cap >= n, "buffer too small: %llu words needed", (unsigned long long)n);
+    int32_t* o = out;
+    *o++ = (int32_t)plans.size();
+    for (size_t i = 0; i < plans.size(); i++) {
+        const GroupPlan& gp = plans[i];
+        int ca = 0; while (ca < 32 && !((gp.passmask >> ca) & 1u)) ca++;
+        int cb = 32; while (cb > 0 && !((gp.passmask >> (cb - 1)) & 1u)) cb--;
+        *o++ = gp.G; *o++ = gp.kd; *o++ = fast[i] ? 1 : 0; *o++ = (int32_t)gp.table_bytes; *o++ = ca; *o++ = cb;
+        *o++ = (int32_t)gp.pass_first; *o++ = (int32_t)gp.pass_last;
+        for (int g = 0; g < gp.G; g++) {
+            *o++ = (int32_t)gp.col0[g]; *o++ = (int32_t)gp.ncol[g]; *o++ = (int32_t)gp.lo[g]; *o++ = (int32_t)gp.shift[g];
+            *o++ = (int32_t)gp.shift2[g]; *o++ = (int32_t)gp.mask4[g]; *o++ = (int32_t)gp.base[g]; *o++ = (int32_t)gp.colmask[g];
+        }
+    }
+    *n_used = n;
+    return BAMM_OK;
+}
+
 extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
                               bamm_em** out) {
     REQUIRE(out, "out is NULL");

@@ -45,6 +45,12 @@ int         bamm_version(void);                    /* 10000*major + 100*minor + 
 const char* bamm_last_error(void);                 /* text of the last failure on this thread */
 int         bamm_device_count(int* count);
 int         bamm_set_device(int device);           /* device used by objects created afterwards on this thread */
+/* The column-group plan of the packed E-step for (W, K, K_bg) under a shared-memory budget, as plain numbers; host
+ * arithmetic only, no device needed (the planner replaces the per-position loop bounds of EM::EStep, src/refinement/EM.cpp:149-196,
+ * by table lookups; DESIGN.md "column groups"). out: [npass] then per pass {G, kd, fast, table_bytes, first column, end column,
+ * is_first, is_last} followed by G x {col0, ncol, lo, shift, shift2, mask4, base, colmask}. npass = 0: no packed plan fits. */
+int         bamm_plan_describe(int W, int K, int K_bg_model, int reduced, uint64_t table_budget_bytes, int32_t* out, uint64_t cap,
+                               uint64_t* n_used);
 int         bamm_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
 
 /* ---- sequence set  (replaces Sequence::kmer_ / getKmer(), src/init/Sequence.cpp:35-41, Sequence.h:56-58) ---- */
