@@ -78,6 +78,41 @@ struct Trace {
         t0 = t1;
     }
 };
+// Pinned host scalars of the EM objects (log likelihood, sum of posteriors, sum|dv| read back every iteration): slots of one
+// process-wide pinned slab — a pinned allocation per object costs milliseconds (FDR creates an EM object per fold).
+static std::mutex g_pin_mu;
+static unsigned long long* g_pin_slab = nullptr;
+static std::vector<int> g_pin_free;
+constexpr int PIN_SLOTS = 256, PIN_SLOT_WORDS = 4;
+static cudaError_t pinned_scalars_get(unsigned long long** out) {
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        if (!g_pin_slab) {
+            void* p = nullptr;
+            if (cudaHostAlloc(&p, (size_t)PIN_SLOTS * PIN_SLOT_WORDS * sizeof(unsigned long long), cudaHostAllocPortable) == cudaSuccess) {
+                g_pin_slab = static_cast<unsigned long long*>(p);
+                for (int i = PIN_SLOTS - 1; i >= 0; i--) g_pin_free.push_back(i);
+            } else cudaGetLastError();
+        }
+        if (g_pin_slab && !g_pin_free.empty()) {
+            *out = g_pin_slab + (size_t)g_pin_free.back() * PIN_SLOT_WORDS;
+            g_pin_free.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaMallocHost(out, PIN_SLOT_WORDS * sizeof(unsigned long long));
+}
+static void pinned_scalars_put(unsigned long long* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        if (g_pin_slab && p >= g_pin_slab && p < g_pin_slab + (size_t)PIN_SLOTS * PIN_SLOT_WORDS) {
+            g_pin_free.push_back((int)((p - g_pin_slab) / PIN_SLOT_WORDS));
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
 static uint64_t ipow_u64(uint64_t b, int e) { uint64_t r = 1; while (e-- > 0) r *= b; return r; }
 
 // ------------------------------------------------------------------------------------------- objects
@@ -105,7 +140,15 @@ struct bamm_seqset {
     // sets encoded from FASTA text on the device: stored positions of the forward undefined bases, until the patches arrive
     uint64_t* d_zero_pos = nullptr;
     uint64_t n_zero_fwd = 0;
+    // bamm_seqset_create: the uploads run on their own stream while the host checks the offsets and the first kernels start
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_codes = nullptr, ev_patches = nullptr;
 };
+static void seqset_copy_done(bamm_seqset* s) {      // waits for the uploads and drops the stream
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); s->copy_stream = nullptr; }
+    if (s->ev_codes) { cudaEventDestroy(s->ev_codes); s->ev_codes = nullptr; }
+    if (s->ev_patches) { cudaEventDestroy(s->ev_patches); s->ev_patches = nullptr; }
+}
 
 struct bamm_em {
     bamm_seqset* ss = nullptr;
@@ -176,6 +219,7 @@ struct bamm_em {
     uint32_t* d_m_ids = nullptr; uint64_t* d_m_roff = nullptr; uint64_t* d_m_woff = nullptr;
     uint64_t* d_m_seloff = nullptr; uint32_t* d_m_sel = nullptr;
     std::vector<uint32_t> h_ids;            // subset -> seqset index (all sequences of the subset, in order)
+    bool whole_set = false;                 // identity subset of an all-regular set: h_ids / h_r_off are made on first use (host_lists)
     // host (pinned)
     unsigned long long* h_scal = nullptr;   // 2 scalars
     float* h_vdiff = nullptr;
@@ -209,55 +253,92 @@ extern "C" int bamm_device_info(int* sm_count, int* cc_major, int* cc_minor, uin
 // ------------------------------------------------------------------------------------------- seqset
 extern "C" void bamm_seqset_destroy(bamm_seqset* s);
 // host bookkeeping + device allocation of codes / offsets (codes are filled by the caller: H2D copy or a device kernel)
-static int seqset_new(const uint64_t* offsets, uint64_t nseq, int A, bamm_seqset** out) {
+// upload_codes: host codes to copy (bamm_seqset_create); the copy is started first, on the set's copy stream, and the host
+// pass over the offsets runs while the bases travel. ev_codes marks codes + offsets in place.
+static int seqset_new(const uint64_t* offsets, uint64_t nseq, int A, bamm_seqset** out, const uint8_t* upload_codes = nullptr) {
     REQUIRE(out, "out is NULL");
     *out = nullptr;
     REQUIRE(offsets, "offsets is NULL");
     REQUIRE(A >= 2 && A <= 6, "alphabet size %d not in [2,6]", A);
     REQUIRE(offsets[0] == 0, "offsets[0] must be 0");
     REQUIRE(nseq < (1ull << 32), "too many sequences");
-    uint64_t maxL = 0, minL = ~0ull;
-    for (uint64_t n = 0; n < nseq; n++) {
-        REQUIRE(offsets[n + 1] >= offsets[n], "offsets not monotone at %llu", (unsigned long long)n);
-        uint64_t L = offsets[n + 1] - offsets[n];
-        if (L > maxL) maxL = L;
-        if (L < minL) minL = L;
-    }
+    if (!upload_codes)
+        for (uint64_t n = 0; n < nseq; n++) REQUIRE(offsets[n + 1] >= offsets[n], "offsets not monotone at %llu", (unsigned long long)n);
     const uint64_t npos = offsets[nseq];
     bamm_seqset* s = new (std::nothrow) bamm_seqset();
     if (!s) return fail(BAMM_E_NOMEM, "host allocation failed");
     int dev; cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { delete s; return fail(BAMM_E_CUDA, "no CUDA device: %s", cudaGetErrorString(e)); }
-    s->device = dev; s->A = A; s->nseq = nseq; s->npos = npos; s->npatch = 0; s->maxL = maxL; s->minL = nseq ? minL : 0;
-    s->h_off.assign(offsets, offsets + nseq + 1);
+    s->device = dev; s->A = A; s->nseq = nseq; s->npos = npos; s->npatch = 0;
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
 #define CUS(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { bamm_seqset_destroy(s); \
     return fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); } } while (0)
     CUS(dev_malloc(&s->d_codes, npos ? npos : 1));
     CUS(dev_malloc(&s->d_off, (nseq + 1) * sizeof(uint64_t)));
-    CUS(cudaMemcpy(s->d_off, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (upload_codes) {
+        CUS(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CUS(cudaEventCreateWithFlags(&s->ev_codes, cudaEventDisableTiming));
+        CUS(cudaEventCreateWithFlags(&s->ev_patches, cudaEventDisableTiming));
+        CUS(cudaMemcpyAsync(s->d_off, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->copy_stream));
+        if (npos) CUS(cudaMemcpyAsync(s->d_codes, upload_codes, npos, cudaMemcpyHostToDevice, s->copy_stream));
+        CUS(cudaEventRecord(s->ev_codes, s->copy_stream));
+    } else {
+        CUS(cudaMemcpy(s->d_off, offsets, (nseq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    uint64_t maxL = 0, minL = ~0ull, bad = ~0ull;
+    for (uint64_t n = 0; n < nseq; n++) {
+        if (offsets[n + 1] < offsets[n]) { bad = n; break; }
+        uint64_t L = offsets[n + 1] - offsets[n];
+        if (L > maxL) maxL = L;
+        if (L < minL) minL = L;
+    }
+    if (bad != ~0ull) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, "offsets not monotone at %llu", (unsigned long long)bad); }
+    s->maxL = maxL; s->minL = nseq ? minL : 0;
+    s->h_off.assign(offsets, offsets + nseq + 1);
     *out = s;
     return BAMM_OK;
 }
 
 // classification + 2-bit packing on the device (no host pass over the bases); d_codes and the patch list are in place
 // known_regular: the caller vouches that every code is in 1..4 (a set the library sampled itself): no classification pass
-static int seqset_finish(bamm_seqset* s, bool known_regular = false) {
+// validate_patches: the patch list came from the caller and is checked first (strictly increasing, inside the set)
+static int seqset_finish(bamm_seqset* s, bool known_regular = false, bool validate_patches = false) {
     const uint64_t nseq = s->nseq, npatch = s->npatch;
     Trace tr("seqset_finish");
     s->h_kind.assign(nseq, 0);
+    const bool classify = s->A == 4 && nseq && !known_regular;
+    uint32_t* d_cover0 = nullptr;
+    if (classify) {
+        CUS(dev_malloc(&s->d_kind, nseq));
+        CUS(dev_malloc(&d_cover0, nseq * sizeof(uint32_t)));
+    }
+    if (s->ev_codes) { cudaError_t ew = cudaStreamWaitEvent(0, s->ev_codes, 0); if (ew != cudaSuccess) { cudaFree(d_cover0); CUS(ew); } }
+    if (classify) {       // needs the bases only: runs while the patch list is still on its way
+        cudaMemsetAsync(d_cover0, 0, nseq * sizeof(uint32_t), 0);
+        k_classify<<<s->sm_count * 8, 256>>>(s->d_codes, s->d_off, nseq, s->d_kind);
+    }
+    if (s->ev_patches) { cudaError_t ew = cudaStreamWaitEvent(0, s->ev_patches, 0); if (ew != cudaSuccess) { cudaFree(d_cover0); CUS(ew); } }
+    if (validate_patches && npatch) {
+        uint32_t* d_bad = nullptr; uint32_t bad = 0;
+        cudaError_t ev = dev_malloc(&d_bad, sizeof(uint32_t));
+        if (ev == cudaSuccess) ev = cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), 0);
+        if (ev == cudaSuccess) {
+            k_validate_patches<<<(unsigned)((npatch + 255) / 256), 256>>>(s->d_ppos, npatch, s->npos, d_bad);
+            ev = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+        }
+        cudaFree(d_bad);
+        if (ev != cudaSuccess || bad) cudaFree(d_cover0);
+        CUS(ev);
+        if (bad) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, bad & 1u ? "patch position out of range" : "patch positions must be strictly increasing"); }
+    }
     if (s->A == 4 && nseq && known_regular) {
         CUS(dev_malloc(&s->d_kind, nseq));
         CUS(cudaMemset(s->d_kind, 1, nseq));
         s->h_kind.assign(nseq, 1);
     }
     if (s->A == 4 && nseq) {
-        uint32_t* d_cover = nullptr;
+        uint32_t* d_cover = d_cover0;
         if (!known_regular) {
-        CUS(dev_malloc(&s->d_kind, nseq));
-        CUS(dev_malloc(&d_cover, nseq * sizeof(uint32_t)));
-        CUS(cudaMemset(d_cover, 0, nseq * sizeof(uint32_t)));
-        k_classify<<<s->sm_count * 8, 256>>>(s->d_codes, s->d_off, nseq, s->d_kind);
         if (npatch) k_check_patches<<<(unsigned)((npatch + 255) / 256), 256>>>(s->d_ppos, npatch, s->d_off, nseq, s->d_kind, d_cover);
         k_finish_kinds<<<(unsigned)((nseq + 255) / 256), 256>>>(s->d_off, nseq, d_cover, s->d_kind);
         cudaError_t ec = cudaMemcpy(s->h_kind.data(), s->d_kind, nseq, cudaMemcpyDeviceToHost);
@@ -307,30 +388,21 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
     REQUIRE(npatch == 0 || (patch_pos && patch_kmer), "patch arrays are NULL");
     bamm_seqset* s = nullptr;
     Trace tr("seqset_create");
-    { int rc = seqset_new(offsets, nseq, A, &s); if (rc) return rc; }
-    tr.mark("host checks + alloc + offsets H2D");
-    const uint64_t npos = s->npos;
+    // uploads on the copy stream: offsets, bases, then the patch list; the host pass over the offsets, the classification of
+    // the bases and the patch checks (on the device: 11 entries per both-strand sequence) start as soon as their input is there
+    { int rc = seqset_new(offsets, nseq, A, &s, codes); if (rc) return rc; }
+    tr.mark("alloc + host checks (uploads in flight)");
     s->npatch = npatch;
-    CUS(cudaMemcpy(s->d_codes, codes, npos, cudaMemcpyHostToDevice));
-    tr.mark("codes H2D");
     if (npatch) {
         CUS(dev_malloc(&s->d_ppos, npatch * sizeof(uint64_t)));
         CUS(dev_malloc(&s->d_pkmer, npatch * sizeof(uint64_t)));
-        CUS(cudaMemcpy(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
-        CUS(cudaMemcpy(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice));
-        // the list must be strictly increasing and inside the set: checked on the device (11 entries per both-strand sequence)
-        uint32_t* d_bad = nullptr; uint32_t bad = 0;
-        CUS(dev_malloc(&d_bad, sizeof(uint32_t)));
-        cudaMemset(d_bad, 0, sizeof(uint32_t));
-        k_validate_patches<<<(unsigned)((npatch + 255) / 256), 256>>>(s->d_ppos, npatch, npos, d_bad);
-        cudaError_t ev = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
-        cudaFree(d_bad);
-        CUS(ev);
-        if (bad) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, bad & 1u ? "patch position out of range" : "patch positions must be strictly increasing"); }
+        CUS(cudaMemcpyAsync(s->d_ppos, patch_pos, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice, s->copy_stream));
+        CUS(cudaMemcpyAsync(s->d_pkmer, patch_kmer, npatch * sizeof(uint64_t), cudaMemcpyHostToDevice, s->copy_stream));
     }
-    tr.mark("patch list H2D + checks");
-    { int rc = seqset_finish(s); if (rc) return rc; }
-    tr.mark("classify + pack");
+    CUS(cudaEventRecord(s->ev_patches, s->copy_stream));
+    { int rc = seqset_finish(s, false, true); if (rc) return rc; }
+    seqset_copy_done(s);                           // the caller's buffers are free again
+    tr.mark("uploads + classify + pack");
     *out = s;
     return BAMM_OK;
 }
@@ -342,6 +414,7 @@ extern "C" void bamm_seqset_destroy(bamm_seqset* s) {
     for (auto& kv : s->index) cudaFree(kv.second.d);
     for (auto& kv : s->ypatch) cudaFree(kv.second);
     cudaFree(s->d_kind); cudaFree(s->d_pseq); cudaFree(s->d_words); cudaFree(s->d_zero_pos);
+    seqset_copy_done(s);
     cudaFree(s->d_codes); cudaFree(s->d_off); cudaFree(s->d_ppos); cudaFree(s->d_pkmer);
     delete s;
 }
@@ -486,8 +559,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     cudaFree(em->d_vdiff); cudaFree(em->d_vdiff_part);
     cudaFree(em->d_m_ids); cudaFree(em->d_m_roff); cudaFree(em->d_m_woff); cudaFree(em->d_m_seloff); cudaFree(em->d_m_sel);
     for (cudaEvent_t e : em->loop_ev) cudaEventDestroy(e);
-    if (em->h_scal) cudaFreeHost(em->h_scal);
-    if (em->h_vdiff) cudaFreeHost(em->h_vdiff);
+    pinned_scalars_put(em->h_scal);                    // h_vdiff lives in the same slot
     for (int i = 0; i < 4; i++) if (em->ev[i]) cudaEventDestroy(em->ev[i]);
     if (em->stream) cudaStreamDestroy(em->stream);
     delete em;
@@ -667,22 +739,19 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         em->plan.Yn = em->Yn; em->plan.Zn = em->Yn; em->plan.q = 0.3f;
     }
     // ---- split the subset
-    em->h_r_off.resize(nsub + 1);
-    std::vector<uint32_t> ids(nsub), gen_ids, pk_ids;
+    std::vector<uint32_t> ids, gen_ids, pk_ids;
     std::vector<uint64_t> gen_roff, pk_roff;
+    uint64_t max_lw1_pk = 0;
+    if (!subset && packed_ok && s->nregular == s->nseq && s->minL >= (uint64_t)W && nsub > 0) {
+        // the whole set, every sequence regular and long enough: the lists are the identity and the set's own offsets
+        // (prefix sums of L) — made on the device below; no host pass over the sequences
+        em->whole_set = true;
+        max_lw1_pk = s->maxL - (uint64_t)W + 1;
+    } else {
+    em->h_r_off.resize(nsub + 1);
+    ids.resize(nsub);
     pk_ids.reserve(nsub); pk_roff.reserve(nsub);
     em->h_r_off[0] = 0;
-    uint64_t max_lw1_pk = 0;
-    if (!subset && packed_ok && s->nregular == s->nseq && s->minL >= (uint64_t)W) {
-        // the whole set, every sequence regular and long enough: identity lists without per-sequence decisions
-        pk_ids.resize(nsub); pk_roff.resize(nsub);
-        for (uint64_t i = 0; i < nsub; i++) {
-            ids[i] = (uint32_t)i; pk_ids[i] = (uint32_t)i;
-            pk_roff[i] = s->h_off[i];                           // prefix sums of L of the whole set = its offsets
-            em->h_r_off[i + 1] = s->h_off[i + 1];
-        }
-        max_lw1_pk = s->maxL - (uint64_t)W + 1;
-    } else
     for (uint64_t i = 0; i < nsub; i++) {
         const uint64_t n = subset ? subset[i] : i;
         if (n >= s->nseq) { delete em; return fail(BAMM_E_INVALID, "subset[%llu]=%llu out of range", (unsigned long long)i, (unsigned long long)n); }
@@ -697,9 +766,10 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             gen_ids.push_back((uint32_t)n); gen_roff.push_back(em->h_r_off[i]);
         }
     }
-    em->rsize = em->h_r_off[nsub];
-    em->h_ids = ids;
-    em->ngen = (uint32_t)gen_ids.size(); em->npk = (uint32_t)pk_ids.size();
+    }
+    em->rsize = em->whole_set ? s->npos : em->h_r_off[nsub];
+    em->h_ids.swap(ids);
+    em->ngen = (uint32_t)gen_ids.size(); em->npk = em->whole_set ? (uint32_t)nsub : (uint32_t)pk_ids.size();
     tr.mark("subset split (host)");
     IndexArray* ia = nullptr;
     if (em->ngen) { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) { delete em; return rc; } }
@@ -716,8 +786,16 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     };
     CUE(upload(gen_ids.data(), gen_ids.size() * 4, (void**)&em->d_gen_ids));
     CUE(upload(gen_roff.data(), gen_roff.size() * 8, (void**)&em->d_gen_roff));
-    CUE(upload(pk_ids.data(), pk_ids.size() * 4, (void**)&em->d_pk_ids));
-    CUE(upload(pk_roff.data(), pk_roff.size() * 8, (void**)&em->d_pk_roff));
+    if (em->whole_set) {
+        CUE(dev_malloc(&em->d_pk_ids, nsub * 4));
+        CUE(dev_malloc(&em->d_pk_roff, nsub * 8));
+        k_iota_u32<<<(unsigned)((nsub + 255) / 256), 256>>>(em->d_pk_ids, nsub);
+        CUE(cudaGetLastError());
+        CUE(cudaMemcpy(em->d_pk_roff, s->d_off, nsub * 8, cudaMemcpyDeviceToDevice));
+    } else {
+        CUE(upload(pk_ids.data(), pk_ids.size() * 4, (void**)&em->d_pk_ids));
+        CUE(upload(pk_roff.data(), pk_roff.size() * 8, (void**)&em->d_pk_roff));
+    }
     tr.mark("index / ypatch + id uploads");
     CUE(dev_malloc(&em->d_r, (em->rsize ? em->rsize : 1) * sizeof(float)));
     CUE(cudaMemset(em->d_r, 0, (em->rsize ? em->rsize : 1) * sizeof(float)));   // the packed E-step never touches the tail i >= LW1
@@ -733,8 +811,10 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     CUE(cudaMemset(em->d_xbuf, 0, ((uint64_t)em->nbin + 2) * sizeof(unsigned long long)));
     CUE(dev_malloc(&em->d_vdiff, sizeof(float)));
     CUE(dev_malloc(&em->d_vdiff_part, 16 * sizeof(double)));
-    CUE(cudaMallocHost(&em->h_scal, 2 * sizeof(unsigned long long)));
-    CUE(cudaMallocHost(&em->h_vdiff, sizeof(float)));
+    tr.mark("model buffers");
+    CUE(pinned_scalars_get(&em->h_scal));                                          // one pinned slot: 2 scalars + sum|dv|
+    em->h_vdiff = reinterpret_cast<float*>(em->h_scal + 2);
+    tr.mark("pinned scalars");
     em->nparts = 1;
     // ---- generic path geometry (only when some sequence needs it): persistent grid of 512-thread CTAs
     if (em->ngen) {
@@ -785,6 +865,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             if (mstep_w_dispatch(em, nullptr, nullptr, 0)) { fail(BAMM_E_CUDA, "cannot opt in to shared memory for the packed M-step"); bamm_em_destroy(em); return BAMM_E_CUDA; }
             if ((uint32_t)em->grid_pl > em->nparts) em->nparts = (uint32_t)em->grid_pl;
         }
+        tr.mark("M-step geometry + opt-in");
         // active list: one region per E-step warp, sized as a fraction of the warp's windows (BAMM_LIST_FRAC, 0 = off)
         double frac = getenv("BAMM_LIST_FRAC") ? atof(getenv("BAMM_LIST_FRAC")) : 0.5;
         std::vector<uint64_t> reg;
@@ -792,9 +873,16 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             em->nregions = (uint32_t)em->grid_pe * (uint32_t)(em->block_pe / 32);
             std::vector<uint64_t> win(em->nregions, 0);
             reg.assign((size_t)em->nregions + 1, 0);
-            for (size_t i = 0; i < pk_ids.size(); i++) {
-                const uint64_t n = pk_ids[i];
-                win[i % em->nregions] += s->h_off[n + 1] - s->h_off[n] - (uint64_t)W + 1;
+            if (em->whole_set && s->minL == s->maxL) {          // equal lengths: sequence i goes to warp i % nregions
+                const uint64_t lw1 = s->maxL - (uint64_t)W + 1, per = em->npk / em->nregions, extra = em->npk % em->nregions;
+                for (uint32_t w = 0; w < em->nregions; w++) win[w] = (per + (w < extra ? 1 : 0)) * lw1;
+            } else {
+                uint32_t w = 0;
+                for (size_t i = 0; i < em->npk; i++) {
+                    const uint64_t n = em->whole_set ? i : pk_ids[i];
+                    win[w] += s->h_off[n + 1] - s->h_off[n] - (uint64_t)W + 1;
+                    if (++w == em->nregions) w = 0;
+                }
             }
             // the list is an accelerator, not a requirement: when memory is short its capacity is halved (down to 1/32 of
             // the windows), below that the M-step scans r
@@ -822,12 +910,20 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             CUE(cudaMemset(em->d_overflow, 0, 4));
         }
     }
-    tr.mark("model buffers + active list");
+    tr.mark("active list");
     CUE(dev_malloc(&em->d_part, (uint64_t)em->nparts * em->nbin * sizeof(unsigned long long)));
 #undef CUE
     tr.mark("partials");
     *out = em;
     return BAMM_OK;
+}
+
+// h_ids / h_r_off of a whole-set object (identity, the set's offsets), made when a host consumer first asks
+static void host_lists(bamm_em* em) {
+    if (!em->whole_set || !em->h_r_off.empty()) return;
+    em->h_ids.resize(em->nsub);
+    for (uint64_t i = 0; i < em->nsub; i++) em->h_ids[i] = (uint32_t)i;
+    em->h_r_off.assign(em->ss->h_off.begin(), em->ss->h_off.begin() + em->nsub + 1);
 }
 
 static int launch_tuple_table(bamm_em* em) {
@@ -856,6 +952,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
     REQUIRE(em && v_all && vbg_all && alpha, "NULL argument");
     REQUIRE(q > 0.0f && q < 1.0f, "q=%g not in (0,1)", (double)q);
     CU(cudaSetDevice(em->device));
+    Trace tr("set_model");
     if (em->npk) {
         const bool reduced = leading_columns_are_copies(em->dims, em->K, em->W, em->Yn, v_all) && !getenv("BAMM_NO_REDUCED");
         if (!plan_passes(em->W, em->K, em->K_bg, reduced, em->tab_capacity, em->gplans, em->gfast))
@@ -869,6 +966,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
         for (size_t i = 0; i < em->gplans.size(); i++)
             if (estep_packed_dispatch(em, nullptr, i, true)) return fail(BAMM_E_CUDA, "cannot opt in to %u bytes of shared memory", em->gplans[i].table_bytes);
     }
+    tr.mark("plan + table buffer + opt-in");
     CU(cudaMemcpyAsync(em->d_v, v_all, em->model_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
     CU(cudaMemcpyAsync(em->d_vbg, vbg_all, em->bg_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
     CU(cudaMemcpyAsync(em->d_alpha, alpha, (uint64_t)(em->K + 1) * em->W * sizeof(float), cudaMemcpyHostToDevice, em->stream));
@@ -876,6 +974,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
     CU(cudaGetLastError());
     { int rc = launch_tuple_table(em); if (rc) return rc; }
     CU(cudaStreamSynchronize(em->stream));
+    tr.mark("uploads + s + group tables");
     em->q = q; em->model_set = true; em->s_valid = true; em->r_valid = false; em->llh = 0.0f;
     return BAMM_OK;
 }
@@ -1172,6 +1271,7 @@ static int mask_run(bamm_em* em, const YT* Y, float f, float epsilon, int max_it
     float* d_s0 = nullptr; float* d_all = nullptr; uint32_t* d_cnt = nullptr;
     int rc = BAMM_OK;
     uint64_t pos_count = 0;
+    host_lists(em);
     std::vector<uint64_t> woff(nsub + 1, 0);
     for (uint64_t i = 0; i < nsub; i++) woff[i + 1] = woff[i] + (em->h_r_off[i + 1] - em->h_r_off[i]) - (uint64_t)W + 1;
     pos_count = woff[nsub];
@@ -1265,6 +1365,7 @@ extern "C" int bamm_em_mask(bamm_em* em, float f, float epsilon, int max_iter, i
     CU(cudaSetDevice(em->device));
     IndexArray* ia = nullptr;
     { std::lock_guard<std::mutex> g(em->ss->mu); int rc = seqset_index_locked(em->ss, em->K, &ia); if (rc) return rc; }
+    host_lists(em);
     if (!em->d_m_ids) {
         CU(dev_malloc(&em->d_m_ids, em->nsub * sizeof(uint32_t)));
         CU(dev_malloc(&em->d_m_roff, (em->nsub + 1) * sizeof(uint64_t)));
@@ -1376,6 +1477,7 @@ extern "C" int bamm_em_get_r(bamm_em* em, uint64_t first, uint64_t count, float*
         CU(cudaGetLastError());
         em->r_scaled = true;
     }
+    host_lists(em);
     const uint64_t a = em->h_r_off[first], b = em->h_r_off[first + count];
     CU(cudaMemcpyAsync(out, em->d_r + a, (b - a) * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
     CU(cudaStreamSynchronize(em->stream));

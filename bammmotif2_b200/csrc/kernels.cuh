@@ -304,6 +304,12 @@ __global__ void k_peer_sum(const unsigned long long* __restrict__ slots /* [2][w
     xbuf[b] = acc;
 }
 
+// out[i] = i: the sequence list of an EM object over a whole set
+__global__ void k_iota_u32(uint32_t* __restrict__ out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Model update, one CTA. reference: fold of the counts EM.cpp:247-254, Motif::updateV Motif.h:95-136,
 // convergence term EM.cpp:102-107, Motif::calculateLinearS Motif.cpp:485-494. Every formula keeps the
