@@ -1782,13 +1782,10 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
     const size_t tb = (size_t)nbin * 4;
     const bool smem = tb <= (size_t)max_optin;
     const bool packed_ok = s->A == 4 && s->nregular > 0 && W + K <= 32 && ia_Yn <= 65536 && smem && !getenv("BAMM_NO_PACKED");
-    if (!mops && packed_ok && s->nregular == s->nseq && s->minL >= (uint64_t)W) {
-        // whole set regular and long enough (e.g. a sampled negative set): no per-sequence look-ups, the subset is the list
-        pk_ids.resize(nsub);
-        uint64_t worst = 0;
-        for (uint64_t i = 0; i < nsub; i++) { const uint64_t n = subset ? subset[i] : i; pk_ids[i] = (uint32_t)n; worst = n > worst ? n : worst; }
-        REQUIRE(nsub == 0 || worst < s->nseq, "subset index out of range");
-    } else
+    // whole set regular and long enough (e.g. a sampled negative set): no per-sequence look-ups — the caller's subset IS the
+    // list; it is uploaded as it is and narrowed / range-checked on the device (k_ids_from_u64), no host pass
+    const bool dev_ids = !mops && packed_ok && s->nregular == s->nseq && s->minL >= (uint64_t)W && nsub > 0;
+    if (!dev_ids)
     for (uint64_t i = 0; i < nsub; i++) {
         const uint64_t n = subset ? subset[i] : i;
         REQUIRE(n < s->nseq, "subset index out of range");
@@ -1799,12 +1796,13 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
         else { gen_ids.push_back((uint32_t)n); gen_out.push_back((uint32_t)i); }
     }
     const bool identity_out = gen_ids.empty();               // every sequence on the packed path: list index == output index
+    const uint64_t npk = dev_ids ? nsub : pk_ids.size();
     tr.mark("log table + subset split (host)");
     // ZOOPS-only calls on the packed path: prune with column-group tables, re-score exactly near the running maximum
     // (k_score_zoops_packed). eps bounds |cheap - exact|: both are fp32 sums of the same W table entries (|entry| <= S) in
     // different associations, each within (W-1) * 2^-24 * W * S of the real sum; factor 1.5 for slack.
     GroupPlan zplan; bool zfast = false, zoops_fast = false; float two_eps = 0.0f;
-    if (!mops && !pk_ids.empty() && !getenv("BAMM_NO_ZOOPS_FAST")) {
+    if (!mops && npk && !getenv("BAMM_NO_ZOOPS_FAST")) {
         float S = 0.0f;
         for (uint32_t i = 0; i < nbin; i++) { const float a = fabsf(slog[i]); if (!(a <= 3.0e38f)) { S = -1.0f; break; } if (a > S) S = a; }
         const bool reduced = leading_columns_are_copies(d, K, W, Yn, v_all);
@@ -1817,13 +1815,14 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
     IndexArray* ia = nullptr;
     uint16_t* d_yp = nullptr;
     if (!gen_ids.empty()) { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_index_locked(s, K, &ia); if (rc) return rc; }
-    if (!pk_ids.empty())  { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_ypatch_locked(s, K, &d_yp); if (rc) return rc; }
+    if (npk)  { std::lock_guard<std::mutex> g(s->mu); int rc = seqset_ypatch_locked(s, K, &d_yp); if (rc) return rc; }
     tr.mark("plan + index");
     CU(cudaSetDevice(s->device));
     cudaStream_t st; CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float *d_s = nullptr, *d_zoops = nullptr, *d_mops = nullptr, *d_ztab = nullptr; unsigned long long* d_z = nullptr;
     uint32_t *d_gids = nullptr, *d_gout = nullptr, *d_pids = nullptr, *d_pout = nullptr; uint64_t* d_moff = nullptr;
+    uint64_t* d_sub = nullptr; uint32_t* d_bad = nullptr; uint32_t bad = 0;
     int rc = BAMM_OK;
 #define CUX(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { rc = fail(e2_ == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e2_)); goto done; } } while (0)
     {
@@ -1832,14 +1831,24 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
         CUX(dev_malloc(&d_z, (nsub ? nsub : 1) * 8));
         CUX(dev_malloc(&d_gids, (gen_ids.size() ? gen_ids.size() : 1) * 4));
         CUX(dev_malloc(&d_gout, (gen_ids.size() ? gen_ids.size() : 1) * 4));
-        CUX(dev_malloc(&d_pids, (pk_ids.size() ? pk_ids.size() : 1) * 4));
-        CUX(dev_malloc(&d_pout, (pk_ids.size() && !identity_out ? pk_ids.size() : 1) * 4));
+        CUX(dev_malloc(&d_pids, (npk ? npk : 1) * 4));
+        CUX(dev_malloc(&d_pout, (npk && !identity_out ? npk : 1) * 4));
+        if (dev_ids) {
+            CUX(dev_malloc(&d_bad, 4));
+            CUX(cudaMemsetAsync(d_bad, 0, 4, st));
+            if (subset) {
+                CUX(dev_malloc(&d_sub, nsub * 8));
+                CUX(cudaMemcpyAsync(d_sub, subset, nsub * 8, cudaMemcpyHostToDevice, st));
+            }
+            k_ids_from_u64<<<(unsigned)((nsub + 255) / 256), 256, 0, st>>>(d_sub, nsub, s->nseq, d_pids, d_bad);
+            CUX(cudaGetLastError());
+        }
         CUX(dev_malloc(&d_moff, moff.size() * 8));
         if (mops) CUX(dev_malloc(&d_mops, (moff[nsub] ? moff[nsub] : 1) * 4));
         CUX(cudaMemcpyAsync(d_s, slog.data(), (uint64_t)nbin * 4, cudaMemcpyHostToDevice, st));
         CUX(cudaMemcpyAsync(d_gids, gen_ids.data(), gen_ids.size() * 4, cudaMemcpyHostToDevice, st));
         CUX(cudaMemcpyAsync(d_gout, gen_out.data(), gen_out.size() * 4, cudaMemcpyHostToDevice, st));
-        CUX(cudaMemcpyAsync(d_pids, pk_ids.data(), pk_ids.size() * 4, cudaMemcpyHostToDevice, st));
+        if (!dev_ids) CUX(cudaMemcpyAsync(d_pids, pk_ids.data(), pk_ids.size() * 4, cudaMemcpyHostToDevice, st));
         if (!identity_out) CUX(cudaMemcpyAsync(d_pout, pk_out.data(), pk_out.size() * 4, cudaMemcpyHostToDevice, st));
         CUX(cudaMemcpyAsync(d_moff, moff.data(), moff.size() * 8, cudaMemcpyHostToDevice, st));
         int per_sm = smem ? (int)((size_t)(max_optin + 1024) / (tb + 1024)) : 4;
@@ -1848,8 +1857,8 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
         CUX(cudaEventCreate(&ev0)); CUX(cudaEventCreate(&ev1));
         tr.mark("alloc + H2D");
         CUX(cudaEventRecord(ev0, st));
-        if (!pk_ids.empty()) {
-            PackedView pv; pv.words = s->d_words; pv.seqs = s->d_pseq; pv.ypatch = d_yp; pv.seq_ids = d_pids; pv.r_off = nullptr; pv.nlist = (uint32_t)pk_ids.size();
+        if (npk) {
+            PackedView pv; pv.words = s->d_words; pv.seqs = s->d_pseq; pv.ypatch = d_yp; pv.seq_ids = d_pids; pv.r_off = nullptr; pv.nlist = (uint32_t)npk;
             Plan pl; pl.W = W; pl.K = K; pl.T = 1; pl.C = W; pl.Yn = Yn; pl.Zn = Yn; pl.q = 0.f;
             if (zoops_fast) {
                 CUX(dev_malloc(&d_ztab, zplan.table_bytes));
@@ -1883,7 +1892,9 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
         CUX(cudaMemcpyAsync(zoops, d_zoops, nsub * 4, cudaMemcpyDeviceToHost, st));
         CUX(cudaMemcpyAsync(z, d_z, nsub * 8, cudaMemcpyDeviceToHost, st));
         if (mops) CUX(cudaMemcpyAsync(mops, d_mops, moff[nsub] * 4, cudaMemcpyDeviceToHost, st));
+        if (dev_ids) CUX(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
         CUX(cudaStreamSynchronize(st));
+        if (bad) { rc = fail(BAMM_E_INVALID, "subset index out of range"); goto done; }
         CUX(cudaEventElapsedTime(&g_score_ms, ev0, ev1));
         tr.mark("D2H");
     }
@@ -1891,7 +1902,7 @@ done:
 #undef CUX
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    cudaFree(d_ztab);
+    cudaFree(d_ztab); cudaFree(d_sub); cudaFree(d_bad);
     cudaFree(d_s); cudaFree(d_zoops); cudaFree(d_z); cudaFree(d_gids); cudaFree(d_gout); cudaFree(d_pids); cudaFree(d_pout); cudaFree(d_moff); cudaFree(d_mops);
     cudaStreamDestroy(st);
     return rc;

@@ -304,6 +304,16 @@ __global__ void k_peer_sum(const unsigned long long* __restrict__ slots /* [2][w
     xbuf[b] = acc;
 }
 
+// sequence list of a scoring call from the caller's 64-bit subset (NULL = the whole set): narrowed to 32 bits, range-checked
+// (an index outside the set raises the flag and is replaced by 0, so the kernels that follow stay inside the set)
+__global__ void k_ids_from_u64(const uint64_t* __restrict__ subset, uint64_t n, uint64_t nseq, uint32_t* __restrict__ out, uint32_t* __restrict__ bad) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = subset ? subset[i] : i;
+    if (v >= nseq) { *bad = 1u; v = 0; }
+    out[i] = (uint32_t)v;
+}
+
 // out[i] = i: the sequence list of an EM object over a whole set
 __global__ void k_iota_u32(uint32_t* __restrict__ out, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -201,6 +201,15 @@ def test_error_paths(capi):
     # a negative set needs at least one draw per record
     with pytest.raises(capi.BammError):
         short.sample_negatives(0)
+    # a scoring subset outside the set: caught on the device when the whole set is regular (ZOOPS-only call), on the host otherwise
+    reg = capi.SeqSet(np.array([1, 2, 3, 4, 1, 2, 3, 4, 4, 3], np.uint8), np.array([0, 5, 10], np.uint64), 4)
+    v1 = np.full(4 * 4, 0.25, np.float32)
+    with pytest.raises(capi.BammError, match="out of range"):
+        reg.score(4, 0, 0, v1, np.full(4, 0.25, np.float32), subset=np.array([1, 2], np.uint64), want_mops=False)
+    with pytest.raises(capi.BammError, match="out of range"):
+        reg.score(4, 0, 0, v1, np.full(4, 0.25, np.float32), subset=np.array([1, 2], np.uint64), want_mops=True)
+    _, zo, zz = reg.score(4, 0, 0, v1, np.full(4, 0.25, np.float32), subset=np.array([1, 0, 1], np.uint64), want_mops=False)
+    assert len(zo) == 3 and zo[0] == zo[2] and zz[0] == zz[2]
     # empty subset is legal and a no-op
     e0 = capi.EM(ss, 7, 0, 0, subset=np.zeros(0, np.uint64))
     e0.set_model(g["m1_v_init"], g["bg_v"], g["m1_alpha"], g.q)
