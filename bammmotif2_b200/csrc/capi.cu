@@ -255,7 +255,9 @@ extern "C" void bamm_seqset_destroy(bamm_seqset* s);
 // host bookkeeping + device allocation of codes / offsets (codes are filled by the caller: H2D copy or a device kernel)
 // upload_codes: host codes to copy (bamm_seqset_create); the copy is started first, on the set's copy stream, and the host
 // pass over the offsets runs while the bases travel. ev_codes marks codes + offsets in place.
-static int seqset_new(const uint64_t* offsets, uint64_t nseq, int A, bamm_seqset** out, const uint8_t* upload_codes = nullptr) {
+// own_offsets: the vector `offsets` points into; it is moved into the set instead of copied (10^7 records of a negative set)
+static int seqset_new(const uint64_t* offsets, uint64_t nseq, int A, bamm_seqset** out, const uint8_t* upload_codes = nullptr,
+                      std::vector<uint64_t>* own_offsets = nullptr) {
     REQUIRE(out, "out is NULL");
     *out = nullptr;
     REQUIRE(offsets, "offsets is NULL");
@@ -294,7 +296,8 @@ static int seqset_new(const uint64_t* offsets, uint64_t nseq, int A, bamm_seqset
     }
     if (bad != ~0ull) { bamm_seqset_destroy(s); return fail(BAMM_E_INVALID, "offsets not monotone at %llu", (unsigned long long)bad); }
     s->maxL = maxL; s->minL = nseq ? minL : 0;
-    s->h_off.assign(offsets, offsets + nseq + 1);
+    if (own_offsets) s->h_off.swap(*own_offsets);
+    else s->h_off.assign(offsets, offsets + nseq + 1);
     *out = s;
     return BAMM_OK;
 }
@@ -305,7 +308,7 @@ static int seqset_new(const uint64_t* offsets, uint64_t nseq, int A, bamm_seqset
 static int seqset_finish(bamm_seqset* s, bool known_regular = false, bool validate_patches = false) {
     const uint64_t nseq = s->nseq, npatch = s->npatch;
     Trace tr("seqset_finish");
-    s->h_kind.assign(nseq, 0);
+    s->h_kind.assign(nseq, s->A == 4 && known_regular ? 1 : 0);
     const bool classify = s->A == 4 && nseq && !known_regular;
     uint32_t* d_cover0 = nullptr;
     if (classify) {
@@ -334,7 +337,6 @@ static int seqset_finish(bamm_seqset* s, bool known_regular = false, bool valida
     if (s->A == 4 && nseq && known_regular) {
         CUS(dev_malloc(&s->d_kind, nseq));
         CUS(cudaMemset(s->d_kind, 1, nseq));
-        s->h_kind.assign(nseq, 1);
     }
     if (s->A == 4 && nseq) {
         uint32_t* d_cover = d_cover0;
@@ -347,7 +349,8 @@ static int seqset_finish(bamm_seqset* s, bool known_regular = false, bool valida
         }
         tr.mark("classify + kinds D2H");
         // packed-stream layout on the device: word counts -> exclusive scan -> PackedSeq records (no host pass, no upload)
-        for (uint64_t n = 0; n < nseq; n++) s->nregular += s->h_kind[n] != 0;
+        if (known_regular) s->nregular = nseq;
+        else for (uint64_t n = 0; n < nseq; n++) s->nregular += s->h_kind[n] != 0;
         if (s->nregular) {
             unsigned long long* d_wc = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0;
             CUS(dev_malloc(&d_wc, (nseq + 1) * 2 * sizeof(unsigned long long)));
@@ -1684,7 +1687,7 @@ static int sample_negatives_impl(bamm_seqset* pos, const uint64_t* subset, uint6
             for (uint64_t m = 0; m < fold; m++, g++) noff[g + 1] = noff[g] + L;
         }
         tr.mark("set-wide model + per-template bars + offsets (host)");
-        rc = seqset_new(noff.data(), nneg, pos->A, &neg);
+        rc = seqset_new(noff.data(), nneg, pos->A, &neg, nullptr, &noff);
         if (rc) goto done;
         tr.mark("seqset_new (alloc + offsets H2D)");
         LfgTables t; lfg_tables(seed, t);
