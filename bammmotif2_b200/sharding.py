@@ -92,3 +92,32 @@ def negative_kmer_counts(codes_kmer_order2, offsets, A):
     out[A:A + A * A] = np.bincount((y % (A * A))[local >= 1], minlength=A * A)
     out[A + A * A:] = np.bincount(y[local >= 2], minlength=A ** 3)
     return out
+
+
+# ---- scores of a sharded scoring call -> rank 0 --------------------------------------------------------------
+def gather_scores(zoops, z, shard_sizes, group=None, device=None):
+    """ZOOPS score (float32) and argmax (int64) per sequence of every rank's shard, concatenated in rank order on EVERY
+    rank (all_gather of shards padded to the largest one; NCCL on the GPUs, gloo in the CPU tests). Rank 0 then runs the
+    reference's host-side sort / precision-recall walk (FDR::calculatePR, src/evaluation/FDR.cpp:147-332) on the whole set.
+    shard_sizes: number of sequences each rank scored (known to every rank from shard_bounds)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    assert len(shard_sizes) == world
+    mine = int(shard_sizes[dist.get_rank(group)])
+    assert len(zoops) == mine and len(z) == mine
+    cap = max(int(max(shard_sizes)), 1)
+    # one 8-byte word per sequence: score bits in the low half, argmax in the high half (window starts are < 2^31)
+    zi = np.asarray(z, np.int64)
+    assert mine == 0 or (zi.min() >= 0 and zi.max() < (1 << 31))
+    word = np.zeros(cap, np.int64)
+    word[:mine] = np.ascontiguousarray(zoops, np.float32).view(np.uint32).astype(np.int64) | (zi << 32)
+    t = torch.from_numpy(word)
+    if device is not None:
+        t = t.to(device)
+    allw = torch.empty(world * cap, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(allw, t, group=group)
+    allw = allw.cpu().numpy().reshape(world, cap)
+    parts = [allw[r, :int(shard_sizes[r])] for r in range(world)]
+    words = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+    return (words & 0xffffffff).astype(np.uint32).view(np.float32), (words >> 32).astype(np.int64)

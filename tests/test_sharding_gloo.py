@@ -144,3 +144,34 @@ def test_negative_sampling_shards_gloo():
     assert out[0][1] == 0
     assert out[1][1] == fold * int(L[:out[0][2]].sum())
     assert out[1][1] + fold * int(L[out[0][2]:].sum()) == len(g["neg_codes"])       # one draw per sampled base
+
+
+def _score_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    L = rng.integers(30, 400, size=101)
+    zo_all = rng.standard_normal(101).astype(np.float32)
+    zo_all[5] = -np.inf                                         # a window score can be -inf (log of a zero probability)
+    z_all = rng.integers(0, L - 20)
+    bounds = sharding.shard_bounds(L, world)
+    lo, hi = bounds[rank]
+    zo, z = sharding.gather_scores(zo_all[lo:hi], z_all[lo:hi], [e - s for s, e in bounds])
+    np.save(os.path.join(out, "zo%d.npy" % rank), zo)
+    np.save(os.path.join(out, "z%d.npy" % rank), z)
+    if rank == 0:
+        np.save(os.path.join(out, "zo_all.npy"), zo_all)
+        np.save(os.path.join(out, "z_all.npy"), z_all)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gathered_scores_equal_the_unsharded_arrays(world, tmp_path):
+    """Row e, scoring: every rank's ZOOPS scores + argmax arrive in sequence order, bit for bit (ragged shards)."""
+    port = 29620 + world + (os.getpid() % 200)
+    mp.spawn(_score_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    zo_all, z_all = np.load(tmp_path / "zo_all.npy"), np.load(tmp_path / "z_all.npy")
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / ("zo%d.npy" % r)).view(np.uint32), zo_all.view(np.uint32))
+        assert np.array_equal(np.load(tmp_path / ("z%d.npy" % r)), z_all)
