@@ -14,6 +14,15 @@
 
 int main( int nargs, char* args[] ){
     auto t0_wall = std::chrono::high_resolution_clock::now();
+    // BAMM_TRACE: wall time of every stage of the driver on stderr (the library prints its own phases with the same switch)
+    const bool trace = getenv( "BAMM_TRACE" ) != NULL;
+    auto t_mark = t0_wall;
+    auto mark = [&]( const char* stage ){
+        if( !trace ) return;
+        const auto t = std::chrono::high_resolution_clock::now();
+        std::cerr << "[bamm host] " << stage << " " << std::chrono::duration<double, std::milli>( t - t_mark ).count() << " ms" << std::endl;
+        t_mark = t;
+    };
     std::cout << std::endl
               << "======================================" << std::endl
               << "=      Welcome to use BaMM!motif     =" << std::endl
@@ -27,6 +36,7 @@ int main( int nargs, char* args[] ){
         return 1;
     }
     if( const char* dev = getenv( "BAMM_DEVICE" ) ) BAMM_CHECK( bamm_set_device( atoi( dev ) ) );
+    mark( "options + FASTA" );
 
     std::vector<Sequence*> posSet = Global::posSequenceSet->getSequences();
 
@@ -34,10 +44,12 @@ int main( int nargs, char* args[] ){
         ? new BackgroundModel( Global::bgModelFilename )
         : new BackgroundModel( posSet, Global::bgModelOrder, Global::bgModelAlpha, Global::interpolateBG, Global::outputFileBasename );
     bgModel->write( Global::outputDirectory, Global::outputFileBasename );      // always written (mainBaMM.cpp:51)
+    mark( "background model" );
 
     MotifSet motif_set( Global::initialModelFilename, Global::addColumns.at( 0 ), Global::addColumns.at( 1 ), Global::initialModelTag,
                         Global::posSequenceSet, bgModel->getV(), Global::bgModelOrder, Global::modelOrder, Global::modelAlpha,
                         Global::maxPWM, Global::q );
+    mark( "initial motifs" );
 
     // sequences shorter than the widest motif cannot hold a window (mainBaMM.cpp:75-83)
     {
@@ -65,6 +77,7 @@ int main( int nargs, char* args[] ){
         negSequences = negseq.sample_bgseqset_by_fold( Global::mFold );
         negSet = negSequences->getSequences();
     }
+    mark( "negative set" );
 
     for( size_t n = 0; n < motif_set.getN(); n++ ){
         Motif* motif = new Motif( *motif_set.getMotifs()[n] );
@@ -77,6 +90,7 @@ int main( int nargs, char* args[] ){
             if( !Global::advanceEM ) model.optimize(); else model.mask();
             if( Global::saveBaMMs ) model.write( Global::outputDirectory, motifName, Global::ss );
             std::cout << "optimized q = " << model.getQ() << std::endl;
+            mark( "EM" );
         } else {
             std::cout << "Note: the model is not optimized!\n";
         }
@@ -116,8 +130,10 @@ int main( int nargs, char* args[] ){
             FDR fdr( posSet, negSet, motif, bgModel, Global::cvFold, Global::mops, Global::zoops,
                      Global::savePRs, Global::savePvalues, Global::saveLogOdds );
             fdr.evaluateMotif( Global::EM, Global::CGS, Global::optimizeQ, Global::advanceEM, Global::f );
+            mark( "FDR folds" );
             fdr.write( Global::outputDirectory, Global::outputFileBasename + "_motif_" + std::to_string( n + 1 ) );
             delete motif;
+            mark( "FDR statistics + files" );
         }
     }
 
