@@ -166,9 +166,9 @@ void EM::write( char* odir, std::string basename, bool ss ){
         for( size_t k = 0; k <= K_; k++ ){
             const float* nk = n_.data() + motif_->offsetOfOrder( k );
             for( size_t y = 0; y < Y_[k + 1]; y++ ) ofile_n << static_cast<int>( nk[y * W_ + j] ) << '\t';
-            ofile_n << std::endl;
+            ofile_n << '\n';
         }
-        ofile_n << std::endl;
+        ofile_n << '\n';
     }
 
     fetchR();
@@ -184,7 +184,7 @@ void EM::write( char* odir, std::string basename, bool ss ){
                 ofile_pos << seqs_[n]->getHeader() << '\t' << L << '\t' << ( ( i < L ) ? '+' : '-' ) << '\t'
                           << i + 1 << ".." << i + W_ << '\t';
                 for( size_t b = i; b < i + W_; b++ ) ofile_pos << Alphabet::getBase( codes[b] );
-                ofile_pos << std::endl;
+                ofile_pos << '\n';
             }
         }
     }

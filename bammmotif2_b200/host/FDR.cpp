@@ -196,50 +196,51 @@ void FDR::calculatePvalues(){
 
 void FDR::print(){}
 
-// file formats: reference FDR::write, src/evaluation/FDR.cpp:338-450
+// file formats: reference FDR::write, src/evaluation/FDR.cpp:338-450 (rows end in '\n', not std::endl: the same bytes without a
+// flush per row — the statistics files have one row per scored sequence)
 void FDR::write( char* odir, std::string basename ){
     const std::string opath = std::string( odir ) + '/' + basename;
     if( savePRs_ ){
         if( zoops_ ){
             std::ofstream out( opath + ".zoops.stats" );
             out << "TP" << '\t' << "FP" << '\t' << "FDR" << '\t' << "Recall" << '\t' << "p-value" << '\t'
-                << ( float )negSeqs_.size() / ( float )posSeqs_.size() << '\t' << occ_frac_ << std::endl;
+                << ( float )negSeqs_.size() / ( float )posSeqs_.size() << '\t' << occ_frac_ << '\n';
             for( size_t i = 0; i < ZOOPS_FDR_.size(); i++ ){
                 out << ZOOPS_TP_[i] << '\t' << ZOOPS_FP_[i] << '\t' << ZOOPS_FDR_[i] << '\t' << ZOOPS_Rec_[i] << '\t'
-                    << PN_Pvalue_[i] << '\t' << std::endl;
+                    << PN_Pvalue_[i] << '\t' << '\n';
             }
         }
         if( mops_ ){
             std::ofstream out( opath + ".mops.stats" );
-            out << "TP" << '\t' << "FP" << '\t' << "FDR" << '\t' << "Recall" << '\t' << occ_mult_ << std::endl;
+            out << "TP" << '\t' << "FP" << '\t' << "FDR" << '\t' << "Recall" << '\t' << occ_mult_ << '\n';
             for( size_t i = 0; i < MOPS_FDR_.size(); i++ ){
-                out << MOPS_TP_[i] << '\t' << MOPS_FP_[i] << '\t' << MOPS_FDR_[i] << '\t' << MOPS_Rec_[i] << '\t' << std::endl;
+                out << MOPS_TP_[i] << '\t' << MOPS_FP_[i] << '\t' << MOPS_FDR_[i] << '\t' << MOPS_Rec_[i] << '\t' << '\n';
             }
         }
     }
     if( savePvalues_ ){
         if( zoops_ ){
             std::ofstream out( opath + ".zoops.pvalues" );
-            for( float p : ZOOPS_Pvalue_ ) out << std::setprecision( 3 ) << p << std::endl;
+            for( float p : ZOOPS_Pvalue_ ) out << std::setprecision( 3 ) << p << '\n';
         }
         if( mops_ ){
             std::ofstream out( opath + ".mops.pvalues" );
-            for( float p : MOPS_Pvalue_ ) out << std::setprecision( 3 ) << p << std::endl;
+            for( float p : MOPS_Pvalue_ ) out << std::setprecision( 3 ) << p << '\n';
         }
     }
     if( saveLogOdds_ ){
         if( zoops_ ){
             std::ofstream out( opath + ".zoops.logOdds" );
-            out << "positive" << '\t' << "negative" << std::endl;
+            out << "positive" << '\t' << "negative" << '\n';
             for( size_t i = 0; i < posScoreMax_.size(); i++ ){
-                out << std::setprecision( 6 ) << posScoreMax_[i] << '\t' << at( negScoreMax_, i * negSeqs_.size() / posSeqs_.size() ) << std::endl;
+                out << std::setprecision( 6 ) << posScoreMax_[i] << '\t' << at( negScoreMax_, i * negSeqs_.size() / posSeqs_.size() ) << '\n';
             }
         }
         if( mops_ ){
             std::ofstream out( opath + ".mops.logOdds" );
-            out << "positive" << '\t' << "negative" << std::endl;
+            out << "positive" << '\t' << "negative" << '\n';
             for( size_t i = 0; i < posScoreAll_.size(); i++ ){
-                out << std::setprecision( 6 ) << posScoreAll_[i] << '\t' << at( negScoreAll_, i * negSeqs_.size() / posSeqs_.size() ) << std::endl;
+                out << std::setprecision( 6 ) << posScoreAll_[i] << '\t' << at( negScoreAll_, i * negSeqs_.size() / posSeqs_.size() ) << '\n';
             }
         }
     }
@@ -247,5 +248,5 @@ void FDR::write( char* odir, std::string basename ){
 
 void FDR::saveUnsortedLogOdds( std::string opath, std::vector<float> logOdds ){
     std::ofstream ofile( opath );
-    for( size_t i = 0; i < logOdds.size(); i++ ) ofile << i + 1 << '\t' << std::setprecision( 6 ) << logOdds[i] << std::endl;
+    for( size_t i = 0; i < logOdds.size(); i++ ) ofile << i + 1 << '\t' << std::setprecision( 6 ) << logOdds[i] << '\n';
 }

@@ -101,7 +101,7 @@ void ScoreSeqSet::write( char* odir, std::string basename, float pvalCutoff, boo
                 ofile << seqSet_[n]->getHeader() << '\t' << seqlen << '\t' << ( ( i < seqlen ) ? '+' : '-' ) << '\t'
                       << i + 1 << ".." << end << '\t';
                 for( size_t m = i; m < end; m++ ) ofile << Alphabet::getBase( codes[m] );
-                ofile << '\t' << std::setprecision( 3 ) << mops_p_values_[n][i] << '\t' << mops_e_values_[n][i] << std::endl;
+                ofile << '\t' << std::setprecision( 3 ) << mops_p_values_[n][i] << '\t' << mops_e_values_[n][i] << '\n';
             }
         }
     }
@@ -120,6 +120,6 @@ void ScoreSeqSet::writeLogOdds( char* odir, std::string basename, bool ss ){
         ofile << seqSet_[n]->getHeader() << '\t' << seqlen << '\t' << ( ( z_[n] < seqlen ) ? '+' : '-' ) << '\t'
               << z_[n] + 1 << ".." << end << '\t';
         for( size_t m = z_[n]; m < end; m++ ) ofile << Alphabet::getBase( codes[m] );
-        ofile << '\t' << std::setprecision( 3 ) << zoops_scores_[n] << std::endl;
+        ofile << '\t' << std::setprecision( 3 ) << zoops_scores_[n] << '\n';
     }
 }

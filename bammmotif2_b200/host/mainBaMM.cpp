@@ -17,6 +17,8 @@ int main( int nargs, char* args[] ){
     // BAMM_TRACE: wall time of every stage of the driver on stderr (the library prints its own phases with the same switch)
     const bool trace = getenv( "BAMM_TRACE" ) != NULL;
     auto t_mark = t0_wall;
+    auto epoch = [](){ return std::chrono::duration<double>( std::chrono::system_clock::now().time_since_epoch() ).count(); };
+    if( trace ) std::cerr << "[bamm host] main entered at " << std::fixed << std::setprecision( 3 ) << epoch() << std::defaultfloat << std::setprecision( 6 ) << std::endl;
     auto mark = [&]( const char* stage ){
         if( !trace ) return;
         const auto t = std::chrono::high_resolution_clock::now();
@@ -146,5 +148,7 @@ int main( int nargs, char* args[] ){
     negSequences.reset();
     delete bgModel;
     Global::destruct();
+    mark( "host teardown" );
+    if( trace ) std::cerr << "[bamm host] main left at " << std::fixed << std::setprecision( 3 ) << epoch() << std::endl;
     return 0;
 }

@@ -13,7 +13,7 @@ mkdir -p $D/ours
 t0=$(date +%s.%N)
 BAMM_TRACE=1 bammmotif2_b200/bin/BaMMmotif $D/ours $D/in.fasta --bindingSiteFile $D/sites.block --EM -k 2 -K 2 --FDR -m 10 -n 5 > $D/ours.log 2> gpurun_out/${TAG}.err
 t1=$(date +%s.%N)
-echo "wall $(python -c "print('%.2f' % ($t1-$t0))") s" | tee gpurun_out/${TAG}.txt
+echo "wall $(python -c "print('%.2f' % ($t1-$t0))") s; launched at $t0, reaped at $t1" | tee gpurun_out/${TAG}.txt
 grep "bamm host" gpurun_out/${TAG}.err | tee -a gpurun_out/${TAG}.txt
 grep -c "bamm trace" gpurun_out/${TAG}.err
 tail -2 $D/ours.log
