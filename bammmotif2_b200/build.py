@@ -55,7 +55,7 @@ def build_lib(force=False, verbose=False):
 HOST_SOURCES = ["Alphabet", "SequenceSet", "BackgroundModel", "Motif", "MotifSet", "EM", "ScoreSeqSet", "SeqGenerator", "FDR", "Global"]
 # -ffp-contract=off: the host arithmetic (background model, site initialisation, p-values) follows the reference's
 # operation order in plain IEEE fp32, without fused multiply-adds
-HOST_FLAGS = ["-std=c++17", "-O2", "-Wall", "-ffp-contract=off"]
+HOST_FLAGS = ["-std=c++17", "-O2", "-Wall", "-ffp-contract=off", "-pthread"]
 
 
 def build_host(force=False):
@@ -78,7 +78,7 @@ def build_host(force=False):
         deps = [objs[n] for n in HOST_SOURCES] + [objs[main]]
         if force or not _newer(out, deps + [LIB]):
             subprocess.check_call([gxx, "-o", out, objs[main]] + [objs[n] for n in HOST_SOURCES] +
-                                  ["-L" + HERE, "-lbamm_b200", "-Wl,-rpath,$ORIGIN/.."], env=env)
+                                  ["-L" + HERE, "-lbamm_b200", "-Wl,-rpath,$ORIGIN/..", "-pthread"], env=env)
         outs.append(out)
     return outs
 

@@ -5,6 +5,7 @@
 #include <iomanip>
 #include <iostream>
 #include <memory>
+#include <thread>
 
 #include "EM.h"
 #include "FDR.h"
@@ -32,7 +33,11 @@ int main( int nargs, char* args[] ){
               << "======================================" << std::endl;
 
     srand( 42 );                                    // reference: mainBaMM.cpp:22
+    // the first CUDA call creates the device context (0.8 s and more on a multi-GPU box): it runs beside option parsing and
+    // the FASTA reader; a failure is not reported here — the first real device call of the main thread reports it
+    std::thread warm( [](){ const char* dev = getenv( "BAMM_DEVICE" ); bamm_set_device( dev ? atoi( dev ) : 0 ); } );
     Global::init( nargs, args );
+    warm.join();
     if( Global::CGS ){
         std::cerr << "Error: collapsed Gibbs sampling (--CGS) is not part of the B200 path; use --EM." << std::endl;
         return 1;
