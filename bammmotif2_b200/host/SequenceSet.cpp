@@ -262,15 +262,9 @@ bool SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singl
         pos = end + 1;
     }
     flush();
-    // stored lengths, as the host reader reports them
-    size_t maxStored = 0, minStored = std::numeric_limits<size_t>::max();
-    for( uint32_t l : recL0 ){
-        const size_t L = singleStrand ? l : 2 * static_cast<size_t>( l ) + 1;
-        maxStored = std::max( maxStored, L ); minStored = std::min( minStored, L );
-    }
+    // lengths of the records as read (one strand), as the host reader reports them
     maxL_ = recL0.empty() ? 0 : maxL;
     minL_ = recL0.empty() ? std::numeric_limits<size_t>::max() : minL;
-    ( void )maxStored; ( void )minStored;
 
     const size_t A = Alphabet::getSize();
     uint8_t lut[256], comp[256];
