@@ -80,7 +80,8 @@ def measured_traffic(workload, nseq, mstep_dominant):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock / throttle reasons while the timed region runs: NVML polled every 2 ms on a thread (plus one sample when the
+    region starts and one when it ends, so that even a 4 ms region has two); nvidia-smi every 200 ms where NVML is missing."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -90,7 +91,44 @@ class ClockSampler:
         self.proc = None
         self.lines = []
 
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
+    def _nvml_sample(self):
+        n = self.nvml
+        self.nv_sm.append(float(n.nvmlDeviceGetClockInfo(self.nv_h, n.NVML_CLOCK_SM)))
+        bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.nv_h))
+        for bit, name in self.NVML_REASONS:
+            if bits & bit:
+                self.nv_reasons.add(name)
+
+    def _nvml_loop(self):
+        while not self.nv_stop.is_set():
+            try:
+                self._nvml_sample()
+            except Exception:
+                return
+            self.nv_stop.wait(0.002)
+
+    def _start_nvml(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.nv_h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.nv_h, pynvml.NVML_CLOCK_SM))
+            self.nv_sm, self.nv_reasons, self.nv_stop = [], set(), threading.Event()
+            self._nvml_sample()
+            self.nv_t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.nv_t.start()
+            return True
+        except Exception:
+            self.nvml = None
+            return False
+
     def start(self):
+        self.nvml = None
+        if self._start_nvml():
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -105,6 +143,16 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.nv_stop.set()
+            self.nv_t.join(timeout=1)
+            try:
+                self._nvml_sample()
+            except Exception:
+                pass
+            sm = sorted(self.nv_sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.nv_max, "samples": len(sm),
+                    "reasons": sorted(self.nv_reasons), "source": "nvml, 2 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
