@@ -1,6 +1,6 @@
 """Builds the in-tree native artefacts of bammmotif2_b200 with nvcc / g++ (no torch, no JIT cache):
 
-    libbamm_b200.so   the C-ABI library (include/bamm_b200.h): csrc/capi.cu + csrc/*.cuh, sm_100a only
+    libbamm_b200.so   the C-ABI library (include/bamm_b200.h): csrc/capi.cu (+ capi_*.inl, one translation unit) + csrc/*.cuh, sm_100a only
     bin/BaMMmotif     the C++ host side (host/*.cpp: the reference's class surface over the C ABI) as the drop-in CLI
     bin/host_check    test helper for the CPU-only parts of the host classes
 
@@ -41,8 +41,9 @@ def _newer(target, deps):
 
 def build_lib(force=False, verbose=False):
     srcs = [os.path.join(HERE, "csrc", "capi.cu")]
-    deps = srcs + [os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "packed.cuh"),
-                   os.path.join(ROOT, "include", "bamm_b200.h"), __file__]
+    cdir = os.path.join(HERE, "csrc")
+    deps = srcs + [os.path.join(cdir, f) for f in sorted(os.listdir(cdir)) if f.endswith((".cuh", ".inl"))] + \
+           [os.path.join(ROOT, "include", "bamm_b200.h"), __file__]
     if not force and _newer(LIB, deps):
         return LIB
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs

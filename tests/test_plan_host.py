@@ -1,4 +1,4 @@
-"""Host logic of the packed E-step, no GPU: the column-group planner (capi.cu make_group_plan / plan_passes) through
+"""Host logic of the packed E-step, no GPU: the column-group planner (csrc/capi_em.inl make_group_plan / plan_passes) through
 bamm_plan_describe. The plan replaces the per-position products of EM::EStep (reference src/refinement/EM.cpp:149-196) by
 one table lookup per column group; here its invariants are checked for every width / order / budget, and the bit-field
 extraction the kernels do with (kd, shift, shift2, mask4) is replayed in integers against the definition of a group's
