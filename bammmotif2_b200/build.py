@@ -39,17 +39,36 @@ def _newer(target, deps):
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
+# translation units of the library: capi.cu carries the C ABI and the small kernels, each launch_*.cu one family of heavily
+# templated kernels (csrc/launch.h); every unit depends on every header (cheap to state, the units build in parallel)
+LIB_UNITS = ["capi", "launch_estep", "launch_mstep", "launch_score"]
+
+
 def build_lib(force=False, verbose=False):
-    srcs = [os.path.join(HERE, "csrc", "capi.cu")]
+    from concurrent.futures import ThreadPoolExecutor
     cdir = os.path.join(HERE, "csrc")
-    deps = srcs + [os.path.join(cdir, f) for f in sorted(os.listdir(cdir)) if f.endswith((".cuh", ".inl"))] + \
-           [os.path.join(ROOT, "include", "bamm_b200.h"), __file__]
-    if not force and _newer(LIB, deps):
-        return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    odir = os.path.join(HERE, "build", "lib")
+    os.makedirs(odir, exist_ok=True)
+    headers = [os.path.join(cdir, f) for f in sorted(os.listdir(cdir)) if f.endswith((".cuh", ".inl", ".h"))] + \
+              [os.path.join(ROOT, "include", "bamm_b200.h"), __file__]
     env = dict(os.environ)
     env.pop("CXX", None); env.pop("CC", None)          # the image exports a gcc wrapper without libgomp specs
-    subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd, env=env)
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs = []
+    objs = []
+    for u in LIB_UNITS:
+        src, obj = os.path.join(cdir, u + ".cu"), os.path.join(odir, u + ".o")
+        objs.append(obj)
+        if force or not _newer(obj, [src] + headers):
+            jobs.append([nvcc_path()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj] + ccbin)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            for rc in ex.map(lambda cmd: subprocess.call(cmd, env=env), jobs):
+                if rc:
+                    raise RuntimeError("nvcc failed")
+    if jobs or not _newer(LIB, objs):
+        subprocess.check_call([nvcc_path(), "-shared", "-o", LIB] + objs + ccbin, env=env)
     return LIB
 
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "bamm_em_loop_timing": (C.c_int, [_vp, C.POINTER(C.c_int), _f32p, _f32p, _f32p, _f32p]),
     "bamm_em_set_exchange_buffer": (C.c_int, [_vp, _vp, C.c_uint64]),
     "bamm_em_launch_count": (C.c_int, [_vp, _u64p]),
+    "bamm_em_estep_info": (C.c_int, [_vp, _u64p]),
     "bamm_em_destroy": (None, [_vp]),
     "bamm_em_exchange_buffer": (C.c_int, [_vp, C.POINTER(_vp), _u64p]),
     "bamm_em_set_global_nseq": (C.c_int, [_vp, C.c_uint64]),
@@ -380,6 +381,13 @@ class EM:
         n = C.c_uint64(0)
         _check(load().bamm_em_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def estep_info(self):
+        """How the last E-step ran (bamm_em_estep_info): dict(pruned, G, G_bound, dense_ran, candidates, active, passes, plain_smem)."""
+        a = (C.c_uint64 * 8)()
+        _check(load().bamm_em_estep_info(self.h, a))
+        return dict(pruned=bool(a[0]), G=int(a[1]), G_bound=int(a[2]), dense_ran=bool(a[3]), candidates=int(a[4]), active=int(a[5]),
+                    passes=int(a[6]), plain_smem=bool(a[7]))
 
     def set_exchange_buffer(self, dev_ptr, words):
         _check(load().bamm_em_set_exchange_buffer(self.h, _vp(dev_ptr), words))

@@ -3,6 +3,7 @@
 #include "../../include/bamm_b200.h"
 #include "kernels.cuh"
 #include "packed.cuh"
+#include "launch.h"
 #include "negatives.cuh"
 #include "stats.cuh"
 #include <cub/device/device_scan.cuh>
@@ -176,7 +177,23 @@ struct bamm_em {
     std::vector<char> gfast;         // per pass: every group's bit field sits below bit 32 of the window word
     size_t tab_capacity = 0;    // bytes available for the group tables (= opt-in shared memory)
     float* d_tab = nullptr;     // group tables, concatenated; tab_capacity bytes per pass
+    float* d_tab_alt = nullptr; // second buffer: launch_update writes the next tables there and swaps, so the tables of the last
+                                // E-step stay available (bamm_em_get_r materialises r from them, bamm_em_get_s returns them)
     size_t tab_passes = 0;      // passes d_tab has room for
+    uint32_t plain_words = 0;   // > 0: the plain [j][y] table rides in shared memory behind the group tables (single columns of masked windows)
+    // pruned E-step (estep.cuh): bound plan + tables, candidate list, device-side flags
+    bool cand_ok = false;       // candidate list allocated (bamm_em_create)
+    bool sparse = false;        // the current plans use the pruned path (bamm_em_set_model)
+    bool stage = false;         // the exact pass stages the sequence words in shared memory
+    GroupPlan bplan; bool bfast = false;
+    BoundLevels blev;
+    float* d_btab = nullptr;    // bound tables
+    float* d_U = nullptr;       // maxima of s over dropped context bases, per level
+    uint32_t* d_cand = nullptr; uint2* d_cand_seq = nullptr; uint64_t* d_creg_off = nullptr;
+    uint32_t* d_eflags = nullptr;   // CandList::flags (4 words)
+    bool r_mat = true;          // d_r holds the posteriors of the last E-step (false after a pruned E-step until bamm_em_get_r)
+    const float *d_s_e = nullptr, *d_sT_e = nullptr, *d_tab_e = nullptr;   // the tables the last E-step read
+    float q_e = 0.3f;           // ... and its prior
     // active list (windows that survive the M-step's fixed-point rounding), one region per E-step warp
     uint32_t nregions = 0;
     ActiveEntry* d_act = nullptr;
@@ -206,6 +223,7 @@ struct bamm_em {
     float* d_r = nullptr;
     float* d_s = nullptr;         // [j][y]
     float* d_sT = nullptr;        // the same table in the reference's [y][j] order (row gathers of the patched k-mers)
+    float *d_s_alt = nullptr, *d_sT_alt = nullptr;   // second buffers, see d_tab_alt
     float* d_v = nullptr;         // all orders
     float* d_vK_prev = nullptr;
     float* d_n = nullptr;         // all orders (float, reference layout)

@@ -21,7 +21,9 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     for (int p = 0; p < MAX_PEERS; p++) if (em->peer_mapped[p]) cudaIpcCloseMemHandle(em->peer_mapped[p]);
     cudaFree(em->d_peer_local); cudaFree(em->d_peer_done);
     cudaFree(em->d_act); cudaFree(em->d_scale); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
-    cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab);
+    cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab); cudaFree(em->d_tab_alt);
+    cudaFree(em->d_btab); cudaFree(em->d_U); cudaFree(em->d_cand); cudaFree(em->d_cand_seq); cudaFree(em->d_creg_off); cudaFree(em->d_eflags);
+    cudaFree(em->d_s_alt); cudaFree(em->d_sT_alt);
     cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_sT); cudaFree(em->d_v);
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
     if (em->own_xbuf) cudaFree(em->d_xbuf);
@@ -34,7 +36,6 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     delete em;
 }
 
-static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, size_t pass, bool optin_only);
 static int mstep_w_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, int mode);
 
 template <typename K> static int max_smem_optin(K kernel, size_t bytes) {
@@ -136,6 +137,64 @@ static bool plan_passes(int W, int K, int K_bg, bool reduced, size_t budget, std
     for (size_t i = 0; i + 1 < cuts.size(); i++) {
         make_group_plan(W, K, K_bg, reduced, budget, cuts[i], cuts[i + 1], gp, f);
         plans.push_back(gp); fast.push_back((char)f);
+    }
+    return true;
+}
+
+// ---- bound plan of the pruned E-step (estep.cuh) -------------------------------------------------------------------
+// The fewest groups of at most 7 bases (64 KB tables) / 6 bases (16 KB) whose base ranges cover columns 0..W-1 within `budget`;
+// spare bases go to the left of the first group (the background context of column 0) and then into overlaps between
+// neighbouring groups, so that fewer leading columns of a group lose context. Group g owns the columns right of group g-1's
+// last base. Returns false when W columns cannot be covered.
+static bool make_bound_plan(int W, int K, int K_bg, size_t budget, GroupPlan& gp, bool& fast) {
+    int best_n7 = -1, best_n6 = -1;
+    for (int G = 1; G <= 8 && best_n7 < 0; G++)
+        for (int n7 = std::min(G, 3); n7 >= 0; n7--) {           // more 7-base groups first: more spare bases
+            const int n6 = G - n7;
+            if ((size_t)n7 * 65536 + (size_t)n6 * 16384 > budget) continue;
+            if (7 * n7 + 6 * n6 < W) continue;
+            best_n7 = n7; best_n6 = n6; break;
+        }
+    if (best_n7 < 0) return false;
+    const int G = best_n7 + best_n6;
+    memset(&gp, 0, sizeof(gp));
+    gp.W = W; gp.K = K; gp.G = G; gp.Yn = 1u << (2 * (K + 1));
+    int spare = 7 * best_n7 + 6 * best_n6 - W;
+    const int ctx0 = std::min(K_bg, K);
+    int lo = -std::min(spare, ctx0);
+    spare += lo;
+    uint32_t base = 0;
+    int prev_hi = -1;
+    for (int g = 0; g < G; g++) {
+        int T = g < best_n7 ? 7 : 6;
+        if (g > 0) { const int ov = std::min(spare, K); lo = prev_hi + 1 - ov; spare -= ov; }
+        int hi = lo + T - 1;
+        if (hi > W - 1) { hi = W - 1; T = hi - lo + 1; }
+        if (hi <= prev_hi) return false;
+        gp.col0[g] = prev_hi + 1; gp.ncol[g] = hi - prev_hi; gp.lo[g] = lo;
+        gp.base[g] = base;
+        gp.mask4[g] = (uint32_t)(((1ull << (2 * T)) - 1ull) << 2);
+        gp.colmask[g] = (uint32_t)(((hi >= 31 ? 0xffffffffull : ((2ull << hi) - 1ull))) & ~((1ull << gp.col0[g]) - 1ull));
+        base += 4u << (2 * T);
+        prev_hi = hi;
+    }
+    if (prev_hi != W - 1) return false;
+    gp.table_bytes = base;
+    gp.passmask = (uint32_t)((W >= 32 ? 0x100000000ull : (1ull << W)) - 1ull);
+    gp.pass_first = 1; gp.pass_last = 1;
+    // alignment of the window word, as in make_group_plan: kd >= -lo[0] (oldest base read), kd <= 31-W, one-shift extraction
+    // needs kd >= 15 - hi[0]
+    const int hi0 = gp.col0[0] + gp.ncol[0] - 1;
+    const int kd_min = -gp.lo[0], kd_max = 31 - W;
+    if (kd_min > kd_max) return false;
+    const int kd_fast = std::max(kd_min, 15 - hi0);
+    fast = kd_fast <= kd_max;
+    gp.kd = fast ? kd_fast : kd_min;
+    for (int g = 0; g < G; g++) {
+        const int hi = gp.col0[g] + gp.ncol[g] - 1;
+        const int sh = 60 - 2 * (hi + gp.kd);
+        gp.shift[g] = (uint32_t)sh;
+        gp.shift2[g] = sh > 32 ? (uint32_t)(sh - 32) : 0u;
     }
     return true;
 }
@@ -271,6 +330,8 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     tr.mark("r alloc + memset");
     CUE(dev_malloc(&em->d_s, (uint64_t)em->nbin * sizeof(float)));
     CUE(dev_malloc(&em->d_sT, (uint64_t)em->nbin * sizeof(float)));
+    CUE(dev_malloc(&em->d_s_alt, (uint64_t)em->nbin * sizeof(float)));
+    CUE(dev_malloc(&em->d_sT_alt, (uint64_t)em->nbin * sizeof(float)));
     CUE(dev_malloc(&em->d_v, em->model_size * sizeof(float)));
     CUE(dev_malloc(&em->d_vK_prev, (uint64_t)em->nbin * sizeof(float)));
     CUE(dev_malloc(&em->d_n, em->model_size * sizeof(float)));
@@ -337,19 +398,21 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         tr.mark("M-step geometry + opt-in");
         // active list: one region per E-step warp, sized as a fraction of the warp's windows (BAMM_LIST_FRAC, 0 = off)
         double frac = getenv("BAMM_LIST_FRAC") ? atof(getenv("BAMM_LIST_FRAC")) : 0.5;
-        std::vector<uint64_t> reg;
+        if (s->nwords >= (1ull << 32)) frac = 0.0;          // list entries address the stream with 32-bit word offsets
+        std::vector<uint64_t> reg, win, nsq;
         if (frac > 0.0) {
             em->nregions = (uint32_t)em->grid_pe * (uint32_t)(em->block_pe / 32);
-            std::vector<uint64_t> win(em->nregions, 0);
+            win.assign(em->nregions, 0); nsq.assign(em->nregions, 0);
             reg.assign((size_t)em->nregions + 1, 0);
             if (em->whole_set && s->minL == s->maxL) {          // equal lengths: sequence i goes to warp i % nregions
                 const uint64_t lw1 = s->maxL - (uint64_t)W + 1, per = em->npk / em->nregions, extra = em->npk % em->nregions;
-                for (uint32_t w = 0; w < em->nregions; w++) win[w] = (per + (w < extra ? 1 : 0)) * lw1;
+                for (uint32_t w = 0; w < em->nregions; w++) { nsq[w] = per + (w < extra ? 1 : 0); win[w] = nsq[w] * lw1; }
             } else {
                 uint32_t w = 0;
                 for (size_t i = 0; i < em->npk; i++) {
                     const uint64_t n = em->whole_set ? i : pk_ids[i];
                     win[w] += s->h_off[n + 1] - s->h_off[n] - (uint64_t)W + 1;
+                    nsq[w]++;
                     if (++w == em->nregions) w = 0;
                 }
             }
@@ -377,6 +440,28 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             CUE(cudaMemset(em->d_act_cnt, 0, (uint64_t)em->nregions * 8));
             CUE(dev_malloc(&em->d_overflow, 4));
             CUE(cudaMemset(em->d_overflow, 0, 4));
+            // candidate list of the pruned E-step: one region per warp for a fraction of its windows (BAMM_CAND_FRAC). The exact
+            // pass lists at most the candidates plus the windows over the N and the truncated tail of every sequence, so a
+            // region of the active list that holds all of those cannot overflow there.
+            const double cfrac = getenv("BAMM_CAND_FRAC") ? atof(getenv("BAMM_CAND_FRAC")) : 0.30;
+            if (cfrac > 0.0 && !getenv("BAMM_NO_SPARSE")) {
+                std::vector<uint64_t> creg((size_t)em->nregions + 1, 0);
+                bool ok = true;
+                for (uint32_t w = 0; w < em->nregions && ok; w++) {
+                    const uint64_t masked = nsq[w] * (uint64_t)(2 * W + K + 2), rcap = reg[w + 1] - reg[w];
+                    uint64_t cap = (uint64_t)(cfrac * (double)win[w]) + 256;
+                    if (cap > win[w]) cap = win[w];
+                    if (cap + masked > rcap) { if (rcap <= masked && win[w]) ok = false; else cap = rcap > masked ? rcap - masked : 0; }
+                    creg[w + 1] = creg[w] + cap;
+                }
+                if (ok && dev_malloc(&em->d_cand, (creg[em->nregions] ? creg[em->nregions] : 1) * sizeof(uint32_t)) == cudaSuccess) {
+                    CUE(dev_malloc(&em->d_cand_seq, (size_t)em->npk * sizeof(uint2)));
+                    CUE(upload(creg.data(), creg.size() * 8, (void**)&em->d_creg_off));
+                    CUE(dev_malloc(&em->d_eflags, 16));
+                    CUE(cudaMemset(em->d_eflags, 0, 16));
+                    em->cand_ok = true;
+                } else cudaGetLastError();
+            }
         }
     }
     tr.mark("active list");
@@ -395,13 +480,22 @@ static void host_lists(bamm_em* em) {
     em->h_r_off.assign(em->ss->h_off.begin(), em->ss->h_off.begin() + em->nsub + 1);
 }
 
-static int launch_tuple_table(bamm_em* em) {
+// group tables of the exact plan(s) from the [j][y] table `d_s` into `d_tab_dst`; bound tables of the pruned path
+static int launch_tables(bamm_em* em, const float* d_s, float* d_tab_dst) {
     if (!em->npk) return BAMM_OK;
     for (size_t i = 0; i < em->gplans.size(); i++) {
         const uint32_t total = em->gplans[i].table_bytes >> 2;
         const uint32_t blocks = (total + 255) / 256;
-        k_make_group_tables<false><<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(em->d_s, em->gplans[i], (float*)((char*)em->d_tab + i * em->tab_capacity));
+        k_make_group_tables<false><<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(d_s, em->gplans[i], (float*)((char*)d_tab_dst + i * em->tab_capacity));
         CU(cudaGetLastError());
+    }
+    if (em->sparse) {
+        k_bound_levels<<<1, 1024, 0, em->stream>>>(d_s, em->W, em->K, em->blev, em->d_U);
+        CU(cudaGetLastError());
+        const uint32_t total = em->bplan.table_bytes >> 2, blocks = (total + 255) / 256;
+        k_make_bound_tables<<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(d_s, em->d_U, em->blev, em->bplan, em->d_btab);
+        CU(cudaGetLastError());
+        em->launches += 2;
     }
     return BAMM_OK;
 }
@@ -426,14 +520,48 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
         const bool reduced = leading_columns_are_copies(em->dims, em->K, em->W, em->Yn, v_all) && !getenv("BAMM_NO_REDUCED");
         if (!plan_passes(em->W, em->K, em->K_bg, reduced, em->tab_capacity, em->gplans, em->gfast))
             return fail(BAMM_E_STATE, "no column-group plan fits shared memory");
+        // a single-pass plan that leaves room for the plain [j][y] table behind the group tables (the single columns of masked
+        // windows then come from shared memory) is preferred when it costs at most one more group
+        em->plain_words = 0;
+        const size_t plain_bytes = ((size_t)em->nbin + (size_t)em->W) * sizeof(float);      // rows padded by one float in shared memory
+        if (em->gplans.size() == 1 && plain_bytes + 4096 <= em->tab_capacity && !getenv("BAMM_NO_PLAIN_SMEM")) {
+            std::vector<GroupPlan> pp; std::vector<char> pf;
+            if (plan_passes(em->W, em->K, em->K_bg, reduced, em->tab_capacity - plain_bytes, pp, pf) && pp.size() == 1 && pp[0].G <= em->gplans[0].G + 1) {
+                em->gplans.swap(pp); em->gfast.swap(pf); em->plain_words = em->nbin;
+            }
+        }
+        // pruned path: worth it when the bound needs at least three lookups fewer than the exact product (BAMM_SPARSE=1: whenever fewer)
+        em->sparse = false;
+        if (em->cand_ok && em->gplans.size() == 1 && !getenv("BAMM_NO_SPARSE") && em->K >= 1 &&
+            make_bound_plan(em->W, em->K, em->K_bg, em->tab_capacity, em->bplan, em->bfast)) {
+            const int need = getenv("BAMM_SPARSE") && atoi(getenv("BAMM_SPARSE")) > 0 ? 1 : 3;
+            em->sparse = em->bplan.G + need <= em->gplans[0].G;
+        }
         if (em->gplans.size() > em->tab_passes) {
             CU(cudaStreamSynchronize(em->stream));
-            cudaFree(em->d_tab); em->d_tab = nullptr; em->tab_passes = 0;
+            cudaFree(em->d_tab); cudaFree(em->d_tab_alt); em->d_tab = em->d_tab_alt = nullptr; em->tab_passes = 0;
             CU(dev_malloc(&em->d_tab, em->gplans.size() * em->tab_capacity));
+            CU(dev_malloc(&em->d_tab_alt, em->gplans.size() * em->tab_capacity));
             em->tab_passes = em->gplans.size();
         }
+        const EStepLaunch l = {em->grid_pe, em->block_pe, em->stream};
         for (size_t i = 0; i < em->gplans.size(); i++)
-            if (estep_packed_dispatch(em, nullptr, i, true)) return fail(BAMM_E_CUDA, "cannot opt in to %u bytes of shared memory", em->gplans[i].table_bytes);
+            if (launch_estep_dense(l, true, em->gfast[i] != 0, em->gplans.size() > 1, nullptr, em->gplans[i], nullptr, nullptr, nullptr, em->plain_words, nullptr, nullptr, nullptr, nullptr))
+                return fail(BAMM_E_CUDA, "cannot opt in to %u bytes of shared memory", em->gplans[i].table_bytes);
+        if (em->sparse) {
+            if (!em->d_btab) {
+                CU(dev_malloc(&em->d_btab, em->tab_capacity));
+                uint32_t off = 0;
+                memset(&em->blev, 0, sizeof(em->blev));
+                for (int a = 1; a <= em->K && a < 12; a++) { em->blev.off[a] = off; off += (uint32_t)em->W << (2 * a); }
+                CU(dev_malloc(&em->d_U, (size_t)(off ? off : 1) * sizeof(float)));
+            }
+            // per-warp staging of the sequence words in the exact pass, when shared memory has room left
+            em->stage = (size_t)em->gplans[0].table_bytes + (em->plain_words ? plain_bytes : 0) + estep_stage_bytes(em->block_pe) <= em->tab_capacity && !getenv("BAMM_NO_STAGE");
+            if (launch_estep_bound(l, true, em->bfast, nullptr, em->bplan, nullptr, nullptr) ||
+                launch_estep_exact(l, true, em->gfast[0] != 0, nullptr, em->gplans[0], nullptr, nullptr, nullptr, em->plain_words, em->stage, nullptr, nullptr, nullptr))
+                return fail(BAMM_E_CUDA, "cannot opt in to shared memory for the pruned E-step");
+        }
     }
     tr.mark("plan + table buffer + opt-in");
     CU(cudaMemcpyAsync(em->d_v, v_all, em->model_size * sizeof(float), cudaMemcpyHostToDevice, em->stream));
@@ -441,41 +569,27 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
     CU(cudaMemcpyAsync(em->d_alpha, alpha, (uint64_t)(em->K + 1) * em->W * sizeof(float), cudaMemcpyHostToDevice, em->stream));
     k_make_s<<<64, 256, 0, em->stream>>>(em->dims, em->d_v, em->d_vbg, em->d_s, em->d_sT, em->d_vK_prev);
     CU(cudaGetLastError());
-    { int rc = launch_tuple_table(em); if (rc) return rc; }
+    { int rc = launch_tables(em, em->d_s, em->d_tab); if (rc) return rc; }
     CU(cudaStreamSynchronize(em->stream));
     tr.mark("uploads + s + group tables");
     em->q = q; em->model_set = true; em->s_valid = true; em->r_valid = false; em->llh = 0.0f;
     return BAMM_OK;
 }
 
-// k_estep_packed is instantiated for every group count the planner can choose, in both extraction modes;
-// optin_only sets the shared-memory attribute instead of launching.
 static ActiveList alist_of(const bamm_em* em) {
     ActiveList al; al.ent = em->d_act; al.scale = em->d_scale; al.reg_off = em->d_reg_off;
     al.cnt = em->d_act_cnt; al.cnt_back = em->d_act_cnt ? em->d_act_cnt + em->nregions : nullptr; al.overflow = em->d_overflow;
     return al;
 }
-template <int G, bool FAST, bool MULTI> static int estep_packed_one(bamm_em* em, const PackedView* pv, size_t pass, bool optin_only) {
-    GroupPlan gp = em->gplans[pass]; gp.q = em->q;
-    gp.thr0 = FX_HALF_UNIT * (1.0f - em->q) * 0.999f;
-    if (optin_only) return max_smem_optin(k_estep_packed<G, FAST, MULTI>, gp.table_bytes);
-    k_estep_packed<G, FAST, MULTI><<<em->grid_pe, em->block_pe, gp.table_bytes, em->stream>>>(*pv, gp, (const float*)((const char*)em->d_tab + pass * em->tab_capacity),
-                                                                                       em->d_s, em->d_sT, em->d_r, em->d_xbuf + em->nbin, alist_of(em));
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+static CandList clist_of(const bamm_em* em) {
+    CandList cl; cl.ent = em->d_cand; cl.reg_off = em->d_creg_off; cl.seq = em->d_cand_seq; cl.flags = em->d_eflags;
+    return cl;
 }
-template <int G> static int estep_packed_g(bamm_em* em, const PackedView* pv, size_t pass, bool optin_only) {
-    const bool multi = em->gplans.size() > 1;
-    if (em->gfast[pass]) return multi ? estep_packed_one<G, true, true>(em, pv, pass, optin_only) : estep_packed_one<G, true, false>(em, pv, pass, optin_only);
-    return multi ? estep_packed_one<G, false, true>(em, pv, pass, optin_only) : estep_packed_one<G, false, false>(em, pv, pass, optin_only);
-}
-static int estep_packed_dispatch(bamm_em* em, const PackedView* pv, size_t pass, bool optin_only) {
-    switch (em->gplans[pass].G) {
-#define BAMM_CASE(g) case g: return estep_packed_g<g>(em, pv, pass, optin_only);
-        BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
-        BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
-#undef BAMM_CASE
-        default: return -1;
-    }
+// plan of pass `pass` with the launch-time parameters filled in
+static GroupPlan plan_for_launch(const bamm_em* em, size_t pass, float q) {
+    GroupPlan gp = em->gplans[pass]; gp.q = q;
+    gp.thr0 = FX_HALF_UNIT * (1.0f - q) * 0.999f;
+    return gp;
 }
 
 static SubsetView view_of(const bamm_em* em) {
@@ -489,17 +603,37 @@ static PackedView pview_of(const bamm_em* em) {
 }
 
 static int launch_estep(bamm_em* em) {
-    em->launches += (em->npk ? em->gplans.size() : 0) + (em->ngen ? 1 : 0);
+    em->launches += 1 + (em->npk ? em->gplans.size() + (em->sparse ? 2 : 0) : 0) + (em->ngen ? 1 : 0);
     unsigned long long* scal = em->d_xbuf + em->nbin;
-    CU(cudaMemsetAsync(scal, 0, 2 * sizeof(unsigned long long), em->stream));
+    k_estep_begin<<<1, 32, 0, em->stream>>>(scal, em->d_overflow, em->d_eflags);
+    CU(cudaGetLastError());
     if (em->npk) {
         PackedView pv = pview_of(em);
-        if (em->d_overflow) CU(cudaMemsetAsync(em->d_overflow, 0, 4, em->stream));
-        for (size_t pass = 0; pass < em->gplans.size(); pass++)
-            if (estep_packed_dispatch(em, &pv, pass, false)) return fail(BAMM_E_CUDA, "packed E-step launch failed");
+        const EStepLaunch l = {em->grid_pe, em->block_pe, em->stream};
+        const ActiveList al = alist_of(em);
+        const bool multi = em->gplans.size() > 1;
+        if (em->sparse) {
+            // bounds -> exact evaluation of the candidates; the dense kernel only runs when the candidate list overflowed
+            const CandList cl = clist_of(em);
+            GroupPlan bp = em->bplan; bp.q = em->q;
+            bp.thr0 = FX_HALF_UNIT * (1.0f - em->q) * 0.999f * 0.9999f;          // margin: bound and product round differently
+            const GroupPlan gp = plan_for_launch(em, 0, em->q);
+            if (launch_estep_bound(l, false, em->bfast, &pv, bp, em->d_btab, &cl)) return fail(BAMM_E_CUDA, "E-step launch failed (bounds)");
+            if (launch_estep_exact(l, false, em->gfast[0] != 0, &pv, gp, em->d_tab, em->d_s, em->d_sT, em->plain_words, em->stage, &cl, scal, &al))
+                return fail(BAMM_E_CUDA, "E-step launch failed (candidates)");
+            if (launch_estep_dense(l, false, em->gfast[0] != 0, false, &pv, gp, em->d_tab, em->d_s, em->d_sT, em->plain_words, em->d_r, scal, &al, em->d_eflags))
+                return fail(BAMM_E_CUDA, "packed E-step launch failed");
+        } else {
+            for (size_t pass = 0; pass < em->gplans.size(); pass++)
+                if (launch_estep_dense(l, false, em->gfast[pass] != 0, multi, &pv, plan_for_launch(em, pass, em->q), (const float*)((const char*)em->d_tab + pass * em->tab_capacity),
+                                       em->d_s, em->d_sT, em->plain_words, em->d_r, scal, &al, nullptr))
+                    return fail(BAMM_E_CUDA, "packed E-step launch failed");
+        }
         em->r_scaled = false;
+        em->r_mat = !em->sparse;
         CU(cudaGetLastError());
     }
+    em->d_s_e = em->d_s; em->d_sT_e = em->d_sT; em->d_tab_e = em->d_tab; em->q_e = em->q;
     if (em->ngen) {
         IndexArray& ia = em->ss->index[em->K];
         SubsetView sv = view_of(em);
@@ -515,26 +649,13 @@ static int launch_estep(bamm_em* em) {
     return BAMM_OK;
 }
 
-// packed M-step kernels: one instantiation per column count of a CTA. mode 0: opt in to the shared memory of both kernels,
-// 1: launch the list kernel, 2: launch the scan kernel (conditional on the list's overflow flag when there is a list)
-template <int NC> static int mstep_w_one(bamm_em* em, const PackedView* pv, const Plan* pl, int mode) {
-    const size_t smem = (size_t)2 * em->m_tab.nrep * em->m_tab.rstride * 4;
-    if (mode == 0) return max_smem_optin(k_mstep_list_w<NC>, smem) | max_smem_optin(k_mstep_scan_w<NC>, smem);
-    if (mode == 1) k_mstep_list_w<NC><<<em->grid_pl, 1024, smem, em->stream>>>(*pv, *pl, alist_of(em), em->nregions, em->m_nsplit, em->m_tab, em->d_part);
-    else k_mstep_scan_w<NC><<<em->grid_pl, 1024, smem, em->stream>>>(*pv, *pl, em->d_r, em->r_scaled ? nullptr : em->d_scale,
-                                                                    em->d_act ? em->d_overflow : nullptr, em->m_nsplit, em->m_tab, em->d_part);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
+// packed M-step kernels (launch_mstep.cu). mode 0: opt in to the shared memory of both kernels, 1: launch the list kernel,
+// 2: launch the scan kernel (conditional on the list's overflow flag when there is a list)
 static int mstep_w_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, int mode) {
-    switch (em->m_nc) {
-#define BAMM_CASE(w) case w: return mstep_w_one<w>(em, pv, pl, mode);
-        BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
-        BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
-        BAMM_CASE(17) BAMM_CASE(18) BAMM_CASE(19) BAMM_CASE(20) BAMM_CASE(21) BAMM_CASE(22) BAMM_CASE(23) BAMM_CASE(24)
-        BAMM_CASE(25) BAMM_CASE(26) BAMM_CASE(27) BAMM_CASE(28) BAMM_CASE(29) BAMM_CASE(30) BAMM_CASE(31) BAMM_CASE(32)
-#undef BAMM_CASE
-        default: return -1;
-    }
+    const size_t smem = (size_t)2 * em->m_tab.nrep * em->m_tab.rstride * 4;
+    const ActiveList al = alist_of(em);
+    return launch_mstep_packed(em->m_nc, mode, em->grid_pl, smem, em->stream, pv, pl, &al, em->nregions, em->m_nsplit, em->m_tab, em->d_part,
+                               em->d_r, em->r_scaled ? nullptr : em->d_scale, em->d_act ? em->d_overflow : nullptr);
 }
 
 static int launch_mstep_accumulate(bamm_em* em) {
@@ -551,6 +672,12 @@ static int launch_mstep_accumulate(bamm_em* em) {
             uint64_t tot = 0, mx = 0; for (uint32_t x : c) { tot += x; if (x > mx) mx = x; }
             fprintf(stderr, "[bamm] active list: %llu entries (%.4f of r), max region %llu, overflow %u, G=%d fast=%d delta=%d table %u B\n",
                     (unsigned long long)tot, (double)tot / (double)em->rsize, (unsigned long long)mx, ov, em->gplans[0].G, (int)em->gfast[0], em->gplans[0].kd, em->gplans[0].table_bytes);
+            if (em->sparse) {
+                uint32_t f[4] = {0, 0, 0, 0};
+                cudaMemcpy(f, em->d_eflags, 16, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[bamm] pruned E-step: G1=%d fast=%d, %llu candidates (%.4f of r), dense fall-back %u, hold %u\n", em->bplan.G, (int)em->bfast,
+                        (unsigned long long)f[2] | ((unsigned long long)f[3] << 32), (double)((unsigned long long)f[2] | ((unsigned long long)f[3] << 32)) / (double)em->rsize, f[0], f[1]);
+            }
         }
         // the E-step listed the windows that matter; the scan kernel only does work (device-side decision) if a region
         // overflowed, or when there is no list
@@ -600,14 +727,20 @@ static int launch_mstep_local(bamm_em* em) {
 
 static int launch_update(bamm_em* em) {
     em->launches += 1 + (em->npk ? 1 : 0);
+    // the next E-step's tables go to the second buffers, which then become the current ones: the tables of the last E-step stay
+    // readable (bamm_em_get_r, bamm_em_get_s)
     // large tables: one thread-block cluster of 8 CTAs instead of one CTA
     if ((uint64_t)em->nbin >= 16384 && em->d_vdiff_part && !getenv("BAMM_NO_CLUSTER_UPDATE"))
         k_update_model_cluster<<<UPDATE_CLUSTER, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha,
-                                                                      em->d_s, em->d_sT, em->d_vdiff, em->d_vdiff_part);
+                                                                      em->d_s_alt, em->d_sT_alt, em->d_vdiff, em->d_vdiff_part);
     else
-        k_update_model<<<1, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha, em->d_s, em->d_sT, em->d_vdiff);
+        k_update_model<<<1, 1024, 0, em->stream>>>(em->dims, em->d_xbuf, em->d_n, em->d_v, em->d_vK_prev, em->d_vbg, em->d_alpha, em->d_s_alt, em->d_sT_alt, em->d_vdiff);
     CU(cudaGetLastError());
-    return launch_tuple_table(em);
+    std::swap(em->d_s, em->d_s_alt); std::swap(em->d_sT, em->d_sT_alt);
+    if (!em->npk) return BAMM_OK;
+    const int rc = launch_tables(em, em->d_s, em->d_tab_alt);
+    std::swap(em->d_tab, em->d_tab_alt);
+    return rc;
 }
 
 static int read_scalars(bamm_em* em, bool want_vdiff) {
@@ -815,7 +948,7 @@ static int mask_run(bamm_em* em, const YT* Y, float f, float epsilon, int max_it
             if (llh_diff < 0 && it > 10) iterate = false;
         }
         if (iterations) *iterations = it;
-        em->r_valid = true; em->r_scaled = true;
+        em->r_valid = true; em->r_scaled = true; em->r_mat = true;
     }
 done:
 #undef CUX
@@ -929,7 +1062,8 @@ extern "C" int bamm_em_get_s(bamm_em* em, float* s) {
     REQUIRE(em && s, "NULL argument");
     CU(cudaSetDevice(em->device));
     std::vector<float> t(em->nbin);
-    CU(cudaMemcpyAsync(t.data(), em->d_s, (uint64_t)em->nbin * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
+    // the table the last E-step read (what Motif::getS() holds after EM::optimize, EM.cpp:144), or the current one before any
+    CU(cudaMemcpyAsync(t.data(), em->r_valid && em->d_s_e ? em->d_s_e : em->d_s, (uint64_t)em->nbin * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
     CU(cudaStreamSynchronize(em->stream));
     for (uint32_t y = 0; y < em->Yn; y++) for (int j = 0; j < em->W; j++) s[(uint64_t)y * em->W + j] = t[(uint64_t)j * em->Yn + y];
     return BAMM_OK;
@@ -941,6 +1075,17 @@ extern "C" int bamm_em_get_r(bamm_em* em, uint64_t first, uint64_t count, float*
     REQUIRE(first + count <= em->nsub, "sequence range out of bounds");
     if (!em->r_valid) return fail(BAMM_E_STATE, "no E-step has run");
     CU(cudaSetDevice(em->device));
+    if (!em->r_mat && em->npk) {
+        // the pruned E-step does not write r: run the dense kernel once with the tables of that E-step (no list, no scalars;
+        // the normalisers it stores are bit-identical to the ones already there)
+        PackedView pv = pview_of(em);
+        const EStepLaunch l = {em->grid_pe, em->block_pe, em->stream};
+        ActiveList al = alist_of(em); al.ent = nullptr;
+        if (launch_estep_dense(l, false, em->gfast[0] != 0, false, &pv, plan_for_launch(em, 0, em->q_e), em->d_tab_e, em->d_s_e, em->d_sT_e, em->plain_words, em->d_r, nullptr, &al, nullptr))
+            return fail(BAMM_E_CUDA, "packed E-step launch failed (materialising r)");
+        em->launches += 1;
+        em->r_mat = true; em->r_scaled = false;
+    }
     if (!em->r_scaled) {            // the packed E-step keeps r unnormalised; finish it before it leaves the device
         k_normalise_r<<<em->ss->sm_count * 8, 256, 0, em->stream>>>(pview_of(em), em->W, em->d_scale, em->d_r);
         CU(cudaGetLastError());
@@ -960,6 +1105,30 @@ extern "C" int bamm_em_exchange_buffer(bamm_em* em, void** dev_ptr, uint64_t* wo
 }
 extern "C" int bamm_em_set_global_nseq(bamm_em* em, uint64_t n) { REQUIRE(em, "em is NULL"); em->nseq_global = n; return BAMM_OK; }
 extern "C" int bamm_em_launch_count(bamm_em* em, uint64_t* kernels) { REQUIRE(em && kernels, "NULL argument"); *kernels = em->launches; return BAMM_OK; }
+extern "C" int bamm_em_estep_info(bamm_em* em, uint64_t info[8]) {
+    REQUIRE(em && info, "NULL argument");
+    CU(cudaSetDevice(em->device));
+    CU(cudaStreamSynchronize(em->stream));
+    for (int i = 0; i < 8; i++) info[i] = 0;
+    info[0] = em->sparse ? 1 : 0;
+    info[1] = em->gplans.empty() ? 0 : (uint64_t)em->gplans[0].G;
+    info[2] = em->sparse ? (uint64_t)em->bplan.G : 0;
+    info[3] = 1;
+    if (em->sparse && em->d_eflags) {
+        uint32_t f[4] = {0, 0, 0, 0};
+        CU(cudaMemcpy(f, em->d_eflags, 16, cudaMemcpyDeviceToHost));
+        info[3] = f[0] ? 1 : 0;
+        info[4] = (uint64_t)f[2] | ((uint64_t)f[3] << 32);
+    }
+    if (em->d_act_cnt && em->nregions) {
+        std::vector<uint32_t> c(2 * (size_t)em->nregions);
+        CU(cudaMemcpy(c.data(), em->d_act_cnt, c.size() * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t x : c) info[5] += x;
+    }
+    info[6] = em->gplans.size();
+    info[7] = em->plain_words ? 1 : 0;
+    return BAMM_OK;
+}
 extern "C" int bamm_em_stream(bamm_em* em, void** stream) { REQUIRE(em && stream, "NULL argument"); *stream = (void*)em->stream; return BAMM_OK; }
 
 

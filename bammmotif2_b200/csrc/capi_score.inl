@@ -1,26 +1,6 @@
 // capi_score.inl — part of capi.cu (one translation unit: included there, in this order).
 // log-odds scoring (rows a-9 / a-10) and score statistics (row f-1)
 // ------------------------------------------------------------------------------------------- scoring
-template <int G, bool FAST>
-static int score_zoops_one(const GroupPlan& gp, int sms, cudaStream_t st, const PackedView& pv, const float* d_tab, const float* d_s, float two_eps,
-                           float* d_zoops, unsigned long long* d_z, const uint32_t* d_out, size_t plain_bytes) {
-    const size_t smem = (size_t)gp.table_bytes + plain_bytes;
-    if (cudaFuncSetAttribute(k_score_zoops_packed<G, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    k_score_zoops_packed<G, FAST><<<sms, 1024, smem, st>>>(pv, gp, d_tab, d_s, two_eps, d_zoops, d_z, d_out);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-static int score_zoops_dispatch(const GroupPlan& gp, bool fast, int sms, cudaStream_t st, const PackedView& pv, const float* d_tab, const float* d_s,
-                                float two_eps, float* d_zoops, unsigned long long* d_z, const uint32_t* d_out, size_t plain_bytes) {
-    switch (gp.G) {
-#define BAMM_CASE(g) case g: return fast ? score_zoops_one<g, true>(gp, sms, st, pv, d_tab, d_s, two_eps, d_zoops, d_z, d_out, plain_bytes) \
-                                         : score_zoops_one<g, false>(gp, sms, st, pv, d_tab, d_s, two_eps, d_zoops, d_z, d_out, plain_bytes);
-        BAMM_CASE(1) BAMM_CASE(2) BAMM_CASE(3) BAMM_CASE(4) BAMM_CASE(5) BAMM_CASE(6) BAMM_CASE(7) BAMM_CASE(8)
-        BAMM_CASE(9) BAMM_CASE(10) BAMM_CASE(11) BAMM_CASE(12) BAMM_CASE(13) BAMM_CASE(14) BAMM_CASE(15) BAMM_CASE(16)
-#undef BAMM_CASE
-        default: return -1;
-    }
-}
-
 extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model,
                                   const float* v_all, const float* vbg_all, float* zoops, uint64_t* z, float* mops) {
     REQUIRE(s && v_all && vbg_all && zoops && z, "NULL argument");
@@ -134,7 +114,7 @@ extern "C" int bamm_score_logodds(bamm_seqset* s, const uint64_t* subset, uint64
                 const uint32_t total = zplan.table_bytes >> 2, blocks = (total + 255) / 256;
                 k_make_group_tables<true><<<blocks < 1184 ? blocks : 1184, 256, 0, st>>>(d_s, zplan, d_ztab);
                 CUX(cudaGetLastError());
-                if (score_zoops_dispatch(zplan, zfast, s->sm_count, st, pv, d_ztab, d_s, two_eps, d_zoops, d_z, identity_out ? nullptr : d_pout, tb)) {
+                if (launch_score_zoops(zplan, zfast, s->sm_count, st, pv, d_ztab, d_s, two_eps, d_zoops, d_z, identity_out ? nullptr : d_pout, tb)) {
                     rc = fail(BAMM_E_CUDA, "ZOOPS scoring launch failed: %s", cudaGetErrorString(cudaGetLastError())); goto done;
                 }
             } else {

@@ -9,24 +9,13 @@
 //   counts : 64-bit fixed-point (scale 2^40) per (j,y); integer sums are associative, which makes the M-step
 //            bit-reproducible for any CTA schedule, any grid size and any number of GPUs.
 #pragma once
+#pragma once
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <stdint.h>
+#include "common.cuh"
 
 namespace bamm {
-
-constexpr int   FX_SHIFT      = 40;                       // counts: value * 2^40
-constexpr float FX_SCALE_F    = 1099511627776.0f;         // 2^40
-constexpr double FX_INV_D     = 1.0 / 1099511627776.0;
-constexpr double SC_SCALE_D   = 4294967296.0;             // scalars (llh, sum r): value * 2^32
-constexpr double SC_INV_D     = 1.0 / 4294967296.0;
-constexpr unsigned FULL = 0xffffffffu;
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // k-mer index build: y[i] = (sum_{t=0..K} digit(code[i-t]) * A^t) mod A^(K+1), digit(0) = 0 (patched afterwards),

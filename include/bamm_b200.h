@@ -149,6 +149,13 @@ int bamm_em_last_timing(bamm_em* em, float* estep_ms, float* mstep_ms);
 int bamm_em_loop_timing(bamm_em* em, int* iters, float* estep_ms, float* maccum_ms, float* update_ms, float* total_ms);
 /* number of CUDA kernels this object has launched so far (E-step, M-step, reduce, update, table kernels) */
 int bamm_em_launch_count(bamm_em* em, uint64_t* kernels);
+/* how the last E-step of the packed path ran (diagnostics; synchronises the EM stream). The per-position loop of EM::EStep
+ * (src/refinement/EM.cpp:149-196) is evaluated either for every window (dense) or, when the plan allows it, only for the
+ * windows whose upper bound can reach the M-step's threshold (pruned). info[0] pruned path enabled for the
+ * current model, [1] groups of the exact product, [2] groups of the bound (0: none), [3] the dense kernel ran in the last E-step
+ * (always 1 when [0] is 0), [4] candidate windows listed by the bound pass of the last E-step, [5] windows in the active list,
+ * [6] column passes of the exact plan, [7] the plain table rides in shared memory (0/1). */
+int bamm_em_estep_info(bamm_em* em, uint64_t info[8]);
 void bamm_em_destroy(bamm_em* em);
 
 /* ---- multi-GPU (sequences sharded over ranks, one process per GPU) ---------------------------- */

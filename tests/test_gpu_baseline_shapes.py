@@ -7,8 +7,10 @@ SEVERAL sequences and the benchmarked kernel plans are the ones that run:
   K=5, W=20       10 000 x 500 bp                      (two column passes of the exact E-step)
   A=6, K=5, W=12  10 000 x 100 bp                      (EXTENDED alphabet: generic index-array path)
 
-each on the default path and with an active list that overflows (BAMM_LIST_FRAC=0.000001: device-side fall-back to the dense
-E-step + scan M-step). Reference: EM::EStep / MStep, src/refinement/EM.cpp:139-259; Motif::updateV, src/init/Motif.h:95-136.
+each on the default path (c3: the PRUNED E-step — bound pass, exact pass over the candidates, list M-step) and with an active
+list too small for anything (BAMM_LIST_FRAC=0.000001: dense E-step + scan M-step); c3 also with a candidate list that
+overflows (BAMM_CAND_FRAC=0.000001: bound pass gives up on the device, dense E-step + list M-step). The formulations must
+agree in every bit of the model (same tables, same multiplication order, integer normaliser and counts). Reference: EM::EStep / MStep, src/refinement/EM.cpp:139-259; Motif::updateV, src/init/Motif.h:95-136.
 
 Tolerance (BASELINE.json north_star): r, llh, n, v within 1e-5 relative per iteration. The reference accumulates counts and
 the log likelihood sequentially in fp32; over 10^7 terms that sum itself is only good to ~1e-4, so the counts and the
@@ -104,6 +106,8 @@ def test_per_iteration_parity_on_baseline_shapes(capi, oracle, shape):
     alpha = hostmodel.default_motif_alpha(K, W)
     v0 = hostmodel.motif_from_sites(sites, A, K, alpha, vbg)
     variants = [{}, {"BAMM_LIST_FRAC": "0.000001"}]
+    if shape == "c3_40k":
+        variants.append({"BAMM_CAND_FRAC": "0.000001"})
     ems = []
     for env in variants:
         old = {k: os.environ.get(k) for k in env}
@@ -131,6 +135,13 @@ def test_per_iteration_parity_on_baseline_shapes(capi, oracle, shape):
         for env, em in zip(variants, ems):
             tag = "%s it%d %s" % (shape, it + 1, env or "default")
             llh = em.estep()
+            info = em.estep_info()
+            if shape == "c3_40k":       # the benchmarked plan: pruned by default, the two fall-backs when a list is too small
+                assert info["pruned"] == ("BAMM_LIST_FRAC" not in env), (tag, info)
+                assert info["dense_ran"] == bool(env), (tag, info)
+                if not env:
+                    assert 0 < info["candidates"] < 0.2 * nseq * L and info["G_bound"] + 3 <= info["G"], (tag, info)
+                    print(tag, info)
             assert abs(llh - llh_ref) <= RTOL * abs(llh_ref) + 1e-7 * nseq, tag
             r = em.r()
             assert np.all(r.reshape(nseq, L)[:, L - W + 1:] == 0), tag                  # zero tail (EM.cpp:190-192)
@@ -140,7 +151,8 @@ def test_per_iteration_parity_on_baseline_shapes(capi, oracle, shape):
             m = em.model()
             _assert_rel(m, v_ref, RTOL, 1e-7 / float(alpha[K].min()), "v " + tag)
             models.append(m)
-        assert np.array_equal(models[0], models[1]), "list and scan M-step must give the same bits"
+        for m in models[1:]:
+            assert np.array_equal(models[0], m), "pruned / dense E-step and list / scan M-step must give the same bits"
         v = models[0]
     # the fused loop (no r read-back between the steps) reaches the same model bits as the step-wise calls
     em = capi.EM(ss, W, K, Kbg)
