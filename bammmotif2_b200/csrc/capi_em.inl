@@ -142,57 +142,65 @@ static bool plan_passes(int W, int K, int K_bg, bool reduced, size_t budget, std
 }
 
 // ---- bound plan of the pruned E-step (estep.cuh) -------------------------------------------------------------------
-// The fewest groups of at most 7 bases (64 KB tables) / 6 bases (16 KB) whose base ranges cover columns 0..W-1 within `budget`;
-// spare bases go to the left of the first group (the background context of column 0) and then into overlaps between
-// neighbouring groups, so that fewer leading columns of a group lose context. Group g owns the columns right of group g-1's
-// last base. Returns false when W columns cannot be covered.
+// Groups of T <= 6 bases whose tables are indexed by T+1 bases (two neighbouring windows per entry, k_make_bound_tables): the
+// fewest groups (6-base groups first: 64 KB each, then 5 bases: 16 KB, ...) whose base ranges cover columns 0..W-1 within
+// `budget`. Spare bases: one to the left of the first group (background context of column 0), the rest as overlaps of the
+// LAST groups with their predecessors, so that fewer leading columns of those groups lose context. Group g owns the columns
+// right of group g-1's last base. Returns false when W columns cannot be covered (or W+1 bases do not fit one window word).
 static bool make_bound_plan(int W, int K, int K_bg, size_t budget, GroupPlan& gp, bool& fast) {
-    int best_n7 = -1, best_n6 = -1;
-    for (int G = 1; G <= 8 && best_n7 < 0; G++)
-        for (int n7 = std::min(G, 3); n7 >= 0; n7--) {           // more 7-base groups first: more spare bases
-            const int n6 = G - n7;
-            if ((size_t)n7 * 65536 + (size_t)n6 * 16384 > budget) continue;
-            if (7 * n7 + 6 * n6 < W) continue;
-            best_n7 = n7; best_n6 = n6; break;
+    if (W + 1 > 31) return false;
+    std::vector<int> T;
+    {
+        size_t bytes = 0; int bases = 0;
+        while (bases < W && (int)T.size() < 8) {
+            int t = 6;
+            while (t >= 1 && bytes + ((size_t)4 << (2 * (t + 1))) > budget) t--;
+            if (t < 1) return false;
+            // the last group only takes what it needs (plus context it can use)
+            if (bases + t > W + K) t = std::max(1, W + K - bases);
+            T.push_back(t); bytes += (size_t)4 << (2 * (t + 1)); bases += t;
         }
-    if (best_n7 < 0) return false;
-    const int G = best_n7 + best_n6;
+        if (bases < W) return false;
+    }
+    const int G = (int)T.size();
+    int spare = 0; for (int t : T) spare += t; spare -= W;
     memset(&gp, 0, sizeof(gp));
     gp.W = W; gp.K = K; gp.G = G; gp.Yn = 1u << (2 * (K + 1));
-    int spare = 7 * best_n7 + 6 * best_n6 - W;
-    const int ctx0 = std::min(K_bg, K);
-    int lo = -std::min(spare, ctx0);
-    spare += lo;
+    const int lead = std::min(spare, std::min(1, std::min(K_bg, K)));
+    spare -= lead;
+    std::vector<int> ov(G, 0);
+    for (int g = G - 1; g >= 1 && spare > 0; g--) { ov[g] = std::min(spare, std::min(K, T[g] - 1)); spare -= ov[g]; }
+    int lo = -lead - spare;                                  // anything still left goes to the front as well
     uint32_t base = 0;
     int prev_hi = -1;
     for (int g = 0; g < G; g++) {
-        int T = g < best_n7 ? 7 : 6;
-        if (g > 0) { const int ov = std::min(spare, K); lo = prev_hi + 1 - ov; spare -= ov; }
-        int hi = lo + T - 1;
-        if (hi > W - 1) { hi = W - 1; T = hi - lo + 1; }
+        if (g > 0) lo = prev_hi + 1 - ov[g];
+        int hi = lo + T[g] - 1;
+        if (hi > W - 1) hi = W - 1;
         if (hi <= prev_hi) return false;
+        const int Tg = hi - lo + 1;
         gp.col0[g] = prev_hi + 1; gp.ncol[g] = hi - prev_hi; gp.lo[g] = lo;
         gp.base[g] = base;
-        gp.mask4[g] = (uint32_t)(((1ull << (2 * T)) - 1ull) << 2);
+        gp.mask4[g] = (uint32_t)(((1ull << (2 * (Tg + 1))) - 1ull) << 2);
         gp.colmask[g] = (uint32_t)(((hi >= 31 ? 0xffffffffull : ((2ull << hi) - 1ull))) & ~((1ull << gp.col0[g]) - 1ull));
-        base += 4u << (2 * T);
+        base += 4u << (2 * (Tg + 1));
         prev_hi = hi;
     }
-    if (prev_hi != W - 1) return false;
+    if (prev_hi != W - 1 || (size_t)base > budget) return false;
     gp.table_bytes = base;
-    gp.passmask = (uint32_t)((W >= 32 ? 0x100000000ull : (1ull << W)) - 1ull);
+    gp.passmask = (uint32_t)((1ull << W) - 1ull);
     gp.pass_first = 1; gp.pass_last = 1;
-    // alignment of the window word, as in make_group_plan: kd >= -lo[0] (oldest base read), kd <= 31-W, one-shift extraction
-    // needs kd >= 15 - hi[0]
+    // alignment of the window word (32 bases from p-kd, p = the FIRST window of the pair): kd >= -lo[0] (oldest base read),
+    // base p+W (last base of the second window) inside the word: kd <= 31-(W+1); one-shift extraction needs kd >= 15-(hi[0]+1)
     const int hi0 = gp.col0[0] + gp.ncol[0] - 1;
-    const int kd_min = -gp.lo[0], kd_max = 31 - W;
+    const int kd_min = -gp.lo[0], kd_max = 31 - (W + 1);
     if (kd_min > kd_max) return false;
-    const int kd_fast = std::max(kd_min, 15 - hi0);
+    const int kd_fast = std::max(kd_min, 15 - (hi0 + 1));
     fast = kd_fast <= kd_max;
     gp.kd = fast ? kd_fast : kd_min;
     for (int g = 0; g < G; g++) {
         const int hi = gp.col0[g] + gp.ncol[g] - 1;
-        const int sh = 60 - 2 * (hi + gp.kd);
+        const int sh = 60 - 2 * (hi + 1 + gp.kd);
         gp.shift[g] = (uint32_t)sh;
         gp.shift2[g] = sh > 32 ? (uint32_t)(sh - 32) : 0u;
     }
@@ -493,7 +501,7 @@ static int launch_tables(bamm_em* em, const float* d_s, float* d_tab_dst) {
         k_bound_levels<<<1, 1024, 0, em->stream>>>(d_s, em->W, em->K, em->blev, em->d_U);
         CU(cudaGetLastError());
         const uint32_t total = em->bplan.table_bytes >> 2, blocks = (total + 255) / 256;
-        k_make_bound_tables<<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(d_s, em->d_U, em->blev, em->bplan, em->d_btab);
+        k_make_bound_tables<<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(d_s, em->d_U, em->blev, em->bplan, (uint32_t*)em->d_btab);
         CU(cudaGetLastError());
         em->launches += 2;
     }
@@ -534,8 +542,9 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
         em->sparse = false;
         if (em->cand_ok && em->gplans.size() == 1 && !getenv("BAMM_NO_SPARSE") && em->K >= 1 &&
             make_bound_plan(em->W, em->K, em->K_bg, em->tab_capacity, em->bplan, em->bfast)) {
+            // the bound pass costs G1/2 lookups per window (two windows per entry)
             const int need = getenv("BAMM_SPARSE") && atoi(getenv("BAMM_SPARSE")) > 0 ? 1 : 3;
-            em->sparse = em->bplan.G + need <= em->gplans[0].G;
+            em->sparse = (em->bplan.G + 1) / 2 + need <= em->gplans[0].G;
         }
         if (em->gplans.size() > em->tab_passes) {
             CU(cudaStreamSynchronize(em->stream));

@@ -313,8 +313,9 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
 }
 
 // ---- pruned E-step, part 1: bounds ---------------------------------------------------------------------------------
-// gp here is the BOUND plan: G1 groups over base ranges [lo, hi]; tab[g][z] >= product of the group's columns for every
-// sequence context outside the range (k_make_bound_tables). Windows in [n0,n1) (over the N) and from tl on (truncated) are
+// gp here is the BOUND plan: G1 groups over base ranges [lo, hi]; an entry of tab[g] holds, as two bfloat16 rounded up, bounds of
+// the product of the group's columns for window p and for window p+1, valid for every sequence context outside the range
+// (k_make_bound_tables): G1 lookups per TWO windows. Windows in [n0,n1) (over the N) and from tl on (truncated) are
 // left to k_eexact, which always evaluates them. The records of the next sequence (list entry two ahead, PackedSeq one ahead)
 // and its first stream words are requested while the current one is processed: a warp never waits for a chain of loads.
 template <int G1, bool FAST>
@@ -331,15 +332,13 @@ k_ebound(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
     const int W = gp.W, K = gp.K, KD = gp.kd;
     const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
     GroupConsts<G1> gc; load_consts<G1>(gc, gp, tab_s);
-#pragma unroll
-    for (int g = 0; g < G1; g++) asm volatile("" : "+r"(gc.sh[g]), "+r"(gc.mk[g]), "+r"(gc.ab[g]));   // keep the extraction constants in registers
-    const float thr = gp.thr0;                               // already lowered by the rounding margin of the bound
     uint32_t* __restrict__ creg = cl.ent + cl.reg_off[warp];
     const uint32_t ccap = (uint32_t)(cl.reg_off[warp + 1] - cl.reg_off[warp]);
     uint32_t cpos = 0;
     bool ok = true;
-    const int lane_word = (lane - KD) >> 4;
-    const int sft = 2 * ((lane - KD) & 15);
+    // a lane owns the windows 2 lane, 2 lane + 1 of every chunk of 64: one entry of a pair table bounds both
+    const int lane_word = (2 * lane - KD) >> 4;
+    const int sft = 2 * ((2 * lane - KD) & 15);
     uint32_t li = warp;
     if (li < pv.nlist) {
         PackedSeq sq = pv.seqs[pv.seq_ids[li]];
@@ -354,27 +353,36 @@ k_ebound(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
             uint32_t n_nn = 0u;
             if (more) { sq_next = pv.seqs[n_next]; if (li_next + nwarps < pv.nlist) n_nn = pv.seq_ids[li_next + nwarps]; }
             const int L = (int)sq.L, LW1 = L - W + 1, mid = (int)sq.mid;
-            const float pos = gp.q / (float)LW1;
+            // bound * q/LW1 >= thr0  <=>  bound >= thr0 LW1 / q (thr0 already carries the rounding margin of the bound)
+            const float thr = gp.thr0 * (float)LW1 / gp.q;
             const int tl = min(max(L - 2 * W + 2, 0), LW1);
             int n0 = tl, n1 = tl;
             if (mid >= 0) { n0 = min(max(mid - W + 1, 0), tl); n1 = min(mid + K + 1, tl); }
             const uint32_t start = cpos;
-            const int nch = (tl + 31) >> 5;
+            const int nch = (tl + 63) >> 6;
             uint32_t u0 = 0, u1 = 0, u2 = 0;
-            // The hot loop only records, per lane, WHICH of its windows pass (bit c of `mine` = window lane + 32 c of this block
-            // of up to 32 chunks): no vote, no range test, no store per chunk. The windows that are not this kernel's (over the
-            // N, truncated tail, past the end) are cleared from the mask afterwards and the survivors written in one go.
-            for (int cb = 0; cb < nch && ok; cb += 32) {
-                const int ce = min(nch, cb + 32);
+            // The hot loop only records, per lane, WHICH of its windows pass (bit c = window 2 lane + 64 c, bit 16 + c = the
+            // window after it, for a block of up to 16 chunks): no vote, no range test, no store per chunk. The windows that
+            // are not this kernel's (over the N, truncated tail, past the end) are cleared from the mask afterwards and the
+            // survivors written in one go.
+            for (int cb = 0; cb < nch && ok; cb += 16) {
+                const int ce = min(nch, cb + 16);
                 const bool last_block = ce == nch;
-                const int c_pf = last_block ? max(ce - 8, cb) : ce;      // chunk before which the next sequence's first words are requested
+                const int c_pf = last_block ? max(ce - 4, cb) : ce;      // chunk before which the next sequence's first words are requested
                 uint32_t mine = 0u, bit = 1u;
                 auto chunk = [&]() {
                     const uint32_t whi = __funnelshift_l(t1, t0, sft), wlo = __funnelshift_l(t2, t1, sft);
-                    wl += 2;
-                    t0 = t2; t1 = wl[1]; t2 = wl[2];
-                    const float bound = groups_prod<G1, FAST>(gc, whi, wlo, pos);
-                    if (bound >= thr) mine |= bit;
+                    wl += 4;
+                    t0 = wl[0]; t1 = wl[1]; t2 = wl[2];
+                    float b0 = 1.0f, b1 = 1.0f;
+#pragma unroll
+                    for (int g = 0; g < G1; g++) {
+                        const uint32_t e = __float_as_uint(lds_f32(group_offset<G1, FAST>(gc, g, whi, wlo), gc.ab[g]));
+                        const float f0 = __uint_as_float(e << 16), f1 = __uint_as_float(e & 0xffff0000u);
+                        b0 = g ? b0 * f0 : f0; b1 = g ? b1 * f1 : f1;
+                    }
+                    if (b0 >= thr) mine |= bit;
+                    if (b1 >= thr) mine |= bit << 16;
                     bit <<= 1;
                 };
 #pragma unroll 2
@@ -382,14 +390,19 @@ k_ebound(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
                 if (last_block) { const uint32_t* __restrict__ wn = pv.words + sq_next.word_off + lane_word; u0 = wn[0]; u1 = wn[1]; u2 = wn[2]; }
 #pragma unroll 2
                 for (int c = c_pf; c < ce; c++) chunk();
-                // this lane's windows of the block: p = lane + 32 (cb + c), c = 0..31; keep c with p < tl and p outside [n0, n1)
-                const int pb = lane + 32 * cb;
-                const int c_tl = tl > pb ? min((tl - pb + 31) >> 5, 32) : 0;                 // c < c_tl  <=>  p < tl
-                uint32_t keep = c_tl >= 32 ? 0xffffffffu : ((1u << c_tl) - 1u);
-                if (n1 > n0) {
-                    const int ca = n0 > pb ? (n0 - pb + 31) >> 5 : 0, cz = n1 > pb ? (n1 - pb + 31) >> 5 : 0;   // c in [ca, cz)  <=>  n0 <= p < n1
-                    const uint32_t ma = ca >= 32 ? 0xffffffffu : ((1u << ca) - 1u), mz = cz >= 32 ? 0xffffffffu : ((1u << cz) - 1u);
-                    keep &= ~(mz & ~ma);
+                // this lane's windows of the block: p = pb + h + 64 c (h = 0, 1; c = 0..15); keep those with p < tl outside [n0, n1)
+                const int pb = 2 * lane + 64 * cb;
+                uint32_t keep = 0u;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int q0 = pb + h;
+                    const int c_tl = tl > q0 ? min((tl - q0 + 63) >> 6, 16) : 0;             // c < c_tl  <=>  p < tl
+                    uint32_t k16 = (1u << c_tl) - 1u;
+                    if (n1 > n0) {
+                        const int ca = n0 > q0 ? min((n0 - q0 + 63) >> 6, 16) : 0, cz = n1 > q0 ? min((n1 - q0 + 63) >> 6, 16) : 0;   // c in [ca, cz)  <=>  n0 <= p < n1
+                        k16 &= ~(((1u << cz) - 1u) & ~((1u << ca) - 1u));
+                    }
+                    keep |= k16 << (16 * h);
                 }
                 mine &= keep;
                 // exclusive prefix of the lanes' counts -> each lane writes its windows behind those of the lower lanes
@@ -401,9 +414,9 @@ k_ebound(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
                 if (cpos + total > ccap) { ok = false; break; }
                 uint32_t at = cpos + incl - mycnt;
                 while (mine) {
-                    const int c = __ffs(mine) - 1;
+                    const int b = __ffs(mine) - 1;
                     mine &= mine - 1u;
-                    creg[at++] = (uint32_t)(pb + 32 * c);
+                    creg[at++] = (uint32_t)(pb + 64 * (b & 15) + (b >> 4));
                 }
                 cpos += total;
             }

@@ -204,23 +204,35 @@ k_bound_levels(const float* __restrict__ s /* [j][Yn] */, int W, int K, BoundLev
         __syncthreads();
     }
 }
-// tab[g][z] = prod_{j in group g} U_avail(j)[j][...]: an upper bound (up to fp32 rounding, covered by the margin in the
-// kernel's threshold) of the product of the group's columns for EVERY context left of the group's bases
-__global__ void k_make_bound_tables(const float* __restrict__ s, const float* __restrict__ U, BoundLevels bl, GroupPlan gp, float* __restrict__ tab) {
+// f_g(z) = prod_{j in group g} U_avail(j)[j][...] over the group's T bases lo..hi: an upper bound of the product of the group's
+// columns for EVERY context left of the group's bases. The table is indexed by T+1 bases (lo..hi+1) and an entry holds TWO
+// bounds as bfloat16, rounded UP: low half = f_g of window p (bases lo..hi), high half = f_g of window p+1 (bases lo+1..hi+1),
+// so one 32-bit lookup serves two neighbouring windows.
+__device__ __forceinline__ uint32_t bf16_up(float x) {      // smallest bfloat16 >= x (x finite, >= 0)
+    uint32_t b = __float_as_uint(x);
+    if (b & 0xffffu) b = (b | 0xffffu) + 1u;
+    return b >> 16;
+}
+__global__ void k_make_bound_tables(const float* __restrict__ s, const float* __restrict__ U, BoundLevels bl, GroupPlan gp, uint32_t* __restrict__ tab) {
     const uint32_t total = gp.table_bytes >> 2;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int g = 0;
         while (g + 1 < gp.G && i >= (gp.base[g + 1] >> 2)) g++;
-        const uint32_t z = i - (gp.base[g] >> 2);
-        const int hi = gp.col0[g] + gp.ncol[g] - 1;
-        float p = 1.0f;
-        for (int t = 0; t < gp.ncol[g]; t++) {
-            const int j = gp.col0[g] + t;
-            const int avail = min(j - gp.lo[g] + 1, gp.K + 1);
-            const uint32_t y = (z >> (2 * (hi - j))) & ((1u << (2 * avail)) - 1u);
-            p *= (avail == gp.K + 1) ? s[(uint32_t)j * gp.Yn + y] : U[bl.off[avail] + ((uint32_t)j << (2 * avail)) + y];
+        const uint32_t z2 = i - (gp.base[g] >> 2);
+        const int hi = gp.col0[g] + gp.ncol[g] - 1, T = hi - gp.lo[g] + 1;
+        uint32_t packed = 0u;
+        for (int h = 0; h < 2; h++) {
+            const uint32_t z = h == 0 ? (z2 >> 2) : (z2 & ((1u << (2 * T)) - 1u));
+            float p = 1.0f;
+            for (int t = 0; t < gp.ncol[g]; t++) {
+                const int j = gp.col0[g] + t;
+                const int avail = min(j - gp.lo[g] + 1, gp.K + 1);
+                const uint32_t y = (z >> (2 * (hi - j))) & ((1u << (2 * avail)) - 1u);
+                p *= (avail == gp.K + 1) ? s[(uint32_t)j * gp.Yn + y] : U[bl.off[avail] + ((uint32_t)j << (2 * avail)) + y];
+            }
+            packed |= bf16_up(p) << (16 * h);
         }
-        tab[i] = p;
+        tab[i] = packed;
     }
 }
 // start of an E-step: scalars and list-overflow flag cleared; the dense-hold counter of the pruned path ticks down

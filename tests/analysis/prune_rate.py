@@ -13,7 +13,7 @@ alpha_div = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 W = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 L0, Kbg, A, Q = 500, 2, 4, 0.3
-iters = [0, 1, 3, 6, 13]
+iters = [0, 3, 8]
 fwd, sites, _ = synth.planted_sequences(1234, nseq, L0, W)
 codes = synth.stored_both_strands(fwd)
 ppos, pkmer = synth.middle_n_patches(codes, 1234)
@@ -38,13 +38,17 @@ def plan_bound(S, groups):
     """groups: list of (lo, hi) base ranges relative to the window start; column j belongs to the group that holds base p+j."""
     b = np.ones((ns, full))
     for j in range(W):
-        g = [x for x in groups if x[0] <= j <= x[1]][-1]
+        g = max([x for x in groups if x[0] <= j <= x[1]], key=lambda x: j - x[0])
         avail = min(j - g[0] + 1, K + 1)
         U = S[:, j].reshape(A ** (K + 1 - avail), A ** avail).max(axis=0)
         b *= U[(ks % (A ** avail))[:, j:j + full]]
     return b
 
 PLANS = {
+    "pairs a: [0..5|6..11|12..17|18..19]": [(0, 5), (6, 11), (12, 17), (18, 19)],
+    "pairs b: [-2..3|4..9|10..15|15..19]": [(-2, 3), (4, 9), (10, 15), (15, 19)],
+    "pairs c: [-2..3|3..8|9..14|15..19]": [(-2, 3), (3, 8), (9, 14), (15, 19)],
+    "pairs d: [-1..4|5..10|11..16|15..19]": [(-1, 4), (5, 10), (11, 16), (15, 19)],
     "3x7 [-1..5|6..12|13..19]": [(-1, 5), (6, 12), (13, 19)],
     "3: [-2..4|5..12(8b,16bit)|13..19]": [(-2, 4), (5, 12), (13, 19)],
     "3: 8b,8b,7b 16-bit [-2..5|6..13|13..19]": [(-2, 5), (6, 13), (13, 19)],
