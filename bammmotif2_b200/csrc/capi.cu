@@ -190,6 +190,7 @@ struct bamm_em {
     float* d_btab = nullptr;    // bound tables
     float* d_U = nullptr;       // maxima of s over dropped context bases, per level
     uint32_t* d_cand = nullptr; uint2* d_cand_seq = nullptr; uint64_t* d_creg_off = nullptr;
+    ulonglong2* d_seqacc = nullptr;  // per list sequence: normaliser terms of its masked windows (k_emasked -> k_eexact)
     uint32_t* d_eflags = nullptr;   // CandList::flags (4 words)
     bool r_mat = true;          // d_r holds the posteriors of the last E-step (false after a pruned E-step until bamm_em_get_r)
     const float *d_s_e = nullptr, *d_sT_e = nullptr, *d_tab_e = nullptr;   // the tables the last E-step read

@@ -22,7 +22,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     cudaFree(em->d_peer_local); cudaFree(em->d_peer_done);
     cudaFree(em->d_act); cudaFree(em->d_scale); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
     cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab); cudaFree(em->d_tab_alt);
-    cudaFree(em->d_btab); cudaFree(em->d_U); cudaFree(em->d_cand); cudaFree(em->d_cand_seq); cudaFree(em->d_creg_off); cudaFree(em->d_eflags);
+    cudaFree(em->d_btab); cudaFree(em->d_U); cudaFree(em->d_cand); cudaFree(em->d_cand_seq); cudaFree(em->d_seqacc); cudaFree(em->d_creg_off); cudaFree(em->d_eflags);
     cudaFree(em->d_s_alt); cudaFree(em->d_sT_alt);
     cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_sT); cudaFree(em->d_v);
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
@@ -464,6 +464,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
                 }
                 if (ok && dev_malloc(&em->d_cand, (creg[em->nregions] ? creg[em->nregions] : 1) * sizeof(uint32_t)) == cudaSuccess) {
                     CUE(dev_malloc(&em->d_cand_seq, (size_t)em->npk * sizeof(uint2)));
+                    CUE(dev_malloc(&em->d_seqacc, (size_t)em->npk * sizeof(ulonglong2)));
                     CUE(upload(creg.data(), creg.size() * 8, (void**)&em->d_creg_off));
                     CUE(dev_malloc(&em->d_eflags, 16));
                     CUE(cudaMemset(em->d_eflags, 0, 16));
@@ -540,7 +541,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
         }
         // pruned path: worth it when the bound needs at least three lookups fewer than the exact product (BAMM_SPARSE=1: whenever fewer)
         em->sparse = false;
-        if (em->cand_ok && em->gplans.size() == 1 && !getenv("BAMM_NO_SPARSE") && em->K >= 1 &&
+        if (em->cand_ok && em->gplans.size() == 1 && em->plain_words && !getenv("BAMM_NO_SPARSE") && em->K >= 1 &&
             make_bound_plan(em->W, em->K, em->K_bg, em->tab_capacity, em->bplan, em->bfast)) {
             // the bound pass costs G1/2 lookups per window (two windows per entry)
             const int need = getenv("BAMM_SPARSE") && atoi(getenv("BAMM_SPARSE")) > 0 ? 1 : 3;
@@ -567,8 +568,9 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
             }
             // per-warp staging of the sequence words in the exact pass, when shared memory has room left
             em->stage = (size_t)em->gplans[0].table_bytes + (em->plain_words ? plain_bytes : 0) + estep_stage_bytes(em->block_pe) <= em->tab_capacity && !getenv("BAMM_NO_STAGE");
-            if (launch_estep_bound(l, true, em->bfast, nullptr, em->bplan, nullptr, nullptr) ||
-                launch_estep_exact(l, true, em->gfast[0] != 0, nullptr, em->gplans[0], nullptr, nullptr, nullptr, em->plain_words, em->stage, nullptr, nullptr, nullptr))
+            if (launch_estep_masked(l, true, em->gfast[0] != 0, nullptr, em->gplans[0], nullptr, nullptr, em->plain_words, nullptr, nullptr, nullptr) ||
+                launch_estep_bound(l, true, em->bfast, nullptr, em->bplan, nullptr, nullptr) ||
+                launch_estep_exact(l, true, em->gfast[0] != 0, nullptr, em->gplans[0], nullptr, nullptr, nullptr, em->plain_words, em->stage, nullptr, nullptr, nullptr, nullptr))
                 return fail(BAMM_E_CUDA, "cannot opt in to shared memory for the pruned E-step");
         }
     }
@@ -612,7 +614,7 @@ static PackedView pview_of(const bamm_em* em) {
 }
 
 static int launch_estep(bamm_em* em) {
-    em->launches += 1 + (em->npk ? em->gplans.size() + (em->sparse ? 2 : 0) : 0) + (em->ngen ? 1 : 0);
+    em->launches += 1 + (em->npk ? em->gplans.size() + (em->sparse ? 3 : 0) : 0) + (em->ngen ? 1 : 0);
     unsigned long long* scal = em->d_xbuf + em->nbin;
     k_estep_begin<<<1, 32, 0, em->stream>>>(scal, em->d_overflow, em->d_eflags);
     CU(cudaGetLastError());
@@ -627,8 +629,10 @@ static int launch_estep(bamm_em* em) {
             GroupPlan bp = em->bplan; bp.q = em->q;
             bp.thr0 = FX_HALF_UNIT * (1.0f - em->q) * 0.999f * 0.9999f;          // margin: bound and product round differently
             const GroupPlan gp = plan_for_launch(em, 0, em->q);
+            if (launch_estep_masked(l, false, em->gfast[0] != 0, &pv, gp, em->d_tab, em->d_s, em->plain_words, &cl, em->d_seqacc, &al))
+                return fail(BAMM_E_CUDA, "E-step launch failed (masked windows)");
             if (launch_estep_bound(l, false, em->bfast, &pv, bp, em->d_btab, &cl)) return fail(BAMM_E_CUDA, "E-step launch failed (bounds)");
-            if (launch_estep_exact(l, false, em->gfast[0] != 0, &pv, gp, em->d_tab, em->d_s, em->d_sT, em->plain_words, em->stage, &cl, scal, &al))
+            if (launch_estep_exact(l, false, em->gfast[0] != 0, &pv, gp, em->d_tab, em->d_s, em->d_sT, em->plain_words, em->stage, &cl, em->d_seqacc, scal, &al))
                 return fail(BAMM_E_CUDA, "E-step launch failed (candidates)");
             if (launch_estep_dense(l, false, em->gfast[0] != 0, false, &pv, gp, em->d_tab, em->d_s, em->d_sT, em->plain_words, em->d_r, scal, &al, em->d_eflags))
                 return fail(BAMM_E_CUDA, "packed E-step launch failed");

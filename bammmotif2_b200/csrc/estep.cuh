@@ -111,13 +111,30 @@ __device__ __forceinline__ float masked_prod(const GroupConsts<G>& c, const Grou
         if (jb >= ja) ncols = ((jb >= 31 ? 0xffffffffu : ((2u << jb) - 1u))) & ~((1u << ja) - 1u) & mt.passmask;
     }
     uint32_t cols = valid;
+    const uint32_t bad = ~valid | ncols;    // a group is whole and untouched when none of its columns is missing or patched
 #pragma unroll
     for (int g = 0; g < G; g++) {
         const uint32_t cm = gp.colmask[g];
-        const bool good = ((cm & ~valid) == 0u) && ((cm & ncols) == 0u);
-        if (good) { prod *= lds_f32(group_offset<G, FAST>(c, g, whi, wlo), c.ab[g]); cols &= ~cm; }   // lanes without the group stay off the shared-memory pipe
+        const uint32_t off = group_offset<G, FAST>(c, g, whi, wlo);
+        const bool good = (cm & bad) == 0u;
+        float v = 1.0f;
+        if (good) v = lds_f32(off, c.ab[g]);        // lanes without the group stay off the shared-memory pipe
+        prod *= v;
+        cols = good ? cols & ~cm : cols;
     }
-    if (__any_sync(__activemask(), over_n)) {
+    if (mt.plain_s) {
+        // plain table in shared memory: one loop over the columns the groups left, k-mer from the stream or from the patch list
+        const int jn = mid - p;
+        while (cols) {
+            const int j = __ffs(cols) - 1;
+            cols &= cols - 1u;
+            uint32_t y = field(w, 62 - 2 * mt.KD - 2 * j, mt.maskK);
+            if (over_n && (uint32_t)(j - jn) <= (uint32_t)K) y = yp[j - jn];
+            prod *= lds_f32(((uint32_t)j * (mt.Yn + 1u) + y) << 2, mt.plain_s);
+        }
+        return prod;
+    }
+    if (__any_sync(FULL, over_n)) {
         for (int d0 = 0; d0 <= K; d0 += 4) {
             float f[4];
 #pragma unroll
@@ -126,7 +143,7 @@ __device__ __forceinline__ float masked_prod(const GroupConsts<G>& c, const Grou
                 f[u] = 1.0f;
                 if (d <= K && over_n && j >= 0 && j <= jmax && ((mt.passmask >> j) & 1u)) {
                     const uint32_t y = yp[d];
-                    f[u] = mt.plain_s ? lds_f32(((uint32_t)j * (mt.Yn + 1u) + y) << 2, mt.plain_s) : __ldg(&mt.s_rows[(uint64_t)y * W + j]);
+                    f[u] = __ldg(&mt.s_rows[(uint64_t)y * W + j]);
                 }
             }
 #pragma unroll
@@ -143,7 +160,7 @@ __device__ __forceinline__ float masked_prod(const GroupConsts<G>& c, const Grou
                 const int j = __ffs(cols) - 1;
                 cols &= cols - 1u;
                 const uint32_t y = field(w, 62 - 2 * mt.KD - 2 * j, mt.maskK);
-                f[u] = mt.plain_s ? lds_f32(((uint32_t)j * (mt.Yn + 1u) + y) << 2, mt.plain_s) : __ldg(&mt.s_g[(uint32_t)j * mt.Yn + y]);
+                f[u] = __ldg(&mt.s_g[(uint32_t)j * mt.Yn + y]);
             }
         }
 #pragma unroll
@@ -432,6 +449,127 @@ k_ebound(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
     if (lane == 0 && cpos) atomicAdd(reinterpret_cast<unsigned long long*>(cl.flags + 2), (unsigned long long)cpos);
 }
 
+// ---- pruned E-step, part 0: the windows over the N and the truncated tail ----------------------------------------------
+// Every sequence has W+K windows over the structural N and W-1 truncated windows (EM.cpp:167); they need the masked evaluation
+// and most truncated ones are active, so they are evaluated for all sequences — with the sequences ACROSS the lanes: lane l
+// owns sequence 32 i + l and all lanes walk the same window index t. For window t the set of whole groups and of single
+// columns is the same in every lane (it only depends on W, K and t), so there is no mask arithmetic and no divergence; the
+// window word advances by one base per step in registers. The partial normaliser of every sequence goes to `seqacc`
+// (k_eexact starts from it), the windows that reach the threshold to the back of the warp's region of the active list.
+// Multiplication order = masked_prod's: whole groups ascending, then the remaining columns ascending.
+// Sequences whose ranges are clipped (shorter than 2W-2, N too close to an end) make their warp take the generic route.
+struct MaskedStep { uint32_t good, cols; };     // per window index: bit g = group g whole, bit j = column j from the plain table
+template <int G, bool FAST>
+__global__ void __launch_bounds__(BAMM_E_THREADS, 1)
+k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
+          uint32_t plain_words, CandList cl, ulonglong2* __restrict__ seqacc, ActiveList al) {
+    extern __shared__ float tab[];
+    __shared__ MaskedStep steps[2][48];           // [0]: truncated windows t = p - tl, [1]: windows over the N, t = p - (mid-W+1)
+    if (cl.flags[0] != 0u) return;
+    for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
+    for (uint32_t i = threadIdx.x; i < plain_words; i += blockDim.x) tab[(gp.table_bytes >> 2) + i + i / gp.Yn] = s_g[i];   // rows padded by one float
+    const int W = gp.W, K = gp.K, KD = gp.kd;
+    const int nt_tail = W - 1, nt_n = W + K;
+    if (threadIdx.x < 96) {
+        const int which = threadIdx.x >= 48, t = threadIdx.x - 48 * which;
+        uint32_t valid = 0xffffffffu >> (32 - W), ncols = 0u;
+        if (!which) { const int jmax = W - 2 - t; valid = jmax >= 0 ? ((2u << jmax) - 1u) : 0u; }
+        else { const int jn = W - 1 - t, ja = max(jn, 0), jb = min(jn + K, W - 1); if (jb >= ja) ncols = ((2u << jb) - 1u) & ~((1u << ja) - 1u); }
+        const uint32_t bad = ~valid | ncols;
+        uint32_t good = 0u, cols = valid;
+        for (int g = 0; g < G; g++) if ((gp.colmask[g] & bad) == 0u) { good |= 1u << g; cols &= ~gp.colmask[g]; }
+        steps[which][t].good = good; steps[which][t].cols = cols;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
+    const float thr0 = gp.thr0;
+    GroupConsts<G> gc; load_consts<G>(gc, gp, tab_s);
+    const uint32_t plain_s = tab_s + gp.table_bytes, maskK = gp.Yn - 1u, ystride = gp.Yn + 1u;
+    MaskedTabs mt; mt.s_g = s_g; mt.s_rows = nullptr; mt.plain_s = plain_s;
+    mt.Yn = gp.Yn; mt.maskK = maskK; mt.passmask = 0xffffffffu; mt.W = W; mt.K = K; mt.KD = KD;
+    Emitter em; em.init(al, warp, true);
+    // a warp takes the sequences k_eexact gives it (li = warp mod nwarps), 32 at a time: the two kernels share the warp's region
+    for (uint64_t k0 = 0; warp + nwarps * k0 < pv.nlist; k0 += 32) {
+        const uint64_t li64 = warp + (uint64_t)nwarps * (k0 + lane);
+        const bool have = li64 < pv.nlist;
+        const uint32_t li = have ? (uint32_t)li64 : 0u;
+        const uint32_t n = have ? pv.seq_ids[li] : 0u;
+        PackedSeq sq; sq.word_off = 2; sq.L = (uint32_t)(2 * W + K + 2); sq.mid = 0xffffffffu;
+        if (have) sq = pv.seqs[n];
+        const int L = (int)sq.L, LW1 = L - W + 1, mid = (int)sq.mid;
+        const uint32_t* __restrict__ wseq = pv.words + sq.word_off;
+        const uint32_t woff = (uint32_t)sq.word_off;
+        const uint16_t* __restrict__ yp = pv.ypatch + (uint64_t)n * (K + 1);
+        const float pos = gp.q / (float)LW1;
+        const int tl = min(max(L - 2 * W + 2, 0), LW1);
+        int n0 = tl, n1 = tl;
+        if (mid >= 0) { n0 = min(max(mid - W + 1, 0), tl); n1 = min(mid + K + 1, tl); }
+        NormAcc acc; acc.clear();
+        const bool regular = !have || (L >= 2 * W - 2 && (mid < 0 || (mid >= W - 1 && mid + K + 1 <= tl)));
+        if (__all_sync(FULL, regular)) {
+#pragma unroll 1
+            for (int part = 0; part < 2; part++) {
+                // part 0: p = tl + t, columns 0 .. W-2-t; part 1: p = mid-W+1 + t, N under column W-1-t
+                const int nt = part ? nt_n : nt_tail;
+                const bool mine = have && (part == 0 || mid >= 0);
+                const int p_first = part ? n0 : tl;
+                // window word of p_first (bases from p_first - KD) and the 16 bases behind it, advanced one base per step
+                int b0 = (mine ? p_first : 0) - KD;
+                uint32_t whi, wlo;
+                window_bits(wseq, b0, whi, wlo);
+                uint32_t nxt = wseq[(b0 >> 4) + 2] << (2 * (b0 & 15));       // bases b0+32 .. : 16 - (b0 & 15) of them left
+                int nleft = 16 - (b0 & 15);
+                int nw = (b0 >> 4) + 3;                                       // next stream word
+#pragma unroll 1
+                for (int t = 0; t < nt; t++) {
+                    const MaskedStep st = steps[part][t];
+                    const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
+                    float prod = 1.0f;
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        if ((st.good >> g) & 1u) prod *= lds_f32(group_offset<G, FAST>(gc, g, whi, wlo), gc.ab[g]);
+                    const int jn = W - 1 - t;                                 // part 1: column of the N
+                    for (uint32_t c = st.cols; c; c &= c - 1u) {
+                        const int j = __ffs(c) - 1;
+                        uint32_t y = field(w, 62 - 2 * KD - 2 * j, maskK);
+                        if (part && (uint32_t)(j - jn) <= (uint32_t)K) y = mine ? yp[j - jn] : 0u;
+                        prod *= lds_f32(((uint32_t)j * ystride + y) << 2, plain_s);
+                    }
+                    const float val = mine ? prod * pos : 0.0f;
+                    acc.add(val);
+                    em.template put<true>(al, val >= thr0, woff, pcode_of(p_first + t, part ? W - 1 : W - 2 - t, part != 0), val, li);
+                    // next base
+                    whi = __funnelshift_l(wlo, whi, 2); wlo = __funnelshift_l(nxt, wlo, 2); nxt <<= 2;
+                    if (--nleft == 0) { nxt = wseq[nw++]; nleft = 16; }
+                }
+            }
+        } else {
+            // generic route: every lane walks its own list of masked windows, masked_prod per window
+            const int nn = n1 - n0, nm = have ? nn + (LW1 - tl) : 0;
+            int nm_max = nm;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nm_max = max(nm_max, __shfl_xor_sync(FULL, nm_max, o));
+#pragma unroll 1
+            for (int idx = 0; idx < nm_max; idx++) {
+                const bool on = idx < nm;
+                const int p = on ? (idx < nn ? n0 + idx : tl + (idx - nn)) : 0;
+                uint32_t whi, wlo;
+                window_bits(wseq, p - KD, whi, wlo);
+                const int jmax = on ? min(W - 1, L - W - p) : -1;
+                const float prod = masked_prod<G, FAST>(gc, gp, mt, whi, wlo, p, jmax, mid, yp, 1.0f);
+                const float val = on ? prod * pos : 0.0f;
+                acc.add(val);
+                em.template put<true>(al, val >= thr0, woff, pcode_of(p, jmax, mid >= 0 && p <= mid + K && p + W - 1 >= mid), val, li);
+            }
+        }
+        if (have) seqacc[li] = make_ulonglong2(acc.a, acc.b);
+    }
+    al.cnt_back[warp] = em.bpos;
+}
+
 // ---- pruned E-step, part 2: exact evaluation of the listed windows -------------------------------------------------
 // gp is the exact plan of the dense kernel. Per sequence: the candidates in batches of 32, then the windows over the N and the
 // truncated tail (masked evaluation), then the normaliser. The stream words of the sequence (up to STAGE_SEQ_WORDS, i.e. about
@@ -443,7 +581,7 @@ template <int G, bool FAST>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
          const float* __restrict__ s_rows, uint32_t plain_words, uint32_t stage /* 0: no staging buffer */, CandList cl,
-         unsigned long long* __restrict__ scal, ActiveList al) {
+         const ulonglong2* __restrict__ seqacc, unsigned long long* __restrict__ scal, ActiveList al) {
     extern __shared__ float tab[];
     if (cl.flags[0] != 0u) return;
     for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
@@ -461,6 +599,7 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
     MaskedTabs mt; mt.s_g = s_g; mt.s_rows = s_rows; mt.plain_s = plain_words ? tab_s + gp.table_bytes : 0u;
     mt.Yn = gp.Yn; mt.maskK = gp.Yn - 1; mt.passmask = 0xffffffffu; mt.W = W; mt.K = K; mt.KD = KD;
     Emitter em; em.init(al, warp, true);
+    em.bpos = al.cnt_back[warp];                                        // the back of the region is k_emasked's
     uint32_t* const stg = reinterpret_cast<uint32_t*>(tab + (gp.table_bytes >> 2) + plain_smem_words(plain_words, gp.Yn)) + (threadIdx.x >> 5) * STAGE_WORDS;
     const uint32_t* __restrict__ creg = cl.ent + cl.reg_off[warp];
     uint32_t li = warp;
@@ -509,20 +648,7 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
                 acc.add(val);
                 em.template put<false>(al, val >= thr0, woff, pcode_of(p, W - 1, false), val, li);
             }
-            const int nn = n1 - n0, nm = nn + (LW1 - tl);
-#pragma unroll 1
-            for (int m0 = 0; m0 < nm; m0 += 32) {
-                const int idx = m0 + lane;
-                const bool on = idx < nm;
-                const int p = on ? (idx < nn ? n0 + idx : tl + (idx - nn)) : 0;
-                uint32_t whi, wlo;
-                window_bits(wsrc, p - KD, whi, wlo);
-                const int jmax = on ? min(W - 1, L - W - p) : -1;
-                const float prod = masked_prod<G, FAST>(gc, gp, mt, whi, wlo, p, jmax, mid, yp, 1.0f);
-                const float val = on ? prod * pos : 0.0f;
-                acc.add(val);
-                em.template put<true>(al, val >= thr0, woff, pcode_of(p, jmax, mid >= 0 && p <= mid + K && p + W - 1 >= mid), val, li);
-            }
+            if (lane == 0) { const ulonglong2 m = seqacc[li]; acc.a += m.x; acc.b += m.y; }      // the masked windows (k_emasked)
             finish_sequence(acc, one_minus_q, lane, li, al.scale, llh_fx, rsum_fx);
             if (!more) break;
             li = li_next; n = n_next; n_next = n_nn; sq = sq_next; sc = sc_next;
@@ -532,7 +658,7 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
         if (llh_fx) atomicAdd(&scal[0], (unsigned long long)llh_fx);
         if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);
     }
-    al.cnt[warp] = em.lpos; al.cnt_back[warp] = em.bpos;
+    al.cnt[warp] = em.lpos;
 }
 
 }  // namespace bamm
