@@ -510,6 +510,12 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
         NormAcc acc; acc.clear();
         const bool regular = !have || (L >= 2 * W - 2 && (mid < 0 || (mid >= W - 1 && mid + K + 1 <= tl)));
         if (__all_sync(FULL, regular)) {
+            // the K+1 patched k-mers of this lane's sequence, two per register (a load per use would touch 32 lines)
+            uint32_t ypk[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+            if (have && mid >= 0) {
+#pragma unroll
+                for (int d = 0; d < 12; d++) if (d <= K) ypk[d >> 1] |= (uint32_t)yp[d] << (16 * (d & 1));
+            }
 #pragma unroll 1
             for (int part = 0; part < 2; part++) {
                 // part 0: p = tl + t, columns 0 .. W-2-t; part 1: p = mid-W+1 + t, N under column W-1-t
@@ -535,7 +541,13 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
                     for (uint32_t c = st.cols; c; c &= c - 1u) {
                         const int j = __ffs(c) - 1;
                         uint32_t y = field(w, 62 - 2 * KD - 2 * j, maskK);
-                        if (part && (uint32_t)(j - jn) <= (uint32_t)K) y = mine ? yp[j - jn] : 0u;
+                        if (part && (uint32_t)(j - jn) <= (uint32_t)K) {          // warp-uniform: pick the register without indexing
+                            const int d = j - jn;
+                            uint32_t pk = ypk[0];
+#pragma unroll
+                            for (int q = 1; q < 6; q++) pk = (d >> 1) == q ? ypk[q] : pk;
+                            y = (pk >> (16 * (d & 1))) & 0xffffu;
+                        }
                         prod *= lds_f32(((uint32_t)j * ystride + y) << 2, plain_s);
                     }
                     const float val = mine ? prod * pos : 0.0f;
