@@ -458,13 +458,15 @@ k_ebound(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
 // (k_eexact starts from it), the windows that reach the threshold to the back of the warp's region of the active list.
 // Multiplication order = masked_prod's: whole groups ascending, then the remaining columns ascending.
 // Sequences whose ranges are clipped (shorter than 2W-2, N too close to an end) make their warp take the generic route.
-struct MaskedStep { uint32_t good, cols; };     // per window index: bit g = group g whole, bit j = column j from the plain table
+// per window index: bit g of good = group g whole; the other columns come from the plain table, in ascending order: the
+// unpatched ones below the N's k-mers (lo), the K+1 patched ones, the unpatched ones above (hi)
+struct MaskedStep { uint32_t good, lo, hi, pad; };
 template <int G, bool FAST>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
           uint32_t plain_words, CandList cl, ulonglong2* __restrict__ seqacc, ActiveList al) {
     extern __shared__ float tab[];
-    __shared__ MaskedStep steps[2][48];           // [0]: truncated windows t = p - tl, [1]: windows over the N, t = p - (mid-W+1)
+    __shared__ __align__(16) MaskedStep steps[2][48];   // [0]: truncated windows t = p - tl, [1]: windows over the N, t = p - (mid-W+1)
     if (cl.flags[0] != 0u) return;
     for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
     for (uint32_t i = threadIdx.x; i < plain_words; i += blockDim.x) tab[(gp.table_bytes >> 2) + i + i / gp.Yn] = s_g[i];   // rows padded by one float
@@ -478,7 +480,10 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
         const uint32_t bad = ~valid | ncols;
         uint32_t good = 0u, cols = valid;
         for (int g = 0; g < G; g++) if ((gp.colmask[g] & bad) == 0u) { good |= 1u << g; cols &= ~gp.colmask[g]; }
-        steps[which][t].good = good; steps[which][t].cols = cols;
+        cols &= ~ncols;                           // the patched columns have their own (unrolled) loop
+        const int jn = W - 1 - t;
+        const uint32_t below = which && jn > 0 ? ((1u << min(jn, 31)) - 1u) : (which ? 0u : 0xffffffffu);
+        steps[which][t].good = good; steps[which][t].lo = cols & below; steps[which][t].hi = cols & ~below; steps[which][t].pad = 0u;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -514,7 +519,7 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
             uint32_t ypk[6] = {0u, 0u, 0u, 0u, 0u, 0u};
             if (have && mid >= 0) {
 #pragma unroll
-                for (int d = 0; d < 12; d++) if (d <= K) ypk[d >> 1] |= (uint32_t)yp[d] << (16 * (d & 1));
+                for (int d = 0; d < 11; d++) if (d <= K) ypk[d >> 1] |= (uint32_t)yp[d] << (16 * (d & 1));
             }
 #pragma unroll 1
             for (int part = 0; part < 2; part++) {
@@ -537,19 +542,23 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
 #pragma unroll
                     for (int g = 0; g < G; g++)
                         if ((st.good >> g) & 1u) prod *= lds_f32(group_offset<G, FAST>(gc, g, whi, wlo), gc.ab[g]);
-                    const int jn = W - 1 - t;                                 // part 1: column of the N
-                    for (uint32_t c = st.cols; c; c &= c - 1u) {
-                        const int j = __ffs(c) - 1;
-                        uint32_t y = field(w, 62 - 2 * KD - 2 * j, maskK);
-                        if (part && (uint32_t)(j - jn) <= (uint32_t)K) {          // warp-uniform: pick the register without indexing
-                            const int d = j - jn;
-                            uint32_t pk = ypk[0];
-#pragma unroll
-                            for (int q = 1; q < 6; q++) pk = (d >> 1) == q ? ypk[q] : pk;
-                            y = (pk >> (16 * (d & 1))) & 0xffffu;
-                        }
+                    auto single = [&](int j) {                               // column j with the k-mer of the stream
+                        const uint32_t y = field(w, 62 - 2 * KD - 2 * j, maskK);
                         prod *= lds_f32(((uint32_t)j * ystride + y) << 2, plain_s);
+                    };
+                    for (uint32_t c = st.lo; c; c &= c - 1u) single(__ffs(c) - 1);
+                    if (part) {
+                        const int jn = W - 1 - t;                             // column of the N: patched k-mer d sits in column jn + d
+#pragma unroll
+                        for (int d = 0; d < 11; d++) {
+                            const int j = jn + d;
+                            if (d <= K && j >= 0 && j < W) {                  // warp-uniform
+                                const uint32_t y = (ypk[d >> 1] >> (16 * (d & 1))) & 0xffffu;
+                                prod *= lds_f32(((uint32_t)j * ystride + y) << 2, plain_s);
+                            }
+                        }
                     }
+                    for (uint32_t c = st.hi; c; c &= c - 1u) single(__ffs(c) - 1);
                     const float val = mine ? prod * pos : 0.0f;
                     acc.add(val);
                     em.template put<true>(al, val >= thr0, woff, pcode_of(p_first + t, part ? W - 1 : W - 2 - t, part != 0), val, li);
