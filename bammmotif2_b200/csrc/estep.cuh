@@ -49,8 +49,8 @@ struct NormAcc {
 
 // end of a sequence: normaliser, its reciprocal for the consumers of the unnormalised posteriors, log likelihood term
 // (EM.cpp:183-195) and sum of the posteriors (optimize_q, EM.cpp:505-519)
-__device__ __forceinline__ void finish_sequence(NormAcc acc, float one_minus_q, int lane, uint32_t li, float* __restrict__ scale,
-                                                long long& llh_fx, long long& rsum_fx) {
+__device__ __forceinline__ float finish_sequence(NormAcc acc, float one_minus_q, int lane, uint32_t li, float* __restrict__ scale,
+                                                 long long& llh_fx, long long& rsum_fx) {
     acc.warp_reduce();
     const double sd = acc.total();
     const float norm = (float)((double)one_minus_q + sd);
@@ -60,6 +60,7 @@ __device__ __forceinline__ void finish_sequence(NormAcc acc, float one_minus_q, 
         llh_fx += __double2ll_rn((double)logf(norm) * SC_SCALE_D);
         rsum_fx += __double2ll_rn((double)((float)sd * rnorm) * SC_SCALE_D);
     }
+    return norm;
 }
 
 // ---- window evaluation ---------------------------------------------------------------------------------------------
@@ -657,6 +658,12 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
             int n0 = tl, n1 = tl;
             if (mid >= 0) { n0 = min(max(mid - W + 1, 0), tl); n1 = min(mid + K + 1, tl); }
             NormAcc acc; acc.clear();
+            // Up to two batches are held back until the normaliser is known: a window whose posterior rounds to zero in the
+            // M-step's fixed point (val / norm < 2^-41; about a quarter of those above the a-priori threshold, because norm
+            // is large wherever the sequence holds a site) is then not listed at all. Longer lists are written as they come.
+            const bool defer = sc.y <= 64u;
+            float v0 = 0.0f, v1 = 0.0f;
+            int q0 = 0, q1 = 0;
 #pragma unroll 1
             for (uint32_t e0 = 0; e0 < sc.y; e0 += 32) {
                 const bool on = e0 + lane < sc.y;
@@ -667,10 +674,17 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
                 const float prod = groups_prod<G, FAST>(gc, whi, wlo, 1.0f);
                 const float val = on ? prod * pos : 0.0f;
                 acc.add(val);
-                em.template put<false>(al, val >= thr0, woff, pcode_of(p, W - 1, false), val, li);
+                if (!defer) em.template put<false>(al, val >= thr0, woff, pcode_of(p, W - 1, false), val, li);
+                else if (e0 == 0u) { v0 = val; q0 = p; }
+                else { v1 = val; q1 = p; }
             }
             if (lane == 0) { const ulonglong2 m = seqacc[li]; acc.a += m.x; acc.b += m.y; }      // the masked windows (k_emasked)
-            finish_sequence(acc, one_minus_q, lane, li, al.scale, llh_fx, rsum_fx);
+            const float norm = finish_sequence(acc, one_minus_q, lane, li, al.scale, llh_fx, rsum_fx);
+            if (defer && sc.y) {
+                const float thr = fmaxf(thr0, FX_HALF_UNIT * 0.999f * norm);
+                em.template put<false>(al, v0 >= thr, woff, pcode_of(q0, W - 1, false), v0, li);
+                if (sc.y > 32u) em.template put<false>(al, v1 >= thr, woff, pcode_of(q1, W - 1, false), v1, li);
+            }
             if (!more) break;
             li = li_next; n = n_next; n_next = n_nn; sq = sq_next; sc = sc_next;
         }

@@ -47,7 +47,7 @@ __device__ __forceinline__ void atoms_add_carry(uint32_t addr, uint32_t hioff, u
 constexpr int M_BATCH = 8;
 template <int NC, bool MASKED>
 __device__ __forceinline__ void scatter_cols(unsigned long long up, uint32_t maskK, uint32_t lo_s, uint32_t hi_off, uint32_t yn4,
-                                             uint32_t xlo, uint32_t xhi, int jrel_max) {
+                                             uint32_t xlo, uint32_t xhi, int jrel_max, int jmax_u = 31 /* warp-uniform bound of jrel_max */) {
     const uint32_t ulo = (uint32_t)up, uhi = (uint32_t)(up >> 32);
     const bool hi_nz = xhi != 0u;
 #pragma unroll
@@ -56,7 +56,7 @@ __device__ __forceinline__ void scatter_cols(unsigned long long up, uint32_t mas
 #pragma unroll
         for (int k = 0; k < M_BATCH; k++) {
             const int jj = g0 + k;
-            if (jj < NC) {
+            if (jj < NC && (!MASKED || jj <= jmax_u)) {                    // columns no lane of the warp has are skipped (uniform)
                 const int sh = 2 * (NC - 1 - jj);
                 const uint32_t y = (sh >= 32 ? (uhi >> (sh - 32)) : __funnelshift_r(ulo, uhi, sh)) & maskK;
                 adr[k] = lo_s + (uint32_t)jj * yn4 + (y << 2);
@@ -66,7 +66,7 @@ __device__ __forceinline__ void scatter_cols(unsigned long long up, uint32_t mas
 #pragma unroll
         for (int k = 0; k < M_BATCH; k++) {
             const int jj = g0 + k;
-            if (jj < NC) {
+            if (jj < NC && (!MASKED || jj <= jmax_u)) {
                 const bool on = !MASKED || jj <= jrel_max;
                 const bool carry = on && (uint32_t)~old[k] < xlo;          // old + xlo wrapped
                 if (carry || (on && hi_nz)) reds_add(adr[k] + hi_off, xhi + (carry ? 1u : 0u));
@@ -178,7 +178,8 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
                 }
             }
             __syncwarp();
-            scatter_cols<NC, true>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), jrel_max);
+            // the truncated windows arrive sorted by their last column (k_emasked lists them window index by window index)
+            scatter_cols<NC, true>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), jrel_max, __reduce_max_sync(FULL, jrel_max));
         }
     }
     __syncthreads();
