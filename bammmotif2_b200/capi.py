@@ -55,6 +55,7 @@ SIGNATURES = {
     "bamm_em_r_size": (C.c_uint64, [_vp]),
     "bamm_em_last_timing": (C.c_int, [_vp, _f32p, _f32p]),
     "bamm_em_loop_timing": (C.c_int, [_vp, C.POINTER(C.c_int), _f32p, _f32p, _f32p, _f32p]),
+    "bamm_em_loop_timing_estep": (C.c_int, [_vp, _f32p, _f32p, _f32p]),
     "bamm_em_set_exchange_buffer": (C.c_int, [_vp, _vp, C.c_uint64]),
     "bamm_em_launch_count": (C.c_int, [_vp, _u64p]),
     "bamm_em_estep_info": (C.c_int, [_vp, _u64p]),
@@ -376,6 +377,12 @@ class EM:
         e, m, up, t = C.c_float(0), C.c_float(0), C.c_float(0), C.c_float(0)
         _check(load().bamm_em_loop_timing(self.h, C.byref(it), C.byref(e), C.byref(m), C.byref(up), C.byref(t)))
         return it.value, e.value, m.value, up.value, t.value
+
+    def loop_timing_estep(self):
+        """(masked_ms, bound_ms, exact_ms): the E-step share of loop_timing() by kernel of the pruned path."""
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        _check(load().bamm_em_loop_timing_estep(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def launch_count(self):
         n = C.c_uint64(0)

@@ -156,7 +156,7 @@ struct bamm_em {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    std::vector<cudaEvent_t> loop_ev;       // 4 per iteration of the last bamm_em_iterate call: E | M accumulate | reduce+update
+    std::vector<cudaEvent_t> loop_ev;       // LOOP_EV per iteration of the last bamm_em_iterate call (capi_em.inl, launch_iteration)
     int loop_iters = 0;
     bool own_xbuf = true;
     int W = 0, K = 0, K_bg_model = 0, K_bg = 0, A = 4;

@@ -613,7 +613,7 @@ static PackedView pview_of(const bamm_em* em) {
     return pv;
 }
 
-static int launch_estep(bamm_em* em) {
+static int launch_estep(bamm_em* em, cudaEvent_t* split = nullptr /* 2 events: after the masked windows, after the bounds */) {
     em->launches += 1 + (em->npk ? em->gplans.size() + (em->sparse ? 3 : 0) : 0) + (em->ngen ? 1 : 0);
     unsigned long long* scal = em->d_xbuf + em->nbin;
     k_estep_begin<<<1, 32, 0, em->stream>>>(scal, em->d_overflow, em->d_eflags);
@@ -631,12 +631,15 @@ static int launch_estep(bamm_em* em) {
             const GroupPlan gp = plan_for_launch(em, 0, em->q);
             if (launch_estep_masked(l, false, em->gfast[0] != 0, &pv, gp, em->d_tab, em->d_s, em->plain_words, &cl, em->d_seqacc, &al))
                 return fail(BAMM_E_CUDA, "E-step launch failed (masked windows)");
+            if (split) CU(cudaEventRecord(split[0], em->stream));
             if (launch_estep_bound(l, false, em->bfast, &pv, bp, em->d_btab, &cl)) return fail(BAMM_E_CUDA, "E-step launch failed (bounds)");
+            if (split) CU(cudaEventRecord(split[1], em->stream));
             if (launch_estep_exact(l, false, em->gfast[0] != 0, &pv, gp, em->d_tab, em->d_s, em->d_sT, em->plain_words, em->stage, &cl, em->d_seqacc, scal, &al))
                 return fail(BAMM_E_CUDA, "E-step launch failed (candidates)");
             if (launch_estep_dense(l, false, em->gfast[0] != 0, false, &pv, gp, em->d_tab, em->d_s, em->d_sT, em->plain_words, em->d_r, scal, &al, em->d_eflags))
                 return fail(BAMM_E_CUDA, "packed E-step launch failed");
         } else {
+            if (split) { CU(cudaEventRecord(split[0], em->stream)); CU(cudaEventRecord(split[1], em->stream)); }
             for (size_t pass = 0; pass < em->gplans.size(); pass++)
                 if (launch_estep_dense(l, false, em->gfast[pass] != 0, multi, &pv, plan_for_launch(em, pass, em->q), (const float*)((const char*)em->d_tab + pass * em->tab_capacity),
                                        em->d_s, em->d_sT, em->plain_words, em->d_r, scal, &al, nullptr))
@@ -994,16 +997,19 @@ extern "C" int bamm_em_mask(bamm_em* em, float f, float epsilon, int max_iter, i
     return BAMM_OK;
 }
 
-// launches of one iteration with optional event brackets (ev4 = 4 events or nullptr)
-static int launch_iteration(bamm_em* em, cudaEvent_t* ev4) {
-    if (ev4) CU(cudaEventRecord(ev4[0], em->stream));
-    int rc = launch_estep(em); if (rc) return rc;
-    if (ev4) CU(cudaEventRecord(ev4[1], em->stream));
+// launches of one iteration with optional event brackets (ev = LOOP_EV events or nullptr):
+// start | masked windows | bounds | rest of the E-step | M-step accumulation | reduce + update
+constexpr int LOOP_EV = 6;
+static int launch_iteration(bamm_em* em, cudaEvent_t* ev) {
+    if (ev) CU(cudaEventRecord(ev[0], em->stream));
+    int rc = launch_estep(em, ev ? ev + 1 : nullptr); if (rc) return rc;
+    if (ev && !em->npk) { CU(cudaEventRecord(ev[1], em->stream)); CU(cudaEventRecord(ev[2], em->stream)); }
+    if (ev) CU(cudaEventRecord(ev[3], em->stream));
     rc = launch_mstep_accumulate(em); if (rc) return rc;
-    if (ev4) CU(cudaEventRecord(ev4[2], em->stream));
+    if (ev) CU(cudaEventRecord(ev[4], em->stream));
     rc = launch_mstep_reduce(em); if (rc) return rc;
     rc = launch_update(em); if (rc) return rc;
-    if (ev4) CU(cudaEventRecord(ev4[3], em->stream));
+    if (ev) CU(cudaEventRecord(ev[5], em->stream));
     return BAMM_OK;
 }
 
@@ -1012,10 +1018,10 @@ extern "C" int bamm_em_iterate(bamm_em* em, int n_iter, float* llh_last, float* 
     if (!em->model_set) return fail(BAMM_E_STATE, "bamm_em_set_model has not been called");
     REQUIRE(n_iter >= 0, "n_iter must be >= 0");
     CU(cudaSetDevice(em->device));
-    while ((int)em->loop_ev.size() < 4 * n_iter) { cudaEvent_t e; CU(cudaEventCreate(&e)); em->loop_ev.push_back(e); }
+    while ((int)em->loop_ev.size() < LOOP_EV * n_iter) { cudaEvent_t e; CU(cudaEventCreate(&e)); em->loop_ev.push_back(e); }
     em->loop_iters = 0;
     for (int it = 0; it < n_iter; it++) {
-        int rc = launch_iteration(em, &em->loop_ev[4 * it]); if (rc) return rc;
+        int rc = launch_iteration(em, &em->loop_ev[LOOP_EV * it]); if (rc) return rc;
     }
     em->loop_iters = n_iter;
     em->r_valid = n_iter > 0 || em->r_valid;
@@ -1025,23 +1031,39 @@ extern "C" int bamm_em_iterate(bamm_em* em, int n_iter, float* llh_last, float* 
     return BAMM_OK;
 }
 
-extern "C" int bamm_em_loop_timing(bamm_em* em, int* iters, float* estep_ms, float* maccum_ms, float* update_ms, float* total_ms) {
-    REQUIRE(em, "em is NULL");
+static int loop_times(bamm_em* em, float out[5], float* total) {
     CU(cudaSetDevice(em->device));
     CU(cudaStreamSynchronize(em->stream));
-    float e = 0, m = 0, u = 0, t = 0, x;
+    for (int k = 0; k < 5; k++) out[k] = 0.0f;
+    float x;
     for (int it = 0; it < em->loop_iters; it++) {
-        cudaEvent_t* ev = &em->loop_ev[4 * it];
-        CU(cudaEventElapsedTime(&x, ev[0], ev[1])); e += x;
-        CU(cudaEventElapsedTime(&x, ev[1], ev[2])); m += x;
-        CU(cudaEventElapsedTime(&x, ev[2], ev[3])); u += x;
+        cudaEvent_t* ev = &em->loop_ev[LOOP_EV * it];
+        for (int k = 0; k < 5; k++) { CU(cudaEventElapsedTime(&x, ev[k], ev[k + 1])); out[k] += x; }
     }
-    if (em->loop_iters) CU(cudaEventElapsedTime(&t, em->loop_ev[0], em->loop_ev[4 * em->loop_iters - 1]));
+    *total = 0.0f;
+    if (em->loop_iters) CU(cudaEventElapsedTime(total, em->loop_ev[0], em->loop_ev[LOOP_EV * em->loop_iters - 1]));
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_loop_timing(bamm_em* em, int* iters, float* estep_ms, float* maccum_ms, float* update_ms, float* total_ms) {
+    REQUIRE(em, "em is NULL");
+    float t[5], tot;
+    int rc = loop_times(em, t, &tot); if (rc) return rc;
     if (iters) *iters = em->loop_iters;
-    if (estep_ms) *estep_ms = e;
-    if (maccum_ms) *maccum_ms = m;
-    if (update_ms) *update_ms = u;
-    if (total_ms) *total_ms = t;
+    if (estep_ms) *estep_ms = t[0] + t[1] + t[2];
+    if (maccum_ms) *maccum_ms = t[3];
+    if (update_ms) *update_ms = t[4];
+    if (total_ms) *total_ms = tot;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_loop_timing_estep(bamm_em* em, float* masked_ms, float* bound_ms, float* exact_ms) {
+    REQUIRE(em, "em is NULL");
+    float t[5], tot;
+    int rc = loop_times(em, t, &tot); if (rc) return rc;
+    if (masked_ms) *masked_ms = t[0];
+    if (bound_ms) *bound_ms = t[1];
+    if (exact_ms) *exact_ms = t[2];
     return BAMM_OK;
 }
 

@@ -67,8 +67,8 @@ def peaks():
 
 
 def measured_traffic(workload, nseq, mstep_dominant):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json,
-    written by tools/ncu_traffic.py); only valid for the workload and size that capture was taken on."""
+    """DRAM bytes per iteration of the dominant phase (all its kernels) from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py); only valid for the workload and size that capture was taken on."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         t = json.load(open(p))
@@ -569,14 +569,30 @@ def main():
     roof = None
     if world == 1:
         iters, e_ms, m_ms, u_ms, _ = em.loop_timing()
+        mk_ms, bd_ms, ex_ms = em.loop_timing_estep()
+        info = em.estep_info()
         peak, peak_src = peaks()
-        dom_name, dom_ms = ("k_mstep (M-step accumulation)", m_ms) if m_ms >= e_ms else ("k_estep (E-step)", e_ms)
-        bytes_per_launch = 6.0 * pos_local          # ALGORITHMIC: 2 B k-mer index + 4 B r per position, per kernel
-        ach = bytes_per_launch / (dom_ms / iters * 1e-3) / 1e9
+        # 12 B per position and iteration = E-step (2 B k-mer index + 4 B r) + M-step (2 B index + 4 B r). The E-step is
+        # the dominant phase; on the pruned path it is three kernels, of which the bound pass touches every position.
+        e_dom = e_ms >= m_ms
+        bytes_phase = 6.0 * pos_local
+        dom_ms = e_ms if e_dom else m_ms
+        ach = bytes_phase / (dom_ms / iters * 1e-3) / 1e9
+        if info["pruned"]:
+            dom_name = "E-step = k_emasked + k_ebound + k_eexact (pruned path, G=%d exact / G1=%d bound groups)" % (info["G"], info["G_bound"])
+        else:
+            dom_name = "E-step = k_estep_packed (dense, G=%d groups, %d pass(es))" % (info["G"], info["passes"])
+        if not e_dom:
+            dom_name = "M-step accumulation (k_mstep_list_w / k_mstep_scan_w)"
+        traffic = measured_traffic(args.workload, nseq, not e_dom)
         roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": measured_traffic(args.workload, nseq, m_ms >= e_ms), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_phase,
+                "convention": "algorithmic bytes of the phase (6 B per stored position: 2 B k-mer index + 4 B posterior) / its mean device time per iteration",
                 "estep_ms": e_ms / iters, "mstep_accum_ms": m_ms / iters, "reduce_update_ms": u_ms / iters,
+                "estep_kernels_ms": {"k_emasked": mk_ms / iters, "k_ebound": bd_ms / iters, "k_eexact": ex_ms / iters},
+                "k_ebound_index_GBps": (2.0 * pos_local / (bd_ms / iters * 1e-3) / 1e9) if bd_ms > 0 else None,
+                "candidates_frac": info["candidates"] / float(pos_local), "active_frac": info["active"] / float(pos_local),
+                "dense_fallback": bool(info["dense_ran"]) if info["pruned"] else None,
                 "whole_iteration_frac_of_12B_roofline": (12.0 * pos_local / (ms_total / args.steps * 1e-3) / 1e9) / peak}
     llh_after = None
     if world == 1:

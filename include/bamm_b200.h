@@ -147,6 +147,10 @@ int bamm_em_last_timing(bamm_em* em, float* estep_ms, float* mstep_ms);
 /* device times of the last bamm_em_iterate call, summed over its iterations (CUDA events on the EM stream):
  * E-step kernel, M-step accumulation kernel, reduce + model update, and first-launch-to-last-completion. */
 int bamm_em_loop_timing(bamm_em* em, int* iters, float* estep_ms, float* maccum_ms, float* update_ms, float* total_ms);
+/* the E-step share of bamm_em_loop_timing by kernel of the pruned path: the windows over the N and the
+ * truncated windows (k_emasked), the bound pass (k_ebound), the exact pass over the candidates (k_eexact, plus the dense
+ * kernel when it ran). Without the pruned path the whole E-step is in exact_ms. */
+int bamm_em_loop_timing_estep(bamm_em* em, float* masked_ms, float* bound_ms, float* exact_ms);
 /* number of CUDA kernels this object has launched so far (E-step, M-step, reduce, update, table kernels) */
 int bamm_em_launch_count(bamm_em* em, uint64_t* kernels);
 /* how the last E-step of the packed path ran (diagnostics; synchronises the EM stream). The per-position loop of EM::EStep
