@@ -68,6 +68,7 @@ SIGNATURES = {
     "bamm_em_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "bamm_em_peer_alloc": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "bamm_em_peer_attach": (C.c_int, [_vp, _vp]),
+    "bamm_em_peer_wait": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), _u64p]),
     "bamm_score_last_timing": (C.c_int, [_f32p]),
     "bamm_seqset_sample_pwm_sites": (C.c_int, [_vp, _u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, _f32p, C.c_float, C.POINTER(C.c_double), C.POINTER(C.c_int32), _u64p]),
     "bamm_sort_scores": (C.c_int, [_f32p, C.c_uint64, C.c_int]),
@@ -415,6 +416,12 @@ class EM:
         buf = C.create_string_buffer(64)
         _check(load().bamm_em_peer_alloc(self.h, rank, world, C.cast(buf, _vp)))
         return buf.raw
+
+    def peer_wait(self, reset=True):
+        """(total_ms, waits): device time spent waiting for the slowest rank in the peer exchange since the last reset."""
+        ms, n = C.c_double(0), C.c_uint64(0)
+        _check(load().bamm_em_peer_wait(self.h, int(reset), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def peer_attach(self, handles):
         """handles: world x 64 bytes (rank order). Afterwards mstep_local pushes to every rank over NVLink."""

@@ -19,7 +19,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     cudaSetDevice(em->device);
     if (em->stream) cudaStreamSynchronize(em->stream);
     for (int p = 0; p < MAX_PEERS; p++) if (em->peer_mapped[p]) cudaIpcCloseMemHandle(em->peer_mapped[p]);
-    cudaFree(em->d_peer_local); cudaFree(em->d_peer_done);
+    cudaFree(em->d_peer_local); cudaFree(em->d_peer_done); cudaFree(em->d_peer_wait);
     cudaFree(em->d_act); cudaFree(em->d_scale); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
     cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab); cudaFree(em->d_tab_alt);
     cudaFree(em->d_btab); cudaFree(em->d_U); cudaFree(em->d_cand); cudaFree(em->d_cand_seq); cudaFree(em->d_seqacc); cudaFree(em->d_creg_off); cudaFree(em->d_eflags);
@@ -726,7 +726,7 @@ static int launch_mstep_reduce(bamm_em* em) {
         CU(cudaGetLastError());
         const size_t slot_bytes = (size_t)2 * em->peer_world * words * sizeof(unsigned long long);
         k_peer_sum<<<(words + 255) / 256, 256, 0, em->stream>>>((const unsigned long long*)em->d_peer_local, (const unsigned int*)(em->d_peer_local + slot_bytes),
-                                                                em->peer_world, em->nbin, parity, em->peer_epoch, em->d_xbuf);
+                                                                em->peer_world, em->nbin, parity, em->peer_epoch, em->d_xbuf, em->d_peer_wait);
         CU(cudaGetLastError());
         em->launches += 1;
         return BAMM_OK;
@@ -1180,12 +1180,27 @@ extern "C" int bamm_em_peer_alloc(bamm_em* em, int rank, int world, void* ipc_ha
     CU(cudaMemset(em->d_peer_local, 0, bytes));
     CU(cudaMalloc(&em->d_peer_done, sizeof(unsigned int)));
     CU(cudaMemset(em->d_peer_done, 0, sizeof(unsigned int)));
+    CU(cudaMalloc(&em->d_peer_wait, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(em->d_peer_wait, 0, 2 * sizeof(unsigned long long)));
     CU(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, em->d_peer_local));
     static_assert(sizeof(h) == 64, "CUDA IPC handle size");
     memcpy(ipc_handle_out, &h, sizeof(h));
     em->peer_rank = rank; em->peer_world = world;
+    return BAMM_OK;
+}
+
+extern "C" int bamm_em_peer_wait(bamm_em* em, int reset, double* total_ms, uint64_t* waits) {
+    REQUIRE(em && total_ms && waits, "NULL argument");
+    *total_ms = 0.0; *waits = 0;
+    if (!em->d_peer_wait) return BAMM_OK;
+    CU(cudaSetDevice(em->device));
+    CU(cudaStreamSynchronize(em->stream));
+    unsigned long long w[2] = {0, 0};
+    CU(cudaMemcpy(w, em->d_peer_wait, sizeof(w), cudaMemcpyDeviceToHost));
+    *total_ms = (double)w[0] * 1e-6; *waits = w[1];
+    if (reset) CU(cudaMemset(em->d_peer_wait, 0, sizeof(w)));
     return BAMM_OK;
 }
 

@@ -277,14 +277,24 @@ __global__ void k_reduce_push(const unsigned long long* __restrict__ part, uint3
     }
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// wait_acc: nullptr, or two counters — nanoseconds CTA 0 spent waiting for the slowest rank (summed) and the number of waits
 __global__ void k_peer_sum(const unsigned long long* __restrict__ slots /* [2][world][words] local */, const unsigned int* flags /* [world] local */,
-                           int world, uint32_t nbin, uint32_t parity, uint32_t epoch, unsigned long long* __restrict__ xbuf) {
+                           int world, uint32_t nbin, uint32_t parity, uint32_t epoch, unsigned long long* __restrict__ xbuf,
+                           unsigned long long* __restrict__ wait_acc) {
     const uint32_t words = nbin + 2;
+    const bool timed = wait_acc != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    const unsigned long long t0 = timed ? global_timer_ns() : 0ull;
     if (threadIdx.x < (unsigned)world) {
         const volatile unsigned int* f = flags + threadIdx.x;
         while ((int)(*f - epoch) < 0) __nanosleep(200);      // epochs only grow; wrap-safe comparison
     }
     __syncthreads();
+    if (timed) { wait_acc[0] += global_timer_ns() - t0; wait_acc[1] += 1ull; }
     __threadfence_system();
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= words) return;

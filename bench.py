@@ -16,6 +16,7 @@ JSON keys follow the driver's contract; extra objects:
 `--impl reference` times only the CPU reference arm on the same workload definition (bounded sample per step).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -52,6 +53,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling run (one set split over the ranks)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="sequences in the CPU sample (default by workload)")
     return ap.parse_args()
 
@@ -483,7 +485,7 @@ def main():
     nseq = args.nseq or wl["nseq"]
     A = 4
     # every rank holds a shard of ONE data set: same planted motif and binding sites, its own sequences
-    data = make_data(wl, nseq, args.seed + 1000 * rank, pinned=True, motif_seed=args.seed if world > 1 else None)
+    data = make_data(wl, nseq, args.seed + 1000 * rank, pinned=True, motif_seed=args.seed)
     bp_local = nseq * wl["L0"]
     pos_local = nseq * data["L"]
     bp_total = bp_local * world
@@ -527,8 +529,8 @@ def main():
             exchange = "nccl all-reduce (int64)"
 
     def run_iters(n):
-        if world == 1:
-            em.iterate(n)
+        if world == 1 or xt is None:
+            em.iterate(n)          # the loop runs inside the library (bamm_em_iterate); with peers attached the exchange is part of it
             return
         with torch.cuda.stream(stream):
             for _ in range(n):
@@ -541,12 +543,14 @@ def main():
 
     run_iters(args.warmup)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()              # before the barrier: starting NVML takes milliseconds, which the other ranks would spend waiting
+    if world > 1:
+        if xt is None:
+            em.peer_wait(reset=True)  # waits of the warm-up (ranks arrive at different times) do not count
+        dist.barrier()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = em.launch_count()
     e0.record(stream)
@@ -564,6 +568,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     value = bp_total * args.steps / (ms_total * 1e-3)
+    model_sha1 = hashlib.sha1(em.model().tobytes()).hexdigest()
+    per_rank = None
+    if world > 1:
+        # every rank's own device times of the timed loop and its wait for the slowest rank inside the exchange
+        it_r, e_r, m_r, u_r, tot_r = em.loop_timing() if xt is None else (args.steps, 0.0, 0.0, 0.0, e0.elapsed_time(e1))
+        wait_ms, waits = em.peer_wait(reset=True) if xt is None else (0.0, 0)
+        mine = torch.tensor([e_r / max(it_r, 1), m_r / max(it_r, 1), u_r / max(it_r, 1), tot_r / max(it_r, 1), wait_ms / max(waits, 1)], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        cols = ["estep_ms", "mstep_accum_ms", "reduce_exchange_update_ms", "iteration_ms", "peer_wait_ms"]
+        per_rank = {c: [round(float(t[i].item()), 4) for t in allr] for i, c in enumerate(cols)}
+        per_rank["note"] = "peer_wait_ms: mean wait for the slowest rank per exchange of the timed loop (device clock, CTA 0 of k_peer_sum)"
+        # identical models on every rank (integer exchange): all ranks must hold the same bits
+        hs = [None] * world
+        dist.all_gather_object(hs, model_sha1)
+        per_rank["models_identical"] = len(set(hs)) == 1
 
     # per-kernel device times (CUDA events on the EM stream, recorded by the library inside the timed loop)
     roof = None
@@ -597,6 +617,44 @@ def main():
     llh_after = None
     if world == 1:
         llh_after = em.iterate(0)[0]
+
+    # ---- strong scaling: ONE set of wl["nseq"] sequences (rank 0's data) split into contiguous blocks over the ranks -----------
+    strong = None
+    if world > 1 and not args.no_strong:
+        em.close(); ss.close()
+        torch.cuda.synchronize()
+        full = data if rank == 0 else make_data(wl, nseq, args.seed, pinned=False, motif_seed=args.seed)
+        lo, hi = (rank * nseq) // world, ((rank + 1) * nseq) // world          # equal lengths: contiguous blocks of equal size
+        L = full["L"]
+        codes_s = np.ascontiguousarray(full["codes"][lo:hi])
+        sel = (full["ppos"] >= np.uint64(lo * L)) & (full["ppos"] < np.uint64(hi * L))
+        offs = np.arange(hi - lo + 1, dtype=np.uint64) * np.uint64(L)
+        ss = capi.SeqSet(codes_s.reshape(-1), offs, A, full["ppos"][sel] - np.uint64(lo * L), full["pkmer"][sel])
+        v0s, vbgs, alphas = initial_model(capi, ss, wl, full["sites"], sum_over_ranks)
+        em = capi.EM(ss, wl["W"], wl["K"], wl["K_bg"])
+        em.set_model(v0s, vbgs, alphas, Q)
+        em.set_global_nseq(nseq)
+        xt_keep, xt = xt, None
+        if attach_peers(em):
+            em.iterate(args.warmup)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            st = torch.cuda.ExternalStream(em.stream(), device=torch.device("cuda", local_rank))
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(st)
+            em.iterate(args.steps)
+            s1.record(st)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            t = torch.tensor([s0.elapsed_time(s1)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_strong = float(t.item()) / args.steps
+            hs = [None] * world
+            dist.all_gather_object(hs, hashlib.sha1(em.model().tobytes()).hexdigest())
+            strong = {"what": "the %d sequences of rank 0's set in %d contiguous blocks, same iterations from the same initial model" % (nseq, world),
+                      "ms_per_step": ms_strong, "value": nseq * wl["L0"] / (ms_strong * 1e-3), "unit": UNIT,
+                      "model_sha1": hs[0], "models_identical": len(set(hs)) == 1,
+                      "compare": "model_sha1 equals the N=1 line's model_sha1 when the sharded model is bit-identical to the single-GPU one"}
+        xt = xt_keep
+        del full
 
     # ---- end-to-end through the C ABI from host buffers -------------------------------------------------------
     e2e = None
@@ -676,6 +734,11 @@ def main():
             line["cpu_baseline"] = cpu
         if llh_after is not None:
             line["config"]["llh_after"] = llh_after
+        line["model_sha1"] = model_sha1 if world == 1 else None
+        if per_rank:
+            line["per_rank"] = per_rank
+        if strong:
+            line["strong"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

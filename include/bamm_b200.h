@@ -190,6 +190,9 @@ int bamm_em_finish_iteration(bamm_em* em, int optimize_q, float* llh, float* vdi
  */
 int bamm_em_peer_alloc(bamm_em* em, int rank, int world, void* ipc_handle_out /* 64 bytes */);
 int bamm_em_peer_attach(bamm_em* em, const void* ipc_handles /* world * 64 bytes */);
+/* time this rank's device spent waiting for the slowest rank before it could sum the exchanged counts (the per-iteration
+ * all-reduce of EM::MStep's n), summed over the iterations since the last reset, and the number of waits */
+int bamm_em_peer_wait(bamm_em* em, int reset, double* total_ms, uint64_t* waits);
 /* CUDA stream (cudaStream_t as void*) the EM object launches on, so callers can order collectives after it */
 int bamm_em_stream(bamm_em* em, void** stream);
 
