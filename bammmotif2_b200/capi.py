@@ -55,6 +55,8 @@ SIGNATURES = {
     "bamm_em_r_size": (C.c_uint64, [_vp]),
     "bamm_em_last_timing": (C.c_int, [_vp, _f32p, _f32p]),
     "bamm_em_loop_timing": (C.c_int, [_vp, C.POINTER(C.c_int), _f32p, _f32p, _f32p, _f32p]),
+    "bamm_set_device_group": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "bamm_get_device_group": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "bamm_em_loop_timing_estep": (C.c_int, [_vp, _f32p, _f32p, _f32p]),
     "bamm_em_set_exchange_buffer": (C.c_int, [_vp, _vp, C.c_uint64]),
     "bamm_em_launch_count": (C.c_int, [_vp, _u64p]),
@@ -113,6 +115,12 @@ def model_size(A, K, W):
 
 def bg_size(A, K):
     return sum(A ** (k + 1) for k in range(K + 1))
+
+
+def set_device_group(devices):
+    """Devices one process drives together (bamm_set_device_group); [] or one device switches the group off."""
+    arr = (C.c_int * max(len(devices), 1))(*devices)
+    _check(load().bamm_set_device_group(arr, len(devices)))
 
 
 def device_count():

@@ -141,6 +141,7 @@ struct bamm_seqset {
     // sets encoded from FASTA text on the device: stored positions of the forward undefined bases, until the patches arrive
     uint64_t* d_zero_pos = nullptr;
     uint64_t n_zero_fwd = 0;
+    std::map<int, bamm_seqset*> replicas;   // device -> copy of this set on that device (device groups, capi_group.inl)
     // bamm_seqset_create: the uploads run on their own stream while the host checks the offsets and the first kernels start
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_codes = nullptr, ev_patches = nullptr;
@@ -152,6 +153,11 @@ static void seqset_copy_done(bamm_seqset* s) {      // waits for the uploads and
 }
 
 struct bamm_em {
+    // device group: a non-empty list makes this object a facade (no device state of its own) over one object per device, each
+    // over a contiguous block of the subset; shard_first[d] = first subset position of shard d (capi_group.inl)
+    std::vector<bamm_em*> shards;
+    std::vector<uint64_t> shard_first;
+    bool peer_sums_global = false;   // the scalars in d_xbuf are sums over all ranks (after an exchange), not this rank's own
     bamm_seqset* ss = nullptr;
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -433,6 +439,8 @@ extern "C" int bamm_seqset_create(const uint8_t* codes, const uint64_t* offsets,
 
 extern "C" void bamm_seqset_destroy(bamm_seqset* s) {
     if (!s) return;
+    for (auto& kv : s->replicas) bamm_seqset_destroy(kv.second);
+    s->replicas.clear();
     cudaSetDevice(s->device);
     for (auto& kv : s->index) cudaFree(kv.second.d);
     for (auto& kv : s->ypatch) cudaFree(kv.second);
@@ -556,6 +564,7 @@ extern "C" int bamm_seqset_count_kmers(bamm_seqset* s, int K, uint64_t* n_all) {
 
 // The entry points, by subject (one translation unit; the order matters: later parts use the helpers of earlier ones)
 #include "capi_em.inl"
+#include "capi_group.inl"
 #include "capi_negatives.inl"
 #include "capi_score.inl"
 #include "capi_fasta.inl"

@@ -1,6 +1,18 @@
 // capi_em.inl — part of capi.cu (one translation unit: included there, in this order).
 // EM objects: column-group planner, create / set_model, E-step / M-step / update launches, optimize, mask, NVLink peer exchange
 // ------------------------------------------------------------------------------------------- EM
+// device groups (capi_group.inl): an EM object over several devices is a facade over one shard object per device
+static bool group_wanted(const bamm_seqset* s, uint64_t nsub);
+static int group_create(bamm_seqset* s, const uint64_t* subset, uint64_t nsub, int W, int K, int K_bg_model, bamm_em** out);
+static void group_destroy(bamm_em* em);
+static int group_set_model(bamm_em* em, const float* v_all, const float* vbg_all, const float* alpha, float q);
+static int group_optimize(bamm_em* em, int optimize_q, float epsilon, int max_iter, int* iterations, float* llh_trace, float* vdiff_trace, float* q_trace);
+static int group_iterate(bamm_em* em, int n_iter, float* llh_last, float* vdiff_last);
+static int group_estep(bamm_em* em, float* llh);
+static int group_mstep(bamm_em* em);
+static int group_get_r(bamm_em* em, uint64_t first, uint64_t count, float* out);
+#define IS_GROUP(em) ((em) && !(em)->shards.empty())
+#define NOT_FOR_GROUPS(em, what) REQUIRE(!IS_GROUP(em), what " is not available on an EM object that spans a device group")
 static void fill_dims(ModelDims& d, int A, int K, int W, int K_bg) {
     memset(&d, 0, sizeof(d));
     d.A = A; d.K = K; d.W = W; d.K_bg = K_bg;
@@ -16,6 +28,7 @@ static void fill_dims(ModelDims& d, int A, int K, int W, int K_bg) {
 
 extern "C" void bamm_em_destroy(bamm_em* em) {
     if (!em) return;
+    if (IS_GROUP(em)) { group_destroy(em); return; }
     cudaSetDevice(em->device);
     if (em->stream) cudaStreamSynchronize(em->stream);
     for (int p = 0; p < MAX_PEERS; p++) if (em->peer_mapped[p]) cudaIpcCloseMemHandle(em->peer_mapped[p]);
@@ -246,6 +259,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     REQUIRE(K >= 0 && K <= 10 && K_bg_model >= 0 && K_bg_model <= 10, "order out of range");
     Trace tr("em_create");
     if (!subset) nsub = s->nseq;
+    if (group_wanted(s, nsub)) return group_create(s, subset, nsub, W, K, K_bg_model, out);
     REQUIRE(nsub < (1ull << 32), "subset too large");
     const uint64_t Yn64 = ipow_u64((uint64_t)s->A, K + 1);
     REQUIRE(Yn64 * (uint64_t)W < (1ull << 31), "table too large");
@@ -522,6 +536,7 @@ static bool leading_columns_are_copies(const ModelDims& dims, int K, int W, uint
 
 extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* vbg_all, const float* alpha, float q) {
     REQUIRE(em && v_all && vbg_all && alpha, "NULL argument");
+    if (IS_GROUP(em)) return group_set_model(em, v_all, vbg_all, alpha, q);
     REQUIRE(q > 0.0f && q < 1.0f, "q=%g not in (0,1)", (double)q);
     CU(cudaSetDevice(em->device));
     Trace tr("set_model");
@@ -650,6 +665,7 @@ static int launch_estep(bamm_em* em, cudaEvent_t* split = nullptr /* 2 events: a
         CU(cudaGetLastError());
     }
     em->d_s_e = em->d_s; em->d_sT_e = em->d_sT; em->d_tab_e = em->d_tab; em->q_e = em->q;
+    em->peer_sums_global = false;
     if (em->ngen) {
         IndexArray& ia = em->ss->index[em->K];
         SubsetView sv = view_of(em);
@@ -729,6 +745,7 @@ static int launch_mstep_reduce(bamm_em* em) {
                                                                 em->peer_world, em->nbin, parity, em->peer_epoch, em->d_xbuf, em->d_peer_wait);
         CU(cudaGetLastError());
         em->launches += 1;
+        em->peer_sums_global = true;
         return BAMM_OK;
     }
     k_reduce_parts<<<(em->nbin + 255) / 256, 256, 0, em->stream>>>(em->d_part, em->nparts, em->nbin, em->d_xbuf);
@@ -774,6 +791,7 @@ static float q_from_rsum(const bamm_em* em) {     // reference: EM.cpp:515
 
 extern "C" int bamm_em_estep_local(bamm_em* em) {
     REQUIRE(em, "em is NULL");
+    NOT_FOR_GROUPS(em, "bamm_em_estep_local");
     if (!em->model_set) return fail(BAMM_E_STATE, "bamm_em_set_model has not been called");
     CU(cudaSetDevice(em->device));
     CU(cudaEventRecord(em->ev[0], em->stream));
@@ -784,6 +802,7 @@ extern "C" int bamm_em_estep_local(bamm_em* em) {
 }
 
 extern "C" int bamm_em_estep(bamm_em* em, float* llh) {
+    if (IS_GROUP(em)) return group_estep(em, llh);
     int rc = bamm_em_estep_local(em); if (rc) return rc;
     rc = read_scalars(em, false); if (rc) return rc;
     if (llh) *llh = em->llh;
@@ -792,6 +811,7 @@ extern "C" int bamm_em_estep(bamm_em* em, float* llh) {
 
 extern "C" int bamm_em_mstep_local(bamm_em* em) {
     REQUIRE(em, "em is NULL");
+    NOT_FOR_GROUPS(em, "bamm_em_mstep_local");
     if (!em->r_valid) return fail(BAMM_E_STATE, "M-step needs the r of an E-step");
     CU(cudaSetDevice(em->device));
     CU(cudaEventRecord(em->ev[2], em->stream));
@@ -800,6 +820,7 @@ extern "C" int bamm_em_mstep_local(bamm_em* em) {
 
 extern "C" int bamm_em_finish_iteration(bamm_em* em, int optimize_q, float* llh, float* vdiff) {
     REQUIRE(em, "em is NULL");
+    NOT_FOR_GROUPS(em, "bamm_em_finish_iteration");
     CU(cudaSetDevice(em->device));
     int rc = launch_update(em); if (rc) return rc;
     CU(cudaEventRecord(em->ev[3], em->stream));
@@ -813,6 +834,7 @@ extern "C" int bamm_em_finish_iteration(bamm_em* em, int optimize_q, float* llh,
 
 extern "C" int bamm_em_set_exchange_buffer(bamm_em* em, void* dev_ptr, uint64_t words) {
     REQUIRE(em && dev_ptr, "NULL argument");
+    NOT_FOR_GROUPS(em, "bamm_em_set_exchange_buffer");
     REQUIRE(words == (uint64_t)em->nbin + 2, "exchange buffer must hold %llu 64-bit words", (unsigned long long)em->nbin + 2);
     CU(cudaSetDevice(em->device));
     CU(cudaStreamSynchronize(em->stream));
@@ -823,6 +845,7 @@ extern "C" int bamm_em_set_exchange_buffer(bamm_em* em, void* dev_ptr, uint64_t 
 }
 
 extern "C" int bamm_em_mstep(bamm_em* em) {
+    if (IS_GROUP(em)) return group_mstep(em);
     int rc = bamm_em_mstep_local(em); if (rc) return rc;
     rc = launch_update(em); if (rc) return rc;
     CU(cudaEventRecord(em->ev[3], em->stream));
@@ -832,6 +855,19 @@ extern "C" int bamm_em_mstep(bamm_em* em) {
 
 extern "C" int bamm_em_optimize_q(bamm_em* em, float* q) {
     REQUIRE(em, "em is NULL");
+    if (IS_GROUP(em)) {                       // every shard holds the global sum of the posteriors after an exchange; before one, sum the shards
+        float qs = 0.0f;
+        for (bamm_em* sh : em->shards) { int rc = bamm_em_optimize_q(sh, &qs); if (rc) return rc; }
+        if (!em->shards[0]->peer_sums_global) {
+            double n1 = 0.0;
+            for (bamm_em* sh : em->shards) n1 += (double)(long long)sh->h_scal[1] * SC_INV_D;
+            qs = ((float)em->nsub - (float)n1 + 1.f) / ((float)em->nsub + 2.f);
+            for (bamm_em* sh : em->shards) sh->q = qs;
+        }
+        em->q = qs;
+        if (q) *q = qs;
+        return BAMM_OK;
+    }
     if (!em->r_valid) return fail(BAMM_E_STATE, "optimize_q needs the r of an E-step");
     CU(cudaSetDevice(em->device));
     int rc = read_scalars(em, false); if (rc) return rc;
@@ -843,6 +879,7 @@ extern "C" int bamm_em_optimize_q(bamm_em* em, float* q) {
 extern "C" int bamm_em_optimize(bamm_em* em, int optimize_q, float epsilon, int max_iter, int* iterations,
                                 float* llh_trace, float* vdiff_trace, float* q_trace) {
     REQUIRE(em, "em is NULL");
+    if (IS_GROUP(em)) return group_optimize(em, optimize_q, epsilon, max_iter, iterations, llh_trace, vdiff_trace, q_trace);
     if (!em->model_set) return fail(BAMM_E_STATE, "bamm_em_set_model has not been called");
     REQUIRE(max_iter >= 1, "max_iter must be >= 1");
     CU(cudaSetDevice(em->device));
@@ -974,6 +1011,7 @@ done:
 
 extern "C" int bamm_em_mask(bamm_em* em, float f, float epsilon, int max_iter, int* iterations, float* llh, uint64_t* n_kept, float* r_cutoff) {
     REQUIRE(em, "em is NULL");
+    NOT_FOR_GROUPS(em, "bamm_em_mask (EM::mask runs on one device: create the object with bamm_set_device_group of one device)");
     if (!em->model_set) return fail(BAMM_E_STATE, "bamm_em_set_model has not been called");
     REQUIRE(max_iter >= 1, "max_iter must be >= 1");
     REQUIRE(f > 0.0f && f < 1.0f, "fraction f=%g not in (0,1)", (double)f);
@@ -1015,6 +1053,7 @@ static int launch_iteration(bamm_em* em, cudaEvent_t* ev) {
 
 extern "C" int bamm_em_iterate(bamm_em* em, int n_iter, float* llh_last, float* vdiff_last) {
     REQUIRE(em, "em is NULL");
+    if (IS_GROUP(em)) return group_iterate(em, n_iter, llh_last, vdiff_last);
     if (!em->model_set) return fail(BAMM_E_STATE, "bamm_em_set_model has not been called");
     REQUIRE(n_iter >= 0, "n_iter must be >= 0");
     CU(cudaSetDevice(em->device));
@@ -1046,6 +1085,7 @@ static int loop_times(bamm_em* em, float out[5], float* total) {
 }
 
 extern "C" int bamm_em_loop_timing(bamm_em* em, int* iters, float* estep_ms, float* maccum_ms, float* update_ms, float* total_ms) {
+    if (IS_GROUP(em)) return bamm_em_loop_timing(em->shards[0], iters, estep_ms, maccum_ms, update_ms, total_ms);        // identical on every shard (global sums) / shard 0 as the sample
     REQUIRE(em, "em is NULL");
     float t[5], tot;
     int rc = loop_times(em, t, &tot); if (rc) return rc;
@@ -1058,6 +1098,7 @@ extern "C" int bamm_em_loop_timing(bamm_em* em, int* iters, float* estep_ms, flo
 }
 
 extern "C" int bamm_em_loop_timing_estep(bamm_em* em, float* masked_ms, float* bound_ms, float* exact_ms) {
+    if (IS_GROUP(em)) return bamm_em_loop_timing_estep(em->shards[0], masked_ms, bound_ms, exact_ms);        // identical on every shard (global sums) / shard 0 as the sample
     REQUIRE(em, "em is NULL");
     float t[5], tot;
     int rc = loop_times(em, t, &tot); if (rc) return rc;
@@ -1068,6 +1109,7 @@ extern "C" int bamm_em_loop_timing_estep(bamm_em* em, float* masked_ms, float* b
 }
 
 extern "C" int bamm_em_last_timing(bamm_em* em, float* estep_ms, float* mstep_ms) {
+    if (IS_GROUP(em)) return bamm_em_last_timing(em->shards[0], estep_ms, mstep_ms);        // identical on every shard (global sums) / shard 0 as the sample
     REQUIRE(em, "em is NULL");
     CU(cudaSetDevice(em->device));
     CU(cudaStreamSynchronize(em->stream));
@@ -1080,6 +1122,7 @@ extern "C" int bamm_em_last_timing(bamm_em* em, float* estep_ms, float* mstep_ms
 }
 
 extern "C" int bamm_em_get_model(bamm_em* em, float* v_all) {
+    if (IS_GROUP(em)) return bamm_em_get_model(em->shards[0], v_all);        // identical on every shard (global sums) / shard 0 as the sample
     REQUIRE(em && v_all, "NULL argument");
     CU(cudaSetDevice(em->device));
     CU(cudaMemcpyAsync(v_all, em->d_v, em->model_size * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
@@ -1087,6 +1130,7 @@ extern "C" int bamm_em_get_model(bamm_em* em, float* v_all) {
     return BAMM_OK;
 }
 extern "C" int bamm_em_get_counts(bamm_em* em, float* n_all) {
+    if (IS_GROUP(em)) return bamm_em_get_counts(em->shards[0], n_all);        // identical on every shard (global sums) / shard 0 as the sample
     REQUIRE(em && n_all, "NULL argument");
     CU(cudaSetDevice(em->device));
     CU(cudaMemcpyAsync(n_all, em->d_n, em->model_size * sizeof(float), cudaMemcpyDeviceToHost, em->stream));
@@ -1094,6 +1138,7 @@ extern "C" int bamm_em_get_counts(bamm_em* em, float* n_all) {
     return BAMM_OK;
 }
 extern "C" int bamm_em_get_s(bamm_em* em, float* s) {
+    if (IS_GROUP(em)) return bamm_em_get_s(em->shards[0], s);        // identical on every shard (global sums) / shard 0 as the sample
     REQUIRE(em && s, "NULL argument");
     CU(cudaSetDevice(em->device));
     std::vector<float> t(em->nbin);
@@ -1103,10 +1148,11 @@ extern "C" int bamm_em_get_s(bamm_em* em, float* s) {
     for (uint32_t y = 0; y < em->Yn; y++) for (int j = 0; j < em->W; j++) s[(uint64_t)y * em->W + j] = t[(uint64_t)j * em->Yn + y];
     return BAMM_OK;
 }
-extern "C" int bamm_em_get_q(bamm_em* em, float* q) { REQUIRE(em && q, "NULL argument"); *q = em->q; return BAMM_OK; }
-extern "C" uint64_t bamm_em_r_size(const bamm_em* em) { return em ? em->rsize : 0; }
+extern "C" int bamm_em_get_q(bamm_em* em, float* q) { REQUIRE(em && q, "NULL argument"); *q = IS_GROUP(em) ? em->shards[0]->q : em->q; return BAMM_OK; }
+extern "C" uint64_t bamm_em_r_size(const bamm_em* em) { return em ? em->rsize : 0; }       // a group object carries the sum of its shards
 extern "C" int bamm_em_get_r(bamm_em* em, uint64_t first, uint64_t count, float* out) {
     REQUIRE(em && out, "NULL argument");
+    if (IS_GROUP(em)) return group_get_r(em, first, count, out);
     REQUIRE(first + count <= em->nsub, "sequence range out of bounds");
     if (!em->r_valid) return fail(BAMM_E_STATE, "no E-step has run");
     CU(cudaSetDevice(em->device));
@@ -1135,12 +1181,24 @@ extern "C" int bamm_em_get_r(bamm_em* em, uint64_t first, uint64_t count, float*
 
 extern "C" int bamm_em_exchange_buffer(bamm_em* em, void** dev_ptr, uint64_t* words) {
     REQUIRE(em && dev_ptr && words, "NULL argument");
+    NOT_FOR_GROUPS(em, "bamm_em_exchange_buffer");
     *dev_ptr = em->d_xbuf; *words = (uint64_t)em->nbin + 2;
     return BAMM_OK;
 }
-extern "C" int bamm_em_set_global_nseq(bamm_em* em, uint64_t n) { REQUIRE(em, "em is NULL"); em->nseq_global = n; return BAMM_OK; }
-extern "C" int bamm_em_launch_count(bamm_em* em, uint64_t* kernels) { REQUIRE(em && kernels, "NULL argument"); *kernels = em->launches; return BAMM_OK; }
+extern "C" int bamm_em_set_global_nseq(bamm_em* em, uint64_t n) {
+    REQUIRE(em, "em is NULL");
+    em->nseq_global = n;
+    for (bamm_em* sh : em->shards) sh->nseq_global = n;
+    return BAMM_OK;
+}
+extern "C" int bamm_em_launch_count(bamm_em* em, uint64_t* kernels) {
+    REQUIRE(em && kernels, "NULL argument");
+    *kernels = em->launches;
+    for (bamm_em* sh : em->shards) *kernels += sh->launches;
+    return BAMM_OK;
+}
 extern "C" int bamm_em_estep_info(bamm_em* em, uint64_t info[8]) {
+    if (IS_GROUP(em)) return bamm_em_estep_info(em->shards[0], info);        // identical on every shard (global sums) / shard 0 as the sample
     REQUIRE(em && info, "NULL argument");
     CU(cudaSetDevice(em->device));
     CU(cudaStreamSynchronize(em->stream));
@@ -1164,12 +1222,13 @@ extern "C" int bamm_em_estep_info(bamm_em* em, uint64_t info[8]) {
     info[7] = em->plain_words ? 1 : 0;
     return BAMM_OK;
 }
-extern "C" int bamm_em_stream(bamm_em* em, void** stream) { REQUIRE(em && stream, "NULL argument"); *stream = (void*)em->stream; return BAMM_OK; }
+extern "C" int bamm_em_stream(bamm_em* em, void** stream) { REQUIRE(em && stream, "NULL argument"); NOT_FOR_GROUPS(em, "bamm_em_stream"); *stream = (void*)em->stream; return BAMM_OK; }
 
 
 // ---- NVLink peer exchange ------------------------------------------------------------------------------------------
 extern "C" int bamm_em_peer_alloc(bamm_em* em, int rank, int world, void* ipc_handle_out) {
     REQUIRE(em && ipc_handle_out, "NULL argument");
+    NOT_FOR_GROUPS(em, "bamm_em_peer_alloc");
     REQUIRE(world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world, "rank %d / world %d out of range (max %d ranks)", rank, world, MAX_PEERS);
     REQUIRE(!em->d_peer_local, "peer buffer already allocated");
     CU(cudaSetDevice(em->device));
@@ -1193,6 +1252,7 @@ extern "C" int bamm_em_peer_alloc(bamm_em* em, int rank, int world, void* ipc_ha
 
 extern "C" int bamm_em_peer_wait(bamm_em* em, int reset, double* total_ms, uint64_t* waits) {
     REQUIRE(em && total_ms && waits, "NULL argument");
+    if (IS_GROUP(em)) return bamm_em_peer_wait(em->shards[0], reset, total_ms, waits);
     *total_ms = 0.0; *waits = 0;
     if (!em->d_peer_wait) return BAMM_OK;
     CU(cudaSetDevice(em->device));
@@ -1206,6 +1266,7 @@ extern "C" int bamm_em_peer_wait(bamm_em* em, int reset, double* total_ms, uint6
 
 extern "C" int bamm_em_peer_attach(bamm_em* em, const void* ipc_handles) {
     REQUIRE(em && ipc_handles, "NULL argument");
+    NOT_FOR_GROUPS(em, "bamm_em_peer_attach");
     if (!em->d_peer_local) return fail(BAMM_E_STATE, "bamm_em_peer_alloc has not been called");
     CU(cudaSetDevice(em->device));
     const size_t words = (size_t)em->nbin + 2;

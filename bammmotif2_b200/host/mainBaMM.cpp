@@ -6,12 +6,37 @@
 #include <iostream>
 #include <memory>
 #include <thread>
+#include <vector>
+#include <cstdlib>
 
 #include "EM.h"
 #include "FDR.h"
 #include "Global.h"
 #include "ScoreSeqSet.h"
 #include "SeqGenerator.h"
+
+// devices named by BAMM_DEVICES (list "0,2,3" and / or ranges "0-7"), else BAMM_DEVICE, else device 0
+static std::vector<int> deviceList(){
+    std::vector<int> out;
+    if( const char* e = getenv( "BAMM_DEVICES" ) ){
+        const char* p = e;
+        while( *p ){
+            char* end = nullptr;
+            long a = strtol( p, &end, 10 );
+            if( end == p ) break;
+            long b = a;
+            if( *end == '-' ){ p = end + 1; b = strtol( p, &end, 10 ); }
+            for( long d = a; d <= b && out.size() < 16; d++ ) out.push_back( static_cast<int>( d ) );
+            p = ( *end == ',' ) ? end + 1 : end;
+            if( *end != ',' && *end != 0 ) break;
+        }
+    }
+    if( out.empty() ){
+        const char* dev = getenv( "BAMM_DEVICE" );
+        out.push_back( dev ? atoi( dev ) : 0 );
+    }
+    return out;
+}
 
 int main( int nargs, char* args[] ){
     auto t0_wall = std::chrono::high_resolution_clock::now();
@@ -35,14 +60,20 @@ int main( int nargs, char* args[] ){
     srand( 42 );                                    // reference: mainBaMM.cpp:22
     // the first CUDA call creates the device context (0.8 s and more on a multi-GPU box): it runs beside option parsing and
     // the FASTA reader; a failure is not reported here — the first real device call of the main thread reports it
-    std::thread warm( [](){ const char* dev = getenv( "BAMM_DEVICE" ); bamm_set_device( dev ? atoi( dev ) : 0 ); } );
+    // BAMM_DEVICES="0,1,2,3" or "0-7": one process drives all of them (EM::optimize splits the sequences over the devices and
+    // exchanges the counts over NVLink; everything else stays on the first one). BAMM_DEVICE=n: a single device.
+    std::vector<int> devices = deviceList();
+    std::thread warm( [devices](){ for( int d : devices ){ bamm_set_device( d ); } bamm_set_device( devices[0] ); } );
+    if( devices[0] != 0 ) bamm_set_device( devices[0] );      // the FASTA reader may already create the device copy of the set
     Global::init( nargs, args );
     warm.join();
     if( Global::CGS ){
         std::cerr << "Error: collapsed Gibbs sampling (--CGS) is not part of the B200 path; use --EM." << std::endl;
         return 1;
     }
-    if( const char* dev = getenv( "BAMM_DEVICE" ) ) BAMM_CHECK( bamm_set_device( atoi( dev ) ) );
+    BAMM_CHECK( bamm_set_device( devices[0] ) );
+    // EM::mask (--advanceEM) runs on one device
+    if( devices.size() > 1 && !Global::advanceEM ) BAMM_CHECK( bamm_set_device_group( devices.data(), static_cast<int>( devices.size() ) ) );
     mark( "options + FASTA" );
 
     std::vector<Sequence*> posSet = Global::posSequenceSet->getSequences();

@@ -52,6 +52,14 @@ int         bamm_set_device(int device);           /* device used by objects cre
 int         bamm_plan_describe(int W, int K, int K_bg_model, int reduced, uint64_t table_budget_bytes, int32_t* out, uint64_t cap,
                                uint64_t* n_used);
 int         bamm_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+/* Device group: several devices of one box driven by ONE process (the reference parallelises EM::EStep / MStep over the
+ * sequences with OpenMP, src/refinement/EM.cpp:148-149, 230; here the sequences are cut into one contiguous block per device).
+ * After this call, EM objects created over a sequence set that lives on devices[0] span all devices of the group (large enough
+ * subsets only): bamm_em_optimize / bamm_em_iterate / bamm_em_estep / bamm_em_mstep run every block on its device and exchange
+ * the count tensor over NVLink peer memory; results are bit-identical to one device. n = 0 or 1 switches the group off.
+ * Everything else (sequence sets, scoring, negative sampling, bamm_em_mask) stays on devices[0]. */
+int         bamm_set_device_group(const int* devices, int n);
+int         bamm_get_device_group(int* devices, int cap, int* n);
 
 /* ---- sequence set  (replaces Sequence::kmer_ / getKmer(), src/init/Sequence.cpp:35-41, Sequence.h:56-58) ---- */
 /*
