@@ -339,3 +339,27 @@ def test_cli_advance_em_against_reference_binary(bins, tmp_path):
     for fn in ("syn_motif_1.ihbcp", "syn_motif_1.ihbp"):
         a, b = parse_numbers(open(tmp_path / "ref" / fn, "rb").read()), parse_numbers(open(tmp_path / "our" / fn, "rb").read())
         assert a.shape == b.shape and np.all(np.abs(a - b) <= 1.2e-3 * np.abs(a) + 1e-30), fn
+
+
+@pytest.mark.gpu
+def test_cli_two_devices_write_the_same_files(bins, tmp_path):
+    """BAMM_DEVICES=0,1: EM::optimize (also inside the FDR folds, reference src/evaluation/FDR.cpp:37-73) splits the sequences
+    over two devices of one process. Every output file must be byte-identical to the one-device run (skipped on one device)."""
+    from bammmotif2_b200 import capi, synth
+    capi.load()
+    if capi.device_count() < 2:
+        pytest.skip("needs two devices")
+    fwd, sites, _ = synth.planted_sequences(99, 12000, 150, 12)
+    fa, bs = str(tmp_path / "syn.fasta"), str(tmp_path / "sites.block")
+    synth.write_fasta(fa, fwd)
+    synth.write_sites(bs, sites)
+    args = ["--bindingSiteFile", bs, "--EM", "-k", "2", "-K", "2", "--FDR", "-m", "2", "-n", "3", "--saveBaMMs", "--verbose"]
+    outs = {}
+    for name, devs in (("one", "0"), ("two", "0,1")):
+        p = run([os.path.join(bins, "BaMMmotif"), str(tmp_path / name), fa] + args, env=dict(os.environ, BAMM_DEVICES=devs, BAMM_GROUP_MIN_SEQS="1000"))
+        outs[name] = [l for l in p.stdout.split("\n") if " iter, llh=" in l]
+    assert outs["one"] == outs["two"] and len(outs["one"]) > 3
+    files = sorted(os.listdir(tmp_path / "one"))
+    assert files == sorted(os.listdir(tmp_path / "two")) and any(f.endswith(".ihbcp") for f in files) and any(f.endswith(".zoops.stats") for f in files)
+    for fn in files:
+        assert open(tmp_path / "one" / fn, "rb").read() == open(tmp_path / "two" / fn, "rb").read(), fn
