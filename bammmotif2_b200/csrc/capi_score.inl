@@ -166,35 +166,63 @@ extern "C" int bamm_score_last_timing(float* kernel_ms) {
 // ------------------------------------------------------------------------------------------- score statistics (row f-1)
 static int device_sort_f32(float* d_keys, uint64_t n, bool descending, cudaStream_t st) {
     if (n < 2) return BAMM_OK;
-    REQUIRE(n < (1ull << 31), "too many scores for one sort call");
     float* d_alt = nullptr; void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cudaError_t e = dev_malloc(&d_alt, n * sizeof(float));
-    if (e != cudaSuccess) return fail(BAMM_E_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(BAMM_E_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
     cub::DoubleBuffer<float> buf(d_keys, d_alt);
-    if (descending) cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, buf, (int)n, 0, 32, st);
-    else            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, buf, (int)n, 0, 32, st);
+    const unsigned long long items = n;                                // 64-bit item count: no 2^31 limit
+    if (descending) cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, buf, items, 0, 32, st);
+    else            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, buf, items, 0, 32, st);
     e = dev_malloc(&d_tmp, tmp_bytes ? tmp_bytes : 16);
+    const bool nomem = e == cudaErrorMemoryAllocation;
     if (e == cudaSuccess) {
-        if (descending) e = cub::DeviceRadixSort::SortKeysDescending(d_tmp, tmp_bytes, buf, (int)n, 0, 32, st);
-        else            e = cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, buf, (int)n, 0, 32, st);
+        if (descending) e = cub::DeviceRadixSort::SortKeysDescending(d_tmp, tmp_bytes, buf, items, 0, 32, st);
+        else            e = cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, buf, items, 0, 32, st);
     }
     if (e == cudaSuccess && buf.Current() != d_keys) e = cudaMemcpyAsync(d_keys, buf.Current(), n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d_alt); cudaFree(d_tmp);
-    if (e != cudaSuccess) return fail(BAMM_E_CUDA, "device sort failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nomem ? BAMM_E_NOMEM : BAMM_E_CUDA, "device sort failed: %s", cudaGetErrorString(e)); }
     return BAMM_OK;
 }
 
-extern "C" int bamm_sort_scores(float* scores, uint64_t n, int descending) {
-    REQUIRE(scores || n == 0, "scores is NULL");
-    if (n < 2) return BAMM_OK;
+// one run of at most `n` scores through the device; BAMM_E_NOMEM when the device cannot hold it (2 n floats + workspace)
+static int sort_run_on_device(float* scores, uint64_t n, bool descending) {
     float* d = nullptr;
-    CU(dev_malloc(&d, n * sizeof(float)));
-    cudaError_t e = cudaMemcpy(d, scores, n * sizeof(float), cudaMemcpyHostToDevice);
-    int rc = e == cudaSuccess ? device_sort_f32(d, n, descending != 0, 0) : fail(BAMM_E_CUDA, "H2D failed: %s", cudaGetErrorString(e));
+    cudaError_t e = dev_malloc(&d, n * sizeof(float));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? BAMM_E_NOMEM : BAMM_E_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpy(d, scores, n * sizeof(float), cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? device_sort_f32(d, n, descending, 0) : fail(BAMM_E_CUDA, "H2D failed: %s", cudaGetErrorString(e));
     if (!rc) { e = cudaMemcpy(scores, d, n * sizeof(float), cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(BAMM_E_CUDA, "D2H failed: %s", cudaGetErrorString(e)); }
     cudaFree(d);
     return rc;
+}
+
+// Sorts like std::sort (the reference's sorts in FDR::calculatePR / calculatePvalues, src/evaluation/FDR.cpp:161-162, 207-208) for
+// ANY n: one device sort when the device can hold the vector; otherwise runs of halving size sorted on the device and merged on
+// the host; a run the device cannot take at all is sorted on the host. BAMM_SORT_RUN caps the run length (tests).
+extern "C" int bamm_sort_scores(float* scores, uint64_t n, int descending) {
+    REQUIRE(scores || n == 0, "scores is NULL");
+    if (n < 2) return BAMM_OK;
+    const bool desc = descending != 0;
+    uint64_t run = n;
+    if (const char* cap = getenv("BAMM_SORT_RUN")) { const uint64_t c = (uint64_t)atoll(cap); if (c >= 2 && c < run) run = c; }
+    auto host_sort = [&](float* a, float* b) { if (desc) std::sort(a, b, std::greater<float>()); else std::sort(a, b); };
+    for (;;) {
+        int rc = BAMM_OK;
+        uint64_t done = 0;
+        for (; done < n && rc == BAMM_OK; done += run) rc = sort_run_on_device(scores + done, std::min(run, n - done), desc);
+        if (rc == BAMM_OK) break;
+        if (rc != BAMM_E_NOMEM) return rc;
+        if (run <= (1ull << 20)) { host_sort(scores, scores + n); return BAMM_OK; }   // no room for even a small run: host
+        run = (run + 1) / 2;                                                           // sorted prefixes stay sorted: harmless
+    }
+    for (uint64_t width = run; width < n; width *= 2)                                  // merge neighbouring runs
+        for (uint64_t lo = 0; lo + width < n; lo += 2 * width) {
+            float* a = scores + lo; float* m = a + width; float* b = scores + std::min(n, lo + 2 * width);
+            if (desc) std::inplace_merge(a, m, b, std::greater<float>()); else std::inplace_merge(a, m, b);
+        }
+    return BAMM_OK;
 }
 
 extern "C" int bamm_mops_pvalues(const float* neg_scores, uint64_t nneg, const float* pos_scores, uint64_t npos, uint64_t n_pos_sequences,
@@ -212,7 +240,7 @@ extern "C" int bamm_mops_pvalues(const float* neg_scores, uint64_t nneg, const f
         rc = device_sort_f32(d_neg, nneg, false, 0);
         if (rc) goto done;
         // rate parameter of the exponential tail from the first nTop sorted values, in the reference's order (ScoreSeqSet.cpp:88-96)
-        const size_t nTop = (size_t)std::min(100, (int)nneg / 10);
+        const size_t nTop = (size_t)std::min<uint64_t>(100, nneg / 10);
         std::vector<float> head(nTop + 1);
         CUX(cudaMemcpy(head.data(), d_neg, (nTop + 1) * sizeof(float), cudaMemcpyDeviceToHost));
         const float S_ntop = head[nTop];

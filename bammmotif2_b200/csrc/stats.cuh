@@ -30,7 +30,9 @@ k_mops_pvalues(const float* __restrict__ neg, unsigned long long negN, const flo
         if (FPl == negN) p = 1.0f;
         else if (FPl < 10 && fabsf(lambda) > eps) p = nTop / (float)negN * expf(-(Sl - S_ntop) / lambda);
         else {
-            const float SlHigher = neg[negN - FPl - 1], SlLower = neg[negN - FPl];
+            // FPl == 0 (no negative above Sl) only gets here without a usable tail fit: the reference then reads one element
+            // past its vector (ScoreSeqSet.cpp:112); Sl itself stands in for it, which gives p = 1 / negN
+            const float SlHigher = neg[negN - FPl - 1], SlLower = FPl ? neg[negN - FPl] : Sl;
             p = ((float)FPl + (SlHigher - Sl + eps) / (SlHigher - SlLower + eps)) / (float)negN;
         }
         pval[i] = p;

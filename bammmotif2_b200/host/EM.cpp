@@ -60,7 +60,7 @@ int EM::optimize(){
     iterations_ = static_cast<size_t>( iterations );
     if( verbose_ ){
         // same lines, same order as the reference prints them inside its loop (EM.cpp:99, 112-115)
-        float prev = 0.0f;          // llikelihood_ starts at 0 (EM.h:61)
+        float prev = llikelihood_;  // the member starts at 0 (EM.h:61) and carries over between calls, as in the reference
         for( int it = 0; it < iterations; it++ ){
             if( optimizeQ_ && it < 5 ) std::cout << "optimized q=" << qtrace[it] << std::endl;
             std::cout << it + 1 << " iter, llh=" << llh[it] << ", diff_llh=" << llh[it] - prev << ", v_diff=" << vdiff[it] << std::endl;

@@ -34,6 +34,7 @@ public:
     const std::vector<float>& zoopsFDR() const      { return ZOOPS_FDR_; }
     const std::vector<float>& zoopsRecall() const   { return ZOOPS_Rec_; }
     const std::vector<float>& pnPvalues() const     { return PN_Pvalue_; }
+    const std::vector<float>& zoopsPvalues() const  { return ZOOPS_Pvalue_; }
     float                     occFrac() const       { return occ_frac_; }
     // feeds score vectors directly (tests of the statistics without a device)
     void    setScores( std::vector<float> posMax, std::vector<float> negMax ){ posScoreMax_ = posMax; negScoreMax_ = negMax; }

@@ -264,6 +264,13 @@ int Global::readArguments( int nargs, char* args[] ){
     ignored = opt.present( "B3" );
     ignored = opt.present( "B3prime" );
     advanceEM = opt.present( "advanceEM" );
+    if( advanceEM && optimizeQ ){
+        // EM::mask of the reference re-estimates q after EVERY sequence of its first pass from the posteriors of ALL sequences,
+        // most of them not computed yet (EM.cpp:316 inside the loop of :281): an O(N^2) order-dependent quirk that is not
+        // reproduced (deviations). Rejected before any work is done.
+        std::cerr << "Error: --advanceEM cannot be combined with --optimizeQ on the B200 path." << std::endl;
+        exit( 1 );
+    }
     opt.value( "threads", 0, threads );
     ( void )ignored;
 

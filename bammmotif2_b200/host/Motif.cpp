@@ -1,4 +1,5 @@
 #include "Motif.h"
+#include "Device.h"
 
 #include <cmath>
 #include <fstream>
@@ -40,6 +41,12 @@ void Motif::bindViews(){
 
 Motif::Motif( size_t length, size_t K, std::vector<float> alpha, float** v_bg, size_t k_bg, float glob_q )
     : W_( length ), K_( K ), q_( glob_q ), v_bg_( v_bg ), k_bg_( k_bg ){
+    if( W_ < 1 || W_ > BAMM_MAX_MOTIF_WIDTH ){
+        // the device kernels keep one window (W columns + K context bases) in a 32-base word; the reference has no such limit
+        std::cerr << "Error: motif width " << W_ << " (including --extend columns) is outside [1, " << BAMM_MAX_MOTIF_WIDTH
+                  << "], the range of the B200 path." << std::endl;
+        exit( 1 );
+    }
     allocate();
     if( v_bg_ == NULL ){
         // uniform order-2 background (reference: src/init/Motif.cpp:19-28)

@@ -132,7 +132,9 @@ int main( int argc, char** argv ){
         FDR fdr( pos, neg, &dummy, NULL, 4, false, true, true, false, false );
         fdr.setScores( slurp<float>( argv[5] ), slurp<float>( argv[6] ) );
         fdr.calculatePR();
+        fdr.calculatePvalues();                     // FDR.cpp:278-330 (needs the scores sorted or not: it sorts them itself)
         const std::string out = argv[7];
+        dump( out + "/zoops_pvalue.f32", fdr.zoopsPvalues().data(), fdr.zoopsPvalues().size() );
         dump( out + "/TP.f32", fdr.zoopsTP().data(), fdr.zoopsTP().size() );
         dump( out + "/FP.f32", fdr.zoopsFP().data(), fdr.zoopsFP().size() );
         dump( out + "/FDR.f32", fdr.zoopsFDR().data(), fdr.zoopsFDR().size() );

@@ -43,6 +43,10 @@ typedef struct bamm_em     bamm_em;       /* one EM problem: subset of a seqset,
 /* ---- library / device ----------------------------------------------------------------------- */
 int         bamm_version(void);                    /* 10000*major + 100*minor + patch */
 const char* bamm_last_error(void);                 /* text of the last failure on this thread */
+/* Limits of the device path (the reference has none of them; calls outside return BAMM_E_INVALID):
+ *   motif width W (after --extend) in [1, BAMM_MAX_MOTIF_WIDTH]: a window and its context are handled as one 32-base word;
+ *   model orders K, K_bg in [0, 10] (the reference hashes at most 11-mers, src/init/Sequence.cpp:36). */
+#define BAMM_MAX_MOTIF_WIDTH 32
 int         bamm_device_count(int* count);
 int         bamm_set_device(int device);           /* device used by objects created afterwards on this thread */
 /* The column-group plan of the packed E-step for (W, K, K_bg) under a shared-memory budget, as plain numbers; host

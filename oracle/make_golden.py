@@ -67,9 +67,11 @@ def write_inputs(tmp, seqs, sites):
 
 
 def run_case(name, fasta, sitefile, args, r_iters="1", max_iter=None, dump_neg=False, keep=None, extra_inputs=None, init=("--bindingSiteFile",),
-             dump_mask=False):
+             dump_mask=False, dump_pvalues=False):
     tmp = tempfile.mkdtemp(prefix="golden_")
     env = dict(os.environ, BAMM_DUMP_R_ITERS=r_iters, OMP_NUM_THREADS="1")
+    if dump_pvalues:
+        env["BAMM_DUMP_PVALUES"] = "1"
     if dump_mask:
         env["BAMM_DUMP_MASK"] = "1"
     if max_iter:
@@ -160,8 +162,24 @@ def mask_cases():
     shutil.rmtree(tmp)
 
 
+def pvalue_case():
+    """Score statistics (SURVEY.md §8 row f-1): ScoreSeqSet::calcPvalues of every positive window against all negative window
+    scores (what --scoreSeqset computes, mainBaMM.cpp:203-230) and FDR::calculatePvalues with --savePvalues, MOPS and ZOOPS."""
+    keep = lambda k: "_pval_" in k or ("_fdr_" in k and "All" not in k and "mops" not in k) or k in ("m1_score_mops", "pos_offsets")
+    tmp = tempfile.mkdtemp(prefix="golden_in_")
+    seqs, sites = synth(seed=41, nseq=50, L0=24, W=7)
+    d = os.path.join(tmp, "pval")
+    os.makedirs(d)
+    fa, bs = write_inputs(d, seqs, sites)
+    run_case("syn_pval", fa, bs, ["--EM", "-k", "2", "-K", "2", "--FDR", "-n", "4", "--savePvalues"], r_iters="",
+             keep=keep, dump_pvalues=True)
+    shutil.rmtree(tmp)
+
+
 def main():
     subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    if "--only-pval" in sys.argv:
+        return pvalue_case()
     if "--only-mask" in sys.argv:
         return mask_cases()
     if "--only-pwm" in sys.argv:
@@ -192,6 +210,7 @@ def main():
     pwm_case()
     neg_cases()
     mask_cases()
+    pvalue_case()
 
 
 if __name__ == "__main__":

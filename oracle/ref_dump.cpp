@@ -249,6 +249,22 @@ int main(int nargs, char* args[]) {
             dump_f32(mp + "score_mops", mops); dump_f32(mp + "score_zoops", zo); dump_u64(mp + "score_z", z);
             std::vector<float> s; for (size_t y = 0; y < Y[K + 1]; y++) for (size_t j = 0; j < W; j++) s.push_back(motif->getS()[y][j]);
             dump_f32(mp + "score_logs", s);
+            // p-values of every positive window against all negative window scores, as mainBaMM.cpp:203-230 computes them
+            // for --scoreSeqset (ScoreSeqSet::calcPvalues, src/seq_scoring/ScoreSeqSet.cpp:70-126)
+            if (getenv("BAMM_DUMP_PVALUES")) {
+                ScoreSeqSet sn(motif, bgModel, negSet);
+                sn.calcLogOdds();
+                std::vector<std::vector<float>> na = sn.getMopsScores();
+                std::vector<float> negScores;
+                for (size_t n = 0; n < negSet.size(); n++) negScores.insert(negScores.end(), na[n].begin(), na[n].end());
+                sc.calcPvalues(ms, negScores);
+                std::vector<float> pv, evv;
+                for (size_t n = 0; n < posSet.size(); n++) {
+                    pv.insert(pv.end(), sc.mops_p_values_[n].begin(), sc.mops_p_values_[n].end());
+                    evv.insert(evv.end(), sc.mops_e_values_[n].begin(), sc.mops_e_values_[n].end());
+                }
+                dump_f32(mp + "pval_neg_all", negScores); dump_f32(mp + "pval_p", pv); dump_f32(mp + "pval_e", evv);
+            }
         }
 
         if (Global::FDR) {
@@ -260,6 +276,10 @@ int main(int nargs, char* args[]) {
             dump_f32(mp + "fdr_TP", fdr.ZOOPS_TP_); dump_f32(mp + "fdr_FP", fdr.ZOOPS_FP_);
             dump_f32(mp + "fdr_FDR", fdr.ZOOPS_FDR_); dump_f32(mp + "fdr_Rec", fdr.ZOOPS_Rec_);
             dump_f32(mp + "fdr_PNpval", fdr.PN_Pvalue_);
+            if (Global::savePvalues) {        // FDR::calculatePvalues (src/evaluation/FDR.cpp:278-330): ranks of the ZOOPS / MOPS scores
+                dump_f32(mp + "fdr_zoops_pvalue", fdr.ZOOPS_Pvalue_); dump_f32(mp + "fdr_mops_pvalue", fdr.MOPS_Pvalue_);
+                dump_f32(mp + "fdr_posScoreAll", fdr.posScoreAll_); dump_f32(mp + "fdr_negScoreAll", fdr.negScoreAll_);
+            }
             std::vector<float> occ(1, fdr.occ_frac_); dump_f32(mp + "fdr_occ_frac", occ);
             fdr.write(Global::outputDirectory, Global::outputFileBasename + "_motif_" + std::to_string(m + 1));
         }

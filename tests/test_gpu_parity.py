@@ -519,6 +519,37 @@ def test_device_sort_and_mops_pvalues(capi):
     assert np.array_equal(e, (p * np.float32(777)).astype(np.float32))
 
 
+def test_mops_pvalues_against_reference(capi):
+    """Row f-1 pinned to the reference: bamm_mops_pvalues on the scores the reference fed its own ScoreSeqSet::calcPvalues
+    (src/seq_scoring/ScoreSeqSet.cpp:70-126; golden made by oracle/ref_dump with BAMM_DUMP_PVALUES). Rank search, the p = 1 branch
+    and the interpolation branch must be bit-identical (same fp32 operations); the exponential tail differs by the device's expf."""
+    g = Golden("syn_pval")
+    neg, pos, p_ref, e_ref = g["m1_pval_neg_all"], g["m1_score_mops"], g["m1_pval_p"], g["m1_pval_e"]
+    posN = len(g["pos_offsets"]) - 1
+    p, e = capi.mops_pvalues(neg, pos, posN)
+    s = np.sort(neg)
+    negN = len(s)
+    nTop = min(100, negN // 10)
+    lam = np.float32(0)
+    for n in range(nTop):
+        lam = np.float32(lam + np.float32(s[n] - s[nTop]))
+    lam = np.float32(lam / np.float32(nTop))
+    FPl = negN - np.searchsorted(s, pos, side="right")
+    tail = (FPl != negN) & (FPl < 10) & (abs(lam) > 1e-5)
+    assert (~tail).sum() > 1000
+    assert np.array_equal(p[~tail], p_ref[~tail]) and np.array_equal(e[~tail], e_ref[~tail])
+    if tail.any():
+        assert np.all(np.abs(p[tail] - p_ref[tail]) <= 4e-6 * np.abs(p_ref[tail]))
+        assert np.all(np.abs(e[tail] - e_ref[tail]) <= 4e-6 * np.abs(e_ref[tail]))
+    # the sort behind it, also in runs merged on the host (the route for vectors the device cannot hold at once)
+    import os
+    os.environ["BAMM_SORT_RUN"] = "50000"
+    try:
+        assert np.array_equal(capi.sort_scores(neg), s) and np.array_equal(capi.sort_scores(neg, descending=True), s[::-1])
+    finally:
+        del os.environ["BAMM_SORT_RUN"]
+
+
 @pytest.mark.parametrize("case", ["mask_k2", "mask_k3_ss"])
 def test_mask_advanced_em_against_reference(capi, oracle, case):
     """Row f-4: bamm_em_mask against the reference's EM::mask (goldens made by ref_dump, f = 0.05). The first phase and the
