@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--full", action="store_true", help="workload c4: the WHOLE --FDR run through the drop-in CLI (bin/BaMMmotif) instead of one fold's scoring")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling run (one set split over the ranks)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="sequences in the CPU sample (default by workload)")
     return ap.parse_args()
@@ -314,7 +315,80 @@ def c4_reference(wl, sample_nseq, seed, steps, warmup):
                        "(the reference scores serially)" % (res["npos_seq"], wl["L0"], res["nneg_seq"], res["mfold"], wl["W"], wl["K"], len(per)))
 
 
+C4F_METRIC = "FDR cross-validation sequences/s (whole --FDR run of the CLI: 5 folds of EM + scoring, 10x negatives, statistics, files)"
+
+
+def run_c4_full(args, wl):
+    """BASELINE.json configs[3] end to end through the drop-in command line (reference: mainBaMM.cpp:119-170 -> FDR::evaluateMotif,
+    src/evaluation/FDR.cpp:28-145, calculatePR :147-276, write): FASTA in, .zoops.stats out. One process; --gpus N hands it N devices
+    (BAMM_DEVICES: EM::optimize of every fold is split over them). value = (positives + sampled negatives scored) / wall seconds.
+    --impl reference: the reference's own binary (oracle/_ref/BaMMmotif_ref, all host threads) on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ref = args.impl == "reference"
+    nseq = args.nseq or (args.cpu_sample or 5_000 if ref else wl["nseq"])
+    exe = os.path.join(ROOT, "oracle", "_ref", "BaMMmotif_ref") if ref else os.path.join(ROOT, "bammmotif2_b200", "bin", "BaMMmotif")
+    if not os.path.exists(exe):
+        raise SystemExit("%s is not built" % exe)
+    tmp = tempfile.mkdtemp(prefix="bamm_c4_")
+    t0 = time.perf_counter()
+    fwd, sites, _ = synth.planted_sequences(args.seed, nseq, wl["L0"], wl["W"])
+    fa, bs, out = os.path.join(tmp, "in.fasta"), os.path.join(tmp, "sites.block"), os.path.join(tmp, "out")
+    synth.write_fasta(fa, fwd)
+    synth.write_sites(bs, sites)
+    os.makedirs(out)
+    t_gen = time.perf_counter() - t0
+    cmd = [exe, out, fa, "--bindingSiteFile", bs, "--EM", "-k", str(wl["K"]), "-K", str(wl["K_bg"]), "--FDR", "-m", str(wl["mfold"]), "-n", str(wl["cvfold"])]
+    env = dict(os.environ)
+    if ref:
+        cmd += ["--threads", str(os.cpu_count() or 1)]
+    else:
+        env.update(BAMM_DEVICES=",".join(str(d) for d in range(max(args.gpus, 1))), BAMM_TRACE="1")
+    t0 = time.perf_counter()
+    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    wall = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise SystemExit("CLI failed: %s" % p.stderr[-500:])
+    stages = {}
+    for l in p.stderr.splitlines():
+        if l.startswith("[bamm host] ") and l.rstrip().endswith(" ms"):
+            t = l[len("[bamm host] "):].rsplit(" ", 2)
+            stages[t[0]] = float(t[1])
+    mfold = wl["mfold"]
+    for l in p.stdout.splitlines():                 # the reference raises mFold for small sets (mainBaMM.cpp:102-106)
+        if "mFold" in l and "=" in l:
+            try: mfold = int(l.split("=")[-1].strip())
+            except ValueError: pass
+    stats = [f for f in os.listdir(out) if f.endswith(".zoops.stats")]
+    head = open(os.path.join(out, stats[0])).readline().split() if stats else []
+    scored = nseq // wl["cvfold"] * wl["cvfold"] + nseq * mfold // wl["cvfold"] * wl["cvfold"]
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    value = scored / wall
+    gpu_s = sum(v for k, v in stages.items() if k in ("negative set", "EM", "FDR folds")) * 1e-3
+    line = {"metric": C4F_METRIC, "value": value, "unit": C4_UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": wall * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "synthetic %d x %d bp positives, --EM -k %d -K %d --FDR -m %d -n %d through the command line (FASTA in, files out)" % (
+                           nseq, wl["L0"], wl["K"], wl["K_bg"], mfold, wl["cvfold"]),
+                       "sequences_scored": scored, "wall_s": wall, "fasta_written_s": t_gen, "stages_ms": stages or None,
+                       "device_path_s": gpu_s if stages else None, "occurrence_fraction": float(head[-1]) if head else None, "seed": args.seed,
+                       "note": "wall clock of the whole process; the device path (negative sampling + EM + 5 folds of EM and scoring) is device_path_s, "
+                               "the rest is FASTA parsing and the 11-million-line statistics file on the host"},
+            "e2e": {"value": value, "unit": C4_UNIT, "h2d_bytes_per_step": int(nseq * (2 * wl["L0"] + 1)) if not ref else 0, "d2h_bytes_per_step": int(12 * scored) if not ref else 0,
+                    "seconds": wall, "what": "the same run: this workload is end to end by construction"},
+            "gpu_launches": None if ref else "not counted (separate process)"}
+    if ref:
+        line.update({"impl": "reference", "gpu_launches": 0,
+                     "cpu_baseline": {"value": value, "unit": C4_UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                      "sample": "%d x %d bp positives, mFold %d (the reference raises it for sets below 5000 sequences), its own binary" % (nseq, wl["L0"], mfold)}})
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def run_c4(args, wl):
+    if args.full:
+        return run_c4_full(args, wl)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

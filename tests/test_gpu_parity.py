@@ -538,9 +538,11 @@ def test_mops_pvalues_against_reference(capi):
     tail = (FPl != negN) & (FPl < 10) & (abs(lam) > 1e-5)
     assert (~tail).sum() > 1000
     assert np.array_equal(p[~tail], p_ref[~tail]) and np.array_equal(e[~tail], e_ref[~tail])
-    if tail.any():
-        assert np.all(np.abs(p[tail] - p_ref[tail]) <= 4e-6 * np.abs(p_ref[tail]))
-        assert np.all(np.abs(e[tail] - e_ref[tail]) <= 4e-6 * np.abs(e_ref[tail]))
+    if tail.any():      # the reference's rate parameter is fitted to the LOWEST scores (ascending sort, :85-96), so the tail can overflow to inf
+        for ours, ref in ((p[tail], p_ref[tail]), (e[tail], e_ref[tail])):
+            fin = np.isfinite(ref)
+            assert np.array_equal(ours[~fin], ref[~fin])
+            assert np.all(np.abs(ours[fin] - ref[fin]) <= 4e-6 * np.abs(ref[fin]))
     # the sort behind it, also in runs merged on the host (the route for vectors the device cannot hold at once)
     import os
     os.environ["BAMM_SORT_RUN"] = "50000"
