@@ -15,6 +15,9 @@ WORKLOADS = {
     # BASELINE.json configs[3]: --FDR, 5 folds, mFold=10 sampled negatives, order 3; one "step" scores one fold's test set
     "c4": dict(nseq=1_000_000, L0=500, W=12, K=3, K_bg=2, mfold=10, cvfold=5,
                desc="synthetic 1M x 500 bp positives, 10x sampled negatives (device), order-3 W=12, one fold of 5-fold FDR scoring (ZOOPS)"),
+    # BASELINE.json configs[4]: multi-motif EM from the reference's shipped PWMs (example/PWM_peng10.meme, six motifs), order 5,
+    # EXTENDED (ACGTMH) alphabet; runs through the drop-in CLI (bench.py --workload c5)
+    "c5": dict(nseq=100_000, L0=500, W=12, K=5, K_bg=2, desc="synthetic 100k x 500 bp, six motifs of PWM_peng10.meme, order 5, EXTENDED alphabet (CLI)"),
     "tiny": dict(nseq=2_000, L0=100, W=10, K=2, K_bg=2, desc="smoke-sized planted-motif set"),
 }
 

@@ -386,6 +386,61 @@ def run_c4_full(args, wl):
     return 0
 
 
+def run_c5(args, wl):
+    """BASELINE.json configs[4] through the drop-in command line: --PWMFile (the reference's shipped PWM_peng10.meme: six motifs,
+    Motif::initFromPWM, src/init/Motif.cpp:192-333, incl. its alength quirk) --EM -k 5 --alphabet EXTENDED, one EM::optimize per
+    motif (mainBaMM.cpp:119-170). The 6-letter alphabet runs on the index-array kernels (csrc/kernels.cuh). value = input bases x EM
+    iterations of all motifs / seconds in EM::optimize; e2e = the same over the wall clock of the process."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ref = args.impl == "reference"
+    nseq = args.nseq or ((args.cpu_sample or 1_000) if ref else wl["nseq"])
+    exe = os.path.join(ROOT, "oracle", "_ref", "BaMMmotif_ref") if ref else os.path.join(ROOT, "bammmotif2_b200", "bin", "BaMMmotif")
+    if not os.path.exists(exe):
+        raise SystemExit("%s is not built" % exe)
+    tmp = tempfile.mkdtemp(prefix="bamm_c5_")
+    fwd, _, _ = synth.planted_sequences(args.seed, nseq, wl["L0"], wl["W"])
+    fa, meme, out = os.path.join(tmp, "in.fasta"), os.path.join(tmp, "pwm.meme"), os.path.join(tmp, "out")
+    synth.write_fasta(fa, fwd)
+    # the reference's example/PWM_peng10.meme travels inside a test fixture (tests/golden/jund_pwm_k1.npz, made by oracle/make_golden.py)
+    open(meme, "wb").write(bytes(np.load(os.path.join(ROOT, "tests", "golden", "jund_pwm_k1.npz"))["sites_text"]))
+    os.makedirs(out)
+    nmotif = 6
+    cmd = [exe, out, fa, "--PWMFile", meme, "--maxPWM", str(nmotif), "--EM", "-k", str(wl["K"]), "-K", str(wl["K_bg"]), "--alphabet", "EXTENDED", "--verbose"]
+    env = dict(os.environ)
+    if ref:
+        cmd += ["--threads", str(os.cpu_count() or 1)]
+    else:
+        env.update(BAMM_DEVICES=",".join(str(d) for d in range(max(args.gpus, 1))), BAMM_TRACE="1")
+    t0 = time.perf_counter()
+    p = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    wall = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise SystemExit("CLI failed: %s" % p.stderr[-500:])
+    iters = sum(1 for l in p.stdout.splitlines() if " iter, llh=" in l)
+    em_s = sum(float(l.split("Runtime for EM:")[1].split("seconds")[0]) for l in p.stdout.splitlines() if "Runtime for EM:" in l)
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    bp = nseq * wl["L0"]
+    value = bp * iters / em_s if em_s > 0 else 0.0
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": iters, "warmup": 0, "ms_per_step": em_s / max(iters, 1) * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "nseq": nseq, "L0": wl["L0"], "K": wl["K"], "K_bg": wl["K_bg"], "alphabet": "EXTENDED (A=6)", "motifs": nmotif,
+                       "em_iterations_all_motifs": iters, "em_seconds": em_s, "wall_s": wall, "seed": args.seed,
+                       "positions_iter_per_s": nseq * (2 * wl["L0"] + 1) * iters / em_s if em_s > 0 else 0.0,
+                       "step": "one EM iteration of one motif (EM::optimize until the reference's stop rule, six motifs one after the other)"},
+            "e2e": {"value": bp * iters / wall, "unit": UNIT, "h2d_bytes_per_step": int(nseq * (2 * wl["L0"] + 1) / max(iters, 1)) if not ref else 0,
+                    "d2h_bytes_per_step": 20 if not ref else 0, "seconds": wall, "what": "FASTA in, six .ihbcp files out: wall clock of the whole process"},
+            "gpu_launches": None if ref else "not counted (separate process)"}
+    if ref:
+        line.update({"impl": "reference", "gpu_launches": 0,
+                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                      "sample": "%d x %d bp, same command line, the reference's own binary" % (nseq, wl["L0"])}})
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def run_c4(args, wl):
     if args.full:
         return run_c4_full(args, wl)
@@ -530,6 +585,8 @@ def main():
     wl = dict(synth.WORKLOADS[args.workload], name=args.workload)
     if args.workload == "c4":
         return run_c4(args, wl)
+    if args.workload == "c5":
+        return run_c5(args, wl)
     wl["cpu_sample"] = {"c3": 40_000, "c2": 50_000, "tiny": 2_000}[args.workload]
     if args.K >= 0 or args.W or args.L0:              # sweep variants are labelled as such: not a BASELINE.json config
         if args.K >= 0: wl["K"] = args.K; wl["K_bg"] = min(wl["K_bg"], args.K)
