@@ -196,6 +196,9 @@ struct bamm_em {
     float* d_btab = nullptr;    // bound tables
     float* d_U = nullptr;       // maxima of s over dropped context bases, per level
     uint32_t* d_cand = nullptr; uint2* d_cand_seq = nullptr; uint64_t* d_creg_off = nullptr;
+    uint64_t cand_slots = 0;         // entries of the candidate list
+    float* d_cand_part = nullptr;    // column passes: partial product per candidate slot (k_eexact)
+    float* d_mask_part = nullptr;    // column passes: partial product per masked window of every sequence (k_emasked)
     ulonglong2* d_seqacc = nullptr;  // per list sequence: normaliser terms of its masked windows (k_emasked -> k_eexact)
     uint32_t* d_eflags = nullptr;   // CandList::flags (4 words)
     bool r_mat = true;          // d_r holds the posteriors of the last E-step (false after a pruned E-step until bamm_em_get_r)

@@ -35,7 +35,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     cudaFree(em->d_peer_local); cudaFree(em->d_peer_done); cudaFree(em->d_peer_wait);
     cudaFree(em->d_act); cudaFree(em->d_scale); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
     cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab); cudaFree(em->d_tab_alt);
-    cudaFree(em->d_btab); cudaFree(em->d_U); cudaFree(em->d_cand); cudaFree(em->d_cand_seq); cudaFree(em->d_seqacc); cudaFree(em->d_creg_off); cudaFree(em->d_eflags);
+    cudaFree(em->d_btab); cudaFree(em->d_U); cudaFree(em->d_cand); cudaFree(em->d_cand_seq); cudaFree(em->d_seqacc); cudaFree(em->d_cand_part); cudaFree(em->d_mask_part); cudaFree(em->d_creg_off); cudaFree(em->d_eflags);
     cudaFree(em->d_s_alt); cudaFree(em->d_sT_alt);
     cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_sT); cudaFree(em->d_v);
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
@@ -476,6 +476,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
                     if (cap + masked > rcap) { if (rcap <= masked && win[w]) ok = false; else cap = rcap > masked ? rcap - masked : 0; }
                     creg[w + 1] = creg[w] + cap;
                 }
+                em->cand_slots = creg[em->nregions];
                 if (ok && dev_malloc(&em->d_cand, (creg[em->nregions] ? creg[em->nregions] : 1) * sizeof(uint32_t)) == cudaSuccess) {
                     CUE(dev_malloc(&em->d_cand_seq, (size_t)em->npk * sizeof(uint2)));
                     CUE(dev_malloc(&em->d_seqacc, (size_t)em->npk * sizeof(ulonglong2)));
@@ -556,11 +557,15 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
         }
         // pruned path: worth it when the bound needs at least three lookups fewer than the exact product (BAMM_SPARSE=1: whenever fewer)
         em->sparse = false;
-        if (em->cand_ok && em->gplans.size() == 1 && em->plain_words && !getenv("BAMM_NO_SPARSE") && em->K >= 1 &&
+        const bool multi_pass = em->gplans.size() > 1;
+        if (em->cand_ok && (em->plain_words || multi_pass) && !getenv("BAMM_NO_SPARSE") && em->K >= 1 &&
             make_bound_plan(em->W, em->K, em->K_bg, em->tab_capacity, em->bplan, em->bfast)) {
-            // the bound pass costs G1/2 lookups per window (two windows per entry)
+            // the bound pass costs G1/2 lookups per window (two windows per entry); with column passes the exact product costs
+            // the groups of all passes plus a round trip of the partial product per extra pass
+            int Gall = 0;
+            for (const GroupPlan& g : em->gplans) Gall += g.G;
             const int need = getenv("BAMM_SPARSE") && atoi(getenv("BAMM_SPARSE")) > 0 ? 1 : 3;
-            em->sparse = (em->bplan.G + 1) / 2 + need <= em->gplans[0].G;
+            em->sparse = (em->bplan.G + 1) / 2 + need <= Gall;
         }
         if (em->gplans.size() > em->tab_passes) {
             CU(cudaStreamSynchronize(em->stream));
@@ -581,12 +586,19 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
                 for (int a = 1; a <= em->K && a < 12; a++) { em->blev.off[a] = off; off += (uint32_t)em->W << (2 * a); }
                 CU(dev_malloc(&em->d_U, (size_t)(off ? off : 1) * sizeof(float)));
             }
-            // per-warp staging of the sequence words in the exact pass, when shared memory has room left
-            em->stage = (size_t)em->gplans[0].table_bytes + (em->plain_words ? plain_bytes : 0) + estep_stage_bytes(em->block_pe) <= em->tab_capacity && !getenv("BAMM_NO_STAGE");
-            if (launch_estep_masked(l, true, em->gfast[0] != 0, nullptr, em->gplans[0], nullptr, nullptr, em->plain_words, nullptr, nullptr, nullptr) ||
-                launch_estep_bound(l, true, em->bfast, nullptr, em->bplan, nullptr, nullptr) ||
-                launch_estep_exact(l, true, em->gfast[0] != 0, nullptr, em->gplans[0], nullptr, nullptr, nullptr, em->plain_words, em->stage, nullptr, nullptr, nullptr, nullptr))
-                return fail(BAMM_E_CUDA, "cannot opt in to shared memory for the pruned E-step");
+            // per-warp staging of the sequence words in the exact pass, when shared memory has room left in every pass
+            em->stage = !getenv("BAMM_NO_STAGE");
+            for (const GroupPlan& g : em->gplans)
+                if ((size_t)g.table_bytes + (em->plain_words ? plain_bytes : 0) + estep_stage_bytes(em->block_pe) > em->tab_capacity) em->stage = false;
+            if (launch_estep_bound(l, true, em->bfast, nullptr, em->bplan, nullptr, nullptr)) return fail(BAMM_E_CUDA, "cannot opt in to shared memory for the pruned E-step");
+            for (size_t i = 0; i < em->gplans.size(); i++)
+                if (launch_estep_masked(l, true, em->gfast[i] != 0, nullptr, em->gplans[i], nullptr, nullptr, nullptr, em->plain_words, nullptr, nullptr, nullptr, nullptr) ||
+                    launch_estep_exact(l, true, em->gfast[i] != 0, nullptr, em->gplans[i], nullptr, nullptr, nullptr, em->plain_words, em->stage, nullptr, nullptr, nullptr, nullptr, nullptr))
+                    return fail(BAMM_E_CUDA, "cannot opt in to shared memory for the pruned E-step");
+            if (multi_pass && !em->d_cand_part) {      // partial products between the column passes: per candidate slot, per masked window
+                CU(dev_malloc(&em->d_cand_part, (size_t)(em->cand_slots ? em->cand_slots : 1) * sizeof(float)));
+                CU(dev_malloc(&em->d_mask_part, (size_t)em->npk * (size_t)(2 * em->W + em->K - 1) * sizeof(float)));
+            }
         }
     }
     tr.mark("plan + table buffer + opt-in");
@@ -643,16 +655,24 @@ static int launch_estep(bamm_em* em, cudaEvent_t* split = nullptr /* 2 events: a
             const CandList cl = clist_of(em);
             GroupPlan bp = em->bplan; bp.q = em->q;
             bp.thr0 = FX_HALF_UNIT * (1.0f - em->q) * 0.999f * 0.9999f;          // margin: bound and product round differently
-            const GroupPlan gp = plan_for_launch(em, 0, em->q);
-            if (launch_estep_masked(l, false, em->gfast[0] != 0, &pv, gp, em->d_tab, em->d_s, em->plain_words, &cl, em->d_seqacc, &al))
-                return fail(BAMM_E_CUDA, "E-step launch failed (masked windows)");
+            const size_t np = em->gplans.size();
+            auto tab_of = [&](size_t pass) { return (const float*)((const char*)em->d_tab + pass * em->tab_capacity); };
+            for (size_t pass = 0; pass < np; pass++)
+                if (launch_estep_masked(l, false, em->gfast[pass] != 0, &pv, plan_for_launch(em, pass, em->q), tab_of(pass), em->d_s, em->d_sT, em->plain_words, &cl,
+                                        em->d_seqacc, np > 1 ? em->d_mask_part : nullptr, &al))
+                    return fail(BAMM_E_CUDA, "E-step launch failed (masked windows)");
             if (split) CU(cudaEventRecord(split[0], em->stream));
             if (launch_estep_bound(l, false, em->bfast, &pv, bp, em->d_btab, &cl)) return fail(BAMM_E_CUDA, "E-step launch failed (bounds)");
             if (split) CU(cudaEventRecord(split[1], em->stream));
-            if (launch_estep_exact(l, false, em->gfast[0] != 0, &pv, gp, em->d_tab, em->d_s, em->d_sT, em->plain_words, em->stage, &cl, em->d_seqacc, scal, &al))
-                return fail(BAMM_E_CUDA, "E-step launch failed (candidates)");
-            if (launch_estep_dense(l, false, em->gfast[0] != 0, false, &pv, gp, em->d_tab, em->d_s, em->d_sT, em->plain_words, em->d_r, scal, &al, em->d_eflags))
-                return fail(BAMM_E_CUDA, "packed E-step launch failed");
+            for (size_t pass = 0; pass < np; pass++)
+                if (launch_estep_exact(l, false, em->gfast[pass] != 0, &pv, plan_for_launch(em, pass, em->q), tab_of(pass), em->d_s, em->d_sT, em->plain_words, em->stage, &cl,
+                                       em->d_seqacc, np > 1 ? em->d_cand_part : nullptr, scal, &al))
+                    return fail(BAMM_E_CUDA, "E-step launch failed (candidates)");
+            for (size_t pass = 0; pass < np; pass++)
+                if (launch_estep_dense(l, false, em->gfast[pass] != 0, np > 1, &pv, plan_for_launch(em, pass, em->q), tab_of(pass), em->d_s, em->d_sT, em->plain_words, em->d_r, scal,
+                                       &al, em->d_eflags))
+                    return fail(BAMM_E_CUDA, "packed E-step launch failed");
+            em->launches += 3 * (np - 1);
         } else {
             if (split) { CU(cudaEventRecord(split[0], em->stream)); CU(cudaEventRecord(split[1], em->stream)); }
             for (size_t pass = 0; pass < em->gplans.size(); pass++)
@@ -1162,9 +1182,11 @@ extern "C" int bamm_em_get_r(bamm_em* em, uint64_t first, uint64_t count, float*
         PackedView pv = pview_of(em);
         const EStepLaunch l = {em->grid_pe, em->block_pe, em->stream};
         ActiveList al = alist_of(em); al.ent = nullptr;
-        if (launch_estep_dense(l, false, em->gfast[0] != 0, false, &pv, plan_for_launch(em, 0, em->q_e), em->d_tab_e, em->d_s_e, em->d_sT_e, em->plain_words, em->d_r, nullptr, &al, nullptr))
-            return fail(BAMM_E_CUDA, "packed E-step launch failed (materialising r)");
-        em->launches += 1;
+        for (size_t pass = 0; pass < em->gplans.size(); pass++)
+            if (launch_estep_dense(l, false, em->gfast[pass] != 0, em->gplans.size() > 1, &pv, plan_for_launch(em, pass, em->q_e),
+                                   (const float*)((const char*)em->d_tab_e + pass * em->tab_capacity), em->d_s_e, em->d_sT_e, em->plain_words, em->d_r, nullptr, &al, nullptr))
+                return fail(BAMM_E_CUDA, "packed E-step launch failed (materialising r)");
+        em->launches += em->gplans.size();
         em->r_mat = true; em->r_scaled = false;
     }
     if (!em->r_scaled) {            // the packed E-step keeps r unnormalised; finish it before it leaves the device

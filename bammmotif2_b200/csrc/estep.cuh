@@ -97,8 +97,9 @@ struct MaskedTabs {
 };
 // window p of a sequence of length L with the structural N at `mid` (-1: none), product over the columns j <= jmax that exist
 // (EM.cpp:167) and belong to this column pass. Whole untouched groups come from the group tables (ascending g), then the
-// columns whose k-mer holds a draw of the N (the K+1 patched k-mers `yp` of the sequence, ascending position), then the other
-// single columns (ascending j). A full window away from the N multiplies exactly what groups_prod multiplies.
+// remaining columns in ascending j from the plain table — with the k-mer of the stream, or, where it holds a draw of the N,
+// the patched k-mer `yp[j - (mid - p)]` of the sequence. A full window away from the N multiplies exactly what groups_prod
+// multiplies; k_emasked multiplies in the same order.
 template <int G, bool FAST>
 __device__ __forceinline__ float masked_prod(const GroupConsts<G>& c, const GroupPlan& gp, const MaskedTabs& mt, uint32_t whi, uint32_t wlo,
                                              int p, int jmax, int mid, const uint16_t* yp, float prod) {
@@ -123,49 +124,15 @@ __device__ __forceinline__ float masked_prod(const GroupConsts<G>& c, const Grou
         prod *= v;
         cols = good ? cols & ~cm : cols;
     }
-    if (mt.plain_s) {
-        // plain table in shared memory: one loop over the columns the groups left, k-mer from the stream or from the patch list
-        const int jn = mid - p;
-        while (cols) {
-            const int j = __ffs(cols) - 1;
-            cols &= cols - 1u;
-            uint32_t y = field(w, 62 - 2 * mt.KD - 2 * j, mt.maskK);
-            if (over_n && (uint32_t)(j - jn) <= (uint32_t)K) y = yp[j - jn];
-            prod *= lds_f32(((uint32_t)j * (mt.Yn + 1u) + y) << 2, mt.plain_s);
-        }
-        return prod;
-    }
-    if (__any_sync(FULL, over_n)) {
-        for (int d0 = 0; d0 <= K; d0 += 4) {
-            float f[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int d = d0 + u, j = mid + d - p;
-                f[u] = 1.0f;
-                if (d <= K && over_n && j >= 0 && j <= jmax && ((mt.passmask >> j) & 1u)) {
-                    const uint32_t y = yp[d];
-                    f[u] = __ldg(&mt.s_rows[(uint64_t)y * W + j]);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) prod *= f[u];
-        }
-        cols &= ~ncols;
-    }
-    while (cols) {                          // four per round so that their loads are in flight together
-        float f[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            f[u] = 1.0f;
-            if (cols) {
-                const int j = __ffs(cols) - 1;
-                cols &= cols - 1u;
-                const uint32_t y = field(w, 62 - 2 * mt.KD - 2 * j, mt.maskK);
-                f[u] = __ldg(&mt.s_g[(uint32_t)j * mt.Yn + y]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) prod *= f[u];
+    // one loop over the columns the groups left, in ascending order: k-mer from the stream or from the patch list, value from the
+    // shared-memory copy of the plain table or from the global one (column passes, tables beyond shared memory)
+    const int jn = mid - p;
+    while (cols) {
+        const int j = __ffs(cols) - 1;
+        cols &= cols - 1u;
+        uint32_t y = field(w, 62 - 2 * mt.KD - 2 * j, mt.maskK);
+        if (over_n && (uint32_t)(j - jn) <= (uint32_t)K) y = yp[j - jn];
+        prod *= mt.plain_s ? lds_f32(((uint32_t)j * (mt.Yn + 1u) + y) << 2, mt.plain_s) : __ldg(&mt.s_g[(uint32_t)j * mt.Yn + y]);
     }
     return prod;
 }
@@ -465,7 +432,8 @@ struct MaskedStep { uint32_t good, lo, hi, pad; };
 template <int G, bool FAST>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
-          uint32_t plain_words, CandList cl, ulonglong2* __restrict__ seqacc, ActiveList al) {
+          const float* __restrict__ s_rows, uint32_t plain_words, CandList cl, ulonglong2* __restrict__ seqacc,
+          float* __restrict__ partial /* column passes: [nlist][2W+K-1] partial products, else nullptr */, ActiveList al) {
     extern __shared__ float tab[];
     __shared__ __align__(16) MaskedStep steps[2][48];   // [0]: truncated windows t = p - tl, [1]: windows over the N, t = p - (mid-W+1)
     if (cl.flags[0] != 0u) return;
@@ -479,7 +447,7 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
         if (!which) { const int jmax = W - 2 - t; valid = jmax >= 0 ? ((2u << jmax) - 1u) : 0u; }
         else { const int jn = W - 1 - t, ja = max(jn, 0), jb = min(jn + K, W - 1); if (jb >= ja) ncols = ((2u << jb) - 1u) & ~((1u << ja) - 1u); }
         const uint32_t bad = ~valid | ncols;
-        uint32_t good = 0u, cols = valid;
+        uint32_t good = 0u, cols = valid & gp.passmask;             // only the columns of this pass
         for (int g = 0; g < G; g++) if ((gp.colmask[g] & bad) == 0u) { good |= 1u << g; cols &= ~gp.colmask[g]; }
         cols &= ~ncols;                           // the patched columns have their own (unrolled) loop
         const int jn = W - 1 - t;
@@ -494,9 +462,12 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
     const float thr0 = gp.thr0;
     GroupConsts<G> gc; load_consts<G>(gc, gp, tab_s);
     const uint32_t plain_s = tab_s + gp.table_bytes, maskK = gp.Yn - 1u, ystride = gp.Yn + 1u;
-    MaskedTabs mt; mt.s_g = s_g; mt.s_rows = nullptr; mt.plain_s = plain_s;
-    mt.Yn = gp.Yn; mt.maskK = maskK; mt.passmask = 0xffffffffu; mt.W = W; mt.K = K; mt.KD = KD;
-    Emitter em; em.init(al, warp, true);
+    const bool first = gp.pass_first != 0, last = gp.pass_last != 0;       // column passes: partial products travel through `part`
+    const uint32_t plain_on = plain_words ? plain_s : 0u;
+    MaskedTabs mt; mt.s_g = s_g; mt.s_rows = s_rows; mt.plain_s = plain_on;
+    mt.Yn = gp.Yn; mt.maskK = maskK; mt.passmask = gp.passmask; mt.W = W; mt.K = K; mt.KD = KD;
+    const int npart = 2 * W + K - 1;
+    Emitter em; em.init(al, warp, last);
     // a warp takes the sequences k_eexact gives it (li = warp mod nwarps), 32 at a time: the two kernels share the warp's region
     for (uint64_t k0 = 0; warp + nwarps * k0 < pv.nlist; k0 += 32) {
         const uint64_t li64 = warp + (uint64_t)nwarps * (k0 + lane);
@@ -539,13 +510,17 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
                 for (int t = 0; t < nt; t++) {
                     const MaskedStep st = steps[part][t];
                     const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
+                    float* const pp = partial ? partial + (size_t)li * npart + (part ? nt_tail : 0) + t : nullptr;
                     float prod = 1.0f;
+                    if (!first && mine) prod = *pp;
 #pragma unroll
                     for (int g = 0; g < G; g++)
                         if ((st.good >> g) & 1u) prod *= lds_f32(group_offset<G, FAST>(gc, g, whi, wlo), gc.ab[g]);
+                    auto plain_at = [&](int j, uint32_t y) {                 // s[j][y]: shared-memory copy, or the global table
+                        return plain_on ? lds_f32(((uint32_t)j * ystride + y) << 2, plain_s) : __ldg(&s_g[(uint32_t)j * gp.Yn + y]);
+                    };
                     auto single = [&](int j) {                               // column j with the k-mer of the stream
-                        const uint32_t y = field(w, 62 - 2 * KD - 2 * j, maskK);
-                        prod *= lds_f32(((uint32_t)j * ystride + y) << 2, plain_s);
+                        prod *= plain_at(j, field(w, 62 - 2 * KD - 2 * j, maskK));
                     };
                     for (uint32_t c = st.lo; c; c &= c - 1u) single(__ffs(c) - 1);
                     if (part) {
@@ -553,16 +528,19 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
 #pragma unroll
                         for (int d = 0; d < 11; d++) {
                             const int j = jn + d;
-                            if (d <= K && j >= 0 && j < W) {                  // warp-uniform
+                            if (d <= K && j >= 0 && j < W && ((gp.passmask >> j) & 1u)) {          // warp-uniform
                                 const uint32_t y = (ypk[d >> 1] >> (16 * (d & 1))) & 0xffffu;
-                                prod *= lds_f32(((uint32_t)j * ystride + y) << 2, plain_s);
+                                prod *= plain_at(j, y);
                             }
                         }
                     }
                     for (uint32_t c = st.hi; c; c &= c - 1u) single(__ffs(c) - 1);
-                    const float val = mine ? prod * pos : 0.0f;
-                    acc.add(val);
-                    em.template put<true>(al, val >= thr0, woff, pcode_of(p_first + t, part ? W - 1 : W - 2 - t, part != 0), val, li);
+                    if (!last) { if (mine) *pp = prod; }
+                    else {
+                        const float val = mine ? prod * pos : 0.0f;
+                        acc.add(val);
+                        em.template put<true>(al, val >= thr0, woff, pcode_of(p_first + t, part ? W - 1 : W - 2 - t, part != 0), val, li);
+                    }
                     // next base
                     whi = __funnelshift_l(wlo, whi, 2); wlo = __funnelshift_l(nxt, wlo, 2); nxt <<= 2;
                     if (--nleft == 0) { nxt = wseq[nw++]; nleft = 16; }
@@ -581,15 +559,21 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
                 uint32_t whi, wlo;
                 window_bits(wseq, p - KD, whi, wlo);
                 const int jmax = on ? min(W - 1, L - W - p) : -1;
-                const float prod = masked_prod<G, FAST>(gc, gp, mt, whi, wlo, p, jmax, mid, yp, 1.0f);
-                const float val = on ? prod * pos : 0.0f;
-                acc.add(val);
-                em.template put<true>(al, val >= thr0, woff, pcode_of(p, jmax, mid >= 0 && p <= mid + K && p + W - 1 >= mid), val, li);
+                float* const pp = partial && idx < npart ? partial + (size_t)li * npart + idx : nullptr;
+                float prod = 1.0f;
+                if (!first && on && pp) prod = *pp;
+                prod = masked_prod<G, FAST>(gc, gp, mt, whi, wlo, p, jmax, mid, yp, prod);
+                if (!last) { if (on && pp) *pp = prod; }
+                else {
+                    const float val = on ? prod * pos : 0.0f;
+                    acc.add(val);
+                    em.template put<true>(al, val >= thr0, woff, pcode_of(p, jmax, mid >= 0 && p <= mid + K && p + W - 1 >= mid), val, li);
+                }
             }
         }
-        if (have) seqacc[li] = make_ulonglong2(acc.a, acc.b);
+        if (have && last) seqacc[li] = make_ulonglong2(acc.a, acc.b);
     }
-    al.cnt_back[warp] = em.bpos;
+    if (last) al.cnt_back[warp] = em.bpos;
 }
 
 // ---- pruned E-step, part 2: exact evaluation of the listed windows -------------------------------------------------
@@ -603,7 +587,8 @@ template <int G, bool FAST>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
          const float* __restrict__ s_rows, uint32_t plain_words, uint32_t stage /* 0: no staging buffer */, CandList cl,
-         const ulonglong2* __restrict__ seqacc, unsigned long long* __restrict__ scal, ActiveList al) {
+         const ulonglong2* __restrict__ seqacc, float* __restrict__ partial /* column passes: one float per candidate slot, else nullptr */,
+         unsigned long long* __restrict__ scal, ActiveList al) {
     extern __shared__ float tab[];
     if (cl.flags[0] != 0u) return;
     for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
@@ -620,8 +605,10 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
     GroupConsts<G> gc; load_consts<G>(gc, gp, tab_s);
     MaskedTabs mt; mt.s_g = s_g; mt.s_rows = s_rows; mt.plain_s = plain_words ? tab_s + gp.table_bytes : 0u;
     mt.Yn = gp.Yn; mt.maskK = gp.Yn - 1; mt.passmask = 0xffffffffu; mt.W = W; mt.K = K; mt.KD = KD;
-    Emitter em; em.init(al, warp, true);
+    const bool first = gp.pass_first != 0, last = gp.pass_last != 0;       // column passes (tables of all columns beyond shared memory)
+    Emitter em; em.init(al, warp, last);
     em.bpos = al.cnt_back[warp];                                        // the back of the region is k_emasked's
+    float* const preg = partial ? partial + cl.reg_off[warp] : nullptr;
     uint32_t* const stg = reinterpret_cast<uint32_t*>(tab + (gp.table_bytes >> 2) + plain_smem_words(plain_words, gp.Yn)) + (threadIdx.x >> 5) * STAGE_WORDS;
     const uint32_t* __restrict__ creg = cl.ent + cl.reg_off[warp];
     uint32_t li = warp;
@@ -671,13 +658,18 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
                 if (e0 + 32 + lane < sc.y) c_first = cand[e0 + 32 + lane];      // next batch
                 uint32_t whi, wlo;
                 window_bits(wsrc, p - KD, whi, wlo);
-                const float prod = groups_prod<G, FAST>(gc, whi, wlo, 1.0f);
+                float* const pp = preg ? preg + sc.x + e0 + lane : nullptr;
+                float prod = 1.0f;
+                if (!first && on) prod = *pp;
+                prod = groups_prod<G, FAST>(gc, whi, wlo, prod);
+                if (!last) { if (on) *pp = prod; continue; }
                 const float val = on ? prod * pos : 0.0f;
                 acc.add(val);
                 if (!defer) em.template put<false>(al, val >= thr0, woff, pcode_of(p, W - 1, false), val, li);
                 else if (e0 == 0u) { v0 = val; q0 = p; }
                 else { v1 = val; q1 = p; }
             }
+            if (!last) { if (!more) break; li = li_next; n = n_next; n_next = n_nn; sq = sq_next; sc = sc_next; continue; }
             if (lane == 0) { const ulonglong2 m = seqacc[li]; acc.a += m.x; acc.b += m.y; }      // the masked windows (k_emasked)
             const float norm = finish_sequence(acc, one_minus_q, lane, li, al.scale, llh_fx, rsum_fx);
             if (defer && sc.y) {
@@ -689,6 +681,7 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
             li = li_next; n = n_next; n_next = n_nn; sq = sq_next; sc = sc_next;
         }
     }
+    if (!last) return;
     if (lane == 0) {
         if (llh_fx) atomicAdd(&scal[0], (unsigned long long)llh_fx);
         if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);

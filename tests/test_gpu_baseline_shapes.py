@@ -4,7 +4,7 @@ SEVERAL sequences and the benchmarked kernel plans are the ones that run:
 
   c3 down-sample  40 000 x 500 bp, W=20, K=4, K_bg=2   (the G=8 one-shift plan of the headline configuration)
   c2 full         50 000 x 200 bp, W=12, K=2
-  K=5, W=20       10 000 x 500 bp                      (two column passes of the exact E-step)
+  K=5, W=20       10 000 x 500 bp                      (column passes: the pruned E-step carries partial products between them)
   A=6, K=5, W=12  10 000 x 100 bp                      (EXTENDED alphabet: generic index-array path)
 
 each on the default path (c3: the PRUNED E-step — bound pass, exact pass over the candidates, list M-step) and with an active
@@ -136,6 +136,9 @@ def test_per_iteration_parity_on_baseline_shapes(capi, oracle, shape):
             tag = "%s it%d %s" % (shape, it + 1, env or "default")
             llh = em.estep()
             info = em.estep_info()
+            if shape == "k5_w20" and not env:
+                assert info["pruned"] and info["passes"] > 1 and not info["dense_ran"], (tag, info)     # pruned path with column passes
+                print(tag, info)
             if shape == "c3_40k":       # the benchmarked plan: pruned by default, the two fall-backs when a list is too small
                 assert info["pruned"] == ("BAMM_LIST_FRAC" not in env), (tag, info)
                 assert info["dense_ran"] == bool(env), (tag, info)
