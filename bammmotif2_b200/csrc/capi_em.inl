@@ -280,7 +280,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
     bool packed_ok = s->A == 4 && s->nregular > 0 && Yn64 <= 65536 &&
                      Yn64 * 8 <= (uint64_t)max_optin && !getenv("BAMM_NO_PACKED");
     em->tab_capacity = (size_t)max_optin;
-    if (getenv("BAMM_TABLE_BYTES")) em->tab_capacity = std::min(em->tab_capacity, (size_t)atol(getenv("BAMM_TABLE_BYTES")));
+    if (getenv("BAMM_TABLE_BYTES")) em->tab_capacity = std::min(em->tab_capacity, (size_t)atol(getenv("BAMM_TABLE_BYTES")) & ~(size_t)255);   // the tables of a pass start 16-byte aligned (bulk copies)
     if (packed_ok) {
         // both variants (with / without the reduced context of the leading columns) must be plannable
         std::vector<GroupPlan> tmp; std::vector<char> f;

@@ -119,6 +119,39 @@ constexpr uint32_t DENSE_HOLD = 8;
 
 struct MTables { uint32_t nrep, rstride; };      // packed M-step: table copies per CTA and their stride in words (rstride >= NC * Yn)
 
+// ---- table staging: global -> shared memory with the TMA (1-D bulk copies, no tensor map) --------------------------
+// Thread 0 arms an mbarrier with the byte count and issues cp.async.bulk copies of up to 64 KB; every thread of the CTA then
+// waits on the barrier's phase. The copy engine moves the tables while the threads do other set-up work (copying the padded
+// plain table, building step tables), instead of 50 dependent load / store rounds per thread. bytes: multiple of 16; both
+// pointers 16-byte aligned. Call bulk_stage_begin from all threads (it contains a __syncthreads), bulk_stage_wait before the
+// first use of the tables. One staging per kernel launch (phase 0 of the barrier).
+__device__ __forceinline__ void bulk_stage_begin(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* mbar) {
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes) : "memory");
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+        const char* src = static_cast<const char*>(gmem_src);
+        for (uint32_t off = 0; off < bytes; off += 65536u) {
+            const uint32_t n = bytes - off < 65536u ? bytes - off : 65536u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst + off), "l"(src + off), "r"(n), "r"(mb) : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void bulk_stage_wait(unsigned long long* mbar) {
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar);
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mb), "r"(0u) : "memory");
+    } while (!done);
+}
+
 // shared-memory load at (per-lane byte offset) + (warp-uniform base): one LDS with a uniform-register base operand
 __device__ __forceinline__ float lds_f32(uint32_t off, uint32_t ubase) {
     float v;

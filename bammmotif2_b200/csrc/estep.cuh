@@ -181,10 +181,12 @@ __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g /* [W][Yn] */,
                const float* __restrict__ s_rows /* [Yn][W] */, uint32_t plain_words, float* __restrict__ r, unsigned long long* __restrict__ scal,
                ActiveList al, const uint32_t* __restrict__ only_if) {
-    extern __shared__ float tab[];
+    extern __shared__ __align__(16) float tab[];
+    __shared__ unsigned long long stage_bar;
     if (only_if != nullptr && *only_if == 0u) return;
-    for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
+    bulk_stage_begin(tab, tab_g, gp.table_bytes, &stage_bar);
     for (uint32_t i = threadIdx.x; i < plain_words; i += blockDim.x) tab[(gp.table_bytes >> 2) + i + i / gp.Yn] = s_g[i];   // rows padded by one float
+    bulk_stage_wait(&stage_bar);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -306,11 +308,12 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
 template <int G1, bool FAST>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_ebound(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, CandList cl) {
-    extern __shared__ float tab[];
+    extern __shared__ __align__(16) float tab[];
+    __shared__ unsigned long long stage_bar;
     volatile uint32_t* flags = cl.flags;
     if (flags[0] != 0u) return;
-    for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
-    __syncthreads();
+    bulk_stage_begin(tab, tab_g, gp.table_bytes, &stage_bar);
+    bulk_stage_wait(&stage_bar);
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
@@ -429,15 +432,16 @@ k_ebound(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
 // per window index: bit g of good = group g whole; the other columns come from the plain table, in ascending order: the
 // unpatched ones below the N's k-mers (lo), the K+1 patched ones, the unpatched ones above (hi)
 struct MaskedStep { uint32_t good, lo, hi, pad; };
-template <int G, bool FAST>
+template <int G, bool FAST, bool LEAN /* one pass with the plain table in shared memory: no partial products, no global table */>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
           const float* __restrict__ s_rows, uint32_t plain_words, CandList cl, ulonglong2* __restrict__ seqacc,
           float* __restrict__ partial /* column passes: [nlist][2W+K-1] partial products, else nullptr */, ActiveList al) {
-    extern __shared__ float tab[];
+    extern __shared__ __align__(16) float tab[];
+    __shared__ unsigned long long stage_bar;
     __shared__ __align__(16) MaskedStep steps[2][48];   // [0]: truncated windows t = p - tl, [1]: windows over the N, t = p - (mid-W+1)
     if (cl.flags[0] != 0u) return;
-    for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
+    bulk_stage_begin(tab, tab_g, gp.table_bytes, &stage_bar);
     for (uint32_t i = threadIdx.x; i < plain_words; i += blockDim.x) tab[(gp.table_bytes >> 2) + i + i / gp.Yn] = s_g[i];   // rows padded by one float
     const int W = gp.W, K = gp.K, KD = gp.kd;
     const int nt_tail = W - 1, nt_n = W + K;
@@ -454,6 +458,7 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
         const uint32_t below = which && jn > 0 ? ((1u << min(jn, 31)) - 1u) : (which ? 0u : 0xffffffffu);
         steps[which][t].good = good; steps[which][t].lo = cols & below; steps[which][t].hi = cols & ~below; steps[which][t].pad = 0u;
     }
+    bulk_stage_wait(&stage_bar);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -462,8 +467,8 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
     const float thr0 = gp.thr0;
     GroupConsts<G> gc; load_consts<G>(gc, gp, tab_s);
     const uint32_t plain_s = tab_s + gp.table_bytes, maskK = gp.Yn - 1u, ystride = gp.Yn + 1u;
-    const bool first = gp.pass_first != 0, last = gp.pass_last != 0;       // column passes: partial products travel through `part`
-    const uint32_t plain_on = plain_words ? plain_s : 0u;
+    const bool first = LEAN || gp.pass_first != 0, last = LEAN || gp.pass_last != 0;    // column passes: partial products travel through `partial`
+    const uint32_t plain_on = LEAN ? plain_s : (plain_words ? plain_s : 0u);
     MaskedTabs mt; mt.s_g = s_g; mt.s_rows = s_rows; mt.plain_s = plain_on;
     mt.Yn = gp.Yn; mt.maskK = maskK; mt.passmask = gp.passmask; mt.W = W; mt.K = K; mt.KD = KD;
     const int npart = 2 * W + K - 1;
@@ -510,14 +515,14 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
                 for (int t = 0; t < nt; t++) {
                     const MaskedStep st = steps[part][t];
                     const unsigned long long w = ((unsigned long long)whi << 32) | wlo;
-                    float* const pp = partial ? partial + (size_t)li * npart + (part ? nt_tail : 0) + t : nullptr;
+                    float* const pp = !LEAN && partial ? partial + (size_t)li * npart + (part ? nt_tail : 0) + t : nullptr;
                     float prod = 1.0f;
-                    if (!first && mine) prod = *pp;
+                    if (!LEAN && !first && mine) prod = *pp;
 #pragma unroll
                     for (int g = 0; g < G; g++)
                         if ((st.good >> g) & 1u) prod *= lds_f32(group_offset<G, FAST>(gc, g, whi, wlo), gc.ab[g]);
                     auto plain_at = [&](int j, uint32_t y) {                 // s[j][y]: shared-memory copy, or the global table
-                        return plain_on ? lds_f32(((uint32_t)j * ystride + y) << 2, plain_s) : __ldg(&s_g[(uint32_t)j * gp.Yn + y]);
+                        return (LEAN || plain_on) ? lds_f32(((uint32_t)j * ystride + y) << 2, plain_s) : __ldg(&s_g[(uint32_t)j * gp.Yn + y]);
                     };
                     auto single = [&](int j) {                               // column j with the k-mer of the stream
                         prod *= plain_at(j, field(w, 62 - 2 * KD - 2 * j, maskK));
@@ -528,14 +533,14 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
 #pragma unroll
                         for (int d = 0; d < 11; d++) {
                             const int j = jn + d;
-                            if (d <= K && j >= 0 && j < W && ((gp.passmask >> j) & 1u)) {          // warp-uniform
+                            if (d <= K && j >= 0 && j < W && (LEAN || ((gp.passmask >> j) & 1u))) {          // warp-uniform
                                 const uint32_t y = (ypk[d >> 1] >> (16 * (d & 1))) & 0xffffu;
                                 prod *= plain_at(j, y);
                             }
                         }
                     }
                     for (uint32_t c = st.hi; c; c &= c - 1u) single(__ffs(c) - 1);
-                    if (!last) { if (mine) *pp = prod; }
+                    if (!LEAN && !last) { if (mine) *pp = prod; }
                     else {
                         const float val = mine ? prod * pos : 0.0f;
                         acc.add(val);
@@ -583,16 +588,18 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
 // three shared-memory reads instead of a gather; longer sequences gather from global memory. The records of the next
 // sequence are requested one sequence ahead.
 constexpr int STAGE_SEQ_WORDS = 96, STAGE_WORDS = STAGE_SEQ_WORDS + 8;      // + 16 patched k-mers (uint16)
-template <int G, bool FAST>
+template <int G, bool FAST, bool MULTI /* column passes: partial products between them */>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
          const float* __restrict__ s_rows, uint32_t plain_words, uint32_t stage /* 0: no staging buffer */, CandList cl,
          const ulonglong2* __restrict__ seqacc, float* __restrict__ partial /* column passes: one float per candidate slot, else nullptr */,
          unsigned long long* __restrict__ scal, ActiveList al) {
-    extern __shared__ float tab[];
+    extern __shared__ __align__(16) float tab[];
+    __shared__ unsigned long long stage_bar;
     if (cl.flags[0] != 0u) return;
-    for (uint32_t i = threadIdx.x; i < (gp.table_bytes >> 2); i += blockDim.x) tab[i] = tab_g[i];
+    bulk_stage_begin(tab, tab_g, gp.table_bytes, &stage_bar);
     for (uint32_t i = threadIdx.x; i < plain_words; i += blockDim.x) tab[(gp.table_bytes >> 2) + i + i / gp.Yn] = s_g[i];   // rows padded by one float
+    bulk_stage_wait(&stage_bar);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -605,10 +612,10 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
     GroupConsts<G> gc; load_consts<G>(gc, gp, tab_s);
     MaskedTabs mt; mt.s_g = s_g; mt.s_rows = s_rows; mt.plain_s = plain_words ? tab_s + gp.table_bytes : 0u;
     mt.Yn = gp.Yn; mt.maskK = gp.Yn - 1; mt.passmask = 0xffffffffu; mt.W = W; mt.K = K; mt.KD = KD;
-    const bool first = gp.pass_first != 0, last = gp.pass_last != 0;       // column passes (tables of all columns beyond shared memory)
+    const bool first = !MULTI || gp.pass_first != 0, last = !MULTI || gp.pass_last != 0;   // column passes (tables of all columns beyond shared memory)
     Emitter em; em.init(al, warp, last);
     em.bpos = al.cnt_back[warp];                                        // the back of the region is k_emasked's
-    float* const preg = partial ? partial + cl.reg_off[warp] : nullptr;
+    float* const preg = MULTI && partial ? partial + cl.reg_off[warp] : nullptr;
     uint32_t* const stg = reinterpret_cast<uint32_t*>(tab + (gp.table_bytes >> 2) + plain_smem_words(plain_words, gp.Yn)) + (threadIdx.x >> 5) * STAGE_WORDS;
     const uint32_t* __restrict__ creg = cl.ent + cl.reg_off[warp];
     uint32_t li = warp;
@@ -658,18 +665,18 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
                 if (e0 + 32 + lane < sc.y) c_first = cand[e0 + 32 + lane];      // next batch
                 uint32_t whi, wlo;
                 window_bits(wsrc, p - KD, whi, wlo);
-                float* const pp = preg ? preg + sc.x + e0 + lane : nullptr;
+                float* const pp = MULTI && preg ? preg + sc.x + e0 + lane : nullptr;
                 float prod = 1.0f;
-                if (!first && on) prod = *pp;
+                if (MULTI && !first && on) prod = *pp;
                 prod = groups_prod<G, FAST>(gc, whi, wlo, prod);
-                if (!last) { if (on) *pp = prod; continue; }
+                if (MULTI && !last) { if (on) *pp = prod; continue; }
                 const float val = on ? prod * pos : 0.0f;
                 acc.add(val);
                 if (!defer) em.template put<false>(al, val >= thr0, woff, pcode_of(p, W - 1, false), val, li);
                 else if (e0 == 0u) { v0 = val; q0 = p; }
                 else { v1 = val; q1 = p; }
             }
-            if (!last) { if (!more) break; li = li_next; n = n_next; n_next = n_nn; sq = sq_next; sc = sc_next; continue; }
+            if (MULTI && !last) { if (!more) break; li = li_next; n = n_next; n_next = n_nn; sq = sq_next; sc = sc_next; continue; }
             if (lane == 0) { const ulonglong2 m = seqacc[li]; acc.a += m.x; acc.b += m.y; }      // the masked windows (k_emasked)
             const float norm = finish_sequence(acc, one_minus_q, lane, li, al.scale, llh_fx, rsum_fx);
             if (defer && sc.y) {
@@ -681,7 +688,7 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
             li = li_next; n = n_next; n_next = n_nn; sq = sq_next; sc = sc_next;
         }
     }
-    if (!last) return;
+    if (MULTI && !last) return;
     if (lane == 0) {
         if (llh_fx) atomicAdd(&scal[0], (unsigned long long)llh_fx);
         if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);
