@@ -557,14 +557,16 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
         }
         // pruned path: worth it when the bound needs at least three lookups fewer than the exact product (BAMM_SPARSE=1: whenever fewer)
         em->sparse = false;
-        const bool multi_pass = em->gplans.size() > 1;
-        if (em->cand_ok && (em->plain_words || multi_pass) && !getenv("BAMM_NO_SPARSE") && em->K >= 1 &&
+        const bool multi_pass = em->gplans.size() > 1;       // (without the plain table in shared memory the single columns come from global memory)
+        if (em->cand_ok && !getenv("BAMM_NO_SPARSE") &&
             make_bound_plan(em->W, em->K, em->K_bg, em->tab_capacity, em->bplan, em->bfast)) {
             // the bound pass costs G1/2 lookups per window (two windows per entry); with column passes the exact product costs
             // the groups of all passes plus a round trip of the partial product per extra pass
             int Gall = 0;
             for (const GroupPlan& g : em->gplans) Gall += g.G;
-            const int need = getenv("BAMM_SPARSE") && atoi(getenv("BAMM_SPARSE")) > 0 ? 1 : 3;
+            // measured (profiles/r2j_sparse_threshold.txt): worth it as soon as the bound is cheaper than the product at all — K=1 W=20
+            // (G = 4 against 2 lookups per window): 1.40 -> 0.89 ms per 300k sequences. BAMM_SPARSE_MARGIN asks for more.
+            const int need = getenv("BAMM_SPARSE_MARGIN") ? atoi(getenv("BAMM_SPARSE_MARGIN")) : 1;
             em->sparse = (em->bplan.G + 1) / 2 + need <= Gall;
         }
         if (em->gplans.size() > em->tab_passes) {
