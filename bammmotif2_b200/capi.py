@@ -55,6 +55,7 @@ SIGNATURES = {
     "bamm_em_r_size": (C.c_uint64, [_vp]),
     "bamm_em_last_timing": (C.c_int, [_vp, _f32p, _f32p]),
     "bamm_em_loop_timing": (C.c_int, [_vp, C.POINTER(C.c_int), _f32p, _f32p, _f32p, _f32p]),
+    "bamm_bound_plan_describe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_int32), C.c_uint64, _u64p]),
     "bamm_set_device_group": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "bamm_get_device_group": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
     "bamm_em_loop_timing_estep": (C.c_int, [_vp, _f32p, _f32p, _f32p]),
@@ -115,6 +116,19 @@ def model_size(A, K, W):
 
 def bg_size(A, K):
     return sum(A ** (k + 1) for k in range(K + 1))
+
+
+def bound_plan_describe(W, K, K_bg, budget=232448):
+    """Bound plan of the pruned E-step as a dict (host arithmetic, no device): G, kd, fast, table_bytes, groups[...]; None without a plan."""
+    buf = (C.c_int32 * 256)()
+    n = C.c_uint64(0)
+    _check(load().bamm_bound_plan_describe(W, K, K_bg, budget, buf, 256, C.byref(n)))
+    if buf[0] == 0:
+        return None
+    G = buf[0]
+    names = ("col0", "ncol", "lo", "shift", "shift2", "mask4", "base")
+    groups = [dict(zip(names, [int(buf[4 + 7 * g + i]) & 0xffffffff if names[i] == "mask4" else int(buf[4 + 7 * g + i]) for i in range(7)])) for g in range(G)]
+    return dict(G=G, kd=int(buf[1]), fast=bool(buf[2]), table_bytes=int(buf[3]), groups=groups)
 
 
 def set_device_group(devices):

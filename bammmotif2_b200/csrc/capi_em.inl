@@ -179,7 +179,7 @@ static bool make_bound_plan(int W, int K, int K_bg, size_t budget, GroupPlan& gp
     int spare = 0; for (int t : T) spare += t; spare -= W;
     memset(&gp, 0, sizeof(gp));
     gp.W = W; gp.K = K; gp.G = G; gp.Yn = 1u << (2 * (K + 1));
-    const int lead = std::min(spare, std::min(1, std::min(K_bg, K)));
+    const int lead = std::min(std::min(spare, 31 - (W + 1)), std::min(1, std::min(K_bg, K)));    // the window word must still hold base p+W
     spare -= lead;
     std::vector<int> ov(G, 0);
     for (int g = G - 1; g >= 1 && spare > 0; g--) { ov[g] = std::min(spare, std::min(K, T[g] - 1)); spare -= ov[g]; }
@@ -245,6 +245,27 @@ extern "C" int bamm_plan_describe(int W, int K, int K_bg_model, int reduced, uin
             *o++ = (int32_t)gp.col0[g]; *o++ = (int32_t)gp.ncol[g]; *o++ = (int32_t)gp.lo[g]; *o++ = (int32_t)gp.shift[g];
             *o++ = (int32_t)gp.shift2[g]; *o++ = (int32_t)gp.mask4[g]; *o++ = (int32_t)gp.base[g]; *o++ = (int32_t)gp.colmask[g];
         }
+    }
+    *n_used = n;
+    return BAMM_OK;
+}
+
+// The bound plan of the pruned E-step as plain numbers (no device work).
+extern "C" int bamm_bound_plan_describe(int W, int K, int K_bg_model, uint64_t table_budget_bytes, int32_t* out, uint64_t cap, uint64_t* n_used) {
+    REQUIRE(out && n_used, "NULL argument");
+    REQUIRE(W >= 1 && W <= 32, "motif width W=%d not in [1,32]", W);
+    REQUIRE(K >= 0 && K <= 10 && K_bg_model >= 0 && K_bg_model <= 10, "order out of range");
+    GroupPlan gp; bool fast = false;
+    *n_used = 0;
+    REQUIRE(cap >= 1, "buffer too small");
+    if (!make_bound_plan(W, K, K_bg_model < K ? K_bg_model : K, (size_t)table_budget_bytes, gp, fast)) { out[0] = 0; *n_used = 1; return BAMM_OK; }
+    const uint64_t n = 4 + 7 * (uint64_t)gp.G;
+    REQUIRE(cap >= n, "buffer too small: %llu words needed", (unsigned long long)n);
+    int32_t* o = out;
+    *o++ = gp.G; *o++ = gp.kd; *o++ = fast ? 1 : 0; *o++ = (int32_t)gp.table_bytes;
+    for (int g = 0; g < gp.G; g++) {
+        *o++ = gp.col0[g]; *o++ = gp.ncol[g]; *o++ = gp.lo[g]; *o++ = (int32_t)gp.shift[g]; *o++ = (int32_t)gp.shift2[g];
+        *o++ = (int32_t)gp.mask4[g]; *o++ = (int32_t)gp.base[g];
     }
     *n_used = n;
     return BAMM_OK;

@@ -63,7 +63,12 @@ int main( int nargs, char* args[] ){
     // BAMM_DEVICES="0,1,2,3" or "0-7": one process drives all of them (EM::optimize splits the sequences over the devices and
     // exchanges the counts over NVLink; everything else stays on the first one). BAMM_DEVICE=n: a single device.
     std::vector<int> devices = deviceList();
-    std::thread warm( [devices](){ for( int d : devices ){ bamm_set_device( d ); } bamm_set_device( devices[0] ); } );
+    std::thread warm( [devices](){          // one context per device, created side by side
+        std::vector<std::thread> more;
+        for( size_t i = 1; i < devices.size(); i++ ) more.emplace_back( [d = devices[i]](){ bamm_set_device( d ); } );
+        bamm_set_device( devices[0] );
+        for( std::thread& t : more ) t.join();
+    } );
     if( devices[0] != 0 ) bamm_set_device( devices[0] );      // the FASTA reader may already create the device copy of the set
     Global::init( nargs, args );
     warm.join();

@@ -55,6 +55,11 @@ int         bamm_set_device(int device);           /* device used by objects cre
  * is_first, is_last} followed by G x {col0, ncol, lo, shift, shift2, mask4, base, colmask}. npass = 0: no packed plan fits. */
 int         bamm_plan_describe(int W, int K, int K_bg_model, int reduced, uint64_t table_budget_bytes, int32_t* out, uint64_t cap,
                                uint64_t* n_used);
+/* The bound plan of the pruned E-step: groups of up to 6 bases whose tables, indexed by one base more, hold an
+ * upper bound of the group's columns for window p and for window p+1 — what replaces the per-window product of EM::EStep
+ * (src/refinement/EM.cpp:167-176) for the 95 % of windows that cannot matter. out: {G, kd, fast, table_bytes} followed by G x
+ * {first column, columns, first base, shift, shift2, mask4, base}. G = 0: no plan (W + 1 bases do not fit one window word). */
+int         bamm_bound_plan_describe(int W, int K, int K_bg_model, uint64_t table_budget_bytes, int32_t* out, uint64_t cap, uint64_t* n_used);
 int         bamm_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
 /* Device group: several devices of one box driven by ONE process (the reference parallelises EM::EStep / MStep over the
  * sequences with OpenMP, src/refinement/EM.cpp:148-149, 230; here the sequences are cut into one contiguous block per device).

@@ -100,3 +100,69 @@ def test_plan_rejects_bad_arguments():
         capi.plan_describe(0, 2)
     with pytest.raises(capi.BammError):
         capi.plan_describe(33, 2)
+
+
+# ---- bound plan of the pruned E-step (csrc/capi_em.inl make_bound_plan, csrc/packed.cuh k_bound_levels / k_make_bound_tables) --------
+def bf16_up(x):
+    """Smallest bfloat16 >= x (x >= 0), as float32 — what k_make_bound_tables stores."""
+    b = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    b = np.where(b & 0xffff, (b | 0xffff) + 1, b) >> 16
+    return (b << 16).astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("K,K_bg", [(0, 0), (1, 1), (2, 2), (4, 2), (5, 2)])
+def test_bound_plan_invariants_and_bound_property(K, K_bg):
+    """For every width: the groups tile the columns, their tables fit the budget, the (kd, shift, mask4) extraction of the kernel
+    yields the bases lo .. hi+1 of a group — and, with tables built as the device builds them (maximum of s over the context bases
+    left of the group, product over the group's columns, rounded up to bfloat16), the product of the looked-up entries is an
+    upper bound of the exact window product (reference: the per-window product of EM::EStep, src/refinement/EM.cpp:167-176) for
+    window p (low half) and window p+1 (high half)."""
+    rng = np.random.default_rng(17 + K)
+    Yn = 4 ** (K + 1)
+    seen = 0
+    for W in (6, 8, 12, 13, 20, 24, 30):
+        plan = capi.bound_plan_describe(W, K, K_bg)
+        assert plan is not None, W
+        G, kd, groups = plan["G"], plan["kd"], plan["groups"]
+        assert sum(4 * 4 ** (g["ncol"] + g["col0"] - g["lo"] + 1) for g in groups) == plan["table_bytes"] <= 232448
+        assert groups[0]["col0"] == 0 and groups[-1]["col0"] + groups[-1]["ncol"] == W
+        for a, b in zip(groups, groups[1:]):
+            assert b["col0"] == a["col0"] + a["ncol"] and a["lo"] <= a["col0"] and b["lo"] <= b["col0"]
+        assert -groups[0]["lo"] <= kd <= 31 - (W + 1)
+        # a model with strong context dependence, reduced leading columns like Motif::updateV produces (Motif.h:126-128)
+        s = rng.lognormal(0.0, 1.0, size=(W, Yn)).astype(np.float32)
+        for j in range(min(K, W)):
+            period = 4 ** (max(j, K_bg) + 1)
+            s[j] = s[j][np.arange(Yn) % period]
+        bases = rng.integers(0, 4, size=400)
+        def y_at(i, nb):                      # k-mer index of the nb newest bases ending at position i (zero before the sequence)
+            return sum((int(bases[i - t]) if i - t >= 0 else 0) << (2 * t) for t in range(nb))
+        tabs = []
+        for g in groups:
+            hi, lo = g["col0"] + g["ncol"] - 1, g["lo"]
+            T = hi - lo + 1
+            z = np.arange(4 ** T)
+            f = np.ones(4 ** T, np.float32)
+            for j in range(g["col0"], hi + 1):
+                avail = min(j - lo + 1, K + 1)
+                U = s[j].reshape(4 ** (K + 1 - avail), 4 ** avail).max(axis=0)          # maximum over the missing (older) context bases
+                f = (f * U[(z >> (2 * (hi - j))) & (4 ** avail - 1)]).astype(np.float32)
+            z2 = np.arange(4 ** (T + 1))
+            tabs.append((bf16_up(f[z2 >> 2]), bf16_up(f[z2 & (4 ** T - 1)])))
+        for p in range(0, 300, 7):
+            w = window_word(bases, p, kd)
+            b0 = b1 = np.float32(1.0)
+            for g, (lo_half, hi_half) in zip(groups, tabs):
+                hi = g["col0"] + g["ncol"] - 1
+                idx = extract(w, g, plan["fast"]) >> 2
+                T1 = hi - g["lo"] + 2
+                want = sum((int(bases[p + g["lo"] + t]) if 0 <= p + g["lo"] + t else 0) << (2 * (T1 - 1 - t)) for t in range(T1))
+                assert idx == want, (W, K, p, g)
+                b0, b1 = np.float32(b0 * lo_half[idx]), np.float32(b1 * hi_half[idx])
+            for q, b in ((p, b0), (p + 1, b1)):
+                exact = np.float64(1.0)
+                for j in range(W):
+                    exact *= np.float64(s[j][y_at(q + j, K + 1)])
+                assert float(b) >= exact * (1 - 1e-4), (W, K, q, float(b), exact)
+                seen += 1
+    assert seen > 500
