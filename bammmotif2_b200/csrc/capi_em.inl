@@ -486,7 +486,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             // candidate list of the pruned E-step: one region per warp for a fraction of its windows (BAMM_CAND_FRAC). The exact
             // pass lists at most the candidates plus the windows over the N and the truncated tail of every sequence, so a
             // region of the active list that holds all of those cannot overflow there.
-            const double cfrac = getenv("BAMM_CAND_FRAC") ? atof(getenv("BAMM_CAND_FRAC")) : 0.30;
+            const double cfrac = getenv("BAMM_CAND_FRAC") ? atof(getenv("BAMM_CAND_FRAC")) : 0.42;
             if (cfrac > 0.0 && !getenv("BAMM_NO_SPARSE")) {
                 std::vector<uint64_t> creg((size_t)em->nregions + 1, 0);
                 bool ok = true;
@@ -599,7 +599,7 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
         }
         const EStepLaunch l = {em->grid_pe, em->block_pe, em->stream};
         for (size_t i = 0; i < em->gplans.size(); i++)
-            if (launch_estep_dense(l, true, em->gfast[i] != 0, em->gplans.size() > 1, nullptr, em->gplans[i], nullptr, nullptr, nullptr, em->plain_words, nullptr, nullptr, nullptr, nullptr))
+            if (launch_estep_dense(l, true, em->gfast[i] != 0, em->gplans.size() > 1, nullptr, em->gplans[i], nullptr, nullptr, em->plain_words, nullptr, nullptr, nullptr, nullptr))
                 return fail(BAMM_E_CUDA, "cannot opt in to %u bytes of shared memory", em->gplans[i].table_bytes);
         if (em->sparse) {
             if (!em->d_btab) {
@@ -615,8 +615,8 @@ extern "C" int bamm_em_set_model(bamm_em* em, const float* v_all, const float* v
                 if ((size_t)g.table_bytes + (em->plain_words ? plain_bytes : 0) + estep_stage_bytes(em->block_pe) > em->tab_capacity) em->stage = false;
             if (launch_estep_bound(l, true, em->bfast, nullptr, em->bplan, nullptr, nullptr)) return fail(BAMM_E_CUDA, "cannot opt in to shared memory for the pruned E-step");
             for (size_t i = 0; i < em->gplans.size(); i++)
-                if (launch_estep_masked(l, true, em->gfast[i] != 0, nullptr, em->gplans[i], nullptr, nullptr, nullptr, em->plain_words, nullptr, nullptr, nullptr, nullptr) ||
-                    launch_estep_exact(l, true, em->gfast[i] != 0, nullptr, em->gplans[i], nullptr, nullptr, nullptr, em->plain_words, em->stage, nullptr, nullptr, nullptr, nullptr, nullptr))
+                if (launch_estep_masked(l, true, em->gfast[i] != 0, nullptr, em->gplans[i], nullptr, nullptr, em->plain_words, nullptr, nullptr, nullptr, nullptr) ||
+                    launch_estep_exact(l, true, em->gfast[i] != 0, nullptr, em->gplans[i], nullptr, nullptr, em->plain_words, em->stage, nullptr, nullptr, nullptr, nullptr, nullptr))
                     return fail(BAMM_E_CUDA, "cannot opt in to shared memory for the pruned E-step");
             if (multi_pass && !em->d_cand_part) {      // partial products between the column passes: per candidate slot, per masked window
                 CU(dev_malloc(&em->d_cand_part, (size_t)(em->cand_slots ? em->cand_slots : 1) * sizeof(float)));
@@ -681,18 +681,18 @@ static int launch_estep(bamm_em* em, cudaEvent_t* split = nullptr /* 2 events: a
             const size_t np = em->gplans.size();
             auto tab_of = [&](size_t pass) { return (const float*)((const char*)em->d_tab + pass * em->tab_capacity); };
             for (size_t pass = 0; pass < np; pass++)
-                if (launch_estep_masked(l, false, em->gfast[pass] != 0, &pv, plan_for_launch(em, pass, em->q), tab_of(pass), em->d_s, em->d_sT, em->plain_words, &cl,
+                if (launch_estep_masked(l, false, em->gfast[pass] != 0, &pv, plan_for_launch(em, pass, em->q), tab_of(pass), em->d_s, em->plain_words, &cl,
                                         em->d_seqacc, np > 1 ? em->d_mask_part : nullptr, &al))
                     return fail(BAMM_E_CUDA, "E-step launch failed (masked windows)");
             if (split) CU(cudaEventRecord(split[0], em->stream));
             if (launch_estep_bound(l, false, em->bfast, &pv, bp, em->d_btab, &cl)) return fail(BAMM_E_CUDA, "E-step launch failed (bounds)");
             if (split) CU(cudaEventRecord(split[1], em->stream));
             for (size_t pass = 0; pass < np; pass++)
-                if (launch_estep_exact(l, false, em->gfast[pass] != 0, &pv, plan_for_launch(em, pass, em->q), tab_of(pass), em->d_s, em->d_sT, em->plain_words, em->stage, &cl,
+                if (launch_estep_exact(l, false, em->gfast[pass] != 0, &pv, plan_for_launch(em, pass, em->q), tab_of(pass), em->d_s, em->plain_words, em->stage, &cl,
                                        em->d_seqacc, np > 1 ? em->d_cand_part : nullptr, scal, &al))
                     return fail(BAMM_E_CUDA, "E-step launch failed (candidates)");
             for (size_t pass = 0; pass < np; pass++)
-                if (launch_estep_dense(l, false, em->gfast[pass] != 0, np > 1, &pv, plan_for_launch(em, pass, em->q), tab_of(pass), em->d_s, em->d_sT, em->plain_words, em->d_r, scal,
+                if (launch_estep_dense(l, false, em->gfast[pass] != 0, np > 1, &pv, plan_for_launch(em, pass, em->q), tab_of(pass), em->d_s, em->plain_words, em->d_r, scal,
                                        &al, em->d_eflags))
                     return fail(BAMM_E_CUDA, "packed E-step launch failed");
             em->launches += 3 * (np - 1);
@@ -700,7 +700,7 @@ static int launch_estep(bamm_em* em, cudaEvent_t* split = nullptr /* 2 events: a
             if (split) { CU(cudaEventRecord(split[0], em->stream)); CU(cudaEventRecord(split[1], em->stream)); }
             for (size_t pass = 0; pass < em->gplans.size(); pass++)
                 if (launch_estep_dense(l, false, em->gfast[pass] != 0, multi, &pv, plan_for_launch(em, pass, em->q), (const float*)((const char*)em->d_tab + pass * em->tab_capacity),
-                                       em->d_s, em->d_sT, em->plain_words, em->d_r, scal, &al, nullptr))
+                                       em->d_s, em->plain_words, em->d_r, scal, &al, nullptr))
                     return fail(BAMM_E_CUDA, "packed E-step launch failed");
         }
         em->r_scaled = false;
@@ -1207,7 +1207,7 @@ extern "C" int bamm_em_get_r(bamm_em* em, uint64_t first, uint64_t count, float*
         ActiveList al = alist_of(em); al.ent = nullptr;
         for (size_t pass = 0; pass < em->gplans.size(); pass++)
             if (launch_estep_dense(l, false, em->gfast[pass] != 0, em->gplans.size() > 1, &pv, plan_for_launch(em, pass, em->q_e),
-                                   (const float*)((const char*)em->d_tab_e + pass * em->tab_capacity), em->d_s_e, em->d_sT_e, em->plain_words, em->d_r, nullptr, &al, nullptr))
+                                   (const float*)((const char*)em->d_tab_e + pass * em->tab_capacity), em->d_s_e, em->plain_words, em->d_r, nullptr, &al, nullptr))
                 return fail(BAMM_E_CUDA, "packed E-step launch failed (materialising r)");
         em->launches += em->gplans.size();
         em->r_mat = true; em->r_scaled = false;

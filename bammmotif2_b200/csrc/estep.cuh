@@ -89,7 +89,6 @@ __host__ __device__ __forceinline__ uint32_t plain_smem_words(uint32_t plain_wor
 // launch-invariant inputs of the masked evaluation
 struct MaskedTabs {
     const float* s_g;         // plain table [j][y], global
-    const float* s_rows;      // the same table as [y][j], global (row loads for the patched k-mers)
     uint32_t plain_s;         // shared-window address of a [j][y] copy in shared memory (rows Yn+1 floats apart: the lanes of a warp
                               // read one k-mer in different columns, or different k-mers in one column), or 0 when there is none
     uint32_t Yn, maskK, passmask;
@@ -179,7 +178,7 @@ __device__ __forceinline__ uint32_t pcode_of(int p, int jmax, bool over_n) {
 template <int G, bool FAST, bool MULTI>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g /* [W][Yn] */,
-               const float* __restrict__ s_rows /* [Yn][W] */, uint32_t plain_words, float* __restrict__ r, unsigned long long* __restrict__ scal,
+               uint32_t plain_words, float* __restrict__ r, unsigned long long* __restrict__ scal,
                ActiveList al, const uint32_t* __restrict__ only_if) {
     extern __shared__ __align__(16) float tab[];
     __shared__ unsigned long long stage_bar;
@@ -199,7 +198,7 @@ k_estep_packed(PackedView pv, const __grid_constant__ GroupPlan gp, const float*
     // a window can only reach the M-step's threshold r >= 2^-41 if val >= 2^-41 (1-q): norm >= 1-q (margin for rounding)
     const float thr0 = gp.thr0;
     GroupConsts<G> gc; load_consts<G>(gc, gp, tab_s);
-    MaskedTabs mt; mt.s_g = s_g; mt.s_rows = s_rows; mt.plain_s = plain_words ? tab_s + gp.table_bytes : 0u;
+    MaskedTabs mt; mt.s_g = s_g; mt.plain_s = plain_words ? tab_s + gp.table_bytes : 0u;
     mt.Yn = gp.Yn; mt.maskK = gp.Yn - 1; mt.passmask = MULTI ? gp.passmask : 0xffffffffu; mt.W = W; mt.K = K; mt.KD = KD;
     const bool first = !MULTI || gp.pass_first != 0, last = !MULTI || gp.pass_last != 0;    // CTA-uniform
     Emitter em; em.init(al, warp, last);
@@ -435,7 +434,7 @@ struct MaskedStep { uint32_t good, lo, hi, pad; };
 template <int G, bool FAST, bool LEAN /* one pass with the plain table in shared memory: no partial products, no global table */>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
-          const float* __restrict__ s_rows, uint32_t plain_words, CandList cl, ulonglong2* __restrict__ seqacc,
+          uint32_t plain_words, CandList cl, ulonglong2* __restrict__ seqacc,
           float* __restrict__ partial /* column passes: [nlist][2W+K-1] partial products, else nullptr */, ActiveList al) {
     extern __shared__ __align__(16) float tab[];
     __shared__ unsigned long long stage_bar;
@@ -469,7 +468,7 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
     const uint32_t plain_s = tab_s + gp.table_bytes, maskK = gp.Yn - 1u, ystride = gp.Yn + 1u;
     const bool first = LEAN || gp.pass_first != 0, last = LEAN || gp.pass_last != 0;    // column passes: partial products travel through `partial`
     const uint32_t plain_on = LEAN ? plain_s : (plain_words ? plain_s : 0u);
-    MaskedTabs mt; mt.s_g = s_g; mt.s_rows = s_rows; mt.plain_s = plain_on;
+    MaskedTabs mt; mt.s_g = s_g; mt.plain_s = plain_on;
     mt.Yn = gp.Yn; mt.maskK = maskK; mt.passmask = gp.passmask; mt.W = W; mt.K = K; mt.KD = KD;
     const int npart = 2 * W + K - 1;
     Emitter em; em.init(al, warp, last);
@@ -591,7 +590,7 @@ constexpr int STAGE_SEQ_WORDS = 96, STAGE_WORDS = STAGE_SEQ_WORDS + 8;      // +
 template <int G, bool FAST, bool MULTI /* column passes: partial products between them */>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
-         const float* __restrict__ s_rows, uint32_t plain_words, uint32_t stage /* 0: no staging buffer */, CandList cl,
+         uint32_t plain_words, uint32_t stage /* 0: no staging buffer */, CandList cl,
          const ulonglong2* __restrict__ seqacc, float* __restrict__ partial /* column passes: one float per candidate slot, else nullptr */,
          unsigned long long* __restrict__ scal, ActiveList al) {
     extern __shared__ __align__(16) float tab[];
@@ -610,8 +609,6 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
     const float one_minus_q = 1.0f - gp.q;
     const float thr0 = gp.thr0;
     GroupConsts<G> gc; load_consts<G>(gc, gp, tab_s);
-    MaskedTabs mt; mt.s_g = s_g; mt.s_rows = s_rows; mt.plain_s = plain_words ? tab_s + gp.table_bytes : 0u;
-    mt.Yn = gp.Yn; mt.maskK = gp.Yn - 1; mt.passmask = 0xffffffffu; mt.W = W; mt.K = K; mt.KD = KD;
     const bool first = !MULTI || gp.pass_first != 0, last = !MULTI || gp.pass_last != 0;   // column passes (tables of all columns beyond shared memory)
     Emitter em; em.init(al, warp, last);
     em.bpos = al.cnt_back[warp];                                        // the back of the region is k_emasked's

@@ -12,18 +12,18 @@ struct EStepLaunch {              // geometry + stream of the packed E-step kern
 
 // dense E-step (estep.cuh: k_estep_packed<G, FAST, MULTI>). optin_only: set the shared-memory attribute instead of launching.
 int launch_estep_dense(const EStepLaunch& l, bool optin_only, bool fast, bool multi, const PackedView* pv, const GroupPlan& gp,
-                       const float* d_tab, const float* d_s, const float* d_s_rows, uint32_t plain_words, float* d_r,
+                       const float* d_tab, const float* d_s, uint32_t plain_words, float* d_r,
                        unsigned long long* d_scal, const ActiveList* al, const uint32_t* only_if);
 // (d_partial: column passes — the partial products of the earlier passes, one float per masked window / candidate slot; else NULL)
 // pruned E-step: windows over the N and truncated windows of every sequence (k_emasked<G, FAST>), bounds (k_ebound<G1, FAST>)
 // and exact evaluation of the candidates (k_eexact<G, FAST>)
 int launch_estep_masked(const EStepLaunch& l, bool optin_only, bool fast, const PackedView* pv, const GroupPlan& gp, const float* d_tab,
-                        const float* d_s, const float* d_s_rows, uint32_t plain_words, const CandList* cl, ulonglong2* d_seqacc, float* d_partial,
+                        const float* d_s, uint32_t plain_words, const CandList* cl, ulonglong2* d_seqacc, float* d_partial,
                         const ActiveList* al);
 int launch_estep_bound(const EStepLaunch& l, bool optin_only, bool fast, const PackedView* pv, const GroupPlan& gp, const float* d_tab,
                        const CandList* cl);
 int launch_estep_exact(const EStepLaunch& l, bool optin_only, bool fast, const PackedView* pv, const GroupPlan& gp, const float* d_tab,
-                       const float* d_s, const float* d_s_rows, uint32_t plain_words, bool stage, const CandList* cl, const ulonglong2* d_seqacc,
+                       const float* d_s, uint32_t plain_words, bool stage, const CandList* cl, const ulonglong2* d_seqacc,
                        float* d_partial, unsigned long long* d_scal, const ActiveList* al);
 // bytes of the per-warp staging buffers k_eexact appends to its shared memory when `stage` is set
 size_t estep_stage_bytes(int block);

@@ -11,16 +11,16 @@ template <typename KF> static int optin(KF kernel, size_t bytes) {
 
 template <int G, bool FAST, bool MULTI>
 static int dense_one(const EStepLaunch& l, bool optin_only, const PackedView* pv, const GroupPlan& gp, const float* d_tab, const float* d_s,
-                     const float* d_s_rows, uint32_t plain_words, float* d_r, unsigned long long* d_scal, const ActiveList* al, const uint32_t* only_if) {
+                     uint32_t plain_words, float* d_r, unsigned long long* d_scal, const ActiveList* al, const uint32_t* only_if) {
     const size_t smem = (size_t)gp.table_bytes + (size_t)plain_smem_words(plain_words, gp.Yn) * 4;
     if (optin_only) return optin(k_estep_packed<G, FAST, MULTI>, smem);
-    k_estep_packed<G, FAST, MULTI><<<l.grid, l.block, smem, l.stream>>>(*pv, gp, d_tab, d_s, d_s_rows, plain_words, d_r, d_scal, *al, only_if);
+    k_estep_packed<G, FAST, MULTI><<<l.grid, l.block, smem, l.stream>>>(*pv, gp, d_tab, d_s, plain_words, d_r, d_scal, *al, only_if);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 int launch_estep_dense(const EStepLaunch& l, bool optin_only, bool fast, bool multi, const PackedView* pv, const GroupPlan& gp,
-                       const float* d_tab, const float* d_s, const float* d_s_rows, uint32_t plain_words, float* d_r,
+                       const float* d_tab, const float* d_s, uint32_t plain_words, float* d_r,
                        unsigned long long* d_scal, const ActiveList* al, const uint32_t* only_if) {
-#define ARGS l, optin_only, pv, gp, d_tab, d_s, d_s_rows, plain_words, d_r, d_scal, al, only_if
+#define ARGS l, optin_only, pv, gp, d_tab, d_s, plain_words, d_r, d_scal, al, only_if
     switch (gp.G) {
 #define X(g) case g: return fast ? (multi ? dense_one<g, true, true>(ARGS) : dense_one<g, true, false>(ARGS)) \
                                  : (multi ? dense_one<g, false, true>(ARGS) : dense_one<g, false, false>(ARGS));
@@ -51,16 +51,16 @@ size_t estep_stage_bytes(int block) { return (size_t)(block / 32) * STAGE_WORDS 
 
 template <int G, bool FAST, bool LEAN>
 static int masked_one(const EStepLaunch& l, bool optin_only, const PackedView* pv, const GroupPlan& gp, const float* d_tab, const float* d_s,
-                      const float* d_s_rows, uint32_t plain_words, const CandList* cl, ulonglong2* d_seqacc, float* d_partial, const ActiveList* al) {
+                      uint32_t plain_words, const CandList* cl, ulonglong2* d_seqacc, float* d_partial, const ActiveList* al) {
     const size_t smem = (size_t)gp.table_bytes + (size_t)plain_smem_words(plain_words, gp.Yn) * 4;
     if (optin_only) return optin(k_emasked<G, FAST, LEAN>, smem);
-    k_emasked<G, FAST, LEAN><<<l.grid, l.block, smem, l.stream>>>(*pv, gp, d_tab, d_s, d_s_rows, plain_words, *cl, d_seqacc, d_partial, *al);
+    k_emasked<G, FAST, LEAN><<<l.grid, l.block, smem, l.stream>>>(*pv, gp, d_tab, d_s, plain_words, *cl, d_seqacc, d_partial, *al);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 int launch_estep_masked(const EStepLaunch& l, bool optin_only, bool fast, const PackedView* pv, const GroupPlan& gp, const float* d_tab,
-                        const float* d_s, const float* d_s_rows, uint32_t plain_words, const CandList* cl, ulonglong2* d_seqacc, float* d_partial,
+                        const float* d_s, uint32_t plain_words, const CandList* cl, ulonglong2* d_seqacc, float* d_partial,
                         const ActiveList* al) {
-#define ARGS l, optin_only, pv, gp, d_tab, d_s, d_s_rows, plain_words, cl, d_seqacc, d_partial, al
+#define ARGS l, optin_only, pv, gp, d_tab, d_s, plain_words, cl, d_seqacc, d_partial, al
     const bool lean = plain_words != 0 && d_partial == nullptr && gp.pass_first && gp.pass_last;      // one pass, plain table in shared memory
     switch (gp.G) {
 #define X(g) case g: return lean ? (fast ? masked_one<g, true, true>(ARGS) : masked_one<g, false, true>(ARGS)) \
@@ -74,16 +74,16 @@ int launch_estep_masked(const EStepLaunch& l, bool optin_only, bool fast, const 
 
 template <int G, bool FAST, bool MULTI>
 static int exact_one(const EStepLaunch& l, bool optin_only, const PackedView* pv, const GroupPlan& gp, const float* d_tab, const float* d_s,
-                     const float* d_s_rows, uint32_t plain_words, bool stage, const CandList* cl, const ulonglong2* d_seqacc, float* d_partial, unsigned long long* d_scal, const ActiveList* al) {
+                     uint32_t plain_words, bool stage, const CandList* cl, const ulonglong2* d_seqacc, float* d_partial, unsigned long long* d_scal, const ActiveList* al) {
     const size_t smem = (size_t)gp.table_bytes + (size_t)plain_smem_words(plain_words, gp.Yn) * 4 + (stage ? estep_stage_bytes(l.block) : 0);
     if (optin_only) return optin(k_eexact<G, FAST, MULTI>, smem);
-    k_eexact<G, FAST, MULTI><<<l.grid, l.block, smem, l.stream>>>(*pv, gp, d_tab, d_s, d_s_rows, plain_words, stage ? 1u : 0u, *cl, d_seqacc, d_partial, d_scal, *al);
+    k_eexact<G, FAST, MULTI><<<l.grid, l.block, smem, l.stream>>>(*pv, gp, d_tab, d_s, plain_words, stage ? 1u : 0u, *cl, d_seqacc, d_partial, d_scal, *al);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 int launch_estep_exact(const EStepLaunch& l, bool optin_only, bool fast, const PackedView* pv, const GroupPlan& gp, const float* d_tab,
-                       const float* d_s, const float* d_s_rows, uint32_t plain_words, bool stage, const CandList* cl, const ulonglong2* d_seqacc,
+                       const float* d_s, uint32_t plain_words, bool stage, const CandList* cl, const ulonglong2* d_seqacc,
                        float* d_partial, unsigned long long* d_scal, const ActiveList* al) {
-#define ARGS l, optin_only, pv, gp, d_tab, d_s, d_s_rows, plain_words, stage, cl, d_seqacc, d_partial, d_scal, al
+#define ARGS l, optin_only, pv, gp, d_tab, d_s, plain_words, stage, cl, d_seqacc, d_partial, d_scal, al
     const bool multi = !(gp.pass_first && gp.pass_last);
     switch (gp.G) {
 #define X(g) case g: return multi ? (fast ? exact_one<g, true, true>(ARGS) : exact_one<g, false, true>(ARGS)) \
