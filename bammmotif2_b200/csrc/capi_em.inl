@@ -445,17 +445,26 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         std::vector<uint64_t> reg, win, nsq;
         if (frac > 0.0) {
             em->nregions = (uint32_t)em->grid_pe * (uint32_t)(em->block_pe / 32);
-            win.assign(em->nregions, 0); nsq.assign(em->nregions, 0);
+            win.assign(em->nregions, 0); nsq.assign(em->nregions, 0);      // nsq: windows k_emasked may list per region (at most 2W+K+2 per sequence)
+            // windows of a sequence k_emasked evaluates (and may list): those over the structural N plus the truncated tail, as the kernels cut them
+            auto masked_windows = [&](uint64_t L, bool hasN) -> uint64_t {
+                const long long lw1 = (long long)L - W + 1, tl = std::min(std::max((long long)L - 2 * W + 2, 0ll), lw1);
+                long long nn = 0;
+                if (hasN) { const long long mid = ((long long)L - 1) / 2; nn = std::min(mid + K + 1, tl) - std::min(std::max(mid - W + 1, 0ll), tl); }
+                return (uint64_t)(std::max(nn, 0ll) + (lw1 - tl));
+            };
             reg.assign((size_t)em->nregions + 1, 0);
             if (em->whole_set && s->minL == s->maxL) {          // equal lengths: sequence i goes to warp i % nregions
                 const uint64_t lw1 = s->maxL - (uint64_t)W + 1, per = em->npk / em->nregions, extra = em->npk % em->nregions;
-                for (uint32_t w = 0; w < em->nregions; w++) { nsq[w] = per + (w < extra ? 1 : 0); win[w] = nsq[w] * lw1; }
+                const uint64_t mper = masked_windows(s->maxL, s->maxL & 1);     // odd length: counted as a both-strand record with its N
+                for (uint32_t w = 0; w < em->nregions; w++) { const uint64_t c = per + (w < extra ? 1 : 0); nsq[w] = c * mper; win[w] = c * lw1; }
             } else {
                 uint32_t w = 0;
                 for (size_t i = 0; i < em->npk; i++) {
                     const uint64_t n = em->whole_set ? i : pk_ids[i];
-                    win[w] += s->h_off[n + 1] - s->h_off[n] - (uint64_t)W + 1;
-                    nsq[w]++;
+                    const uint64_t lw1 = s->h_off[n + 1] - s->h_off[n] - (uint64_t)W + 1;
+                    win[w] += lw1;
+                    nsq[w] += masked_windows(s->h_off[n + 1] - s->h_off[n], s->h_kind[n] == 2);
                     if (++w == em->nregions) w = 0;
                 }
             }
@@ -491,10 +500,10 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
                 std::vector<uint64_t> creg((size_t)em->nregions + 1, 0);
                 bool ok = true;
                 for (uint32_t w = 0; w < em->nregions && ok; w++) {
-                    const uint64_t masked = nsq[w] * (uint64_t)(2 * W + K + 2), rcap = reg[w + 1] - reg[w];
+                    const uint64_t masked = nsq[w], rcap = reg[w + 1] - reg[w];
                     uint64_t cap = (uint64_t)(cfrac * (double)win[w]) + 256;
                     if (cap > win[w]) cap = win[w];
-                    if (cap + masked > rcap) { if (rcap <= masked && win[w]) ok = false; else cap = rcap > masked ? rcap - masked : 0; }
+                    if (cap + masked > rcap) { if (rcap < masked) ok = false; else cap = rcap - masked; }   // (0: every window of the warp is a masked one)
                     creg[w + 1] = creg[w] + cap;
                 }
                 em->cand_slots = creg[em->nregions];

@@ -164,3 +164,75 @@ def test_per_iteration_parity_on_baseline_shapes(capi, oracle, shape):
     _assert_rel(em.model(), v, RTOL, 0.0, "fused loop vs step-wise " + shape)
     # ... and r after the fused loop is the r of ITS last E-step (EM.h:48-52 contract of getR())
     _assert_rel(em.r(), ems[0].r(), RTOL, 1e-37, "r after the fused loop " + shape)
+
+
+@pytest.mark.parametrize("W,K", [(20, 4), (8, 2), (12, 5)])
+def test_short_and_ragged_sequences_on_the_pruned_path(capi, oracle, W, K):
+    """Sequences of every length from just above W to a few hundred bases, both strands and single-stranded, in one set: the windows
+    over the N and the truncated windows (EM.cpp:167) overlap or fill the whole sequence, so k_emasked takes its generic route for
+    the warps that hold them, the bound pass has nothing to do for some, and the candidate / active regions are ragged. Compared
+    with the oracle per iteration (1e-5) and bit for bit with the dense path (BAMM_NO_SPARSE)."""
+    from bammmotif2_b200 import hostmodel
+    rng = np.random.default_rng(1000 + W)
+    A, Kbg, q, nseq = 4, 2, 0.3, 6000
+    pwm = rng.dirichlet(np.full(4, 0.3), size=W)
+    sites = np.stack([rng.choice(4, size=200, p=pwm[j]) for j in range(W)], axis=1).astype(np.uint8) + 1
+    chunks, kmers, offs = [], [], [0]
+    lens = np.concatenate([rng.integers(W // 2 + 1, 2 * W + 3, size=nseq // 2), rng.integers(2 * W, 180, size=nseq - nseq // 2)])
+    rng.shuffle(lens)
+    for n, L0 in enumerate(lens):
+        fwd = rng.integers(1, 5, size=int(L0), dtype=np.uint8)
+        if L0 >= W and n % 2 == 0:
+            s0 = rng.integers(0, L0 - W + 1)
+            fwd[s0:s0 + W] = sites[n % 200]
+        single = (n % 7 == 3) and L0 >= W                      # some single-stranded records (no N, no reverse strand)
+        codes = fwd if single else np.concatenate([fwd, [0], (5 - fwd)[::-1]]).astype(np.uint8)
+        d = np.where(codes == 0, 0, codes.astype(np.int64) - 1)
+        km = np.zeros(len(codes), np.uint64)
+        for t in range(min(11, len(codes))):
+            dig = d[:len(codes) - t].copy()
+            if not single:
+                isn = np.arange(len(codes) - t) == int(L0)
+                dig[isn] = rng.integers(0, 4, size=int(isn.sum()))        # an independent draw per (position, digit) of the N, Sequence.cpp:38
+            km[t:] += (dig * (4 ** t)).astype(np.uint64)
+        chunks.append(codes); kmers.append(km); offs.append(offs[-1] + len(codes))
+    codes, kmer, offsets = np.concatenate(chunks), np.concatenate(kmers), np.array(offs, np.uint64)
+    assert np.diff(offsets.astype(np.int64)).min() >= W
+    pp, pk = capi.kmer_patches(codes, kmer)
+    ss = capi.SeqSet(codes, offsets, A, pp, pk)
+    nb, vbg = oracle.bg_model(kmer, A, Kbg, hostmodel.default_bg_alpha(Kbg))
+    alpha = hostmodel.default_motif_alpha(K, W)
+    v0 = hostmodel.motif_from_sites(sites, A, K, alpha, vbg)
+    ems = []
+    for env in ({}, {"BAMM_NO_SPARSE": "1"}):
+        os.environ.update(env)
+        try:
+            em = capi.EM(ss, W, K, Kbg)
+            em.set_model(v0, vbg, alpha, q)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        ems.append(em)
+    v = v0
+    for it in range(2):
+        s = oracle.linear_s(v, vbg, A, K, Kbg, W)
+        r_ref, _, llh_ref = oracle.estep(kmer, offsets, A, K, W, s, q, want_double=True)
+        n_ref = oracle.mstep(kmer, offsets, A, K, W, r_ref, accumulate_double=True)
+        v_ref = oracle.update_v(n_ref, alpha.ravel(), vbg, A, K, W, v.copy())
+        out = []
+        for em, name in zip(ems, ("pruned", "dense")):
+            llh = em.estep()
+            info = em.estep_info()
+            # W = 8 is so unspecific that more than 42 % of a warp's windows can pass the bound: the device then falls back to the
+            # dense kernel for the iteration (and must still agree in every bit)
+            assert info["pruned"] == (name == "pruned") and (name == "dense" or W < 12 or not info["dense_ran"]), (name, info)
+            assert abs(llh - llh_ref) <= RTOL * abs(llh_ref) + 1e-7 * nseq, (name, it)
+            r = em.r()
+            _assert_rel(r, r_ref, RTOL, 1e-37, "r %s it%d" % (name, it + 1))
+            em.mstep()
+            _assert_rel(em.counts(), n_ref, RTOL, 1e-7, "n %s it%d" % (name, it + 1))
+            m = em.model()
+            _assert_rel(m, v_ref, RTOL, 1e-7 / float(alpha[K].min()), "v %s it%d" % (name, it + 1))
+            out.append((llh, r, m))
+        assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2]), "pruned and dense path must agree in every bit"
+        v = out[0][2]
