@@ -40,9 +40,17 @@ struct NormAcc {
         a += big ? 0ull : x;
         b += big ? x : 0ull;
     }
+    // sum over the warp, result in every lane: three 22-bit limbs per counter through the integer warp reduction (REDUX) instead
+    // of five rounds of 64-bit shuffles; the counter of large values is zero in almost every warp
+    static __device__ __forceinline__ unsigned long long sum_u64(unsigned long long x) {
+        const unsigned long long s0 = __reduce_add_sync(FULL, (unsigned)(x & 0x3fffffull));
+        const unsigned long long s1 = __reduce_add_sync(FULL, (unsigned)((x >> 22) & 0x3fffffull));
+        const unsigned long long s2 = __reduce_add_sync(FULL, (unsigned)(x >> 44));
+        return s0 + (s1 << 22) + (s2 << 44);
+    }
     __device__ __forceinline__ void warp_reduce() {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+        a = sum_u64(a);
+        b = __any_sync(FULL, b != 0ull) ? sum_u64(b) : 0ull;
     }
     __device__ __forceinline__ double total() const { return (double)a * (1.0 / 8589934592.0) + (double)b * (1.0 / 256.0); }
 };
