@@ -589,12 +589,12 @@ k_emasked(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __re
 }
 
 // ---- pruned E-step, part 2: exact evaluation of the listed windows -------------------------------------------------
-// gp is the exact plan of the dense kernel. Per sequence: the candidates in batches of 32, then the windows over the N and the
-// truncated tail (masked evaluation), then the normaliser. The stream words of the sequence (up to STAGE_SEQ_WORDS, i.e. about
-// 1500 bases) and its patched k-mers are staged in a per-warp slice of shared memory with coalesced loads, so a window word is
+// gp is the exact plan of the dense kernel. Per sequence: the candidates in batches of 32, then the normaliser terms of the
+// windows over the N and of the truncated tail (k_emasked), then the normaliser. The stream words of the sequence (up to
+// STAGE_SEQ_WORDS, i.e. about 1500 bases) are staged in a per-warp slice of shared memory with coalesced loads, so a window word is
 // three shared-memory reads instead of a gather; longer sequences gather from global memory. The records of the next
 // sequence are requested one sequence ahead.
-constexpr int STAGE_SEQ_WORDS = 96, STAGE_WORDS = STAGE_SEQ_WORDS + 8;      // + 16 patched k-mers (uint16)
+constexpr int STAGE_SEQ_WORDS = 96, STAGE_WORDS = STAGE_SEQ_WORDS;
 template <int G, bool FAST, bool MULTI /* column passes: partial products between them */>
 __global__ void __launch_bounds__(BAMM_E_THREADS, 1)
 k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __restrict__ tab_g, const float* __restrict__ s_g,
@@ -636,26 +636,21 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
             uint2 sc_next = sc;
             uint32_t n_nn = 0u;
             if (more) { sq_next = pv.seqs[n_next]; sc_next = cl.seq[li_next]; if (li_next + nwarps < pv.nlist) n_nn = pv.seq_ids[li_next + nwarps]; }
-            const int L = (int)sq.L, LW1 = L - W + 1, mid = (int)sq.mid;
+            const int L = (int)sq.L, LW1 = L - W + 1;
             const uint32_t* __restrict__ wseq = pv.words + sq.word_off;
             const uint32_t woff = (uint32_t)sq.word_off;
             const uint32_t* __restrict__ cand = creg + sc.x;
             uint32_t c_first = lane < sc.y ? cand[lane] : 0u;       // first batch of candidates, in flight with the staging loads
-            const uint32_t* wsrc = wseq;                            // generic pointers: shared staging or global
-            const uint16_t* yp = pv.ypatch + (uint64_t)n * (K + 1);
+            const uint32_t* wsrc = wseq;                            // generic pointer: shared staging or global
             const int last_word = ((L - W - KD) >> 4) + 4;          // staging index of the last word any window of this sequence reads
             if (stage && last_word < STAGE_SEQ_WORDS) {
                 __syncwarp();                                       // the previous sequence's readers are done
                 const uint32_t* __restrict__ g = wseq - 2;          // two pad words in front: windows that start before the sequence
                 for (int k = lane; k <= last_word; k += 32) stg[k] = g[k];
-                if (mid >= 0 && lane <= K) reinterpret_cast<uint16_t*>(stg + STAGE_SEQ_WORDS)[lane] = yp[lane];
                 __syncwarp();
-                wsrc = stg + 2; yp = reinterpret_cast<const uint16_t*>(stg + STAGE_SEQ_WORDS);
+                wsrc = stg + 2;
             }
             const float pos = gp.q / (float)LW1;
-            const int tl = min(max(L - 2 * W + 2, 0), LW1);
-            int n0 = tl, n1 = tl;
-            if (mid >= 0) { n0 = min(max(mid - W + 1, 0), tl); n1 = min(mid + K + 1, tl); }
             NormAcc acc; acc.clear();
             // Up to two batches are held back until the normaliser is known: a window whose posterior rounds to zero in the
             // M-step's fixed point (val / norm < 2^-41; about a quarter of those above the a-priori threshold, because norm
