@@ -1,5 +1,5 @@
 #!/bin/bash
-# Runs on the GPU box (via gpurun): GPU parity tests, smoke, bench lines, microbench. No ncu (see gpu_round.sh).
+# Runs on the GPU box (via gpurun): GPU parity tests, smoke, bench lines, microbench. No ncu (see gpu_round2.sh).
 set -u
 mkdir -p gpurun_out
 TAG=${1:-chk}
