@@ -611,7 +611,7 @@ k_eexact(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
     const int lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-    const int W = gp.W, K = gp.K, KD = gp.kd;
+    const int W = gp.W, KD = gp.kd;
     const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab);
     long long llh_fx = 0, rsum_fx = 0;
     const float one_minus_q = 1.0f - gp.q;
