@@ -228,6 +228,8 @@ struct bamm_em {
     int grid_pe = 0, block_pe = 1024;
     size_t smem_pe = 0;
     uint32_t nparts = 1;
+    uint32_t gen_nrep = 1;          // generic M-step without shared-memory tables: copies of the global count table
+    int gen_nsplit = 0, gen_nc = 0; // ... or column ranges with shared-memory low words (k_mstep_cols), 0 = off
     // device
     uint32_t* d_seq_ids = nullptr;
     uint64_t* d_r_off = nullptr;

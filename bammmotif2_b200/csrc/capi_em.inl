@@ -406,6 +406,23 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         } else {
             em->smem_e = em->smem_m = 0;
             em->grid_e = em->grid_m = sms * 4;
+            // global-memory count tables: a few copies (L2-resident) spread the atomics on hot bins
+            uint32_t nrep = getenv("BAMM_GEN_REPLICAS") ? (uint32_t)std::max(1, atoi(getenv("BAMM_GEN_REPLICAS"))) : 16u;
+            while (nrep > 1 && (uint64_t)nrep * em->nbin * 8 > (128ull << 20)) nrep >>= 1;
+            em->gen_nrep = em->nparts = nrep;
+            // when a few columns of low words fit shared memory: column ranges x sequence shares (k_mstep_cols)
+            const size_t col_bytes = (size_t)em->Yn * 4;
+            if (col_bytes <= (size_t)max_optin && !getenv("BAMM_GEN_NO_COLS")) {
+                em->gen_nc = (int)std::min<size_t>((size_t)W, (size_t)max_optin / col_bytes);
+                em->gen_nsplit = (W + em->gen_nc - 1) / em->gen_nc;
+                em->gen_nc = (W + em->gen_nsplit - 1) / em->gen_nsplit;
+                const int ngroups = std::max(1, sms / em->gen_nsplit);
+                em->grid_m = ngroups * em->gen_nsplit;
+                em->smem_m = (size_t)em->gen_nc * col_bytes;
+                const bool ok = ia->bytes == 2 ? !max_smem_optin(k_mstep_cols<uint16_t>, em->smem_m) : !max_smem_optin(k_mstep_cols<uint32_t>, em->smem_m);
+                if (!ok) { fail(BAMM_E_CUDA, "cannot opt in to %zu bytes of shared memory", em->smem_m); bamm_em_destroy(em); return BAMM_E_CUDA; }
+                em->nparts = (uint32_t)ngroups;
+            }
         }
     }
     // ---- packed path geometry
@@ -723,10 +740,10 @@ static int launch_estep(bamm_em* em, cudaEvent_t* split = nullptr /* 2 events: a
         SubsetView sv = view_of(em);
         if (ia.bytes == 2) {
             if (em->smem_tables) k_estep<uint16_t, true><<<em->grid_e, em->block, em->smem_e, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
-            else                 k_estep<uint16_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+            else                 k_estep<uint16_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_sT, em->q, em->d_r, scal);
         } else {
             if (em->smem_tables) k_estep<uint32_t, true><<<em->grid_e, em->block, em->smem_e, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
-            else                 k_estep<uint32_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
+            else                 k_estep<uint32_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_sT, em->q, em->d_r, scal);
         }
         CU(cudaGetLastError());
     }
@@ -771,12 +788,15 @@ static int launch_mstep_accumulate(bamm_em* em) {
     if (em->ngen) {
         IndexArray& ia = em->ss->index[em->K];
         SubsetView sv = view_of(em);
-        if (ia.bytes == 2) {
-            if (em->smem_tables) k_mstep<uint16_t, true><<<em->grid_m, em->block, em->smem_m, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
-            else                 k_mstep<uint16_t, false><<<em->grid_m, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
+        if (em->gen_nsplit) {
+            if (ia.bytes == 2) k_mstep_cols<uint16_t><<<em->grid_m, 1024, em->smem_m, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, em->gen_nsplit, em->gen_nc);
+            else               k_mstep_cols<uint32_t><<<em->grid_m, 1024, em->smem_m, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, em->gen_nsplit, em->gen_nc);
+        } else if (ia.bytes == 2) {
+            if (em->smem_tables) k_mstep<uint16_t, true><<<em->grid_m, em->block, em->smem_m, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, 1u);
+            else                 k_mstep<uint16_t, false><<<em->grid_m, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, em->gen_nrep);
         } else {
-            if (em->smem_tables) k_mstep<uint32_t, true><<<em->grid_m, em->block, em->smem_m, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
-            else                 k_mstep<uint32_t, false><<<em->grid_m, em->block, 0, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part);
+            if (em->smem_tables) k_mstep<uint32_t, true><<<em->grid_m, em->block, em->smem_m, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, 1u);
+            else                 k_mstep<uint32_t, false><<<em->grid_m, em->block, 0, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, em->gen_nrep);
         }
         CU(cudaGetLastError());
     }

@@ -115,7 +115,7 @@ struct SubsetView {
 // the exchange buffer with one 64-bit atomic per warp: integer sums => order-independent result.
 template <typename YT, bool SMEM>
 __global__ void __launch_bounds__(512)
-k_estep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float* __restrict__ s_g, float q,
+k_estep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float* __restrict__ s_g /* SMEM: [j][y]; else [y][j] */, float q,
         float* __restrict__ r, unsigned long long* __restrict__ scal /* [0]=llh_fx, [1]=rsum_fx */) {
     extern __shared__ float s_sh[];
     const float* s = s_g;
@@ -144,7 +144,9 @@ k_estep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float
             float prod = 1.0f;
             for (int j = 0; j < W; j++) {
                 const uint32_t y = st.get(lane, j);
-                if (j <= jmax) prod *= s[(uint32_t)j * Yn + y];
+                // table in global memory: the [y][j] copy, where the entries lane p reads at column j and lane p+1 read at
+                // column j-1 share a row (same k-mer) => neighbouring lanes reuse the line in L1 one step later
+                if (j <= jmax) prod *= SMEM ? s[(uint32_t)j * Yn + y] : __ldg(s + (uint64_t)y * W + j);
             }
             if (p < LW1) {
                 const float val = prod * pos;
@@ -177,10 +179,12 @@ k_estep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float
 template <typename YT, bool SMEM>
 __global__ void __launch_bounds__(512)
 k_mstep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float* __restrict__ r,
-        unsigned long long* __restrict__ part /* SMEM: [gridDim.x][W*Yn]; else one [W*Yn] table */) {
+        unsigned long long* __restrict__ part /* SMEM: [gridDim.x][W*Yn]; else nrep [W*Yn] tables shared by the CTAs */, uint32_t nrep) {
     extern __shared__ uint32_t lo_sh[];
     const uint32_t nbin = (uint32_t)W * Yn;
-    unsigned long long* mypart = SMEM ? part + (uint64_t)blockIdx.x * nbin : part;
+    // tables too large for shared memory: CTA c adds into copy c % nrep in global memory, so that the few hot bins of a
+    // large alphabet (A = 6 data is mostly ACGT) are not one serialised address for the whole grid
+    unsigned long long* mypart = part + (uint64_t)(SMEM ? blockIdx.x : blockIdx.x % nrep) * nbin;
     if (SMEM) {
         for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) lo_sh[i] = 0u;
         __syncthreads();
@@ -226,6 +230,65 @@ k_mstep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float
             const uint32_t v = lo_sh[i];
             if (v) atomicAdd(&mypart[i], (unsigned long long)v);
         }
+    }
+}
+
+// The same accumulation when the W * Yn table does not fit shared memory but a few columns do (A = 6 at order 5: one
+// column = 187 KB): the grid is cut into nsplit column ranges x ngroups sequence shares, CTA (share g, range c) keeps the low
+// words of columns [c nc, c nc + nc) in shared memory and adds into partial table g. r is read once per column range
+// (L2 / HBM streaming) instead of paying one 64-bit global atomic per window and column.
+constexpr int MC_U = 8;
+template <typename YT>
+__global__ void __launch_bounds__(1024)
+k_mstep_cols(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float* __restrict__ r,
+             unsigned long long* __restrict__ part /* [gridDim.x / nsplit][W*Yn] */, int nsplit, int nc) {
+    extern __shared__ uint32_t lo_sh[];
+    const int split = blockIdx.x % nsplit, g = blockIdx.x / nsplit, ngroups = gridDim.x / nsplit;
+    const int j0 = split * nc, j1 = min(W, j0 + nc);
+    if (j0 >= j1) return;
+    const uint32_t nb = (uint32_t)(j1 - j0) * Yn;
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) lo_sh[i] = 0u;
+    __syncthreads();
+    unsigned long long* mypart = part + (uint64_t)g * W * Yn + (uint64_t)j0 * Yn;
+    const int lane = threadIdx.x & 31;
+    const uint32_t wpc = blockDim.x >> 5;
+    for (uint32_t i = g * wpc + (threadIdx.x >> 5); i < sv.nsub; i += ngroups * wpc) {
+        const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : i;
+        const uint64_t base = sv.seq_off[n], L = sv.seq_off[n + 1] - base;
+        const uint64_t LW1 = L - W + 1;
+        const YT* __restrict__ yn = Y + base;
+        const float* __restrict__ rn = r + sv.r_off[i];
+        // MC_U windows per lane and round: their loads of r and of the k-mer indices are independent and in flight together
+        // (one CTA per SM: the memory latency has to be covered inside the warp)
+        for (uint64_t p0 = lane; p0 < LW1; p0 += 32 * MC_U) {
+            unsigned long long X[MC_U];
+#pragma unroll
+            for (int u = 0; u < MC_U; u++) {
+                const uint64_t p = p0 + 32 * u;
+                const float rv = p < LW1 ? rn[L - W - p] : 0.0f;
+                X[u] = rv > 0.0f ? __float2ull_rn(rv * FX_SCALE_F) : 0ull;
+            }
+            for (int j = j0; j < j1; j++) {
+                uint32_t y[MC_U];
+#pragma unroll
+                for (int u = 0; u < MC_U; u++) y[u] = p0 + 32 * u + j < L ? (uint32_t)yn[p0 + 32 * u + j] : 0u;
+#pragma unroll
+                for (int u = 0; u < MC_U; u++) {
+                    const uint64_t p = p0 + 32 * u;
+                    if (X[u] == 0 || p >= LW1 || (uint64_t)j > L - W - p) continue;     // j <= jmax = min(W-1, L-W-p), EM.cpp:167
+                    const uint32_t xlo = (uint32_t)X[u], xhi = (uint32_t)(X[u] >> 32);
+                    const uint32_t bin = (uint32_t)(j - j0) * Yn + y[u];
+                    const uint32_t old = atomicAdd(&lo_sh[bin], xlo);
+                    const uint32_t h = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
+                    if (h) atomicAdd(&mypart[bin], (unsigned long long)h << 32);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+        const uint32_t v = lo_sh[i];
+        if (v) atomicAdd(&mypart[i], (unsigned long long)v);
     }
 }
 

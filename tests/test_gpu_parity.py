@@ -309,11 +309,11 @@ def test_properties_at_scale(capi):
     assert np.all(np.isfinite(v)) and np.all(v > 0) and np.all(v <= 1.0)   # Motif.h:116 asserts v <= 1 for order 0
 
 
-@pytest.mark.parametrize("A,K,W,packed", [(6, 5, 6, False), (6, 3, 8, False), (4, 6, 8, True), (4, 5, 24, True),
+@pytest.mark.parametrize("A,K,W,packed", [(6, 5, 6, False), (6, 5, 13, False), (6, 4, 12, False), (6, 3, 8, False), (4, 6, 8, True), (4, 5, 24, True),
                                           (4, 4, 31, True), (4, 2, 32, True), (4, 6, 28, True), (4, 0, 32, True)])
 def test_large_tables_against_oracle(capi, oracle, A, K, W, packed):
-    """Orders / alphabets beyond the fixtures: the 6-letter alphabet at order 5 (46 656-row table, 1.1 MB: stays in L2,
-    counts through global atomics), order 6 on ACGT (16 384 rows), and a wide order-5 motif whose table forces one
+    """Orders / alphabets beyond the fixtures: the 6-letter alphabet at order 5 (46 656-row table: one column of low words per CTA in shared
+    memory, k_mstep_cols; order 4 takes six columns per CTA), order 6 on ACGT (16 384 rows), and a wide order-5 motif whose table forces one
     column per group, and motifs so wide that window + context exceed one 32-base window word (column passes of the
     E-step, column splits of the M-step, each with its own word alignment) — two full iterations against the CPU oracle on seeded random sequences (both strands, with the
     rand()-patched middle N)."""
