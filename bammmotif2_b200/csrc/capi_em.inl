@@ -809,7 +809,7 @@ static int launch_mstep_reduce(bamm_em* em) {
         // fused reduce + NVLink push to every rank, then wait-and-sum on this rank (no collective call, no host)
         em->peer_epoch++;
         const uint32_t parity = em->peer_epoch & 1u, words = em->nbin + 2;
-        k_reduce_push<<<(words + 255) / 256, 256, 0, em->stream>>>(em->d_part, em->nparts, em->nbin, em->d_xbuf + em->nbin, em->peer_ptrs,
+        k_reduce_push<<<reduce_grid(words), RP_THREADS, 0, em->stream>>>(em->d_part, em->nparts, em->nbin, em->d_xbuf + em->nbin, em->peer_ptrs,
                                                                    em->peer_rank, em->peer_world, parity, em->peer_epoch, em->d_peer_done);
         CU(cudaGetLastError());
         const size_t slot_bytes = (size_t)2 * em->peer_world * words * sizeof(unsigned long long);
@@ -820,7 +820,7 @@ static int launch_mstep_reduce(bamm_em* em) {
         em->peer_sums_global = true;
         return BAMM_OK;
     }
-    k_reduce_parts<<<(em->nbin + 255) / 256, 256, 0, em->stream>>>(em->d_part, em->nparts, em->nbin, em->d_xbuf);
+    k_reduce_parts<<<reduce_grid(em->nbin), RP_THREADS, 0, em->stream>>>(em->d_part, em->nparts, em->nbin, em->d_xbuf);
     CU(cudaGetLastError());
     return BAMM_OK;
 }

@@ -292,14 +292,31 @@ k_mstep_cols(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const 
     }
 }
 
-// Sum of the per-CTA partial tables (integers: any order gives the same bits) into the exchange buffer.
-__global__ void k_reduce_parts(const unsigned long long* __restrict__ part, uint32_t nparts, uint32_t nbin,
-                               unsigned long long* __restrict__ xbuf) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbin) return;
+// Sum of the per-CTA partial tables (integers: any order gives the same bits) into the exchange buffer. A CTA sums 32
+// consecutive bins; its RP_SUB warps each take every RP_SUB-th partial table (256-byte coalesced reads, nparts / RP_SUB
+// independent loads per thread instead of nparts) and warp 0 adds the RP_SUB partial sums. Launch: RP_THREADS threads,
+// reduce_grid(bins) CTAs.
+constexpr int RP_SUB = 8, RP_THREADS = 32 * RP_SUB;
+static inline unsigned reduce_grid(uint32_t bins) { return (bins + 31u) / 32u; }
+__device__ __forceinline__ unsigned long long sum_parts_cta(const unsigned long long* __restrict__ part, uint32_t nparts, uint32_t nbin,
+                                                            uint32_t b, unsigned long long (*sh)[32]) {
+    const uint32_t sub = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long acc = 0;
-    for (uint32_t c = 0; c < nparts; c++) acc += part[(uint64_t)c * nbin + b];
-    xbuf[b] = acc;
+    if (b < nbin) for (uint32_t c = sub; c < nparts; c += RP_SUB) acc += part[(uint64_t)c * nbin + b];
+    sh[sub][lane] = acc;
+    __syncthreads();
+    if (sub == 0) {
+#pragma unroll
+        for (int u = 1; u < RP_SUB; u++) acc += sh[u][lane];
+    }
+    return acc;                                   // complete in warp 0 only
+}
+__global__ void __launch_bounds__(RP_THREADS)
+k_reduce_parts(const unsigned long long* __restrict__ part, uint32_t nparts, uint32_t nbin, unsigned long long* __restrict__ xbuf) {
+    __shared__ unsigned long long sh[RP_SUB][32];
+    const uint32_t b = blockIdx.x * 32 + (threadIdx.x & 31);
+    const unsigned long long acc = sum_parts_cta(part, nparts, nbin, b, sh);
+    if (threadIdx.x < 32 && b < nbin) xbuf[b] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -312,15 +329,16 @@ __global__ void k_reduce_parts(const unsigned long long* __restrict__ part, uint
 constexpr int MAX_PEERS = 16;
 struct PeerPtrs { unsigned long long* slots[MAX_PEERS]; unsigned int* flags[MAX_PEERS]; };
 
-__global__ void k_reduce_push(const unsigned long long* __restrict__ part, uint32_t nparts, uint32_t nbin,
+__global__ void __launch_bounds__(RP_THREADS)
+k_reduce_push(const unsigned long long* __restrict__ part, uint32_t nparts, uint32_t nbin,
                               const unsigned long long* __restrict__ scal /* 2 scalars of the E-step */,
                               PeerPtrs pp, int rank, int world, uint32_t parity, uint32_t epoch, unsigned int* __restrict__ done) {
+    __shared__ unsigned long long sh[RP_SUB][32];
     const uint32_t words = nbin + 2;
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < words) {
-        unsigned long long acc = 0;
-        if (b < nbin) for (uint32_t c = 0; c < nparts; c++) acc += part[(uint64_t)c * nbin + b];
-        else acc = scal[b - nbin];
+    const uint32_t b = blockIdx.x * 32 + (threadIdx.x & 31);
+    unsigned long long acc = sum_parts_cta(part, nparts, nbin, b, sh);
+    if (threadIdx.x < 32 && b < words) {
+        if (b >= nbin) acc = scal[b - nbin];
         const uint64_t at = ((uint64_t)parity * world + rank) * words + b;
         for (int p = 0; p < world; p++) pp.slots[p][at] = acc;
     }
