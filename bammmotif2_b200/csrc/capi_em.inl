@@ -556,17 +556,21 @@ static int launch_tables(bamm_em* em, const float* d_s, float* d_tab_dst) {
     if (!em->npk) return BAMM_OK;
     for (size_t i = 0; i < em->gplans.size(); i++) {
         const uint32_t total = em->gplans[i].table_bytes >> 2;
-        const uint32_t blocks = (total + 255) / 256;
-        k_make_group_tables<false><<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(d_s, em->gplans[i], (float*)((char*)d_tab_dst + i * em->tab_capacity));
+        float* dst = (float*)((char*)d_tab_dst + i * em->tab_capacity);
+        if (i == 0 && em->sparse && em->K >= 1) {           // + one CTA for the bound levels
+            const uint32_t blocks = (total + 1023) / 1024;
+            k_em_tables<<<(blocks < 296 ? blocks : 296) + 1, 1024, 0, em->stream>>>(d_s, em->gplans[i], dst, em->blev, em->d_U);
+        } else {
+            const uint32_t blocks = (total + 255) / 256;
+            k_make_group_tables<false><<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(d_s, em->gplans[i], dst);
+        }
         CU(cudaGetLastError());
     }
     if (em->sparse) {
-        k_bound_levels<<<1, 1024, 0, em->stream>>>(d_s, em->W, em->K, em->blev, em->d_U);
-        CU(cudaGetLastError());
         const uint32_t total = em->bplan.table_bytes >> 2, blocks = (total + 255) / 256;
         k_make_bound_tables<<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(d_s, em->d_U, em->blev, em->bplan, (uint32_t*)em->d_btab);
         CU(cudaGetLastError());
-        em->launches += 2;
+        em->launches += 1;
     }
     return BAMM_OK;
 }

@@ -164,10 +164,10 @@ __global__ void k_make_ypatch(const uint64_t* __restrict__ ppos, const uint64_t*
 // (newest base in the low digits), y_j = the part of the (K+1)-mer ending at p+j that lies inside the group's bases
 // (digits outside do not influence s[j][.], see above).
 template <bool LOGSUM>
-__global__ void k_make_group_tables(const float* __restrict__ s, GroupPlan gp, float* __restrict__ tab) {
+__device__ __forceinline__ void group_tables_part(const float* __restrict__ s, const GroupPlan& gp, float* __restrict__ tab, uint32_t nblocks) {
     const uint32_t total = gp.table_bytes >> 2;
     const uint32_t maskK = gp.Yn - 1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nblocks * blockDim.x) {
         int g = 0;
         while (g + 1 < gp.G && i >= (gp.base[g + 1] >> 2)) g++;
         const uint32_t z = i - (gp.base[g] >> 2);
@@ -183,6 +183,10 @@ __global__ void k_make_group_tables(const float* __restrict__ s, GroupPlan gp, f
         tab[i] = p;
     }
 }
+template <bool LOGSUM>
+__global__ void k_make_group_tables(const float* __restrict__ s, GroupPlan gp, float* __restrict__ tab) {
+    group_tables_part<LOGSUM>(s, gp, tab, gridDim.x);
+}
 
 // ---- bound tables of the pruned E-step (estep.cuh, k_ebound) ---------------------------------------------------------
 // A bound group covers the bases lo..hi relative to the window start and the columns col0..hi. A column whose context reaches
@@ -190,19 +194,31 @@ __global__ void k_make_group_tables(const float* __restrict__ s, GroupPlan gp, f
 // bases, U_avail[j][y mod 4^avail]. The levels are built top-down: level a = maximum over the 4 values of the next older base
 // of level a+1 (level K+1 is s itself), one CTA, a barrier per level.
 struct BoundLevels { uint32_t off[12]; };     // off[a]: first float of level a (a = 1..K), [j][4^a]
-__global__ void __launch_bounds__(1024)
-k_bound_levels(const float* __restrict__ s /* [j][Yn] */, int W, int K, BoundLevels bl, float* __restrict__ U) {
+constexpr uint32_t LEV_CAP = 11264;           // floats of the levels kept in shared memory as well (44 KB: all of them up to order 4 at W = 32)
+__device__ __forceinline__ void bound_levels_cta(const float* __restrict__ s /* [j][Yn] */, int W, int K, BoundLevels bl, float* __restrict__ U) {
+    __shared__ float lev[LEV_CAP];            // the small levels: the next level reads them here instead of waiting for global memory
     for (int a = K; a >= 1; a--) {
         const uint32_t Ya = 1u << (2 * a), Ysrc = Ya << 2;
-        const float* __restrict__ src = (a == K) ? s : U + bl.off[a + 1];
+        const bool src_sh = a < K && bl.off[a + 1] + (uint32_t)W * Ysrc <= LEV_CAP;
+        const bool dst_sh = bl.off[a] + (uint32_t)W * Ya <= LEV_CAP;
+        const float* src = (a == K) ? s : src_sh ? lev + bl.off[a + 1] : U + bl.off[a + 1];
         float* __restrict__ dst = U + bl.off[a];
         for (uint32_t i = threadIdx.x; i < (uint32_t)W * Ya; i += blockDim.x) {
             const uint32_t j = i >> (2 * a), y = i & (Ya - 1u);
-            const float* __restrict__ row = src + (size_t)j * Ysrc;
-            dst[i] = fmaxf(fmaxf(row[y], row[Ya + y]), fmaxf(row[2u * Ya + y], row[3u * Ya + y]));
+            const float* row = src + (size_t)j * Ysrc;
+            const float v = fmaxf(fmaxf(row[y], row[Ya + y]), fmaxf(row[2u * Ya + y], row[3u * Ya + y]));
+            dst[i] = v;
+            if (dst_sh) lev[bl.off[a] + i] = v;
         }
         __syncthreads();
     }
+}
+// The tables an EM iteration rebuilds first, in one launch: the exact group tables of a pass on all CTAs but the last, which
+// builds the bound levels meanwhile (both only read s).
+__global__ void __launch_bounds__(1024)
+k_em_tables(const float* __restrict__ s, GroupPlan gp, float* __restrict__ tab, BoundLevels bl, float* __restrict__ U) {
+    if (blockIdx.x + 1 == gridDim.x) bound_levels_cta(s, gp.W, gp.K, bl, U);
+    else group_tables_part<false>(s, gp, tab, gridDim.x - 1);
 }
 // f_g(z) = prod_{j in group g} U_avail(j)[j][...] over the group's T bases lo..hi: an upper bound of the product of the group's
 // columns for EVERY context left of the group's bases. The table is indexed by T+1 bases (lo..hi+1) and an entry holds TWO

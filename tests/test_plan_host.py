@@ -102,7 +102,7 @@ def test_plan_rejects_bad_arguments():
         capi.plan_describe(33, 2)
 
 
-# ---- bound plan of the pruned E-step (csrc/capi_em.inl make_bound_plan, csrc/packed.cuh k_bound_levels / k_make_bound_tables) --------
+# ---- bound plan of the pruned E-step (csrc/capi_em.inl make_bound_plan, csrc/packed.cuh bound_levels_cta / k_make_bound_tables) --------
 def bf16_up(x):
     """Smallest bfloat16 >= x (x >= 0), as float32 — what k_make_bound_tables stores."""
     b = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
