@@ -1,4 +1,5 @@
 #include "FDR.h"
+#include "Util.h"
 
 #include <algorithm>
 #include <cassert>
@@ -102,7 +103,7 @@ void FDR::calculatePR(){
     const size_t negN = negSeqs_.size();
     const float mFold = ( float )negN / ( float )posN;
 
-    srand( 42 );                                    // tie-breaks below draw from a fresh libc stream (FDR.cpp:153)
+    util::srand42( 42 );                                    // tie-breaks below draw from a fresh libc stream (FDR.cpp:153)
 
     if( mops_ ){
         sortScores( posScoreAll_, true );
@@ -146,7 +147,7 @@ void FDR::calculatePR(){
             if( ( ps > ns || idx_posMax == 0 || idx_negMax == negN ) && idx_posMax < posN ){
                 Sl = ps;
                 idx_posMax++;
-            } else if( ps == ns && rand() % 2 == 0 && idx_posMax < posN ){
+            } else if( ps == ns && util::rand31() % 2 == 0 && idx_posMax < posN ){
                 Sl = ps;
                 idx_posMax++;
             } else {

@@ -81,16 +81,16 @@ Motif::Motif( const Motif& o )
 Motif::~Motif(){}
 
 // reference: Motif::initFromBindingSites, src/init/Motif.cpp:134-189. One site per line; flanks are filled with
-// random bases drawn with libc rand() (same expression, so the stream stays aligned with the reference).
+// random bases drawn with libc util::rand31() (same expression, so the stream stays aligned with the reference).
 void Motif::initFromBindingSites( char* indir, size_t l_flank, size_t r_flank ){
     std::ifstream file( indir );
     std::string site;
     while( std::getline( file, site ).good() ){
         C_++;
         for( size_t i = 0; i < l_flank; i++ )
-            site.insert( site.begin(), Alphabet::getBase( static_cast<uint8_t>( static_cast<uint8_t>( rand() ) % static_cast<uint8_t>( Y_[1] ) + 1 ) ) );
+            site.insert( site.begin(), Alphabet::getBase( static_cast<uint8_t>( static_cast<uint8_t>( util::rand31() ) % static_cast<uint8_t>( Y_[1] ) + 1 ) ) );
         for( size_t i = 0; i < r_flank; i++ )
-            site.insert( site.end(), Alphabet::getBase( static_cast<uint8_t>( static_cast<uint8_t>( rand() ) % static_cast<uint8_t>( Y_[1] ) + 1 ) ) );
+            site.insert( site.end(), Alphabet::getBase( static_cast<uint8_t>( static_cast<uint8_t>( util::rand31() ) % static_cast<uint8_t>( Y_[1] ) + 1 ) ) );
         if( site.length() != W_ ){
             fprintf( stderr, "Error: Length of binding site on line %d differs.\nBinding sites should have the same length.\n", ( int )C_ );
             exit( 1 );

@@ -16,7 +16,7 @@ SeqGenerator::SeqGenerator( std::vector<Sequence*> seqs, Motif*, size_t sOrder, 
         n_[k].assign( Y_[k + 1], 0 ); n_seq_[k].assign( Y_[k + 1], 0 );
     }
     A_.assign( sOrder_ + 1, 20.f );
-    srand( 42 );            // reference: SeqGenerator.cpp:33-34 — the sampler always restarts the libc stream
+    util::srand42( 42 );            // reference: SeqGenerator.cpp:33-34 — the sampler always restarts the libc stream
 }
 
 SeqGenerator::~SeqGenerator(){}
@@ -111,11 +111,11 @@ void SeqGenerator::rescale_kmer_frequency( Sequence* refSeq ){
 }
 
 // One Markov-chain sample of length L from range_bar_ (reference: SeqGenerator::bg_sequence /
-// bgseq_on_rescaled_v, src/seq_generator/SeqGenerator.cpp:226-348): one rand() per base, inverse-CDF lookup.
+// bgseq_on_rescaled_v, src/seq_generator/SeqGenerator.cpp:226-348): one util::rand31() per base, inverse-CDF lookup.
 void SeqGenerator::sample_into( std::vector<uint8_t>& sequence, size_t L ){
     sequence.assign( L, 0 );
     const size_t A = Y_[1];
-    float random = ( float )rand() / ( float )RAND_MAX;
+    float random = ( float )util::rand31() / ( float )RAND_MAX;
     for( uint8_t y = 0; y < A; y++ ){
         if( random <= range_bar_[0][y] ){ sequence[0] = y + 1; break; }
     }
@@ -123,7 +123,7 @@ void SeqGenerator::sample_into( std::vector<uint8_t>& sequence, size_t L ){
         const size_t order = i < sOrder_ ? i : sOrder_;            // the first bases use shorter contexts
         size_t yk = 0;
         for( size_t k = order; k > 0; k-- ) yk += ( sequence[i - k] - 1 ) * Y_[k];
-        random = ( float )rand() / ( float )RAND_MAX;
+        random = ( float )util::rand31() / ( float )RAND_MAX;
         for( size_t y = yk, a = 1; y < yk + A; y++, a++ ){
             sequence[i] = static_cast<uint8_t>( a );
             if( random <= range_bar_[order][y] ) break;
@@ -150,7 +150,7 @@ std::unique_ptr<SequenceSet> SeqGenerator::sample_bgseqset_by_fold( size_t fold 
         bamm_seqset* h = nullptr;
         const int rc = bamm_seqset_sample_negatives( tmpl->device(), whole ? NULL : indices.data(), indices.size(), fold, 42, &h );
         if( rc == BAMM_OK ){
-            srand( 42 );                                        // the stream position after sampling is never consumed (FDR re-seeds, FDR.cpp:153)
+            util::srand42( 42 );                                        // the stream position after sampling is never consumed (FDR re-seeds, FDR.cpp:153)
             return std::unique_ptr<SequenceSet>( new SequenceSet( SequenceSet::DeviceBuilt(), h, "> bg_seq" ) );
         }
         if( rc != BAMM_E_STATE ){

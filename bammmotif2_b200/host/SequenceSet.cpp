@@ -1,11 +1,16 @@
 #include "SequenceSet.h"
+#include "Util.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
 #include <limits>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 namespace {
 inline size_t ipow( size_t base, size_t exp ){
@@ -199,11 +204,36 @@ void SequenceSet::appendRecord( const std::string& header, const std::string& ba
 // neighbourhoods the device returns — the same draws in the same order as drawPatches() makes from the host arena.
 // The stored codes stay on the device until a host consumer asks for them.
 bool SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singleStrand ){
-    std::string text( bytes, '\0' );
-    file.read( &text[0], static_cast<std::streamsize>( bytes ) );
-    text.resize( static_cast<size_t>( file.gcount() ) );
-    const char* t = text.data();
-    const size_t n = text.size();
+    // BAMM_TRACE: wall time of the reader's phases on stderr
+    const bool trace = getenv( "BAMM_TRACE" ) != NULL;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto mark = [&]( const char* what ){
+        if( !trace ) return;
+        const auto t = std::chrono::steady_clock::now();
+        std::cerr << "[bamm host] FASTA reader: " << what << " " << std::chrono::duration<double, std::milli>( t - t_mark ).count() << " ms" << std::endl;
+        t_mark = t;
+    };
+    // the text: the file mapped read-only (no copy, no zero-filled buffer); read() into a buffer when it cannot be mapped
+    std::string text;
+    const char* t = nullptr;
+    size_t n = 0;
+    struct Mapping {
+        void* p = MAP_FAILED; size_t len = 0; int fd = -1;
+        ~Mapping(){ if( p != MAP_FAILED ) munmap( p, len ); if( fd >= 0 ) close( fd ); }
+    } map;
+    map.fd = open( sequenceFilepath_.c_str(), O_RDONLY );
+    if( map.fd >= 0 ){
+        map.p = mmap( nullptr, bytes, PROT_READ, MAP_PRIVATE | MAP_POPULATE, map.fd, 0 );
+        if( map.p != MAP_FAILED ){ map.len = bytes; t = static_cast<const char*>( map.p ); n = bytes; }
+    }
+    if( !t ){
+        text.assign( bytes, '\0' );
+        file.read( &text[0], static_cast<std::streamsize>( bytes ) );
+        text.resize( static_cast<size_t>( file.gcount() ) );
+        t = text.data();
+        n = text.size();
+    }
+    mark( "file read" );
 
     std::vector<bamm_fasta_seg> segs, pending;
     std::vector<uint32_t> recL0;
@@ -262,6 +292,7 @@ bool SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singl
         pos = end + 1;
     }
     flush();
+    mark( "lines + headers" );
     // lengths of the records as read (one strand), as the host reader reports them
     maxL_ = recL0.empty() ? 0 : maxL;
     minL_ = recL0.empty() ? std::numeric_limits<size_t>::max() : minL;
@@ -284,6 +315,7 @@ bool SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singl
             std::exit( 1 );
         }
     }
+    mark( "bamm_seqset_encode_text" );
     size_t total = 0;
     for( uint64_t c : counts ) total += c;
     baseFrequencies_.resize( A );
@@ -315,6 +347,7 @@ bool SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singl
     }
     std::vector<uint8_t> win( zpos.size() * 21 );
     BAMM_CHECK( bamm_seqset_code_windows( device_, zpos.data(), zbeg.data(), zend.data(), zpos.size(), win.data() ) );
+    mark( "undefined bases + code windows" );
     // the draws of drawPatches(), from the windows: records in order, undefined bases ascending, positions z..z+10 not yet
     // hashed, bases of each 11-mer from the oldest to the newest
     patchPos_.reserve( zpos.size() * 11 ); patchKmer_.reserve( zpos.size() * 11 );
@@ -324,29 +357,56 @@ bool SequenceSet::readFastaDevice( std::ifstream& file, size_t bytes, bool singl
         const uint8_t* w = win.data() + k * 21;                 // w[10 + d] = code at z + d
         const uint64_t z = zpos[k] - curBeg, L = zend[k] - curBeg;
         const uint64_t last = std::min<uint64_t>( L - 1, z + 10 );
+        // zeros among w[0..c]: a span with this base as its only undefined one needs one draw, and the rest of its hash rolls
+        // from position to position (the usual case: the structural N of a record without other undefined bases)
+        int zcum[22]; zcum[0] = 0;
+        for( int c = 0; c < 21; c++ ) zcum[c + 1] = zcum[c] + ( w[c] == 0 ? 1 : 0 );
+        bool rolling = false;
+        size_t hdet = 0;                                        // hash of the span with the undefined base counted as digit 0
         for( uint64_t i = std::max( next, z ); i <= last; i++ ){
             const size_t span = i < 10 ? static_cast<size_t>( i ) + 1 : 11;
+            const int cNew = 10 + static_cast<int>( i - z ), cOld = cNew - static_cast<int>( span ) + 1;   // window cells of the span
             size_t h = 0;
-            for( size_t kk = span; kk > 0; kk-- ){
-                const uint8_t code = w[10 + static_cast<long long>( i - kk + 1 ) - static_cast<long long>( z )];
-                const size_t digit = ( code == 0 ) ? static_cast<size_t>( rand() ) % A : static_cast<size_t>( code - 1 );
-                h += digit * Y_[kk - 1];
+            if( zcum[cNew + 1] - zcum[cOld] == 1 ){
+                if( rolling && i >= 11 ){                       // the previous span was full: its oldest base leaves
+                    hdet = ( hdet - ( w[cOld - 1] ? static_cast<size_t>( w[cOld - 1] - 1 ) : 0 ) * Y_[10] ) * A + static_cast<size_t>( w[cNew] - 1 );
+                } else if( rolling ){                           // the span still grows at the start of the record
+                    hdet = hdet * A + static_cast<size_t>( w[cNew] - 1 );
+                } else {
+                    hdet = 0;
+                    for( size_t kk = span; kk > 0; kk-- ){
+                        const uint8_t code = w[cNew - static_cast<int>( kk ) + 1];
+                        if( code ) hdet += static_cast<size_t>( code - 1 ) * Y_[kk - 1];
+                    }
+                    rolling = true;
+                }
+                h = hdet + ( static_cast<size_t>( util::rand31() ) % A ) * Y_[i - z];
+            } else {
+                rolling = false;
+                for( size_t kk = span; kk > 0; kk-- ){
+                    const uint8_t code = w[cNew - static_cast<int>( kk ) + 1];
+                    const size_t digit = ( code == 0 ) ? static_cast<size_t>( util::rand31() ) % A : static_cast<size_t>( code - 1 );
+                    h += digit * Y_[kk - 1];
+                }
             }
             patchPos_.push_back( curBeg + i );
             patchKmer_.push_back( h );
         }
         next = std::max( next, last + 1 );
     }
+    mark( "rand() draws" );
     BAMM_CHECK( bamm_seqset_finish_patches( device_, patchPos_.data(), patchKmer_.data(), patchPos_.size() ) );
+    mark( "bamm_seqset_finish_patches" );
     codesOnDevice_ = true;
     finalize();
+    mark( "finalize" );
     return true;
 }
 
-// Positions whose 11-mer hash contains a code-0 base: the reference replaces the 0 by rand() % A separately for every
+// Positions whose 11-mer hash contains a code-0 base: the reference replaces the 0 by util::rand31() % A separately for every
 // (position, k) pair while it builds kmer_ (src/init/Sequence.cpp:35-41). The draws are made here in the same order
 // (records in file order, i ascending, bases of the k-mer from oldest to newest), so the libc rand() stream — and with
-// it every later consumer of rand() — stays aligned with the reference.
+// it every later consumer of util::rand31() — stays aligned with the reference.
 void SequenceSet::drawPatches( uint64_t begin, uint64_t end ){
     const uint8_t* c = codes_.data() + begin;
     const size_t L = static_cast<size_t>( end - begin );
@@ -360,7 +420,7 @@ void SequenceSet::drawPatches( uint64_t begin, uint64_t end ){
             size_t h = 0;
             for( size_t k = span; k > 0; k-- ){
                 const uint8_t code = c[i - k + 1];
-                const size_t digit = ( code == 0 ) ? static_cast<size_t>( rand() ) % A : static_cast<size_t>( code - 1 );
+                const size_t digit = ( code == 0 ) ? static_cast<size_t>( util::rand31() ) % A : static_cast<size_t>( code - 1 );
                 h += digit * Y_[k - 1];
             }
             patchPos_.push_back( begin + i );

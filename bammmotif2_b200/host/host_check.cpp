@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "FDR.h"
+#include "Util.h"
 #include "MotifSet.h"
 #include "SeqGenerator.h"
 
@@ -35,7 +36,13 @@ template <typename T> static std::vector<T> slurp( const std::string& path ){
 int main( int argc, char** argv ){
     if( argc < 3 ) return 2;
     const std::string mode = argv[1];
-    srand( 42 );
+    util::srand42( 42 );
+    if( mode == "rand" ){                                    // rand SEED N: N draws of the private libc-compatible stream
+        util::srand42( static_cast<unsigned>( strtoul( argv[2], nullptr, 10 ) ) );
+        const long n = argc > 3 ? atol( argv[3] ) : 10;
+        for( long i = 0; i < n; i++ ) std::cout << util::rand31() << "\n";
+        return 0;
+    }
     if( mode == "parse" ){                                   // timing of the FASTA reader alone
         Alphabet::init( argv[2] );
         const auto t0 = std::chrono::steady_clock::now();

@@ -10,6 +10,7 @@
 #include <cstdlib>
 
 #include "EM.h"
+#include "Util.h"
 #include "FDR.h"
 #include "Global.h"
 #include "ScoreSeqSet.h"
@@ -57,7 +58,7 @@ int main( int nargs, char* args[] ){
               << "=          Version 2.0 (B200 path)   =" << std::endl
               << "======================================" << std::endl;
 
-    srand( 42 );                                    // reference: mainBaMM.cpp:22
+    util::srand42( 42 );                                    // reference: mainBaMM.cpp:22
     // the first CUDA call creates the device context (0.8 s and more on a multi-GPU box): it runs beside option parsing and
     // the FASTA reader; a failure is not reported here — the first real device call of the main thread reports it
     // BAMM_DEVICES="0,1,2,3" or "0-7": one process drives all of them (EM::optimize splits the sequences over the devices and
@@ -111,7 +112,7 @@ int main( int nargs, char* args[] ){
     const bool rest = minSeqN % posSet.size();
     if( posSet.size() < minSeqN ) Global::mFold = minSeqN / posSet.size() + rest;
 
-    // The reference samples the negative set on every run; nothing reads it (or the rand() state it leaves) unless
+    // The reference samples the negative set on every run; nothing reads it (or the util::rand31() state it leaves) unless
     // --FDR / --scoreSeqset is given, so it is sampled only then.
     std::unique_ptr<SequenceSet> negSequences;
     std::vector<Sequence*> negSet;

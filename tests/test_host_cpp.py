@@ -53,6 +53,18 @@ def run(cmd, **kw):
     return p
 
 
+@pytest.mark.parametrize("seed", [42, 1, 0, 2**31 - 1, 123456789])
+def test_private_rand_stream_equals_libc(bins, seed):
+    """host/Util.h LibcRand is the stream every rand()-dependent step of the reference consumes (srand(42) in mainBaMM.cpp:22,
+    SeqGenerator.cpp:33, FDR.cpp:153): same values as this machine's libc srand() / rand(), including the seed-0 rule."""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(ctypes.c_uint(seed))
+    want = [libc.rand() for _ in range(5000)]
+    out = subprocess.run([os.path.join(bins, "host_check"), "rand", str(seed), "5000"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    assert [int(x) for x in out.split()] == want
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_fasta_encoding_and_kmers_bit_exact(bins, case, tmp_path):
     g = Golden(case)
@@ -93,6 +105,32 @@ def test_fasta_encoding_on_the_device_bit_exact(bins, case, tmp_path):
     for fn in ("codes.u8", "offsets.u64", "kmer.u64", "basefreq.f32"):
         assert open(d_host / fn, "rb").read() == open(d_dev / fn, "rb").read(), fn
     assert len(freq) == g.A
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ss", ["0", "1"])
+def test_fasta_device_reader_with_sparse_undefined_bases(bins, ss, tmp_path):
+    """The k-mer hashes around undefined bases in the device reader: one draw plus a rolling hash where the base is the only
+    undefined one of its 11-mer, the digit-by-digit loop elsewhere — records shorter than 11 bases (growing spans), undefined
+    bases next to each other, at the ends and near the strand junction. Same codes, hashes (= same rand() stream) and
+    frequencies as the host loop."""
+    rng = np.random.default_rng(5)
+    fa = tmp_path / "sparse.fasta"
+    with open(fa, "w") as f:
+        for i in range(400):
+            L = int(rng.integers(3, 16)) if i % 3 == 0 else int(rng.integers(20, 120))
+            sq = rng.choice(list("ACGT"), size=L)
+            for z in rng.integers(0, L, size=int(rng.integers(0, 4))):
+                sq[z] = "N"
+            if i % 7 == 0: sq[0] = "N"
+            if i % 11 == 0: sq[-1] = "N"
+            f.write(">s%d\n%s\n" % (i, "".join(sq)))
+    d_host, d_dev = tmp_path / "h", tmp_path / "d"
+    d_host.mkdir(); d_dev.mkdir()
+    run([os.path.join(bins, "host_check"), "encode", "STANDARD", str(fa), ss, str(d_host)], env=dict(os.environ, BAMM_DEVICE_FASTA="0"))
+    run([os.path.join(bins, "host_check"), "encode", "STANDARD", str(fa), ss, str(d_dev)], env=dict(os.environ, BAMM_DEVICE_FASTA="1"))
+    for fn in ("codes.u8", "offsets.u64", "kmer.u64", "basefreq.f32"):
+        assert open(d_host / fn, "rb").read() == open(d_dev / fn, "rb").read(), fn
 
 
 @pytest.mark.gpu
