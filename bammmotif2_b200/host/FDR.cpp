@@ -1,6 +1,7 @@
 #include "FDR.h"
 #include "Util.h"
 
+#include <chrono>
 #include <algorithm>
 #include <cassert>
 #include <cmath>
@@ -46,6 +47,15 @@ void FDR::evaluateMotif( bool EMoptimize, bool CGSoptimize, bool optimizeQ, bool
     std::vector<Sequence*> negSet;
     for( size_t n = 0; n + cvFold_ <= negSeqs_.size(); n += cvFold_ ) negSet.push_back( negSeqs_[n] );
 
+    // BAMM_TRACE: wall time of the phases of every fold on stderr
+    const bool trace = getenv( "BAMM_TRACE" ) != NULL;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto mark = [&]( size_t fold, const char* what ){
+        if( !trace ) return;
+        const auto t = std::chrono::steady_clock::now();
+        std::cerr << "[bamm host] fold " << fold << ": " << what << " " << std::chrono::duration<double, std::milli>( t - t_mark ).count() << " ms" << std::endl;
+        t_mark = t;
+    };
     for( size_t fold = 0; fold < cvFold_; fold++ ){
         Motif* motif = new Motif( *motif_ );
         std::vector<Sequence*> testSet, trainSet;
@@ -54,17 +64,23 @@ void FDR::evaluateMotif( bool EMoptimize, bool CGSoptimize, bool optimizeQ, bool
                 ( f != fold ? trainSet : testSet ).push_back( posSeqs_[n + f] );
             }
         }
+        mark( fold, "train / test split" );
         if( EMoptimize ){
             EM model( motif, bgModel_, trainSet, optimizeQ, false, frac );
+            mark( fold, "EM object" );
             if( advanceEM ) model.mask(); else model.optimize();
             updatedQ = model.getQ();
+            mark( fold, "EM::optimize" );
         }
+        mark( fold, "EM object released" );
         ScoreSeqSet score_testset( motif, bgModel_, testSet );
         score_testset.setKeepMops( mops_ );
         score_testset.calcLogOdds();
+        mark( fold, "scores of the held-out positives" );
         ScoreSeqSet score_negset( motif, bgModel_, negSet );
         score_negset.setKeepMops( mops_ );
         score_negset.calcLogOdds();
+        mark( fold, "scores of the negatives" );
 
         if( mops_ ){
             const std::vector<float>& p = score_testset.flatMopsScores();
@@ -79,6 +95,7 @@ void FDR::evaluateMotif( bool EMoptimize, bool CGSoptimize, bool optimizeQ, bool
             negScoreMax_.insert( negScoreMax_.end(), z.begin(), z.end() );
         }
         delete motif;
+        mark( fold, "scores appended" );
     }
     q_ = updatedQ;
     calculatePR();
@@ -142,6 +159,15 @@ void FDR::calculatePR(){
         assert( lambda > 0.f );
 
         float Sl = 0.f;
+        ZOOPS_TP_.reserve( posN + negN ); ZOOPS_FP_.reserve( posN + negN ); ZOOPS_FDR_.reserve( posN + negN );
+        ZOOPS_Rec_.reserve( posN + negN ); PN_Pvalue_.reserve( posN + negN );
+        // the two neighbours of Sl among the sorted negatives (std::lower_bound / std::upper_bound with std::greater in the
+        // reference, FDR.cpp:245-247): the walk hands out scores in descending order, so both positions only move forward and
+        // are advanced instead of searched; a score above the previous one (the forced first positive) searches again
+        size_t lb = 0, ub = 0;
+        const size_t nNeg = negScoreMax_.size();
+        float lastSl = 0.f;
+        bool searched = false;
         for( size_t i = 0; i < posN + negN; i++ ){
             const float ps = at( posScoreMax_, idx_posMax ), ns = at( negScoreMax_, idx_negMax );
             if( ( ps > ns || idx_posMax == 0 || idx_negMax == negN ) && idx_posMax < posN ){
@@ -162,11 +188,19 @@ void FDR::calculatePR(){
             float p_value;
             if( Sl <= negScoreMax_[n_top] ){
                 // rank among the negatives, interpolated between the neighbouring negative scores
-                const float Sl_upper = *( std::lower_bound( negScoreMax_.begin(), negScoreMax_.end(), Sl, std::greater<float>() ) - 1 );
+                if( !searched || Sl > lastSl ){
+                    lb = static_cast<size_t>( std::lower_bound( negScoreMax_.begin(), negScoreMax_.end(), Sl, std::greater<float>() ) - negScoreMax_.begin() );
+                    ub = static_cast<size_t>( std::upper_bound( negScoreMax_.begin(), negScoreMax_.end(), Sl, std::greater<float>() ) - negScoreMax_.begin() );
+                    searched = true;
+                } else {
+                    while( lb < nNeg && negScoreMax_[lb] > Sl ) lb++;           // first negative that is not above Sl
+                    while( ub < nNeg && !( Sl > negScoreMax_[ub] ) ) ub++;      // first negative below Sl
+                }
+                lastSl = Sl;
+                const float Sl_upper = negScoreMax_[lb ? lb - 1 : 0];           // lb > 0 unless the top negatives all equal Sl (the reference reads before the array then)
                 // (a score below every negative has no lower neighbour; the reference reads one past the end there —
                 //  the score itself is used instead, which puts the p-value at the top of the range)
-                auto lower = std::upper_bound( negScoreMax_.begin(), negScoreMax_.end(), Sl, std::greater<float>() );
-                const float Sl_lower = lower != negScoreMax_.end() ? *lower : Sl;
+                const float Sl_lower = ub < nNeg ? negScoreMax_[ub] : Sl;
                 p_value = ( idx_negMax + ( Sl_upper - Sl ) / ( Sl_upper - Sl_lower + 1e-5 ) ) / ( float )negN;
             } else {
                 p_value = n_top * expf( ( negScoreMax_[n_top] - Sl ) / lambda ) / negN;
