@@ -129,30 +129,45 @@ k_estep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
     long long llh_fx = 0, rsum_fx = 0;
     const float one_minus_q = 1.0f - q;
-    for (uint32_t i = warp; i < sv.nsub; i += nwarps) {
-        const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : i;
-        const uint64_t base = sv.seq_off[n], L = sv.seq_off[n + 1] - base;
+    // the offsets of the NEXT sequence and the k-mer indices of the NEXT 32 windows are loaded while the current ones are
+    // processed: the table gathers of a round depend on its indices, a chain the 16 warps of a CTA do not cover by themselves
+    struct Hdr { uint64_t base, L, roff; };
+    auto load_hdr = [&](uint64_t i) {
+        Hdr h; h.base = 0; h.L = 0; h.roff = 0;
+        if (i < sv.nsub) {
+            const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : (uint32_t)i;
+            h.base = sv.seq_off[n]; h.L = sv.seq_off[n + 1] - h.base; h.roff = sv.r_off[i];
+        }
+        return h;
+    };
+    Hdr hd = load_hdr(warp);
+    for (uint64_t i = warp; i < sv.nsub; i += nwarps) {
+        const Hdr hn = load_hdr(i + nwarps);
+        const uint64_t L = hd.L;
         const uint64_t LW1 = L - W + 1;
-        const YT* __restrict__ yn = Y + base;
-        float* __restrict__ rn = r + sv.r_off[i];
+        const YT* __restrict__ yn = Y + hd.base;
+        float* __restrict__ rn = r + hd.roff;
+        hd = hn;
         const float pos = q / (float)LW1;
         float sum = 0.0f;
+        Strip<YT> st; st.load(yn, lane, L);
         for (uint64_t p0 = 0; p0 < LW1; p0 += 32) {
             const uint64_t p = p0 + lane;
-            Strip<YT> st; st.load(yn, p, L);
+            Strip<YT> nx; nx.load(yn, p + 32, L);
             const int jmax = (p < LW1) ? (int)min((uint64_t)(W - 1), L - W - p) : -1;
             float prod = 1.0f;
             for (int j = 0; j < W; j++) {
                 const uint32_t y = st.get(lane, j);
                 // table in global memory: the [y][j] copy, where the entries lane p reads at column j and lane p+1 read at
                 // column j-1 share a row (same k-mer) => neighbouring lanes reuse the line in L1 one step later
-                if (j <= jmax) prod *= SMEM ? s[(uint32_t)j * Yn + y] : __ldg(s + (uint64_t)y * W + j);
+                if (j <= jmax) prod *= SMEM ? s[(uint32_t)j * Yn + y] : __ldg(s + (y * (uint32_t)W + (uint32_t)j));
             }
             if (p < LW1) {
                 const float val = prod * pos;
                 rn[L - W - p] = val;
                 sum += val;
             }
+            st = nx;
         }
         sum = warp_sum(sum);
         const float norm = one_minus_q + sum;
@@ -237,7 +252,7 @@ k_mstep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float
 // column = 187 KB): the grid is cut into nsplit column ranges x ngroups sequence shares, CTA (share g, range c) keeps the low
 // words of columns [c nc, c nc + nc) in shared memory and adds into partial table g. r is read once per column range
 // (L2 / HBM streaming) instead of paying one 64-bit global atomic per window and column.
-constexpr int MC_U = 8;
+constexpr int MC_U = 4;
 template <typename YT>
 __global__ void __launch_bounds__(1024)
 k_mstep_cols(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float* __restrict__ r,
@@ -252,38 +267,63 @@ k_mstep_cols(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const 
     unsigned long long* mypart = part + (uint64_t)g * W * Yn + (uint64_t)j0 * Yn;
     const int lane = threadIdx.x & 31;
     const uint32_t wpc = blockDim.x >> 5;
-    for (uint32_t i = g * wpc + (threadIdx.x >> 5); i < sv.nsub; i += ngroups * wpc) {
-        const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : i;
-        const uint64_t base = sv.seq_off[n], L = sv.seq_off[n + 1] - base;
-        const uint64_t LW1 = L - W + 1;
-        const YT* __restrict__ yn = Y + base;
-        const float* __restrict__ rn = r + sv.r_off[i];
-        // MC_U windows per lane and round: their loads of r and of the k-mer indices are independent and in flight together
-        // (one CTA per SM: the memory latency has to be covered inside the warp)
-        for (uint64_t p0 = lane; p0 < LW1; p0 += 32 * MC_U) {
+    // One CTA per SM (the table fills shared memory), so the memory latency has to be covered inside the warp: the offsets of the
+    // NEXT sequence are loaded while this one is processed (seq_ids -> seq_off is a chain of two loads), and the loads of the
+    // next round of MC_U windows per lane (r and the k-mer index of the first column) are issued before the atomics of this one.
+    struct Hdr { uint64_t base, L, roff; };
+    auto load_hdr = [&](uint64_t i) {
+        Hdr h; h.base = 0; h.L = 0; h.roff = 0;
+        if (i < sv.nsub) {
+            const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : (uint32_t)i;
+            h.base = sv.seq_off[n]; h.L = sv.seq_off[n + 1] - h.base; h.roff = sv.r_off[i];
+        }
+        return h;
+    };
+    const uint64_t first = (uint64_t)g * wpc + (threadIdx.x >> 5), stride = (uint64_t)ngroups * wpc;
+    Hdr h = load_hdr(first);
+    for (uint64_t i = first; i < sv.nsub; i += stride) {
+        const Hdr hn = load_hdr(i + stride);
+        const uint32_t L = (uint32_t)h.L, LW1 = L - W + 1, lim = L - W;         // stored lengths are below 2^32 (host/SequenceSet.cpp)
+        const YT* __restrict__ yn = Y + h.base + j0;                             // k-mer of the first column of window p: yn[p]
+        const float* __restrict__ rn = r + h.roff + lim;                         // r of window p: rn[-p] (EM.cpp:173, reversed index)
+        float rv[MC_U]; uint32_t yv[MC_U];
+#pragma unroll
+        for (int u = 0; u < MC_U; u++) {
+            const uint32_t p = (uint32_t)lane + 32 * u;
+            const bool in = p < LW1;                                             // then p + j0 <= L - W + j0 < L
+            rv[u] = in ? *(rn - p) : 0.0f;
+            yv[u] = in ? (uint32_t)yn[p] : 0u;
+        }
+        for (uint32_t p0 = lane; p0 < LW1; p0 += 32 * MC_U) {
+            float rnx[MC_U]; uint32_t ynx[MC_U];
+#pragma unroll
+            for (int u = 0; u < MC_U; u++) {                                   // next round
+                const uint32_t p = p0 + 32 * (MC_U + u);
+                const bool in = p < LW1;
+                rnx[u] = in ? *(rn - p) : 0.0f;
+                ynx[u] = in ? (uint32_t)yn[p] : 0u;
+            }
             unsigned long long X[MC_U];
 #pragma unroll
-            for (int u = 0; u < MC_U; u++) {
-                const uint64_t p = p0 + 32 * u;
-                const float rv = p < LW1 ? rn[L - W - p] : 0.0f;
-                X[u] = rv > 0.0f ? __float2ull_rn(rv * FX_SCALE_F) : 0ull;
-            }
+            for (int u = 0; u < MC_U; u++) X[u] = rv[u] > 0.0f ? __float2ull_rn(rv[u] * FX_SCALE_F) : 0ull;      // 0 for p >= LW1
             for (int j = j0; j < j1; j++) {
                 uint32_t y[MC_U];
 #pragma unroll
-                for (int u = 0; u < MC_U; u++) y[u] = p0 + 32 * u + j < L ? (uint32_t)yn[p0 + 32 * u + j] : 0u;
+                for (int u = 0; u < MC_U; u++) y[u] = j == j0 ? yv[u] : (p0 + 32 * u + j < L ? (uint32_t)yn[p0 + 32 * u + (j - j0)] : 0u);
 #pragma unroll
                 for (int u = 0; u < MC_U; u++) {
-                    const uint64_t p = p0 + 32 * u;
-                    if (X[u] == 0 || p >= LW1 || (uint64_t)j > L - W - p) continue;     // j <= jmax = min(W-1, L-W-p), EM.cpp:167
+                    if (X[u] == 0 || p0 + 32 * u + (uint32_t)j > lim) continue;         // j <= jmax = min(W-1, L-W-p), EM.cpp:167
                     const uint32_t xlo = (uint32_t)X[u], xhi = (uint32_t)(X[u] >> 32);
                     const uint32_t bin = (uint32_t)(j - j0) * Yn + y[u];
                     const uint32_t old = atomicAdd(&lo_sh[bin], xlo);
-                    const uint32_t h = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
-                    if (h) atomicAdd(&mypart[bin], (unsigned long long)h << 32);
+                    const uint32_t hc = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
+                    if (hc) atomicAdd(&mypart[bin], (unsigned long long)hc << 32);
                 }
             }
+#pragma unroll
+            for (int u = 0; u < MC_U; u++) { rv[u] = rnx[u]; yv[u] = ynx[u]; }
         }
+        h = hn;
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
