@@ -4,7 +4,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from bammmotif2_b200 import capi, hostmodel
-A, K, Kbg = 6, 5, 2
+A, K, Kbg = 6, int(os.environ.get("K", 5)), 2
 nseq, L0 = int(os.environ.get("NSEQ", 100000)), 500
 rng = np.random.default_rng(3)
 fwd = rng.integers(1, A + 1, size=(nseq, L0), dtype=np.uint8)
@@ -33,6 +33,6 @@ for W in (12, 9, 13):
     em.iterate(2)
     em.iterate(5)
     it, e, m, u, tot = em.loop_timing()
-    print("A=6 K=5 W=%d  %d x %d bp: %.2f ms/iteration (E %.2f, M %.2f, update %.2f)  %.3e positions.iter/s" %
+    print("A=6 K=" + str(K) + " W=%d  %d x %d bp: %.2f ms/iteration (E %.2f, M %.2f, update %.2f)  %.3e positions.iter/s" %
           (W, nseq, L0, tot / it, e / it, m / it, u / it, nseq * L * it / (tot * 1e-3)))
     em.close()
