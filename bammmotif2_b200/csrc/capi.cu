@@ -237,6 +237,7 @@ struct bamm_em {
     float* d_s = nullptr;         // [j][y]
     float* d_sT = nullptr;        // the same table in the reference's [y][j] order (row gathers of the patched k-mers)
     float *d_s_alt = nullptr, *d_sT_alt = nullptr;   // second buffers, see d_tab_alt
+    float* d_rows = nullptr;      // index-array E-step with tables beyond shared memory: [y][W4] rows padded for 16-byte loads
     float* d_v = nullptr;         // all orders
     float* d_vK_prev = nullptr;
     float* d_n = nullptr;         // all orders (float, reference layout)

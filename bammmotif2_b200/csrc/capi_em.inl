@@ -36,7 +36,7 @@ extern "C" void bamm_em_destroy(bamm_em* em) {
     cudaFree(em->d_act); cudaFree(em->d_scale); cudaFree(em->d_act_cnt); cudaFree(em->d_overflow); cudaFree(em->d_reg_off);
     cudaFree(em->d_gen_ids); cudaFree(em->d_gen_roff); cudaFree(em->d_pk_ids); cudaFree(em->d_pk_roff); cudaFree(em->d_tab); cudaFree(em->d_tab_alt);
     cudaFree(em->d_btab); cudaFree(em->d_U); cudaFree(em->d_cand); cudaFree(em->d_cand_seq); cudaFree(em->d_seqacc); cudaFree(em->d_cand_part); cudaFree(em->d_mask_part); cudaFree(em->d_creg_off); cudaFree(em->d_eflags);
-    cudaFree(em->d_s_alt); cudaFree(em->d_sT_alt);
+    cudaFree(em->d_s_alt); cudaFree(em->d_sT_alt); cudaFree(em->d_rows);
     cudaFree(em->d_seq_ids); cudaFree(em->d_r_off); cudaFree(em->d_r); cudaFree(em->d_s); cudaFree(em->d_sT); cudaFree(em->d_v);
     cudaFree(em->d_vK_prev); cudaFree(em->d_n); cudaFree(em->d_vbg); cudaFree(em->d_alpha); cudaFree(em->d_part);
     if (em->own_xbuf) cudaFree(em->d_xbuf);
@@ -410,6 +410,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
             uint32_t nrep = getenv("BAMM_GEN_REPLICAS") ? (uint32_t)std::max(1, atoi(getenv("BAMM_GEN_REPLICAS"))) : 16u;
             while (nrep > 1 && (uint64_t)nrep * em->nbin * 8 > (128ull << 20)) nrep >>= 1;
             em->gen_nrep = em->nparts = nrep;
+            if (W <= 32 && !getenv("BAMM_GEN_NO_ROWS")) CUE(dev_malloc(&em->d_rows, (uint64_t)em->Yn * ((W + 3) & ~3) * sizeof(float)));
             // when a few columns of low words fit shared memory: column ranges x sequence shares (k_mstep_cols)
             const size_t col_bytes = (size_t)em->Yn * 4;
             if (col_bytes <= (size_t)max_optin && !getenv("BAMM_GEN_NO_COLS")) {
@@ -419,7 +420,9 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
                 const int ngroups = std::max(1, sms / em->gen_nsplit);
                 em->grid_m = ngroups * em->gen_nsplit;
                 em->smem_m = (size_t)em->gen_nc * col_bytes;
-                const bool ok = ia->bytes == 2 ? !max_smem_optin(k_mstep_cols<uint16_t>, em->smem_m) : !max_smem_optin(k_mstep_cols<uint32_t>, em->smem_m);
+                const bool one = em->gen_nc == 1;
+                const bool ok = ia->bytes == 2 ? !(one ? max_smem_optin(k_mstep_cols<uint16_t, true>, em->smem_m) : max_smem_optin(k_mstep_cols<uint16_t, false>, em->smem_m))
+                                               : !(one ? max_smem_optin(k_mstep_cols<uint32_t, true>, em->smem_m) : max_smem_optin(k_mstep_cols<uint32_t, false>, em->smem_m));
                 if (!ok) { fail(BAMM_E_CUDA, "cannot opt in to %zu bytes of shared memory", em->smem_m); bamm_em_destroy(em); return BAMM_E_CUDA; }
                 em->nparts = (uint32_t)ngroups;
             }
@@ -693,6 +696,22 @@ static PackedView pview_of(const bamm_em* em) {
     return pv;
 }
 
+// row-form E-step of the index-array path (kernels.cuh, k_estep_rows): pads the [y][j] table to rows of W4 floats, then one
+// instantiation per padded width
+template <typename YT>
+static void estep_rows_dispatch(bamm_em* em, const YT* Y, const SubsetView& sv, unsigned long long* scal) {
+    const int W4 = (em->W + 3) & ~3;
+    const uint32_t total = em->Yn * (uint32_t)W4, blocks = (total + 255) / 256;
+    k_pad_rows<<<blocks < 1184 ? blocks : 1184, 256, 0, em->stream>>>(em->d_sT, em->W, W4, em->Yn, em->d_rows);
+    em->launches += 1;
+#define BAMM_ROWS_CASE(N) case N: k_estep_rows<YT, N><<<em->grid_e, em->block, 0, em->stream>>>(Y, sv, em->W, em->d_rows, em->q, em->d_r, scal); break;
+    switch (W4) {
+        BAMM_ROWS_CASE(4) BAMM_ROWS_CASE(8) BAMM_ROWS_CASE(12) BAMM_ROWS_CASE(16) BAMM_ROWS_CASE(20) BAMM_ROWS_CASE(24) BAMM_ROWS_CASE(28) BAMM_ROWS_CASE(32)
+        default: break;
+    }
+#undef BAMM_ROWS_CASE
+}
+
 static int launch_estep(bamm_em* em, cudaEvent_t* split = nullptr /* 2 events: after the masked windows, after the bounds */) {
     em->launches += 1 + (em->npk ? em->gplans.size() + (em->sparse ? 3 : 0) : 0) + (em->ngen ? 1 : 0);
     unsigned long long* scal = em->d_xbuf + em->nbin;
@@ -742,7 +761,10 @@ static int launch_estep(bamm_em* em, cudaEvent_t* split = nullptr /* 2 events: a
     if (em->ngen) {
         IndexArray& ia = em->ss->index[em->K];
         SubsetView sv = view_of(em);
-        if (ia.bytes == 2) {
+        if (em->d_rows) {                       // tables beyond shared memory: whole rows per position, columns by shuffle
+            if (ia.bytes == 2) estep_rows_dispatch(em, (const uint16_t*)ia.d, sv, scal);
+            else               estep_rows_dispatch(em, (const uint32_t*)ia.d, sv, scal);
+        } else if (ia.bytes == 2) {
             if (em->smem_tables) k_estep<uint16_t, true><<<em->grid_e, em->block, em->smem_e, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_s, em->q, em->d_r, scal);
             else                 k_estep<uint16_t, false><<<em->grid_e, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_sT, em->q, em->d_r, scal);
         } else {
@@ -793,8 +815,10 @@ static int launch_mstep_accumulate(bamm_em* em) {
         IndexArray& ia = em->ss->index[em->K];
         SubsetView sv = view_of(em);
         if (em->gen_nsplit) {
-            if (ia.bytes == 2) k_mstep_cols<uint16_t><<<em->grid_m, 1024, em->smem_m, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, em->gen_nsplit, em->gen_nc);
-            else               k_mstep_cols<uint32_t><<<em->grid_m, 1024, em->smem_m, em->stream>>>((const uint32_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, em->gen_nsplit, em->gen_nc);
+#define BAMM_MCOLS(YT, ONE) k_mstep_cols<YT, ONE><<<em->grid_m, 1024, em->smem_m, em->stream>>>((const YT*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, em->gen_nsplit, em->gen_nc)
+            if (ia.bytes == 2) { if (em->gen_nc == 1) BAMM_MCOLS(uint16_t, true); else BAMM_MCOLS(uint16_t, false); }
+            else               { if (em->gen_nc == 1) BAMM_MCOLS(uint32_t, true); else BAMM_MCOLS(uint32_t, false); }
+#undef BAMM_MCOLS
         } else if (ia.bytes == 2) {
             if (em->smem_tables) k_mstep<uint16_t, true><<<em->grid_m, em->block, em->smem_m, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, 1u);
             else                 k_mstep<uint16_t, false><<<em->grid_m, em->block, 0, em->stream>>>((const uint16_t*)ia.d, sv, em->W, em->Yn, em->d_r, em->d_part, em->gen_nrep);

@@ -185,6 +185,96 @@ k_estep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// E-step for tables beyond shared memory, row form. The lanes of a warp own 32 consecutive POSITIONS: lane l loads the whole
+// table row of its k-mer, s[y(i)][0..W) — W4/4 16-byte loads from the padded [y][W4] copy of the table — and window p takes
+// column j from the lane that owns position p+j with one shuffle. A warp then touches 32 rows per 32 windows (3 load
+// instructions at W = 12) where k_estep<., false> issues W gathers of 32 scattered addresses each: the L1 wavefronts, which
+// bound that kernel (ncu: 92 % of the LSU wavefront peak), drop by W / (W4/4). Same factors multiplied in the same order =>
+// the same r, bit for bit. The rows of the next 32 positions and the k-mer indices of the 32 after them are in flight while
+// the current round is multiplied.
+__global__ void k_pad_rows(const float* __restrict__ sT /* [y][W] */, int W, int W4, uint32_t Yn, float* __restrict__ out /* [y][W4] */) {
+    const uint32_t total = Yn * (uint32_t)W4;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t y = i / W4, j = i % W4;
+        out[i] = j < (uint32_t)W ? sT[y * (uint32_t)W + j] : 1.0f;
+    }
+}
+template <typename YT, int W4>
+__global__ void __launch_bounds__(512)
+k_estep_rows(const YT* __restrict__ Y, SubsetView sv, int W, const float* __restrict__ rows /* [y][W4] */, float q,
+             float* __restrict__ r, unsigned long long* __restrict__ scal /* [0]=llh_fx, [1]=rsum_fx */) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    long long llh_fx = 0, rsum_fx = 0;
+    const float one_minus_q = 1.0f - q;
+    struct Hdr { uint64_t base, L, roff; };
+    auto load_hdr = [&](uint64_t i) {
+        Hdr h; h.base = 0; h.L = 0; h.roff = 0;
+        if (i < sv.nsub) {
+            const uint32_t n = sv.seq_ids ? sv.seq_ids[i] : (uint32_t)i;
+            h.base = sv.seq_off[n]; h.L = sv.seq_off[n + 1] - h.base; h.roff = sv.r_off[i];
+        }
+        return h;
+    };
+    auto load_row = [&](float (&dst)[W4], bool on, uint32_t y) {
+        const float4* __restrict__ src = reinterpret_cast<const float4*>(rows + (size_t)y * W4);
+#pragma unroll
+        for (int qd = 0; qd < W4 / 4; qd++) {
+            float4 v = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+            if (on) v = __ldg(src + qd);
+            dst[4 * qd] = v.x; dst[4 * qd + 1] = v.y; dst[4 * qd + 2] = v.z; dst[4 * qd + 3] = v.w;
+        }
+    };
+    Hdr hd = load_hdr(warp);
+    for (uint64_t i = warp; i < sv.nsub; i += nwarps) {
+        const Hdr hn = load_hdr(i + nwarps);
+        const uint32_t L = (uint32_t)hd.L, LW1 = L - W + 1;                      // stored lengths are below 2^32
+        const YT* __restrict__ yn = Y + hd.base;
+        float* __restrict__ rn = r + hd.roff;
+        hd = hn;
+        const float pos = q / (float)LW1;
+        float sum = 0.0f;
+        float cur[W4], nxt[W4];
+        load_row(cur, (uint32_t)lane < L, (uint32_t)lane < L ? (uint32_t)yn[lane] : 0u);
+        uint32_t y1 = 32u + lane < L ? (uint32_t)yn[32 + lane] : 0u;           // k-mer of this lane's position in the next round
+        for (uint32_t p0 = 0; p0 < LW1; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            load_row(nxt, p + 32 < L, y1);
+            y1 = p + 64 < L ? (uint32_t)yn[p + 64] : 0u;
+            const int jmax = (p < LW1) ? (int)min((uint32_t)(W - 1), L - W - p) : -1;
+            float prod = 1.0f;
+#pragma unroll
+            for (int j = 0; j < W4; j++) {
+                // position p+j belongs to lane (lane+j) mod 32 of this round if lane+j < 32, of the next round otherwise
+                if (j >= W) break;                                                   // padding columns (uniform)
+                const float v = __shfl_sync(FULL, lane >= j ? cur[j] : nxt[j], (lane + j) & 31);
+                if (j <= jmax) prod *= v;
+            }
+            if (p < LW1) {
+                const float val = prod * pos;
+                rn[L - W - p] = val;
+                sum += val;
+            }
+#pragma unroll
+            for (int j = 0; j < W4; j++) cur[j] = nxt[j];
+        }
+        sum = warp_sum(sum);
+        const float norm = one_minus_q + sum;
+        __syncwarp();
+        for (uint32_t k = lane; k < L; k += 32) rn[k] = (k < LW1) ? __fdiv_rn(rn[k], norm) : 0.0f;
+        if (lane == 0) {
+            llh_fx += __double2ll_rn((double)logf(norm) * SC_SCALE_D);
+            rsum_fx += __double2ll_rn((double)__fdiv_rn(sum, norm) * SC_SCALE_D);
+        }
+    }
+    if (lane == 0) {
+        if (llh_fx) atomicAdd(&scal[0], (unsigned long long)llh_fx);
+        if (rsum_fx) atomicAdd(&scal[1], (unsigned long long)rsum_fx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // M-step accumulation. reference: EM::MStep, src/refinement/EM.cpp:230-243, gather form:
 //   n[K][y(p+j)][j] += r[L-W-p]   for every window start p and j <= min(W-1, L-W-p).
 // Each r is converted ONCE to 2^40 fixed point (round to nearest) and added with native 32-bit integer shared
@@ -253,7 +343,7 @@ k_mstep(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float
 // words of columns [c nc, c nc + nc) in shared memory and adds into partial table g. r is read once per column range
 // (L2 / HBM streaming) instead of paying one 64-bit global atomic per window and column.
 constexpr int MC_U = 4;
-template <typename YT>
+template <typename YT, bool NC1 /* one column per CTA */>
 __global__ void __launch_bounds__(1024)
 k_mstep_cols(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const float* __restrict__ r,
              unsigned long long* __restrict__ part /* [gridDim.x / nsplit][W*Yn] */, int nsplit, int nc) {
@@ -306,18 +396,39 @@ k_mstep_cols(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const 
             unsigned long long X[MC_U];
 #pragma unroll
             for (int u = 0; u < MC_U; u++) X[u] = rv[u] > 0.0f ? __float2ull_rn(rv[u] * FX_SCALE_F) : 0ull;      // 0 for p >= LW1
-            for (int j = j0; j < j1; j++) {
-                uint32_t y[MC_U];
-#pragma unroll
-                for (int u = 0; u < MC_U; u++) y[u] = j == j0 ? yv[u] : (p0 + 32 * u + j < L ? (uint32_t)yn[p0 + 32 * u + (j - j0)] : 0u);
+            if (NC1) {
+                // one column per CTA (bin = k-mer): the low-word atomics of the round under predicates, then ONE branch for the
+                // rare rest — a carry out of the low word or a posterior >= 2^-8 (high word) goes to the global partial table
+                uint32_t hc[MC_U];
+                uint32_t any = 0u;
 #pragma unroll
                 for (int u = 0; u < MC_U; u++) {
-                    if (X[u] == 0 || p0 + 32 * u + (uint32_t)j > lim) continue;         // j <= jmax = min(W-1, L-W-p), EM.cpp:167
-                    const uint32_t xlo = (uint32_t)X[u], xhi = (uint32_t)(X[u] >> 32);
-                    const uint32_t bin = (uint32_t)(j - j0) * Yn + y[u];
-                    const uint32_t old = atomicAdd(&lo_sh[bin], xlo);
-                    const uint32_t hc = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
-                    if (hc) atomicAdd(&mypart[bin], (unsigned long long)hc << 32);
+                    const uint32_t xlo = (uint32_t)X[u];
+                    hc[u] = (uint32_t)(X[u] >> 32);
+                    if (X[u] != 0 && p0 + 32 * u + (uint32_t)j0 <= lim) {               // j0 <= jmax = min(W-1, L-W-p), EM.cpp:167
+                        const uint32_t old = atomicAdd(&lo_sh[yv[u]], xlo);
+                        hc[u] += (uint32_t)(old + xlo) < old ? 1u : 0u;
+                    } else hc[u] = 0u;
+                    any |= hc[u];
+                }
+                if (any) {
+#pragma unroll
+                    for (int u = 0; u < MC_U; u++) if (hc[u]) atomicAdd(&mypart[yv[u]], (unsigned long long)hc[u] << 32);
+                }
+            } else {
+                for (int j = j0; j < j1; j++) {
+                    uint32_t y[MC_U];
+#pragma unroll
+                    for (int u = 0; u < MC_U; u++) y[u] = j == j0 ? yv[u] : (p0 + 32 * u + j < L ? (uint32_t)yn[p0 + 32 * u + (j - j0)] : 0u);
+#pragma unroll
+                    for (int u = 0; u < MC_U; u++) {
+                        if (X[u] == 0 || p0 + 32 * u + (uint32_t)j > lim) continue;     // j <= jmax = min(W-1, L-W-p), EM.cpp:167
+                        const uint32_t xlo = (uint32_t)X[u], xhi = (uint32_t)(X[u] >> 32);
+                        const uint32_t bin = (uint32_t)(j - j0) * Yn + y[u];
+                        const uint32_t old = atomicAdd(&lo_sh[bin], xlo);
+                        const uint32_t hc = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
+                        if (hc) atomicAdd(&mypart[bin], (unsigned long long)hc << 32);
+                    }
                 }
             }
 #pragma unroll
