@@ -418,6 +418,11 @@ def run_c5(args, wl):
     wall = time.perf_counter() - t0
     if p.returncode != 0:
         raise SystemExit("CLI failed: %s" % p.stderr[-500:])
+    stages = {}
+    for l in p.stderr.splitlines():                 # BAMM_TRACE lines of the driver: wall time per stage (summed when a stage repeats)
+        if l.startswith("[bamm host] ") and l.rstrip().endswith(" ms") and "FASTA reader" not in l:
+            t = l[len("[bamm host] "):].rsplit(" ", 2)
+            stages[t[0]] = stages.get(t[0], 0.0) + float(t[1])
     iters = sum(1 for l in p.stdout.splitlines() if " iter, llh=" in l)
     em_s = sum(float(l.split("Runtime for EM:")[1].split("seconds")[0]) for l in p.stdout.splitlines() if "Runtime for EM:" in l)
     import shutil
@@ -427,7 +432,7 @@ def run_c5(args, wl):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": iters, "warmup": 0, "ms_per_step": em_s / max(iters, 1) * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "nseq": nseq, "L0": wl["L0"], "K": wl["K"], "K_bg": wl["K_bg"], "alphabet": "EXTENDED (A=6)", "motifs": nmotif,
-                       "em_iterations_all_motifs": iters, "em_seconds": em_s, "wall_s": wall, "seed": args.seed,
+                       "em_iterations_all_motifs": iters, "stages_ms": stages or None, "em_seconds": em_s, "wall_s": wall, "seed": args.seed,
                        "positions_iter_per_s": nseq * (2 * wl["L0"] + 1) * iters / em_s if em_s > 0 else 0.0,
                        "step": "one EM iteration of one motif (EM::optimize until the reference's stop rule, six motifs one after the other)"},
             "e2e": {"value": bp * iters / wall, "unit": UNIT, "h2d_bytes_per_step": int(nseq * (2 * wl["L0"] + 1) / max(iters, 1)) if not ref else 0,
