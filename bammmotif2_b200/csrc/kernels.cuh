@@ -370,6 +370,7 @@ k_mstep_cols(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const 
         return h;
     };
     const uint64_t first = (uint64_t)g * wpc + (threadIdx.x >> 5), stride = (uint64_t)ngroups * wpc;
+    const uint32_t lo_base = (uint32_t)__cvta_generic_to_shared(lo_sh);
     Hdr h = load_hdr(first);
     for (uint64_t i = first; i < sv.nsub; i += stride) {
         const Hdr hn = load_hdr(i + stride);
@@ -405,10 +406,12 @@ k_mstep_cols(const YT* __restrict__ Y, SubsetView sv, int W, uint32_t Yn, const 
                 for (int u = 0; u < MC_U; u++) {
                     const uint32_t xlo = (uint32_t)X[u];
                     hc[u] = (uint32_t)(X[u] >> 32);
-                    if (X[u] != 0 && p0 + 32 * u + (uint32_t)j0 <= lim) {               // j0 <= jmax = min(W-1, L-W-p), EM.cpp:167
-                        const uint32_t old = atomicAdd(&lo_sh[yv[u]], xlo);
-                        hc[u] += (uint32_t)(old + xlo) < old ? 1u : 0u;
-                    } else hc[u] = 0u;
+                    const bool on = X[u] != 0 && p0 + 32 * u + (uint32_t)j0 <= lim;     // j0 <= jmax = min(W-1, L-W-p), EM.cpp:167
+                    // predicated shared-memory atomic: no branch region per window
+                    uint32_t old = 0u;
+                    asm volatile("{ .reg .pred p; setp.ne.u32 p, %3, 0; @p atom.shared.add.u32 %0, [%1], %2; }"
+                                 : "+r"(old) : "r"(lo_base + (yv[u] << 2)), "r"(xlo), "r"((uint32_t)on) : "memory");
+                    hc[u] = on ? hc[u] + ((uint32_t)(old + xlo) < old ? 1u : 0u) : 0u;
                     any |= hc[u];
                 }
                 if (any) {
