@@ -585,6 +585,29 @@ def run_c4(args, wl):
     return 0
 
 
+def bind_near_gpu(torch, local_rank):
+    """N > 1: run this rank's host thread on the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned input buffers are
+    allocated (first touch puts their pages on that node), so that eight concurrent 1.2 GB uploads do not all cross the socket
+    link. Returns the node, or None when the topology is not visible (single node, container without /sys, no permission)."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     args = parse_args()
     wl = dict(synth.WORKLOADS[args.workload], name=args.workload)
@@ -617,6 +640,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    numa = bind_near_gpu(torch, local_rank) if world > 1 and not os.environ.get("BAMM_BENCH_NO_NUMA") else None
 
     nseq = args.nseq or wl["nseq"]
     A = 4
@@ -861,7 +885,8 @@ def main():
                        "positions_per_gpu": pos_local, "positions_iter_per_s": pos_local * world * args.steps / (ms_total * 1e-3),
                        "l2": "inputs (%.1f GB index + r per GPU) exceed the 126 MB L2" % (6.0 * pos_local / 1e9) if 6.0 * pos_local > 2.0e8
                              else "inputs fit in L2; no flush between iterations (EM iterates over resident data)",
-                       "parallelism": "sequence shards, dp%d" % world, "exchange": exchange},
+                       "parallelism": "sequence shards, dp%d" % world, "exchange": exchange,
+                       **({"host_numa_node_rank0": numa} if world > 1 else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         }
         if roof:
