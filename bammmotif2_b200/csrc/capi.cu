@@ -200,7 +200,7 @@ struct bamm_em {
     float* d_cand_part = nullptr;    // column passes: partial product per candidate slot (k_eexact)
     float* d_mask_part = nullptr;    // column passes: partial product per masked window of every sequence (k_emasked)
     ulonglong2* d_seqacc = nullptr;  // per list sequence: normaliser terms of its masked windows (k_emasked -> k_eexact)
-    uint32_t* d_eflags = nullptr;   // CandList::flags (4 words)
+    uint32_t* d_eflags = nullptr;   // CandList::flags (8 words)
     bool r_mat = true;          // d_r holds the posteriors of the last E-step (false after a pruned E-step until bamm_em_get_r)
     const float *d_s_e = nullptr, *d_sT_e = nullptr, *d_tab_e = nullptr;   // the tables the last E-step read
     float q_e = 0.3f;           // ... and its prior

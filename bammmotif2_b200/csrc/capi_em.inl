@@ -531,8 +531,8 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
                     CUE(dev_malloc(&em->d_cand_seq, (size_t)em->npk * sizeof(uint2)));
                     CUE(dev_malloc(&em->d_seqacc, (size_t)em->npk * sizeof(ulonglong2)));
                     CUE(upload(creg.data(), creg.size() * 8, (void**)&em->d_creg_off));
-                    CUE(dev_malloc(&em->d_eflags, 16));
-                    CUE(cudaMemset(em->d_eflags, 0, 16));
+                    CUE(dev_malloc(&em->d_eflags, 32));
+                    CUE(cudaMemset(em->d_eflags, 0, 32));
                     em->cand_ok = true;
                 } else cudaGetLastError();
             }

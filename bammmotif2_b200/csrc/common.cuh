@@ -114,8 +114,12 @@ struct CandList {
     uint2* seq;               // [nlist] (first entry inside the region, count) of every list sequence
     uint32_t* flags;          // [0] != 0: this iteration runs the dense E-step (a region overflowed, or the hold below is active)
                               // [1] iterations the dense E-step stays switched on after an overflow; [2..3] 64-bit candidate count (diagnostics)
+                              // [4] length of the current hold; [5] != 0: a region overflowed in the last E-step (k_estep_begin turns it into a hold)
 };
-constexpr uint32_t DENSE_HOLD = 8;
+// After an overflow the dense E-step runs for 2 iterations, then the bound pass tries again; every further overflow in a row
+// doubles the hold (a model whose posteriors stay diffuse pays log2(iterations) wasted bound passes, one that sharpens after
+// the first iterations is back on the pruned path at once); a pruned iteration that fits resets it.
+constexpr uint32_t DENSE_HOLD_MIN = 2, DENSE_HOLD_MAX = 64;
 
 struct MTables { uint32_t nrep, rstride; };      // packed M-step: table copies per CTA and their stride in words (rstride >= NC * Yn)
 

@@ -423,7 +423,7 @@ k_ebound(PackedView pv, const __grid_constant__ GroupPlan gp, const float* __res
             t0 = u0; t1 = u1; t2 = u2;
         }
     }
-    if (!ok && lane == 0) { flags[1] = DENSE_HOLD; __threadfence(); flags[0] = 1u; }
+    if (!ok && lane == 0) { flags[5] = 1u; __threadfence(); flags[0] = 1u; }
     if (lane == 0 && cpos) atomicAdd(reinterpret_cast<unsigned long long*>(cl.flags + 2), (unsigned long long)cpos);
 }
 

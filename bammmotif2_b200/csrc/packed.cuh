@@ -257,7 +257,12 @@ __global__ void k_estep_begin(unsigned long long* __restrict__ scal, uint32_t* _
         scal[0] = 0ull; scal[1] = 0ull;
         if (overflow) *overflow = 0u;
         if (eflags) {
-            const uint32_t hold = eflags[1];
+            uint32_t hold = eflags[1];
+            if (eflags[5]) {                                      // the last E-step ran over its candidate cap
+                const uint32_t len = eflags[4] ? min(2u * eflags[4], DENSE_HOLD_MAX) : DENSE_HOLD_MIN;
+                eflags[4] = len; eflags[5] = 0u;
+                hold = len;
+            } else if (eflags[0] == 0u) eflags[4] = 0u;           // a pruned E-step that fit: the next overflow starts at the short hold
             eflags[0] = hold ? 1u : 0u;
             eflags[1] = hold ? hold - 1u : 0u;
             eflags[2] = 0u; eflags[3] = 0u;
