@@ -220,7 +220,7 @@ struct bamm_em {
     unsigned int* d_peer_done = nullptr;
     unsigned long long* d_peer_wait = nullptr;  // [0] ns spent waiting for the other ranks in k_peer_sum, [1] number of waits
     int m_nc = 0, m_nsplit = 1; // packed M-step: columns per CTA and number of column splits (packed.cuh, "column split")
-    MTables m_tab = {1, 0};     // table copies per CTA (orders 0 and 1) and their stride in words
+    MTables m_tab = {1, 0, 0};  // table copies per CTA (orders 0 and 1), their stride in words, high words in global memory
     int grid_pl = 0;            // CTAs of the packed M-step kernels (a multiple of m_nsplit)
     uint32_t *d_act_cnt = nullptr, *d_overflow = nullptr;
     uint64_t* d_reg_off = nullptr;

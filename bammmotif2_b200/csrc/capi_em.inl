@@ -436,6 +436,14 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
         // M-step geometry: as many columns per CTA as two 32-bit tables allow, the fewest splits, columns spread evenly
         {
             int nc_max = std::min(32 - K, (int)((size_t)max_optin / ((size_t)em->Yn * 8)));   // K + columns <= 32 bases of one window word
+            // without the high-word table in shared memory twice the columns fit: taken when it saves a pass over the windows
+            // (orders >= 5 at W = 20: 3 -> 2 column splits; order 6: 20 -> 7)
+            const int nc_hg = std::min(32 - K, (int)((size_t)max_optin / ((size_t)em->Yn * 4)));
+            em->m_tab.hi_global = 0;
+            if (nc_max >= 1 && nc_hg >= 1 && nc_hg <= 14 && !getenv("BAMM_M_NO_HI_GLOBAL") &&       // 14: the instantiated widths (launch_mstep.cu)
+                (W + std::min(nc_hg, W) - 1) / std::min(nc_hg, W) < (W + std::min(nc_max, W) - 1) / std::min(nc_max, W)) {
+                nc_max = nc_hg; em->m_tab.hi_global = 1;
+            }
             if (getenv("BAMM_M_COLS")) nc_max = std::max(1, std::min(nc_max, atoi(getenv("BAMM_M_COLS"))));
             if (nc_max > W) nc_max = W;
             em->m_nsplit = (W + nc_max - 1) / nc_max;
@@ -448,6 +456,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
                 if (getenv("BAMM_M_REPLICAS")) nrep = (uint32_t)std::max(1, atoi(getenv("BAMM_M_REPLICAS")));
                 while (nrep & (nrep - 1)) nrep &= nrep - 1;                 // power of two
                 while (nrep > 1 && (size_t)2 * nrep * (((nb + 30) / 32) * 32 + 1) * 4 > (size_t)max_optin) nrep >>= 1;
+                if (em->m_tab.hi_global) nrep = 1;
                 em->m_tab.nrep = nrep;
                 em->m_tab.rstride = nrep > 1 ? ((nb + 30) / 32) * 32 + 1 : nb;
             }
@@ -779,7 +788,7 @@ static int launch_estep(bamm_em* em, cudaEvent_t* split = nullptr /* 2 events: a
 // packed M-step kernels (launch_mstep.cu). mode 0: opt in to the shared memory of both kernels, 1: launch the list kernel,
 // 2: launch the scan kernel (conditional on the list's overflow flag when there is a list)
 static int mstep_w_dispatch(bamm_em* em, const PackedView* pv, const Plan* pl, int mode) {
-    const size_t smem = (size_t)2 * em->m_tab.nrep * em->m_tab.rstride * 4;
+    const size_t smem = (size_t)(em->m_tab.hi_global ? 1 : 2) * em->m_tab.nrep * em->m_tab.rstride * 4;
     const ActiveList al = alist_of(em);
     return launch_mstep_packed(em->m_nc, mode, em->grid_pl, smem, em->stream, pv, pl, &al, em->nregions, em->m_nsplit, em->m_tab, em->d_part,
                                em->d_r, em->r_scaled ? nullptr : em->d_scale, em->d_act ? em->d_overflow : nullptr);

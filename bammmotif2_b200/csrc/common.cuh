@@ -121,7 +121,10 @@ struct CandList {
 // the first iterations is back on the pruned path at once); a pruned iteration that fits resets it.
 constexpr uint32_t DENSE_HOLD_MIN = 2, DENSE_HOLD_MAX = 64;
 
-struct MTables { uint32_t nrep, rstride; };      // packed M-step: table copies per CTA and their stride in words (rstride >= NC * Yn)
+struct MTables {                                  // packed M-step
+    uint32_t nrep, rstride;                       // table copies per CTA and their stride in words (rstride >= NC * Yn)
+    uint32_t hi_global;                           // != 0: no high-word table in shared memory (twice the columns per CTA): the rare
+};                                                // high parts / carries go to the CTA's 64-bit partial table with global atomics
 
 // ---- table staging: global -> shared memory with the TMA (1-D bulk copies, no tensor map) --------------------------
 // Thread 0 arms an mbarrier with the byte count and issues cp.async.bulk copies of up to 64 KB; every thread of the CTA then

@@ -32,11 +32,28 @@ __device__ __forceinline__ uint32_t atoms_add_ret(uint32_t addr, uint32_t x) {
 __device__ __forceinline__ void reds_add(uint32_t addr, uint32_t h) {
     asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(h) : "memory");
 }
+// Where the high parts go: the CTA's second shared-memory table (ghi == nullptr), or — when that table is given up so that twice
+// the columns fit one CTA (orders >= 5: fewer passes over the list) — the CTA's 64-bit partial table in global memory, whose
+// bins [j0 Yn, ...) mirror the shared low-word table (one copy: nrep = 1 there). Rare either way: posteriors >= 2^-8 and the
+// wrap-arounds of a low word.
+// HG is a template parameter of the kernels: the variant with the shared-memory table carries no pointer (it runs at the
+// register limit of 1024 threads per CTA).
+template <bool HG> struct HiDst;
+template <> struct HiDst<false> { __device__ __forceinline__ void set(unsigned long long*, uint32_t) {} };
+template <> struct HiDst<true> {
+    unsigned long long* ghi; uint32_t lo_s;
+    __device__ __forceinline__ void set(unsigned long long* g, uint32_t l) { ghi = g; lo_s = l; }
+};
+__device__ __forceinline__ void hi_add(uint32_t addr, uint32_t hioff, uint32_t h, const HiDst<false>&) { reds_add(addr + hioff, h); }
+__device__ __forceinline__ void hi_add(uint32_t addr, uint32_t, uint32_t h, const HiDst<true>& hd) {
+    atomicAdd(hd.ghi + ((addr - hd.lo_s) >> 2), (unsigned long long)h << 32);
+}
 // guarded single step for the slow paths (windows over the N, truncated windows)
-__device__ __forceinline__ void atoms_add_carry(uint32_t addr, uint32_t hioff, uint32_t xlo, uint32_t xhi) {
+template <bool HG>
+__device__ __forceinline__ void atoms_add_carry(uint32_t addr, uint32_t hioff, uint32_t xlo, uint32_t xhi, const HiDst<HG>& hd) {
     const uint32_t old = atoms_add_ret(addr, xlo);
     const uint32_t h = xhi + ((uint32_t)(old + xlo) < old ? 1u : 0u);
-    if (h) reds_add(addr + hioff, h);
+    if (h) hi_add(addr, hioff, h, hd);
 }
 
 // the NC columns of one window, fully unrolled: `up` holds the window's bases right-aligned so that column j0+jj's k-mer
@@ -45,9 +62,9 @@ __device__ __forceinline__ void atoms_add_carry(uint32_t addr, uint32_t hioff, u
 // Batches of M_BATCH columns: first the low-word atomics of the batch, then the carries / high parts from the returned
 // values, so several atomics of a lane are in flight.
 constexpr int M_BATCH = 8;
-template <int NC, bool MASKED>
+template <int NC, bool MASKED, bool HG>
 __device__ __forceinline__ void scatter_cols(unsigned long long up, uint32_t maskK, uint32_t lo_s, uint32_t hi_off, uint32_t yn4,
-                                             uint32_t xlo, uint32_t xhi, int jrel_max, int jmax_u = 31 /* warp-uniform bound of jrel_max */) {
+                                             uint32_t xlo, uint32_t xhi, const HiDst<HG>& hd, int jrel_max, int jmax_u = 31 /* warp-uniform bound of jrel_max */) {
     const uint32_t ulo = (uint32_t)up, uhi = (uint32_t)(up >> 32);
     const bool hi_nz = xhi != 0u;
 #pragma unroll
@@ -69,7 +86,7 @@ __device__ __forceinline__ void scatter_cols(unsigned long long up, uint32_t mas
             if (jj < NC && (!MASKED || jj <= jmax_u)) {
                 const bool on = !MASKED || jj <= jrel_max;
                 const bool carry = on && (uint32_t)~old[k] < xlo;          // old + xlo wrapped
-                if (carry || (on && hi_nz)) reds_add(adr[k] + hi_off, xhi + (carry ? 1u : 0u));
+                if (carry || (on && hi_nz)) hi_add(adr[k], hi_off, xhi + (carry ? 1u : 0u), hd);
             }
         }
     }
@@ -77,8 +94,9 @@ __device__ __forceinline__ void scatter_cols(unsigned long long up, uint32_t mas
 
 // slow path, one window per lane with a run-time column loop: windows over the N, whose k-mers at positions mid..mid+K
 // hold rand() draws (Sequence.cpp:38) and come from the patch list, and the truncated last W-1 windows (EM.cpp:236)
+template <bool HG>
 __device__ __forceinline__ void scatter_window_slow(const SeqCtx& sc, const Plan& pl, uint32_t lo_s, uint32_t hi_off, int j0, int nc,
-                                                    int p, unsigned long long X) {
+                                                    int p, unsigned long long X, const HiDst<HG>& hd) {
     if (X == 0) return;
     const int W = pl.W, K = pl.K;
     const unsigned long long w = window_word(sc.wd, p + j0 - K); // bases p+j0-K .. p+j0-K+31
@@ -89,7 +107,7 @@ __device__ __forceinline__ void scatter_window_slow(const SeqCtx& sc, const Plan
         uint32_t y = field(w, 62 - 2 * K - 2 * (j - j0), maskK);
         const int d = p + j - sc.mid;
         if (sc.mid >= 0 && d >= 0 && d <= K) y = sc.yp[d];
-        atoms_add_carry(lo_s + (((uint32_t)(j - j0) * pl.Yn + y) << 2), hi_off, xlo, xhi);
+        atoms_add_carry(lo_s + (((uint32_t)(j - j0) * pl.Yn + y) << 2), hi_off, xlo, xhi, hd);
     }
 }
 
@@ -97,27 +115,33 @@ __device__ __forceinline__ void scatter_window_slow(const SeqCtx& sc, const Plan
 // Replicas: for tiny tables (orders 0 and 1: 4 or 16 bins per column) most lanes of a warp hit the same few addresses and
 // the atomics serialise; the CTA then keeps nrep copies of both tables (lane l uses copy l % nrep, copies rstride words
 // apart with rstride = 1 mod 32 so that equal bins of different copies fall into different banks) and sums them here.
+template <bool HG>
 __device__ __forceinline__ void flush_cols(const uint32_t* lo_sh, MTables mt, uint32_t nb, uint32_t Yn, int j0, int W,
                                            unsigned long long* __restrict__ mypart) {
     const uint32_t* hi_sh = lo_sh + mt.nrep * mt.rstride;
     const uint32_t lim = (uint32_t)max(0, min((int)(nb / Yn), W - j0)) * Yn;
     for (uint32_t i = threadIdx.x; i < lim; i += blockDim.x) {
-        unsigned long long lo = 0, hi = 0;
-        for (uint32_t rp = 0; rp < mt.nrep; rp++) { lo += lo_sh[rp * mt.rstride + i]; hi += hi_sh[rp * mt.rstride + i]; }
-        const unsigned long long v = lo + (hi << 32);
-        if (v) mypart[(uint32_t)j0 * Yn + i] = v;
+        if (HG) {                                         // the high parts are in mypart already (global atomics of this CTA)
+            const uint32_t lo = lo_sh[i];
+            if (lo) atomicAdd(&mypart[(uint32_t)j0 * Yn + i], (unsigned long long)lo);
+        } else {
+            unsigned long long lo = 0, hi = 0;
+            for (uint32_t rp = 0; rp < mt.nrep; rp++) { lo += lo_sh[rp * mt.rstride + i]; hi += hi_sh[rp * mt.rstride + i]; }
+            const unsigned long long v = lo + (hi << 32);
+            if (v) mypart[(uint32_t)j0 * Yn + i] = v;
+        }
     }
 }
 
 // M-step from the E-step's active list: every lane scatters one listed window.
-template <int NC>
+template <int NC, bool HG>
 __global__ void __launch_bounds__(1024, 1)
 k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsplit, MTables mt, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
     extern __shared__ uint32_t smem_u32[];
     if (*al.overflow != 0u) return;                                        // k_mstep_scan_w scans r instead
     const uint32_t nb = (uint32_t)NC * pl.Yn;
     uint32_t* lo_sh = smem_u32;
-    for (uint32_t i = threadIdx.x; i < 2 * mt.nrep * mt.rstride; i += blockDim.x) smem_u32[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < (HG ? 1u : 2u) * mt.nrep * mt.rstride; i += blockDim.x) smem_u32[i] = 0u;
     __syncthreads();
     const int split = (int)(blockIdx.x % (uint32_t)nsplit), j0 = split * NC;
     const int lane = threadIdx.x & 31;
@@ -128,6 +152,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
     const int ralign = 62 - 2 * (K + NC - 1);                              // word = bases p+j0-K ..: column j0+NC-1's last base lowest
     const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh) + ((uint32_t)lane & (mt.nrep - 1u)) * mt.rstride * 4u;   // this lane's copy
     const uint32_t hi_off = mt.nrep * mt.rstride * 4u, yn4 = pl.Yn * 4u;
+    HiDst<HG> hd; hd.set(part + (uint64_t)blockIdx.x * ((uint64_t)pl.W * pl.Yn) + (uint64_t)j0 * pl.Yn, lo_s);
     const int nc_valid = min(NC, W - j0);
     const bool split_full = nc_valid == NC;                                // CTA-uniform
     const uint4 none = make_uint4(0u, 0u, 0u, 0u);
@@ -149,8 +174,8 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
                 X = __float2ull_rn(rv * FX_SCALE_F);
                 up = window_word(pv.words + raw.x, (int)(raw.y & ACT_P_MASK) + j0 - K) >> ralign;
             }
-            if (split_full) scatter_cols<NC, false>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), 0);
-            else scatter_cols<NC, true>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), on ? nc_valid - 1 : -1);
+            if (split_full) scatter_cols<NC, false, HG>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), hd, 0);
+            else scatter_cols<NC, true, HG>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), hd, on ? nc_valid - 1 : -1);
         }
         // back of the region (filled downwards): windows of the E-step's masked evaluation — truncated tail windows, windows
         // over the N, and the full windows that share their chunks
@@ -170,7 +195,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
                     const uint32_t n = pv.seq_ids[raw.w];
                     const PackedSeq sq = pv.seqs[n];
                     SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = (int)sq.L; sc.mid = (int)sq.mid;
-                    scatter_window_slow(sc, pl, lo_s, hi_off, j0, NC, p, X);
+                    scatter_window_slow(sc, pl, lo_s, hi_off, j0, NC, p, X, hd);
                     X = 0ull;
                 } else {
                     up = window_word(pv.words + raw.x, p + j0 - K) >> ralign;
@@ -179,18 +204,18 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
             }
             __syncwarp();
             // the truncated windows arrive sorted by their last column (k_emasked lists them window index by window index)
-            scatter_cols<NC, true>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), jrel_max, __reduce_max_sync(FULL, jrel_max));
+            scatter_cols<NC, true, HG>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), hd, jrel_max, __reduce_max_sync(FULL, jrel_max));
         }
     }
     __syncthreads();
-    flush_cols(lo_sh, mt, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
+    flush_cols<HG>(lo_sh, mt, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
 }
 
 // M-step from r itself: one warp per sequence, lanes = 32 consecutive window starts, the packed stream is followed with the
 // E-step's rolling three-word fetch. Chunks without a surviving posterior are skipped after one vote.
 // only_if: nullptr, or a device flag — the kernel runs only when it is non-zero (active list overflowed).
 // scale: nullptr when r is already normalised, else 1/normaliser per list sequence.
-template <int NC>
+template <int NC, bool HG>
 __global__ void __launch_bounds__(1024, 1)
 k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float* __restrict__ scale, const uint32_t* __restrict__ only_if,
                int nsplit, MTables mt, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
@@ -198,7 +223,7 @@ k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float*
     if (only_if != nullptr && *only_if == 0u) return;                      // k_mstep_list_w did the work
     const uint32_t nb = (uint32_t)NC * pl.Yn;
     uint32_t* lo_sh = smem_u32;
-    for (uint32_t i = threadIdx.x; i < 2 * mt.nrep * mt.rstride; i += blockDim.x) smem_u32[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < (HG ? 1u : 2u) * mt.nrep * mt.rstride; i += blockDim.x) smem_u32[i] = 0u;
     __syncthreads();
     const int split = (int)(blockIdx.x % (uint32_t)nsplit), j0 = split * NC;
     const int lane = threadIdx.x & 31;
@@ -209,6 +234,7 @@ k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float*
     const int ralign = 62 - 2 * (K + NC - 1);
     const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh) + ((uint32_t)lane & (mt.nrep - 1u)) * mt.rstride * 4u;   // this lane's copy
     const uint32_t hi_off = mt.nrep * mt.rstride * 4u, yn4 = pl.Yn * 4u;
+    HiDst<HG> hd; hd.set(part + (uint64_t)blockIdx.x * ((uint64_t)pl.W * pl.Yn) + (uint64_t)j0 * pl.Yn, lo_s);
     const int nc_valid = min(NC, W - j0);
     const bool split_full = nc_valid == NC;                                // CTA-uniform
     const int lane_word = (lane + j0 - K) >> 4;                            // this lane's words start at bases lane+j0-K + 32*chunk
@@ -240,18 +266,18 @@ k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float*
             if ((c >= cn0 && c <= cn1) || c >= ctail || !split_full) {     // windows over the N / truncated windows / partial split
                 if (mid >= 0 && p <= mid + K && p + W - 1 >= mid) {
                     SeqCtx sc; sc.wd = pv.words + sq.word_off; sc.yp = pv.ypatch + (uint64_t)n * (K + 1); sc.L = L; sc.mid = mid;
-                    scatter_window_slow(sc, pl, lo_s, hi_off, j0, NC, p, X);
+                    scatter_window_slow(sc, pl, lo_s, hi_off, j0, NC, p, X, hd);
                     X = 0ull;
                 }
                 __syncwarp();
-                scatter_cols<NC, true>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), min(min(W - 1, L - W - p) - j0, nc_valid - 1));
+                scatter_cols<NC, true, HG>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), hd, min(min(W - 1, L - W - p) - j0, nc_valid - 1));
             } else {
-                scatter_cols<NC, false>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), 0);
+                scatter_cols<NC, false, HG>(up, maskK, lo_s, hi_off, yn4, (uint32_t)X, (uint32_t)(X >> 32), hd, 0);
             }
         }
     }
     __syncthreads();
-    flush_cols(lo_sh, mt, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
+    flush_cols<HG>(lo_sh, mt, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
 }
 
 }  // namespace bamm
