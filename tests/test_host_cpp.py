@@ -221,6 +221,70 @@ def test_negative_sampling_device_path_bit_exact(bins, tmp_path):
     assert np.array_equal(np.fromfile(tmp_path / "neg_offsets.u64", np.uint64), g["neg_offsets"])
 
 
+def _pr_walk_restated(pos, neg, posN, negN, q):
+    """FDR::calculatePR's ZOOPS walk (reference: src/evaluation/FDR.cpp:196-262) restated with binary searches per entry, the way the
+    reference finds the neighbours of a score among the negatives; libc supplies the tie-breaks."""
+    import bisect, ctypes, math
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(42)
+    f32 = np.float32
+    pos = np.sort(pos)[::-1].astype(f32); neg = np.sort(neg)[::-1].astype(f32)
+    negasc = (-neg).tolist()                                   # ascending keys for bisect on a descending vector
+    mfold = f32(negN) / f32(posN)
+    n_top = int(min(100, negN // 10))
+    lam = f32(1e-16)
+    for l in range(n_top):
+        lam = f32(lam + f32(neg[l] - neg[n_top]))
+    lam = f32(lam / f32(n_top))
+    ip = ineg = 0
+    TP, FP, PV = [], [], []
+    nan = float("nan")
+    for i in range(posN + negN):
+        ps = float(pos[ip]) if ip < len(pos) else nan
+        ns = float(neg[ineg]) if ineg < len(neg) else nan
+        if (ps > ns or ip == 0 or ineg == negN) and ip < posN:
+            Sl = ps; ip += 1
+        elif ps == ns and libc.rand() % 2 == 0 and ip < posN:
+            Sl = ps; ip += 1
+        else:
+            Sl = ns; ineg += 1
+        tp = f32(ip); fp = f32(f32(ineg) / mfold)
+        TP.append(tp); FP.append(fp)
+        if Sl <= float(neg[n_top]):
+            lb = bisect.bisect_left(negasc, -Sl)               # first negative that is not above Sl
+            ub = bisect.bisect_right(negasc, -Sl)              # first negative below Sl
+            up = float(neg[lb - 1]) if lb > 0 else float(neg[0])
+            lo = float(neg[ub]) if ub < len(neg) else Sl
+            pv = (ineg + float(f32(up - Sl)) / (float(f32(up - lo)) + 1e-5)) / float(f32(negN))
+        else:
+            pv = float(f32(f32(n_top) * f32(math.exp(float(f32(f32(neg[n_top] - f32(Sl)) / lam))))) / f32(negN))
+        PV.append(pv)
+    return np.array(TP, f32), np.array(FP, f32), np.array(PV, np.float64)
+
+
+@pytest.mark.parametrize("seed,ties", [(1, False), (2, True), (3, True)])
+def test_pr_walk_against_a_restatement_with_binary_searches(bins, seed, ties, tmp_path):
+    """host/FDR.cpp advances the two neighbours of a score among the sorted negatives with the walk instead of searching them per
+    entry: same TP / FP and the same rank p-values as a restatement that searches (scores quantised so that ties inside and between
+    the sets are frequent; a first positive below the top negatives, which makes the walk's score go UP once)."""
+    rng = np.random.default_rng(seed)
+    posN, negN = 400, 4000
+    pos = rng.normal(1.0, 2.0, posN).astype(np.float32)
+    neg = rng.normal(0.0, 1.5, negN).astype(np.float32)
+    if ties:
+        pos = np.round(pos * 4) / np.float32(4); neg = np.round(neg * 4) / np.float32(4)
+    if seed == 3:
+        pos = pos - np.float32(6.0)                             # every positive below the 100 best negatives: rank branch, then upwards
+    pos.tofile(tmp_path / "pos.f32"); neg.tofile(tmp_path / "neg.f32")
+    run([os.path.join(bins, "host_check"), "pr", str(posN), str(negN), "0.9", str(tmp_path / "pos.f32"), str(tmp_path / "neg.f32"), str(tmp_path)])
+    TP, FP, PV = _pr_walk_restated(pos, neg, posN, negN, 0.9)
+    assert np.array_equal(np.fromfile(tmp_path / "TP.f32", np.float32), TP)
+    assert np.array_equal(np.fromfile(tmp_path / "FP.f32", np.float32), FP)
+    got = np.fromfile(tmp_path / "PNpval.f32", np.float32).astype(np.float64)
+    # the exponential tail goes through expf (last-bit differences against math.exp); the rank branch is plain arithmetic
+    assert np.allclose(got, PV, rtol=2e-6, atol=1e-9), np.abs(got - PV).max()
+
+
 @pytest.mark.parametrize("case", ["jund_k2", "syn_k3_fdr", "syn_pval"])
 def test_fdr_statistics_bit_exact(bins, case, tmp_path):
     g = Golden(case)
