@@ -108,6 +108,8 @@ def test_per_iteration_parity_on_baseline_shapes(capi, oracle, shape):
     variants = [{}, {"BAMM_LIST_FRAC": "0.000001"}]
     if shape == "c3_40k":
         variants.append({"BAMM_CAND_FRAC": "0.000001"})
+    if shape == "k5_w20":
+        variants.append({"BAMM_M_NO_HI_GLOBAL": "1"})          # M-step with the high-word table in shared memory (3 column splits instead of 2)
     ems = []
     for env in variants:
         old = {k: os.environ.get(k) for k in env}
