@@ -465,7 +465,7 @@ extern "C" int bamm_em_create(bamm_seqset* s, const uint64_t* subset, uint64_t n
                 fail(BAMM_E_INVALID, "too many sequences for one device"); bamm_em_destroy(em); return BAMM_E_INVALID;
             }
             if (mstep_w_dispatch(em, nullptr, nullptr, 0)) { fail(BAMM_E_CUDA, "cannot opt in to shared memory for the packed M-step"); bamm_em_destroy(em); return BAMM_E_CUDA; }
-            if ((uint32_t)em->grid_pl > em->nparts) em->nparts = (uint32_t)em->grid_pl;
+            if (!em->m_tab.hi_global && (uint32_t)em->grid_pl > em->nparts) em->nparts = (uint32_t)em->grid_pl;   // hi_global: one table for all CTAs
         }
         tr.mark("M-step geometry + opt-in");
         // active list: one region per E-step warp, sized as a fraction of the warp's windows (BAMM_LIST_FRAC, 0 = off)

@@ -32,10 +32,11 @@ __device__ __forceinline__ uint32_t atoms_add_ret(uint32_t addr, uint32_t x) {
 __device__ __forceinline__ void reds_add(uint32_t addr, uint32_t h) {
     asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(h) : "memory");
 }
-// Where the high parts go: the CTA's second shared-memory table (ghi == nullptr), or — when that table is given up so that twice
-// the columns fit one CTA (orders >= 5: fewer passes over the list) — the CTA's 64-bit partial table in global memory, whose
-// bins [j0 Yn, ...) mirror the shared low-word table (one copy: nrep = 1 there). Rare either way: posteriors >= 2^-8 and the
-// wrap-arounds of a low word.
+// Where the high parts go: the CTA's second shared-memory table, or — when that table is given up so that twice the columns
+// fit one CTA (orders >= 5: fewer passes over the list) — a 64-bit count table in global memory whose bins [j0 Yn, ...) mirror
+// the shared low-word table (one copy: nrep = 1 there). Rare either way: posteriors >= 2^-8 and the wrap-arounds of a low
+// word. In that mode all CTAs share ONE global table (the flush adds the low words with atomics as well): at 4^6 and more
+// rows per column a partial table per CTA would cost more to clear and to sum than the M-step itself.
 // HG is a template parameter of the kernels: the variant with the shared-memory table carries no pointer (it runs at the
 // register limit of 1024 threads per CTA).
 template <bool HG> struct HiDst;
@@ -136,7 +137,7 @@ __device__ __forceinline__ void flush_cols(const uint32_t* lo_sh, MTables mt, ui
 // M-step from the E-step's active list: every lane scatters one listed window.
 template <int NC, bool HG>
 __global__ void __launch_bounds__(1024, 1)
-k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsplit, MTables mt, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsplit, MTables mt, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn]; HG: one [W*Yn] table */) {
     extern __shared__ uint32_t smem_u32[];
     if (*al.overflow != 0u) return;                                        // k_mstep_scan_w scans r instead
     const uint32_t nb = (uint32_t)NC * pl.Yn;
@@ -152,7 +153,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
     const int ralign = 62 - 2 * (K + NC - 1);                              // word = bases p+j0-K ..: column j0+NC-1's last base lowest
     const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh) + ((uint32_t)lane & (mt.nrep - 1u)) * mt.rstride * 4u;   // this lane's copy
     const uint32_t hi_off = mt.nrep * mt.rstride * 4u, yn4 = pl.Yn * 4u;
-    HiDst<HG> hd; hd.set(part + (uint64_t)blockIdx.x * ((uint64_t)pl.W * pl.Yn) + (uint64_t)j0 * pl.Yn, lo_s);
+    HiDst<HG> hd; hd.set(part + (uint64_t)j0 * pl.Yn, lo_s);            // HG: one global table for all CTAs (atomics only)
     const int nc_valid = min(NC, W - j0);
     const bool split_full = nc_valid == NC;                                // CTA-uniform
     const uint4 none = make_uint4(0u, 0u, 0u, 0u);
@@ -208,7 +209,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
         }
     }
     __syncthreads();
-    flush_cols<HG>(lo_sh, mt, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
+    flush_cols<HG>(lo_sh, mt, nb, pl.Yn, j0, W, HG ? part : part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
 }
 
 // M-step from r itself: one warp per sequence, lanes = 32 consecutive window starts, the packed stream is followed with the
@@ -218,7 +219,7 @@ k_mstep_list_w(PackedView pv, Plan pl, ActiveList al, uint32_t nregions, int nsp
 template <int NC, bool HG>
 __global__ void __launch_bounds__(1024, 1)
 k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float* __restrict__ scale, const uint32_t* __restrict__ only_if,
-               int nsplit, MTables mt, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn] */) {
+               int nsplit, MTables mt, unsigned long long* __restrict__ part /* [gridDim.x][W*Yn]; HG: one [W*Yn] table */) {
     extern __shared__ uint32_t smem_u32[];
     if (only_if != nullptr && *only_if == 0u) return;                      // k_mstep_list_w did the work
     const uint32_t nb = (uint32_t)NC * pl.Yn;
@@ -234,7 +235,7 @@ k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float*
     const int ralign = 62 - 2 * (K + NC - 1);
     const uint32_t lo_s = (uint32_t)__cvta_generic_to_shared(lo_sh) + ((uint32_t)lane & (mt.nrep - 1u)) * mt.rstride * 4u;   // this lane's copy
     const uint32_t hi_off = mt.nrep * mt.rstride * 4u, yn4 = pl.Yn * 4u;
-    HiDst<HG> hd; hd.set(part + (uint64_t)blockIdx.x * ((uint64_t)pl.W * pl.Yn) + (uint64_t)j0 * pl.Yn, lo_s);
+    HiDst<HG> hd; hd.set(part + (uint64_t)j0 * pl.Yn, lo_s);            // HG: one global table for all CTAs (atomics only)
     const int nc_valid = min(NC, W - j0);
     const bool split_full = nc_valid == NC;                                // CTA-uniform
     const int lane_word = (lane + j0 - K) >> 4;                            // this lane's words start at bases lane+j0-K + 32*chunk
@@ -277,7 +278,7 @@ k_mstep_scan_w(PackedView pv, Plan pl, const float* __restrict__ r, const float*
         }
     }
     __syncthreads();
-    flush_cols<HG>(lo_sh, mt, nb, pl.Yn, j0, W, part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
+    flush_cols<HG>(lo_sh, mt, nb, pl.Yn, j0, W, HG ? part : part + (uint64_t)blockIdx.x * ((uint64_t)W * pl.Yn));
 }
 
 }  // namespace bamm
